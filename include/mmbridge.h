@@ -1,0 +1,238 @@
+/*
+ * mmbridge.h — C ABI of libmmbridge.so: the B200 (sm_100a) generation hot path of
+ * Multimodal-Bridges (cesarali/multimodal_particles).
+ *
+ * The reference has no FFI: its hot path is a Python object API.  Each entry
+ * point below names the reference Python interface it stands behind (file:line under
+ * /root/reference/multimodal_particles/, abbreviated mp/).  The binding a reference maintainer
+ * would add is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer except `packed` in mmb_epic_create and the
+ *     MmbStepTable arrays is a DEVICE pointer owned by the caller;
+ *   - return 0 on success, a negative MMB_E* code otherwise; mmb_last_error() gives the text
+ *     (thread-local); nothing throws across the ABI;
+ *   - all compute calls are asynchronous on `stream` (a cudaStream_t passed as void*), make no
+ *     hidden synchronisation and allocate nothing (workspace is sized by mmb_*_workspace_bytes
+ *     and supplied by the caller);
+ *   - tokens and masks are uint8 on the device ([B,N], values 0..S-1 and 0/1); the int64
+ *     [B,N,1] layout of the reference (mp/models/generative/multimodal_bridge_matching.py:13-20)
+ *     is narrowed/widened once per generation by the host shim.
+ */
+#ifndef MMBRIDGE_H
+#define MMBRIDGE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMB_ABI_VERSION 1
+
+enum {
+    MMB_OK = 0,
+    MMB_EINVAL = -1,       /* bad argument / unsupported shape */
+    MMB_ECUDA = -2,        /* CUDA runtime error (text in mmb_last_error) */
+    MMB_ENOMEM = -3,       /* workspace too small / shared memory limit */
+    MMB_EUNSUPPORTED = -4  /* precision or config not built for this path */
+};
+
+/* flags for mmb_bridge_update / mmb_generate */
+enum {
+    MMB_FLAG_MULTIMODAL = 0, /* Euler + jump with the given mask      (mp/.../bridges.py:38-45,179-201) */
+    MMB_FLAG_ABSORBING = 1,  /* birth step first: mask' = mask | born (mp/.../bridges.py:260-286), then used */
+    MMB_FLAG_NO_EULER = 2,   /* leave x untouched  (a lone TelegraphBridge / AbsorbingBridge.solver_step) */
+    MMB_FLAG_NO_JUMP = 4     /* leave k untouched  (a lone LinearUniformBridge / AbsorbingBridge.solver_step) */
+};
+
+/* arithmetic of the EPiC trunk */
+enum {
+    MMB_PREC_FP32 = 0, /* CUDA-core fp32, bit-identical to oracle/mmb_oracle.c */
+    MMB_PREC_BF16 = 1  /* tcgen05 bf16 operands, fp32 accumulate in TMEM */
+};
+
+/*
+ * Shape of the EPiC encoder.  Mirrors the fields of EncoderConfig / JetsDataConfig that the
+ * reference constructors read (mp/models/architectures/epic.py:20-58,
+ * mp/config_classes/multimodal_bridge_matching_config.py:23-91).
+ * Supported: SinusoidalPositionalEncoding time embedding, Linear continuous embedding,
+ * Embedding discrete embedding, no context features (every shipped config).
+ */
+typedef struct MmbEpicDims {
+    int32_t dim_continuous;    /* Dc  data.dim_features_continuous */
+    int32_t vocab_size;        /* S   data.vocab_size_features     */
+    int32_t dim_time_emb;      /* T   encoder.dim_emb_time (= context width) */
+    int32_t dim_cont_emb;      /* C   encoder.dim_emb_features_continuous */
+    int32_t dim_disc_emb;      /* D   encoder.dim_emb_features_discrete   */
+    int32_t dim_hidden_local;  /* H   encoder.dim_hidden_local */
+    int32_t dim_hidden_glob;   /* G   encoder.dim_hidden_glob  */
+    int32_t num_blocks;        /* L   encoder.num_blocks */
+    int32_t skip_connection;   /* encoder.skip_connection */
+    int32_t disc_head_hidden;  /* Sh: 0 = no discrete head; S for MultiModalEPiC.fc_layer
+                                  (mp/.../multimodal_bridge_matching.py:90-100); 56 for
+                                  AbsorbingGenerator.discrete_head_mlp (absorbing_flows.py:41-54) */
+} MmbEpicDims;
+
+/*
+ * Packed weight blob: fp32, weight-norm already folded (W = g * v / ||v||_row,
+ * mp/models/architectures/epic.py:134,171-176,208-215), every matrix row-major [out][in],
+ * each matrix followed by its bias, in this order (in-widths in brackets):
+ *   emb_cont  [C][Dc] + [C]
+ *   emb_disc  [S][D]                      (embedding table, no bias)
+ *   proj.local_0  [H][T+C+D] + [H]
+ *   proj.global_0 [H][2H+T]  + [H]
+ *   proj.global_1 [H][H]     + [H]
+ *   proj.global_2 [G][H]     + [G]
+ *   L x { fc_global1 [H][2H+G+T] + [H]; fc_global2 [G][H] + [G];
+ *         fc_local1  [H][H+G+T]  + [H]; fc_local2  [H][H] + [H] }
+ *   output_layer [Dc+S][H] + [Dc+S]
+ *   if Sh: head0 [Sh][S] + [Sh]; head2 [S][Sh] + [S]
+ */
+typedef struct MmbEpicLayout {
+    size_t emb_cont_w, emb_cont_b, emb_disc;
+    size_t local0_w, local0_b, global0_w, global0_b, global1_w, global1_b, global2_w, global2_b;
+    size_t layer0;       /* offset of the first EPiC layer */
+    size_t layer_stride; /* floats per EPiC layer */
+    size_t l_g1_w, l_g1_b, l_g2_w, l_g2_b, l_l1_w, l_l1_b, l_l2_w, l_l2_b; /* within a layer */
+    size_t out_w, out_b, head0_w, head0_b, head2_w, head2_b;
+    size_t total;
+} MmbEpicLayout;
+
+static inline MmbEpicLayout mmb_epic_layout(const MmbEpicDims* d) {
+    MmbEpicLayout L;
+    size_t o = 0;
+    const size_t Dc = (size_t)d->dim_continuous, S = (size_t)d->vocab_size, T = (size_t)d->dim_time_emb,
+                 C = (size_t)d->dim_cont_emb, D = (size_t)d->dim_disc_emb, H = (size_t)d->dim_hidden_local,
+                 G = (size_t)d->dim_hidden_glob, Sh = (size_t)d->disc_head_hidden;
+    L.emb_cont_w = o; o += C * Dc;
+    L.emb_cont_b = o; o += C;
+    L.emb_disc = o;   o += S * D;
+    L.local0_w = o;   o += H * (T + C + D);
+    L.local0_b = o;   o += H;
+    L.global0_w = o;  o += H * (2 * H + T);
+    L.global0_b = o;  o += H;
+    L.global1_w = o;  o += H * H;
+    L.global1_b = o;  o += H;
+    L.global2_w = o;  o += G * H;
+    L.global2_b = o;  o += G;
+    L.layer0 = o;
+    {
+        size_t p = 0;
+        L.l_g1_w = p; p += H * (2 * H + G + T);
+        L.l_g1_b = p; p += H;
+        L.l_g2_w = p; p += G * H;
+        L.l_g2_b = p; p += G;
+        L.l_l1_w = p; p += H * (H + G + T);
+        L.l_l1_b = p; p += H;
+        L.l_l2_w = p; p += H * H;
+        L.l_l2_b = p; p += H;
+        L.layer_stride = p;
+    }
+    o += L.layer_stride * (size_t)d->num_blocks;
+    L.out_w = o; o += (Dc + S) * H;
+    L.out_b = o; o += (Dc + S);
+    L.head0_w = L.head0_b = L.head2_w = L.head2_b = 0;
+    if (Sh) {
+        L.head0_w = o; o += Sh * S;
+        L.head0_b = o; o += Sh;
+        L.head2_w = o; o += S * Sh;
+        L.head2_b = o; o += S;
+    }
+    L.total = o;
+    return L;
+}
+
+/*
+ * Per-solver-step scalars, computed ON THE HOST with the reference's own fp32 op order so that no
+ * libm-vs-libdevice difference enters:
+ *   t      network time of the step            (mp/.../multimodal_bridge_matching.py:203-211)
+ *   temb   [T] sinusoidal embedding of t        (mp/models/architectures/utils.py:183-198)
+ *   bc,cc  telegraph coefficients B=(w S)/(1-w), C=w, w=exp(-S gamma (1-t))  (bridges.py:125-130)
+ *   sp     absorbing survival probability SP(t) (bridges.py:218-231); unused for MULTIMODAL
+ * Arrays are HOST pointers of length n_steps (temb: n_steps*T); mmb_generate copies nothing — it
+ * reads them when launching each step.
+ */
+typedef struct MmbStepTable {
+    int32_t n_steps;
+    float dt;          /* (1-eps)/(T-1) as fp32 (mbm.py:209) */
+    const float* t;
+    const float* temb;
+    const float* bc;
+    const float* cc;
+    const float* sp;   /* nullable */
+} MmbStepTable;
+
+typedef struct MmbEpicModel MmbEpicModel; /* opaque: device-resident weights in every layout the kernels use */
+
+int mmb_abi_version(void);
+const char* mmb_last_error(void);
+
+/* number of floats mmb_epic_create expects for `dims` (== mmb_epic_layout(dims).total) */
+size_t mmb_epic_packed_floats(const MmbEpicDims* dims);
+
+/*
+ * Build the device-side model from a HOST blob.  Stands behind the reference constructors
+ * EPiCWrapper(config) + MultiModalEPiC.fc_layer (epic.py:20-58, mbm.py:80-100) and
+ * load_state_dict of the keys listed in SURVEY.md §A.6.  Synchronous (one-time).
+ */
+int mmb_epic_create(const MmbEpicDims* dims, const float* packed, size_t n_floats, int device, MmbEpicModel** out);
+void mmb_epic_destroy(MmbEpicModel* m);
+
+/*
+ * One network evaluation.  Stands behind MultiModalEPiC.forward (mbm.py:102-113) ==
+ * EPiCWrapper.forward (epic.py:62-91) + the discrete head; with hidden_out != NULL it is
+ * EPiCWrapper.forward(..., output_hidden_local=True) as AbsorbingGenerator.forward calls it
+ * (absorbing_flows.py:153).
+ *   x [B,N,Dc] f32, k [B,N] u8, mask [B,N] u8,
+ *   temb [B,T] (temb_stride = T) or one row shared by all jets (temb_stride = 0),
+ *   v_out [B,N,Dc], logits_out [B,N,S]; hidden_out [B,N,H] nullable.
+ * An empty jet (mask all zero) produces NaN exactly as epic.py:141 does.
+ */
+int mmb_epic_forward(const MmbEpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
+                     const float* temb, int temb_stride, int B, int N,
+                     float* v_out, float* logits_out, float* hidden_out,
+                     int precision, void* stream);
+
+/*
+ * The fused hybrid update, in place.  Stands behind, in this order,
+ *   AbsorbingBridge.solver_step      (bridges.py:260-286)   [ABSORBING only]
+ *   LinearUniformBridge.solver_step  (bridges.py:38-45)
+ *   TelegraphBridge.solver_step      (bridges.py:179-201) incl. .rate (bridges.py:106-132)
+ * with the Poisson tau-leap replaced by its exactly equivalent one-uniform categorical
+ * (SURVEY.md §A.4 Form B, self slot retained):
+ *   x [B,N,Dc] f32 in/out, k [B,N] u8 in/out, mask [B,N] u8 (in; in/out for ABSORBING),
+ *   v [B,N,Dc], logits [B,N,S], absorb_logit [B,N] (ABSORBING), u_jump [B,N], u_absorb [B,N].
+ * Sub-steps are switched off with MMB_FLAG_NO_EULER / MMB_FLAG_NO_JUMP (their inputs may then be
+ * NULL), which is how the host shim serves a lone bridge.solver_step call.
+ * Returns MMB_EINVAL for S > 32 or Dc > 8.  Tokens outside [0,S) are undefined behaviour on the
+ * device; the host shim keeps the reference's assertion (bridges.py:111-115).
+ */
+int mmb_bridge_update(float* x, uint8_t* k, uint8_t* mask,
+                      const float* v, const float* logits, const float* absorb_logit,
+                      const float* u_jump, const float* u_absorb,
+                      float dt, float bc, float cc, float sp,
+                      int B, int N, int Dc, int S, int flags, void* stream);
+
+/*
+ * Whole generation loop for the multimodal bridge: n_steps x (network, update) with the state
+ * resident on the device.  Stands behind MultiModalBridgeMatching.simulate_dynamics
+ * (mbm.py:199-216) minus the final .cpu().
+ *   u_jump: [n_steps,B,N] pre-drawn uniforms, or NULL to draw in-kernel with Philox4x32-10 keyed by
+ *   (seed, jet_offset + jet, step, particle) — results are then invariant to how jets are sharded.
+ *   workspace: mmb_generate_workspace_bytes(m, B, N, precision) bytes of device memory.
+ */
+size_t mmb_generate_workspace_bytes(const MmbEpicModel* m, int B, int N, int precision);
+int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mask,
+                 const MmbStepTable* steps, const float* u_jump,
+                 uint64_t seed, uint64_t jet_offset, int B, int N,
+                 void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/* uniforms exactly as the in-kernel generator draws them, written to u [n_steps,B,N] (for tests) */
+int mmb_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMBRIDGE_H */

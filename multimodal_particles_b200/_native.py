@@ -1,0 +1,155 @@
+"""ctypes binding of libmmbridge.so (include/mmbridge.h).
+
+There is no CPU fallback: if the library is missing or a call fails, this raises.  PyTorch is used
+only for device memory and streams; every pointer handed over is a ``data_ptr()`` of a contiguous
+CUDA tensor and every launch goes to ``torch.cuda.current_stream()``.
+"""
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from .steptable import CStepTable
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmmbridge.so")
+
+FLAG_MULTIMODAL = 0
+FLAG_ABSORBING = 1
+PREC_FP32 = 0
+PREC_BF16 = 1
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+
+class MmbError(RuntimeError):
+    pass
+
+
+class EpicDims(ctypes.Structure):
+    """ctypes image of ``MmbEpicDims``."""
+
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "dim_continuous", "vocab_size", "dim_time_emb", "dim_cont_emb", "dim_disc_emb",
+        "dim_hidden_local", "dim_hidden_glob", "num_blocks", "skip_connection", "disc_head_hidden")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+# name -> (restype, argtypes); lists every symbol include/mmbridge.h declares
+_vp, _i, _f, _sz, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_uint64
+SIGNATURES = {
+    "mmb_abi_version": (_i, []),
+    "mmb_last_error": (ctypes.c_char_p, []),
+    "mmb_epic_packed_floats": (_sz, [ctypes.POINTER(EpicDims)]),
+    "mmb_epic_create": (_i, [ctypes.POINTER(EpicDims), _vp, _sz, _i, ctypes.POINTER(_vp)]),
+    "mmb_epic_destroy": (None, [_vp]),
+    "mmb_epic_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "mmb_bridge_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _i, _i, _vp]),
+    "mmb_generate_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "mmb_generate": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
+    "mmb_philox_uniforms": (_i, [_vp, _u64, _u64, _i, _i, _i, _vp]),
+}
+
+
+def load():
+    """Load the library once; raise loudly when it has not been built
+    (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MmbError(f"{LIB_PATH} not built: the generation path has no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise MmbError(f"libmmbridge error {rc}: {load().mmb_last_error().decode()}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
+            raise MmbError("libmmbridge takes contiguous CUDA tensors; there is no CPU path")
+
+
+class EpicModel:
+    """Owner of one ``MmbEpicModel*`` (device-resident weights)."""
+
+    def __init__(self, dims: EpicDims, packed: torch.Tensor, device: torch.device):
+        lib = load()
+        packed = packed.detach().to("cpu", torch.float32).contiguous()
+        expect = lib.mmb_epic_packed_floats(ctypes.byref(dims))
+        if packed.numel() != expect:
+            raise MmbError(f"packed weight blob has {packed.numel()} floats, layout wants {expect}")
+        self.dims, self.device = dims, torch.device(device)
+        self._handle = ctypes.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(lib.mmb_epic_create(ctypes.byref(dims), _ptr(packed), packed.numel(), index, ctypes.byref(self._handle)))
+
+    def __del__(self):
+        if getattr(self, "_handle", None) and _lib is not None:
+            _lib.mmb_epic_destroy(self._handle)
+            self._handle = None
+
+    def forward(self, x, k_u8, mask_u8, temb, want_hidden=False, precision="fp32"):
+        """x [B,N,Dc] f32, k/mask [B,N] u8, temb [B,T] or [1,T] -> (v, logits[, hidden])."""
+        _require_cuda(x, k_u8, mask_u8, temb)
+        B, N, _ = x.shape
+        d = self.dims
+        v = torch.empty(B, N, d.dim_continuous, device=x.device, dtype=torch.float32)
+        logits = torch.empty(B, N, d.vocab_size, device=x.device, dtype=torch.float32)
+        hidden = torch.empty(B, N, d.dim_hidden_local, device=x.device, dtype=torch.float32) if want_hidden else None
+        stride = 0 if temb.shape[0] == 1 and B != 1 else d.dim_time_emb
+        with torch.cuda.device(x.device):
+            check(load().mmb_epic_forward(self._handle, _ptr(x), _ptr(k_u8), _ptr(mask_u8), _ptr(temb), stride, B, N,
+                                          _ptr(v), _ptr(logits), _ptr(hidden), PRECISIONS[precision], _stream()))
+        return (v, logits, hidden) if want_hidden else (v, logits)
+
+    def generate(self, x, k_u8, mask_u8, table, u_jump=None, seed=0, jet_offset=0, precision="bf16"):
+        """In-place generation of x/k over all steps of ``table`` (StepTable)."""
+        _require_cuda(x, k_u8, mask_u8, u_jump)
+        B, N, _ = x.shape
+        lib = load()
+        prec = PRECISIONS[precision]
+        need = lib.mmb_generate_workspace_bytes(self._handle, B, N, prec)
+        ws = torch.empty(max(need, 16), device=x.device, dtype=torch.uint8)
+        ctable = CStepTable.from_table(table)
+        with torch.cuda.device(x.device):
+            check(lib.mmb_generate(self._handle, _ptr(x), _ptr(k_u8), _ptr(mask_u8), ctypes.byref(ctable), _ptr(u_jump),
+                                   seed, jet_offset, B, N, _ptr(ws), ws.numel(), prec, _stream()))
+        return x, k_u8
+
+
+def bridge_update(x, k_u8, mask_u8, v, logits, u_jump, dt, bc, cc, absorb_logit=None, u_absorb=None, sp=0.0,
+                  flags=FLAG_MULTIMODAL):
+    """In-place fused Euler + telegraph jump (+ absorbing birth) on device tensors."""
+    _require_cuda(x, k_u8, mask_u8, v, logits, u_jump, absorb_logit, u_absorb)
+    B, N, Dc = x.shape
+    S = logits.shape[-1] if logits is not None else 1
+    with torch.cuda.device(x.device):
+        check(load().mmb_bridge_update(_ptr(x), _ptr(k_u8), _ptr(mask_u8), _ptr(v), _ptr(logits), _ptr(absorb_logit),
+                                       _ptr(u_jump), _ptr(u_absorb), dt, bc, cc, sp, B, N, Dc, S, flags, _stream()))
+
+
+def philox_uniforms(seed, jet_offset, n_steps, B, N, device):
+    u = torch.empty(n_steps, B, N, device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        check(load().mmb_philox_uniforms(_ptr(u), seed, jet_offset, n_steps, B, N, _stream()))
+    return u

@@ -1,0 +1,177 @@
+"""EPiC encoder: parameter containers with the reference's state-dict keys + the native forward.
+
+The reference builds the network from ``torch.nn`` layers and evaluates ~725 eager ops per step
+(mp/models/architectures/epic.py:10-241, utils.py:6-198).  Here the modules only *hold* the
+parameters (so checkpoints load unchanged: ``…weight_g [out,1]``, ``…weight_v [out,in]``, ``…bias``,
+SURVEY.md §A.6); evaluation folds the weight norm once, packs everything into the blob described in
+include/mmbridge.h and calls the sm_100a kernels.  No autograd: this is the generation path.
+"""
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _native
+from .steptable import sinusoidal_time_embedding
+
+
+class WeightNormLinear(nn.Module):
+    """Parameters of ``weight_norm(nn.Linear(i, o))`` (old-style hook, dim=0): ``bias``,
+    ``weight_g`` [o,1], ``weight_v`` [o,i].  Initialised through ``nn.Linear`` so that the RNG
+    stream (and hence random-init weights under a fixed seed) equals the reference's."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        seed_layer = nn.Linear(in_features, out_features)
+        self.bias = nn.Parameter(seed_layer.bias.detach().clone())
+        v = seed_layer.weight.detach().clone()
+        self.weight_g = nn.Parameter(torch.norm_except_dim(v, 2, 0))
+        self.weight_v = nn.Parameter(v)
+
+    def folded(self) -> torch.Tensor:
+        # same ATen function the reference's forward pre-hook runs every step (epic.py:134)
+        return torch._weight_norm(self.weight_v.detach(), self.weight_g.detach(), 0)
+
+
+class SinusoidalPositionalEncoding(nn.Module):
+    """Parameter-free; kept so the module tree matches (utils.py:175-198)."""
+
+    def __init__(self, dim, max_period=10000):
+        super().__init__()
+        self.dim, self.max_period = dim, max_period
+
+    def forward(self, timesteps):
+        return sinusoidal_time_embedding(timesteps.reshape(-1), self.dim, self.max_period)
+
+
+class InputEmbeddings(nn.Module):
+    """utils.py:6-110.  Supported embedding kinds are the ones every shipped config uses."""
+
+    def __init__(self, config):
+        super().__init__()
+        d, e = config.data, config.encoder
+        if e.embedding_time != "SinusoidalPositionalEncoding":
+            raise NotImplementedError("native path supports embedding_time=SinusoidalPositionalEncoding only")
+        if e.embedding_features_continuous != "Linear" or e.embedding_features_discrete != "Embedding":
+            raise NotImplementedError("native path supports Linear continuous / Embedding discrete feature embeddings")
+        if d.dim_context_continuous or d.dim_context_discrete:
+            raise NotImplementedError("context features are not supported by the native path (all shipped configs use 0)")
+        if d.dim_features_discrete != 1:
+            raise NotImplementedError("one discrete token per particle (dim_features_discrete=1)")
+        self.embedding_time = SinusoidalPositionalEncoding(e.dim_emb_time, max_period=10000)
+        dim_cont_emb = e.dim_emb_features_continuous or d.dim_features_continuous
+        self.embedding_continuous = nn.Linear(d.dim_features_continuous, dim_cont_emb)
+        self.embedding_discrete = nn.Embedding(d.vocab_size_features, e.dim_emb_features_discrete)
+
+
+class EPiC_Projection(nn.Module):
+    def __init__(self, dim_local, dim_global, dim_hidden_local, dim_hidden_global):
+        super().__init__()
+        self.local_0 = WeightNormLinear(dim_local, dim_hidden_local)
+        self.global_0 = WeightNormLinear(2 * dim_hidden_local + dim_global, dim_hidden_local)
+        self.global_1 = WeightNormLinear(dim_hidden_local, dim_hidden_local)
+        self.global_2 = WeightNormLinear(dim_hidden_local, dim_hidden_global)
+
+
+class EPiC_layer(nn.Module):
+    def __init__(self, dim_local, dim_global, dim_hidden, dim_context):
+        super().__init__()
+        self.fc_global1 = WeightNormLinear(2 * dim_local + dim_global + dim_context, dim_hidden)
+        self.fc_global2 = WeightNormLinear(dim_hidden, dim_global)
+        self.fc_local1 = WeightNormLinear(dim_local + dim_global + dim_context, dim_hidden)
+        self.fc_local2 = WeightNormLinear(dim_hidden, dim_local)
+
+
+class EPiCNetwork(nn.Module):
+    def __init__(self, dim_input, dim_output, dim_context, num_blocks, dim_hidden_local, dim_hidden_global,
+                 use_skip_connection):
+        super().__init__()
+        self.num_blocks, self.use_skip_connection = num_blocks, use_skip_connection
+        self.epic_proj = EPiC_Projection(dim_input, dim_context, dim_hidden_local, dim_hidden_global)
+        self.epic_layers = nn.ModuleList(
+            [EPiC_layer(dim_hidden_local, dim_hidden_global, dim_hidden_local, dim_context) for _ in range(num_blocks)])
+        self.output_layer = WeightNormLinear(dim_hidden_local, dim_output)
+
+
+def as_u8(t: torch.Tensor) -> torch.Tensor:
+    """[B,N,1] int64 tokens / masks of the reference -> contiguous [B,N] uint8 for the kernels."""
+    return t.reshape(t.shape[0], t.shape[1]).to(torch.uint8).contiguous()
+
+
+class EPiCWrapper(nn.Module):
+    """epic.py:10-91: ``forward(t, x, k, mask, context_continuous, context_discrete,
+    output_hidden_local)`` -> ``h [B,N,Dc+S]`` (masked), optionally also the last local hidden."""
+
+    def __init__(self, config):
+        super().__init__()
+        d, e = config.data, config.encoder
+        self.dim_features_continuous = d.dim_features_continuous
+        self.dim_features_discrete = d.dim_features_discrete
+        self.vocab_size = d.vocab_size_features
+        self.embedding = InputEmbeddings(config)
+        dim_cont_emb = e.dim_emb_features_continuous or d.dim_features_continuous
+        self.epic = EPiCNetwork(
+            dim_input=e.dim_emb_time + dim_cont_emb + e.dim_emb_features_discrete,
+            dim_output=d.dim_features_continuous + d.dim_features_discrete * d.vocab_size_features,
+            dim_context=e.dim_emb_time,
+            num_blocks=e.num_blocks,
+            dim_hidden_local=e.dim_hidden_local,
+            dim_hidden_global=e.dim_hidden_glob,
+            use_skip_connection=e.skip_connection,
+        )
+        self.precision = "fp32"
+        self._dims = dict(dim_continuous=d.dim_features_continuous, vocab_size=d.vocab_size_features,
+                          dim_time_emb=e.dim_emb_time, dim_cont_emb=dim_cont_emb,
+                          dim_disc_emb=e.dim_emb_features_discrete, dim_hidden_local=e.dim_hidden_local,
+                          dim_hidden_glob=e.dim_hidden_glob, num_blocks=e.num_blocks,
+                          skip_connection=int(bool(e.skip_connection)))
+        self._cache = {}
+
+    # ---- packing -----------------------------------------------------------------------------
+    def epic_dims(self, disc_head_hidden: int = 0) -> _native.EpicDims:
+        return _native.EpicDims(**self._dims, disc_head_hidden=disc_head_hidden)
+
+    def pack_weights(self, head: Optional[nn.Sequential] = None) -> torch.Tensor:
+        """Flat fp32 blob in the order of ``mmb_epic_layout`` (include/mmbridge.h)."""
+        emb, net = self.embedding, self.epic
+        parts = [emb.embedding_continuous.weight, emb.embedding_continuous.bias, emb.embedding_discrete.weight]
+
+        def wn(layer: WeightNormLinear):
+            parts.extend([layer.folded(), layer.bias])
+
+        proj = net.epic_proj
+        for layer in (proj.local_0, proj.global_0, proj.global_1, proj.global_2):
+            wn(layer)
+        for block in net.epic_layers:
+            for layer in (block.fc_global1, block.fc_global2, block.fc_local1, block.fc_local2):
+                wn(layer)
+        wn(net.output_layer)
+        if head is not None:
+            parts.extend([head[0].weight, head[0].bias, head[2].weight, head[2].bias])
+        return torch.cat([p.detach().to("cpu", torch.float32).reshape(-1) for p in parts])
+
+    def native_model(self, device, head: Optional[nn.Sequential] = None) -> _native.EpicModel:
+        """Device-resident packed model; rebuilt when any parameter changed (optimizer step,
+        ``load_state_dict``) or the device differs."""
+        params = list(self.parameters()) + (list(head.parameters()) if head is not None else [])
+        stamp = (str(device), head is not None, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        key = "head" if head is not None else "trunk"
+        hit = self._cache.get(key)
+        if hit is None or hit[0] != stamp:
+            hidden = head[0].out_features if head is not None else 0
+            model = _native.EpicModel(self.epic_dims(hidden), self.pack_weights(head), device)
+            self._cache[key] = (stamp, model)
+        return self._cache[key][1]
+
+    # ---- evaluation --------------------------------------------------------------------------
+    def time_embedding(self, t: torch.Tensor) -> torch.Tensor:
+        """t [B,1] (generation) or [B,1,1] (training) -> [B,T]"""
+        return self.embedding.embedding_time(t.reshape(t.shape[0]).float()).contiguous()
+
+    def forward(self, t, x, k=None, mask=None, context_continuous=None, context_discrete=None,
+                output_hidden_local=False):
+        model = self.native_model(x.device)
+        v, z, hidden = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask), self.time_embedding(t),
+                                     want_hidden=True, precision=self.precision)
+        h = torch.cat([v, z], dim=-1)
+        return (h, hidden) if output_hidden_local else h

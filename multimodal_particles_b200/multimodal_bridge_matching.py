@@ -1,0 +1,159 @@
+"""MultiModalBridgeMatching — drop-in for the generation side of
+mp/models/generative/multimodal_bridge_matching.py (:77-146, 199-216, 252-257).
+
+Same constructor argument (``MultimodalBridgeMatchingConfig``), same ``forward(state, batch)``,
+``simulate_dynamics(state, batch)`` and ``predict_step(batch, batch_idx)`` signatures, same output
+containers and tensor layouts, same state-dict keys.  The compute is libmmbridge.so: the loop in
+``simulate_dynamics`` is ONE call of ``mmb_generate`` with the state resident on the GPU, instead
+of ~725 eager ops and 4 host syncs per step.  Training methods
+(``sample_bridges``, losses, ``training_step``) are outside this path and raise.
+"""
+import torch
+from torch import nn
+
+from . import _native
+from .bridges import LinearUniformBridge, TelegraphBridge
+from .epic import EPiCWrapper, as_u8
+from .states import HybridState, MultiHeadOutput
+from .steptable import build_step_table
+
+try:  # Lightning is optional: with it the class plugs into Trainer.predict as the reference does
+    import lightning as L
+    _ModuleBase = L.LightningModule
+except Exception:  # pragma: no cover - lightning is not in this image
+    class _ModuleBase(nn.Module):
+        def save_hyperparameters(self, *args, **kwargs):
+            pass
+
+        def log(self, *args, **kwargs):
+            pass
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+
+class MultiHeadLoss(nn.Module):
+    """Holds ``loss_multihead.weights`` so reference checkpoints load (mp/utils/losses.py:9-20)."""
+
+    def __init__(self, number_of_losses=2):
+        super().__init__()
+        self.weights = nn.Parameter(torch.zeros(number_of_losses))
+
+
+class MultiModalEPiC(nn.Module):
+    """EPiC trunk + discrete head ``Linear -> SELU -> Linear`` on the logit slice (mbm.py:77-113)."""
+
+    def __init__(self, config):
+        super().__init__()
+        d = config.data
+        self.dim_features_continuous = d.dim_features_continuous
+        self.dim_features_discrete = d.dim_features_discrete
+        self.vocab_size = d.vocab_size_features
+        self.output_dim = d.dim_features_continuous + d.dim_features_discrete * d.vocab_size_features
+        self.epic = EPiCWrapper(config)
+        self.add_discrete_head = config.encoder.add_discrete_head
+        if self.add_discrete_head:
+            width = d.dim_features_discrete * d.vocab_size_features
+            self.fc_layer = nn.Sequential(nn.Linear(width, width), nn.SELU(), nn.Linear(width, width))
+        self.precision = "fp32"
+
+    def native_model(self, device) -> _native.EpicModel:
+        return self.epic.native_model(device, self.fc_layer if self.add_discrete_head else None)
+
+    def forward(self, t, x, k, mask=None, context_continuous=None, context_discrete=None):
+        model = self.native_model(x.device)
+        v, logits = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask), self.epic.time_embedding(t),
+                                  precision=self.precision)
+        return v, logits, mask
+
+
+class MultiModalBridgeMatching(_ModuleBase):
+    """Model for hybrid data with varying size (mbm.py:115-269), generation side.
+
+    ``precision``: "fp32" = CUDA-core trunk, bit-identical to the CPU oracle; "bf16" = tcgen05 trunk
+    (default for ``simulate_dynamics``).  ``forward`` always evaluates in fp32 unless asked.
+    """
+
+    def __init__(self, config, precision: str = "bf16"):
+        super().__init__()
+        self.config = config
+        self.vocab_size = config.data.vocab_size_features
+        self.encoder = MultiModalEPiC(config)
+        self.bridge_continuous = LinearUniformBridge(config)
+        self.bridge_discrete = TelegraphBridge(config)
+        self.bridge_absorbing = None
+        self.loss_multihead = MultiHeadLoss(number_of_losses=2)
+        self.precision = precision
+        self.seed = 0           # Philox key of simulate_dynamics when no uniforms are injected
+        self._jets_generated = 0
+        self.save_hyperparameters()
+
+    # ---- network ----------------------------------------------------------------------------
+    def forward(self, state: HybridState, batch=None) -> MultiHeadOutput:
+        continuous, discrete, absorbing = self.encoder(
+            t=state.time, x=state.continuous, k=state.discrete, mask=state.absorbing)
+        return MultiHeadOutput(continuous, discrete, absorbing)
+
+    # ---- generation -------------------------------------------------------------------------
+    def step_table(self):
+        b, e = self.config.bridge, self.config.encoder
+        return build_step_table(b.num_timesteps, b.time_eps, self.vocab_size, b.gamma, e.dim_emb_time)
+
+    @torch.no_grad()
+    def simulate_dynamics(self, state: HybridState, batch=None, uniforms=None, precision=None,
+                          jet_offset=None, return_device=False) -> HybridState:
+        """Generate target data from the source state; returns the final state on the CPU,
+        detached, like the reference (mbm.py:199-216).
+
+        ``uniforms`` [T-1,B,N]: injected jump draws (parity); default: in-kernel Philox keyed by
+        ``(self.seed, global jet index, step, particle)``.  The input state is consumed (the
+        reference mutates it too); ``return_device=True`` skips the final D2H copy.
+        """
+        device = self._compute_device(state)
+        table = self.step_table()
+        x = state.continuous.to(device, torch.float32, copy=True).contiguous()
+        k64 = state.discrete
+        assert bool((k64 >= 0).all()) and bool((k64 < self.vocab_size).all()), \
+            "Values in `k` outside of bound! k_min={}, k_max={}".format(k64.min(), k64.max())
+        k = as_u8(k64.to(device))
+        mask = as_u8(state.absorbing.to(device))
+        B, N, _ = x.shape
+        u = None if uniforms is None else uniforms.to(device, torch.float32).reshape(table.n_steps, B, N).contiguous()
+        if jet_offset is None:
+            jet_offset = self._jets_generated
+            self._jets_generated += B
+        model = self.encoder.native_model(device)
+        model.generate(x, k, mask, table, u_jump=u, seed=self.seed, jet_offset=jet_offset,
+                       precision=precision or self.precision)
+        out = HybridState(
+            time=torch.full((B, 1), float(table.t[-1]), device=device),
+            continuous=x,
+            discrete=k.to(k64.dtype).unsqueeze(-1),
+            absorbing=state.absorbing.to(device),
+        )
+        return out if return_device else out.detach().cpu()
+
+    def predict_step(self, batch, batch_idx) -> HybridState:
+        initial_state = HybridState(None, batch.source_continuous, batch.source_discrete, batch.source_mask)
+        return self.simulate_dynamics(initial_state, batch)
+
+    def _compute_device(self, state) -> torch.device:
+        dev = self.device
+        if dev.type != "cuda":
+            dev = state.continuous.device
+        if dev.type != "cuda":
+            if not torch.cuda.is_available():
+                raise _native.MmbError("generation needs a CUDA device: libmmbridge has no CPU path")
+            dev = torch.device("cuda", torch.cuda.current_device())
+        return dev
+
+    # ---- outside the generation path ----------------------------------------------------------
+    def _training_not_in_scope(self, *args, **kwargs):
+        raise NotImplementedError("training is outside the B200 generation hot path (SURVEY.md §8f N2)")
+
+    sample_bridges = loss_continuous = loss_discrete = training_step = validation_step = _training_not_in_scope
+    configure_optimizers = _training_not_in_scope

@@ -1,0 +1,409 @@
+/*
+ * mmb_oracle.c — CPU restatement of the Multimodal-Bridges generation hot path.
+ * TEST INFRASTRUCTURE ONLY (see mmb_oracle.h).  Parity: PINNED by tests/golden/*.npz.
+ *
+ * Build: oracle/Makefile (gcc -O2 -ffp-contract=off -mfma -fopenmp).  -ffp-contract=off matters:
+ * every fused multiply-add below is an explicit fmaf() and every other product/sum is a separately
+ * rounded IEEE fp32 operation, so the fp32 CUDA path (which spells the same sequence with
+ * __fmaf_rn/__fmul_rn/__fadd_rn/__fdiv_rn) is bit-identical to this file, not merely close.
+ *
+ * Reference lines followed (mp/ = /root/reference/multimodal_particles/):
+ *   time grid / loop        mp/models/generative/multimodal_bridge_matching.py:199-216
+ *   sinusoidal embedding    mp/models/architectures/utils.py:183-198
+ *   input embeddings        mp/models/architectures/utils.py:112-172
+ *   EPiC trunk              mp/models/architectures/epic.py:136-241
+ *   discrete head           mp/models/generative/multimodal_bridge_matching.py:90-113
+ *   Euler step              mp/models/generative/bridges.py:38-45
+ *   telegraph rate + jump   mp/models/generative/bridges.py:106-132,179-201
+ *   absorbing step          mp/models/generative/bridges.py:218-231,251-286
+ *
+ * Order-of-operations choices (free within fp32 rounding of the reference; fixed here and in the
+ * kernels): dot products start from the bias and accumulate with fmaf in ascending input index,
+ * except that the per-jet part of a per-particle layer's input (time embedding, global vector) is
+ * accumulated first; masked sums use the 128-lane tree of tree_sum().
+ */
+#include "mmb_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* exp in IEEE fp32 operations only (Cody-Waite reduction + degree-5 polynomial on r^2 term), so
+ * CPU and GPU agree bit-for-bit; |rel err| < 2 ulp on [-87, 88]. */
+static inline float bits_to_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+float mmbo_expf(float x) {
+    if (x != x) return x;
+    if (x < -87.0f) return 0.0f;
+    if (x > 88.0f) return INFINITY;
+    float n = rintf(x * 1.44269504f);
+    float r = fmaf(n, -0.693359375f, x);
+    r = fmaf(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    float r2 = r * r;
+    float y = fmaf(p, r2, r) + 1.0f;
+    int e = (int)n;
+    return y * bits_to_float((uint32_t)(e + 127) << 23);
+}
+
+static inline float lrelu(float a) { return a > 0.0f ? a : a * 0.01f; }           /* F.leaky_relu */
+static inline float selu(float a) {                                               /* nn.SELU */
+    const float scale = 1.0507009873554804934193349852946f;
+    const float alpha_scale = 1.0507009873554804934193349852946f * 1.6732632423543772848170429916717f;
+    return a > 0.0f ? scale * a : alpha_scale * (mmbo_expf(a) - 1.0f);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al. 2011).  counter = (n>>2, step, jet_lo, jet_hi*4+stream), key = seed */
+static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+static inline float philox_uniform(uint64_t seed, uint64_t jet, int stream_id, int step, int n) {
+    uint32_t c[4] = {(uint32_t)(n >> 2), (uint32_t)step, (uint32_t)jet,
+                     (uint32_t)(jet >> 32) * 4u + (uint32_t)stream_id};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return (float)(c[n & 3] >> 8) * (1.0f / 16777216.0f);
+}
+
+void mmbo_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int stream_id,
+                          int n_steps, int B, int N) {
+    for (int s = 0; s < n_steps; ++s)
+        for (int b = 0; b < B; ++b)
+            for (int n = 0; n < N; ++n)
+                u[((size_t)s * B + b) * N + n] = philox_uniform(seed, jet_offset + (uint64_t)b, stream_id, s, n);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+void mmbo_step_table(int num_timesteps, float time_eps, int S, float gamma, float gamma_absorb, int T,
+                     float* t, float* temb, float* bc, float* cc, float* sp, float* dt) {
+    /* torch.linspace(0, 1-eps, n) fp32: start + i*step for the first half, end - (n-1-i)*step after */
+    const int n = num_timesteps;
+    const float end = (float)(1.0 - (double)time_eps);
+    const float step = (end - 0.0f) / (float)(n - 1);
+    float* grid = (float*)malloc(sizeof(float) * (size_t)n);
+    for (int i = 0; i < n; ++i)
+        grid[i] = (i < n / 2) ? 0.0f + step * (float)i : end - step * (float)(n - 1 - i);
+    *dt = (grid[n - 1] - grid[0]) / (float)(n - 1);
+    const int half = T / 2;
+    for (int i = 1; i < n; ++i) {
+        const float ti = grid[i];
+        t[i - 1] = ti;
+        for (int j = 0; j < half; ++j) {
+            float f = expf((float)(-log(10000.0)) * (float)j / (float)half);
+            float a = ti * f;
+            temb[(size_t)(i - 1) * T + j] = cosf(a);
+            temb[(size_t)(i - 1) * T + half + j] = sinf(a);
+        }
+        if (T % 2) temb[(size_t)(i - 1) * T + T - 1] = 0.0f;
+        float w = expf((float)(-(double)S * (double)gamma) * (1.0f - ti));
+        bc[i - 1] = (w * (float)S) / (1.0f - w);
+        cc[i - 1] = w;
+        if (sp) {
+            float e1 = expf(-gamma_absorb * ti);
+            float num = 1.0f - expf(gamma_absorb * (ti - 1.0f));
+            float den = 1.0f - expf(-gamma_absorb);
+            sp[i - 1] = e1 * num / den;
+        }
+    }
+    free(grid);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* masked-sum order shared with the fp32 kernel: 128 lanes, lane = n mod 128 accumulates its
+ * particles in ascending order from +0; xor-butterfly inside each 32-lane warp; warps in order. */
+static float tree_sum(const float* vals, int stride, int N) {
+    float lane[128];
+    for (int i = 0; i < 128; ++i) lane[i] = 0.0f;
+    for (int n = 0; n < N; ++n) lane[n & 127] = lane[n & 127] + vals[(size_t)n * stride];
+    for (int off = 16; off >= 1; off >>= 1) {
+        float nxt[128];
+        for (int i = 0; i < 128; ++i) nxt[i] = lane[i] + lane[i ^ off];
+        memcpy(lane, nxt, sizeof(lane));
+    }
+    return ((lane[0] + lane[32]) + lane[64]) + lane[96];
+}
+
+static inline float dot_from(float acc, const float* w, const float* in, int n) {
+    for (int i = 0; i < n; ++i) acc = fmaf(w[i], in[i], acc);
+    return acc;
+}
+
+typedef struct {
+    float *xl, *skipl, *l1, *masked; /* [N][H] */
+} Scratch;
+
+static void epic_forward_jet(const MmbEpicDims* d, const MmbEpicLayout* Lo, const float* W,
+                             const float* x, const uint8_t* k, const uint8_t* mask, const float* temb, int N,
+                             float* v_out, float* logits_out, float* hidden_out, Scratch* sc) {
+    const int Dc = d->dim_continuous, S = d->vocab_size, T = d->dim_time_emb, C = d->dim_cont_emb,
+              D = d->dim_disc_emb, H = d->dim_hidden_local, G = d->dim_hidden_glob, L = d->num_blocks,
+              Sh = d->disc_head_hidden;
+    const int K0 = T + C + D;
+    float *xl = sc->xl, *skipl = sc->skipl, *l1 = sc->l1, *masked = sc->masked;
+    float pj[256], pool[768], g0[256], g1[256], xg[256], skipg[256], emb[256], sum[256];
+
+    /* ---- InputEmbeddings + EPiC_Projection.local_0 (utils.py:133-172, epic.py:186) */
+    for (int o = 0; o < H; ++o) pj[o] = dot_from(W[Lo->local0_b + o], W + Lo->local0_w + (size_t)o * K0, temb, T);
+    float cnt = 0.0f;
+    for (int n = 0; n < N; ++n) {
+        const float m = (float)mask[n];
+        cnt += m;
+        if (mask[n]) {
+            for (int c = 0; c < C; ++c)
+                emb[c] = dot_from(W[Lo->emb_cont_b + c], W + Lo->emb_cont_w + (size_t)c * Dc, x + (size_t)n * Dc, Dc);
+            const float* e = W + Lo->emb_disc + (size_t)k[n] * D;
+            for (int o = 0; o < H; ++o) {
+                const float* w = W + Lo->local0_w + (size_t)o * K0;
+                float acc = dot_from(pj[o], w + T, emb, C);
+                acc = dot_from(acc, w + T + C, e, D);
+                xl[(size_t)n * H + o] = lrelu(acc);
+            }
+        } else {
+            for (int o = 0; o < H; ++o) xl[(size_t)n * H + o] = lrelu(W[Lo->local0_b + o]);
+        }
+        for (int o = 0; o < H; ++o) masked[(size_t)n * H + o] = xl[(size_t)n * H + o] * m;
+    }
+    /* ---- meansum_pool + global_0..2 (epic.py:136-143,187-190) */
+    for (int o = 0; o < H; ++o) {
+        sum[o] = tree_sum(masked + o, H, N);
+        pool[o] = sum[o] / cnt;
+        pool[H + o] = sum[o];
+    }
+    for (int i = 0; i < T; ++i) pool[2 * H + i] = temb[i];
+    for (int o = 0; o < H; ++o)
+        g0[o] = lrelu(dot_from(W[Lo->global0_b + o], W + Lo->global0_w + (size_t)o * (2 * H + T), pool, 2 * H + T));
+    for (int o = 0; o < H; ++o)
+        g1[o] = lrelu(dot_from(W[Lo->global1_b + o], W + Lo->global1_w + (size_t)o * H, g0, H));
+    for (int o = 0; o < G; ++o)
+        xg[o] = lrelu(dot_from(W[Lo->global2_b + o], W + Lo->global2_w + (size_t)o * H, g1, H));
+    /* x_local * mask; skips (epic.py:148-149,191) */
+    memcpy(xl, masked, sizeof(float) * (size_t)N * H);
+    if (d->skip_connection) {
+        memcpy(skipl, xl, sizeof(float) * (size_t)N * H);
+        memcpy(skipg, xg, sizeof(float) * (size_t)G);
+    }
+    /* ---- EPiC layers (epic.py:217-241, 152-155) */
+    for (int l = 0; l < L; ++l) {
+        const float* Wl = W + Lo->layer0 + (size_t)l * Lo->layer_stride;
+        for (int n = 0; n < N; ++n) {
+            const float m = (float)mask[n];
+            for (int o = 0; o < H; ++o) masked[(size_t)n * H + o] = xl[(size_t)n * H + o] * m;
+        }
+        for (int o = 0; o < H; ++o) {
+            sum[o] = tree_sum(masked + o, H, N);
+            pool[o] = sum[o] / cnt;
+            pool[H + o] = sum[o];
+        }
+        for (int i = 0; i < G; ++i) pool[2 * H + i] = xg[i];
+        for (int i = 0; i < T; ++i) pool[2 * H + G + i] = temb[i];
+        const int Kg = 2 * H + G + T;
+        for (int o = 0; o < H; ++o)
+            g1[o] = lrelu(dot_from(Wl[Lo->l_g1_b + o], Wl + Lo->l_g1_w + (size_t)o * Kg, pool, Kg));
+        for (int o = 0; o < G; ++o)
+            g0[o] = lrelu(dot_from(Wl[Lo->l_g2_b + o], Wl + Lo->l_g2_w + (size_t)o * H, g1, H) + xg[o]);
+        memcpy(xg, g0, sizeof(float) * (size_t)G);
+        const int Kl = H + G + T;
+        for (int o = 0; o < H; ++o) {
+            const float* w = Wl + Lo->l_l1_w + (size_t)o * Kl;
+            float acc = dot_from(Wl[Lo->l_l1_b + o], w + H, xg, G);
+            pj[o] = dot_from(acc, w + H + G, temb, T);
+        }
+        for (int n = 0; n < N; ++n) {
+            const float m = (float)mask[n];
+            const float* xn = xl + (size_t)n * H;
+            for (int o = 0; o < H; ++o)
+                l1[(size_t)n * H + o] = lrelu(dot_from(pj[o], Wl + Lo->l_l1_w + (size_t)o * Kl, xn, H));
+        }
+        for (int n = 0; n < N; ++n) {
+            const float m = (float)mask[n];
+            float* xn = xl + (size_t)n * H;
+            float nw[256];
+            for (int o = 0; o < H; ++o) {
+                float acc = dot_from(Wl[Lo->l_l2_b + o], Wl + Lo->l_l2_w + (size_t)o * H, l1 + (size_t)n * H, H);
+                nw[o] = lrelu(acc + xn[o]) * m;
+            }
+            for (int o = 0; o < H; ++o) xn[o] = d->skip_connection ? nw[o] + skipl[(size_t)n * H + o] : nw[o];
+        }
+        if (d->skip_connection)
+            for (int o = 0; o < G; ++o) xg[o] = xg[o] + skipg[o];
+    }
+    /* ---- output layer, heads (epic.py:158-162, mbm.py:105-113) */
+    for (int n = 0; n < N; ++n) {
+        const float m = (float)mask[n];
+        const float* xn = xl + (size_t)n * H;
+        float h[64], z1[256];
+        for (int o = 0; o < Dc + S; ++o)
+            h[o] = dot_from(W[Lo->out_b + o], W + Lo->out_w + (size_t)o * H, xn, H) * m;
+        for (int c = 0; c < Dc; ++c) v_out[(size_t)n * Dc + c] = h[c];
+        if (Sh) {
+            for (int o = 0; o < Sh; ++o)
+                z1[o] = selu(dot_from(W[Lo->head0_b + o], W + Lo->head0_w + (size_t)o * S, h + Dc, S));
+            for (int o = 0; o < S; ++o)
+                logits_out[(size_t)n * S + o] = dot_from(W[Lo->head2_b + o], W + Lo->head2_w + (size_t)o * Sh, z1, Sh);
+        } else {
+            for (int o = 0; o < S; ++o) logits_out[(size_t)n * S + o] = h[Dc + o];
+        }
+        if (hidden_out)
+            for (int o = 0; o < H; ++o) hidden_out[(size_t)n * H + o] = xn[o];
+    }
+}
+
+static int dims_ok(const MmbEpicDims* d) {
+    return d->dim_hidden_local <= 256 && d->dim_hidden_glob <= 256 && d->dim_time_emb <= 256 &&
+           d->dim_cont_emb <= 256 && d->disc_head_hidden <= 256 && d->dim_continuous + d->vocab_size <= 64 &&
+           d->vocab_size <= 32;
+}
+
+static Scratch scratch_new(int N, int H) {
+    Scratch s;
+    size_t n = (size_t)N * H;
+    s.xl = (float*)malloc(sizeof(float) * n);
+    s.skipl = (float*)malloc(sizeof(float) * n);
+    s.l1 = (float*)malloc(sizeof(float) * n);
+    s.masked = (float*)malloc(sizeof(float) * n);
+    return s;
+}
+static void scratch_free(Scratch* s) { free(s->xl); free(s->skipl); free(s->l1); free(s->masked); }
+
+void mmbo_epic_forward(const MmbEpicDims* dims, const float* packed,
+                       const float* x, const uint8_t* k, const uint8_t* mask,
+                       const float* temb, int temb_stride, int B, int N,
+                       float* v_out, float* logits_out, float* hidden_out) {
+    if (!dims_ok(dims)) return;
+    const MmbEpicLayout Lo = mmb_epic_layout(dims);
+    const int Dc = dims->dim_continuous, S = dims->vocab_size, H = dims->dim_hidden_local;
+#pragma omp parallel
+    {
+        Scratch sc = scratch_new(N, H);
+#pragma omp for schedule(static)
+        for (int b = 0; b < B; ++b)
+            epic_forward_jet(dims, &Lo, packed, x + (size_t)b * N * Dc, k + (size_t)b * N, mask + (size_t)b * N,
+                             temb + (size_t)b * temb_stride, N, v_out + (size_t)b * N * Dc,
+                             logits_out + (size_t)b * N * S, hidden_out ? hidden_out + (size_t)b * N * H : NULL, &sc);
+        scratch_free(&sc);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* The fused hybrid update for one particle (bridges.py:260-286, 38-45, 106-132, 179-201).
+ * Jump: S independent Poisson(lam_s) draws gated by "at most one jump in total" are, exactly, a
+ * categorical with P(select s) = lam_s * exp(-Lam), Lam = sum_s lam_s, "none selected" = stay and
+ * "s = k selected" = stay (the self slot is retained so the thresholds do not depend on k beyond
+ * q_k).  One uniform decides: first s with u < c_s, c_s = sequential fp32 prefix sum. */
+static inline void update_particle(float* x, uint8_t* k, uint8_t* mask, const float* v, const float* logits,
+                                   const float* absorb_logit, float u_jump, const float* u_absorb,
+                                   float dt, float bc, float cc, float sp, int Dc, int S, int flags) {
+    uint8_t m = *mask;
+    if (flags & MMB_FLAG_ABSORBING) {
+        float sg = 1.0f / (1.0f + mmbo_expf(-absorb_logit[0]));
+        float p = dt * (sp * sg);
+        p = p > 1.0f ? 1.0f : p; /* torch.clamp(max=1): NaN stays NaN -> (u < NaN) false */
+        uint8_t born = (*u_absorb < p) ? 1 : 0;
+        m = (m == 1) ? 1 : born;
+        *mask = m;
+    }
+    const float mf = (float)m;
+    if (!(flags & MMB_FLAG_NO_EULER))
+        for (int c = 0; c < Dc; ++c) x[c] = (x[c] + dt * v[c]) * mf;
+    if (flags & MMB_FLAG_NO_JUMP) return;
+
+    float mx = logits[0];
+    for (int s = 1; s < S; ++s) mx = logits[s] > mx ? logits[s] : mx;
+    float e[32], z = 0.0f;
+    for (int s = 0; s < S; ++s) { e[s] = mmbo_expf(logits[s] - mx); z = z + e[s]; }
+    const int kk = *k;
+    const float qk = e[kk] / z;
+    float lam[32], Lam = 0.0f;
+    for (int s = 0; s < S; ++s) {
+        float q = e[s] / z;
+        float rate = (1.0f + bc * q) + cc * qk;
+        lam[s] = rate * dt;
+        Lam = Lam + lam[s];
+    }
+    const float E = mmbo_expf(-Lam);
+    int nk = kk;
+    float c = 0.0f;
+    for (int s = 0; s < S; ++s) {
+        c = c + lam[s] * E;
+        if (u_jump < c) { nk = s; break; }
+    }
+    *k = (uint8_t)(nk * (int)m);
+}
+
+void mmbo_bridge_update(float* x, uint8_t* k, uint8_t* mask,
+                        const float* v, const float* logits, const float* absorb_logit,
+                        const float* u_jump, const float* u_absorb,
+                        float dt, float bc, float cc, float sp,
+                        int B, int N, int Dc, int S, int flags) {
+    const size_t P = (size_t)B * N;
+#pragma omp parallel for schedule(static)
+    for (size_t p = 0; p < P; ++p)
+        update_particle(x + p * Dc, k + p, mask + p, v ? v + p * Dc : NULL, logits ? logits + p * S : NULL,
+                        absorb_logit ? absorb_logit + p : NULL, u_jump ? u_jump[p] : 2.0f, u_absorb ? u_absorb + p : NULL,
+                        dt, bc, cc, sp, Dc, S, flags);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+int mmbo_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void mmbo_generate(const MmbEpicDims* dims, const float* packed, float* x, uint8_t* k, const uint8_t* mask,
+                   const MmbStepTable* st, const float* u_jump, uint64_t seed, uint64_t jet_offset,
+                   int B, int N, int nthreads) {
+    if (!dims_ok(dims)) return;
+    const MmbEpicLayout Lo = mmb_epic_layout(dims);
+    const int Dc = dims->dim_continuous, S = dims->vocab_size, H = dims->dim_hidden_local, T = dims->dim_time_emb;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        Scratch sc = scratch_new(N, H);
+        float* v = (float*)malloc(sizeof(float) * (size_t)N * Dc);
+        float* lg = (float*)malloc(sizeof(float) * (size_t)N * S);
+        uint8_t* mk = (uint8_t*)malloc((size_t)N);
+#pragma omp for schedule(dynamic, 4)
+        for (int b = 0; b < B; ++b) {
+            float* xb = x + (size_t)b * N * Dc;
+            uint8_t* kb = k + (size_t)b * N;
+            memcpy(mk, mask + (size_t)b * N, (size_t)N);
+            for (int s = 0; s < st->n_steps; ++s) {
+                epic_forward_jet(dims, &Lo, packed, xb, kb, mk, st->temb + (size_t)s * T, N, v, lg, NULL, &sc);
+                for (int n = 0; n < N; ++n) {
+                    float u = u_jump ? u_jump[((size_t)s * B + b) * N + n]
+                                     : philox_uniform(seed, jet_offset + (uint64_t)b, 0, s, n);
+                    update_particle(xb + (size_t)n * Dc, kb + n, mk + n, v + (size_t)n * Dc, lg + (size_t)n * S,
+                                    NULL, u, NULL, st->dt, st->bc[s], st->cc[s], 0.0f, Dc, S, MMB_FLAG_MULTIMODAL);
+                }
+            }
+        }
+        free(v); free(lg); free(mk);
+        scratch_free(&sc);
+    }
+}

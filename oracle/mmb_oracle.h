@@ -1,0 +1,56 @@
+/*
+ * mmb_oracle.h — CPU restatement (plain C) of the Multimodal-Bridges generation hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (multimodal_particles_b200/, the C-ABI
+ * library) may link or call this; only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+ * legs use it, as the checker (and as the timed CPU baseline), never as the thing shipped.
+ *
+ * Parity status: PINNED — against outputs of the unmodified reference executed in the build
+ * container with injected uniforms (tests/golden/make_golden.py writes tests/golden/*.npz;
+ * tests/test_oracle_golden.py checks this file against them).  The reference's own tests hold no
+ * golden vectors for this path.
+ *
+ * Signatures deliberately mirror include/mmbridge.h so that parity tests pass the same buffers to
+ * both sides (host pointers here, device pointers there).
+ */
+#ifndef MMB_ORACLE_H
+#define MMB_ORACLE_H
+
+#include "../include/mmbridge.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+float mmbo_expf(float x);
+
+/* host-side step table with libm, following mbm.py:203-211, utils.py:183-198, bridges.py:125-130,
+ * 218-231.  The product computes the same table with torch ops; tests compare the two. */
+void mmbo_step_table(int num_timesteps, float time_eps, int S, float gamma, float gamma_absorb, int T,
+                     float* t, float* temb, float* bc, float* cc, float* sp, float* dt);
+
+void mmbo_epic_forward(const MmbEpicDims* dims, const float* packed,
+                       const float* x, const uint8_t* k, const uint8_t* mask,
+                       const float* temb, int temb_stride, int B, int N,
+                       float* v_out, float* logits_out, float* hidden_out);
+
+void mmbo_bridge_update(float* x, uint8_t* k, uint8_t* mask,
+                        const float* v, const float* logits, const float* absorb_logit,
+                        const float* u_jump, const float* u_absorb,
+                        float dt, float bc, float cc, float sp,
+                        int B, int N, int Dc, int S, int flags);
+
+void mmbo_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int stream_id,
+                          int n_steps, int B, int N);
+
+/* MultiModalBridgeMatching.simulate_dynamics (mbm.py:199-216); OpenMP over jets (nthreads<=0: all) */
+void mmbo_generate(const MmbEpicDims* dims, const float* packed, float* x, uint8_t* k, const uint8_t* mask,
+                   const MmbStepTable* steps, const float* u_jump, uint64_t seed, uint64_t jet_offset,
+                   int B, int N, int nthreads);
+
+int mmbo_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,121 @@
+"""ctypes access to oracle/libmmb_oracle.so — the CPU checker (test infrastructure only)."""
+import ctypes
+import json
+import os
+import subprocess
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libmmb_oracle.so")
+
+from multimodal_particles_b200._native import EpicDims  # noqa: E402  (plain ctypes struct)
+from multimodal_particles_b200.steptable import CStepTable  # noqa: E402
+
+_lib = None
+_fp = ctypes.POINTER(ctypes.c_float)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src_mtime = max(os.path.getmtime(os.path.join(ORACLE_DIR, f)) for f in ("mmb_oracle.c", "mmb_oracle.h"))
+        if not os.path.exists(ORACLE_SO) or (os.path.getmtime(ORACLE_SO) < src_mtime and os.access(ORACLE_DIR, os.W_OK)):
+            subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+        L = ctypes.CDLL(ORACLE_SO)
+        L.mmbo_expf.restype, L.mmbo_expf.argtypes = ctypes.c_float, [ctypes.c_float]
+        L.mmbo_max_threads.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _p(a, ty=_fp):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+def epic_forward(dims: EpicDims, packed, x, k, mask, temb, want_hidden=False):
+    B, N, Dc = x.shape
+    x, k, mask, temb, packed = f32(x), u8(k).reshape(B, N), u8(mask).reshape(B, N), f32(temb), f32(packed)
+    v = np.empty((B, N, Dc), np.float32)
+    logits = np.empty((B, N, dims.vocab_size), np.float32)
+    hidden = np.empty((B, N, dims.dim_hidden_local), np.float32) if want_hidden else None
+    stride = 0 if temb.reshape(-1, dims.dim_time_emb).shape[0] == 1 and B != 1 else dims.dim_time_emb
+    lib().mmbo_epic_forward(ctypes.byref(dims), _p(packed), _p(x), _p(k, _u8p), _p(mask, _u8p), _p(temb),
+                            ctypes.c_int(stride), B, N, _p(v), _p(logits), _p(hidden))
+    return (v, logits, hidden) if want_hidden else (v, logits)
+
+
+def bridge_update(x, k, mask, v, logits, u_jump, dt, bc, cc, absorb_logit=None, u_absorb=None, sp=0.0, flags=0):
+    """Returns updated copies (x, k, mask)."""
+    B, N, Dc = x.shape
+    S = logits.shape[-1] if logits is not None else 1
+    x, k, mask = f32(x).copy(), u8(k).reshape(B, N).copy(), u8(mask).reshape(B, N).copy()
+    args = [None if a is None else f32(a) for a in (v, logits, absorb_logit, u_jump, u_absorb)]
+    lib().mmbo_bridge_update(_p(x), _p(k, _u8p), _p(mask, _u8p), *[_p(a) for a in args],
+                             ctypes.c_float(dt), ctypes.c_float(bc), ctypes.c_float(cc), ctypes.c_float(sp),
+                             B, N, Dc, S, flags)
+    return x, k, mask
+
+
+def generate(dims: EpicDims, packed, x, k, mask, table, u_jump=None, seed=0, jet_offset=0, nthreads=0):
+    B, N, Dc = x.shape
+    x, k, mask, packed = f32(x).copy(), u8(k).reshape(B, N).copy(), u8(mask).reshape(B, N), f32(packed)
+    u = None if u_jump is None else f32(u_jump)
+    ct = CStepTable.from_table(table)
+    lib().mmbo_generate(ctypes.byref(dims), _p(packed), _p(x), _p(k, _u8p), _p(mask, _u8p), ctypes.byref(ct), _p(u),
+                        ctypes.c_uint64(seed), ctypes.c_uint64(jet_offset), B, N, nthreads)
+    return x, k
+
+
+def philox_uniforms(seed, jet_offset, n_steps, B, N, stream_id=0):
+    u = np.empty((n_steps, B, N), np.float32)
+    lib().mmbo_philox_uniforms(_p(u), ctypes.c_uint64(seed), ctypes.c_uint64(jet_offset), stream_id, n_steps, B, N)
+    return u
+
+
+def step_table_libm(num_timesteps, time_eps, S, gamma, T, gamma_absorb=None):
+    n = num_timesteps - 1
+    t, temb, bc, cc, sp = (np.empty(n, np.float32), np.empty((n, T), np.float32), np.empty(n, np.float32),
+                           np.empty(n, np.float32), np.empty(n, np.float32))
+    dt = ctypes.c_float()
+    lib().mmbo_step_table(num_timesteps, ctypes.c_float(time_eps), S, ctypes.c_float(gamma),
+                          ctypes.c_float(gamma_absorb or 0.0), T, _p(t), _p(temb), _p(bc), _p(cc),
+                          _p(sp) if gamma_absorb is not None else None, ctypes.byref(dt))
+    return SimpleNamespace(t=t, temb=temb, bc=bc, cc=cc, sp=sp, dt=dt.value)
+
+
+# ---- golden fixtures ------------------------------------------------------------------------
+def _ns(d):
+    return SimpleNamespace(**{k: _ns(v) if isinstance(v, dict) else v for k, v in d.items()})
+
+
+def load_mbm_golden(path):
+    """-> (fixture npz, config namespace, model of this repo with the fixture's weights)."""
+    from multimodal_particles_b200.config_classes.multimodal_bridge_matching_config import (
+        MultimodalBridgeMatchingConfig)
+    from multimodal_particles_b200.multimodal_bridge_matching import MultiModalBridgeMatching
+    z = np.load(path)
+    cfg = MultimodalBridgeMatchingConfig.from_dict(json.loads(str(z["config"])))
+    model = MultiModalBridgeMatching(cfg)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model.load_state_dict(sd, strict=True)
+    return z, cfg, model
+
+
+def packed_model(model):
+    enc = model.encoder
+    head = enc.fc_layer if enc.add_discrete_head else None
+    dims = enc.epic.epic_dims(head[0].out_features if head is not None else 0)
+    return dims, enc.epic.pack_weights(head).numpy()
