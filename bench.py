@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — generated jets/sec of the multimodal bridge generation loop (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision bf16|fp32]
+
+A "step" = one full generation (all 99 solver steps) of one batch of synthetic jets per GPU.
+Workload (config.workload) = BASELINE.json configs[1]: EPiC multimodal bridge, JetClass-shaped
+synthetic jets (128 particles, 3 continuous + 8 tokens), batch 4096 per GPU, 100 time points.
+
+  value          whole-job jets/s with the source state already resident in HBM (CUDA events on the
+                 launch stream, max over ranks); N>1 includes the NCCL gather of the generated jets
+                 and the all-reduce of the validation histograms
+  e2e            same metric through the public API MultiModalBridgeMatching.simulate_dynamics with
+                 PINNED HOST tensors in and host tensors out (H2D + D2H inside the timed region)
+  roofline       dominant kernel of the step (the fused generation kernel): algorithmic FLOPs of the
+                 EPiC network (0.819 MFLOP / jet-step) / CUDA-event time, against the
+                 measured bf16 tensor peak; roofline_update = the standalone fused update kernel
+                 (75 B / particle-step) against the measured HBM copy bandwidth
+  cpu_baseline   the CPU oracle (C port of the reference algorithm, OpenMP over jets) on a bounded
+                 sample of the same workload, rank 0, N=1 only
+  --impl reference   times that CPU port alone (the reference is pure Python and does not travel)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "generated jets/sec (128 particles, 100 steps)"
+WORKLOAD = "C2: EPiC multimodal bridge, JetClass-shape synthetic jets, N=128, Dc=3, S=8, B=4096/GPU, 99 solver steps"
+B_PER_GPU, N_PART, N_TIMESTEPS = 4096, 128, 100
+FLOP_PER_JET_STEP = 0.819e6          # SURVEY.md §8d (2*MAC, default widths)
+UPDATE_BYTES_PER_PARTICLE = 75       # SURVEY.md §8d / BASELINE.md §4
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained"), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def build_model(device):
+    import torch
+    from multimodal_particles_b200 import MultiModalBridgeMatching
+    from multimodal_particles_b200.config_classes.multimodal_bridge_matching_config import MultimodalBridgeMatchingConfig
+    cfg = MultimodalBridgeMatchingConfig()
+    cfg.bridge.num_timesteps = N_TIMESTEPS
+    cfg.data.max_num_particles = N_PART
+    torch.manual_seed(0)
+    model = MultiModalBridgeMatching(cfg)
+    return cfg, (model.to(device) if device is not None else model)
+
+
+def source_batch(n_jets, seed):
+    import torch
+    from multimodal_particles_b200.databatch import jetclass_like_databatch
+    return jetclass_like_databatch(n_jets, N_PART, generator=torch.Generator().manual_seed(seed))
+
+
+def cpu_port_jets_per_s(n_jets, repeats=1, seed=1234):
+    """The oracle port on the host cores, all OpenMP threads, same workload distribution."""
+    import oracle_lib as ol
+    _, model = build_model(None)
+    dims, packed = ol.packed_model(model)
+    b = source_batch(n_jets, seed)
+    tab = model.step_table()
+    x, k, m = b.source_continuous.numpy(), b.source_discrete[..., 0].numpy(), b.source_mask[..., 0].numpy()
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        ol.generate(dims, packed, x, k, m, tab, seed=7, jet_offset=0)
+        best = min(best, time.perf_counter() - t0)
+    return n_jets / best, best, ol.lib().mmbo_max_threads()
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU implementation of the path (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    sample = 64
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_jets_per_s(sample)
+    times = []
+    for _ in range(args.steps):
+        _, dt, cores = cpu_port_jets_per_s(sample)
+        times.append(dt)
+    total = sum(times)
+    value = sample * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"{sample} jets x 99 solver steps per step"},
+            "cpu_baseline": {"value": value, "unit": "jets/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} jets x 99 solver steps, OpenMP over jets"},
+            "e2e": {"value": value, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from multimodal_particles_b200 import HybridState, _native
+    from multimodal_particles_b200.epic import as_u8
+    from multimodal_particles_b200 import sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the generation path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    W = max(args.warmup, 3)
+    K = args.steps
+    B = B_PER_GPU
+
+    cfg, model = build_model(device)
+    native = model.encoder.native_model(device)
+    precision = args.precision or ("bf16" if native_supports_bf16(native, _native) else "fp32")
+    table = model.step_table()
+    n_steps = table.n_steps
+    batch = source_batch(B, 1234 + rank)
+    jet_offset = rank * B
+
+    # ---- device-resident arm: fresh source state per iteration (inputs in HBM before timing)
+    n_bufs = W + K
+    xs = [batch.source_continuous.to(device).contiguous() for _ in range(n_bufs)]
+    ks = [as_u8(batch.source_discrete.to(device)) for _ in range(n_bufs)]
+    mask = as_u8(batch.source_mask.to(device))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
+    gather_buf = sharding.GatherBuffers(B, N_PART, 3, world, device) if world > 1 else None
+    hist = sharding.ValidationHistograms(device, vocab_size=cfg.data.vocab_size_features)
+    stream = torch.cuda.current_stream()
+
+    def one_step(i):
+        native.generate(xs[i], ks[i], mask, table, seed=1, jet_offset=jet_offset + 0, precision=precision)
+        if world > 1:
+            counts = hist.accumulate(xs[i], ks[i], mask)
+            sharding.gather_and_reduce(gather_buf, xs[i], ks[i], mask, counts)
+
+    for i in range(W):
+        one_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
+            starts[i].record(stream)
+            one_step(W + i)
+            ends[i].record(stream)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+    if world > 1:
+        dist.barrier()
+    ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- kernel-only timing of the dominant kernel (generation kernel alone, same stream)
+    kern_ms = []
+    for i in range(min(K, 5)):
+        xs[i].copy_(batch.source_continuous.to(device))
+        ks[i].copy_(as_u8(batch.source_discrete.to(device)))
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        native.generate(xs[i], ks[i], mask, table, seed=1, jet_offset=jet_offset, precision=precision)
+        e.record(stream)
+        torch.cuda.synchronize()
+        kern_ms.append(s.elapsed_time(e))
+    kern = sum(kern_ms) / len(kern_ms)
+    pk = peaks()
+    flops = FLOP_PER_JET_STEP * B * n_steps
+    achieved_tf = flops / (kern * 1e-3) / 1e12
+    roofline = {"kernel": f"mmb::generate ({precision})", "bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16"],
+                "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16"], "traffic": None, "peak_source": pk["src"],
+                "algorithmic_flops_per_launch": flops, "ms_per_launch": kern}
+
+    # ---- standalone fused update kernel at an HBM-scale batch (32768 jets), 75 B / particle
+    roofline_update = None
+    if rank == 0:
+        roofline_update = time_update_kernel(torch, _native, device, pk, flush)
+
+    # ---- end-to-end arm: pinned host tensors -> simulate_dynamics -> host tensors
+    pin = lambda t: t.clone().pin_memory()
+    host_states = [HybridState(None, pin(batch.source_continuous), pin(batch.source_discrete), pin(batch.source_mask))
+                   for _ in range(3 + K)]
+    model.precision = precision
+    for i in range(3):
+        model.simulate_dynamics(host_states[i], batch, jet_offset=jet_offset)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        out = model.simulate_dynamics(host_states[3 + i], batch, jet_offset=jet_offset)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / float(te.item())
+    h2d = B * N_PART * (3 * 4 + 8 + 8)     # fp32 x, int64 tokens, int64 mask (reference layout)
+    d2h = B * N_PART * (3 * 4 + 8 + 8) + B * 4
+    assert out.continuous.device.type == "cpu"
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt_cpu, cores = cpu_port_jets_per_s(256)
+            cpu = {"value": v, "unit": "jets/s", "cores": cores, "kind": "port",
+                   "sample": f"256 jets x 99 solver steps of the same workload ({dt_cpu:.1f} s), OpenMP over jets"}
+        launches = K * (1 + (3 if world > 1 else 0))
+        line = {"metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world * B, "precision": precision,
+                           "l2": "flushed between timed iterations (256 MiB memset outside the event pair)",
+                           "rng": "in-kernel Philox4x32-10", "parallelism": f"jets sharded over {world} GPU(s)"},
+                "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "roofline": roofline, "roofline_update": roofline_update,
+                "cpu_baseline": cpu, "clocks": clocks.summary(), "wall_s_timed_region": t_wall}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def native_supports_bf16(native, _native_mod):
+    import torch
+    try:
+        x = torch.zeros(1, 128, 3, device=native.device)
+        k = torch.zeros(1, 128, dtype=torch.uint8, device=native.device)
+        m = torch.ones(1, 128, dtype=torch.uint8, device=native.device)
+        temb = torch.zeros(1, native.dims.dim_time_emb, device=native.device)
+        native.forward(x, k, m, temb, precision="bf16")
+        return True
+    except _native_mod.MmbError:
+        return False
+
+
+def time_update_kernel(torch, _native, device, pk, flush, jets=32768, reps=20):
+    B, N, S = jets, N_PART, 8
+    g = torch.Generator(device=device).manual_seed(3)
+    x = torch.randn(B, N, 3, device=device, generator=g)
+    v = torch.randn(B, N, 3, device=device, generator=g)
+    lg = torch.randn(B, N, S, device=device, generator=g)
+    u = torch.rand(B, N, device=device, generator=g)
+    k = torch.randint(0, S, (B, N), device=device, generator=g, dtype=torch.uint8)
+    m = torch.ones(B, N, device=device, dtype=torch.uint8)
+    stream = torch.cuda.current_stream()
+    for _ in range(3):
+        _native.bridge_update(x, k, m, v, lg, u, 0.0101, 5.0, 0.4)
+    times = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        _native.bridge_update(x, k, m, v, lg, u, 0.0101, 5.0, 0.4)
+        e.record(stream)
+        torch.cuda.synchronize()
+        times.append(s.elapsed_time(e))
+    ms = sum(times) / len(times)
+    nbytes = UPDATE_BYTES_PER_PARTICLE * B * N
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "mmb::bridge_update_vec4_kernel<8>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": gbs / pk["hbm"], "traffic": None, "peak_source": pk["src"], "jets": jets,
+            "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+// mmb_internal.h — declarations shared between the translation units of libmmbridge.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/mmbridge.h"
+
+namespace mmb {
+
+struct StepScalars;
+
+// error plumbing (api.cu): records the message for mmb_last_error() and returns the code
+int fail(int code, const char* fmt, ...);
+int cuda_ok(cudaError_t e, const char* what);
+
+// Device-resident model: the packed fp32 blob (layout of include/mmbridge.h) plus the operand
+// images the tcgen05 path consumes.
+struct EpicModel {
+    MmbEpicDims dims;
+    MmbEpicLayout layout;
+    int device;
+    int sm_count;
+    float* w;             // [layout.total] fp32, device
+    void* tc_image;       // bf16 UMMA operand image + fp32 side tables (epic_tc.cu), device; may be null
+    size_t tc_image_bytes;
+};
+
+// bridge_update.cu
+int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, const float* logits,
+                         const float* absorb, const float* uj, const float* ua, StepScalars sc,
+                         size_t P, int Dc, int S, int flags, cudaStream_t stream);
+int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, cudaStream_t stream);
+
+// epic_fp32.cu — CUDA-core path, bit-identical to the oracle
+int launch_epic_forward_fp32(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
+                             const float* temb, int temb_stride, int B, int N,
+                             float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream);
+// device step table: [n_steps] rows of (bc, cc, sp, pad) followed by [n_steps][T] temb
+int launch_generate_fp32(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table,
+                         int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
+                         int B, int N, cudaStream_t stream);
+
+// epic_tc.cu — tcgen05 path
+bool tc_supported(const MmbEpicDims* d, int N);
+int tc_build_image(EpicModel* m, const float* packed_host);
+int launch_epic_forward_tc(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
+                           const float* temb, int temb_stride, int B, int N,
+                           float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream);
+int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table,
+                       int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
+                       int B, int N, cudaStream_t stream);
+
+}  // namespace mmb

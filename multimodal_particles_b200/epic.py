@@ -30,7 +30,8 @@ class WeightNormLinear(nn.Module):
 
     def folded(self) -> torch.Tensor:
         # same ATen function the reference's forward pre-hook runs every step (epic.py:134)
-        return torch._weight_norm(self.weight_v.detach(), self.weight_g.detach(), 0)
+        # (always on the host, so the packed weights do not depend on where the module lives)
+        return torch._weight_norm(self.weight_v.detach().cpu().float(), self.weight_g.detach().cpu().float(), 0)
 
 
 class SinusoidalPositionalEncoding(nn.Module):
@@ -165,13 +166,16 @@ class EPiCWrapper(nn.Module):
 
     # ---- evaluation --------------------------------------------------------------------------
     def time_embedding(self, t: torch.Tensor) -> torch.Tensor:
-        """t [B,1] (generation) or [B,1,1] (training) -> [B,T]"""
-        return self.embedding.embedding_time(t.reshape(t.shape[0]).float()).contiguous()
+        """t [B,1] (generation) or [B,1,1] (training) -> [B,T] on t's device.  Evaluated on the host
+        (B floats) so the sin/cos are the same libm values whichever device the caller uses; the
+        generation loop does not come through here (it uses the precomputed step table)."""
+        emb = self.embedding.embedding_time(t.detach().reshape(t.shape[0]).float().cpu())
+        return emb.contiguous().to(t.device)
 
     def forward(self, t, x, k=None, mask=None, context_continuous=None, context_discrete=None,
                 output_hidden_local=False):
         model = self.native_model(x.device)
-        v, z, hidden = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask), self.time_embedding(t),
+        v, z, hidden = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask), self.time_embedding(t).to(x.device),
                                      want_hidden=True, precision=self.precision)
         h = torch.cat([v, z], dim=-1)
         return (h, hidden) if output_hidden_local else h

@@ -66,7 +66,7 @@ class MultiModalEPiC(nn.Module):
 
     def forward(self, t, x, k, mask=None, context_continuous=None, context_discrete=None):
         model = self.native_model(x.device)
-        v, logits = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask), self.epic.time_embedding(t),
+        v, logits = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask), self.epic.time_embedding(t).to(x.device),
                                   precision=self.precision)
         return v, logits, mask
 

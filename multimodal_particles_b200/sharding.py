@@ -1,0 +1,73 @@
+"""Multi-GPU layer of the generation path: jets are independent, so ranks
+generate disjoint slices with no data-path collective.  The only exchanges happen once per batch,
+after generation: an all-gather of the generated jets in the compact layout (fp32 features, uint8
+tokens, uint8 masks = 1 792 B / jet at N=128) and an all-reduce (SUM, int64) of the validation
+histograms.  One process per GPU; ``torch.distributed`` is the plumbing (NCCL on GPUs, gloo in the
+CPU tests).  The reference has no distributed code at all: this layer is new.
+"""
+from dataclasses import dataclass
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of ``total`` jets for ``rank``; sizes differ by at most one and the
+    slices tile [0, total).  ``lo`` is also the rank's Philox ``jet_offset``, which makes the
+    generated jets independent of ``world``."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+@dataclass
+class GatherBuffers:
+    """Preallocated receive buffers for the per-batch all-gather (no allocation in the loop)."""
+
+    x: torch.Tensor
+    k: torch.Tensor
+    mask: torch.Tensor
+
+    def __init__(self, batch: int, n: int, dim_continuous: int, world: int, device):
+        self.x = torch.empty(world * batch, n, dim_continuous, device=device, dtype=torch.float32)
+        self.k = torch.empty(world * batch, n, device=device, dtype=torch.uint8)
+        self.mask = torch.empty(world * batch, n, device=device, dtype=torch.uint8)
+
+
+class ValidationHistograms:
+    """Per-GPU int64 counts that the all-reduce sums: particle-level histograms of the three
+    continuous features, the token multiplicities and the particle multiplicity per jet (the
+    observables of JetClassHighLevelFeatures that need no clustering, jets.py:90-107)."""
+
+    def __init__(self, device, vocab_size=8, bins=64, lo=-5.0, hi=5.0, max_particles=128):
+        self.device, self.vocab_size, self.bins, self.lo, self.hi = device, vocab_size, bins, lo, hi
+        self.max_particles = max_particles
+        self.size = 3 * bins + vocab_size + (max_particles + 1)
+
+    def accumulate(self, x: torch.Tensor, k_u8: torch.Tensor, mask_u8: torch.Tensor) -> torch.Tensor:
+        live = mask_u8.bool()
+        counts = torch.zeros(self.size, dtype=torch.int64, device=x.device)
+        scale = self.bins / (self.hi - self.lo)
+        for c in range(x.shape[-1]):
+            idx = ((x[..., c][live] - self.lo) * scale).floor().clamp_(0, self.bins - 1).long()
+            counts[c * self.bins:(c + 1) * self.bins] += torch.bincount(idx, minlength=self.bins)
+        off = 3 * self.bins
+        counts[off:off + self.vocab_size] += torch.bincount(k_u8[live].long(), minlength=self.vocab_size)
+        off += self.vocab_size
+        mult = mask_u8.sum(dim=1, dtype=torch.int64).clamp_(max=self.max_particles)
+        counts[off:] += torch.bincount(mult, minlength=self.max_particles + 1)
+        return counts
+
+
+def gather_and_reduce(buffers: GatherBuffers, x, k_u8, mask_u8, counts=None):
+    """All-gather the generated jets into ``buffers`` and sum ``counts`` over ranks (in place)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        buffers.x.copy_(x), buffers.k.copy_(k_u8), buffers.mask.copy_(mask_u8)
+        return counts
+    dist.all_gather_into_tensor(buffers.x, x.contiguous())
+    dist.all_gather_into_tensor(buffers.k, k_u8.contiguous())
+    dist.all_gather_into_tensor(buffers.mask, mask_u8.contiguous())
+    if counts is not None:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts

@@ -331,11 +331,12 @@ static inline void update_particle(float* x, uint8_t* k, uint8_t* mask, const fl
     float e[32], z = 0.0f;
     for (int s = 0; s < S; ++s) { e[s] = mmbo_expf(logits[s] - mx); z = z + e[s]; }
     const int kk = *k;
-    const float qk = e[kk] / z;
+    const float zinv = 1.0f / z; /* q_s = e_s * (1/z): one IEEE division per particle */
+    const float ck = cc * (e[kk] * zinv);
     float lam[32], Lam = 0.0f;
     for (int s = 0; s < S; ++s) {
-        float q = e[s] / z;
-        float rate = (1.0f + bc * q) + cc * qk;
+        float q = e[s] * zinv;
+        float rate = (1.0f + bc * q) + ck;
         lam[s] = rate * dt;
         Lam = Lam + lam[s];
     }
