@@ -10,79 +10,118 @@
 #include "mmb_device.cuh"
 #include "mmb_internal.h"
 
+#include <stdlib.h>
+
 namespace mmb {
 
-template <typename T>
-__device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+// NF consecutive floats -> registers with the widest aligned vector (16 B when NF % 4 == 0, else 8 B)
+template <int NF, bool STREAM>
+__device__ __forceinline__ void load_floats(const float* __restrict__ p, float (&out)[NF]) {
+    if constexpr (NF % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NF / 4; ++i) {
+            const float4 q = STREAM ? __ldcs(reinterpret_cast<const float4*>(p) + i) : reinterpret_cast<const float4*>(p)[i];
+            out[4 * i] = q.x; out[4 * i + 1] = q.y; out[4 * i + 2] = q.z; out[4 * i + 3] = q.w;
+        }
+    } else if constexpr (NF % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < NF / 2; ++i) {
+            const float2 q = STREAM ? __ldcs(reinterpret_cast<const float2*>(p) + i) : reinterpret_cast<const float2*>(p)[i];
+            out[2 * i] = q.x; out[2 * i + 1] = q.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) out[i] = STREAM ? __ldcs(p + i) : p[i];
+    }
+}
 
-__device__ __forceinline__ float f4c(const float4& q, int c) { return c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w; }
+template <int NF>
+__device__ __forceinline__ void store_floats(float* __restrict__ p, const float (&v)[NF]) {
+    if constexpr (NF % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NF / 4; ++i)
+            reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else if constexpr (NF % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < NF / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) p[i] = v[i];
+    }
+}
 
-template <int S>
-__global__ void __launch_bounds__(256)
-bridge_update_vec4_kernel(float* __restrict__ x, uint8_t* __restrict__ k, uint8_t* __restrict__ mask,
-                          const float* __restrict__ v, const float* __restrict__ logits,
-                          const float* __restrict__ absorb, const float* __restrict__ uj,
-                          const float* __restrict__ ua, StepScalars sc, size_t groups, int flags) {
+template <int PPT>
+__device__ __forceinline__ void load_bytes(const uint8_t* __restrict__ p, int (&out)[PPT]) {
+    if constexpr (PPT == 4) {
+        const uchar4 q = *reinterpret_cast<const uchar4*>(p);
+        out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+    } else if constexpr (PPT == 2) {
+        const uchar2 q = *reinterpret_cast<const uchar2*>(p);
+        out[0] = q.x; out[1] = q.y;
+    } else {
+        out[0] = *p;
+    }
+}
+
+template <int PPT>
+__device__ __forceinline__ void store_bytes(uint8_t* __restrict__ p, const int (&v)[PPT]) {
+    if constexpr (PPT == 4) *reinterpret_cast<uchar4*>(p) = make_uchar4(v[0], v[1], v[2], v[3]);
+    else if constexpr (PPT == 2) *reinterpret_cast<uchar2*>(p) = make_uchar2(v[0], v[1]);
+    else *p = (uint8_t)v[0];
+}
+
+// Dc = 3.  Each thread owns PPT consecutive particles; group g covers particles [g*PPT, (g+1)*PPT).
+template <int S, int PPT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+bridge_update_vec_kernel(float* __restrict__ x, uint8_t* __restrict__ k, uint8_t* __restrict__ mask,
+                         const float* __restrict__ v, const float* __restrict__ logits,
+                         const float* __restrict__ absorb, const float* __restrict__ uj,
+                         const float* __restrict__ ua, StepScalars sc, size_t groups, int flags) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= groups) return;
     const bool do_euler = !(flags & MMB_FLAG_NO_EULER), do_jump = !(flags & MMB_FLAG_NO_JUMP),
                do_birth = (flags & MMB_FLAG_ABSORBING) != 0;
 
-    // ---- all loads first (independent; ~300 B in flight per thread)
-    float4 xr[3], vr[3], lr[S], ur = make_float4(2.f, 2.f, 2.f, 2.f), ar, uar;
-    uchar4 m4 = reinterpret_cast<const uchar4*>(mask)[g];
-    uchar4 k4 = make_uchar4(0, 0, 0, 0);
+    // ---- all loads first: independent, 75*PPT bytes in flight per thread
+    float xs[3 * PPT], vs[3 * PPT], lg[S * PPT], u[PPT], a[PPT], ub[PPT];
+    int m[PPT], kk[PPT];
+    load_bytes<PPT>(mask + g * PPT, m);
     if (do_euler) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            xr[i] = reinterpret_cast<const float4*>(x)[g * 3 + i];
-            vr[i] = ld_stream(reinterpret_cast<const float4*>(v) + g * 3 + i);
-        }
+        load_floats<3 * PPT, false>(x + g * 3 * PPT, xs);
+        load_floats<3 * PPT, true>(v + g * 3 * PPT, vs);
     }
     if (do_jump) {
-        k4 = reinterpret_cast<const uchar4*>(k)[g];
-        ur = ld_stream(reinterpret_cast<const float4*>(uj) + g);
-#pragma unroll
-        for (int i = 0; i < S; ++i) lr[i] = ld_stream(reinterpret_cast<const float4*>(logits) + g * S + i);
+        load_bytes<PPT>(k + g * PPT, kk);
+        load_floats<PPT, true>(uj + g * PPT, u);
+        load_floats<S * PPT, true>(logits + g * S * PPT, lg);
     }
     if (do_birth) {
-        ar = ld_stream(reinterpret_cast<const float4*>(absorb) + g);
-        uar = ld_stream(reinterpret_cast<const float4*>(ua) + g);
+        load_floats<PPT, true>(absorb + g * PPT, a);
+        load_floats<PPT, true>(ua + g * PPT, ub);
     }
-
     // ---- birth (bridges.py:260-286)
-    int m[4] = {m4.x, m4.y, m4.z, m4.w};
     if (do_birth) {
-        const float a[4] = {ar.x, ar.y, ar.z, ar.w}, u[4] = {uar.x, uar.y, uar.z, uar.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = absorbing_birth(m[j], a[j], u[j], sc);
-        reinterpret_cast<uchar4*>(mask)[g] = make_uchar4(m[0], m[1], m[2], m[3]);
+        for (int j = 0; j < PPT; ++j) m[j] = absorbing_birth(m[j], a[j], ub[j], sc);
+        store_bytes<PPT>(mask + g * PPT, m);
     }
-    // ---- Euler (bridges.py:38-45): 12 floats = particles 0..3 x (3 features), particle j owns 3j..3j+2
+    // ---- Euler (bridges.py:38-45)
     if (do_euler) {
-        float xs[12] = {xr[0].x, xr[0].y, xr[0].z, xr[0].w, xr[1].x, xr[1].y, xr[1].z, xr[1].w,
-                        xr[2].x, xr[2].y, xr[2].z, xr[2].w};
-        const float vs[12] = {vr[0].x, vr[0].y, vr[0].z, vr[0].w, vr[1].x, vr[1].y, vr[1].z, vr[1].w,
-                              vr[2].x, vr[2].y, vr[2].z, vr[2].w};
 #pragma unroll
-        for (int i = 0; i < 12; ++i) xs[i] = euler(xs[i], vs[i], sc.dt, (float)m[i / 3]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-            reinterpret_cast<float4*>(x)[g * 3 + i] = make_float4(xs[4 * i], xs[4 * i + 1], xs[4 * i + 2], xs[4 * i + 3]);
+        for (int i = 0; i < 3 * PPT; ++i) xs[i] = euler(xs[i], vs[i], sc.dt, (float)m[i / 3]);
+        store_floats<3 * PPT>(x + g * 3 * PPT, xs);
     }
     // ---- telegraph jump (bridges.py:106-132,179-201)
     if (do_jump) {
-        const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
-        const float u[4] = {ur.x, ur.y, ur.z, ur.w};
-        int nk[4];
+        int nk[PPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float lg[S];
+        for (int j = 0; j < PPT; ++j) {
+            float l[S];
 #pragma unroll
-            for (int s = 0; s < S; ++s) lg[s] = f4c(lr[(j * S + s) >> 2], (j * S + s) & 3);
-            nk[j] = telegraph_jump<S>(lg, kk[j], u[j], sc) * m[j];
+            for (int s = 0; s < S; ++s) l[s] = lg[j * S + s];
+            nk[j] = telegraph_jump<S>(l, kk[j], u[j], sc) * m[j];
         }
-        reinterpret_cast<uchar4*>(k)[g] = make_uchar4(nk[0], nk[1], nk[2], nk[3]);
+        store_bytes<PPT>(k + g * PPT, nk);
     }
 }
 
@@ -107,6 +146,16 @@ bridge_update_generic_kernel(float* __restrict__ x, uint8_t* __restrict__ k, uin
         k[p] = (uint8_t)(telegraph_jump_rt(logits + p * S, S, k[p], uj[p], sc) * m);
 }
 
+// tuning knob MMB_UPDATE_VARIANT = 10*particles_per_thread + min CTAs/SM (profiles/r01_update_variants.md)
+static int update_variant() {
+    static int v = [] {
+        const char* e = getenv("MMB_UPDATE_VARIANT");
+        const int q = e ? atoi(e) : 25;
+        return (q == 42 || q == 24 || q == 26 || q == 18) ? q : 25;
+    }();
+    return v;
+}
+
 static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, const float* logits,
@@ -117,13 +166,25 @@ int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, co
                         aligned16(logits) && aligned16(absorb) && aligned16(uj) && aligned16(ua) &&
                         (reinterpret_cast<uintptr_t>(k) & 3u) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3u) == 0;
     if (vec_ok && P >= 4) {
-        const size_t groups = P / 4;
+        const int var = update_variant();
+        const int ppt = var / 10;
+        const size_t groups = P / ppt;
         const unsigned grid = (unsigned)((groups + 255) / 256);
-        if (S == 4 && !(flags & MMB_FLAG_NO_JUMP))
-            bridge_update_vec4_kernel<4><<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, groups, flags);
-        else
-            bridge_update_vec4_kernel<8><<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, groups, flags);
-        done = groups * 4;
+        const bool s4 = (S == 4 && !(flags & MMB_FLAG_NO_JUMP));
+#define MMB_LAUNCH(PP, MB)                                                                                              \
+    do {                                                                                                                \
+        if (s4) bridge_update_vec_kernel<4, PP, MB><<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, groups, flags); \
+        else bridge_update_vec_kernel<8, PP, MB><<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, groups, flags);   \
+    } while (0)
+        switch (var) {
+            case 42: MMB_LAUNCH(4, 2); break;
+            case 24: MMB_LAUNCH(2, 4); break;
+            case 26: MMB_LAUNCH(2, 6); break;
+            case 18: MMB_LAUNCH(1, 8); break;
+            default: MMB_LAUNCH(2, 5); break;
+        }
+#undef MMB_LAUNCH
+        done = groups * ppt;
     }
     if (done < P) {
         const size_t count = P - done;
