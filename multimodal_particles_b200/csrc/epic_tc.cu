@@ -1,10 +1,669 @@
-// epic_tc.cu — tcgen05 path (placeholder until the kernels land in this round)
+// epic_tc.cu — the EPiC network + hybrid update on 5th-gen tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// Shape of the problem: the default EPiC (hidden 16) is eight tiny per-particle GEMMs per solver
+// step, K = N = 16, separated by element-wise work and two masked poolings — a strictly serial
+// chain per jet, 99 steps long.  HBM is irrelevant once the loop is fused (state in registers for
+// the whole generation); what bounds it is issue slots and the latency of the chain.  Design:
+//
+//   * one jet = one UMMA tile: M = 128 rows = the (padded) particles of the jet, thread r of a
+//     128-thread group owns particle r, its TMEM lane r and its row of the A operand;
+//   * every per-particle Linear is ONE tcgen05.mma (M128 x N16 x K16, bf16 operands from shared
+//     memory, fp32 accumulator in TMEM); weights sit in shared memory for the whole kernel in the
+//     canonical no-swizzle K-major layout; the epilogue (bias, leaky-ReLU, residual, mask, skip)
+//     runs on the accumulator row pulled back with tcgen05.ld and writes the next A operand as bf16;
+//   * algebraic folds keep K at 16: W0·[temb, A x + a, E[k]] = (time vector) + (W0c A) x + (W0d E)[k]
+//     so the first layer's A row is [x_hi, x_lo, onehot(k)] (x split in two bf16 for 16-bit
+//     mantissa); the global vector and the time embedding enter the local layers as a per-jet fp32
+//     bias computed once per layer, not as 32 more K columns;
+//   * masked sum pooling is a GEMM too: ones[128 x 128] · XL[128 x 16] — the activation tile just
+//     written as the next A operand is re-read as an MN-major B operand (K = particles), eight
+//     K-steps into a second TMEM accumulator, issued together with the next layer's GEMM.  Every
+//     TMEM lane then holds all 16 column sums, so the warp that runs the tiny global MLP reads
+//     them with one tcgen05.ld — no shuffles, no shared-memory reduction;
+//   * two jets per CTA (256 threads) share one copy of the weights; several CTAs per SM interleave
+//     their chains to hide the MMA -> commit -> mbarrier -> tcgen05.ld round trips.
+//
+// Numerics: bf16 operands, fp32 accumulate, fp32 residual stream / biases / global MLP / update.
+// Not bit-comparable with the fp32 path; tests/test_gpu_tc.py states the tolerance.
+//
+// Reference semantics: SURVEY.md §A.2 (mp/models/architectures/epic.py:136-241, utils.py:112-172,
+// mp/models/generative/multimodal_bridge_matching.py:90-113,199-216, bridges.py:38-45,106-132,179-201).
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "mmb_device.cuh"
 #include "mmb_internal.h"
+
 namespace mmb {
-bool tc_supported(const MmbEpicDims*, int) { return false; }
-int tc_build_image(EpicModel*, const float*) { return MMB_OK; }
-int launch_epic_forward_tc(const EpicModel*, const float*, const uint8_t*, const uint8_t*, const float*, int, int, int,
-                           float*, float*, float*, cudaStream_t) { return fail(MMB_EUNSUPPORTED, "tcgen05 path not built"); }
-int launch_generate_tc(const EpicModel*, float*, uint8_t*, const uint8_t*, const float*, int, float, const float*,
-                       uint64_t, uint64_t, int, int, cudaStream_t) { return fail(MMB_EUNSUPPORTED, "tcgen05 path not built"); }
+namespace {
+
+constexpr int kH = 16;      // hidden width this path is built for
+constexpr int kGP = 32;     // global width, padded
+constexpr int kJPC = 2;     // jets per CTA
+constexpr int kRows = 128;  // UMMA M
+constexpr int kMaxL = 4;
+constexpr int kMaxT = 32;
+
+// ---- image layout (host builds, kernel copies to shared memory) --------------------------------
+// bf16 region: n_bops matrices of [16 out][16 k] in UMMA canonical K-major no-swizzle layout
+//   (core matrix = 8 rows x 16 B; k-chunks 128 B apart (LBO), 8-row groups 256 B apart (SBO)).
+// fp32 region: vectors and [k][o] matrices for the CUDA-core side (o fastest: conflict-free reads).
+struct TcLayout {
+    int L, G, T, Sh, skip, n_bops;
+    // float offsets
+    int b0, c0, w0t, g0m, g0s, g0t, g0b, g1, g1b, g2, g2b, layer0, layer_stride;
+    int l_g1m, l_g1s, l_g1g, l_g1t, l_g1b, l_g2, l_g2b, l_l1g, l_l1t, l_l1b, l_l2b;  // within a layer
+    int bout, bh0, bh2, n_floats;
+    __host__ __device__ int bop_local0() const { return 0; }
+    __host__ __device__ int bop_l1(int l) const { return 1 + 2 * l; }
+    __host__ __device__ int bop_l2(int l) const { return 2 + 2 * l; }
+    __host__ __device__ int bop_out() const { return 1 + 2 * L; }
+    __host__ __device__ int bop_h0() const { return 2 + 2 * L; }
+    __host__ __device__ int bop_h2() const { return 3 + 2 * L; }
+};
+
+TcLayout make_layout(const MmbEpicDims& d) {
+    TcLayout t{};
+    t.L = d.num_blocks; t.G = d.dim_hidden_glob; t.T = d.dim_time_emb; t.Sh = d.disc_head_hidden; t.skip = d.skip_connection;
+    t.n_bops = 4 + 2 * t.L;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += n; return r; };
+    t.b0 = take(16); t.c0 = take(16); t.w0t = take(t.T * 16);
+    t.g0m = take(256); t.g0s = take(256); t.g0t = take(t.T * 16); t.g0b = take(16);
+    t.g1 = take(256); t.g1b = take(16);
+    t.g2 = take(16 * kGP); t.g2b = take(kGP);
+    t.layer0 = o;
+    {
+        int p = 0;
+        auto tk = [&](int n) { int r = p; p += n; return r; };
+        t.l_g1m = tk(256); t.l_g1s = tk(256); t.l_g1g = tk(kGP * 16); t.l_g1t = tk(t.T * 16); t.l_g1b = tk(16);
+        t.l_g2 = tk(16 * kGP); t.l_g2b = tk(kGP);
+        t.l_l1g = tk(kGP * 16); t.l_l1t = tk(t.T * 16); t.l_l1b = tk(16); t.l_l2b = tk(16);
+        t.layer_stride = p;
+    }
+    o += t.layer_stride * t.L;
+    t.bout = take(16); t.bh0 = take(16); t.bh2 = take(16);
+    t.n_floats = (o + 3) & ~3;
+    return t;
 }
+
+// element (row, k) of a [16 x 16] K-major operand -> index in bf16 units
+inline int bop_index(int row, int k) { return (row / 8) * 128 + (k / 8) * 64 + (row % 8) * 8 + (k % 8); }
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 in, fp32 accumulate); one thread issues
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, no swizzle (SURVEY/DESIGN: bits 0-13 addr>>4, 16-29 LBO>>4,
+// 32-45 SBO>>4, 46-47 version=1, 61-63 layout=0)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor kind::f16: D fp32 (bit 4), A/B bf16 (bits 7,10), N>>3 at 17, M>>4 at 24; b_mn = B is MN-major
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// this thread's 16-wide row -> its slot of the A operand (two 16-byte chunks, K-major canonical)
+__device__ __forceinline__ void store_a_row(uint8_t* abuf, int row, const float (&v)[16]) {
+    uint8_t* p = abuf + (row >> 3) * 256 + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(p + 128) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+}
+
+__device__ __forceinline__ float lrelu_fast(float a) { return fmaxf(a, 0.01f * a); }
+__device__ __forceinline__ float selu_fast(float a) {
+    const float scale = 1.0507009873554804934193349852946f;
+    const float alpha_scale = 1.0507009873554804934193349852946f * 1.6732632423543772848170429916717f;
+    return a > 0.0f ? scale * a : alpha_scale * (__expf(a) - 1.0f);
+}
+
+struct TcParams {
+    const uint8_t* image;  // [bf16 bops][fp32 region]
+    TcLayout lay;
+    // state / inputs
+    float* x;              // GENERATE: in/out [B,N,Dc]; forward: in
+    uint8_t* k;            // GENERATE: in/out [B,N];    forward: in
+    const uint8_t* mask;
+    const float* temb;     // forward: [B or 1][T] with stride; generate: table temb [n_steps][T]
+    int temb_stride;
+    const float* step_tab; // generate: [n_steps][4] (bc, cc, sp, t)
+    int n_steps;
+    float dt;
+    const float* u_jump;   // [n_steps,B,N] or null
+    uint64_t seed, jet_offset;
+    int B, N;
+    float *v_out, *logits_out, *hidden_out;  // forward outputs
+};
+
+// per-group shared scratch (floats)
+struct JetVec {
+    float gv[16], gv2[16], xg[kGP], xgmid[kGP], skipg[kGP], bias_l1[16];
+    float tv_bias0[16], tv_g0[16], tv_g1[kMaxL][16], tv_l1[kMaxL][16];
+    int cnt[4];
+};
+
+template <int DC, int S, bool GENERATE>
+__global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const TcLayout& lay = p.lay;
+    const int tid = threadIdx.x;
+    // ---- carve
+    uint8_t* s_bops = smem;                                   // n_bops * 512 B
+    uint8_t* s_ones = s_bops + lay.n_bops * 512;              // 4 KB: A operand of the pooling GEMM
+    float* s_wf = reinterpret_cast<float*>(s_ones + 4096);    // fp32 tables
+    uint8_t* s_grp = reinterpret_cast<uint8_t*>(s_wf + lay.n_floats);
+    constexpr int kGrpBytes = 4096 + ((sizeof(JetVec) + 15) & ~15) + 16;
+    __shared__ uint32_t s_tmem_slot;
+
+    // ---- one-time: weights -> smem, ones, barriers, TMEM
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.image);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        const int n16 = lay.n_bops * 32;  // 512 B per operand
+        for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+        const uint4* srcf = reinterpret_cast<const uint4*>(p.image + lay.n_bops * 512);
+        uint4* dstf = reinterpret_cast<uint4*>(s_wf);
+        for (int i = tid; i < lay.n_floats / 4; i += blockDim.x) dstf[i] = __ldg(srcf + i);
+        const uint32_t one2 = 0x3F803F80u;  // bf16 1.0 twice
+        for (int i = tid; i < 256; i += blockDim.x) reinterpret_cast<uint4*>(s_ones)[i] = make_uint4(one2, one2, one2, one2);
+    }
+    const int grp = tid >> 7, gt = tid & 127, wq = gt >> 5, lane = tid & 31;
+    uint8_t* abuf = s_grp + grp * kGrpBytes;
+    JetVec& jv = *reinterpret_cast<JetVec*>(abuf + 4096);
+    const uint32_t mbar = smem_u32(abuf + 4096 + ((sizeof(JetVec) + 15) & ~15));
+    if (gt == 0) mbar_init(mbar, 1);
+    if (tid < 32) tmem_alloc(smem_u32(&s_tmem_slot), kJPC * 32);
+    fence_barrier_init();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_slot;
+    const uint32_t t_main = tmem_base + grp * 32 + ((uint32_t)(wq * 32) << 16);
+    const uint32_t t_pool = t_main + 16;
+    const uint32_t d_main = tmem_base + grp * 32, d_pool = d_main + 16;
+
+    const long jet = (long)blockIdx.x * kJPC + grp;
+    if (jet < p.B) {
+        const int N = p.N, r = gt;
+        const bool valid = r < N;
+        const size_t pidx = (size_t)jet * N + r;
+        // ---- state
+        float xs[DC];
+        int kk = 0, m = 0;
+        if (valid) {
+#pragma unroll
+            for (int c = 0; c < DC; ++c) xs[c] = p.x[pidx * DC + c];
+            kk = p.k[pidx];
+            m = p.mask[pidx] ? 1 : 0;
+        } else {
+#pragma unroll
+            for (int c = 0; c < DC; ++c) xs[c] = 0.0f;
+        }
+        const float mf = (float)m;
+        {
+            const unsigned bal = __ballot_sync(0xffffffffu, m);
+            if (lane == 0) jv.cnt[wq] = __popc(bal);
+        }
+        group_bar(1 + grp);
+        const float inv_cnt = 1.0f / (float)(jv.cnt[0] + jv.cnt[1] + jv.cnt[2] + jv.cnt[3]);
+
+        const uint32_t a_addr = smem_u32(abuf);
+        const uint64_t a_desc = smem_desc(a_addr, 128, 256);
+        const uint64_t ones_desc = smem_desc(smem_u32(s_ones), 128, 256);
+        const uint32_t bops_addr = smem_u32(s_bops);
+        constexpr uint32_t idesc_k = instr_desc(128, 16, false);
+        constexpr uint32_t idesc_pool = instr_desc(128, 16, true);
+        uint32_t phase = 0;
+        const int T = lay.T, L = lay.L;
+        const int o16 = lane & 15, hf = lane >> 4;
+
+        const int n_steps = GENERATE ? p.n_steps : 1;
+        for (int step = 0; step < n_steps; ++step) {
+            // ---- (a) time vectors (warp 0) and the first A row [x_hi, x_lo, onehot(k)] * m
+            if (wq == 0) {
+                const float* te = GENERATE ? p.temb + (size_t)step * T : p.temb + (size_t)jet * p.temb_stride;
+                const int t0 = hf * (T / 2), t1 = t0 + T / 2;
+                float a0 = hf ? 0.0f : s_wf[lay.c0 + o16], a1 = hf ? 0.0f : s_wf[lay.g0b + o16];
+                for (int t = t0; t < t1; ++t) {
+                    const float tv = __ldg(te + t);
+                    a0 = fmaf(s_wf[lay.w0t + t * 16 + o16], tv, a0);
+                    a1 = fmaf(s_wf[lay.g0t + t * 16 + o16], tv, a1);
+                }
+                a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+                if (hf == 0) { jv.tv_bias0[o16] = a0; jv.tv_g0[o16] = a1; }
+                for (int l = 0; l < L; ++l) {
+                    const float* Wl = s_wf + lay.layer0 + l * lay.layer_stride;
+                    float b0 = hf ? 0.0f : Wl[lay.l_g1b + o16], b1 = hf ? 0.0f : Wl[lay.l_l1b + o16];
+                    for (int t = t0; t < t1; ++t) {
+                        const float tv = __ldg(te + t);
+                        b0 = fmaf(Wl[lay.l_g1t + t * 16 + o16], tv, b0);
+                        b1 = fmaf(Wl[lay.l_l1t + t * 16 + o16], tv, b1);
+                    }
+                    b0 += __shfl_xor_sync(0xffffffffu, b0, 16);
+                    b1 += __shfl_xor_sync(0xffffffffu, b1, 16);
+                    if (hf == 0) { jv.tv_g1[l][o16] = b0; jv.tv_l1[l][o16] = b1; }
+                }
+            }
+            {
+                float row[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) row[i] = 0.0f;
+#pragma unroll
+                for (int c = 0; c < DC; ++c) {
+                    const float hi = __bfloat162float(__float2bfloat16_rn(xs[c]));
+                    row[c] = hi * mf;
+                    row[DC + c] = (xs[c] - hi) * mf;
+                }
+#pragma unroll
+                for (int s = 0; s < S; ++s) row[2 * DC + s] = (kk == s) ? mf : 0.0f;
+                store_a_row(abuf, r, row);
+            }
+            fence_proxy_async();
+            group_bar(1 + grp);
+            // ---- (b) local_0
+            if (gt == 0) {
+                tc_fence_after();
+                umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_local0() * 512, 128, 256), idesc_k, 0);
+                umma_commit(mbar);
+            }
+            mbar_wait(mbar, phase); phase ^= 1;
+            tc_fence_after();
+            float acc[16], xl[16], skipl[16];
+            tmem_ld16(t_main, acc);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float b = m ? jv.tv_bias0[i] : s_wf[lay.b0 + i];
+                xl[i] = lrelu_fast(acc[i] + b) * mf;
+                skipl[i] = lay.skip ? xl[i] : 0.0f;
+            }
+            store_a_row(abuf, r, xl);
+            tc_fence_before();
+            fence_proxy_async();
+            group_bar(1 + grp);
+
+            for (int l = 0; l < L; ++l) {
+                const float* Wl = s_wf + lay.layer0 + l * lay.layer_stride;
+                // ---- (d) pooling GEMM (ones x XL, K = 128 particles) + fc_local1 on the same tile
+                if (gt == 0) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)  // K-step j = particles 16j..16j+15: two 8-row groups, MN-major
+                        umma(d_pool, ones_desc, smem_desc(a_addr + j * 512, 256, 128), idesc_pool, j > 0);
+                    umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_l1(l) * 512, 128, 256), idesc_k, 0);
+                    umma_commit(mbar);
+                }
+                mbar_wait(mbar, phase); phase ^= 1;
+                tc_fence_after();
+                // ---- (e) global path on warp 0 of the group (fp32, CUDA cores)
+                if (wq == 0) {
+                    float sv[16];
+                    tmem_ld16(t_pool, sv);
+                    if (l == 0) {  // EPiC_Projection globals (epic.py:187-190)
+                        float g = hf ? 0.0f : jv.tv_g0[o16];
+                        const float* Wsel = s_wf + (hf ? lay.g0s : lay.g0m);
+                        const float sc = hf ? 1.0f : inv_cnt;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) g = fmaf(Wsel[k * 16 + o16], sv[k] * sc, g);
+                        g += __shfl_xor_sync(0xffffffffu, g, 16);
+                        if (hf == 0) jv.gv[o16] = lrelu_fast(g);
+                        __syncwarp();
+                        g = hf ? 0.0f : s_wf[lay.g1b + o16];
+#pragma unroll
+                        for (int kq = 0; kq < 8; ++kq) g = fmaf(s_wf[lay.g1 + (hf * 8 + kq) * 16 + o16], jv.gv[hf * 8 + kq], g);
+                        g += __shfl_xor_sync(0xffffffffu, g, 16);
+                        if (hf == 0) jv.gv2[o16] = lrelu_fast(g);
+                        __syncwarp();
+                        g = s_wf[lay.g2b + lane];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) g = fmaf(s_wf[lay.g2 + k * kGP + lane], jv.gv2[k], g);
+                        g = lrelu_fast(g);
+                        jv.xg[lane] = g;
+                        jv.skipg[lane] = lay.skip ? g : 0.0f;
+                        __syncwarp();
+                    }
+                    // EPiC_layer globals (epic.py:228-232)
+                    float g = hf ? 0.0f : jv.tv_g1[l][o16];
+                    {
+                        const float* Wsel = Wl + (hf ? lay.l_g1s : lay.l_g1m);
+                        const float sc = hf ? 1.0f : inv_cnt;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) g = fmaf(Wsel[k * 16 + o16], sv[k] * sc, g);
+                    }
+#pragma unroll
+                    for (int q = 0; q < kGP / 2; ++q) g = fmaf(Wl[lay.l_g1g + (hf * (kGP / 2) + q) * 16 + o16], jv.xg[hf * (kGP / 2) + q], g);
+                    g += __shfl_xor_sync(0xffffffffu, g, 16);
+                    __syncwarp();
+                    if (hf == 0) jv.gv[o16] = lrelu_fast(g);
+                    __syncwarp();
+                    g = Wl[lay.l_g2b + lane];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) g = fmaf(Wl[lay.l_g2 + k * kGP + lane], jv.gv[k], g);
+                    const float xmid = lrelu_fast(g + jv.xg[lane]);
+                    __syncwarp();
+                    jv.xgmid[lane] = xmid;
+                    jv.xg[lane] = xmid + jv.skipg[lane];
+                    __syncwarp();
+                    // per-jet bias of fc_local1: time part + Wl1[:, H:H+G] xg   (epic.py:233-238)
+                    g = hf ? 0.0f : jv.tv_l1[l][o16];
+#pragma unroll
+                    for (int q = 0; q < kGP / 2; ++q) g = fmaf(Wl[lay.l_l1g + (hf * (kGP / 2) + q) * 16 + o16], jv.xgmid[hf * (kGP / 2) + q], g);
+                    g += __shfl_xor_sync(0xffffffffu, g, 16);
+                    if (hf == 0) jv.bias_l1[o16] = g;
+                    tc_fence_before();
+                }
+                group_bar(1 + grp);
+                // ---- (f) fc_local1 epilogue -> A operand of fc_local2
+                tc_fence_after();
+                tmem_ld16(t_main, acc);
+                {
+                    float l1[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) l1[i] = lrelu_fast(acc[i] + jv.bias_l1[i]);
+                    store_a_row(abuf, r, l1);
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                group_bar(1 + grp);
+                // ---- (g) fc_local2
+                if (gt == 0) {
+                    tc_fence_after();
+                    umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_l2(l) * 512, 128, 256), idesc_k, 0);
+                    umma_commit(mbar);
+                }
+                mbar_wait(mbar, phase); phase ^= 1;
+                tc_fence_after();
+                tmem_ld16(t_main, acc);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) xl[i] = lrelu_fast(acc[i] + Wl[lay.l_l2b + i] + xl[i]) * mf + skipl[i];
+                store_a_row(abuf, r, xl);
+                tc_fence_before();
+                fence_proxy_async();
+                group_bar(1 + grp);
+            }
+            // ---- (i) output layer (epic.py:158-162)
+            if (gt == 0) {
+                tc_fence_after();
+                umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_out() * 512, 128, 256), idesc_k, 0);
+                umma_commit(mbar);
+            }
+            mbar_wait(mbar, phase); phase ^= 1;
+            tc_fence_after();
+            tmem_ld16(t_main, acc);
+            float h[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) h[i] = (acc[i] + s_wf[lay.bout + i]) * mf;
+            float lg[S];
+            if (lay.Sh) {  // discrete head Linear -> SELU -> Linear on the logit slice (mbm.py:90-111)
+                store_a_row(abuf, r, h);
+                tc_fence_before();
+                fence_proxy_async();
+                group_bar(1 + grp);
+                if (gt == 0) {
+                    tc_fence_after();
+                    umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_h0() * 512, 128, 256), idesc_k, 0);
+                    umma_commit(mbar);
+                }
+                mbar_wait(mbar, phase); phase ^= 1;
+                tc_fence_after();
+                tmem_ld16(t_main, acc);
+                {
+                    float z1[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z1[i] = selu_fast(acc[i] + s_wf[lay.bh0 + i]);
+                    store_a_row(abuf, r, z1);
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                group_bar(1 + grp);
+                if (gt == 0) {
+                    tc_fence_after();
+                    umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_h2() * 512, 128, 256), idesc_k, 0);
+                    umma_commit(mbar);
+                }
+                mbar_wait(mbar, phase); phase ^= 1;
+                tc_fence_after();
+                tmem_ld16(t_main, acc);
+#pragma unroll
+                for (int s = 0; s < S; ++s) lg[s] = acc[s] + s_wf[lay.bh2 + s];
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; ++s) lg[s] = h[DC + s];
+            }
+            tc_fence_before();  // orders this step's last tcgen05.ld before the next step's first MMA (via the group barrier)
+
+            if constexpr (GENERATE) {
+                // ---- (k) hybrid update in registers (bridges.py:38-45,179-201)
+                const StepScalars sc{p.dt, __ldg(p.step_tab + step * 4 + 0), __ldg(p.step_tab + step * 4 + 1), 0.0f};
+#pragma unroll
+                for (int c = 0; c < DC; ++c) xs[c] = euler(xs[c], h[c], p.dt, mf);
+                if (valid) {
+                    const float u = p.u_jump ? __ldg(p.u_jump + ((size_t)step * p.B + jet) * N + r)
+                                             : philox_uniform(p.seed, p.jet_offset + (uint64_t)jet, 0, step, r);
+                    kk = telegraph_jump<S>(lg, kk, u, sc) * m;
+                }
+            } else {
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < DC; ++c) p.v_out[pidx * DC + c] = h[c];
+#pragma unroll
+                    for (int s = 0; s < S; ++s) p.logits_out[pidx * S + s] = lg[s];
+                    if (p.hidden_out) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(p.hidden_out + pidx * 16 + i) = make_float4(xl[i], xl[i + 1], xl[i + 2], xl[i + 3]);
+                    }
+                }
+            }
+        }
+        if constexpr (GENERATE) {
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < DC; ++c) p.x[pidx * DC + c] = xs[c];
+                p.k[pidx] = (uint8_t)kk;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem_base, kJPC * 32);
+}
+
+size_t tc_smem_bytes(const TcLayout& lay) {
+    const size_t grp = 4096 + ((sizeof(JetVec) + 15) & ~15) + 16;
+    return (size_t)lay.n_bops * 512 + 4096 + (size_t)lay.n_floats * 4 + kJPC * grp + 1024;
+}
+
+template <int DC, int S, bool GEN>
+int launch(const TcParams& p, cudaStream_t stream) {
+    const size_t bytes = tc_smem_bytes(p.lay);
+    auto kern = epic_tc_kernel<DC, S, GEN>;
+    if (int rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "tc smem attribute")) return rc;
+    const int grid = (p.B + kJPC - 1) / kJPC;
+    kern<<<grid, kJPC * 128, bytes, stream>>>(p);
+    return cuda_ok(cudaGetLastError(), "epic_tc launch");
+}
+
+template <bool GEN>
+int dispatch(const MmbEpicDims& d, const TcParams& p, cudaStream_t stream) {
+    if (d.dim_continuous == 3 && d.vocab_size == 8) return launch<3, 8, GEN>(p, stream);
+    if (d.dim_continuous == 3 && d.vocab_size == 4) return launch<3, 4, GEN>(p, stream);
+    return fail(MMB_EUNSUPPORTED, "tcgen05 path instantiated for (Dc,S) in {(3,8),(3,4)}");
+}
+
+}  // namespace
+
+bool tc_supported(const MmbEpicDims* d, int N) {
+    return d->dim_hidden_local == kH && d->dim_hidden_glob <= kGP && d->dim_time_emb <= kMaxT && d->dim_time_emb % 2 == 0 &&
+           d->num_blocks >= 1 && d->num_blocks <= kMaxL && d->disc_head_hidden <= 16 && d->dim_continuous == 3 &&
+           (d->vocab_size == 8 || d->vocab_size == 4) && N <= kRows && N >= 1;
+}
+
+// Build the device image from the packed fp32 blob (host): bf16 UMMA operands + fp32 side tables.
+int tc_build_image(EpicModel* m, const float* W) {
+    const MmbEpicDims& d = m->dims;
+    const MmbEpicLayout& Lo = m->layout;
+    const TcLayout lay = make_layout(d);
+    const int Dc = d.dim_continuous, S = d.vocab_size, T = d.dim_time_emb, C = d.dim_cont_emb, D = d.dim_disc_emb,
+              H = kH, G = d.dim_hidden_glob, L = d.num_blocks, Sh = d.disc_head_hidden;
+    const int K0 = T + C + D;
+    std::vector<__nv_bfloat16> bops((size_t)lay.n_bops * 256, __float2bfloat16(0.0f));
+    std::vector<float> wf((size_t)lay.n_floats, 0.0f);
+    auto setb = [&](int op, int row, int k, double v) { bops[(size_t)op * 256 + bop_index(row, k)] = __float2bfloat16((float)v); };
+
+    // local_0 folded: columns [x_hi | x_lo | onehot]
+    for (int o = 0; o < H; ++o) {
+        const float* w0 = W + Lo.local0_w + (size_t)o * K0;
+        for (int j = 0; j < Dc; ++j) {
+            double acc = 0;
+            for (int c = 0; c < C; ++c) acc += (double)w0[T + c] * W[Lo.emb_cont_w + (size_t)c * Dc + j];
+            setb(lay.bop_local0(), o, j, acc);
+            setb(lay.bop_local0(), o, Dc + j, acc);
+        }
+        for (int s = 0; s < S; ++s) {
+            double acc = 0;
+            for (int dd = 0; dd < D; ++dd) acc += (double)w0[T + C + dd] * W[Lo.emb_disc + (size_t)s * D + dd];
+            setb(lay.bop_local0(), o, 2 * Dc + s, acc);
+        }
+        double c0 = W[Lo.local0_b + o];
+        for (int c = 0; c < C; ++c) c0 += (double)w0[T + c] * W[Lo.emb_cont_b + c];
+        wf[lay.b0 + o] = W[Lo.local0_b + o];
+        wf[lay.c0 + o] = (float)c0;
+        for (int t = 0; t < T; ++t) wf[lay.w0t + t * 16 + o] = w0[t];
+        // projection globals
+        const float* g0 = W + Lo.global0_w + (size_t)o * (2 * H + T);
+        for (int k = 0; k < H; ++k) { wf[lay.g0m + k * 16 + o] = g0[k]; wf[lay.g0s + k * 16 + o] = g0[H + k]; }
+        for (int t = 0; t < T; ++t) wf[lay.g0t + t * 16 + o] = g0[2 * H + t];
+        wf[lay.g0b + o] = W[Lo.global0_b + o];
+        for (int k = 0; k < H; ++k) wf[lay.g1 + k * 16 + o] = W[Lo.global1_w + (size_t)o * H + k];
+        wf[lay.g1b + o] = W[Lo.global1_b + o];
+    }
+    for (int g = 0; g < G; ++g) {
+        for (int k = 0; k < H; ++k) wf[lay.g2 + k * kGP + g] = W[Lo.global2_w + (size_t)g * H + k];
+        wf[lay.g2b + g] = W[Lo.global2_b + g];
+    }
+    for (int l = 0; l < L; ++l) {
+        const float* Wl = W + Lo.layer0 + (size_t)l * Lo.layer_stride;
+        float* F = wf.data() + lay.layer0 + (size_t)l * lay.layer_stride;
+        const int Kg = 2 * H + G + T, Kl = H + G + T;
+        for (int o = 0; o < H; ++o) {
+            const float* g1 = Wl + Lo.l_g1_w + (size_t)o * Kg;
+            for (int k = 0; k < H; ++k) { F[lay.l_g1m + k * 16 + o] = g1[k]; F[lay.l_g1s + k * 16 + o] = g1[H + k]; }
+            for (int g = 0; g < G; ++g) F[lay.l_g1g + g * 16 + o] = g1[2 * H + g];
+            for (int t = 0; t < T; ++t) F[lay.l_g1t + t * 16 + o] = g1[2 * H + G + t];
+            F[lay.l_g1b + o] = Wl[Lo.l_g1_b + o];
+            const float* l1 = Wl + Lo.l_l1_w + (size_t)o * Kl;
+            for (int k = 0; k < H; ++k) setb(lay.bop_l1(l), o, k, l1[k]);
+            for (int g = 0; g < G; ++g) F[lay.l_l1g + g * 16 + o] = l1[H + g];
+            for (int t = 0; t < T; ++t) F[lay.l_l1t + t * 16 + o] = l1[H + G + t];
+            F[lay.l_l1b + o] = Wl[Lo.l_l1_b + o];
+            for (int k = 0; k < H; ++k) setb(lay.bop_l2(l), o, k, Wl[Lo.l_l2_w + (size_t)o * H + k]);
+            F[lay.l_l2b + o] = Wl[Lo.l_l2_b + o];
+        }
+        for (int g = 0; g < G; ++g) {
+            for (int k = 0; k < H; ++k) F[lay.l_g2 + k * kGP + g] = Wl[Lo.l_g2_w + (size_t)g * H + k];
+            F[lay.l_g2b + g] = Wl[Lo.l_g2_b + g];
+        }
+    }
+    for (int o = 0; o < Dc + S; ++o) {
+        for (int k = 0; k < H; ++k) setb(lay.bop_out(), o, k, W[Lo.out_w + (size_t)o * H + k]);
+        wf[lay.bout + o] = W[Lo.out_b + o];
+    }
+    if (Sh) {
+        for (int o = 0; o < Sh; ++o) {
+            for (int s = 0; s < S; ++s) setb(lay.bop_h0(), o, Dc + s, W[Lo.head0_w + (size_t)o * S + s]);
+            wf[lay.bh0 + o] = W[Lo.head0_b + o];
+        }
+        for (int o = 0; o < S; ++o) {
+            for (int k = 0; k < Sh; ++k) setb(lay.bop_h2(), o, k, W[Lo.head2_w + (size_t)o * Sh + k]);
+            wf[lay.bh2 + o] = W[Lo.head2_b + o];
+        }
+    }
+    const size_t nb = bops.size() * sizeof(__nv_bfloat16), nf = wf.size() * sizeof(float);
+    m->tc_image_bytes = nb + nf;
+    if (int rc = cuda_ok(cudaMalloc(&m->tc_image, m->tc_image_bytes), "cudaMalloc tc image")) return rc;
+    if (int rc = cuda_ok(cudaMemcpy(m->tc_image, bops.data(), nb, cudaMemcpyHostToDevice), "tc image upload")) return rc;
+    return cuda_ok(cudaMemcpy(static_cast<uint8_t*>(m->tc_image) + nb, wf.data(), nf, cudaMemcpyHostToDevice), "tc image upload");
+}
+
+int launch_epic_forward_tc(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
+                           const float* temb, int temb_stride, int B, int N,
+                           float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream) {
+    if (B == 0) return MMB_OK;
+    TcParams p{};
+    p.image = static_cast<const uint8_t*>(m->tc_image);
+    p.lay = make_layout(m->dims);
+    p.x = const_cast<float*>(x); p.k = const_cast<uint8_t*>(k); p.mask = mask;
+    p.temb = temb; p.temb_stride = temb_stride; p.n_steps = 1;
+    p.B = B; p.N = N; p.v_out = v_out; p.logits_out = logits_out; p.hidden_out = hidden_out;
+    return dispatch<false>(m->dims, p, stream);
+}
+
+int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table,
+                       int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
+                       int B, int N, cudaStream_t stream) {
+    if (B == 0 || n_steps == 0) return MMB_OK;
+    TcParams p{};
+    p.image = static_cast<const uint8_t*>(m->tc_image);
+    p.lay = make_layout(m->dims);
+    p.x = x; p.k = k; p.mask = mask;
+    p.step_tab = dev_table; p.temb = dev_table + (size_t)n_steps * 4; p.temb_stride = 0;
+    p.n_steps = n_steps; p.dt = dt; p.u_jump = u_jump; p.seed = seed; p.jet_offset = jet_offset;
+    p.B = B; p.N = N;
+    return dispatch<true>(m->dims, p, stream);
+}
+
+}  // namespace mmb
