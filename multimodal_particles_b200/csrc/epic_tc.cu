@@ -61,12 +61,20 @@ struct TcLayout {
     __host__ __device__ int bop_out() const { return 1 + 2 * L; }
     __host__ __device__ int bop_h0() const { return 2 + 2 * L; }
     __host__ __device__ int bop_h2() const { return 3 + 2 * L; }
+    // bias operands ([o][0] = hi, [o][1] = lo as bf16): consumed as one more K-step against a mask/ones A tile
+    // every weight operand w has a low-order companion at w + n_weights(): W = hi + lo with both halves
+    // bf16, issued as two K-steps, so the weights enter with ~16 mantissa bits (the activations stay bf16)
+    __host__ __device__ int n_weights() const { return 4 + 2 * L; }
+    __host__ __device__ int bop_bias_l2(int l) const { return 8 + 4 * L + l; }
+    __host__ __device__ int bop_bias_out() const { return 8 + 5 * L; }
+    __host__ __device__ int bop_bias_h0() const { return 9 + 5 * L; }
+    __host__ __device__ int bop_bias_h2() const { return 10 + 5 * L; }
 };
 
 TcLayout make_layout(const MmbEpicDims& d) {
     TcLayout t{};
     t.L = d.num_blocks; t.G = d.dim_hidden_glob; t.T = d.dim_time_emb; t.Sh = d.disc_head_hidden; t.skip = d.skip_connection;
-    t.n_bops = 4 + 2 * t.L;
+    t.n_bops = 11 + 5 * t.L;
     int o = 0;
     auto take = [&](int n) { int r = o; o += n; return r; };
     t.b0 = take(16); t.c0 = take(16); t.w0t = take(t.T * 16);
@@ -162,6 +170,69 @@ __device__ __forceinline__ void store_a_row(uint8_t* abuf, int row, const float 
     *reinterpret_cast<uint4*>(p + 128) = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
 }
 
+// same, rows of dead particles written as zeros (the mask multiply of epic.py:191,241 at pack time)
+__device__ __forceinline__ void store_a_row_masked(uint8_t* abuf, int row, const float (&v)[16], bool live) {
+    uint8_t* p = abuf + (row >> 3) * 256 + (row & 7) * 16;
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = live ? pack_bf16(v[2 * i], v[2 * i + 1]) : 0u;
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(p + 128) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// 16 floats from 16-byte aligned shared memory
+__device__ __forceinline__ void lds16(const float* p, float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 q = reinterpret_cast<const float4*>(p)[i];
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+    }
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Telegraph jump of the bf16 mode: same categorical (Form B) as mmb::telegraph_jump, evaluated with
+// fast intrinsics and without branches — the logits already carry bf16 rounding, so the exact-exp
+// contract of the fp32 path buys nothing here.
+template <int S>
+__device__ __forceinline__ int telegraph_jump_fast(const float (&lg)[S], int k, float u, const StepScalars& sc) {
+    float mx = lg[0];
+#pragma unroll
+    for (int s = 1; s < S; ++s) mx = fmaxf(mx, lg[s]);
+    float e[S], z = 0.0f, ek = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        e[s] = __expf(lg[s] - mx);
+        z += e[s];
+        ek = (k == s) ? e[s] : ek;
+    }
+    const float zinv = __fdividef(1.0f, z);
+    const float base = (1.0f + sc.cc * ek * zinv) * sc.dt, slope = sc.bc * zinv * sc.dt;
+    float lam[S], Lam = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        lam[s] = fmaf(e[s], slope, base);
+        Lam += lam[s];
+    }
+    const float E = __expf(-Lam);
+    float c = 0.0f;
+    int below = 0;  // number of thresholds c_s <= u  ==  index of the first s with u < c_s
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        c = fmaf(lam[s], E, c);
+        below += (u >= c) ? 1 : 0;
+    }
+    return below < S ? below : k;
+}
+
 __device__ __forceinline__ float lrelu_fast(float a) { return fmaxf(a, 0.01f * a); }
 __device__ __forceinline__ float selu_fast(float a) {
     const float scale = 1.0507009873554804934193349852946f;
@@ -187,6 +258,9 @@ struct TcParams {
     float *v_out, *logits_out, *hidden_out;  // forward outputs
 };
 
+// per-group shared memory: A tile (4 KB), mask tile (4 KB), dynamic bias operand of local_0 (512 B)
+constexpr int kGrpFixed = 4096 + 4096 + 512;
+
 // per-group shared scratch (floats)
 struct JetVec {
     float gv[16], gv2[16], xg[kGP], xgmid[kGP], skipg[kGP], bias_l1[16];
@@ -194,7 +268,7 @@ struct JetVec {
     int cnt[4];
 };
 
-template <int DC, int S, bool GENERATE>
+template <int DC, int S, int SH, bool GENERATE>
 __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcLayout& lay = p.lay;
@@ -204,7 +278,7 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
     uint8_t* s_ones = s_bops + lay.n_bops * 512;              // 4 KB: A operand of the pooling GEMM
     float* s_wf = reinterpret_cast<float*>(s_ones + 4096);    // fp32 tables
     uint8_t* s_grp = reinterpret_cast<uint8_t*>(s_wf + lay.n_floats);
-    constexpr int kGrpBytes = 4096 + ((sizeof(JetVec) + 15) & ~15) + 16;
+    constexpr int kGrpBytes = kGrpFixed + ((sizeof(JetVec) + 15) & ~15) + 16;
     __shared__ uint32_t s_tmem_slot;
 
     // ---- one-time: weights -> smem, ones, barriers, TMEM
@@ -221,8 +295,10 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
     }
     const int grp = tid >> 7, gt = tid & 127, wq = gt >> 5, lane = tid & 31;
     uint8_t* abuf = s_grp + grp * kGrpBytes;
-    JetVec& jv = *reinterpret_cast<JetVec*>(abuf + 4096);
-    const uint32_t mbar = smem_u32(abuf + 4096 + ((sizeof(JetVec) + 15) & ~15));
+    uint8_t* amask = abuf + 4096;   // A tile of the bias K-steps: columns 0,1 = mask of the row's particle
+    uint8_t* bb0 = abuf + 8192;     // B tile carrying this step's local_0 bias (hi, lo) in columns 0,1
+    JetVec& jv = *reinterpret_cast<JetVec*>(abuf + kGrpFixed);
+    const uint32_t mbar = smem_u32(abuf + kGrpFixed + ((sizeof(JetVec) + 15) & ~15));
     if (gt == 0) mbar_init(mbar, 1);
     if (tid < 32) tmem_alloc(smem_u32(&s_tmem_slot), kJPC * 32);
     fence_barrier_init();
@@ -245,14 +321,22 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
         int kk = 0, m = 0;
         if (valid) {
 #pragma unroll
-            for (int c = 0; c < DC; ++c) xs[c] = p.x[pidx * DC + c];
-            kk = p.k[pidx];
             m = p.mask[pidx] ? 1 : 0;
+            // dead particles: the first Euler step multiplies them to 0 (bridges.py:42) and nothing reads them before
+            for (int c = 0; c < DC; ++c) xs[c] = m ? p.x[pidx * DC + c] : 0.0f;
+            kk = m ? p.k[pidx] : 0;
         } else {
 #pragma unroll
             for (int c = 0; c < DC; ++c) xs[c] = 0.0f;
         }
         const float mf = (float)m;
+        const bool live = m != 0;
+        {
+            uint8_t* q = amask + (r >> 3) * 256 + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(q) = make_uint4(live ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(q + 128) = make_uint4(0u, 0u, 0u, 0u);
+            if (gt < 32) reinterpret_cast<uint4*>(bb0)[gt] = make_uint4(0u, 0u, 0u, 0u);
+        }
         {
             const unsigned bal = __ballot_sync(0xffffffffu, m);
             if (lane == 0) jv.cnt[wq] = __popc(bal);
@@ -261,11 +345,20 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
         const float inv_cnt = 1.0f / (float)(jv.cnt[0] + jv.cnt[1] + jv.cnt[2] + jv.cnt[3]);
 
         const uint32_t a_addr = smem_u32(abuf);
+        const uint32_t bops_addr = smem_u32(s_bops);
         const uint64_t a_desc = smem_desc(a_addr, 128, 256);
         const uint64_t ones_desc = smem_desc(smem_u32(s_ones), 128, 256);
-        const uint32_t bops_addr = smem_u32(s_bops);
+        const uint64_t amask_desc = smem_desc(smem_u32(amask), 128, 256);
+        const uint64_t bb0_desc = smem_desc(smem_u32(bb0), 128, 256);
+        auto bop_desc = [&](int op) { return smem_desc(bops_addr + op * 512, 128, 256); };
         constexpr uint32_t idesc_k = instr_desc(128, 16, false);
         constexpr uint32_t idesc_pool = instr_desc(128, 16, true);
+        const int n_w = lay.n_weights();
+        // D = A * (Whi + Wlo)^T: two K-steps on the same A tile
+        auto gemm = [&](int op) {
+            umma(d_main, a_desc, bop_desc(op), idesc_k, 0);
+            umma(d_main, a_desc, bop_desc(op + n_w), idesc_k, 1);
+        };
         uint32_t phase = 0;
         const int T = lay.T, L = lay.L;
         const int o16 = lane & 15, hf = lane >> 4;
@@ -284,7 +377,11 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
                 }
                 a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
                 a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-                if (hf == 0) { jv.tv_bias0[o16] = a0; jv.tv_g0[o16] = a1; }
+                if (hf == 0) {
+                    const float hi = __bfloat162float(__float2bfloat16_rn(a0));
+                    *reinterpret_cast<uint32_t*>(bb0 + (o16 >> 3) * 256 + (o16 & 7) * 16) = pack_bf16(hi, a0 - hi);
+                    jv.tv_g0[o16] = a1;
+                }
                 for (int l = 0; l < L; ++l) {
                     const float* Wl = s_wf + lay.layer0 + l * lay.layer_stride;
                     float b0 = hf ? 0.0f : Wl[lay.l_g1b + o16], b1 = hf ? 0.0f : Wl[lay.l_l1b + o16];
@@ -305,19 +402,20 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
 #pragma unroll
                 for (int c = 0; c < DC; ++c) {
                     const float hi = __bfloat162float(__float2bfloat16_rn(xs[c]));
-                    row[c] = hi * mf;
-                    row[DC + c] = (xs[c] - hi) * mf;
+                    row[c] = hi;
+                    row[DC + c] = xs[c] - hi;
                 }
 #pragma unroll
-                for (int s = 0; s < S; ++s) row[2 * DC + s] = (kk == s) ? mf : 0.0f;
-                store_a_row(abuf, r, row);
+                for (int s = 0; s < S; ++s) row[2 * DC + s] = (kk == s) ? 1.0f : 0.0f;
+                store_a_row_masked(abuf, r, row, live);
             }
             fence_proxy_async();
             group_bar(1 + grp);
             // ---- (b) local_0
             if (gt == 0) {
                 tc_fence_after();
-                umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_local0() * 512, 128, 256), idesc_k, 0);
+                gemm(lay.bop_local0());
+                umma(d_main, amask_desc, bb0_desc, idesc_k, 1);  // + bias on live rows; dead rows stay exactly 0
                 umma_commit(mbar);
             }
             mbar_wait(mbar, phase); phase ^= 1;
@@ -326,8 +424,7 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
             tmem_ld16(t_main, acc);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const float b = m ? jv.tv_bias0[i] : s_wf[lay.b0 + i];
-                xl[i] = lrelu_fast(acc[i] + b) * mf;
+                xl[i] = lrelu_fast(acc[i]);
                 skipl[i] = lay.skip ? xl[i] : 0.0f;
             }
             store_a_row(abuf, r, xl);
@@ -343,7 +440,7 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
 #pragma unroll
                     for (int j = 0; j < 8; ++j)  // K-step j = particles 16j..16j+15: two 8-row groups, MN-major
                         umma(d_pool, ones_desc, smem_desc(a_addr + j * 512, 256, 128), idesc_pool, j > 0);
-                    umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_l1(l) * 512, 128, 256), idesc_k, 0);
+                    gemm(lay.bop_l1(l));
                     umma_commit(mbar);
                 }
                 mbar_wait(mbar, phase); phase ^= 1;
@@ -410,9 +507,10 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
                 tc_fence_after();
                 tmem_ld16(t_main, acc);
                 {
-                    float l1[16];
+                    float l1[16], bl[16];
+                    lds16(jv.bias_l1, bl);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) l1[i] = lrelu_fast(acc[i] + jv.bias_l1[i]);
+                    for (int i = 0; i < 16; ++i) l1[i] = lrelu_fast(acc[i] + bl[i]);
                     store_a_row(abuf, r, l1);
                 }
                 tc_fence_before();
@@ -421,15 +519,16 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
                 // ---- (g) fc_local2
                 if (gt == 0) {
                     tc_fence_after();
-                    umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_l2(l) * 512, 128, 256), idesc_k, 0);
+                    gemm(lay.bop_l2(l));
+                    umma(d_main, amask_desc, bop_desc(lay.bop_bias_l2(l)), idesc_k, 1);
                     umma_commit(mbar);
                 }
                 mbar_wait(mbar, phase); phase ^= 1;
                 tc_fence_after();
                 tmem_ld16(t_main, acc);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) xl[i] = lrelu_fast(acc[i] + Wl[lay.l_l2b + i] + xl[i]) * mf + skipl[i];
-                store_a_row(abuf, r, xl);
+                for (int i = 0; i < 16; ++i) xl[i] = lrelu_fast(acc[i] + xl[i]) + skipl[i];  // dead rows: unused garbage, zeroed at pack
+                store_a_row_masked(abuf, r, xl, live);
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
@@ -437,24 +536,24 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
             // ---- (i) output layer (epic.py:158-162)
             if (gt == 0) {
                 tc_fence_after();
-                umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_out() * 512, 128, 256), idesc_k, 0);
+                gemm(lay.bop_out());
+                umma(d_main, amask_desc, bop_desc(lay.bop_bias_out()), idesc_k, 1);  // dead rows: A row 0, no bias -> h = 0
                 umma_commit(mbar);
             }
             mbar_wait(mbar, phase); phase ^= 1;
             tc_fence_after();
-            tmem_ld16(t_main, acc);
             float h[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) h[i] = (acc[i] + s_wf[lay.bout + i]) * mf;
+            tmem_ld16(t_main, h);
             float lg[S];
-            if (lay.Sh) {  // discrete head Linear -> SELU -> Linear on the logit slice (mbm.py:90-111)
+            if constexpr (SH > 0) {  // discrete head Linear -> SELU -> Linear on the logit slice (mbm.py:90-111)
                 store_a_row(abuf, r, h);
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
                 if (gt == 0) {
                     tc_fence_after();
-                    umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_h0() * 512, 128, 256), idesc_k, 0);
+                    gemm(lay.bop_h0());
+                    umma(d_main, ones_desc, bop_desc(lay.bop_bias_h0()), idesc_k, 1);  // all rows: fc(0) on dead rows as the reference
                     umma_commit(mbar);
                 }
                 mbar_wait(mbar, phase); phase ^= 1;
@@ -463,7 +562,7 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
                 {
                     float z1[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) z1[i] = selu_fast(acc[i] + s_wf[lay.bh0 + i]);
+                    for (int i = 0; i < 16; ++i) z1[i] = i < SH ? selu_fast(acc[i]) : 0.0f;
                     store_a_row(abuf, r, z1);
                 }
                 tc_fence_before();
@@ -471,14 +570,22 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
                 group_bar(1 + grp);
                 if (gt == 0) {
                     tc_fence_after();
-                    umma(d_main, a_desc, smem_desc(bops_addr + lay.bop_h2() * 512, 128, 256), idesc_k, 0);
+                    gemm(lay.bop_h2());
+                    umma(d_main, ones_desc, bop_desc(lay.bop_bias_h2()), idesc_k, 1);
                     umma_commit(mbar);
                 }
                 mbar_wait(mbar, phase); phase ^= 1;
                 tc_fence_after();
-                tmem_ld16(t_main, acc);
+                if constexpr (S <= 8) {
+                    float l8[8];
+                    tmem_ld8(t_main, l8);
 #pragma unroll
-                for (int s = 0; s < S; ++s) lg[s] = acc[s] + s_wf[lay.bh2 + s];
+                    for (int s = 0; s < S; ++s) lg[s] = l8[s];
+                } else {
+                    tmem_ld16(t_main, acc);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) lg[s] = acc[s];
+                }
             } else {
 #pragma unroll
                 for (int s = 0; s < S; ++s) lg[s] = h[DC + s];
@@ -489,11 +596,11 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
                 // ---- (k) hybrid update in registers (bridges.py:38-45,179-201)
                 const StepScalars sc{p.dt, __ldg(p.step_tab + step * 4 + 0), __ldg(p.step_tab + step * 4 + 1), 0.0f};
 #pragma unroll
-                for (int c = 0; c < DC; ++c) xs[c] = euler(xs[c], h[c], p.dt, mf);
+                for (int c = 0; c < DC; ++c) xs[c] = fmaf(p.dt, h[c], xs[c]);  // h = 0 on dead rows, x there stays 0
                 if (valid) {
                     const float u = p.u_jump ? __ldg(p.u_jump + ((size_t)step * p.B + jet) * N + r)
                                              : philox_uniform(p.seed, p.jet_offset + (uint64_t)jet, 0, step, r);
-                    kk = telegraph_jump<S>(lg, kk, u, sc) * m;
+                    kk = telegraph_jump_fast<S>(lg, kk, u, sc) * m;
                 }
             } else {
                 if (valid) {
@@ -504,7 +611,8 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
                     if (p.hidden_out) {
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(p.hidden_out + pidx * 16 + i) = make_float4(xl[i], xl[i + 1], xl[i + 2], xl[i + 3]);
+                            *reinterpret_cast<float4*>(p.hidden_out + pidx * 16 + i) =
+                                live ? make_float4(xl[i], xl[i + 1], xl[i + 2], xl[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
             }
@@ -523,14 +631,14 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
 }
 
 size_t tc_smem_bytes(const TcLayout& lay) {
-    const size_t grp = 4096 + ((sizeof(JetVec) + 15) & ~15) + 16;
+    const size_t grp = kGrpFixed + ((sizeof(JetVec) + 15) & ~15) + 16;
     return (size_t)lay.n_bops * 512 + 4096 + (size_t)lay.n_floats * 4 + kJPC * grp + 1024;
 }
 
-template <int DC, int S, bool GEN>
+template <int DC, int S, int SH, bool GEN>
 int launch(const TcParams& p, cudaStream_t stream) {
     const size_t bytes = tc_smem_bytes(p.lay);
-    auto kern = epic_tc_kernel<DC, S, GEN>;
+    auto kern = epic_tc_kernel<DC, S, SH, GEN>;
     if (int rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "tc smem attribute")) return rc;
     const int grid = (p.B + kJPC - 1) / kJPC;
     kern<<<grid, kJPC * 128, bytes, stream>>>(p);
@@ -539,17 +647,21 @@ int launch(const TcParams& p, cudaStream_t stream) {
 
 template <bool GEN>
 int dispatch(const MmbEpicDims& d, const TcParams& p, cudaStream_t stream) {
-    if (d.dim_continuous == 3 && d.vocab_size == 8) return launch<3, 8, GEN>(p, stream);
-    if (d.dim_continuous == 3 && d.vocab_size == 4) return launch<3, 4, GEN>(p, stream);
-    return fail(MMB_EUNSUPPORTED, "tcgen05 path instantiated for (Dc,S) in {(3,8),(3,4)}");
+    const int sh = d.disc_head_hidden;
+    if (d.dim_continuous == 3 && d.vocab_size == 8 && sh == 8) return launch<3, 8, 8, GEN>(p, stream);
+    if (d.dim_continuous == 3 && d.vocab_size == 8 && sh == 0) return launch<3, 8, 0, GEN>(p, stream);
+    if (d.dim_continuous == 3 && d.vocab_size == 4 && sh == 4) return launch<3, 4, 4, GEN>(p, stream);
+    if (d.dim_continuous == 3 && d.vocab_size == 4 && sh == 0) return launch<3, 4, 0, GEN>(p, stream);
+    return fail(MMB_EUNSUPPORTED, "tcgen05 path instantiated for (Dc,S,head) in {(3,8,8),(3,8,0),(3,4,4),(3,4,0)}");
 }
 
 }  // namespace
 
 bool tc_supported(const MmbEpicDims* d, int N) {
     return d->dim_hidden_local == kH && d->dim_hidden_glob <= kGP && d->dim_time_emb <= kMaxT && d->dim_time_emb % 2 == 0 &&
-           d->num_blocks >= 1 && d->num_blocks <= kMaxL && d->disc_head_hidden <= 16 && d->dim_continuous == 3 &&
-           (d->vocab_size == 8 || d->vocab_size == 4) && N <= kRows && N >= 1;
+           d->num_blocks >= 1 && d->num_blocks <= kMaxL && d->dim_continuous == 3 &&
+           (d->vocab_size == 8 || d->vocab_size == 4) && (d->disc_head_hidden == 0 || d->disc_head_hidden == d->vocab_size) &&
+           N <= kRows && N >= 1;
 }
 
 // Build the device image from the packed fp32 blob (host): bf16 UMMA operands + fp32 side tables.
@@ -562,7 +674,11 @@ int tc_build_image(EpicModel* m, const float* W) {
     const int K0 = T + C + D;
     std::vector<__nv_bfloat16> bops((size_t)lay.n_bops * 256, __float2bfloat16(0.0f));
     std::vector<float> wf((size_t)lay.n_floats, 0.0f);
-    auto setb = [&](int op, int row, int k, double v) { bops[(size_t)op * 256 + bop_index(row, k)] = __float2bfloat16((float)v); };
+    auto setb = [&](int op, int row, int k, double v) {
+        const __nv_bfloat16 hi = __float2bfloat16((float)v);
+        bops[(size_t)op * 256 + bop_index(row, k)] = hi;
+        bops[(size_t)(op + lay.n_weights()) * 256 + bop_index(row, k)] = __float2bfloat16((float)(v - (double)__bfloat162float(hi)));
+    };
 
     // local_0 folded: columns [x_hi | x_lo | onehot]
     for (int o = 0; o < H; ++o) {
@@ -631,6 +747,18 @@ int tc_build_image(EpicModel* m, const float* W) {
             for (int k = 0; k < Sh; ++k) setb(lay.bop_h2(), o, k, W[Lo.head2_w + (size_t)o * Sh + k]);
             wf[lay.bh2 + o] = W[Lo.head2_b + o];
         }
+    }
+    auto set_bias = [&](int op, int o, float b) {
+        const __nv_bfloat16 hi = __float2bfloat16(b);
+        bops[(size_t)op * 256 + bop_index(o, 0)] = hi;
+        bops[(size_t)op * 256 + bop_index(o, 1)] = __float2bfloat16(b - __bfloat162float(hi));
+    };
+    for (int l = 0; l < L; ++l)
+        for (int o = 0; o < H; ++o) set_bias(lay.bop_bias_l2(l), o, W[Lo.layer0 + (size_t)l * Lo.layer_stride + Lo.l_l2_b + o]);
+    for (int o = 0; o < Dc + S; ++o) set_bias(lay.bop_bias_out(), o, W[Lo.out_b + o]);
+    if (Sh) {
+        for (int o = 0; o < Sh; ++o) set_bias(lay.bop_bias_h0(), o, W[Lo.head0_b + o]);
+        for (int o = 0; o < S; ++o) set_bias(lay.bop_bias_h2(), o, W[Lo.head2_b + o]);
     }
     const size_t nb = bops.size() * sizeof(__nv_bfloat16), nf = wf.size() * sizeof(float);
     m->tc_image_bytes = nb + nf;
