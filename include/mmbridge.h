@@ -232,6 +232,17 @@ int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mas
 /* uniforms exactly as the in-kernel generator draws them, written to u [n_steps,B,N] (for tests) */
 int mmb_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, void* stream);
 
+/*
+ * Validation histograms of a generated batch, ACCUMULATED into counts (caller zeroes it): the
+ * per-GPU buffer that the multi-GPU layer all-reduces.  Layout of counts (uint64):
+ *   [Dc][bins] per-particle histograms of the continuous features over [lo,hi) (out-of-range values
+ *   go to the edge bins) | [S] token counts | [max_mult+1] particle multiplicity per jet (clamped).
+ * Only live particles (mask != 0) are counted.  Stands behind the jet-level observables of
+ * JetClassHighLevelFeatures that need no clustering (mp/data/particle_clouds/jets.py:90-107).
+ */
+int mmb_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,
+                              int bins, float lo, float hi, int max_mult, uint64_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

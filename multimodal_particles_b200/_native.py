@@ -52,6 +52,7 @@ SIGNATURES = {
     "mmb_generate_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "mmb_generate": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
     "mmb_philox_uniforms": (_i, [_vp, _u64, _u64, _i, _i, _i, _vp]),
+    "mmb_validation_histograms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp]),
 }
 
 
@@ -153,3 +154,13 @@ def philox_uniforms(seed, jet_offset, n_steps, B, N, device):
     with torch.cuda.device(device):
         check(load().mmb_philox_uniforms(_ptr(u), seed, jet_offset, n_steps, B, N, _stream()))
     return u
+
+
+def validation_histograms(x, k_u8, mask_u8, counts, vocab_size, bins, lo, hi, max_mult):
+    """Accumulate the validation histograms of (x, k, mask) into ``counts`` (int64, on device)."""
+    _require_cuda(x, k_u8, mask_u8, counts)
+    B, N, Dc = x.shape
+    with torch.cuda.device(x.device):
+        check(load().mmb_validation_histograms(_ptr(x), _ptr(k_u8), _ptr(mask_u8), B, N, Dc, vocab_size, bins, lo, hi,
+                                               max_mult, _ptr(counts), _stream()))
+    return counts

@@ -156,4 +156,15 @@ int mmb_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_step
     return launch_philox_uniforms(u, seed, jet_offset, n_steps, B, N, static_cast<cudaStream_t>(stream));
 }
 
+int mmb_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,
+                              int bins, float lo, float hi, int max_mult, uint64_t* counts, void* stream) {
+    if (!x || !k || !mask || !counts) return fail(MMB_EINVAL, "mmb_validation_histograms: null argument");
+    if (B < 0 || N < 0 || Dc < 1 || S < 1 || bins < 1 || max_mult < 0 || !(hi > lo))
+        return fail(MMB_EINVAL, "mmb_validation_histograms: bad shape or range");
+    if ((size_t)(Dc * bins + S + max_mult + 1) * 4 > 48 * 1024) return fail(MMB_EINVAL, "mmb_validation_histograms: too many bins");
+    if (B == 0 || N == 0) return MMB_OK;
+    return launch_validation_histograms(x, k, mask, B, N, Dc, S, bins, lo, hi, max_mult,
+                                        reinterpret_cast<unsigned long long*>(counts), static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -33,6 +33,10 @@ int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, co
                          size_t P, int Dc, int S, int flags, cudaStream_t stream);
 int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, cudaStream_t stream);
 
+// histograms.cu
+int launch_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,
+                                 int bins, float lo, float hi, int max_mult, unsigned long long* counts, cudaStream_t stream);
+
 // epic_fp32.cu — CUDA-core path, bit-identical to the oracle
 int launch_epic_forward_fp32(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
                              const float* temb, int temb_stride, int B, int N,

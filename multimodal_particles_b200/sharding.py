@@ -46,9 +46,14 @@ class ValidationHistograms:
         self.size = 3 * bins + vocab_size + (max_particles + 1)
 
     def accumulate(self, x: torch.Tensor, k_u8: torch.Tensor, mask_u8: torch.Tensor) -> torch.Tensor:
+        if x.is_cuda:  # one kernel (csrc/histograms.cu); the torch ops below are the host-side statement of it
+            from . import _native
+            counts = torch.zeros(self.size, dtype=torch.int64, device=x.device)
+            return _native.validation_histograms(x, k_u8, mask_u8, counts, self.vocab_size, self.bins, self.lo, self.hi,
+                                                 self.max_particles)
         live = mask_u8.bool()
         counts = torch.zeros(self.size, dtype=torch.int64, device=x.device)
-        scale = self.bins / (self.hi - self.lo)
+        scale = float(torch.tensor(self.bins / (self.hi - self.lo), dtype=torch.float32))
         for c in range(x.shape[-1]):
             idx = ((x[..., c][live] - self.lo) * scale).floor().clamp_(0, self.bins - 1).long()
             counts[c * self.bins:(c + 1) * self.bins] += torch.bincount(idx, minlength=self.bins)

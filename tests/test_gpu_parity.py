@@ -246,3 +246,18 @@ def test_full_size_c2_properties():
     xo, ko = ol.generate(dims, packed, b.source_continuous[sl].numpy(), b.source_discrete[sl, :, 0].numpy(),
                          b.source_mask[sl, :, 0].numpy(), model.step_table(), seed=42, jet_offset=2048)
     assert np.array_equal(out.continuous[sl].numpy(), xo) and np.array_equal(out.discrete[sl, :, 0].numpy(), ko)
+
+
+def test_validation_histograms_kernel_matches_host_statement():
+    """csrc/histograms.cu == the torch statement of the same counts (sharding.ValidationHistograms on CPU)."""
+    from multimodal_particles_b200 import sharding
+    g = torch.Generator().manual_seed(4)
+    b = jetclass_like_databatch(300, generator=g)
+    x = (b.source_continuous * 2.5).contiguous()           # some values beyond [-5, 5): edge bins
+    k = b.source_discrete[..., 0].to(torch.uint8).contiguous()
+    m = b.source_mask[..., 0].to(torch.uint8).contiguous()
+    hist = sharding.ValidationHistograms("cpu", vocab_size=8)
+    want = hist.accumulate(x, k, m)
+    got = hist.accumulate(x.to(DEV), k.to(DEV), m.to(DEV))
+    assert got.is_cuda and torch.equal(got.cpu(), want)
+    assert int(want[-129:].sum()) == 300 and int(want[:64].sum()) == int(m.sum())
