@@ -364,6 +364,116 @@ void mmbo_bridge_update(float* x, uint8_t* k, uint8_t* mask,
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* absorbing-rate transformer head (absorbing_flows.py:94-131).  h is kept as [N][C] (particle-major);
+ * the reference's [B,C,N] layout is a transpose of it. */
+size_t mmbo_absorb_head_floats(int H, int C, int n_blocks) {
+    size_t lin = (size_t)C * C + C, nrm = 2 * (size_t)C;
+    return (size_t)C * (H + 2) + C + (size_t)n_blocks * (3 * nrm + 6 * lin) + lin + C + 1;
+}
+
+static inline float swishf(float a) { return a * (1.0f / (1.0f + mmbo_expf(-a))); }
+
+/* GroupNorm(32 groups, eps 1e-6, affine) over [N][C] (gsdm.py:34-35) */
+static void group_norm(const float* in, float* out, const float* g, const float* b, int N, int C) {
+    const int gs = C / 32;
+    for (int grp = 0; grp < 32; ++grp) {
+        double s = 0.0, q = 0.0;
+        for (int n = 0; n < N; ++n)
+            for (int c = grp * gs; c < (grp + 1) * gs; ++c) { double v = in[(size_t)n * C + c]; s += v; q += v * v; }
+        const double cnt = (double)N * gs, mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + 1e-6)), mf = (float)mean;
+        for (int n = 0; n < N; ++n)
+            for (int c = grp * gs; c < (grp + 1) * gs; ++c)
+                out[(size_t)n * C + c] = (in[(size_t)n * C + c] - mf) * rstd * g[c] + b[c];
+    }
+}
+
+static void linear_rows(const float* in, float* out, const float* W, const float* b, int N, int Cin, int Cout) {
+    for (int n = 0; n < N; ++n)
+        for (int o = 0; o < Cout; ++o)
+            out[(size_t)n * Cout + o] = dot_from(b[o], W + (size_t)o * Cin, in + (size_t)n * Cin, Cin);
+}
+
+void mmbo_absorb_head(const float* W, int H, int C, int n_heads, int n_blocks,
+                      const float* hidden, const uint8_t* mask, const float* tbias, int tbias_stride,
+                      int B, int N, float* logit_out) {
+    const size_t lin = (size_t)C * C + C;
+#pragma omp parallel
+    {
+        float* x = (float*)malloc(sizeof(float) * (size_t)N * C);
+        float* t1 = (float*)malloc(sizeof(float) * (size_t)N * C);
+        float* t2 = (float*)malloc(sizeof(float) * (size_t)N * C);
+        float* q = (float*)malloc(sizeof(float) * (size_t)N * C);
+        float* kk = (float*)malloc(sizeof(float) * (size_t)N * C);
+        float* vv = (float*)malloc(sizeof(float) * (size_t)N * C);
+        float* sc = (float*)malloc(sizeof(float) * (size_t)N);
+        float* in0 = (float*)malloc(sizeof(float) * (size_t)(H + 2));
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < B; ++b) {
+            const float* p = W;
+            /* transformer_1_proj_in on cat[x_local_last, one_hot(mask)] (absorbing_flows.py:113-118) */
+            for (int n = 0; n < N; ++n) {
+                for (int i = 0; i < H; ++i) in0[i] = hidden[((size_t)b * N + n) * H + i];
+                in0[H] = mask[(size_t)b * N + n] ? 0.0f : 1.0f;
+                in0[H + 1] = mask[(size_t)b * N + n] ? 1.0f : 0.0f;
+                for (int o = 0; o < C; ++o)
+                    x[(size_t)n * C + o] = dot_from(p[(size_t)C * (H + 2) + o], p + (size_t)o * (H + 2), in0, H + 2);
+            }
+            p += (size_t)C * (H + 2) + C;
+            const int dh = C / n_heads;
+            const float scale = 1.0f / sqrtf((float)dh);
+            for (int blk = 0; blk < n_blocks; ++blk) {
+                const float *n1g = p, *n1b = p + C, *c1 = p + 2 * C, *n2g = c1 + lin, *n2b = n2g + C, *c2 = n2b + C,
+                            *ng = c2 + lin, *nb = ng + C, *wq = nb + C, *wk = wq + lin, *wv = wk + lin, *wo = wv + lin;
+                p = wo + lin;
+                const float* tb = tbias + (size_t)b * tbias_stride + (size_t)blk * C;
+                /* ResnetBlock (gsdm.py:54-66) */
+                group_norm(x, t1, n1g, n1b, N, C);
+                for (size_t i = 0; i < (size_t)N * C; ++i) t1[i] = swishf(t1[i]);
+                linear_rows(t1, t2, c1, c1 + (size_t)C * C, N, C, C);
+                for (int n = 0; n < N; ++n)
+                    for (int c = 0; c < C; ++c) t2[(size_t)n * C + c] += tb[c];
+                group_norm(t2, t1, n2g, n2b, N, C);
+                for (size_t i = 0; i < (size_t)N * C; ++i) t1[i] = swishf(t1[i]);
+                linear_rows(t1, t2, c2, c2 + (size_t)C * C, N, C, C);
+                for (size_t i = 0; i < (size_t)N * C; ++i) x[i] += t2[i];
+                /* AttnBlock (gsdm.py:142-168): all N slots attend to all N slots, no padding mask */
+                group_norm(x, t1, ng, nb, N, C);
+                linear_rows(t1, q, wq, wq + (size_t)C * C, N, C, C);
+                linear_rows(t1, kk, wk, wk + (size_t)C * C, N, C, C);
+                linear_rows(t1, vv, wv, wv + (size_t)C * C, N, C, C);
+                for (int h = 0; h < n_heads; ++h)
+                    for (int qi = 0; qi < N; ++qi) {
+                        float mx = -INFINITY;
+                        for (int ki = 0; ki < N; ++ki) {
+                            float a = dot_from(0.0f, kk + (size_t)ki * C + h * dh, q + (size_t)qi * C + h * dh, dh) * scale;
+                            sc[ki] = a;
+                            mx = a > mx ? a : mx;
+                        }
+                        float z = 0.0f;
+                        for (int ki = 0; ki < N; ++ki) { sc[ki] = mmbo_expf(sc[ki] - mx); z += sc[ki]; }
+                        const float zi = 1.0f / z;
+                        for (int d = 0; d < dh; ++d) {
+                            float acc = 0.0f;
+                            for (int ki = 0; ki < N; ++ki) acc = fmaf(vv[(size_t)ki * C + h * dh + d], sc[ki] * zi, acc);
+                            t2[(size_t)qi * C + h * dh + d] = acc;
+                        }
+                    }
+                linear_rows(t2, t1, wo, wo + (size_t)C * C, N, C, C);
+                for (size_t i = 0; i < (size_t)N * C; ++i) x[i] += t1[i];
+            }
+            /* pre_rate_proj, post_rate_proj (absorbing_flows.py:127-131) */
+            linear_rows(x, t1, p, p + (size_t)C * C, N, C, C);
+            p += lin;
+            for (int n = 0; n < N; ++n) logit_out[(size_t)b * N + n] = dot_from(p[C], p, t1 + (size_t)n * C, C);
+        }
+        free(x); free(t1); free(t2); free(q); free(kk); free(vv); free(sc); free(in0);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 int mmbo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

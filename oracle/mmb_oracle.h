@@ -48,6 +48,21 @@ void mmbo_generate(const MmbEpicDims* dims, const float* packed, float* x, uint8
                    const MmbStepTable* steps, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                    int B, int N, int nthreads);
 
+/*
+ * Absorbing-rate head of AbsorbingGenerator (mp/models/generative/absorbing/absorbing_flows.py:94-131;
+ * gsdm.py:34-66,142-168): Linear(H+2 -> C) on [last local hidden, one_hot(mask)], n_blocks x
+ * (ResnetBlock, AttnBlock) over the N particle slots, Linear(C->C), Linear(C->1).
+ * Weight blob (fp32, row-major [out][in], each followed by its bias), in this order:
+ *   proj_in [C][H+2]+[C];  per block: norm1 g[C] b[C]; conv1 [C][C]+[C]; norm2 g b; conv2 [C][C]+[C];
+ *   attn norm g b; q [C][C]+[C]; k; v; proj_out;   then pre_rate [C][C]+[C]; post_rate [1][C]+[1].
+ * tbias [B or 1][n_blocks][C] = temb_proj_b(swish(temb_net(timestep_embedding(1000 t)))) computed by the
+ * caller (per-step constants at generation time); stride 0 = shared by all jets.
+ */
+size_t mmbo_absorb_head_floats(int H, int C, int n_blocks);
+void mmbo_absorb_head(const float* W, int H, int C, int n_heads, int n_blocks,
+                      const float* hidden /*[B,N,H]*/, const uint8_t* mask /*[B,N]*/,
+                      const float* tbias, int tbias_stride, int B, int N, float* logit_out /*[B,N]*/);
+
 int mmbo_max_threads(void);
 
 #ifdef __cplusplus

@@ -119,3 +119,44 @@ def packed_model(model):
     head = enc.fc_layer if enc.add_discrete_head else None
     dims = enc.epic.epic_dims(head[0].out_features if head is not None else 0)
     return dims, enc.epic.pack_weights(head).numpy()
+
+
+# ---- absorbing flow -----------------------------------------------------------------------------
+def absorb_head(packed, H, C, n_heads, n_blocks, hidden, mask, tbias):
+    """tbias [B or 1, n_blocks, C] -> rate logits [B, N]"""
+    B, N, _ = hidden.shape
+    hidden, mask, tbias, packed = f32(hidden), u8(mask).reshape(B, N), f32(tbias), f32(packed)
+    lib().mmbo_absorb_head_floats.restype = ctypes.c_size_t
+    assert packed.size == lib().mmbo_absorb_head_floats(H, C, n_blocks), "head blob size"
+    out = np.empty((B, N), np.float32)
+    stride = 0 if tbias.shape[0] == 1 and B != 1 else n_blocks * C
+    lib().mmbo_absorb_head(_p(packed), H, C, n_heads, n_blocks, _p(hidden), _p(mask, _u8p), _p(tbias), stride, B, N, _p(out))
+    return out
+
+
+def load_absorbing_golden(path):
+    from multimodal_particles_b200.absorbing_flows import AbsorbingFlow
+    from multimodal_particles_b200.config_classes.absorbing_flows_config import AbsorbingConfig
+    z = np.load(path)
+    cfg = AbsorbingConfig.from_dict(json.loads(str(z["config"])))
+    model = AbsorbingFlow(cfg)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model.load_state_dict(sd, strict=True)
+    return z, cfg, model
+
+
+def absorbing_step(model, trunk, head_blob, x, k, mask, temb, tbias, u_jump, u_absorb, dt, bc, cc, sp):
+    """One step of AbsorbingFlow.simulate_dynamics with oracle pieces -> (x, k, mask, heads)."""
+    dims, packed = trunk
+    g = model.generator
+    v, logits, hidden = epic_forward(dims, packed, x, k, mask, temb, want_hidden=True)
+    a = absorb_head(head_blob, g.encoder_output_dim_local, g.transformer_dim, g.n_heads, g.n_attn_blocks, hidden, mask, tbias)
+    x, k, mask = bridge_update(x, k, mask, v, logits, u_jump, dt, bc, cc, absorb_logit=a, u_absorb=u_absorb, sp=sp, flags=1)
+    return x, k, mask, (v, logits, a)
+
+
+def absorbing_trunk(model):
+    g = model.generator
+    head = g.discrete_head_mlp if g.add_discrete_head else None
+    dims = g.epic.epic_dims(head[0].out_features if head is not None else 0)
+    return dims, g.epic.pack_weights(head).numpy()
