@@ -233,6 +233,38 @@ int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mas
 int mmb_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, void* stream);
 
 /*
+ * Absorbing-rate transformer head of AbsorbingGenerator (mp/models/generative/absorbing/absorbing_flows.py:56-131;
+ * blocks: mp/models/architectures/gsdm.py:38-66,142-168).  Built for transformer_dim = 128, n_heads = 2.
+ * Packed blob (fp32, every matrix row-major [out][in] followed by its bias):
+ *   transformer_1_proj_in [C][H+2]+[C];
+ *   per block: res.norm1 g[C] b[C]; res.conv1 [C][C]+[C]; res.norm2 g b; res.conv2 [C][C]+[C];
+ *              attn.norm g b; attn.q [C][C]+[C]; attn.k; attn.v; attn.proj_out;
+ *   pre_rate_proj [C][C]+[C]; post_rate_proj [1][C]+[1].
+ * The time term of every ResnetBlock, temb_proj_b(swish(temb_net(timestep_embedding(1000 t)))), is an input
+ * (tbias [B or 1][n_blocks][C], stride 0 = one time for all jets): at generation time it is a per-step constant
+ * the host computes once per step table.
+ */
+typedef struct MmbAbsorbHead MmbAbsorbHead;
+int mmb_absorb_head_create(int hidden, int transformer_dim, int n_heads, int n_blocks, const float* packed, size_t n_floats,
+                           int device, MmbAbsorbHead** out);
+void mmb_absorb_head_destroy(MmbAbsorbHead* head);
+/* hidden [B,N,H] (EPiC last local hidden), mask [B,N] u8 -> logit_out [B,N] (heads.absorbing[...,0]) */
+int mmb_absorb_head_forward(const MmbAbsorbHead* head, const float* hidden, const uint8_t* mask, const float* tbias,
+                            int tbias_stride, int B, int N, float* logit_out, void* stream);
+
+/*
+ * Whole generation loop of the absorbing flow: per step trunk + discrete head (mmb_epic_forward with the last
+ * hidden), rate head, then mmb_bridge_update(MMB_FLAG_ABSORBING).  Stands behind AbsorbingFlow.simulate_dynamics
+ * (absorbing_flows.py:255-275) minus the final .cpu().  mask is in/out (particles are born).
+ *   tbias: HOST [n_steps][n_blocks][C];  u_jump / u_absorb: device [n_steps,B,N] or NULL for Philox streams 0 / 1.
+ */
+size_t mmb_generate_absorbing_workspace_bytes(const MmbEpicModel* model, const MmbAbsorbHead* head, int B, int N, int n_steps);
+int mmb_generate_absorbing(const MmbEpicModel* model, const MmbAbsorbHead* head, float* x, uint8_t* k, uint8_t* mask,
+                           const MmbStepTable* steps, const float* tbias, const float* u_jump, const float* u_absorb,
+                           uint64_t seed, uint64_t jet_offset, int B, int N, void* workspace, size_t workspace_bytes,
+                           int precision, void* stream);
+
+/*
  * Validation histograms of a generated batch, ACCUMULATED into counts (caller zeroes it): the
  * per-GPU buffer that the multi-GPU layer all-reduces.  Layout of counts (uint64):
  *   [Dc][bins] per-particle histograms of the continuous features over [lo,hi) (out-of-range values

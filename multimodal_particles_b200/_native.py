@@ -52,6 +52,12 @@ SIGNATURES = {
     "mmb_generate_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "mmb_generate": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
     "mmb_philox_uniforms": (_i, [_vp, _u64, _u64, _i, _i, _i, _vp]),
+    "mmb_absorb_head_create": (_i, [_i, _i, _i, _i, _vp, _sz, _i, ctypes.POINTER(_vp)]),
+    "mmb_absorb_head_destroy": (None, [_vp]),
+    "mmb_absorb_head_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mmb_generate_absorbing_workspace_bytes": (_sz, [_vp, _vp, _i, _i, _i]),
+    "mmb_generate_absorbing": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _vp, _vp, _u64, _u64, _i, _i,
+                                    _vp, _sz, _i, _vp]),
     "mmb_validation_histograms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp]),
 }
 
@@ -164,3 +170,50 @@ def validation_histograms(x, k_u8, mask_u8, counts, vocab_size, bins, lo, hi, ma
         check(load().mmb_validation_histograms(_ptr(x), _ptr(k_u8), _ptr(mask_u8), B, N, Dc, vocab_size, bins, lo, hi,
                                                max_mult, _ptr(counts), _stream()))
     return counts
+
+
+class AbsorbHead:
+    """Owner of one ``MmbAbsorbHead*`` (device-resident transformer rate head)."""
+
+    def __init__(self, hidden, transformer_dim, n_heads, n_blocks, packed: torch.Tensor, device):
+        lib = load()
+        packed = packed.detach().to("cpu", torch.float32).contiguous()
+        self.device, self.n_blocks, self.dim = torch.device(device), n_blocks, transformer_dim
+        self._handle = ctypes.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(lib.mmb_absorb_head_create(hidden, transformer_dim, n_heads, n_blocks, _ptr(packed), packed.numel(), index,
+                                         ctypes.byref(self._handle)))
+
+    def __del__(self):
+        if getattr(self, "_handle", None) and _lib is not None:
+            _lib.mmb_absorb_head_destroy(self._handle)
+            self._handle = None
+
+    def forward(self, hidden, mask_u8, tbias):
+        """hidden [B,N,H] f32, mask [B,N] u8, tbias [B or 1, n_blocks, C] -> rate logits [B,N]"""
+        hidden, tbias = hidden.contiguous(), tbias.contiguous()
+        _require_cuda(hidden, mask_u8, tbias)
+        B, N, _ = hidden.shape
+        out = torch.empty(B, N, device=hidden.device, dtype=torch.float32)
+        stride = 0 if tbias.shape[0] == 1 and B != 1 else self.n_blocks * self.dim
+        with torch.cuda.device(hidden.device):
+            check(load().mmb_absorb_head_forward(self._handle, _ptr(hidden), _ptr(mask_u8), _ptr(tbias), stride, B, N, _ptr(out),
+                                                 _stream()))
+        return out
+
+
+def generate_absorbing(trunk: EpicModel, head: AbsorbHead, x, k_u8, mask_u8, table, tbias_host, u_jump=None, u_absorb=None,
+                       seed=0, jet_offset=0, precision="bf16"):
+    """In-place absorbing-flow generation of x / k / mask over all steps of ``table``."""
+    _require_cuda(x, k_u8, mask_u8, u_jump, u_absorb)
+    B, N, _ = x.shape
+    lib = load()
+    tb = tbias_host.detach().to("cpu", torch.float32).contiguous()
+    need = lib.mmb_generate_absorbing_workspace_bytes(trunk._handle, head._handle, B, N, table.n_steps)
+    ws = torch.empty(max(need, 16), device=x.device, dtype=torch.uint8)
+    ctable = CStepTable.from_table(table)
+    with torch.cuda.device(x.device):
+        check(lib.mmb_generate_absorbing(trunk._handle, head._handle, _ptr(x), _ptr(k_u8), _ptr(mask_u8), ctypes.byref(ctable),
+                                         _ptr(tb), _ptr(u_jump), _ptr(u_absorb), seed, jet_offset, B, N, _ptr(ws), ws.numel(),
+                                         PRECISIONS[precision], _stream()))
+    return x, k_u8, mask_u8

@@ -1,0 +1,499 @@
+// absorb_head_tc.cu — the absorbing-rate transformer head on tcgen05 tensor cores (sm_100a).
+//
+// AbsorbingGenerator.absorbing_head (mp/models/generative/absorbing/absorbing_flows.py:94-131):
+// Linear(H+2 -> 128) on [last local hidden, one_hot(mask)], then n_blocks x (ResnetBlock, AttnBlock)
+// (mp/models/architectures/gsdm.py:38-66,142-168) over the N particle slots of a jet, then
+// Linear(128->128), Linear(128->1).  72 MFLOP per jet-step: ~99 % of the absorbing
+// flow's arithmetic, and real GEMM work (M = 128 particles, N = K = 128 channels).
+//
+// One CTA owns one jet at a time (persistent over jets); thread r owns particle r = TMEM lane r.
+//   * the residual stream X [128 x 128] fp32 lives in TMEM for the whole head; conv2 and proj_out
+//     accumulate straight into it (the residual add is the accumulate flag), their biases ride on
+//     one more K-step against a ones tile;
+//   * every 1x1 conv is 8 tcgen05.mma M128 x N128 x K16 (bf16 operands, canonical no-swizzle
+//     K-major tiles); weights stream L2 -> shared memory with cp.async.bulk (1-D TMA) into a
+//     two-stage ring, one 36 KB slot per matrix, one phase ahead of their use;
+//   * attention per head: S = Q K^T (4 K-steps) into TMEM, row softmax by the thread that owns the
+//     query (its lane holds the whole row — no cross-thread reduction), P as bf16 A operand,
+//     O = P V with V consumed as an MN-major B operand (no transpose), 1/rowsum applied to O;
+//   * GroupNorm(32) statistics: per-thread partial sums over its 128 channels, one shared-memory
+//     reduction across particles, then normalise + swish while packing the next A operand.
+// Numerics: bf16 operands, fp32 accumulate / statistics / softmax.  Checked against the fp32 oracle
+// with the tolerance stated in tests/test_gpu_absorbing.py.
+#include <cuda_bf16.h>
+
+#include <vector>
+
+#include "mmb_device.cuh"
+#include "mmb_internal.h"
+
+namespace mmb {
+namespace {
+
+constexpr int kC = 128;            // transformer width this kernel is built for
+constexpr int kHeads = 2, kDh = 64;
+constexpr int kSlot = 36864;       // bytes per streamed matrix: 32 KB weight tile + 4 KB bias tile
+constexpr int kMaxBlocks = 4;
+
+// ---- PTX wrappers (same conventions as epic_tc.cu) ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float swish_fast(float a) { return a * __fdividef(1.0f, 1.0f + __expf(-a)); }
+
+// [128 rows x 128 k] bf16 tile, K-major canonical: 8-row groups 2048 B apart (SBO), 16-byte k-chunks
+// 128 B apart (LBO).  Thread `row` stores columns [32*chunk4, 32*chunk4+32) of its row (4 x 16 B).
+__device__ __forceinline__ void store_row32(uint8_t* tile, int row, int chunk4, const float (&v)[32]) {
+    uint8_t* p = tile + (row >> 3) * 2048 + (row & 7) * 16 + chunk4 * 4 * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(p + c * 128) = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                                                            pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+}
+
+// fp32 side table (floats), per block then the folded rate vector
+struct HeadTable {
+    // per block: n1g n1b b1 n2g n2b n3g n3b bq bk bv  (10 x 128)
+    static constexpr int kPerBlock = 10 * kC;
+    __host__ __device__ static int rate_w(int nblk) { return nblk * kPerBlock; }       // [128] post^T pre
+    __host__ __device__ static int rate_c(int nblk) { return nblk * kPerBlock + kC; }  // scalar
+    __host__ __device__ static int floats(int nblk) { return nblk * kPerBlock + kC + 4; }
+};
+
+struct HeadParams {
+    const uint8_t* image;    // n_seq slots of kSlot bytes (bf16 operand tiles)
+    const float* table;      // HeadTable
+    int n_blocks, H;
+    const float* hidden;     // [B,N,H]
+    const uint8_t* mask;     // [B,N]
+    const float* tbias;      // [B or 1][n_blocks][128]
+    int tbias_stride;
+    int B, N;
+    float* logit_out;        // [B,N]
+};
+
+constexpr int kSmemW = 2 * kSlot;                         // weight ring
+constexpr int kOffA = kSmemW, kOffQ = kOffA + 32768, kOffK = kOffQ + 32768, kOffV = kOffK + 32768;
+constexpr int kOffOnes = kOffV + 32768, kOffTab = kOffOnes + 4096;
+
+__global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t s_tmem_slot;
+    __shared__ __align__(8) uint64_t s_bars[3];  // full[0], full[1], mma
+    __shared__ float s_stat[64];                 // mean[32], rstd[32]
+    const int tid = threadIdx.x, r = tid, warp = tid >> 5;
+    const int nblk = p.n_blocks, n_seq = 1 + 6 * nblk;
+    uint8_t *sA = smem + kOffA, *sQ = smem + kOffQ, *sK = smem + kOffK, *sV = smem + kOffV, *sOnes = smem + kOffOnes;
+    float* sTab = reinterpret_cast<float*>(smem + kOffTab);
+    float* sRed = reinterpret_cast<float*>(sK);   // [128][65] floats, aliases K/V tiles (dead during GroupNorm)
+    uint8_t* sA0 = sV;                            // [128 x 32] proj_in operand, aliases V (dead at jet start)
+
+    for (int i = tid; i < HeadTable::floats(nblk); i += 128) sTab[i] = __ldg(p.table + i);
+    for (int i = tid; i < 256; i += 128) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    const uint32_t bar_full0 = smem_u32(&s_bars[0]), bar_full1 = smem_u32(&s_bars[1]), bar_mma = smem_u32(&s_bars[2]);
+    if (tid == 0) { mbar_init(bar_full0, 1); mbar_init(bar_full1, 1); mbar_init(bar_mma, 1); }
+    if (warp == 0) tmem_alloc(smem_u32(&s_tmem_slot), 512);
+    fence_barrier_init();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_slot;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t dX = tmem, dACC = tmem + 128, dS0 = tmem + 256, dS1 = tmem + 384;
+
+    const int my_jets = p.B > (int)blockIdx.x ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t total_mats = (uint32_t)my_jets * n_seq;
+    const uint32_t wbase = smem_u32(smem);
+    auto issue_load = [&](uint32_t i) {  // thread 0 only
+        const uint32_t bar = (i & 1) ? bar_full1 : bar_full0;
+        mbar_expect_tx(bar, kSlot);
+        bulk_g2s(wbase + (i & 1) * kSlot, p.image + (size_t)(i % n_seq) * kSlot, kSlot, bar);
+    };
+    if (tid == 0) {
+        if (total_mats > 0) issue_load(0);
+        if (total_mats > 1) issue_load(1);
+    }
+    uint32_t wseq = 0, mma_phase = 0;
+    constexpr uint32_t idesc128 = instr_desc(128, 128, false), idesc64mn = instr_desc(128, 64, true);
+    const uint64_t ones_desc = smem_desc(smem_u32(sOnes), 128, 256);
+    const uint32_t aA = smem_u32(sA), aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+
+    // D (+)= A[128 x 16*nk] * W^T with the streamed matrix `wseq`; optional bias K-step; commit.  Thread 0.
+    auto gemm_w = [&](uint32_t d, uint32_t a_addr, uint32_t a_sbo, int nk, bool accumulate, bool bias) {
+        const uint32_t wb = wbase + (wseq & 1) * kSlot;
+        mbar_wait((wseq & 1) ? bar_full1 : bar_full0, (wseq >> 1) & 1);
+        tc_fence_after();
+        for (int j = 0; j < nk; ++j)
+            umma(d, smem_desc(a_addr + j * 256, 128, a_sbo), smem_desc(wb + j * 256, 128, 2048), idesc128, (accumulate || j > 0) ? 1u : 0u);
+        if (bias) umma(d, ones_desc, smem_desc(wb + 32768, 128, 256), idesc128, 1u);
+        umma_commit(bar_mma);
+    };
+    // all threads: wait for the committed MMAs; the ring slot of matrix `wseq` is free again -> prefetch wseq+2
+    auto mma_done = [&](bool used_weights) {
+        mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
+        tc_fence_after();
+        if (used_weights) {
+            if (tid == 0 && wseq + 2 < total_mats) issue_load(wseq + 2);
+            ++wseq;
+        }
+    };
+
+    // GroupNorm(32 groups of 4 channels) over the N live rows of a TMEM tile (+ per-channel bias) -> bf16 A tile
+    auto group_norm_to_A = [&](uint32_t d_src, const float* bias /*nullable, smem*/, const float* bias2 /*nullable, global*/,
+                               const float* gamma, const float* beta, bool swish, bool valid) {
+        float v[32];
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+            tmem_ld32(d_src + lane_off + c4 * 32, v);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                float s = 0.0f, q = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float a = v[4 * g + j];
+                    if (bias) a += bias[c4 * 32 + 4 * g + j];
+                    if (bias2) a += __ldg(bias2 + c4 * 32 + 4 * g + j);
+                    s += a; q = fmaf(a, a, q);
+                }
+                sRed[r * 65 + c4 * 8 + g] = valid ? s : 0.0f;
+                sRed[r * 65 + 32 + c4 * 8 + g] = valid ? q : 0.0f;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            float s = 0.0f, q = 0.0f;
+            for (int i = 0; i < 128; ++i) { s += sRed[i * 65 + tid]; q += sRed[i * 65 + 32 + tid]; }
+            const float inv = 1.0f / (4.0f * (float)p.N);
+            const float mean = s * inv;
+            const float var = fmaxf(q * inv - mean * mean, 0.0f);
+            s_stat[tid] = mean;
+            s_stat[32 + tid] = rsqrtf(var + 1e-6f);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+            tmem_ld32(d_src + lane_off + c4 * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = c4 * 32 + j;
+                float a = v[j];
+                if (bias) a += bias[c];
+                if (bias2) a += __ldg(bias2 + c);
+                a = (a - s_stat[c >> 2]) * s_stat[32 + (c >> 2)] * gamma[c] + beta[c];
+                v[j] = swish ? swish_fast(a) : a;
+            }
+            store_row32(sA, r, c4, v);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+    };
+    // ACC (+ bias) -> bf16 tile (Q, K or V)
+    auto acc_to_tile = [&](uint8_t* tile, const float* bias) {
+        float v[32];
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; ++c4) {
+            tmem_ld32(dACC + lane_off + c4 * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += bias[c4 * 32 + j];
+            store_row32(tile, r, c4, v);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+    };
+
+    for (int jet = blockIdx.x; jet < p.B; jet += gridDim.x) {
+        const bool valid = r < p.N;
+        const size_t pidx = (size_t)jet * p.N + r;
+        // ---- proj_in on [hidden, one_hot(mask)]  (absorbing_flows.py:113-118)
+        {
+            float row[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) row[i] = 0.0f;
+            if (valid) {
+                for (int i = 0; i < p.H; ++i) row[i] = p.hidden[pidx * p.H + i];
+                const int m = p.mask[pidx] ? 1 : 0;
+                row[p.H] = m ? 0.0f : 1.0f;
+                row[p.H + 1] = m ? 1.0f : 0.0f;
+            }
+            uint8_t* q = sA0 + (r >> 3) * 512 + (r & 7) * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(q + c * 128) = make_uint4(pack_bf16(row[8 * c], row[8 * c + 1]), pack_bf16(row[8 * c + 2], row[8 * c + 3]),
+                                                                    pack_bf16(row[8 * c + 4], row[8 * c + 5]), pack_bf16(row[8 * c + 6], row[8 * c + 7]));
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) gemm_w(dX, smem_u32(sA0), 512, 2, false, true);
+        mma_done(true);
+
+        const float* tb = p.tbias + (size_t)jet * p.tbias_stride;
+        for (int blk = 0; blk < nblk; ++blk) {
+            const float* T = sTab + blk * HeadTable::kPerBlock;
+            // ---- ResnetBlock (gsdm.py:54-66)
+            group_norm_to_A(dX, nullptr, nullptr, T + 0 * kC, T + 1 * kC, true, valid);
+            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // conv1
+            mma_done(true);
+            group_norm_to_A(dACC, T + 2 * kC, tb + blk * kC, T + 3 * kC, T + 4 * kC, true, valid);
+            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true);               // X += conv2(.) + b2
+            mma_done(true);
+            // ---- AttnBlock (gsdm.py:142-168)
+            group_norm_to_A(dX, nullptr, nullptr, T + 5 * kC, T + 6 * kC, false, valid);
+            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // q
+            mma_done(true);
+            acc_to_tile(sQ, T + 7 * kC);
+            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // k
+            mma_done(true);
+            acc_to_tile(sK, T + 8 * kC);
+            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // v
+            mma_done(true);
+            acc_to_tile(sV, T + 9 * kC);
+            if (tid == 0) {                                                  // S_h = Q_h K_h^T, K = 64
+                tc_fence_after();
+                for (int h = 0; h < kHeads; ++h)
+                    for (int j = 0; j < 4; ++j)
+                        umma(h ? dS1 : dS0, smem_desc(aQ + h * 1024 + j * 256, 128, 2048), smem_desc(aK + h * 1024 + j * 256, 128, 2048),
+                             idesc128, j > 0);
+                umma_commit(bar_mma);
+            }
+            mma_done(false);
+            // softmax over the N keys of this thread's query row; P (unnormalised) -> A tile (head 0) / Q tile (head 1)
+            float rinv[kHeads];
+#pragma unroll 1
+            for (int h = 0; h < kHeads; ++h) {
+                const uint32_t dS = (h ? dS1 : dS0) + lane_off;
+                float v[32], mx = -3.0e38f;
+#pragma unroll 1
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    tmem_ld32(dS + c4 * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = (c4 * 32 + j < p.N) ? fmaxf(mx, v[j]) : mx;
+                }
+                float sum = 0.0f;
+                const float sc = 0.125f * 1.4426950408889634f;  // dh^-1/2 * log2(e)
+#pragma unroll 1
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    tmem_ld32(dS + c4 * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float e = (c4 * 32 + j < p.N) ? exp2f((v[j] - mx) * sc) : 0.0f;
+                        // the sum runs over the bf16-rounded weights the PV GEMM will actually use
+                        v[j] = __bfloat162float(__float2bfloat16_rn(e));
+                        sum += v[j];
+                    }
+                    store_row32(h ? sQ : sA, r, c4, v);
+                }
+                rinv[h] = 1.0f / sum;
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {                                                  // O_h = P_h V_h, K = 128 keys, N = 64
+                tc_fence_after();
+                for (int h = 0; h < kHeads; ++h)
+                    for (int j = 0; j < 8; ++j)
+                        umma(dACC + h * 64, smem_desc((h ? aQ : aA) + j * 256, 128, 2048),
+                             smem_desc(aV + h * 1024 + j * 4096, 2048, 128), idesc64mn, j > 0);
+                umma_commit(bar_mma);
+            }
+            mma_done(false);
+            {
+                float v[32];
+#pragma unroll 1
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    tmem_ld32(dACC + lane_off + c4 * 32, v);
+                    const float ri = rinv[c4 >> 1];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= ri;
+                    store_row32(sA, r, c4, v);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true);               // X += proj_out(.) + b
+            mma_done(true);
+        }
+        // ---- rate = post_rate_proj(pre_rate_proj(X)) folded into one 128-vector (absorbing_flows.py:127-131)
+        {
+            const float* w = sTab + HeadTable::rate_w(nblk);
+            float acc = sTab[HeadTable::rate_c(nblk)], v[32];
+#pragma unroll 1
+            for (int c4 = 0; c4 < 4; ++c4) {
+                tmem_ld32(dX + lane_off + c4 * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc = fmaf(w[c4 * 32 + j], v[j], acc);
+            }
+            if (valid) p.logit_out[pidx] = acc;
+        }
+        tc_fence_before();
+        __syncthreads();  // X and the operand tiles are rewritten by the next jet
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// element (row o, k) of a K-major tile with 8-row groups `sbo` bytes apart -> bf16 index
+inline size_t tile_index(int o, int k, int sbo) { return ((size_t)(o / 8) * sbo + (size_t)(k / 8) * 128 + (o % 8) * 16 + (k % 8) * 2) / 2; }
+
+}  // namespace
+
+struct AbsorbHead {
+    int H, C, n_heads, n_blocks, device, sm_count;
+    void* image;   // n_seq * kSlot bytes
+    float* table;  // HeadTable
+};
+
+int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, size_t n_floats, int device, AbsorbHead** out) {
+    if (C != kC || n_heads != kHeads || n_blocks < 1 || n_blocks > kMaxBlocks || H < 1 || H > 30)
+        return fail(MMB_EUNSUPPORTED, "absorbing head is built for transformer_dim=128, n_heads=2, 1..4 blocks, hidden<=30");
+    const size_t lin = (size_t)C * C + C;
+    const size_t expect = (size_t)C * (H + 2) + C + (size_t)n_blocks * (6 * C + 6 * lin) + lin + C + 1;
+    if (n_floats != expect) return fail(MMB_EINVAL, "absorbing head blob has %zu floats, layout wants %zu", n_floats, expect);
+    const int n_seq = 1 + 6 * n_blocks;
+    std::vector<__nv_bfloat16> img((size_t)n_seq * kSlot / 2, __float2bfloat16(0.0f));
+    std::vector<float> tab((size_t)HeadTable::floats(n_blocks), 0.0f);
+    auto put_matrix = [&](int slot, const float* Wm, int in_dim) {
+        for (int o = 0; o < C; ++o)
+            for (int k = 0; k < in_dim; ++k) img[(size_t)slot * kSlot / 2 + tile_index(o, k, 2048)] = __float2bfloat16(Wm[(size_t)o * in_dim + k]);
+    };
+    auto put_bias = [&](int slot, const float* b) {
+        for (int o = 0; o < C; ++o) {
+            const __nv_bfloat16 hi = __float2bfloat16(b[o]);
+            img[(size_t)slot * kSlot / 2 + 32768 / 2 + tile_index(o, 0, 256)] = hi;
+            img[(size_t)slot * kSlot / 2 + 32768 / 2 + tile_index(o, 1, 256)] = __float2bfloat16(b[o] - __bfloat162float(hi));
+        }
+    };
+    const float* p = W;
+    put_matrix(0, p, H + 2);
+    put_bias(0, p + (size_t)C * (H + 2));
+    p += (size_t)C * (H + 2) + C;
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        float* T = tab.data() + (size_t)blk * HeadTable::kPerBlock;
+        const float *n1g = p, *n1b = p + C, *c1 = p + 2 * C, *n2g = c1 + lin, *n2b = n2g + C, *c2 = n2b + C, *ng = c2 + lin,
+                    *nb = ng + C, *wq = nb + C, *wk = wq + lin, *wv = wk + lin, *wo = wv + lin;
+        p = wo + lin;
+        const int s0 = 1 + 6 * blk;
+        put_matrix(s0 + 0, c1, C);
+        put_matrix(s0 + 1, c2, C); put_bias(s0 + 1, c2 + (size_t)C * C);
+        put_matrix(s0 + 2, wq, C); put_matrix(s0 + 3, wk, C); put_matrix(s0 + 4, wv, C);
+        put_matrix(s0 + 5, wo, C); put_bias(s0 + 5, wo + (size_t)C * C);
+        for (int c = 0; c < C; ++c) {
+            T[0 * kC + c] = n1g[c]; T[1 * kC + c] = n1b[c]; T[2 * kC + c] = c1[(size_t)C * C + c];
+            T[3 * kC + c] = n2g[c]; T[4 * kC + c] = n2b[c]; T[5 * kC + c] = ng[c]; T[6 * kC + c] = nb[c];
+            T[7 * kC + c] = wq[(size_t)C * C + c]; T[8 * kC + c] = wk[(size_t)C * C + c]; T[9 * kC + c] = wv[(size_t)C * C + c];
+        }
+    }
+    {   // fold Linear(C->C) then Linear(C->1): w = post^T pre, c = post . pre_b + post_b
+        const float *pre = p, *pre_b = p + (size_t)C * C, *post = p + lin, *post_b = post + C;
+        for (int c = 0; c < C; ++c) {
+            double acc = 0;
+            for (int o = 0; o < C; ++o) acc += (double)post[o] * pre[(size_t)o * C + c];
+            tab[HeadTable::rate_w(n_blocks) + c] = (float)acc;
+        }
+        double acc = post_b[0];
+        for (int o = 0; o < C; ++o) acc += (double)post[o] * pre_b[o];
+        tab[HeadTable::rate_c(n_blocks)] = (float)acc;
+    }
+    int prev = 0;
+    if (int rc = cuda_ok(cudaGetDevice(&prev), "cudaGetDevice")) return rc;
+    if (int rc = cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return rc;
+    AbsorbHead* h = new AbsorbHead{H, C, n_heads, n_blocks, device, 148, nullptr, nullptr};
+    int rc = cuda_ok(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), "sm count");
+    if (!rc) rc = cuda_ok(cudaMalloc(&h->image, img.size() * 2), "cudaMalloc head image");
+    if (!rc) rc = cuda_ok(cudaMalloc(&h->table, tab.size() * 4), "cudaMalloc head table");
+    if (!rc) rc = cuda_ok(cudaMemcpy(h->image, img.data(), img.size() * 2, cudaMemcpyHostToDevice), "head image upload");
+    if (!rc) rc = cuda_ok(cudaMemcpy(h->table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice), "head table upload");
+    cudaSetDevice(prev);
+    if (rc) { absorb_head_destroy(h); return rc; }
+    *out = h;
+    return MMB_OK;
+}
+
+void absorb_head_destroy(AbsorbHead* h) {
+    if (!h) return;
+    if (h->image) cudaFree(h->image);
+    if (h->table) cudaFree(h->table);
+    delete h;
+}
+
+int absorb_head_hidden(const AbsorbHead* h) { return h->H; }
+int absorb_head_blocks(const AbsorbHead* h) { return h->n_blocks; }
+
+int launch_absorb_head(const AbsorbHead* h, const float* hidden, const uint8_t* mask, const float* tbias, int tbias_stride,
+                       int B, int N, float* logit_out, cudaStream_t stream) {
+    if (N < 1 || N > 128) return fail(MMB_EUNSUPPORTED, "absorbing head handles 1..128 particle slots per jet (got %d)", N);
+    if (B == 0) return MMB_OK;
+    HeadParams p{static_cast<const uint8_t*>(h->image), h->table, h->n_blocks, h->H, hidden, mask, tbias, tbias_stride, B, N, logit_out};
+    const size_t bytes = kOffTab + (size_t)HeadTable::floats(h->n_blocks) * 4 + 1024;
+    if (int rc = cuda_ok(cudaFuncSetAttribute(absorb_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "head smem attribute"))
+        return rc;
+    const int grid = B < h->sm_count ? B : h->sm_count;
+    absorb_head_tc_kernel<<<grid, 128, bytes, stream>>>(p);
+    return cuda_ok(cudaGetLastError(), "absorb_head launch");
+}
+
+}  // namespace mmb

@@ -153,7 +153,82 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
 
 int mmb_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, void* stream) {
     if (!u || n_steps < 0 || B < 0 || N < 0) return fail(MMB_EINVAL, "mmb_philox_uniforms: bad argument");
-    return launch_philox_uniforms(u, seed, jet_offset, n_steps, B, N, static_cast<cudaStream_t>(stream));
+    return launch_philox_uniforms(u, seed, jet_offset, 0, 0, n_steps, B, N, static_cast<cudaStream_t>(stream));
+}
+
+int mmb_absorb_head_create(int hidden, int transformer_dim, int n_heads, int n_blocks, const float* packed, size_t n_floats,
+                           int device, MmbAbsorbHead** out) {
+    if (!packed || !out) return fail(MMB_EINVAL, "mmb_absorb_head_create: null argument");
+    AbsorbHead* h = nullptr;
+    if (int rc = absorb_head_create(hidden, transformer_dim, n_heads, n_blocks, packed, n_floats, device, &h)) return rc;
+    *out = reinterpret_cast<MmbAbsorbHead*>(h);
+    return MMB_OK;
+}
+
+void mmb_absorb_head_destroy(MmbAbsorbHead* h) { absorb_head_destroy(reinterpret_cast<AbsorbHead*>(h)); }
+
+int mmb_absorb_head_forward(const MmbAbsorbHead* head, const float* hidden, const uint8_t* mask, const float* tbias,
+                            int tbias_stride, int B, int N, float* logit_out, void* stream) {
+    if (!head || !hidden || !mask || !tbias || !logit_out) return fail(MMB_EINVAL, "mmb_absorb_head_forward: null argument");
+    if (B < 0 || N < 0) return fail(MMB_EINVAL, "mmb_absorb_head_forward: negative size");
+    return launch_absorb_head(reinterpret_cast<const AbsorbHead*>(head), hidden, mask, tbias, tbias_stride, B, N, logit_out,
+                              static_cast<cudaStream_t>(stream));
+}
+
+// workspace of mmb_generate_absorbing (floats): step table image | tbias [steps][blocks][128] | v | logits | hidden | a | uj | ua
+static size_t absorbing_ws_floats(const EpicModel* m, const AbsorbHead* h, int B, int N, int n_steps) {
+    const size_t P = (size_t)B * N;
+    return table_floats(n_steps, m->dims.dim_time_emb) + (size_t)n_steps * absorb_head_blocks(h) * 128 +
+           P * (m->dims.dim_continuous + m->dims.vocab_size + m->dims.dim_hidden_local + 3) + 64;
+}
+
+size_t mmb_generate_absorbing_workspace_bytes(const MmbEpicModel* model, const MmbAbsorbHead* head, int B, int N, int n_steps) {
+    if (!model || !head || B < 0 || N < 0 || n_steps < 0) return 0;
+    return absorbing_ws_floats(reinterpret_cast<const EpicModel*>(model), reinterpret_cast<const AbsorbHead*>(head), B, N, n_steps) * sizeof(float);
+}
+
+int mmb_generate_absorbing(const MmbEpicModel* model, const MmbAbsorbHead* head, float* x, uint8_t* k, uint8_t* mask,
+                           const MmbStepTable* st, const float* tbias, const float* u_jump, const float* u_absorb,
+                           uint64_t seed, uint64_t jet_offset, int B, int N, void* workspace, size_t workspace_bytes,
+                           int precision, void* stream) {
+    const EpicModel* m = reinterpret_cast<const EpicModel*>(model);
+    const AbsorbHead* h = reinterpret_cast<const AbsorbHead*>(head);
+    if (!m || !h || !x || !k || !mask || !st || !tbias || !workspace) return fail(MMB_EINVAL, "mmb_generate_absorbing: null argument");
+    if (!st->temb || !st->bc || !st->cc || !st->sp) return fail(MMB_EINVAL, "mmb_generate_absorbing: step table needs temb, bc, cc, sp");
+    if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate_absorbing: negative size");
+    if (absorb_head_hidden(h) != m->dims.dim_hidden_local) return fail(MMB_EINVAL, "head expects hidden %d, trunk has %d", absorb_head_hidden(h), m->dims.dim_hidden_local);
+    const int T = m->dims.dim_time_emb, n = st->n_steps, Dc = m->dims.dim_continuous, S = m->dims.vocab_size, H = m->dims.dim_hidden_local;
+    const int nblk = absorb_head_blocks(h);
+    if (workspace_bytes < absorbing_ws_floats(m, h, B, N, n) * sizeof(float)) return fail(MMB_ENOMEM, "mmb_generate_absorbing: workspace too small");
+    if (B == 0 || N == 0 || n == 0) return MMB_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t P = (size_t)B * N, tf = table_floats(n, T), nb = (size_t)n * nblk * 128;
+    std::vector<float> img(tf + nb);
+    memcpy(img.data() + (size_t)n * 4, st->temb, (size_t)n * T * sizeof(float));
+    memcpy(img.data() + tf, tbias, nb * sizeof(float));
+    if (int rc = cuda_ok(cudaMemcpyAsync(workspace, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, s), "table upload")) return rc;
+    float* ws = static_cast<float*>(workspace);
+    const float* temb_dev = ws + (size_t)n * 4;
+    const float* tb_dev = ws + tf;
+    float* v = ws + tf + nb;
+    float* logits = v + P * Dc;
+    float* hidden = logits + P * S;
+    float* alog = hidden + P * H;
+    float* uj = alog + P;
+    float* ua = uj + P;
+    for (int i = 0; i < n; ++i) {
+        // heads from the OLD mask (absorbing_flows.py:270), then birth -> Euler -> jump with the new one (:271-273)
+        int rc = mmb_epic_forward(model, x, k, mask, temb_dev + (size_t)i * T, 0, B, N, v, logits, hidden, precision, stream);
+        if (!rc) rc = launch_absorb_head(h, hidden, mask, tb_dev + (size_t)i * nblk * 128, 0, B, N, alog, s);
+        const float* pj = u_jump ? u_jump + (size_t)i * P : uj;
+        const float* pa = u_absorb ? u_absorb + (size_t)i * P : ua;
+        if (!rc && !u_jump) rc = launch_philox_uniforms(uj, seed, jet_offset, 0, i, 1, B, N, s);
+        if (!rc && !u_absorb) rc = launch_philox_uniforms(ua, seed, jet_offset, 1, i, 1, B, N, s);
+        if (!rc) rc = launch_bridge_update(x, k, mask, v, logits, alog, pj, pa, StepScalars{st->dt, st->bc[i], st->cc[i], st->sp[i]},
+                                           P, Dc, S, MMB_FLAG_ABSORBING, s);
+        if (rc) return rc;
+    }
+    return MMB_OK;
 }
 
 int mmb_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,

@@ -195,21 +195,22 @@ int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, co
 }
 
 // ---- uniforms exactly as the generation kernels draw them (tests) ------------------------------
-__global__ void philox_uniforms_kernel(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N) {
+__global__ void philox_uniforms_kernel(float* u, uint64_t seed, uint64_t jet_offset, int stream_id, int step0, int n_steps, int B, int N) {
     const size_t total = (size_t)n_steps * B * N;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int n = (int)(i % N);
         const int b = (int)((i / N) % B);
         const int s = (int)(i / ((size_t)N * B));
-        u[i] = philox_uniform(seed, jet_offset + (uint64_t)b, 0, s, n);
+        u[i] = philox_uniform(seed, jet_offset + (uint64_t)b, stream_id, step0 + s, n);
     }
 }
 
-int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, cudaStream_t stream) {
+int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int stream_id, int step0, int n_steps, int B, int N,
+                           cudaStream_t stream) {
     const size_t total = (size_t)n_steps * B * N;
     if (total == 0) return MMB_OK;
     const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    philox_uniforms_kernel<<<grid, 256, 0, stream>>>(u, seed, jet_offset, n_steps, B, N);
+    philox_uniforms_kernel<<<grid, 256, 0, stream>>>(u, seed, jet_offset, stream_id, step0, n_steps, B, N);
     return cuda_ok(cudaGetLastError(), "philox_uniforms launch");
 }
 

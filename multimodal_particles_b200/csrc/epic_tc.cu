@@ -657,16 +657,63 @@ int dispatch(const MmbEpicDims& d, const TcParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+// the fused discrete head handles Sh == S (MultiModalEPiC.fc_layer); any other width (AbsorbingGenerator's 56) runs
+// the tensor-core trunk headless and a small per-particle MLP kernel on its logit slice
+static bool head_fused(const MmbEpicDims& d) { return d.disc_head_hidden == 0 || d.disc_head_hidden == d.vocab_size; }
+static MmbEpicDims tc_dims(const MmbEpicDims& d) {
+    MmbEpicDims t = d;
+    if (!head_fused(d)) t.disc_head_hidden = 0;
+    return t;
+}
+
+// logits <- W2 selu(W1 z + b1) + b2 in place, z = logits (the raw output-layer slice)   (absorbing_flows.py:41-54,133-138)
+template <int S>
+__global__ void __launch_bounds__(256) discrete_head_mlp_kernel(const float* __restrict__ W, MmbEpicLayout Lo, int Sh,
+                                                                float* __restrict__ logits, size_t P) {
+    extern __shared__ float sw[];  // W1 [Sh][S], b1 [Sh], W2^T [Sh][S], b2 [S]
+    for (int i = threadIdx.x; i < Sh * S; i += blockDim.x) {
+        sw[i] = __ldg(W + Lo.head0_w + i);
+        const int s = i / Sh, j = i % Sh;                       // head2_w is [S][Sh]
+        sw[Sh * S + Sh + j * S + s] = __ldg(W + Lo.head2_w + i);
+    }
+    for (int i = threadIdx.x; i < Sh; i += blockDim.x) sw[Sh * S + i] = __ldg(W + Lo.head0_b + i);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) sw[2 * Sh * S + Sh + i] = __ldg(W + Lo.head2_b + i);
+    __syncthreads();
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float z[S], out[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { z[s] = logits[p * S + s]; out[s] = sw[2 * Sh * S + Sh + s]; }
+    for (int j = 0; j < Sh; ++j) {
+        float a = sw[Sh * S + j];
+#pragma unroll
+        for (int s = 0; s < S; ++s) a = fmaf(sw[j * S + s], z[s], a);
+        a = a > 0.0f ? 1.0507009873554805f * a : 1.7580993408473766f * (__expf(a) - 1.0f);
+#pragma unroll
+        for (int s = 0; s < S; ++s) out[s] = fmaf(sw[Sh * S + Sh + j * S + s], a, out[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) logits[p * S + s] = out[s];
+}
+
+static int launch_discrete_head_mlp(const EpicModel* m, float* logits, size_t P, cudaStream_t stream) {
+    const int S = m->dims.vocab_size, Sh = m->dims.disc_head_hidden;
+    const size_t bytes = (size_t)(2 * Sh * S + Sh + S) * sizeof(float);
+    const unsigned grid = (unsigned)((P + 255) / 256);
+    if (S == 8) discrete_head_mlp_kernel<8><<<grid, 256, bytes, stream>>>(m->w, m->layout, Sh, logits, P);
+    else discrete_head_mlp_kernel<4><<<grid, 256, bytes, stream>>>(m->w, m->layout, Sh, logits, P);
+    return cuda_ok(cudaGetLastError(), "discrete_head_mlp launch");
+}
+
 bool tc_supported(const MmbEpicDims* d, int N) {
     return d->dim_hidden_local == kH && d->dim_hidden_glob <= kGP && d->dim_time_emb <= kMaxT && d->dim_time_emb % 2 == 0 &&
            d->num_blocks >= 1 && d->num_blocks <= kMaxL && d->dim_continuous == 3 &&
-           (d->vocab_size == 8 || d->vocab_size == 4) && (d->disc_head_hidden == 0 || d->disc_head_hidden == d->vocab_size) &&
-           N <= kRows && N >= 1;
+           (d->vocab_size == 8 || d->vocab_size == 4) && d->disc_head_hidden <= 256 && N <= kRows && N >= 1;
 }
 
 // Build the device image from the packed fp32 blob (host): bf16 UMMA operands + fp32 side tables.
 int tc_build_image(EpicModel* m, const float* W) {
-    const MmbEpicDims& d = m->dims;
+    const MmbEpicDims d = tc_dims(m->dims);
     const MmbEpicLayout& Lo = m->layout;
     const TcLayout lay = make_layout(d);
     const int Dc = d.dim_continuous, S = d.vocab_size, T = d.dim_time_emb, C = d.dim_cont_emb, D = d.dim_disc_emb,
@@ -773,17 +820,19 @@ int launch_epic_forward_tc(const EpicModel* m, const float* x, const uint8_t* k,
     if (B == 0) return MMB_OK;
     TcParams p{};
     p.image = static_cast<const uint8_t*>(m->tc_image);
-    p.lay = make_layout(m->dims);
+    p.lay = make_layout(tc_dims(m->dims));
     p.x = const_cast<float*>(x); p.k = const_cast<uint8_t*>(k); p.mask = mask;
     p.temb = temb; p.temb_stride = temb_stride; p.n_steps = 1;
     p.B = B; p.N = N; p.v_out = v_out; p.logits_out = logits_out; p.hidden_out = hidden_out;
-    return dispatch<false>(m->dims, p, stream);
+    if (int rc = dispatch<false>(tc_dims(m->dims), p, stream)) return rc;
+    return head_fused(m->dims) ? MMB_OK : launch_discrete_head_mlp(m, logits_out, (size_t)B * N, stream);
 }
 
 int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table,
                        int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                        int B, int N, cudaStream_t stream) {
     if (B == 0 || n_steps == 0) return MMB_OK;
+    if (!head_fused(m->dims)) return fail(MMB_EUNSUPPORTED, "fused tcgen05 generation needs the discrete head width to be 0 or S");
     TcParams p{};
     p.image = static_cast<const uint8_t*>(m->tc_image);
     p.lay = make_layout(m->dims);

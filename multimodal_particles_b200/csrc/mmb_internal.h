@@ -31,7 +31,17 @@ struct EpicModel {
 int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, const float* logits,
                          const float* absorb, const float* uj, const float* ua, StepScalars sc,
                          size_t P, int Dc, int S, int flags, cudaStream_t stream);
-int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, cudaStream_t stream);
+int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int stream_id, int step0, int n_steps, int B, int N,
+                           cudaStream_t stream);
+
+// absorb_head_tc.cu — transformer absorbing-rate head on tcgen05
+struct AbsorbHead;
+int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, size_t n_floats, int device, AbsorbHead** out);
+void absorb_head_destroy(AbsorbHead* h);
+int absorb_head_hidden(const AbsorbHead* h);
+int absorb_head_blocks(const AbsorbHead* h);
+int launch_absorb_head(const AbsorbHead* h, const float* hidden, const uint8_t* mask, const float* tbias, int tbias_stride,
+                       int B, int N, float* logit_out, cudaStream_t stream);
 
 // histograms.cu
 int launch_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,
