@@ -6,7 +6,9 @@
 // Linear(128->128), Linear(128->1).  72 MFLOP per jet-step: ~99 % of the absorbing
 // flow's arithmetic, and real GEMM work (M = 128 particles, N = K = 128 channels).
 //
-// One CTA owns one jet at a time (persistent over jets); thread r owns particle r = TMEM lane r.
+// One CTA (256 threads) owns one jet at a time (persistent over jets).  Particle r = TMEM lane r is served by two
+// threads: warp w < 4 handles channels [0,64) of rows 32w..32w+31, warp w+4 channels [64,128) of the same rows —
+// which is also "one thread per (query, attention head)", so softmax rows and their 1/rowsum never leave a thread.
 //   * the residual stream X [128 x 128] fp32 lives in TMEM for the whole head; conv2 and proj_out
 //     accumulate straight into it (the residual add is the accumulate flag), their biases ride on
 //     one more K-step against a ones tile;
@@ -135,20 +137,24 @@ constexpr int kSmemW = 2 * kSlot;                         // weight ring
 constexpr int kOffA = kSmemW, kOffQ = kOffA + 32768, kOffK = kOffQ + 32768, kOffV = kOffK + 32768;
 constexpr int kOffOnes = kOffV + 32768, kOffTab = kOffOnes + 4096;
 
-__global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams p) {
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t s_tmem_slot;
     __shared__ __align__(8) uint64_t s_bars[3];  // full[0], full[1], mma
     __shared__ float s_stat[64];                 // mean[32], rstd[32]
-    const int tid = threadIdx.x, r = tid, warp = tid >> 5;
+    __shared__ float s_part[4][64];              // GroupNorm partial column sums (4 row quarters)
+    __shared__ float s_dot[128];                 // rate-vector partial of the upper-half threads
+    const int tid = threadIdx.x, r = tid & 127, half = tid >> 7, warp = tid >> 5;
     const int nblk = p.n_blocks, n_seq = 1 + 6 * nblk;
     uint8_t *sA = smem + kOffA, *sQ = smem + kOffQ, *sK = smem + kOffK, *sV = smem + kOffV, *sOnes = smem + kOffOnes;
     float* sTab = reinterpret_cast<float*>(smem + kOffTab);
     float* sRed = reinterpret_cast<float*>(sK);   // [128][65] floats, aliases K/V tiles (dead during GroupNorm)
     uint8_t* sA0 = sV;                            // [128 x 32] proj_in operand, aliases V (dead at jet start)
 
-    for (int i = tid; i < HeadTable::floats(nblk); i += 128) sTab[i] = __ldg(p.table + i);
-    for (int i = tid; i < 256; i += 128) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    for (int i = tid; i < HeadTable::floats(nblk); i += kThreads) sTab[i] = __ldg(p.table + i);
+    for (int i = tid; i < 256; i += kThreads) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     const uint32_t bar_full0 = smem_u32(&s_bars[0]), bar_full1 = smem_u32(&s_bars[1]), bar_mma = smem_u32(&s_bars[2]);
     if (tid == 0) { mbar_init(bar_full0, 1); mbar_init(bar_full1, 1); mbar_init(bar_mma, 1); }
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem_slot), 512);
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_slot;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = ((uint32_t)((warp & 3) * 32) << 16) + half * 64;  // this thread's lane and its 64-column half
     const uint32_t dX = tmem, dACC = tmem + 128, dS0 = tmem + 256, dS1 = tmem + 384;
 
     const int my_jets = p.B > (int)blockIdx.x ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -203,26 +209,35 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
                                const float* gamma, const float* beta, bool swish, bool valid) {
         float v[32];
 #pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-            tmem_ld32(d_src + lane_off + c4 * 32, v);
+        for (int c2 = 0; c2 < 2; ++c2) {
+            const int c0 = half * 64 + c2 * 32;
+            tmem_ld32(d_src + lane_off + c2 * 32, v);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
                 float s = 0.0f, q = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float a = v[4 * g + j];
-                    if (bias) a += bias[c4 * 32 + 4 * g + j];
-                    if (bias2) a += __ldg(bias2 + c4 * 32 + 4 * g + j);
+                    if (bias) a += bias[c0 + 4 * g + j];
+                    if (bias2) a += __ldg(bias2 + c0 + 4 * g + j);
                     s += a; q = fmaf(a, a, q);
                 }
-                sRed[r * 65 + c4 * 8 + g] = valid ? s : 0.0f;
-                sRed[r * 65 + 32 + c4 * 8 + g] = valid ? q : 0.0f;
+                sRed[r * 65 + (c0 >> 2) + g] = valid ? s : 0.0f;
+                sRed[r * 65 + 32 + (c0 >> 2) + g] = valid ? q : 0.0f;
             }
         }
         __syncthreads();
+        {   // 256 threads: column (tid & 63) of the [128][64] partials, rows of quarter (tid >> 6)
+            const int col = tid & 63, qt = tid >> 6;
+            float acc = 0.0f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) acc += sRed[(qt * 32 + i) * 65 + col];
+            s_part[qt][col] = acc;
+        }
+        __syncthreads();
         if (tid < 32) {
-            float s = 0.0f, q = 0.0f;
-            for (int i = 0; i < 128; ++i) { s += sRed[i * 65 + tid]; q += sRed[i * 65 + 32 + tid]; }
+            const float s = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+            const float q = (s_part[0][32 + tid] + s_part[1][32 + tid]) + (s_part[2][32 + tid] + s_part[3][32 + tid]);
             const float inv = 1.0f / (4.0f * (float)p.N);
             const float mean = s * inv;
             const float var = fmaxf(q * inv - mean * mean, 0.0f);
@@ -231,18 +246,19 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
         }
         __syncthreads();
 #pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-            tmem_ld32(d_src + lane_off + c4 * 32, v);
+        for (int c2 = 0; c2 < 2; ++c2) {
+            const int c0 = half * 64 + c2 * 32;
+            tmem_ld32(d_src + lane_off + c2 * 32, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const int c = c4 * 32 + j;
+                const int c = c0 + j;
                 float a = v[j];
                 if (bias) a += bias[c];
                 if (bias2) a += __ldg(bias2 + c);
                 a = (a - s_stat[c >> 2]) * s_stat[32 + (c >> 2)] * gamma[c] + beta[c];
                 v[j] = swish ? swish_fast(a) : a;
             }
-            store_row32(sA, r, c4, v);
+            store_row32(sA, r, half * 2 + c2, v);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -252,11 +268,11 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
     auto acc_to_tile = [&](uint8_t* tile, const float* bias) {
         float v[32];
 #pragma unroll 1
-        for (int c4 = 0; c4 < 4; ++c4) {
-            tmem_ld32(dACC + lane_off + c4 * 32, v);
+        for (int c2 = 0; c2 < 2; ++c2) {
+            tmem_ld32(dACC + lane_off + c2 * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias[c4 * 32 + j];
-            store_row32(tile, r, c4, v);
+            for (int j = 0; j < 32; ++j) v[j] += bias[half * 64 + c2 * 32 + j];
+            store_row32(tile, r, half * 2 + c2, v);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -271,13 +287,14 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
             float row[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) row[i] = 0.0f;
-            if (valid) {
+            if (valid && half == 0) {
                 for (int i = 0; i < p.H; ++i) row[i] = p.hidden[pidx * p.H + i];
                 const int m = p.mask[pidx] ? 1 : 0;
                 row[p.H] = m ? 0.0f : 1.0f;
                 row[p.H + 1] = m ? 1.0f : 0.0f;
             }
             uint8_t* q = sA0 + (r >> 3) * 512 + (r & 7) * 16;
+            if (half == 0)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 *reinterpret_cast<uint4*>(q + c * 128) = make_uint4(pack_bf16(row[8 * c], row[8 * c + 1]), pack_bf16(row[8 * c + 2], row[8 * c + 3]),
@@ -320,10 +337,10 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
             }
             mma_done(false);
             // softmax over the N keys of this thread's query row; P (unnormalised) -> A tile (head 0) / Q tile (head 1)
-            float rinv[kHeads];
-#pragma unroll 1
-            for (int h = 0; h < kHeads; ++h) {
-                const uint32_t dS = (h ? dS1 : dS0) + lane_off;
+            float rinv;
+            {
+                const int h = half;  // this thread's head: S_h row r, 128 keys
+                const uint32_t dS = (h ? dS1 : dS0) + ((uint32_t)((warp & 3) * 32) << 16);
                 float v[32], mx = -3.0e38f;
 #pragma unroll 1
                 for (int c4 = 0; c4 < 4; ++c4) {
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
                     }
                     store_row32(h ? sQ : sA, r, c4, v);
                 }
-                rinv[h] = 1.0f / sum;
+                rinv = 1.0f / sum;
             }
             tc_fence_before();
             fence_proxy_async();
@@ -360,14 +377,13 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
             }
             mma_done(false);
             {
-                float v[32];
+                float v[32];  // columns [64*half, 64*half+64) of O = head `half`: normalised by this thread's own row sum
 #pragma unroll 1
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    tmem_ld32(dACC + lane_off + c4 * 32, v);
-                    const float ri = rinv[c4 >> 1];
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    tmem_ld32(dACC + lane_off + c2 * 32, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= ri;
-                    store_row32(sA, r, c4, v);
+                    for (int j = 0; j < 32; ++j) v[j] *= rinv;
+                    store_row32(sA, r, half * 2 + c2, v);
                 }
             }
             tc_fence_before();
@@ -379,14 +395,16 @@ __global__ void __launch_bounds__(128, 1) absorb_head_tc_kernel(const HeadParams
         // ---- rate = post_rate_proj(pre_rate_proj(X)) folded into one 128-vector (absorbing_flows.py:127-131)
         {
             const float* w = sTab + HeadTable::rate_w(nblk);
-            float acc = sTab[HeadTable::rate_c(nblk)], v[32];
+            float acc = half ? 0.0f : sTab[HeadTable::rate_c(nblk)], v[32];
 #pragma unroll 1
-            for (int c4 = 0; c4 < 4; ++c4) {
-                tmem_ld32(dX + lane_off + c4 * 32, v);
+            for (int c2 = 0; c2 < 2; ++c2) {
+                tmem_ld32(dX + lane_off + c2 * 32, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc = fmaf(w[c4 * 32 + j], v[j], acc);
+                for (int j = 0; j < 32; ++j) acc = fmaf(w[half * 64 + c2 * 32 + j], v[j], acc);
             }
-            if (valid) p.logit_out[pidx] = acc;
+            if (half) s_dot[r] = acc;
+            __syncthreads();
+            if (valid && !half) p.logit_out[pidx] = acc + s_dot[r];
         }
         tc_fence_before();
         __syncthreads();  // X and the operand tiles are rewritten by the next jet
@@ -492,7 +510,7 @@ int launch_absorb_head(const AbsorbHead* h, const float* hidden, const uint8_t* 
     if (int rc = cuda_ok(cudaFuncSetAttribute(absorb_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "head smem attribute"))
         return rc;
     const int grid = B < h->sm_count ? B : h->sm_count;
-    absorb_head_tc_kernel<<<grid, 128, bytes, stream>>>(p);
+    absorb_head_tc_kernel<<<grid, kThreads, bytes, stream>>>(p);
     return cuda_ok(cudaGetLastError(), "absorb_head launch");
 }
 
