@@ -40,7 +40,8 @@ namespace {
 
 constexpr int kH = 16;      // hidden width this path is built for
 constexpr int kGP = 32;     // global width, padded
-constexpr int kJPC = 2;     // jets per CTA
+constexpr int kJPC = 4;     // jets per CTA (512 threads); two CTAs per SM -> 8 jets in flight
+constexpr int kTmemPerJet = 64;  // columns: main 16 | pool 16 | skip 16 | spare (allocation must be a power of two)
 constexpr int kRows = 128;  // UMMA M
 constexpr int kMaxL = 4;
 constexpr int kMaxT = 32;
@@ -189,6 +190,17 @@ __device__ __forceinline__ void lds16(const float* p, float (&v)[16]) {
     }
 }
 
+// park 16 fp32 values in this thread's TMEM lane (the trunk's skip connection lives there between layers)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                   "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                   "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -269,7 +281,7 @@ struct JetVec {
 };
 
 template <int DC, int S, int SH, bool GENERATE>
-__global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcLayout& lay = p.lay;
     const int tid = threadIdx.x;
@@ -300,16 +312,16 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
     JetVec& jv = *reinterpret_cast<JetVec*>(abuf + kGrpFixed);
     const uint32_t mbar = smem_u32(abuf + kGrpFixed + ((sizeof(JetVec) + 15) & ~15));
     if (gt == 0) mbar_init(mbar, 1);
-    if (tid < 32) tmem_alloc(smem_u32(&s_tmem_slot), kJPC * 32);
+    if (tid < 32) tmem_alloc(smem_u32(&s_tmem_slot), kJPC * kTmemPerJet);
     fence_barrier_init();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem_slot;
-    const uint32_t t_main = tmem_base + grp * 32 + ((uint32_t)(wq * 32) << 16);
-    const uint32_t t_pool = t_main + 16;
-    const uint32_t d_main = tmem_base + grp * 32, d_pool = d_main + 16;
+    const uint32_t t_main = tmem_base + grp * kTmemPerJet + ((uint32_t)(wq * 32) << 16);
+    const uint32_t t_pool = t_main + 16, t_skip = t_main + 32;
+    const uint32_t d_main = tmem_base + grp * kTmemPerJet, d_pool = d_main + 16;
 
     const long jet = (long)blockIdx.x * kJPC + grp;
     if (jet < p.B) {
@@ -420,13 +432,11 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
             }
             mbar_wait(mbar, phase); phase ^= 1;
             tc_fence_after();
-            float acc[16], xl[16], skipl[16];
+            float acc[16], xl[16];
             tmem_ld16(t_main, acc);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                xl[i] = lrelu_fast(acc[i]);
-                skipl[i] = lay.skip ? xl[i] : 0.0f;
-            }
+            for (int i = 0; i < 16; ++i) xl[i] = lrelu_fast(acc[i]);
+            if (lay.skip) tmem_st16(t_skip, xl);   // x_local_skip (epic.py:148) parked in TMEM, not in registers
             store_a_row(abuf, r, xl);
             tc_fence_before();
             fence_proxy_async();
@@ -527,7 +537,12 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
                 tc_fence_after();
                 tmem_ld16(t_main, acc);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) xl[i] = lrelu_fast(acc[i] + xl[i]) + skipl[i];  // dead rows: unused garbage, zeroed at pack
+                for (int i = 0; i < 16; ++i) xl[i] = lrelu_fast(acc[i] + xl[i]);  // dead rows: unused garbage, zeroed at pack
+                if (lay.skip) {
+                    tmem_ld16(t_skip, acc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) xl[i] += acc[i];
+                }
                 store_a_row_masked(abuf, r, xl, live);
                 tc_fence_before();
                 fence_proxy_async();
@@ -536,33 +551,23 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
             // ---- (i) output layer (epic.py:158-162)
             if (gt == 0) {
                 tc_fence_after();
+                // with a discrete head the operand is [W_out(v rows) ; F1 W_out(z rows)]: the output layer and the first
+                // head Linear have no nonlinearity between them, so columns DC.. are already F1 z + f1 (mbm.py:105-111)
                 gemm(lay.bop_out());
-                umma(d_main, amask_desc, bop_desc(lay.bop_bias_out()), idesc_k, 1);  // dead rows: A row 0, no bias -> h = 0
+                umma(d_main, amask_desc, bop_desc(lay.bop_bias_out()), idesc_k, 1);  // live rows: b_out | F1 b_out_z
+                if constexpr (SH > 0) umma(d_main, ones_desc, bop_desc(lay.bop_bias_h0()), idesc_k, 1);  // all rows: f1 (fc(0) on dead rows)
                 umma_commit(mbar);
             }
             mbar_wait(mbar, phase); phase ^= 1;
             tc_fence_after();
             float h[16];
-            tmem_ld16(t_main, h);
+            tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
             float lg[S];
-            if constexpr (SH > 0) {  // discrete head Linear -> SELU -> Linear on the logit slice (mbm.py:90-111)
-                store_a_row(abuf, r, h);
-                tc_fence_before();
-                fence_proxy_async();
-                group_bar(1 + grp);
-                if (gt == 0) {
-                    tc_fence_after();
-                    gemm(lay.bop_h0());
-                    umma(d_main, ones_desc, bop_desc(lay.bop_bias_h0()), idesc_k, 1);  // all rows: fc(0) on dead rows as the reference
-                    umma_commit(mbar);
-                }
-                mbar_wait(mbar, phase); phase ^= 1;
-                tc_fence_after();
-                tmem_ld16(t_main, acc);
+            if constexpr (SH > 0) {
                 {
                     float z1[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) z1[i] = i < SH ? selu_fast(acc[i]) : 0.0f;
+                    for (int i = 0; i < 16; ++i) z1[i] = i < SH ? selu_fast(h[DC + (i < SH ? i : 0)]) : 0.0f;
                     store_a_row(abuf, r, z1);
                 }
                 tc_fence_before();
@@ -627,7 +632,7 @@ __global__ void __launch_bounds__(kJPC * 128, 3) epic_tc_kernel(const TcParams p
     }
     tc_fence_before();
     __syncthreads();
-    if (tid < 32) tmem_dealloc(tmem_base, kJPC * 32);
+    if (tid < 32) tmem_dealloc(tmem_base, kJPC * kTmemPerJet);
 }
 
 size_t tc_smem_bytes(const TcLayout& lay) {
@@ -781,15 +786,18 @@ int tc_build_image(EpicModel* m, const float* W) {
             F[lay.l_g2b + g] = Wl[Lo.l_g2_b + g];
         }
     }
-    for (int o = 0; o < Dc + S; ++o) {
-        for (int k = 0; k < H; ++k) setb(lay.bop_out(), o, k, W[Lo.out_w + (size_t)o * H + k]);
-        wf[lay.bout + o] = W[Lo.out_b + o];
-    }
-    if (Sh) {
-        for (int o = 0; o < Sh; ++o) {
-            for (int s = 0; s < S; ++s) setb(lay.bop_h0(), o, Dc + s, W[Lo.head0_w + (size_t)o * S + s]);
-            wf[lay.bh0 + o] = W[Lo.head0_b + o];
-        }
+    if (!Sh) {
+        for (int o = 0; o < Dc + S; ++o)
+            for (int k = 0; k < H; ++k) setb(lay.bop_out(), o, k, W[Lo.out_w + (size_t)o * H + k]);
+    } else {  // rows [0,Dc): output layer (velocity); rows [Dc,Dc+Sh): head Linear 0 folded through the output layer
+        for (int o = 0; o < Dc; ++o)
+            for (int k = 0; k < H; ++k) setb(lay.bop_out(), o, k, W[Lo.out_w + (size_t)o * H + k]);
+        for (int j = 0; j < Sh; ++j)
+            for (int k = 0; k < H; ++k) {
+                double acc = 0;
+                for (int s = 0; s < S; ++s) acc += (double)W[Lo.head0_w + (size_t)j * S + s] * W[Lo.out_w + (size_t)(Dc + s) * H + k];
+                setb(lay.bop_out(), Dc + j, k, acc);
+            }
         for (int o = 0; o < S; ++o) {
             for (int k = 0; k < Sh; ++k) setb(lay.bop_h2(), o, k, W[Lo.head2_w + (size_t)o * Sh + k]);
             wf[lay.bh2 + o] = W[Lo.head2_b + o];
@@ -802,9 +810,16 @@ int tc_build_image(EpicModel* m, const float* W) {
     };
     for (int l = 0; l < L; ++l)
         for (int o = 0; o < H; ++o) set_bias(lay.bop_bias_l2(l), o, W[Lo.layer0 + (size_t)l * Lo.layer_stride + Lo.l_l2_b + o]);
-    for (int o = 0; o < Dc + S; ++o) set_bias(lay.bop_bias_out(), o, W[Lo.out_b + o]);
-    if (Sh) {
-        for (int o = 0; o < Sh; ++o) set_bias(lay.bop_bias_h0(), o, W[Lo.head0_b + o]);
+    if (!Sh) {
+        for (int o = 0; o < Dc + S; ++o) set_bias(lay.bop_bias_out(), o, W[Lo.out_b + o]);
+    } else {
+        for (int o = 0; o < Dc; ++o) set_bias(lay.bop_bias_out(), o, W[Lo.out_b + o]);
+        for (int j = 0; j < Sh; ++j) {
+            double acc = 0;
+            for (int s = 0; s < S; ++s) acc += (double)W[Lo.head0_w + (size_t)j * S + s] * W[Lo.out_b + Dc + s];
+            set_bias(lay.bop_bias_out(), Dc + j, (float)acc);
+            set_bias(lay.bop_bias_h0(), Dc + j, W[Lo.head0_b + j]);
+        }
         for (int o = 0; o < S; ++o) set_bias(lay.bop_bias_h2(), o, W[Lo.head2_b + o]);
     }
     const size_t nb = bops.size() * sizeof(__nv_bfloat16), nf = wf.size() * sizeof(float);
