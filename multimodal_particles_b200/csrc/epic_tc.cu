@@ -306,6 +306,9 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         for (int i = tid; i < 256; i += blockDim.x) reinterpret_cast<uint4*>(s_ones)[i] = make_uint4(one2, one2, one2, one2);
     }
     const int grp = tid >> 7, gt = tid & 127, wq = gt >> 5, lane = tid & 31;
+    // the "special" warp of a group issues its MMAs and runs its per-jet global MLP; warp w lives on SM sub-partition
+    // w % 4, so rotating the role with the group index spreads that serial work over all four schedulers
+    const int swq = grp & 3;
     uint8_t* abuf = s_grp + grp * kGrpBytes;
     uint8_t* amask = abuf + 4096;   // A tile of the bias K-steps: columns 0,1 = mask of the row's particle
     uint8_t* bb0 = abuf + 8192;     // B tile carrying this step's local_0 bias (hi, lo) in columns 0,1
@@ -362,7 +365,9 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         const uint64_t ones_desc = smem_desc(smem_u32(s_ones), 128, 256);
         const uint64_t amask_desc = smem_desc(smem_u32(amask), 128, 256);
         const uint64_t bb0_desc = smem_desc(smem_u32(bb0), 128, 256);
-        auto bop_desc = [&](int op) { return smem_desc(bops_addr + op * 512, 128, 256); };
+        const uint64_t bops_desc0 = smem_desc(bops_addr, 128, 256);
+        auto bop_desc = [&](int op) { return bops_desc0 + (uint64_t)(op * 32); };   // 512 B per operand, address field is >> 4
+        const uint64_t pool_desc0 = smem_desc(a_addr, 256, 128);                      // A tile re-read MN-major
         constexpr uint32_t idesc_k = instr_desc(128, 16, false);
         constexpr uint32_t idesc_pool = instr_desc(128, 16, true);
         const int n_w = lay.n_weights();
@@ -372,13 +377,19 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             umma(d_main, a_desc, bop_desc(op + n_w), idesc_k, 1);
         };
         uint32_t phase = 0;
+        // MMA completion: warp 0 polls the mbarrier, warps 1-3 block on the named barrier (no issue slots burnt spinning)
+        auto wait_mma = [&]() {
+            if (wq == swq) mbar_wait(mbar, phase);
+            phase ^= 1;
+            group_bar(1 + grp);
+        };
         const int T = lay.T, L = lay.L;
         const int o16 = lane & 15, hf = lane >> 4;
 
         const int n_steps = GENERATE ? p.n_steps : 1;
         for (int step = 0; step < n_steps; ++step) {
             // ---- (a) time vectors (warp 0) and the first A row [x_hi, x_lo, onehot(k)] * m
-            if (wq == 0) {
+            if (wq == swq) {
                 const float* te = GENERATE ? p.temb + (size_t)step * T : p.temb + (size_t)jet * p.temb_stride;
                 const int t0 = hf * (T / 2), t1 = t0 + T / 2;
                 float a0 = hf ? 0.0f : s_wf[lay.c0 + o16], a1 = hf ? 0.0f : s_wf[lay.g0b + o16];
@@ -424,13 +435,13 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             fence_proxy_async();
             group_bar(1 + grp);
             // ---- (b) local_0
-            if (gt == 0) {
+            if (gt == swq * 32) {
                 tc_fence_after();
                 gemm(lay.bop_local0());
                 umma(d_main, amask_desc, bb0_desc, idesc_k, 1);  // + bias on live rows; dead rows stay exactly 0
                 umma_commit(mbar);
             }
-            mbar_wait(mbar, phase); phase ^= 1;
+            wait_mma();
             tc_fence_after();
             float acc[16], xl[16];
             tmem_ld16(t_main, acc);
@@ -445,18 +456,19 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             for (int l = 0; l < L; ++l) {
                 const float* Wl = s_wf + lay.layer0 + l * lay.layer_stride;
                 // ---- (d) pooling GEMM (ones x XL, K = 128 particles) + fc_local1 on the same tile
-                if (gt == 0) {
+                if (gt == swq * 32) {
                     tc_fence_after();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)  // K-step j = particles 16j..16j+15: two 8-row groups, MN-major
-                        umma(d_pool, ones_desc, smem_desc(a_addr + j * 512, 256, 128), idesc_pool, j > 0);
+                        umma(d_pool, ones_desc, pool_desc0 + (uint64_t)(j * 32), idesc_pool, j > 0);
                     gemm(lay.bop_l1(l));
                     umma_commit(mbar);
                 }
-                mbar_wait(mbar, phase); phase ^= 1;
-                tc_fence_after();
-                // ---- (e) global path on warp 0 of the group (fp32, CUDA cores)
-                if (wq == 0) {
+                phase ^= 1;
+                // ---- (e) global path on warp 0 of the group (fp32, CUDA cores); the other warps park at the barrier below
+                if (wq == swq) {
+                    mbar_wait(mbar, phase ^ 1);
+                    tc_fence_after();
                     float sv[16];
                     tmem_ld16(t_pool, sv);
                     if (l == 0) {  // EPiC_Projection globals (epic.py:187-190)
@@ -527,13 +539,13 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 fence_proxy_async();
                 group_bar(1 + grp);
                 // ---- (g) fc_local2
-                if (gt == 0) {
+                if (gt == swq * 32) {
                     tc_fence_after();
                     gemm(lay.bop_l2(l));
                     umma(d_main, amask_desc, bop_desc(lay.bop_bias_l2(l)), idesc_k, 1);
                     umma_commit(mbar);
                 }
-                mbar_wait(mbar, phase); phase ^= 1;
+                wait_mma();
                 tc_fence_after();
                 tmem_ld16(t_main, acc);
 #pragma unroll
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 group_bar(1 + grp);
             }
             // ---- (i) output layer (epic.py:158-162)
-            if (gt == 0) {
+            if (gt == swq * 32) {
                 tc_fence_after();
                 // with a discrete head the operand is [W_out(v rows) ; F1 W_out(z rows)]: the output layer and the first
                 // head Linear have no nonlinearity between them, so columns DC.. are already F1 z + f1 (mbm.py:105-111)
@@ -558,7 +570,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 if constexpr (SH > 0) umma(d_main, ones_desc, bop_desc(lay.bop_bias_h0()), idesc_k, 1);  // all rows: f1 (fc(0) on dead rows)
                 umma_commit(mbar);
             }
-            mbar_wait(mbar, phase); phase ^= 1;
+            wait_mma();
             tc_fence_after();
             float h[16];
             tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
@@ -573,13 +585,13 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
-                if (gt == 0) {
+                if (gt == swq * 32) {
                     tc_fence_after();
                     gemm(lay.bop_h2());
                     umma(d_main, ones_desc, bop_desc(lay.bop_bias_h2()), idesc_k, 1);
                     umma_commit(mbar);
                 }
-                mbar_wait(mbar, phase); phase ^= 1;
+                wait_mma();
                 tc_fence_after();
                 if constexpr (S <= 8) {
                     float l8[8];
