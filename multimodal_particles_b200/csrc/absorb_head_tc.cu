@@ -100,7 +100,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float swish_fast(float a) { return a * __fdividef(1.0f, 1.0f + __expf(-a)); }
+// x sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU (tanh.approx) instead of ex2 + rcp
+__device__ __forceinline__ float swish_fast(float a) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * a));
+    const float ha = 0.5f * a;
+    return fmaf(ha, t, ha);
+}
 
 // [128 rows x 128 k] bf16 tile, K-major canonical: 8-row groups 2048 B apart (SBO), 16-byte k-chunks
 // 128 B apart (LBO).  Thread `row` stores columns [32*chunk4, 32*chunk4+32) of its row (4 x 16 B).
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t s_tmem_slot;
     __shared__ __align__(8) uint64_t s_bars[3];  // full[0], full[1], mma
-    __shared__ float s_stat[64];                 // mean[32], rstd[32]
+    __shared__ float s_stat[256];                // per channel: scale = rstd*gamma [128], shift = beta - mean*scale (+bias) [128]
     __shared__ float s_part[4][64];              // GroupNorm partial column sums (4 row quarters)
     __shared__ float s_dot[128];                 // rate-vector partial of the upper-half threads
     const int tid = threadIdx.x, r = tid & 127, half = tid >> 7, warp = tid >> 5;
@@ -235,14 +241,19 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             s_part[qt][col] = acc;
         }
         __syncthreads();
-        if (tid < 32) {
-            const float s = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
-            const float q = (s_part[0][32 + tid] + s_part[1][32 + tid]) + (s_part[2][32 + tid] + s_part[3][32 + tid]);
+        if (tid < 128) {  // one thread per channel: y = x*scale + shift with the statistics of its group folded in
+            const int g = tid >> 2;
+            const float s = (s_part[0][g] + s_part[1][g]) + (s_part[2][g] + s_part[3][g]);
+            const float q = (s_part[0][32 + g] + s_part[1][32 + g]) + (s_part[2][32 + g] + s_part[3][32 + g]);
             const float inv = 1.0f / (4.0f * (float)p.N);
             const float mean = s * inv;
             const float var = fmaxf(q * inv - mean * mean, 0.0f);
-            s_stat[tid] = mean;
-            s_stat[32 + tid] = rsqrtf(var + 1e-6f);
+            const float scale = rsqrtf(var + 1e-6f) * gamma[tid];
+            float pre = 0.0f;
+            if (bias) pre += bias[tid];
+            if (bias2) pre += __ldg(bias2 + tid);
+            s_stat[tid] = scale;
+            s_stat[128 + tid] = fmaf(pre - mean, scale, beta[tid]);
         }
         __syncthreads();
 #pragma unroll 1
@@ -252,10 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int c = c0 + j;
-                float a = v[j];
-                if (bias) a += bias[c];
-                if (bias2) a += __ldg(bias2 + c);
-                a = (a - s_stat[c >> 2]) * s_stat[32 + (c >> 2)] * gamma[c] + beta[c];
+                const float a = fmaf(v[j], s_stat[c], s_stat[128 + c]);
                 v[j] = swish ? swish_fast(a) : a;
             }
             store_row32(sA, r, half * 2 + c2, v);
