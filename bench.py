@@ -273,8 +273,8 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / float(te.item())
-    h2d = B * N_PART * (3 * 4 + 8 + 8)     # fp32 x, int64 tokens, int64 mask (reference layout)
-    d2h = B * N_PART * (3 * 4 + 8 + 8) + B * 4
+    h2d = B * N_PART * (3 * 4 + 8 + 8)     # fp32 x, int64 tokens, int64 mask (reference layout), from pinned memory
+    d2h = B * N_PART * (3 * 4 + 1)         # fp32 x + uint8 tokens (widened on the host; the mask is unchanged and stays put)
     assert out.continuous.device.type == "cpu"
 
     if rank == 0:
