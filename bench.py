@@ -37,6 +37,7 @@ WORKLOAD = "C2: EPiC multimodal bridge, JetClass-shape synthetic jets, N=128, Dc
 B_PER_GPU, N_PART, N_TIMESTEPS = 4096, 128, 100
 FLOP_PER_JET_STEP = 0.819e6          # SURVEY.md §8d (2*MAC, default widths)
 UPDATE_BYTES_PER_PARTICLE = 75       # SURVEY.md §8d / BASELINE.md §4
+CPU_SAMPLE_JETS = 16384              # bounded CPU sample: ~15 s on 16 host threads at ~1.1 K jets/s
 
 
 def peaks():
@@ -123,8 +124,8 @@ def run_reference(args, rank):
     """--impl reference: the CPU implementation of the path (oracle port), rank 0 only."""
     if rank != 0:
         return
-    sample = 64
-    for _ in range(max(args.warmup, 1)):
+    sample = 4096                        # ~4 s per step on 16 host threads
+    for _ in range(max(min(args.warmup, 1), 1)):
         cpu_port_jets_per_s(sample)
     times = []
     for _ in range(args.steps):
@@ -280,9 +281,10 @@ def main():
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, dt_cpu, cores = cpu_port_jets_per_s(256)
+            cpu_port_jets_per_s(256)                                  # warm-up (thread pool, page faults)
+            v, dt_cpu, cores = cpu_port_jets_per_s(CPU_SAMPLE_JETS)   # ~10-20 s of CPU work
             cpu = {"value": v, "unit": "jets/s", "cores": cores, "kind": "port",
-                   "sample": f"256 jets x 99 solver steps of the same workload ({dt_cpu:.1f} s), OpenMP over jets"}
+                   "sample": f"{CPU_SAMPLE_JETS} jets x 99 solver steps of the same workload ({dt_cpu:.1f} s), OpenMP over jets"}
         launches = K * (1 + (3 if world > 1 else 0))
         line = {"metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

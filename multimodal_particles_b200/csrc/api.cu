@@ -114,8 +114,8 @@ size_t mmb_generate_workspace_bytes(const MmbEpicModel* handle, int B, int N, in
     const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
     (void)B; (void)N; (void)precision;
     if (!m) return 0;
-    // room for the device image of a step table of up to 4096 steps
-    return table_floats(4096, m->dims.dim_time_emb) * sizeof(float);
+    // room for the device image of a step table of up to 4096 steps + the tcgen05 path's per-step time vectors
+    return (table_floats(4096, m->dims.dim_time_emb) + tc_generate_scratch_floats(&m->dims, 4096)) * sizeof(float);
 }
 
 int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t* mask,
@@ -127,7 +127,8 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate: negative size");
     const int T = m->dims.dim_time_emb, n = st->n_steps;
     const size_t need = table_floats(n, T) * sizeof(float);
-    if (workspace_bytes < need) return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B < %zu B", workspace_bytes, need);
+    if (workspace_bytes < need + tc_generate_scratch_floats(&m->dims, n) * sizeof(float))
+        return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B too small for %d steps", workspace_bytes, n);
     if (B == 0 || N == 0 || n == 0) return MMB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     // stage the table (a few KB); pageable source: the copy is staged before the call returns
@@ -146,7 +147,8 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     if (precision == MMB_PREC_BF16) {
         if (!m->tc_image || !tc_supported(&m->dims, N))
             return fail(MMB_EUNSUPPORTED, "tcgen05 path is built for H=16, G<=32, Dc+S<=16, head<=16, N<=128; use fp32");
-        return launch_generate_tc(m, x, k, mask, table, n, st->dt, u_jump, seed, jet_offset, B, N, s);
+        return launch_generate_tc(m, x, k, mask, table, static_cast<float*>(workspace) + table_floats(n, T), n, st->dt, u_jump, seed,
+                                  jet_offset, B, N, s);
     }
     return fail(MMB_EINVAL, "unknown precision %d", precision);
 }
@@ -241,5 +243,8 @@ int mmb_validation_histograms(const float* x, const uint8_t* k, const uint8_t* m
     return launch_validation_histograms(x, k, mask, B, N, Dc, S, bins, lo, hi, max_mult,
                                         reinterpret_cast<unsigned long long*>(counts), static_cast<cudaStream_t>(stream));
 }
+
+// debug only (not part of include/mmbridge.h): phase timestamps of the tcgen05 generation kernel, see tools/tc_trace.py
+int mmb_debug_read_trace(long long* out, int n) { return tc_read_trace(out, n); }
 
 }  // extern "C"

@@ -30,6 +30,8 @@
 // mp/models/generative/multimodal_bridge_matching.py:90-113,199-216, bridges.py:38-45,106-132,179-201).
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "mmb_device.cuh"
@@ -268,6 +270,8 @@ struct TcParams {
     uint64_t seed, jet_offset;
     int B, N;
     float *v_out, *logits_out, *hidden_out;  // forward outputs
+    const float* tvec;     // generate: [n_steps][2+2L][16] per-step time vectors from tc_time_vectors_kernel; forward: null
+    long long* trace;      // debug: clock64() stamps of jet 0, step 3 (tools/tc_trace.py); null in production
 };
 
 // per-group shared memory: A tile (4 KB), mask tile (4 KB), dynamic bias operand of local_0 (512 B)
@@ -387,9 +391,27 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         const int o16 = lane & 15, hf = lane >> 4;
 
         const int n_steps = GENERATE ? p.n_steps : 1;
+#define MMB_TRACE(id) do { if (p.trace && jet == 0 && step == 3 && gt == 32 * ((swq + 1) & 3)) p.trace[id] = clock64(); } while (0)
         for (int step = 0; step < n_steps; ++step) {
+            MMB_TRACE(0);
             // ---- (a) time vectors (warp 0) and the first A row [x_hi, x_lo, onehot(k)] * m
-            if (wq == swq) {
+            if (GENERATE && p.tvec) {
+                // the time is shared by all jets at generation: the vectors were computed once per step by the prologue kernel
+                if (wq == swq) {
+                    const float* tv = p.tvec + (size_t)step * (2 + 2 * L) * 16;
+                    const int vi = lane >> 4;   // two vectors per pass
+                    for (int v0 = 0; v0 < 2 + 2 * L; v0 += 2) {
+                        const float val = __ldg(tv + (v0 + vi) * 16 + o16);
+                        const int v = v0 + vi;
+                        if (v == 0) {
+                            const float hi = __bfloat162float(__float2bfloat16_rn(val));
+                            *reinterpret_cast<uint32_t*>(bb0 + (o16 >> 3) * 256 + (o16 & 7) * 16) = pack_bf16(hi, val - hi);
+                        } else if (v == 1) jv.tv_g0[o16] = val;
+                        else if ((v & 1) == 0) jv.tv_g1[(v - 2) >> 1][o16] = val;
+                        else jv.tv_l1[(v - 2) >> 1][o16] = val;
+                    }
+                }
+            } else if (wq == swq) {
                 const float* te = GENERATE ? p.temb + (size_t)step * T : p.temb + (size_t)jet * p.temb_stride;
                 const int t0 = hf * (T / 2), t1 = t0 + T / 2;
                 float a0 = hf ? 0.0f : s_wf[lay.c0 + o16], a1 = hf ? 0.0f : s_wf[lay.g0b + o16];
@@ -434,6 +456,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             }
             fence_proxy_async();
             group_bar(1 + grp);
+            MMB_TRACE(1);
             // ---- (b) local_0
             if (gt == swq * 32) {
                 tc_fence_after();
@@ -443,6 +466,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             }
             wait_mma();
             tc_fence_after();
+            MMB_TRACE(2);
             float acc[16], xl[16];
             tmem_ld16(t_main, acc);
 #pragma unroll
@@ -452,6 +476,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_before();
             fence_proxy_async();
             group_bar(1 + grp);
+            MMB_TRACE(3);
 
             for (int l = 0; l < L; ++l) {
                 const float* Wl = s_wf + lay.layer0 + l * lay.layer_stride;
@@ -525,6 +550,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     tc_fence_before();
                 }
                 group_bar(1 + grp);
+                MMB_TRACE(4 + 4 * l);
                 // ---- (f) fc_local1 epilogue -> A operand of fc_local2
                 tc_fence_after();
                 tmem_ld16(t_main, acc);
@@ -538,6 +564,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
+                MMB_TRACE(5 + 4 * l);
                 // ---- (g) fc_local2
                 if (gt == swq * 32) {
                     tc_fence_after();
@@ -546,6 +573,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     umma_commit(mbar);
                 }
                 wait_mma();
+                MMB_TRACE(6 + 4 * l);
                 tc_fence_after();
                 tmem_ld16(t_main, acc);
 #pragma unroll
@@ -559,6 +587,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
+                MMB_TRACE(7 + 4 * l);
             }
             // ---- (i) output layer (epic.py:158-162)
             if (gt == swq * 32) {
@@ -572,6 +601,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             }
             wait_mma();
             tc_fence_after();
+            MMB_TRACE(12);
             float h[16];
             tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
             float lg[S];
@@ -593,6 +623,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 }
                 wait_mma();
                 tc_fence_after();
+                MMB_TRACE(14);
                 if constexpr (S <= 8) {
                     float l8[8];
                     tmem_ld8(t_main, l8);
@@ -608,6 +639,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 for (int s = 0; s < S; ++s) lg[s] = h[DC + s];
             }
             tc_fence_before();  // orders this step's last tcgen05.ld before the next step's first MMA (via the group barrier)
+            MMB_TRACE(15);
 
             if constexpr (GENERATE) {
                 // ---- (k) hybrid update in registers (bridges.py:38-45,179-201)
@@ -619,6 +651,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                                              : philox_uniform(p.seed, p.jet_offset + (uint64_t)jet, 0, step, r);
                     kk = telegraph_jump_fast<S>(lg, kk, u, sc) * m;
                 }
+                MMB_TRACE(16);
             } else {
                 if (valid) {
 #pragma unroll
@@ -720,6 +753,45 @@ static int launch_discrete_head_mlp(const EpicModel* m, float* logits, size_t P,
     if (S == 8) discrete_head_mlp_kernel<8><<<grid, 256, bytes, stream>>>(m->w, m->layout, Sh, logits, P);
     else discrete_head_mlp_kernel<4><<<grid, 256, bytes, stream>>>(m->w, m->layout, Sh, logits, P);
     return cuda_ok(cudaGetLastError(), "discrete_head_mlp launch");
+}
+
+// Per-step time vectors of the generation loop (same for every jet): v0 = local_0 bias c0 + W0t temb, v1 = G0 bias + G0t temb,
+// then per layer (fc_global1 bias + time part, fc_local1 bias + time part).  One block per step, one thread per output.
+__global__ void tc_time_vectors_kernel(const uint8_t* __restrict__ image, TcLayout lay, const float* __restrict__ temb, float* __restrict__ tvec) {
+    const float* wf = reinterpret_cast<const float*>(image + lay.n_bops * 512);
+    const int step = blockIdx.x, v = threadIdx.x >> 4, o = threadIdx.x & 15;
+    if (v >= 2 + 2 * lay.L) return;
+    const float* te = temb + (size_t)step * lay.T;
+    int base, mat;
+    if (v == 0) { base = lay.c0; mat = lay.w0t; }
+    else if (v == 1) { base = lay.g0b; mat = lay.g0t; }
+    else {
+        const int lo = lay.layer0 + ((v - 2) >> 1) * lay.layer_stride;
+        base = lo + ((v & 1) ? lay.l_l1b : lay.l_g1b);
+        mat = lo + ((v & 1) ? lay.l_l1t : lay.l_g1t);
+    }
+    // same split-in-halves summation order as the in-kernel path (two partial sums over t, then added)
+    float a0 = wf[base + o], a1 = 0.0f;
+    for (int t = 0; t < lay.T / 2; ++t) a0 = fmaf(wf[mat + t * 16 + o], te[t], a0);
+    for (int t = lay.T / 2; t < lay.T; ++t) a1 = fmaf(wf[mat + t * 16 + o], te[t], a1);
+    tvec[((size_t)step * (2 + 2 * lay.L) + v) * 16 + o] = a0 + a1;
+}
+
+size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps) { return (size_t)n_steps * (2 + 2 * d->num_blocks) * 16; }
+
+// MMB_TC_TRACE=1: per-phase clock64() stamps of jet 0 (tools/tc_trace.py reads them through mmb_debug_read_trace)
+static long long* g_trace_dev = nullptr;
+static long long* tc_trace_buffer() {
+    static const bool on = [] { const char* e = getenv("MMB_TC_TRACE"); return e && e[0] == '1'; }();
+    if (!on) return nullptr;
+    if (!g_trace_dev && cudaMalloc(&g_trace_dev, 64 * sizeof(long long)) == cudaSuccess) cudaMemset(g_trace_dev, 0, 64 * sizeof(long long));
+    return g_trace_dev;
+}
+int tc_read_trace(long long* out, int n) {
+    if (!g_trace_dev) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, g_trace_dev, sizeof(long long) * (n < 64 ? n : 64), cudaMemcpyDeviceToHost);
+    return n < 64 ? n : 64;
 }
 
 bool tc_supported(const MmbEpicDims* d, int N) {
@@ -855,7 +927,7 @@ int launch_epic_forward_tc(const EpicModel* m, const float* x, const uint8_t* k,
     return head_fused(m->dims) ? MMB_OK : launch_discrete_head_mlp(m, logits_out, (size_t)B * N, stream);
 }
 
-int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table,
+int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
                        int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                        int B, int N, cudaStream_t stream) {
     if (B == 0 || n_steps == 0) return MMB_OK;
@@ -867,6 +939,12 @@ int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* 
     p.step_tab = dev_table; p.temb = dev_table + (size_t)n_steps * 4; p.temb_stride = 0;
     p.n_steps = n_steps; p.dt = dt; p.u_jump = u_jump; p.seed = seed; p.jet_offset = jet_offset;
     p.B = B; p.N = N;
+    p.trace = tc_trace_buffer();
+    if (scratch) {
+        tc_time_vectors_kernel<<<n_steps, 16 * (2 + 2 * kMaxL), 0, stream>>>(p.image, p.lay, p.temb, scratch);
+        if (int rc = cuda_ok(cudaGetLastError(), "tc_time_vectors launch")) return rc;
+        p.tvec = scratch;
+    }
     return dispatch<true>(m->dims, p, stream);
 }
 

@@ -58,11 +58,13 @@ int launch_generate_fp32(const EpicModel* m, float* x, uint8_t* k, const uint8_t
 
 // epic_tc.cu — tcgen05 path
 bool tc_supported(const MmbEpicDims* d, int N);
+int tc_read_trace(long long* out, int n);
 int tc_build_image(EpicModel* m, const float* packed_host);
 int launch_epic_forward_tc(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
                            const float* temb, int temb_stride, int B, int N,
                            float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream);
-int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table,
+size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps);
+int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
                        int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                        int B, int N, cudaStream_t stream);
 
