@@ -264,6 +264,107 @@ int mmb_generate_absorbing(const MmbEpicModel* model, const MmbAbsorbHead* head,
                            uint64_t seed, uint64_t jet_offset, int B, int N, void* workspace, size_t workspace_bytes,
                            int precision, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Trans-dimensional jump diffusion (BASELINE config "transepic").
+ *
+ * TransdimensionalEPiC.forward (mp/models/generative/transdimensional/transdimensional_model.py:245-426,
+ * called through EpsilonPrecond.forward :124-133): EPiC trunk with the last local hidden, then two
+ * 128-wide transformer stacks (gsdm.py ResnetBlock + AttnBlock): the first gives the per-jet x0-dimension
+ * logits (hence the birth rate, mp/models/generative/diffusion/noising.py:166-216) and the nearest-particle
+ * logits, the second — fed with the distance to the chosen nearest particle — gives mean and std of the
+ * particle that a birth adds.
+ */
+typedef struct MmbTransDims {
+    int32_t hidden;          /* H  encoder.dim_hidden_local (width of the trunk's last local hidden) */
+    int32_t vocab_size;      /* S  data.vocab_size_features (one-hot channels) */
+    int32_t transformer_dim; /* C  encoder.transformer_dim (= temb_dim); built for 128 */
+    int32_t n_heads;         /*    encoder.n_heads; built for 2 */
+    int32_t n_blocks;        /*    encoder.n_attn_blocks */
+    int32_t max_particles;   /* R  rdim of post_rate_proj = data.max_num_particles (rate_use_x0_pred) */
+} MmbTransDims;
+
+/* StepForwardRate / ConstForwardRate (noising.py:123-164): rate(t) = scalar*[t > cut] + offset (step),
+ * scalar (const);  integral(t) = (t-cut)*scalar*[t > cut] + offset*t (step), scalar*t (const). */
+typedef struct MmbForwardRate {
+    int32_t kind;  /* 0 = step, 1 = const */
+    float scalar, offset, rate_cut_t;
+} MmbForwardRate;
+
+/*
+ * Packed blob (fp32, every matrix row-major [out][in] followed by its bias), C = transformer_dim:
+ *   temb_net [C][C]+[C];
+ *   res_blocks[i].temb_proj [C][C]+[C], i < n_blocks;  vec_res_blocks[i].temb_proj [C][C]+[C], i < n_blocks;
+ *   stack 1: transformer_1_proj_in [C][H+S]+[C]; n_blocks x block; pre_rate_proj [C][C]+[C];
+ *            post_rate_proj [R][C]+[R]; near_atom_proj [1][C]+[1];
+ *   stack 2: vec_transformer_in_proj [C][H+S+3]+[C]; n_blocks x block; vec_weighting_proj [1][C]+[1];
+ *            pre_auto_proj [C][C]+[C]; post_auto_proj [2S+1][C]+[2S+1];
+ * with block = res.norm1 g b; res.conv1; res.norm2 g b; res.conv2; attn.norm g b; attn.q; attn.k; attn.v; attn.proj_out
+ * (the block layout of mmb_absorb_head_create).
+ */
+typedef struct MmbTransHeads MmbTransHeads;
+size_t mmb_trans_packed_floats(const MmbTransDims* dims);
+int mmb_trans_create(const MmbTransDims* dims, const float* packed, size_t n_floats, int device, MmbTransHeads** out);
+void mmb_trans_destroy(MmbTransHeads* heads);
+
+/*
+ * One network evaluation = EpsilonPrecond.forward(st_batch, ts, predict='eps', forward_rate, nearest_atom)
+ * (transdimensional_model.py:124-133 -> :245-426), including StructuredDataBatch.
+ * from_st_batch_to_multimodal_bridge_databatch (structure.py:226-250: tokens = argmax of the one-hot block after
+ * F.softmax WITHOUT dim, i.e. over the BATCH axis of the 3-D tensor; prefix mask from dims).
+ *   x [B,N,3], onehot [B,N,S] (the latent tuple_batch), dims [B] int32 (1..N), ts [B];
+ *   nearest_in [B] int32, or NULL to sample it from softmax(near_atom_logits) over all N slots with the
+ *   uniform u_nearest [B] (inverse CDF; replaces rnd.multinomial, transdimensional_model.py:335-339);
+ *   trunk: an MmbEpicModel created with disc_head_hidden = 0 (fc_layer is constructed but never applied).
+ * Outputs: d_xt [B, N*(3+S)] (all continuous slots, then all one-hot slots, :277-280), rate [B],
+ *   auto_mean / auto_std [B, N*(3+S)] (zero outside slot `dims`; NULL = skip), x0_dim_logits [B,R],
+ *   near_atom_logits [B,N], nearest_out [B] int32 (NULL = skip).
+ */
+size_t mmb_trans_forward_workspace_bytes(const MmbEpicModel* trunk, const MmbTransHeads* heads, int B, int N);
+int mmb_trans_forward(const MmbEpicModel* trunk, const MmbTransHeads* heads,
+                      const float* x, const float* onehot, const int32_t* dims, const float* ts,
+                      const int32_t* nearest_in, const float* u_nearest, const MmbForwardRate* forward_rate,
+                      int B, int N,
+                      float* d_xt, float* rate, float* auto_mean, float* auto_std, float* x0_dim_logits,
+                      float* near_atom_logits, int32_t* nearest_out,
+                      void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/*
+ * JumpSampler.sample (mp/models/generative/transdimensional/sampler.py:157-324; live subset: uniform dt, no corrector,
+ * no conditioning, sample_near_atom) — reverse VP-SDE Euler-Maruyama on the flat latents with a birth jump per step.
+ * The per-step scalars are a host table computed with torch fp32 ops in the reference's order (all jets share ts):
+ *   ts, c_decay = 2 - sqrt(1 - beta dt), c_score = beta dt, c_noise = sqrt(beta dt) (0 where the reference adds no
+ *   noise: no_noise_final_step), inv_std = 1/clamp(std(ts), 1e-3), jump_dt = dt.
+ * State in/out: x [B,N,3], onehot [B,N,S], dims [B] int32 — the caller initialises them like sampler.py:170-183
+ * (x_T ~ N(0,I), dims = 1, delete_dims, adjust_st_batch) or passes any intermediate state.
+ * Noise: either injected (device pointers; parity runs)
+ *   z_diff [n_steps][B][N*(3+S)] (rnd.randn_like(xt)), u_near [n_steps][B], u_jump [n_steps][B],
+ *   z_new [n_steps][B][3+S] (the draw that lands in the new slot),
+ * or all NULL: in-kernel Philox4x32-10 keyed by (seed, jet_offset + jet, step, element) + Box-Muller.
+ */
+typedef struct MmbJumpSchedule {
+    int32_t n_steps;
+    const float* ts;       /* HOST [n_steps] */
+    const float* c_decay;  /* HOST [n_steps] */
+    const float* c_score;  /* HOST [n_steps] */
+    const float* c_noise;  /* HOST [n_steps] */
+    const float* inv_std;  /* HOST [n_steps] */
+    float jump_dt;
+} MmbJumpSchedule;
+size_t mmb_trans_sample_workspace_bytes(const MmbEpicModel* trunk, const MmbTransHeads* heads, int B, int N);
+int mmb_trans_sample(const MmbEpicModel* trunk, const MmbTransHeads* heads, float* x, float* onehot, int32_t* dims,
+                     const MmbJumpSchedule* schedule, const MmbForwardRate* forward_rate,
+                     const float* z_diff, const float* u_near, const float* u_jump, const float* z_new,
+                     uint64_t seed, uint64_t jet_offset, int B, int N,
+                     void* workspace, size_t workspace_bytes, int precision, void* stream);
+/* one sampler update alone (sampler.py:221-255 + adjust_st_batch, jets_dataloader.py:433-478): the fused,
+ * HBM-bound kernel of the loop.  v [B,N,3], logits [B,N,S] are the two halves of D_xt; new_mean/new_std [B][3+S]
+ * the compact mean/std of the slot a birth fills; step selects the Philox counters when the noise pointers are NULL. */
+int mmb_trans_sampler_update(float* x, float* onehot, int32_t* dims, const float* v, const float* logits, const float* rate,
+                             const float* new_mean, const float* new_std,
+                             float c_decay, float c_score, float c_noise, float inv_std, float jump_dt,
+                             const float* z_diff, const float* u_jump, const float* z_new,
+                             uint64_t seed, uint64_t jet_offset, int step, int B, int N, int S, void* stream);
+
 /*
  * Validation histograms of a generated batch, ACCUMULATED into counts (caller zeroes it): the
  * per-GPU buffer that the multi-GPU layer all-reduces.  Layout of counts (uint64):

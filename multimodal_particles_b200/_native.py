@@ -37,6 +37,36 @@ class EpicDims(ctypes.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class TransDims(ctypes.Structure):
+    """ctypes image of ``MmbTransDims``."""
+
+    _fields_ = [(n, ctypes.c_int32) for n in ("hidden", "vocab_size", "transformer_dim", "n_heads", "n_blocks", "max_particles")]
+
+
+class ForwardRate(ctypes.Structure):
+    """ctypes image of ``MmbForwardRate`` (kind 0 = step, 1 = const)."""
+
+    _fields_ = [("kind", ctypes.c_int32), ("scalar", ctypes.c_float), ("offset", ctypes.c_float), ("rate_cut_t", ctypes.c_float)]
+
+
+_fptr = ctypes.POINTER(ctypes.c_float)
+
+
+class JumpSchedule(ctypes.Structure):
+    """ctypes image of ``MmbJumpSchedule``; keeps the numpy arrays it points into alive."""
+
+    _fields_ = [("n_steps", ctypes.c_int32), ("ts", _fptr), ("c_decay", _fptr), ("c_score", _fptr), ("c_noise", _fptr),
+                ("inv_std", _fptr), ("jump_dt", ctypes.c_float)]
+
+    @classmethod
+    def from_schedule(cls, sched):
+        import numpy as np
+        keep = [np.ascontiguousarray(getattr(sched, n), dtype=np.float32) for n in ("ts", "c_decay", "c_score", "c_noise", "inv_std")]
+        out = cls(int(sched.n_steps), *[a.ctypes.data_as(_fptr) for a in keep], float(sched.jump_dt))
+        out._keep = keep
+        return out
+
+
 _lib = None
 
 # name -> (restype, argtypes); lists every symbol include/mmbridge.h declares
@@ -59,6 +89,17 @@ SIGNATURES = {
     "mmb_generate_absorbing": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _vp, _vp, _u64, _u64, _i, _i,
                                     _vp, _sz, _i, _vp]),
     "mmb_validation_histograms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp]),
+    "mmb_trans_packed_floats": (_sz, [ctypes.POINTER(TransDims)]),
+    "mmb_trans_create": (_i, [ctypes.POINTER(TransDims), _vp, _sz, _i, ctypes.POINTER(_vp)]),
+    "mmb_trans_destroy": (None, [_vp]),
+    "mmb_trans_forward_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
+    "mmb_trans_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ForwardRate), _i, _i,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "mmb_trans_sample_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
+    "mmb_trans_sample": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(JumpSchedule), ctypes.POINTER(ForwardRate),
+                              _vp, _vp, _vp, _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
+    "mmb_trans_sampler_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _vp, _vp, _vp,
+                                      _u64, _u64, _i, _i, _i, _i, _vp]),
 }
 
 
@@ -217,3 +258,91 @@ def generate_absorbing(trunk: EpicModel, head: AbsorbHead, x, k_u8, mask_u8, tab
                                          _ptr(tb), _ptr(u_jump), _ptr(u_absorb), seed, jet_offset, B, N, _ptr(ws), ws.numel(),
                                          PRECISIONS[precision], _stream()))
     return x, k_u8, mask_u8
+
+
+# ---- trans-dimensional jump diffusion -----------------------------------------------------------------
+class TransHeads:
+    """Owner of one ``MmbTransHeads*`` (device-resident transformer stacks of TransdimensionalEPiC)."""
+
+    def __init__(self, dims: TransDims, packed: torch.Tensor, device):
+        lib = load()
+        packed = packed.detach().to("cpu", torch.float32).contiguous()
+        expect = lib.mmb_trans_packed_floats(ctypes.byref(dims))
+        if packed.numel() != expect:
+            raise MmbError(f"packed trans-heads blob has {packed.numel()} floats, layout wants {expect}")
+        self.dims, self.device = dims, torch.device(device)
+        self._handle = ctypes.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(lib.mmb_trans_create(ctypes.byref(dims), _ptr(packed), packed.numel(), index, ctypes.byref(self._handle)))
+
+    def __del__(self):
+        if getattr(self, "_handle", None) and _lib is not None:
+            _lib.mmb_trans_destroy(self._handle)
+            self._handle = None
+
+
+def _i32(t, device):
+    return None if t is None else t.to(device=device, dtype=torch.int32).contiguous()
+
+
+def _f32(t, device):
+    return None if t is None else t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def trans_forward(trunk: EpicModel, heads: TransHeads, x, onehot, dims, ts, nearest_in, u_nearest, forward_rate: ForwardRate,
+                  precision="bf16", want_auto=True):
+    """One TransdimensionalEPiC evaluation on device tensors -> namespace(d_xt, rate, auto_mean, auto_std, x0_dim_logits,
+    near_atom_logits, nearest)."""
+    from types import SimpleNamespace
+    dev = x.device
+    x, onehot = _f32(x, dev), _f32(onehot, dev)
+    _require_cuda(x, onehot)
+    B, N, _ = x.shape
+    S, R = heads.dims.vocab_size, heads.dims.max_particles
+    F = 3 + S
+    dims, ts, nearest_in, u_nearest = _i32(dims, dev), _f32(ts, dev), _i32(nearest_in, dev), _f32(u_nearest, dev)
+    new = lambda *shape, dtype=torch.float32: torch.empty(*shape, device=dev, dtype=dtype)
+    out = SimpleNamespace(d_xt=new(B, N * F), rate=new(B), auto_mean=new(B, N * F) if want_auto else None,
+                          auto_std=new(B, N * F) if want_auto else None, x0_dim_logits=new(B, R), near_atom_logits=new(B, N),
+                          nearest=new(B, dtype=torch.int32))
+    lib = load()
+    need = lib.mmb_trans_forward_workspace_bytes(trunk._handle, heads._handle, B, N)
+    ws = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        check(lib.mmb_trans_forward(trunk._handle, heads._handle, _ptr(x), _ptr(onehot), _ptr(dims), _ptr(ts), _ptr(nearest_in),
+                                    _ptr(u_nearest), ctypes.byref(forward_rate), B, N, _ptr(out.d_xt), _ptr(out.rate),
+                                    _ptr(out.auto_mean), _ptr(out.auto_std), _ptr(out.x0_dim_logits), _ptr(out.near_atom_logits),
+                                    _ptr(out.nearest), _ptr(ws), ws.numel(), PRECISIONS[precision], _stream()))
+    return out
+
+
+def trans_sample(trunk: EpicModel, heads: TransHeads, x, onehot, dims, sched, forward_rate: ForwardRate, noise=None, seed=0,
+                 jet_offset=0, precision="bf16"):
+    """In-place JumpSampler loop on x [B,N,3], onehot [B,N,S], dims [B] int32 (device)."""
+    _require_cuda(x, onehot, dims)
+    assert dims.dtype == torch.int32
+    B, N, _ = x.shape
+    dev = x.device
+    get = lambda name: _f32(getattr(noise, name), dev) if noise is not None else None
+    z_diff, u_near, u_jump, z_new = get("z_diff"), get("u_near"), get("u_jump"), get("z_new")
+    lib = load()
+    need = lib.mmb_trans_sample_workspace_bytes(trunk._handle, heads._handle, B, N)
+    ws = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
+    csched = JumpSchedule.from_schedule(sched)
+    with torch.cuda.device(dev):
+        check(lib.mmb_trans_sample(trunk._handle, heads._handle, _ptr(x), _ptr(onehot), _ptr(dims), ctypes.byref(csched),
+                                   ctypes.byref(forward_rate), _ptr(z_diff), _ptr(u_near), _ptr(u_jump), _ptr(z_new), seed,
+                                   jet_offset, B, N, _ptr(ws), ws.numel(), PRECISIONS[precision], _stream()))
+    return x, onehot, dims
+
+
+def trans_sampler_update(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score, c_noise, inv_std, jump_dt,
+                         z_diff=None, u_jump=None, z_new=None, seed=0, jet_offset=0, step=0):
+    """One fused sampler update in place (the HBM-bound kernel of the loop)."""
+    _require_cuda(x, onehot, dims, v, logits, rate, new_mean, new_std, z_diff, u_jump, z_new)
+    B, N, _ = x.shape
+    S = onehot.shape[-1]
+    with torch.cuda.device(x.device):
+        check(load().mmb_trans_sampler_update(_ptr(x), _ptr(onehot), _ptr(dims), _ptr(v), _ptr(logits), _ptr(rate), _ptr(new_mean),
+                                              _ptr(new_std), c_decay, c_score, c_noise, inv_std, jump_dt, _ptr(z_diff), _ptr(u_jump),
+                                              _ptr(z_new), seed, jet_offset, step, B, N, S, _stream()))

@@ -396,6 +396,69 @@ static void linear_rows(const float* in, float* out, const float* W, const float
             out[(size_t)n * Cout + o] = dot_from(b[o], W + (size_t)o * Cin, in + (size_t)n * Cin, Cin);
 }
 
+typedef struct { float *t1, *t2, *q, *kk, *vv, *sc; } TfScratch;
+static TfScratch tf_scratch_new(int N, int C) {
+    TfScratch s;
+    s.t1 = (float*)malloc(sizeof(float) * (size_t)N * C);
+    s.t2 = (float*)malloc(sizeof(float) * (size_t)N * C);
+    s.q = (float*)malloc(sizeof(float) * (size_t)N * C);
+    s.kk = (float*)malloc(sizeof(float) * (size_t)N * C);
+    s.vv = (float*)malloc(sizeof(float) * (size_t)N * C);
+    s.sc = (float*)malloc(sizeof(float) * (size_t)N);
+    return s;
+}
+static void tf_scratch_free(TfScratch* s) { free(s->t1); free(s->t2); free(s->q); free(s->kk); free(s->vv); free(s->sc); }
+
+/* n_blocks x (ResnetBlock, AttnBlock) on x [N][C] in place (gsdm.py:54-66,142-168); tb [n_blocks][C] is the
+ * temb_proj(swish(temb)) term of each ResnetBlock.  Returns the blob pointer after the last block. */
+static const float* tf_blocks(const float* p, float* x, const float* tb_all, int N, int C, int n_heads, int n_blocks, TfScratch* s) {
+    const size_t lin = (size_t)C * C + C;
+    float *t1 = s->t1, *t2 = s->t2, *q = s->q, *kk = s->kk, *vv = s->vv, *sc = s->sc;
+    const int dh = C / n_heads;
+    const float scale = 1.0f / sqrtf((float)dh);
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        const float *n1g = p, *n1b = p + C, *c1 = p + 2 * C, *n2g = c1 + lin, *n2b = n2g + C, *c2 = n2b + C,
+                    *ng = c2 + lin, *nb = ng + C, *wq = nb + C, *wk = wq + lin, *wv = wk + lin, *wo = wv + lin;
+        p = wo + lin;
+        const float* tb = tb_all + (size_t)blk * C;
+        /* ResnetBlock (gsdm.py:54-66) */
+        group_norm(x, t1, n1g, n1b, N, C);
+        for (size_t i = 0; i < (size_t)N * C; ++i) t1[i] = swishf(t1[i]);
+        linear_rows(t1, t2, c1, c1 + (size_t)C * C, N, C, C);
+        for (int n = 0; n < N; ++n)
+            for (int c = 0; c < C; ++c) t2[(size_t)n * C + c] += tb[c];
+        group_norm(t2, t1, n2g, n2b, N, C);
+        for (size_t i = 0; i < (size_t)N * C; ++i) t1[i] = swishf(t1[i]);
+        linear_rows(t1, t2, c2, c2 + (size_t)C * C, N, C, C);
+        for (size_t i = 0; i < (size_t)N * C; ++i) x[i] += t2[i];
+        /* AttnBlock (gsdm.py:142-168): all N slots attend to all N slots, no padding mask */
+        group_norm(x, t1, ng, nb, N, C);
+        linear_rows(t1, q, wq, wq + (size_t)C * C, N, C, C);
+        linear_rows(t1, kk, wk, wk + (size_t)C * C, N, C, C);
+        linear_rows(t1, vv, wv, wv + (size_t)C * C, N, C, C);
+        for (int h = 0; h < n_heads; ++h)
+            for (int qi = 0; qi < N; ++qi) {
+                float mx = -INFINITY;
+                for (int ki = 0; ki < N; ++ki) {
+                    float a = dot_from(0.0f, kk + (size_t)ki * C + h * dh, q + (size_t)qi * C + h * dh, dh) * scale;
+                    sc[ki] = a;
+                    mx = a > mx ? a : mx;
+                }
+                float z = 0.0f;
+                for (int ki = 0; ki < N; ++ki) { sc[ki] = mmbo_expf(sc[ki] - mx); z += sc[ki]; }
+                const float zi = 1.0f / z;
+                for (int d = 0; d < dh; ++d) {
+                    float acc = 0.0f;
+                    for (int ki = 0; ki < N; ++ki) acc = fmaf(vv[(size_t)ki * C + h * dh + d], sc[ki] * zi, acc);
+                    t2[(size_t)qi * C + h * dh + d] = acc;
+                }
+            }
+        linear_rows(t2, t1, wo, wo + (size_t)C * C, N, C, C);
+        for (size_t i = 0; i < (size_t)N * C; ++i) x[i] += t1[i];
+    }
+    return p;
+}
+
 void mmbo_absorb_head(const float* W, int H, int C, int n_heads, int n_blocks,
                       const float* hidden, const uint8_t* mask, const float* tbias, int tbias_stride,
                       int B, int N, float* logit_out) {
@@ -403,12 +466,7 @@ void mmbo_absorb_head(const float* W, int H, int C, int n_heads, int n_blocks,
 #pragma omp parallel
     {
         float* x = (float*)malloc(sizeof(float) * (size_t)N * C);
-        float* t1 = (float*)malloc(sizeof(float) * (size_t)N * C);
-        float* t2 = (float*)malloc(sizeof(float) * (size_t)N * C);
-        float* q = (float*)malloc(sizeof(float) * (size_t)N * C);
-        float* kk = (float*)malloc(sizeof(float) * (size_t)N * C);
-        float* vv = (float*)malloc(sizeof(float) * (size_t)N * C);
-        float* sc = (float*)malloc(sizeof(float) * (size_t)N);
+        TfScratch s = tf_scratch_new(N, C);
         float* in0 = (float*)malloc(sizeof(float) * (size_t)(H + 2));
 #pragma omp for schedule(dynamic, 1)
         for (int b = 0; b < B; ++b) {
@@ -422,55 +480,360 @@ void mmbo_absorb_head(const float* W, int H, int C, int n_heads, int n_blocks,
                     x[(size_t)n * C + o] = dot_from(p[(size_t)C * (H + 2) + o], p + (size_t)o * (H + 2), in0, H + 2);
             }
             p += (size_t)C * (H + 2) + C;
-            const int dh = C / n_heads;
-            const float scale = 1.0f / sqrtf((float)dh);
-            for (int blk = 0; blk < n_blocks; ++blk) {
-                const float *n1g = p, *n1b = p + C, *c1 = p + 2 * C, *n2g = c1 + lin, *n2b = n2g + C, *c2 = n2b + C,
-                            *ng = c2 + lin, *nb = ng + C, *wq = nb + C, *wk = wq + lin, *wv = wk + lin, *wo = wv + lin;
-                p = wo + lin;
-                const float* tb = tbias + (size_t)b * tbias_stride + (size_t)blk * C;
-                /* ResnetBlock (gsdm.py:54-66) */
-                group_norm(x, t1, n1g, n1b, N, C);
-                for (size_t i = 0; i < (size_t)N * C; ++i) t1[i] = swishf(t1[i]);
-                linear_rows(t1, t2, c1, c1 + (size_t)C * C, N, C, C);
-                for (int n = 0; n < N; ++n)
-                    for (int c = 0; c < C; ++c) t2[(size_t)n * C + c] += tb[c];
-                group_norm(t2, t1, n2g, n2b, N, C);
-                for (size_t i = 0; i < (size_t)N * C; ++i) t1[i] = swishf(t1[i]);
-                linear_rows(t1, t2, c2, c2 + (size_t)C * C, N, C, C);
-                for (size_t i = 0; i < (size_t)N * C; ++i) x[i] += t2[i];
-                /* AttnBlock (gsdm.py:142-168): all N slots attend to all N slots, no padding mask */
-                group_norm(x, t1, ng, nb, N, C);
-                linear_rows(t1, q, wq, wq + (size_t)C * C, N, C, C);
-                linear_rows(t1, kk, wk, wk + (size_t)C * C, N, C, C);
-                linear_rows(t1, vv, wv, wv + (size_t)C * C, N, C, C);
-                for (int h = 0; h < n_heads; ++h)
-                    for (int qi = 0; qi < N; ++qi) {
-                        float mx = -INFINITY;
-                        for (int ki = 0; ki < N; ++ki) {
-                            float a = dot_from(0.0f, kk + (size_t)ki * C + h * dh, q + (size_t)qi * C + h * dh, dh) * scale;
-                            sc[ki] = a;
-                            mx = a > mx ? a : mx;
-                        }
-                        float z = 0.0f;
-                        for (int ki = 0; ki < N; ++ki) { sc[ki] = mmbo_expf(sc[ki] - mx); z += sc[ki]; }
-                        const float zi = 1.0f / z;
-                        for (int d = 0; d < dh; ++d) {
-                            float acc = 0.0f;
-                            for (int ki = 0; ki < N; ++ki) acc = fmaf(vv[(size_t)ki * C + h * dh + d], sc[ki] * zi, acc);
-                            t2[(size_t)qi * C + h * dh + d] = acc;
-                        }
-                    }
-                linear_rows(t2, t1, wo, wo + (size_t)C * C, N, C, C);
-                for (size_t i = 0; i < (size_t)N * C; ++i) x[i] += t1[i];
-            }
+            p = tf_blocks(p, x, tbias + (size_t)b * tbias_stride, N, C, n_heads, n_blocks, &s);
             /* pre_rate_proj, post_rate_proj (absorbing_flows.py:127-131) */
-            linear_rows(x, t1, p, p + (size_t)C * C, N, C, C);
+            linear_rows(x, s.t1, p, p + (size_t)C * C, N, C, C);
             p += lin;
-            for (int n = 0; n < N; ++n) logit_out[(size_t)b * N + n] = dot_from(p[C], p, t1 + (size_t)n * C, C);
+            for (int n = 0; n < N; ++n) logit_out[(size_t)b * N + n] = dot_from(p[C], p, s.t1 + (size_t)n * C, C);
         }
-        free(x); free(t1); free(t2); free(q); free(kk); free(vv); free(sc); free(in0);
+        free(x); free(in0); tf_scratch_free(&s);
     }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Trans-dimensional jump diffusion: TransdimensionalEPiC.forward + JumpSampler.sample
+ * (mp/models/generative/transdimensional/transdimensional_model.py:245-426, sampler.py:157-324,
+ *  structure.py:226-250, mp/models/generative/diffusion/noising.py:15-39,123-216,
+ *  mp/data/particle_clouds/jets_dataloader.py:380-478). */
+size_t mmbo_trans_floats(const MmbTransDims* d) {
+    const size_t C = d->transformer_dim, lin = C * C + C, nrm = 2 * C, H = d->hidden, S = d->vocab_size, R = d->max_particles;
+    const size_t block = 3 * nrm + 6 * lin;
+    return lin + 2 * (size_t)d->n_blocks * lin
+         + (C * (H + S) + C) + d->n_blocks * block + lin + (R * C + R) + (C + 1)
+         + (C * (H + S + 3) + C) + d->n_blocks * block + (C + 1) + lin + ((2 * S + 1) * C + (2 * S + 1));
+}
+
+/* tokens = argmax_s softmax_BATCH(onehot)[b,n,s]: F.softmax without dim on a 3-D tensor normalises over
+ * dim 0 (structure.py:231-232).  Column sums in the order the kernel uses: 8 partial sums over b mod 8
+ * (ascending b), then a balanced tree. */
+void mmbo_trans_tokens(const float* onehot, int B, int N, int S, uint8_t* k) {
+    const int NS = N * S;
+    float* M = (float*)malloc(sizeof(float) * (size_t)NS);
+    float* Z = (float*)malloc(sizeof(float) * (size_t)NS);
+    for (int c = 0; c < NS; ++c) {
+        float mx = -INFINITY;
+        for (int b = 0; b < B; ++b) { float a = onehot[(size_t)b * NS + c]; mx = a > mx ? a : mx; }
+        float part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int b = 0; b < B; ++b) part[b & 7] = part[b & 7] + mmbo_expf(onehot[(size_t)b * NS + c] - mx);
+        M[c] = mx;
+        Z[c] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+    }
+    for (int b = 0; b < B; ++b)
+        for (int n = 0; n < N; ++n) {
+            int best = 0; float bp = -1.0f;
+            for (int s2 = 0; s2 < S; ++s2) {
+                const int c = n * S + s2;
+                const float pr = mmbo_expf(onehot[(size_t)b * NS + c] - M[c]) / Z[c];
+                if (pr > bp) { bp = pr; best = s2; }
+            }
+            k[(size_t)b * N + n] = (uint8_t)best;
+        }
+    free(M); free(Z);
+}
+
+/* per-jet time terms: EPiC sinusoidal embedding of ts (utils.py:183-198) and, for both stacks,
+ * temb_proj_blk(swish(temb_net(get_timestep_embedding(1000 ts, C)))) (gsdm.py:8-26,58; model :288-290) */
+void mmbo_trans_time_terms(const MmbTransDims* d, const float* W, const float* ts, int B, int T,
+                           float* temb_epic /*[B][T]*/, float* tb1 /*[B][n_blocks][C]*/, float* tb2) {
+    const int C = d->transformer_dim, half = C / 2, nb = d->n_blocks;
+    const size_t lin = (size_t)C * C + C;
+    float* e = (float*)malloc(sizeof(float) * C);
+    float* t = (float*)malloc(sizeof(float) * C);
+    for (int b = 0; b < B; ++b) {
+        const int h2 = T / 2;
+        for (int j = 0; j < h2; ++j) {
+            float f = expf((float)(-log(10000.0)) * (float)j / (float)h2);
+            float a = ts[b] * f;
+            temb_epic[(size_t)b * T + j] = cosf(a);
+            temb_epic[(size_t)b * T + h2 + j] = sinf(a);
+        }
+        if (T % 2) temb_epic[(size_t)b * T + T - 1] = 0.0f;
+        const float tt = ts[b] * 1000.0f;
+        const float fe = (float)(log(10000.0) / (double)(half - 1));
+        for (int j = 0; j < half; ++j) {
+            float f = expf((float)j * -fe);
+            e[j] = sinf(tt * f);
+            e[half + j] = cosf(tt * f);
+        }
+        if (C % 2) e[C - 1] = 0.0f;
+        for (int o = 0; o < C; ++o) t[o] = swishf(dot_from(W[(size_t)C * C + o], W + (size_t)o * C, e, C));
+        for (int st = 0; st < 2; ++st)
+            for (int blk = 0; blk < nb; ++blk) {
+                const float* P = W + lin + ((size_t)st * nb + blk) * lin;
+                float* out = (st ? tb2 : tb1) + ((size_t)b * nb + blk) * C;
+                for (int o = 0; o < C; ++o) out[o] = dot_from(P[(size_t)C * C + o], P + (size_t)o * C, t, C);
+            }
+    }
+    free(e); free(t);
+}
+
+static float fr_rate(const MmbForwardRate* fr, float t) {
+    if (fr->kind == 1) return fr->scalar;
+    return fr->scalar * (t > fr->rate_cut_t ? 1.0f : 0.0f) + fr->offset;
+}
+static float fr_integral(const MmbForwardRate* fr, float t) {
+    if (fr->kind == 1) return fr->scalar * t;
+    return (t - fr->rate_cut_t) * fr->scalar * (t > fr->rate_cut_t ? 1.0f : 0.0f) + fr->offset * t;
+}
+static float poisson_logp(float k, float lam) { return (k == 0.0f ? 0.0f : k * logf(lam)) - lam - lgammaf(k + 1.0f); }
+
+/* get_rate_using_x0_pred (noising.py:166-216) for one jet */
+float mmbo_trans_rate(const float* logits, int R, int xt_dim, const MmbForwardRate* fr, float t) {
+    const float I = fr_integral(fr, t);
+    float mx = -INFINITY, z = 0.0f, acc = 0.0f;
+    for (int i = xt_dim - 1; i < R; ++i) mx = logits[i] > mx ? logits[i] : mx;
+    for (int i = xt_dim - 1; i < R; ++i) z += mmbo_expf(logits[i] - mx);
+    for (int i = xt_dim - 1; i < R; ++i) {
+        const float prob = mmbo_expf(logits[i] - mx) / z;
+        float ratio;
+        if (xt_dim > 1) {
+            ratio = (1.0f / I) * (float)((i + 1) - xt_dim);
+            if (ratio < 0.0f) ratio = 0.0f;
+        } else {
+            float m2 = -INFINITY;
+            const int trunc = 2 * R;
+            for (int j = 0; j < trunc; ++j) { float lp = poisson_logp((float)(i + j), I); m2 = lp > m2 ? lp : m2; }
+            float se = 0.0f;
+            for (int j = 0; j < trunc; ++j) se += expf(poisson_logp((float)(i + j), I) - m2);
+            const float dim1 = m2 + logf(se);
+            const float dim2 = i == 0 ? -1000.0f : poisson_logp((float)(i - 1 > 0 ? i - 1 : 0), I);
+            ratio = expf(dim2 - dim1);
+        }
+        acc += ratio * prob;
+    }
+    return fr_rate(fr, t) * acc;
+}
+
+static inline float softplusf(float a) { return a > 20.0f ? a : log1pf(expf(a)); }
+
+void mmbo_trans_forward(const MmbEpicDims* ed, const float* epacked, const MmbTransDims* d, const float* W,
+                        const float* x, const float* onehot, const int32_t* dims, const float* ts,
+                        const int32_t* nearest_in, const float* u_nearest, const MmbForwardRate* fr, int B, int N,
+                        float* d_xt, float* rate, float* auto_mean, float* auto_std, float* x0_dim_logits,
+                        float* near_atom_logits, int32_t* nearest_out, float* new_mean, float* new_std) {
+    const int C = d->transformer_dim, H = d->hidden, S = d->vocab_size, R = d->max_particles, nb = d->n_blocks, T = ed->dim_time_emb;
+    const int F = 3 + S;
+    const size_t lin = (size_t)C * C + C, block = 6 * (size_t)C + 6 * lin;
+    uint8_t* k = (uint8_t*)malloc((size_t)B * N);
+    uint8_t* mask = (uint8_t*)malloc((size_t)B * N);
+    float* temb = (float*)malloc(sizeof(float) * (size_t)B * T);
+    float* tb1 = (float*)malloc(sizeof(float) * (size_t)B * nb * C);
+    float* tb2 = (float*)malloc(sizeof(float) * (size_t)B * nb * C);
+    float* v = (float*)malloc(sizeof(float) * (size_t)B * N * 3);
+    float* lg = (float*)malloc(sizeof(float) * (size_t)B * N * S);
+    float* hid = (float*)malloc(sizeof(float) * (size_t)B * N * H);
+    mmbo_trans_tokens(onehot, B, N, S, k);
+    for (int b = 0; b < B; ++b)
+        for (int n = 0; n < N; ++n) mask[(size_t)b * N + n] = n < dims[b];
+    mmbo_trans_time_terms(d, W, ts, B, T, temb, tb1, tb2);
+    mmbo_epic_forward(ed, epacked, x, k, mask, temb, T, B, N, v, lg, hid);
+    /* D_xt: all continuous slots, then all one-hot slots (model :277-280) */
+    for (int b = 0; b < B; ++b) {
+        memcpy(d_xt + (size_t)b * N * F, v + (size_t)b * N * 3, sizeof(float) * (size_t)N * 3);
+        memcpy(d_xt + (size_t)b * N * F + (size_t)N * 3, lg + (size_t)b * N * S, sizeof(float) * (size_t)N * S);
+    }
+    const float* s1 = W + lin + 2 * (size_t)nb * lin;
+    const size_t in1 = H + S, in2 = H + S + 3;
+    const float* s1_blocks = s1 + (size_t)C * in1 + C;
+    const float* pre_rate = s1_blocks + (size_t)nb * block;
+    const float* post_rate = pre_rate + lin;
+    const float* near_w = post_rate + (size_t)R * C + R;
+    const float* s2 = near_w + C + 1;
+    const float* s2_blocks = s2 + (size_t)C * in2 + C;
+    const float* vecw = s2_blocks + (size_t)nb * block;
+    const float* pre_auto = vecw + C + 1;
+    const float* post_auto = pre_auto + lin;
+    const int PA = 2 * S + 1;
+#pragma omp parallel
+    {
+        float* h = (float*)malloc(sizeof(float) * (size_t)N * C);
+        float* in = (float*)malloc(sizeof(float) * (in2 + 1));
+        float* emb = (float*)malloc(sizeof(float) * (size_t)C);
+        float* pa = (float*)malloc(sizeof(float) * (size_t)PA);
+        float* vw = (float*)malloc(sizeof(float) * (size_t)N);
+        TfScratch s = tf_scratch_new(N, C);
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < B; ++b) {
+            const float* xb = x + (size_t)b * N * 3;
+            const float* ob = onehot + (size_t)b * N * S;
+            const float* hb = hid + (size_t)b * N * H;
+            const uint8_t* mb = mask + (size_t)b * N;
+            /* ---- rate / nearest-particle stack (model :295-334): inputs NOT masked */
+            for (int n = 0; n < N; ++n) {
+                for (int i = 0; i < H; ++i) in[i] = hb[(size_t)n * H + i];
+                for (int i = 0; i < S; ++i) in[H + i] = ob[(size_t)n * S + i];
+                for (int o = 0; o < C; ++o) h[(size_t)n * C + o] = dot_from(s1[(size_t)C * in1 + o], s1 + (size_t)o * in1, in, (int)in1);
+            }
+            tf_blocks(s1_blocks, h, tb1 + (size_t)b * nb * C, N, C, d->n_heads, nb, &s);
+            linear_rows(h, s.t1, pre_rate, pre_rate + (size_t)C * C, N, C, C);
+            for (int c = 0; c < C; ++c) {
+                float acc = 0.0f;
+                for (int n = 0; n < N; ++n) acc += s.t1[(size_t)n * C + c];
+                emb[c] = acc / (float)N;
+            }
+            float* xl = x0_dim_logits + (size_t)b * R;
+            for (int r = 0; r < R; ++r) xl[r] = dot_from(post_rate[(size_t)R * C + r], post_rate + (size_t)r * C, emb, C);
+            rate[b] = mmbo_trans_rate(xl, R, dims[b], fr, ts[b]);
+            float* nl = near_atom_logits + (size_t)b * N;
+            for (int n = 0; n < N; ++n) nl[n] = dot_from(near_w[C], near_w, h + (size_t)n * C, C);
+            int near;
+            if (nearest_in) near = nearest_in[b];
+            else {  /* multinomial(softmax(near_atom_logits)) over ALL N slots, by inverse CDF on one uniform */
+                float mx = -INFINITY, z = 0.0f, c = 0.0f;
+                for (int n = 0; n < N; ++n) mx = nl[n] > mx ? nl[n] : mx;
+                for (int n = 0; n < N; ++n) z += mmbo_expf(nl[n] - mx);
+                near = N - 1;
+                for (int n = 0; n < N; ++n) {
+                    c += mmbo_expf(nl[n] - mx) / z;
+                    if (u_nearest[b] < c) { near = n; break; }
+                }
+            }
+            if (nearest_out) nearest_out[b] = near;
+            /* ---- vector stack (model :341-409): inputs masked */
+            const float xa0 = xb[near * 3], xa1 = xb[near * 3 + 1], xa2 = xb[near * 3 + 2];
+            for (int n = 0; n < N; ++n) {
+                const float m = mb[n] ? 1.0f : 0.0f;
+                const float d0 = xa0 - xb[n * 3], d1 = xa1 - xb[n * 3 + 1], d2 = xa2 - xb[n * 3 + 2];
+                for (int i = 0; i < H; ++i) in[i] = hb[(size_t)n * H + i] * m;
+                for (int i = 0; i < S; ++i) in[H + i] = ob[(size_t)n * S + i] * m;
+                in[H + S] = sqrtf((d0 * d0 + d1 * d1) + d2 * d2) * m;
+                in[H + S + 1] = (n == near ? 1.0f : 0.0f) * m;
+                in[H + S + 2] = (n == near ? 0.0f : 1.0f) * m;
+                for (int o = 0; o < C; ++o) h[(size_t)n * C + o] = dot_from(s2[(size_t)C * in2 + o], s2 + (size_t)o * in2, in, (int)in2);
+            }
+            tf_blocks(s2_blocks, h, tb2 + (size_t)b * nb * C, N, C, d->n_heads, nb, &s);
+            float pm0 = 0.0f, pm1 = 0.0f, pm2 = 0.0f;
+            for (int n = 0; n < N; ++n) {
+                const float w = dot_from(vecw[C], vecw, h + (size_t)n * C, C);
+                const float m = mb[n] ? 1.0f : 0.0f;
+                float d0 = (xa0 - xb[n * 3]) * m, d1 = (xa1 - xb[n * 3 + 1]) * m, d2 = (xa2 - xb[n * 3 + 2]) * m;
+                const float nr = sqrtf((d0 * d0 + d1 * d1) + d2 * d2) + 1e-3f;
+                pm0 += w * (d0 / nr); pm1 += w * (d1 / nr); pm2 += w * (d2 / nr);
+            }
+            pm0 = xa0 + pm0; pm1 = xa1 + pm1; pm2 = xa2 + pm2;
+            linear_rows(h, s.t1, pre_auto, pre_auto + (size_t)C * C, N, C, C);
+            for (int c = 0; c < C; ++c) {
+                float acc = 0.0f;
+                for (int n = 0; n < N; ++n) acc += s.t1[(size_t)n * C + c];
+                emb[c] = acc / (float)N;
+            }
+            for (int r = 0; r < PA; ++r) pa[r] = dot_from(post_auto[(size_t)PA * C + r], post_auto + (size_t)r * C, emb, C);
+            float mean11[64], std11[64];
+            mean11[0] = pm0; mean11[1] = pm1; mean11[2] = pm2;
+            std11[0] = std11[1] = std11[2] = pa[0];
+            for (int s2i = 0; s2i < S; ++s2i) { mean11[3 + s2i] = pa[1 + s2i]; std11[3 + s2i] = pa[1 + S + s2i]; }
+            if (new_mean) for (int i = 0; i < F; ++i) { new_mean[(size_t)b * F + i] = mean11[i]; new_std[(size_t)b * F + i] = std11[i]; }
+            if (auto_mean) {
+                float* am = auto_mean + (size_t)b * N * F;
+                float* as = auto_std + (size_t)b * N * F;
+                memset(am, 0, sizeof(float) * (size_t)N * F);
+                memset(as, 0, sizeof(float) * (size_t)N * F);
+                const int slot = dims[b];   /* get_next_dim_added_mask (structure.py:175-184): the slot a birth fills */
+                if (slot < N) {
+                    for (int c = 0; c < 3; ++c) { am[slot * 3 + c] = mean11[c]; as[slot * 3 + c] = std11[c]; }
+                    for (int s2i = 0; s2i < S; ++s2i) {
+                        am[(size_t)N * 3 + slot * S + s2i] = mean11[3 + s2i];
+                        as[(size_t)N * 3 + slot * S + s2i] = std11[3 + s2i];
+                    }
+                }
+            }
+        }
+        free(h); free(in); free(emb); free(pa); free(vw); tf_scratch_free(&s);
+    }
+    free(k); free(mask); free(temb); free(tb1); free(tb2); free(v); free(lg); free(hid);
+}
+
+static inline float nan_to_num(float a) { return a != a ? 0.0f : (a > 3.4028234664e38f ? 3.4028234664e38f : (a < -3.4028234664e38f ? -3.4028234664e38f : a)); }
+
+/* JetsGraphicalStructure.adjust_st_batch (jets_dataloader.py:433-478): nan_to_num, then remove the mean of the
+ * continuous features of the live particles */
+static void adjust_jet(float* x, float* oh, int dim, int N, int S) {
+    for (int i = 0; i < N * 3; ++i) x[i] = nan_to_num(x[i]);
+    for (int i = 0; i < N * S; ++i) oh[i] = nan_to_num(oh[i]);
+    const int cnt = dim == 0 ? N : dim;
+    for (int c = 0; c < 3; ++c) {
+        float acc = 0.0f;
+        for (int n = 0; n < N; ++n) acc += x[n * 3 + c];
+        const float mean = acc / (float)cnt;
+        for (int n = 0; n < cnt; ++n) x[n * 3 + c] = x[n * 3 + c] - mean;
+    }
+}
+
+/* one JumpSampler update (sampler.py:221-255) with injected noise */
+void mmbo_trans_sampler_update(float* x, float* onehot, int32_t* dims, const float* v, const float* logits, const float* rate,
+                               const float* new_mean, const float* new_std,
+                               float c_decay, float c_score, float c_noise, float inv_std, float jump_dt,
+                               const float* z_diff, const float* u_jump, const float* z_new, int B, int N, int S) {
+    const int F = 3 + S;
+    float* zc = (float*)malloc(sizeof(float) * (size_t)N * 3);
+    for (int b = 0; b < B; ++b) {
+        float* xb = x + (size_t)b * N * 3;
+        float* ob = onehot + (size_t)b * N * S;
+        const float* zb = z_diff + (size_t)b * N * F;
+        const int dim = dims[b];
+        /* noise: delete_dims + adjust_st_batch on the noise batch (sampler.py:224-229) */
+        for (int i = 0; i < N * 3; ++i) zc[i] = (i / 3) < dim ? zb[i] : 0.0f;
+        for (int c = 0; c < 3; ++c) {
+            float acc = 0.0f;
+            for (int n = 0; n < N; ++n) acc += zc[n * 3 + c];
+            const float mean = acc / (float)dim;
+            for (int n = 0; n < dim; ++n) zc[n * 3 + c] = zc[n * 3 + c] - mean;
+        }
+        for (int n = 0; n < N; ++n) {
+            const float m = n < dim ? 1.0f : 0.0f;
+            for (int c = 0; c < 3; ++c) {
+                const float score = -(inv_std * v[((size_t)b * N + n) * 3 + c]);
+                float a = c_decay * xb[n * 3 + c] + m * (c_score * score);
+                if (c_noise != 0.0f) a = a + m * (c_noise * zc[n * 3 + c]);
+                xb[n * 3 + c] = a;
+            }
+            for (int s = 0; s < S; ++s) {
+                const float score = -(inv_std * logits[((size_t)b * N + n) * S + s]);
+                float a = c_decay * ob[n * S + s] + m * (c_score * score);
+                if (c_noise != 0.0f) a = a + m * (c_noise * zb[(size_t)N * 3 + n * S + s]);
+                ob[n * S + s] = a;
+            }
+        }
+        adjust_jet(xb, ob, dim, N, S);
+        /* birth (sampler.py:238-255) */
+        if (u_jump[b] < rate[b] * jump_dt && dim < N) {
+            for (int c = 0; c < 3; ++c)
+                xb[dim * 3 + c] = new_mean[(size_t)b * F + c] + z_new[(size_t)b * F + c] * softplusf(new_std[(size_t)b * F + c]);
+            for (int s = 0; s < S; ++s)
+                ob[dim * S + s] = new_mean[(size_t)b * F + 3 + s] + z_new[(size_t)b * F + 3 + s] * softplusf(new_std[(size_t)b * F + 3 + s]);
+            dims[b] = dim + 1;
+        }
+        adjust_jet(xb, ob, dims[b], N, S);
+    }
+    free(zc);
+}
+
+void mmbo_trans_sample(const MmbEpicDims* ed, const float* epacked, const MmbTransDims* d, const float* W,
+                       float* x, float* onehot, int32_t* dims, const MmbJumpSchedule* sch, const MmbForwardRate* fr,
+                       const float* z_diff, const float* u_near, const float* u_jump, const float* z_new, int B, int N) {
+    const int S = d->vocab_size, F = 3 + S, R = d->max_particles;
+    float* dx = (float*)malloc(sizeof(float) * (size_t)B * N * F);
+    float* v = (float*)malloc(sizeof(float) * (size_t)B * N * 3);
+    float* lg = (float*)malloc(sizeof(float) * (size_t)B * N * S);
+    float* rate = (float*)malloc(sizeof(float) * (size_t)B);
+    float* xl = (float*)malloc(sizeof(float) * (size_t)B * R);
+    float* nl = (float*)malloc(sizeof(float) * (size_t)B * N);
+    float* nm = (float*)malloc(sizeof(float) * (size_t)B * F);
+    float* ns = (float*)malloc(sizeof(float) * (size_t)B * F);
+    float* ts = (float*)malloc(sizeof(float) * (size_t)B);
+    for (int step = 0; step < sch->n_steps; ++step) {
+        for (int b = 0; b < B; ++b) ts[b] = sch->ts[step];
+        mmbo_trans_forward(ed, epacked, d, W, x, onehot, dims, ts, NULL, u_near + (size_t)step * B, fr, B, N,
+                           dx, rate, NULL, NULL, xl, nl, NULL, nm, ns);
+        for (int b = 0; b < B; ++b) {
+            memcpy(v + (size_t)b * N * 3, dx + (size_t)b * N * F, sizeof(float) * (size_t)N * 3);
+            memcpy(lg + (size_t)b * N * S, dx + (size_t)b * N * F + (size_t)N * 3, sizeof(float) * (size_t)N * S);
+        }
+        mmbo_trans_sampler_update(x, onehot, dims, v, lg, rate, nm, ns, sch->c_decay[step], sch->c_score[step], sch->c_noise[step],
+                                  sch->inv_std[step], sch->jump_dt, z_diff + (size_t)step * B * N * F, u_jump + (size_t)step * B,
+                                  z_new + (size_t)step * B * F, B, N, S);
+    }
+    free(dx); free(v); free(lg); free(rate); free(xl); free(nl); free(nm); free(ns); free(ts);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -63,6 +63,29 @@ void mmbo_absorb_head(const float* W, int H, int C, int n_heads, int n_blocks,
                       const float* hidden /*[B,N,H]*/, const uint8_t* mask /*[B,N]*/,
                       const float* tbias, int tbias_stride, int B, int N, float* logit_out /*[B,N]*/);
 
+/*
+ * Trans-dimensional jump diffusion (signatures mirror include/mmbridge.h: mmb_trans_*).
+ * TransdimensionalEPiC.forward (transdimensional_model.py:245-426) and JumpSampler.sample (sampler.py:157-324,
+ * uniform dt, no corrector, no conditioning) with the random draws injected.
+ */
+size_t mmbo_trans_floats(const MmbTransDims* d);
+void mmbo_trans_tokens(const float* onehot, int B, int N, int S, uint8_t* k);
+void mmbo_trans_time_terms(const MmbTransDims* d, const float* W, const float* ts, int B, int T,
+                           float* temb_epic, float* tb1, float* tb2);
+float mmbo_trans_rate(const float* logits, int R, int xt_dim, const MmbForwardRate* fr, float t);
+void mmbo_trans_forward(const MmbEpicDims* ed, const float* epacked, const MmbTransDims* d, const float* W,
+                        const float* x, const float* onehot, const int32_t* dims, const float* ts,
+                        const int32_t* nearest_in, const float* u_nearest, const MmbForwardRate* fr, int B, int N,
+                        float* d_xt, float* rate, float* auto_mean, float* auto_std, float* x0_dim_logits,
+                        float* near_atom_logits, int32_t* nearest_out, float* new_mean, float* new_std);
+void mmbo_trans_sampler_update(float* x, float* onehot, int32_t* dims, const float* v, const float* logits, const float* rate,
+                               const float* new_mean, const float* new_std,
+                               float c_decay, float c_score, float c_noise, float inv_std, float jump_dt,
+                               const float* z_diff, const float* u_jump, const float* z_new, int B, int N, int S);
+void mmbo_trans_sample(const MmbEpicDims* ed, const float* epacked, const MmbTransDims* d, const float* W,
+                       float* x, float* onehot, int32_t* dims, const MmbJumpSchedule* sch, const MmbForwardRate* fr,
+                       const float* z_diff, const float* u_near, const float* u_jump, const float* z_new, int B, int N);
+
 int mmbo_max_threads(void);
 
 #ifdef __cplusplus

@@ -160,3 +160,92 @@ def absorbing_trunk(model):
     head = g.discrete_head_mlp if g.add_discrete_head else None
     dims = g.epic.epic_dims(head[0].out_features if head is not None else 0)
     return dims, g.epic.pack_weights(head).numpy()
+
+
+# ---- trans-dimensional jump diffusion ---------------------------------------------------------------
+from multimodal_particles_b200._native import ForwardRate, JumpSchedule, TransDims  # noqa: E402
+
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def load_trans_golden(path):
+    from multimodal_particles_b200.config_classes.transdimensional_unconditional_config import TransdimensionalEpicConfig
+    from multimodal_particles_b200.transdimensional import TransdimensionalJumpDiffusion
+    z = np.load(path)
+    cfg = TransdimensionalEpicConfig.from_dict(json.loads(str(z["config"])))
+    model = TransdimensionalJumpDiffusion(cfg)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model.load_state_dict(sd, strict=True)
+    return z, cfg, model
+
+
+def trans_packed(model):
+    """-> (EpicDims, trunk blob, TransDims, heads blob) of a TransdimensionalJumpDiffusion of this repo."""
+    m = model.net.model
+    return m.epic.epic_dims(0), m.epic.pack_weights(None).numpy(), m.trans_dims(), m.pack_heads().numpy()
+
+
+def trans_tokens(onehot):
+    B, N, S = onehot.shape
+    k = np.empty((B, N), np.uint8)
+    lib().mmbo_trans_tokens(_p(f32(onehot)), B, N, S, _p(k, _u8p))
+    return k
+
+
+def trans_forward(packed, x, onehot, dims, ts, fr: ForwardRate, nearest=None, u_nearest=None):
+    edims, eblob, tdims, tblob = packed
+    B, N, _ = x.shape
+    S, R, F = tdims.vocab_size, tdims.max_particles, 3 + tdims.vocab_size
+    lib().mmbo_trans_floats.restype = ctypes.c_size_t
+    assert tblob.size == lib().mmbo_trans_floats(ctypes.byref(tdims)), "trans blob size"
+    x, onehot, dims, ts = f32(x), f32(onehot), i32(dims), f32(ts)
+    out = SimpleNamespace(d_xt=np.empty((B, N * F), np.float32), rate=np.empty(B, np.float32),
+                          auto_mean=np.empty((B, N * F), np.float32), auto_std=np.empty((B, N * F), np.float32),
+                          x0_dim_logits=np.empty((B, R), np.float32), near_atom_logits=np.empty((B, N), np.float32),
+                          nearest=np.empty(B, np.int32), new_mean=np.empty((B, F), np.float32), new_std=np.empty((B, F), np.float32))
+    near = None if nearest is None else i32(nearest)
+    un = None if u_nearest is None else f32(u_nearest)
+    lib().mmbo_trans_forward(ctypes.byref(edims), _p(f32(eblob)), ctypes.byref(tdims), _p(f32(tblob)), _p(x), _p(onehot),
+                             _p(dims, _i32p), _p(ts), _p(near, _i32p), _p(un), ctypes.byref(fr), B, N,
+                             _p(out.d_xt), _p(out.rate), _p(out.auto_mean), _p(out.auto_std), _p(out.x0_dim_logits),
+                             _p(out.near_atom_logits), _p(out.nearest, _i32p), _p(out.new_mean), _p(out.new_std))
+    return out
+
+
+def trans_sampler_update(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score, c_noise, inv_std, jump_dt,
+                         z_diff, u_jump, z_new):
+    """Returns updated copies (x, onehot, dims)."""
+    B, N, _ = x.shape
+    S = onehot.shape[-1]
+    x, onehot, dims = f32(x).copy(), f32(onehot).copy(), i32(dims).copy()
+    cf = ctypes.c_float
+    lib().mmbo_trans_sampler_update(_p(x), _p(onehot), _p(dims, _i32p), _p(f32(v)), _p(f32(logits)), _p(f32(rate)), _p(f32(new_mean)),
+                                    _p(f32(new_std)), cf(c_decay), cf(c_score), cf(c_noise), cf(inv_std), cf(jump_dt),
+                                    _p(f32(z_diff)), _p(f32(u_jump)), _p(f32(z_new)), B, N, S)
+    return x, onehot, dims
+
+
+def trans_sample(packed, x, onehot, dims, sched, fr: ForwardRate, z_diff, u_near, u_jump, z_new):
+    """Returns final copies (x, onehot, dims)."""
+    edims, eblob, tdims, tblob = packed
+    B, N, _ = x.shape
+    x, onehot, dims = f32(x).copy(), f32(onehot).copy(), i32(dims).copy()
+    cs = JumpSchedule.from_schedule(sched)
+    lib().mmbo_trans_sample(ctypes.byref(edims), _p(f32(eblob)), ctypes.byref(tdims), _p(f32(tblob)), _p(x), _p(onehot),
+                            _p(dims, _i32p), ctypes.byref(cs), ctypes.byref(fr), _p(f32(z_diff)), _p(f32(u_near)), _p(f32(u_jump)),
+                            _p(f32(z_new)), B, N)
+    return x, onehot, dims
+
+
+def trans_initial_state(z_init, N, S):
+    """x_T ~ N(0,I) -> one centred particle per jet (sampler.py:170-183): the first particle's continuous features
+    are x - x = 0, its one-hot block is the raw draw; everything else is deleted."""
+    B = z_init.shape[0]
+    x = np.zeros((B, N, 3), np.float32)
+    oh = np.zeros((B, N, S), np.float32)
+    oh[:, 0, :] = z_init[:, N * 3: N * 3 + S]
+    return x, oh, np.ones(B, np.int32)

@@ -1,0 +1,101 @@
+"""The CPU oracle's trans-dimensional path against the fixture produced by the reference
+(tests/golden/make_golden_trans.py): TransdimensionalEPiC.forward and JumpSampler.sample."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as ol
+from multimodal_particles_b200.transdimensional import jump_schedule
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "trans.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    z, cfg, model = ol.load_trans_golden(GOLD)
+    return z, cfg, model, ol.trans_packed(model)
+
+
+def test_blob_size_and_forward_rate(gold):
+    z, cfg, model, packed = gold
+    fr = model.forward_rate.as_c()
+    ref = z["forward_rate"]
+    assert fr.kind == 0 and abs(fr.scalar - ref[1]) < 1e-5 * ref[1] and fr.offset == np.float32(ref[2]) and fr.rate_cut_t == np.float32(ref[3])
+
+
+def test_tokens_follow_the_batch_axis_softmax(gold):
+    """structure.py:231-232: F.softmax without dim normalises a 3-D tensor over dim 0 — tokens depend on the batch."""
+    z = gold[0]
+    assert np.array_equal(ol.trans_tokens(z["fwd/onehot"]), z["fwd/tokens"])
+    oh = torch.from_numpy(z["fwd/onehot"])
+    assert not torch.equal(oh.argmax(-1), torch.from_numpy(z["fwd/tokens"]).long()), "fixture should exercise the quirk"
+
+
+def test_forward_given_nearest(gold):
+    z, cfg, model, packed = gold
+    out = ol.trans_forward(packed, z["fwd/x"], z["fwd/onehot"], z["fwd/dims"], z["fwd/ts"], model.forward_rate.as_c(),
+                           nearest=z["fwd/nearest"])
+    np.testing.assert_allclose(out.d_xt, z["fwd/d_xt"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(out.x0_dim_logits, z["fwd/x0_dim_logits"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(out.near_atom_logits, z["fwd/near_atom_logits"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(out.rate, z["fwd/rate"], rtol=2e-4, atol=1e-5)
+    np.testing.assert_allclose(out.auto_mean, z["fwd/auto_mean"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(out.auto_std, z["fwd/auto_std"], rtol=0, atol=5e-5)
+    assert z["fwd/rate"][2] == 0.0 and (z["fwd/auto_mean"][2] == 0).all()   # dims == N: no birth possible
+
+
+def test_forward_sampled_nearest(gold):
+    z, cfg, model, packed = gold
+    out = ol.trans_forward(packed, z["fwd/x"], z["fwd/onehot"], z["fwd/dims"], z["fwd/ts"], model.forward_rate.as_c(),
+                           u_nearest=z["fwd/u_near"])
+    assert np.array_equal(out.nearest, z["fwd/nearest_sampled"])
+    np.testing.assert_allclose(out.auto_mean, z["fwd/auto_mean_sampled"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(out.auto_std, z["fwd/auto_std_sampled"], rtol=0, atol=5e-5)
+
+
+def test_schedule_equals_reference_loop(gold):
+    z, cfg, model, packed = gold
+    sched = jump_schedule(float(z["smp/dt"]), model.noise_schedule)
+    assert sched.n_steps == len(z["smp/ts"]) and np.array_equal(sched.ts, z["smp/ts"])
+
+
+def test_sampler_steps_one_by_one(gold):
+    """every recorded step: oracle forward + update from the reference's state -> the reference's next state"""
+    z, cfg, model, packed = gold
+    fr = model.forward_rate.as_c()
+    sched = jump_schedule(float(z["smp/dt"]), model.noise_schedule)
+    n = sched.n_steps
+    for i in range(n):
+        x, oh, dims = z["smp/x_traj"][i], z["smp/oh_traj"][i], z["smp/dims_traj"][i]
+        B, N, S = oh.shape
+        ts = np.full(B, sched.ts[i], np.float32)
+        f = ol.trans_forward(packed, x, oh, dims, ts, fr, u_nearest=z["smp/u_near"][i])
+        assert np.array_equal(f.nearest, z["smp/nearest_traj"][i])
+        np.testing.assert_allclose(f.rate, z["smp/rate_traj"][i], rtol=3e-4, atol=1e-5)
+        v, lg = f.d_xt[:, :N * 3].reshape(B, N, 3), f.d_xt[:, N * 3:].reshape(B, N, S)
+        x2, oh2, d2 = ol.trans_sampler_update(x, oh, dims, v, lg, f.rate, f.new_mean, f.new_std, sched.c_decay[i], sched.c_score[i],
+                                              sched.c_noise[i], sched.inv_std[i], sched.jump_dt, z["smp/z_diff"][i],
+                                              z["smp/u_jump"][i], z["smp/z_new"][i])
+        if i + 1 < n:
+            rx, ro, rd = z["smp/x_traj"][i + 1], z["smp/oh_traj"][i + 1], z["smp/dims_traj"][i + 1]
+        else:
+            rx, ro, rd = z["smp/x_final"], z["smp/oh_final"], z["smp/dims_final"]
+        assert np.array_equal(d2, rd), f"step {i}"
+        np.testing.assert_allclose(x2, rx, rtol=5e-6, atol=3e-5, err_msg=f"step {i}")
+        np.testing.assert_allclose(oh2, ro, rtol=5e-6, atol=3e-5, err_msg=f"step {i}")
+
+
+def test_sampler_whole_trajectory(gold):
+    z, cfg, model, packed = gold
+    B, N, S = z["smp/oh_final"].shape
+    x, oh, dims = ol.trans_initial_state(z["smp/z_init"], N, S)
+    np.testing.assert_allclose(oh, z["smp/oh_traj"][0], atol=0)
+    np.testing.assert_allclose(x, z["smp/x_traj"][0], atol=1e-7)
+    sched = jump_schedule(float(z["smp/dt"]), model.noise_schedule)
+    x, oh, dims = ol.trans_sample(packed, x, oh, dims, sched, model.forward_rate.as_c(), z["smp/z_diff"], z["smp/u_near"],
+                                  z["smp/u_jump"], z["smp/z_new"])
+    assert np.array_equal(dims, z["smp/dims_final"])
+    np.testing.assert_allclose(x, z["smp/x_final"], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(oh, z["smp/oh_final"], rtol=1e-4, atol=2e-3)
