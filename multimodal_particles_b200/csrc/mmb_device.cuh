@@ -30,6 +30,25 @@ __device__ __forceinline__ float expf_exact(float x) {
     return __fmul_rn(y, __int_as_float((e + 127) << 23));
 }
 
+// expf_exact with gradual underflow below 2^-126 (mmbo_expf_dn): the batch-axis softmax of the trans-dimensional token rule
+__device__ __forceinline__ float expf_exact_dn(float x) {
+    if (!(x < -87.0f)) return expf_exact(x);
+    if (x < -104.0f) return 0.0f;
+    float n = rintf(__fmul_rn(x, 1.44269504f));
+    float r = __fmaf_rn(n, -0.693359375f, x);
+    r = __fmaf_rn(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    float r2 = __fmul_rn(r, r);
+    float y = __fadd_rn(__fmaf_rn(p, r2, r), 1.0f);
+    int e = (int)n + 64;
+    return __fmul_rn(__fmul_rn(y, __int_as_float((e + 127) << 23)), 5.42101086e-20f);
+}
+
 __device__ __forceinline__ float lrelu(float a) { return a > 0.0f ? a : __fmul_rn(a, 0.01f); }
 
 __device__ __forceinline__ float selu(float a) {

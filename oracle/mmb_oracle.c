@@ -55,6 +55,26 @@ float mmbo_expf(float x) {
     return y * bits_to_float((uint32_t)(e + 127) << 23);
 }
 
+/* same function with gradual underflow: results below 2^-126 come out as denormals (down to exp(-104) ~ 2^-150 -> 0),
+ * as torch's exp does.  Only the batch-axis softmax of the trans-dimensional token rule needs this range. */
+float mmbo_expf_dn(float x) {
+    if (!(x < -87.0f)) return mmbo_expf(x);
+    if (x < -104.0f) return 0.0f;
+    float n = rintf(x * 1.44269504f);
+    float r = fmaf(n, -0.693359375f, x);
+    r = fmaf(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    float r2 = r * r;
+    float y = fmaf(p, r2, r) + 1.0f;
+    int e = (int)n + 64;                                          /* y * 2^(e) is a normal number, exactly */
+    return (y * bits_to_float((uint32_t)(e + 127) << 23)) * 5.42101086e-20f;   /* * 2^-64: one rounding into the denormals */
+}
+
 static inline float lrelu(float a) { return a > 0.0f ? a : a * 0.01f; }           /* F.leaky_relu */
 static inline float selu(float a) {                                               /* nn.SELU */
     const float scale = 1.0507009873554804934193349852946f;
@@ -514,7 +534,7 @@ void mmbo_trans_tokens(const float* onehot, int B, int N, int S, uint8_t* k) {
         float mx = -INFINITY;
         for (int b = 0; b < B; ++b) { float a = onehot[(size_t)b * NS + c]; mx = a > mx ? a : mx; }
         float part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int b = 0; b < B; ++b) part[b & 7] = part[b & 7] + mmbo_expf(onehot[(size_t)b * NS + c] - mx);
+        for (int b = 0; b < B; ++b) part[b & 7] = part[b & 7] + mmbo_expf_dn(onehot[(size_t)b * NS + c] - mx);
         M[c] = mx;
         Z[c] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
     }
@@ -523,7 +543,7 @@ void mmbo_trans_tokens(const float* onehot, int B, int N, int S, uint8_t* k) {
             int best = 0; float bp = -1.0f;
             for (int s2 = 0; s2 < S; ++s2) {
                 const int c = n * S + s2;
-                const float pr = mmbo_expf(onehot[(size_t)b * NS + c] - M[c]) / Z[c];
+                const float pr = mmbo_expf_dn(onehot[(size_t)b * NS + c] - M[c]) / Z[c];
                 if (pr > bp) { bp = pr; best = s2; }
             }
             k[(size_t)b * N + n] = (uint8_t)best;

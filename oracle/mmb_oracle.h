@@ -23,6 +23,7 @@ extern "C" {
 #endif
 
 float mmbo_expf(float x);
+float mmbo_expf_dn(float x);   /* with gradual underflow (trans-dimensional token rule) */
 
 /* host-side step table with libm, following mbm.py:203-211, utils.py:183-198, bridges.py:125-130,
  * 218-231.  The product computes the same table with torch ops; tests compare the two. */
