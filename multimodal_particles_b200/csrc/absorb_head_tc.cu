@@ -118,12 +118,12 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int row, int chunk4, 
                                                             pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
 }
 
-// fp32 side table (floats), per block then the folded rate vector
+// fp32 side table (floats), per block then the per-particle output vector
 struct HeadTable {
     // per block: n1g n1b b1 n2g n2b n3g n3b bq bk bv  (10 x 128)
     static constexpr int kPerBlock = 10 * kC;
-    __host__ __device__ static int rate_w(int nblk) { return nblk * kPerBlock; }       // [128] post^T pre
-    __host__ __device__ static int rate_c(int nblk) { return nblk * kPerBlock + kC; }  // scalar
+    __host__ __device__ static int rate_w(int nblk) { return nblk * kPerBlock; }       // [128] per-particle output vector
+    __host__ __device__ static int rate_c(int nblk) { return nblk * kPerBlock + kC; }  // its constant
     __host__ __device__ static int floats(int nblk) { return nblk * kPerBlock + kC + 4; }
 };
 
@@ -131,12 +131,20 @@ struct HeadParams {
     const uint8_t* image;    // n_seq slots of kSlot bytes (bf16 operand tiles)
     const float* table;      // HeadTable
     int n_blocks, H;
+    int mode, S;             // TfStackIO::mode; one-hot width (modes 1, 2)
     const float* hidden;     // [B,N,H]
     const uint8_t* mask;     // [B,N]
+    const float* onehot;     // [B,N,S]   (modes 1, 2)
+    const float* x;          // [B,N,3]   (mode 2)
+    const int32_t* nearest;  // [B]       (mode 2)
     const float* tbias;      // [B or 1][n_blocks][128]
     int tbias_stride;
     int B, N;
-    float* logit_out;        // [B,N]
+    float* logit_out;        // [B,N] per-particle output
+    const float* jet_wT;     // [128][n_jet] per-jet head applied to the mean over the N slots (nullable)
+    const float* jet_b;      // [n_jet]
+    int n_jet;
+    float* jet_out;          // [B][n_jet]
 };
 
 constexpr int kSmemW = 2 * kSlot;                         // weight ring
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     __shared__ float s_stat[256];                // per channel: scale = rstd*gamma [128], shift = beta - mean*scale (+bias) [128]
     __shared__ float s_part[4][64];              // GroupNorm partial column sums (4 row quarters)
     __shared__ float s_dot[128];                 // rate-vector partial of the upper-half threads
+    __shared__ float s_mean[128];                // mean of the residual stream over the N slots (per-jet head)
     const int tid = threadIdx.x, r = tid & 127, half = tid >> 7, warp = tid >> 5;
     const int nblk = p.n_blocks, n_seq = 1 + 6 * nblk;
     uint8_t *sA = smem + kOffA, *sQ = smem + kOffQ, *sK = smem + kOffK, *sV = smem + kOffV, *sOnes = smem + kOffOnes;
@@ -290,16 +299,35 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     for (int jet = blockIdx.x; jet < p.B; jet += gridDim.x) {
         const bool valid = r < p.N;
         const size_t pidx = (size_t)jet * p.N + r;
-        // ---- proj_in on [hidden, one_hot(mask)]  (absorbing_flows.py:113-118)
+        // ---- proj_in: mode 0 [hidden, one_hot(mask)] (absorbing_flows.py:113-118); mode 1 [hidden, onehot]
+        //      (transdimensional_model.py:295-303); mode 2 mask * [hidden, onehot, distance to the nearest particle,
+        //      its one-hot flag pair] (transdimensional_model.py:341-367)
         {
             float row[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) row[i] = 0.0f;
             if (valid && half == 0) {
-                for (int i = 0; i < p.H; ++i) row[i] = p.hidden[pidx * p.H + i];
+                const int H = p.H;
                 const int m = p.mask[pidx] ? 1 : 0;
-                row[p.H] = m ? 0.0f : 1.0f;
-                row[p.H + 1] = m ? 1.0f : 0.0f;
+                for (int i = 0; i < H; ++i) row[i] = p.hidden[pidx * H + i];
+                if (p.mode == 0) {
+                    row[H] = m ? 0.0f : 1.0f;
+                    row[H + 1] = m ? 1.0f : 0.0f;
+                } else {
+                    for (int i = 0; i < p.S; ++i) row[H + i] = p.onehot[pidx * p.S + i];
+                    if (p.mode == 2) {
+                        const int near = p.nearest[jet];
+                        const float* xa = p.x + ((size_t)jet * p.N + near) * 3;
+                        const float* xr = p.x + pidx * 3;
+                        const float d0 = xa[0] - xr[0], d1 = xa[1] - xr[1], d2 = xa[2] - xr[2];
+                        row[H + p.S] = sqrtf((d0 * d0 + d1 * d1) + d2 * d2);
+                        row[H + p.S + 1] = r == near ? 1.0f : 0.0f;
+                        row[H + p.S + 2] = r == near ? 0.0f : 1.0f;
+                        if (!m)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) row[i] = 0.0f;
+                    }
+                }
             }
             uint8_t* q = sA0 + (r >> 3) * 512 + (r & 7) * 16;
             if (half == 0)
@@ -400,7 +428,9 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true);               // X += proj_out(.) + b
             mma_done(true);
         }
-        // ---- rate = post_rate_proj(pre_rate_proj(X)) folded into one 128-vector (absorbing_flows.py:127-131)
+        // ---- per-particle output: one 128-vector against the residual stream (absorbing: post_rate_proj(pre_rate_proj(X))
+        //      folded, absorbing_flows.py:127-131; trans: near_atom_proj / vec_weighting_proj) and, for the per-jet heads,
+        //      the mean of X over the N slots followed by a folded [n_jet x 128] Linear (transdimensional_model.py:309-311,403-405)
         {
             const float* w = sTab + HeadTable::rate_w(nblk);
             float acc = half ? 0.0f : sTab[HeadTable::rate_c(nblk)], v[32];
@@ -409,10 +439,39 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                 tmem_ld32(dX + lane_off + c2 * 32, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc = fmaf(w[half * 64 + c2 * 32 + j], v[j], acc);
+                if (p.n_jet > 0) {   // column sums of this 64-column slice: rows -> sRed, 4 row quarters, then one thread per column
+                    if (c2) __syncthreads();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sRed[r * 65 + half * 32 + j] = valid ? v[j] : 0.0f;
+                    __syncthreads();
+                    {
+                        const int col = tid & 63, qt = tid >> 6;
+                        float a2 = 0.0f;
+#pragma unroll 8
+                        for (int i = 0; i < 32; ++i) a2 += sRed[(qt * 32 + i) * 65 + col];
+                        s_part[qt][col] = a2;
+                    }
+                    __syncthreads();
+                    if (tid < 64) {
+                        const int c = (tid >> 5) * 64 + c2 * 32 + (tid & 31);   // sRed column tid = (half, j)
+                        s_mean[c] = ((s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid])) * (1.0f / (float)p.N);
+                    }
+                }
             }
             if (half) s_dot[r] = acc;
             __syncthreads();
             if (valid && !half) p.logit_out[pidx] = acc + s_dot[r];
+            if (p.n_jet > 0 && tid < p.n_jet) {
+                float a0 = __ldg(p.jet_b + tid), a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll 4
+                for (int c = 0; c < kC; c += 4) {
+                    a0 = fmaf(__ldg(p.jet_wT + (size_t)c * p.n_jet + tid), s_mean[c], a0);
+                    a1 = fmaf(__ldg(p.jet_wT + (size_t)(c + 1) * p.n_jet + tid), s_mean[c + 1], a1);
+                    a2 = fmaf(__ldg(p.jet_wT + (size_t)(c + 2) * p.n_jet + tid), s_mean[c + 2], a2);
+                    a3 = fmaf(__ldg(p.jet_wT + (size_t)(c + 3) * p.n_jet + tid), s_mean[c + 3], a3);
+                }
+                p.jet_out[(size_t)jet * p.n_jet + tid] = (a0 + a1) + (a2 + a3);
+            }
         }
         tc_fence_before();
         __syncthreads();  // X and the operand tiles are rewritten by the next jet
@@ -427,18 +486,24 @@ inline size_t tile_index(int o, int k, int sbo) { return ((size_t)(o / 8) * sbo 
 
 }  // namespace
 
-struct AbsorbHead {
-    int H, C, n_heads, n_blocks, device, sm_count;
-    void* image;   // n_seq * kSlot bytes
-    float* table;  // HeadTable
-};
+// ---- host side: one transformer stack = operand image + side table (+ optional per-jet head) --------------------------
+void tf_stack_free(TfStack* st) {
+    if (st->image) cudaFree(st->image);
+    if (st->table) cudaFree(st->table);
+    if (st->jet_wT) cudaFree(st->jet_wT);
+    if (st->jet_b) cudaFree(st->jet_b);
+    *st = TfStack{};
+}
 
-int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, size_t n_floats, int device, AbsorbHead** out) {
-    if (C != kC || n_heads != kHeads || n_blocks < 1 || n_blocks > kMaxBlocks || H < 1 || H > 30)
-        return fail(MMB_EUNSUPPORTED, "absorbing head is built for transformer_dim=128, n_heads=2, 1..4 blocks, hidden<=30");
+// proj_in [C][Cin]+[C]; blocks: n_blocks x (norm1 g b, conv1, norm2 g b, conv2, attn norm g b, q, k, v, proj_out), every conv
+// [C][C]+[C]; dot_w [C] / dot_c: the per-particle output; jet_w [n_jet][C] / jet_b [n_jet]: the per-jet head (nullable).
+// Allocates on the CURRENT device.
+int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* blocks, int n_blocks, const float* dot_w, float dot_c,
+                   const float* jet_w, const float* jet_b, int n_jet) {
+    constexpr int C = kC;
+    if (n_blocks < 1 || n_blocks > kMaxBlocks || Cin < 1 || Cin > 32 || n_jet < 0 || n_jet > 128)
+        return fail(MMB_EUNSUPPORTED, "transformer stack is built for 1..4 blocks, <= 32 input features, <= 128 per-jet outputs");
     const size_t lin = (size_t)C * C + C;
-    const size_t expect = (size_t)C * (H + 2) + C + (size_t)n_blocks * (6 * C + 6 * lin) + lin + C + 1;
-    if (n_floats != expect) return fail(MMB_EINVAL, "absorbing head blob has %zu floats, layout wants %zu", n_floats, expect);
     const int n_seq = 1 + 6 * n_blocks;
     std::vector<__nv_bfloat16> img((size_t)n_seq * kSlot / 2, __float2bfloat16(0.0f));
     std::vector<float> tab((size_t)HeadTable::floats(n_blocks), 0.0f);
@@ -453,10 +518,9 @@ int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, 
             img[(size_t)slot * kSlot / 2 + 32768 / 2 + tile_index(o, 1, 256)] = __float2bfloat16(b[o] - __bfloat162float(hi));
         }
     };
-    const float* p = W;
-    put_matrix(0, p, H + 2);
-    put_bias(0, p + (size_t)C * (H + 2));
-    p += (size_t)C * (H + 2) + C;
+    put_matrix(0, proj_in, Cin);
+    put_bias(0, proj_in + (size_t)C * Cin);
+    const float* p = blocks;
     for (int blk = 0; blk < n_blocks; ++blk) {
         float* T = tab.data() + (size_t)blk * HeadTable::kPerBlock;
         const float *n1g = p, *n1b = p + C, *c1 = p + 2 * C, *n2g = c1 + lin, *n2b = n2g + C, *c2 = n2b + C, *ng = c2 + lin,
@@ -473,36 +537,81 @@ int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, 
             T[7 * kC + c] = wq[(size_t)C * C + c]; T[8 * kC + c] = wk[(size_t)C * C + c]; T[9 * kC + c] = wv[(size_t)C * C + c];
         }
     }
-    {   // fold Linear(C->C) then Linear(C->1): w = post^T pre, c = post . pre_b + post_b
-        const float *pre = p, *pre_b = p + (size_t)C * C, *post = p + lin, *post_b = post + C;
-        for (int c = 0; c < C; ++c) {
-            double acc = 0;
-            for (int o = 0; o < C; ++o) acc += (double)post[o] * pre[(size_t)o * C + c];
-            tab[HeadTable::rate_w(n_blocks) + c] = (float)acc;
-        }
-        double acc = post_b[0];
-        for (int o = 0; o < C; ++o) acc += (double)post[o] * pre_b[o];
-        tab[HeadTable::rate_c(n_blocks)] = (float)acc;
+    for (int c = 0; c < C; ++c) tab[HeadTable::rate_w(n_blocks) + c] = dot_w[c];
+    tab[HeadTable::rate_c(n_blocks)] = dot_c;
+    *st = TfStack{};
+    st->Cin = Cin; st->n_blocks = n_blocks; st->n_jet = n_jet;
+    int rc = cuda_ok(cudaMalloc(&st->image, img.size() * 2), "cudaMalloc stack image");
+    if (!rc) rc = cuda_ok(cudaMalloc(&st->table, tab.size() * 4), "cudaMalloc stack table");
+    if (!rc) rc = cuda_ok(cudaMemcpy(st->image, img.data(), img.size() * 2, cudaMemcpyHostToDevice), "stack image upload");
+    if (!rc) rc = cuda_ok(cudaMemcpy(st->table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice), "stack table upload");
+    if (!rc && n_jet > 0) {
+        std::vector<float> wT((size_t)C * n_jet);
+        for (int o = 0; o < n_jet; ++o)
+            for (int c = 0; c < C; ++c) wT[(size_t)c * n_jet + o] = jet_w[(size_t)o * C + c];
+        rc = cuda_ok(cudaMalloc(&st->jet_wT, wT.size() * 4), "cudaMalloc jet head");
+        if (!rc) rc = cuda_ok(cudaMalloc(&st->jet_b, (size_t)n_jet * 4), "cudaMalloc jet head bias");
+        if (!rc) rc = cuda_ok(cudaMemcpy(st->jet_wT, wT.data(), wT.size() * 4, cudaMemcpyHostToDevice), "jet head upload");
+        if (!rc) rc = cuda_ok(cudaMemcpy(st->jet_b, jet_b, (size_t)n_jet * 4, cudaMemcpyHostToDevice), "jet head bias upload");
     }
+    if (rc) tf_stack_free(st);
+    return rc;
+}
+
+int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B, int N, cudaStream_t stream) {
+    if (N < 1 || N > 128) return fail(MMB_EUNSUPPORTED, "transformer stack handles 1..128 particle slots per jet (got %d)", N);
+    if (B == 0) return MMB_OK;
+    HeadParams p{};
+    p.image = static_cast<const uint8_t*>(st->image); p.table = st->table; p.n_blocks = st->n_blocks; p.H = io.H;
+    p.mode = io.mode; p.S = io.S; p.hidden = io.hidden; p.mask = io.mask; p.onehot = io.onehot; p.x = io.x; p.nearest = io.nearest;
+    p.tbias = io.tbias; p.tbias_stride = io.tbias_stride; p.B = B; p.N = N; p.logit_out = io.dot_out;
+    p.jet_wT = st->jet_wT; p.jet_b = st->jet_b; p.n_jet = io.jet_out ? st->n_jet : 0; p.jet_out = io.jet_out;
+    const size_t bytes = kOffTab + (size_t)HeadTable::floats(st->n_blocks) * 4 + 1024;
+    if (int rc = cuda_ok(cudaFuncSetAttribute(absorb_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "head smem attribute"))
+        return rc;
+    const int grid = B < sm_count ? B : sm_count;
+    absorb_head_tc_kernel<<<grid, kThreads, bytes, stream>>>(p);
+    return cuda_ok(cudaGetLastError(), "transformer stack launch");
+}
+
+struct AbsorbHead {
+    int H, C, n_heads, n_blocks, device, sm_count;
+    TfStack stack;
+};
+
+int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, size_t n_floats, int device, AbsorbHead** out) {
+    if (C != kC || n_heads != kHeads || n_blocks < 1 || n_blocks > kMaxBlocks || H < 1 || H > 30)
+        return fail(MMB_EUNSUPPORTED, "absorbing head is built for transformer_dim=128, n_heads=2, 1..4 blocks, hidden<=30");
+    const size_t lin = (size_t)C * C + C;
+    const size_t expect = (size_t)C * (H + 2) + C + (size_t)n_blocks * (6 * C + 6 * lin) + lin + C + 1;
+    if (n_floats != expect) return fail(MMB_EINVAL, "absorbing head blob has %zu floats, layout wants %zu", n_floats, expect);
+    const float* blocks = W + (size_t)C * (H + 2) + C;
+    const float* p = blocks + (size_t)n_blocks * (6 * C + 6 * lin);
+    // fold Linear(C->C) then Linear(C->1): w = post^T pre, c = post . pre_b + post_b
+    std::vector<float> dot_w(C);
+    const float *pre = p, *pre_b = p + (size_t)C * C, *post = p + lin, *post_b = post + C;
+    for (int c = 0; c < C; ++c) {
+        double acc = 0;
+        for (int o = 0; o < C; ++o) acc += (double)post[o] * pre[(size_t)o * C + c];
+        dot_w[c] = (float)acc;
+    }
+    double dc = post_b[0];
+    for (int o = 0; o < C; ++o) dc += (double)post[o] * pre_b[o];
     int prev = 0;
     if (int rc = cuda_ok(cudaGetDevice(&prev), "cudaGetDevice")) return rc;
     if (int rc = cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return rc;
-    AbsorbHead* h = new AbsorbHead{H, C, n_heads, n_blocks, device, 148, nullptr, nullptr};
+    AbsorbHead* h = new AbsorbHead{H, C, n_heads, n_blocks, device, 148, TfStack{}};
     int rc = cuda_ok(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), "sm count");
-    if (!rc) rc = cuda_ok(cudaMalloc(&h->image, img.size() * 2), "cudaMalloc head image");
-    if (!rc) rc = cuda_ok(cudaMalloc(&h->table, tab.size() * 4), "cudaMalloc head table");
-    if (!rc) rc = cuda_ok(cudaMemcpy(h->image, img.data(), img.size() * 2, cudaMemcpyHostToDevice), "head image upload");
-    if (!rc) rc = cuda_ok(cudaMemcpy(h->table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice), "head table upload");
+    if (!rc) rc = tf_stack_build(&h->stack, W, H + 2, blocks, n_blocks, dot_w.data(), (float)dc, nullptr, nullptr, 0);
     cudaSetDevice(prev);
-    if (rc) { absorb_head_destroy(h); return rc; }
+    if (rc) { delete h; return rc; }
     *out = h;
     return MMB_OK;
 }
 
 void absorb_head_destroy(AbsorbHead* h) {
     if (!h) return;
-    if (h->image) cudaFree(h->image);
-    if (h->table) cudaFree(h->table);
+    tf_stack_free(&h->stack);
     delete h;
 }
 
@@ -511,15 +620,9 @@ int absorb_head_blocks(const AbsorbHead* h) { return h->n_blocks; }
 
 int launch_absorb_head(const AbsorbHead* h, const float* hidden, const uint8_t* mask, const float* tbias, int tbias_stride,
                        int B, int N, float* logit_out, cudaStream_t stream) {
-    if (N < 1 || N > 128) return fail(MMB_EUNSUPPORTED, "absorbing head handles 1..128 particle slots per jet (got %d)", N);
-    if (B == 0) return MMB_OK;
-    HeadParams p{static_cast<const uint8_t*>(h->image), h->table, h->n_blocks, h->H, hidden, mask, tbias, tbias_stride, B, N, logit_out};
-    const size_t bytes = kOffTab + (size_t)HeadTable::floats(h->n_blocks) * 4 + 1024;
-    if (int rc = cuda_ok(cudaFuncSetAttribute(absorb_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "head smem attribute"))
-        return rc;
-    const int grid = B < h->sm_count ? B : h->sm_count;
-    absorb_head_tc_kernel<<<grid, kThreads, bytes, stream>>>(p);
-    return cuda_ok(cudaGetLastError(), "absorb_head launch");
+    TfStackIO io{};
+    io.mode = 0; io.H = h->H; io.hidden = hidden; io.mask = mask; io.tbias = tbias; io.tbias_stride = tbias_stride; io.dot_out = logit_out;
+    return launch_tf_stack(&h->stack, h->sm_count, io, B, N, stream);
 }
 
 }  // namespace mmb

@@ -34,7 +34,32 @@ int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, co
 int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int stream_id, int step0, int n_steps, int B, int N,
                            cudaStream_t stream);
 
-// absorb_head_tc.cu — transformer absorbing-rate head on tcgen05
+// absorb_head_tc.cu — 128-wide transformer stack (ResnetBlock + AttnBlock) on tcgen05
+struct TfStack {
+    int Cin = 0, n_blocks = 0, n_jet = 0;
+    void* image = nullptr;    // bf16 operand tiles, one 36 KB slot per streamed matrix
+    float* table = nullptr;   // fp32 side table (norm affine, biases, per-particle output vector)
+    float* jet_wT = nullptr;  // [128][n_jet] per-jet head on the slot mean
+    float* jet_b = nullptr;
+};
+struct TfStackIO {
+    int mode;                 // 0: [hidden, one_hot(mask)]; 1: [hidden, onehot]; 2: mask * [hidden, onehot, dist, near, !near]
+    int H, S;
+    const float* hidden;      // [B,N,H]
+    const uint8_t* mask;      // [B,N]
+    const float* onehot;      // [B,N,S]  modes 1, 2
+    const float* x;           // [B,N,3]  mode 2
+    const int32_t* nearest;   // [B]      mode 2
+    const float* tbias;       // [B or 1][n_blocks][128]
+    int tbias_stride;
+    float* dot_out;           // [B,N]
+    float* jet_out;           // [B][n_jet] or null
+};
+int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* blocks, int n_blocks, const float* dot_w, float dot_c,
+                   const float* jet_w, const float* jet_b, int n_jet);
+void tf_stack_free(TfStack* st);
+int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B, int N, cudaStream_t stream);
+
 struct AbsorbHead;
 int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, size_t n_floats, int device, AbsorbHead** out);
 void absorb_head_destroy(AbsorbHead* h);

@@ -1,0 +1,713 @@
+// trans.cu — trans-dimensional jump diffusion on the GPU: TransdimensionalEPiC.forward and the JumpSampler loop.
+//
+// Reference (mp/ = /root/reference/multimodal_particles/):
+//   network      mp/models/generative/transdimensional/transdimensional_model.py:245-426 (through EpsilonPrecond :124-133)
+//   batch view   mp/models/generative/transdimensional/structure.py:226-250
+//   rate         mp/models/generative/diffusion/noising.py:123-216
+//   sampler      mp/models/generative/transdimensional/sampler.py:157-324, adjust_st_batch mp/data/particle_clouds/jets_dataloader.py:433-478
+//
+// One evaluation = a short train of kernels on the caller's stream:
+//   trans_colstats / trans_tokens   tokens = argmax of the batch-axis softmax of the one-hot block (structure.py:231-232), prefix mask
+//   trans_time                      EPiC time embedding + the temb_proj terms of both stacks (per jet, or per step in the sampler)
+//   EPiC trunk                      epic_tc.cu / epic_fp32.cu, with the last local hidden
+//   transformer stack 1             absorb_head_tc.cu (tcgen05): nearest-particle logits + x0-dimension logits (per-jet head)
+//   trans_rate                      birth rate from the x0-dimension logits; nearest particle by inverse CDF on one uniform
+//   transformer stack 2             vector weights + the 2S+1 statistics of the new particle
+//   trans_auto                      mean / std of the particle a birth adds
+//   trans_sampler_update            (sampler only) Euler-Maruyama step, centre-of-mass removal, birth — one HBM-bound pass
+// >99 % of the arithmetic is in the two stacks (144.5 MFLOP per jet-evaluation).
+#include <math.h>
+
+#include <vector>
+
+#include "mmb_device.cuh"
+#include "mmb_internal.h"
+
+namespace mmb {
+
+struct TransHeads {
+    MmbTransDims d;
+    int device, sm_count;
+    TfStack s1, s2;
+    float* time_wT;   // device: (1 + 2 n_blocks) x { W^T [C][C], b [C] }: temb_net, stack-1 temb_proj, stack-2 temb_proj
+    float* logfact;   // device: log(k!) for k < 3 R + 2
+};
+
+namespace {
+
+constexpr int kC = 128;
+
+// ---- tokens: batch-axis softmax (structure.py:231-232) ----------------------------------------------------------------
+// One block per 32 columns of the flattened [N*S] axis; warp w owns the jets b = w (mod 8) in ascending order.
+__global__ void __launch_bounds__(256) trans_colstats_kernel(const float* __restrict__ onehot, int B, int NS, float* __restrict__ M,
+                                                             float* __restrict__ Z) {
+    __shared__ float s_red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const bool ok = c < NS;
+    float mx = -INFINITY;
+    if (ok)
+        for (int b = w; b < B; b += 8) mx = fmaxf(mx, __ldg(onehot + (size_t)b * NS + c));
+    s_red[w][lane] = mx;
+    __syncthreads();
+    mx = s_red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i][lane]);
+    __syncthreads();
+    float part = 0.0f;
+    if (ok)
+        for (int b = w; b < B; b += 8) part = __fadd_rn(part, expf_exact_dn(__fadd_rn(__ldg(onehot + (size_t)b * NS + c), -mx)));
+    s_red[w][lane] = part;
+    __syncthreads();
+    if (w == 0 && ok) {
+        M[c] = mx;
+        Z[c] = __fadd_rn(__fadd_rn(__fadd_rn(s_red[0][lane], s_red[1][lane]), __fadd_rn(s_red[2][lane], s_red[3][lane])),
+                         __fadd_rn(__fadd_rn(s_red[4][lane], s_red[5][lane]), __fadd_rn(s_red[6][lane], s_red[7][lane])));
+    }
+}
+
+__global__ void trans_tokens_kernel(const float* __restrict__ onehot, const float* __restrict__ M, const float* __restrict__ Z,
+                                    const int32_t* __restrict__ dims, int B, int N, int S, uint8_t* __restrict__ k,
+                                    uint8_t* __restrict__ mask) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * N) return;
+    const int n = (int)(i % N), b = (int)(i / N);
+    int best = 0;
+    float bp = -1.0f;
+    for (int s = 0; s < S; ++s) {
+        const int c = n * S + s;
+        const float pr = __fdiv_rn(expf_exact_dn(__fadd_rn(__ldg(onehot + i * S + s), -__ldg(M + c))), __ldg(Z + c));
+        if (pr > bp) { bp = pr; best = s; }
+    }
+    k[i] = (uint8_t)best;
+    mask[i] = n < dims[b] ? 1 : 0;
+}
+
+// ---- time terms (utils.py:183-198; gsdm.py:8-26,58; transdimensional_model.py:288-290) ---------------------------------
+// 128 threads = output channels; a block serves kTimeJets jets so every weight row is read once per block.
+constexpr int kTimeJets = 8;
+__global__ void __launch_bounds__(kC) trans_time_kernel(const float* __restrict__ wT, int nblk, const float* __restrict__ ts, int B, int T,
+                                                        float* __restrict__ temb_epic, float* __restrict__ tb1, float* __restrict__ tb2) {
+    __shared__ float s_in[kTimeJets][kC];
+    const int o = threadIdx.x, j0 = blockIdx.x * kTimeJets;
+    const int half = kC / 2;
+    for (int j = 0; j < kTimeJets; ++j) {
+        const int b = j0 + j;
+        float val = 0.0f;
+        if (b < B) {
+            const float t = __ldg(ts + b);
+            const float fe = (float)(9.210340371976184 / (double)(half - 1));   // ln(10000) / (half - 1)
+            const int jj = o < half ? o : o - half;
+            const float a = (t * 1000.0f) * expf((float)jj * -fe);
+            val = o < half ? sinf(a) : cosf(a);
+            if (o < T) {   // EPiC embedding: [cos(t f), sin(t f)], f_i = exp(-ln(1e4) i / (T/2))
+                const int h2 = T / 2, i2 = o < h2 ? o : o - h2;
+                const float f = expf(-9.210340371976184f * (float)i2 / (float)h2);
+                temb_epic[(size_t)b * T + o] = (T % 2 && o == T - 1) ? 0.0f : (o < h2 ? cosf(t * f) : sinf(t * f));
+            }
+        }
+        s_in[j][o] = val;
+    }
+    __syncthreads();
+    const size_t mat = (size_t)kC * kC + kC;
+    float acc[kTimeJets];
+    {   // temb = temb_net(emb); act = swish(temb)
+        const float* W = wT;
+        const float bias = __ldg(W + (size_t)kC * kC + o);
+#pragma unroll
+        for (int j = 0; j < kTimeJets; ++j) acc[j] = bias;
+        for (int c = 0; c < kC; ++c) {
+            const float w = __ldg(W + (size_t)c * kC + o);
+#pragma unroll
+            for (int j = 0; j < kTimeJets; ++j) acc[j] = fmaf(w, s_in[j][c], acc[j]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kTimeJets; ++j) s_in[j][o] = acc[j] / (1.0f + expf(-acc[j]));
+    __syncthreads();
+    for (int m = 0; m < 2 * nblk; ++m) {
+        const float* W = wT + (size_t)(1 + m) * mat;
+        const float bias = __ldg(W + (size_t)kC * kC + o);
+#pragma unroll
+        for (int j = 0; j < kTimeJets; ++j) acc[j] = bias;
+        for (int c = 0; c < kC; ++c) {
+            const float w = __ldg(W + (size_t)c * kC + o);
+#pragma unroll
+            for (int j = 0; j < kTimeJets; ++j) acc[j] = fmaf(w, s_in[j][c], acc[j]);
+        }
+        float* out = m < nblk ? tb1 : tb2;
+        const int blk = m < nblk ? m : m - nblk;
+#pragma unroll
+        for (int j = 0; j < kTimeJets; ++j)
+            if (j0 + j < B) out[((size_t)(j0 + j) * nblk + blk) * kC + o] = acc[j];
+    }
+}
+
+// ---- rate + nearest particle (noising.py:166-216; transdimensional_model.py:313-339) -----------------------------------
+__device__ __forceinline__ float fr_rate(const MmbForwardRate& fr, float t) {
+    return fr.kind == 1 ? fr.scalar : fr.scalar * (t > fr.rate_cut_t ? 1.0f : 0.0f) + fr.offset;
+}
+__device__ __forceinline__ float fr_integral(const MmbForwardRate& fr, float t) {
+    return fr.kind == 1 ? fr.scalar * t : (t - fr.rate_cut_t) * fr.scalar * (t > fr.rate_cut_t ? 1.0f : 0.0f) + fr.offset * t;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// one warp per jet
+__global__ void __launch_bounds__(128) trans_rate_kernel(const float* __restrict__ x0_logits, const float* __restrict__ near_logits,
+                                                         const int32_t* __restrict__ dims, const float* __restrict__ ts, int ts_stride,
+                                                         const int32_t* __restrict__ nearest_in, const float* __restrict__ u_nearest,
+                                                         MmbForwardRate fr, const float* __restrict__ logfact, int B, int N, int R,
+                                                         float* __restrict__ rate, int32_t* __restrict__ nearest_out) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const float t = __ldg(ts + (size_t)b * ts_stride);
+    const int d = dims[b];
+    const float* lg = x0_logits + (size_t)b * R;
+    const float I = fr_integral(fr, t), logI = logf(I);
+    float mx = -INFINITY;
+    for (int i = d - 1 + lane; i < R; i += 32) mx = fmaxf(mx, lg[i]);
+    mx = warp_max(mx);
+    float z = 0.0f;
+    for (int i = d - 1 + lane; i < R; i += 32) z += expf_exact(lg[i] - mx);
+    z = warp_sum(z);
+    float acc = 0.0f;
+    for (int i = d - 1 + lane; i < R; i += 32) {
+        const float prob = expf_exact(lg[i] - mx) / z;
+        float ratio;
+        if (d > 1) {
+            ratio = fmaxf((1.0f / I) * (float)((i + 1) - d), 0.0f);
+        } else {   // x_t has one particle: ratio of Poisson probabilities with the truncated normaliser (noising.py:199-212)
+            auto logp = [&](int k) { return (k == 0 ? 0.0f : (float)k * logI) - I - __ldg(logfact + k); };
+            float m2 = -INFINITY;
+            for (int j = 0; j < 2 * R; ++j) m2 = fmaxf(m2, logp(i + j));
+            float se = 0.0f;
+            for (int j = 0; j < 2 * R; ++j) se += expf(logp(i + j) - m2);
+            const float dim1 = m2 + logf(se);
+            const float dim2 = i == 0 ? -1000.0f : logp(i - 1);
+            ratio = expf(dim2 - dim1);
+        }
+        acc += ratio * prob;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) rate[b] = fr_rate(fr, t) * acc;
+    // nearest particle: given, or multinomial(softmax(near_atom_logits)) over ALL N slots by inverse CDF — the scan is
+    // sequential in fp32 so that the chosen index is bit-identical to the oracle's
+    if (lane == 0 && nearest_out) {
+        int near;
+        if (nearest_in) near = nearest_in[b];
+        else {
+            const float* nl = near_logits + (size_t)b * N;
+            float m = -INFINITY, zz = 0.0f, c = 0.0f;
+            for (int n = 0; n < N; ++n) m = nl[n] > m ? nl[n] : m;
+            for (int n = 0; n < N; ++n) zz = __fadd_rn(zz, expf_exact(__fadd_rn(nl[n], -m)));
+            const float u = u_nearest[b];
+            near = N - 1;
+            for (int n = 0; n < N; ++n) {
+                c = __fadd_rn(c, __fdiv_rn(expf_exact(__fadd_rn(nl[n], -m)), zz));
+                if (u < c) { near = n; break; }
+            }
+        }
+        nearest_out[b] = near;
+    }
+}
+
+// ---- mean / std of the particle a birth adds (transdimensional_model.py:369-424); one warp per jet ------------------------
+__global__ void __launch_bounds__(128) trans_auto_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask,
+                                                         const int32_t* __restrict__ nearest, const float* __restrict__ vec_w,
+                                                         const float* __restrict__ post_auto, const int32_t* __restrict__ dims,
+                                                         int B, int N, int S, float* __restrict__ new_mean, float* __restrict__ new_std,
+                                                         float* __restrict__ auto_mean, float* __restrict__ auto_std) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int F = 3 + S, near = nearest[b];
+    const float* xb = x + (size_t)b * N * 3;
+    const float xa0 = xb[near * 3], xa1 = xb[near * 3 + 1], xa2 = xb[near * 3 + 2];
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+    for (int n = lane; n < N; n += 32) {
+        const float m = mask[(size_t)b * N + n] ? 1.0f : 0.0f, w = vec_w[(size_t)b * N + n];
+        const float d0 = (xa0 - xb[n * 3]) * m, d1 = (xa1 - xb[n * 3 + 1]) * m, d2 = (xa2 - xb[n * 3 + 2]) * m;
+        const float inv = 1.0f / (sqrtf((d0 * d0 + d1 * d1) + d2 * d2) + 1e-3f);
+        p0 = fmaf(w, d0 * inv, p0); p1 = fmaf(w, d1 * inv, p1); p2 = fmaf(w, d2 * inv, p2);
+    }
+    p0 = xa0 + warp_sum(p0); p1 = xa1 + warp_sum(p1); p2 = xa2 + warp_sum(p2);
+    const float* pa = post_auto + (size_t)b * (2 * S + 1);
+    const int slot = dims[b];
+    for (int i = lane; i < F; i += 32) {
+        const float mean = i == 0 ? p0 : i == 1 ? p1 : i == 2 ? p2 : pa[1 + (i - 3)];
+        const float sd = i < 3 ? pa[0] : pa[1 + S + (i - 3)];
+        if (new_mean) { new_mean[(size_t)b * F + i] = mean; new_std[(size_t)b * F + i] = sd; }
+        if (auto_mean && slot < N) {   // get_next_dim_added_mask (structure.py:175-184): only the slot a birth fills is non-zero
+            const size_t at = (size_t)b * N * F + (i < 3 ? (size_t)slot * 3 + i : (size_t)N * 3 + (size_t)slot * S + (i - 3));
+            auto_mean[at] = mean;
+            auto_std[at] = sd;
+        }
+    }
+}
+
+// ---- one sampler update (sampler.py:221-255 + adjust_st_batch) -----------------------------------------------------------
+// Philox streams of the sampler: 2,3,4 = diffusion noise of a particle (12 normals, 11 used); 5 = per-jet uniforms
+// (word 0: nearest particle, word 1: birth); 6,7,8 = the new particle's 11 normals.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
+    const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(6.283185307179586f * u2, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+__device__ __forceinline__ void philox_normals12(uint64_t seed, uint64_t jet, int stream0, int step, int idx, float (&z)[12]) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const uint4 r = philox_block(seed, jet, stream0 + q, step, idx);
+        box_muller(r.x, r.y, z[4 * q], z[4 * q + 1]);
+        box_muller(r.z, r.w, z[4 * q + 2], z[4 * q + 3]);
+    }
+}
+__device__ __forceinline__ float nan_to_num(float a) {
+    return a != a ? 0.0f : fminf(fmaxf(a, -3.4028234664e38f), 3.4028234664e38f);
+}
+__device__ __forceinline__ float softplus(float a) { return a > 20.0f ? a : log1pf(expf(a)); }
+
+// block-wide sum of three values (128 threads), result broadcast
+__device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (*s_red)[4]) {
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    const int w = threadIdx.x >> 5;
+    __syncthreads();   // previous use of s_red is over
+    if ((threadIdx.x & 31) == 0) { s_red[0][w] = a; s_red[1][w] = b; s_red[2][w] = c; }
+    __syncthreads();
+    a = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
+    b = (s_red[1][0] + s_red[1][1]) + (s_red[1][2] + s_red[1][3]);
+    c = (s_red[2][0] + s_red[2][1]) + (s_red[2][2] + s_red[2][3]);
+}
+
+// one block (128 threads) per jet, thread n = particle slot n
+template <int S>
+__global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __restrict__ x, float* __restrict__ onehot, int32_t* __restrict__ dims,
+                                                                   const float* __restrict__ v, const float* __restrict__ logits,
+                                                                   const float* __restrict__ rate, const float* __restrict__ new_mean,
+                                                                   const float* __restrict__ new_std, float c_decay, float c_score,
+                                                                   float c_noise, float inv_std, float jump_dt,
+                                                                   const float* __restrict__ z_diff, const float* __restrict__ u_jump,
+                                                                   const float* __restrict__ z_new, uint64_t seed, uint64_t jet_offset,
+                                                                   int step, int N) {
+    __shared__ float s_red[3][4];
+    constexpr int F = 3 + S;
+    const int b = blockIdx.x, n = threadIdx.x;
+    const int dim = dims[b];
+    const bool in = n < N, live = n < dim;
+    const size_t pi = (size_t)b * N + n;
+    float xs[3] = {0, 0, 0}, oh[S], z[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) z[i] = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) oh[s] = 0.0f;
+    float vs[3] = {0, 0, 0}, lg[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) lg[s] = 0.0f;
+    if (in) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { xs[c] = x[pi * 3 + c]; vs[c] = __ldg(v + pi * 3 + c); }
+        if constexpr (S % 4 == 0) {
+#pragma unroll
+            for (int s = 0; s < S; s += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(onehot + pi * S + s);
+                const float4 l = __ldg(reinterpret_cast<const float4*>(logits + pi * S + s));
+                oh[s] = a.x; oh[s + 1] = a.y; oh[s + 2] = a.z; oh[s + 3] = a.w;
+                lg[s] = l.x; lg[s + 1] = l.y; lg[s + 2] = l.z; lg[s + 3] = l.w;
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < S; ++s) { oh[s] = onehot[pi * S + s]; lg[s] = __ldg(logits + pi * S + s); }
+        }
+    }
+    if (live && c_noise != 0.0f) {
+        if (z_diff) {
+            const float* zb = z_diff + (size_t)b * N * F;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) z[c] = __ldg(zb + n * 3 + c);
+#pragma unroll
+            for (int s = 0; s < S; ++s) z[3 + s] = __ldg(zb + (size_t)N * 3 + n * S + s);
+        } else {
+            philox_normals12(seed, jet_offset + (uint64_t)b, 2, step, n, z);
+        }
+    }
+    // noise: delete_dims + centre-of-mass removal of its continuous part (sampler.py:224-229)
+    {
+        float a0 = z[0], a1 = z[1], a2 = z[2];
+        block_sum3(a0, a1, a2, s_red);
+        const float inv = 1.0f / (float)dim;
+        if (live) { z[0] -= a0 * inv; z[1] -= a1 * inv; z[2] -= a2 * inv; }
+    }
+    // Euler-Maruyama on the live slots (sampler.py:221-231); dead slots only decay (they hold zeros)
+    const float m = live ? 1.0f : 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float a = c_decay * xs[c] + m * (c_score * -(inv_std * vs[c]));
+        if (c_noise != 0.0f) a = a + m * (c_noise * z[c]);
+        xs[c] = nan_to_num(a);
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        float a = c_decay * oh[s] + m * (c_score * -(inv_std * lg[s]));
+        if (c_noise != 0.0f) a = a + m * (c_noise * z[3 + s]);
+        oh[s] = nan_to_num(a);
+    }
+    // adjust_st_batch: remove the mean of the continuous features over the live particles
+    {
+        float a0 = xs[0], a1 = xs[1], a2 = xs[2];
+        block_sum3(a0, a1, a2, s_red);
+        const float inv = 1.0f / (float)dim;
+        if (live) { xs[0] -= a0 * inv; xs[1] -= a1 * inv; xs[2] -= a2 * inv; }
+    }
+    // birth (sampler.py:238-255): the new particle takes slot `dim`
+    const float uj = u_jump ? __ldg(u_jump + b) : u01(philox_block(seed, jet_offset + (uint64_t)b, 5, step, 0).y);
+    const bool born = (uj < __ldg(rate + b) * jump_dt) && dim < N;
+    int new_dim = dim;
+    if (born) {
+        new_dim = dim + 1;
+        if (n == dim) {
+            float zn[12];
+            if (z_new) {
+#pragma unroll
+                for (int i = 0; i < F; ++i) zn[i] = __ldg(z_new + (size_t)b * F + i);
+            } else {
+                philox_normals12(seed, jet_offset + (uint64_t)b, 6, step, 0, zn);
+            }
+            const float* nm = new_mean + (size_t)b * F;
+            const float* ns = new_std + (size_t)b * F;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xs[c] = nan_to_num(__ldg(nm + c) + zn[c] * softplus(__ldg(ns + c)));
+#pragma unroll
+            for (int s = 0; s < S; ++s) oh[s] = nan_to_num(__ldg(nm + 3 + s) + zn[3 + s] * softplus(__ldg(ns + 3 + s)));
+        }
+    }
+    {   // second adjust_st_batch with the new multiplicity (it runs whether or not a particle was born)
+        float a0 = xs[0], a1 = xs[1], a2 = xs[2];
+        block_sum3(a0, a1, a2, s_red);
+        const float inv = 1.0f / (float)new_dim;
+        if (n < new_dim) { xs[0] -= a0 * inv; xs[1] -= a1 * inv; xs[2] -= a2 * inv; }
+    }
+    if (in) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[pi * 3 + c] = xs[c];
+        if constexpr (S % 4 == 0) {
+#pragma unroll
+            for (int s = 0; s < S; s += 4) *reinterpret_cast<float4*>(onehot + pi * S + s) = make_float4(oh[s], oh[s + 1], oh[s + 2], oh[s + 3]);
+        } else {
+#pragma unroll
+            for (int s = 0; s < S; ++s) onehot[pi * S + s] = oh[s];
+        }
+    }
+    if (n == 0 && born) dims[b] = new_dim;
+}
+
+// broadcast ts[step] for the sampler's per-jet uniform of the nearest particle when drawn in-kernel
+__global__ void trans_philox_u_near_kernel(float* __restrict__ u, uint64_t seed, uint64_t jet_offset, int step, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) u[b] = u01(philox_block(seed, jet_offset + (uint64_t)b, 5, step, 0).x);
+}
+
+inline size_t align64(size_t n) { return (n + 63) & ~(size_t)63; }
+
+// workspace carve-up shared by the forward and the sampler (in floats, every region 256-byte aligned)
+struct TransWs {
+    size_t k, mask, M, Z, temb, tb1, tb2, v, logits, hidden, near_logits, vec_w, x0_logits, post_auto, nearest, new_mean, new_std, rate,
+        u_near, ts, total;
+    TransWs(const MmbEpicDims& e, const MmbTransDims& d, int B, int N, int n_time) {
+        const size_t P = (size_t)B * N, F = 3 + d.vocab_size;
+        size_t at = 0;
+        auto take = [&](size_t floats) { const size_t o = at; at += align64(floats); return o; };
+        k = take((P + 3) / 4); mask = take((P + 3) / 4);
+        M = take((size_t)N * d.vocab_size); Z = take((size_t)N * d.vocab_size);
+        temb = take((size_t)n_time * e.dim_time_emb);
+        tb1 = take((size_t)n_time * d.n_blocks * kC); tb2 = take((size_t)n_time * d.n_blocks * kC);
+        v = take(P * 3); logits = take(P * d.vocab_size); hidden = take(P * e.dim_hidden_local);
+        near_logits = take(P); vec_w = take(P); x0_logits = take((size_t)B * d.max_particles);
+        post_auto = take((size_t)B * (2 * d.vocab_size + 1)); nearest = take(B); new_mean = take((size_t)B * F);
+        new_std = take((size_t)B * F); rate = take(B); u_near = take(B); ts = take(n_time);
+        total = at;
+    }
+};
+
+}  // namespace
+
+// ---- host -------------------------------------------------------------------------------------------------------------
+static size_t trans_floats(const MmbTransDims& d) {
+    const size_t C = d.transformer_dim, lin = C * C + C, H = d.hidden, S = d.vocab_size, R = d.max_particles;
+    const size_t block = 6 * C + 6 * lin;
+    return lin + 2 * (size_t)d.n_blocks * lin + (C * (H + S) + C) + d.n_blocks * block + lin + (R * C + R) + (C + 1) +
+           (C * (H + S + 3) + C) + d.n_blocks * block + (C + 1) + lin + ((2 * S + 1) * C + (2 * S + 1));
+}
+
+static bool trans_dims_ok(const MmbTransDims& d) {
+    return d.transformer_dim == kC && d.n_heads == 2 && d.n_blocks >= 1 && d.n_blocks <= 4 && d.hidden >= 1 && d.vocab_size >= 1 &&
+           d.hidden + d.vocab_size + 3 <= 32 && d.max_particles >= 1 && d.max_particles <= 128 && 2 * d.vocab_size + 1 <= 128;
+}
+
+static void trans_destroy(TransHeads* h) {
+    if (!h) return;
+    tf_stack_free(&h->s1);
+    tf_stack_free(&h->s2);
+    if (h->time_wT) cudaFree(h->time_wT);
+    if (h->logfact) cudaFree(h->logfact);
+    delete h;
+}
+
+static int trans_create(const MmbTransDims* dims, const float* W, size_t n_floats, int device, TransHeads** out) {
+    const MmbTransDims d = *dims;
+    if (!trans_dims_ok(d))
+        return fail(MMB_EUNSUPPORTED, "trans heads are built for transformer_dim=128, n_heads=2, 1..4 blocks, hidden+vocab+3<=32, <=128 particles");
+    if (n_floats != trans_floats(d)) return fail(MMB_EINVAL, "trans heads blob has %zu floats, layout wants %zu", n_floats, trans_floats(d));
+    const int C = kC, H = d.hidden, S = d.vocab_size, R = d.max_particles, nb = d.n_blocks, PA = 2 * S + 1;
+    const size_t lin = (size_t)C * C + C, block = 6 * (size_t)C + 6 * lin;
+    const float* temb_net = W;
+    const float* s1 = W + lin + 2 * (size_t)nb * lin;
+    const float* s1_blocks = s1 + (size_t)C * (H + S) + C;
+    const float* pre_rate = s1_blocks + (size_t)nb * block;
+    const float* post_rate = pre_rate + lin;
+    const float* near_w = post_rate + (size_t)R * C + R;
+    const float* s2 = near_w + C + 1;
+    const float* s2_blocks = s2 + (size_t)C * (H + S + 3) + C;
+    const float* vecw = s2_blocks + (size_t)nb * block;
+    const float* pre_auto = vecw + C + 1;
+    const float* post_auto = pre_auto + lin;
+    // fold mean -> Linear(C->C) -> Linear(C->n): W = post pre, b = post pre_b + post_b (the mean commutes with the first Linear)
+    auto fold = [&](const float* pre, const float* post, int n_out, std::vector<float>& Wf, std::vector<float>& bf) {
+        Wf.assign((size_t)n_out * C, 0.0f);
+        bf.assign(n_out, 0.0f);
+        for (int o = 0; o < n_out; ++o) {
+            for (int c = 0; c < C; ++c) {
+                double acc = 0;
+                for (int j = 0; j < C; ++j) acc += (double)post[(size_t)o * C + j] * pre[(size_t)j * C + c];
+                Wf[(size_t)o * C + c] = (float)acc;
+            }
+            double acc = post[(size_t)n_out * C + o];
+            for (int j = 0; j < C; ++j) acc += (double)post[(size_t)o * C + j] * pre[(size_t)C * C + j];
+            bf[o] = (float)acc;
+        }
+    };
+    std::vector<float> w1, b1, w2, b2;
+    fold(pre_rate, post_rate, R, w1, b1);
+    fold(pre_auto, post_auto, PA, w2, b2);
+    // time matrices, transposed for coalesced reads
+    const int n_mat = 1 + 2 * nb;
+    std::vector<float> tw((size_t)n_mat * lin);
+    for (int m = 0; m < n_mat; ++m) {
+        const float* src = m == 0 ? temb_net : W + lin + (size_t)(m - 1) * lin;
+        float* dst = tw.data() + (size_t)m * lin;
+        for (int o = 0; o < C; ++o)
+            for (int c = 0; c < C; ++c) dst[(size_t)c * C + o] = src[(size_t)o * C + c];
+        for (int o = 0; o < C; ++o) dst[(size_t)C * C + o] = src[(size_t)C * C + o];
+    }
+    std::vector<float> lf((size_t)3 * R + 2);
+    for (size_t k = 0; k < lf.size(); ++k) lf[k] = (float)lgamma((double)k + 1.0);
+
+    int prev = 0;
+    if (int rc = cuda_ok(cudaGetDevice(&prev), "cudaGetDevice")) return rc;
+    if (int rc = cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return rc;
+    TransHeads* h = new TransHeads{d, device, 148, TfStack{}, TfStack{}, nullptr, nullptr};
+    int rc = cuda_ok(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device), "sm count");
+    if (!rc) rc = tf_stack_build(&h->s1, s1, H + S, s1_blocks, nb, near_w, near_w[C], w1.data(), b1.data(), R);
+    if (!rc) rc = tf_stack_build(&h->s2, s2, H + S + 3, s2_blocks, nb, vecw, vecw[C], w2.data(), b2.data(), PA);
+    if (!rc) rc = cuda_ok(cudaMalloc(&h->time_wT, tw.size() * 4), "cudaMalloc time weights");
+    if (!rc) rc = cuda_ok(cudaMemcpy(h->time_wT, tw.data(), tw.size() * 4, cudaMemcpyHostToDevice), "time weights upload");
+    if (!rc) rc = cuda_ok(cudaMalloc(&h->logfact, lf.size() * 4), "cudaMalloc log-factorials");
+    if (!rc) rc = cuda_ok(cudaMemcpy(h->logfact, lf.data(), lf.size() * 4, cudaMemcpyHostToDevice), "log-factorials upload");
+    cudaSetDevice(prev);
+    if (rc) { trans_destroy(h); return rc; }
+    *out = h;
+    return MMB_OK;
+}
+
+static int check_pair(const EpicModel* m, const TransHeads* h, int N) {
+    if (m->dims.dim_hidden_local != h->d.hidden || m->dims.vocab_size != h->d.vocab_size || m->dims.dim_continuous != 3)
+        return fail(MMB_EINVAL, "trunk (H=%d, S=%d, Dc=%d) does not match the trans heads (H=%d, S=%d, Dc=3)", m->dims.dim_hidden_local,
+                    m->dims.vocab_size, m->dims.dim_continuous, h->d.hidden, h->d.vocab_size);
+    if (m->dims.disc_head_hidden != 0) return fail(MMB_EINVAL, "the trans trunk is created without a discrete head (fc_layer is never applied)");
+    if (N < 1 || N > h->d.max_particles) return fail(MMB_EINVAL, "N=%d outside 1..max_particles=%d", N, h->d.max_particles);
+    if (m->dims.dim_time_emb > kC) return fail(MMB_EUNSUPPORTED, "time embedding wider than 128");
+    return MMB_OK;
+}
+
+// everything of one evaluation after the time terms; ts / tb pointers with stride 0 = one time for all jets
+static int trans_eval(const EpicModel* m, const TransHeads* h, const float* x, const float* onehot, const int32_t* dims,
+                      const float* ts, int ts_stride, const float* temb, const float* tb1, const float* tb2, int time_stride,
+                      const int32_t* nearest_in, const float* u_nearest, const MmbForwardRate& fr, int B, int N, float* ws,
+                      const TransWs& L, float* x0_logits_out, float* near_logits_out, float* auto_mean, float* auto_std,
+                      int precision, cudaStream_t s) {
+    const int S = h->d.vocab_size, H = h->d.hidden, R = h->d.max_particles, nb = h->d.n_blocks, T = m->dims.dim_time_emb;
+    const size_t P = (size_t)B * N;
+    uint8_t* k = reinterpret_cast<uint8_t*>(ws + L.k);
+    uint8_t* mask = reinterpret_cast<uint8_t*>(ws + L.mask);
+    int32_t* nearest = reinterpret_cast<int32_t*>(ws + L.nearest);
+    float* x0l = x0_logits_out ? x0_logits_out : ws + L.x0_logits;
+    float* nl = near_logits_out ? near_logits_out : ws + L.near_logits;
+    trans_colstats_kernel<<<(N * S + 31) / 32, 256, 0, s>>>(onehot, B, N * S, ws + L.M, ws + L.Z);
+    trans_tokens_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(onehot, ws + L.M, ws + L.Z, dims, B, N, S, k, mask);
+    if (int rc = cuda_ok(cudaGetLastError(), "trans tokens launch")) return rc;
+    int rc = mmb_epic_forward(reinterpret_cast<const MmbEpicModel*>(m), x, k, mask, temb, time_stride ? T : 0, B, N, ws + L.v, ws + L.logits,
+                              ws + L.hidden, precision, s);
+    if (rc) return rc;
+    TfStackIO io{};
+    io.mode = 1; io.H = H; io.S = S; io.hidden = ws + L.hidden; io.mask = mask; io.onehot = onehot;
+    io.tbias = tb1; io.tbias_stride = time_stride ? nb * kC : 0; io.dot_out = nl; io.jet_out = x0l;
+    if ((rc = launch_tf_stack(&h->s1, h->sm_count, io, B, N, s))) return rc;
+    trans_rate_kernel<<<(B + 3) / 4, 128, 0, s>>>(x0l, nl, dims, ts, ts_stride, nearest_in, u_nearest, fr, h->logfact, B, N, R, ws + L.rate, nearest);
+    if ((rc = cuda_ok(cudaGetLastError(), "trans rate launch"))) return rc;
+    io.mode = 2; io.x = x; io.nearest = nearest; io.tbias = tb2; io.dot_out = ws + L.vec_w; io.jet_out = ws + L.post_auto;
+    if ((rc = launch_tf_stack(&h->s2, h->sm_count, io, B, N, s))) return rc;
+    trans_auto_kernel<<<(B + 3) / 4, 128, 0, s>>>(x, mask, nearest, ws + L.vec_w, ws + L.post_auto, dims, B, N, S, ws + L.new_mean,
+                                                 ws + L.new_std, auto_mean, auto_std);
+    return cuda_ok(cudaGetLastError(), "trans auto launch");
+}
+
+static int launch_sampler_update(float* x, float* onehot, int32_t* dims, const float* v, const float* logits, const float* rate,
+                                 const float* new_mean, const float* new_std, float c_decay, float c_score, float c_noise, float inv_std,
+                                 float jump_dt, const float* z_diff, const float* u_jump, const float* z_new, uint64_t seed,
+                                 uint64_t jet_offset, int step, int B, int N, int S, cudaStream_t s) {
+    if (N > 128 || N < 1) return fail(MMB_EUNSUPPORTED, "sampler update handles 1..128 particle slots per jet");
+#define MMB_UPD(SV)                                                                                                                  \
+    trans_sampler_update_kernel<SV><<<B, 128, 0, s>>>(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score, c_noise, \
+                                                      inv_std, jump_dt, z_diff, u_jump, z_new, seed, jet_offset, step, N)
+    switch (S) {
+        case 4: MMB_UPD(4); break;
+        case 5: MMB_UPD(5); break;
+        case 6: MMB_UPD(6); break;
+        case 8: MMB_UPD(8); break;
+        default: return fail(MMB_EUNSUPPORTED, "sampler update is built for vocab sizes 4, 5, 6, 8 (got %d)", S);
+    }
+#undef MMB_UPD
+    return cuda_ok(cudaGetLastError(), "sampler update launch");
+}
+
+}  // namespace mmb
+
+using namespace mmb;
+
+extern "C" {
+
+size_t mmb_trans_packed_floats(const MmbTransDims* dims) { return dims ? trans_floats(*dims) : 0; }
+
+int mmb_trans_create(const MmbTransDims* dims, const float* packed, size_t n_floats, int device, MmbTransHeads** out) {
+    if (!dims || !packed || !out) return fail(MMB_EINVAL, "mmb_trans_create: null argument");
+    TransHeads* h = nullptr;
+    if (int rc = trans_create(dims, packed, n_floats, device, &h)) return rc;
+    *out = reinterpret_cast<MmbTransHeads*>(h);
+    return MMB_OK;
+}
+
+void mmb_trans_destroy(MmbTransHeads* heads) { trans_destroy(reinterpret_cast<TransHeads*>(heads)); }
+
+size_t mmb_trans_forward_workspace_bytes(const MmbEpicModel* trunk, const MmbTransHeads* heads, int B, int N) {
+    if (!trunk || !heads || B < 0 || N < 0) return 0;
+    return TransWs(reinterpret_cast<const EpicModel*>(trunk)->dims, reinterpret_cast<const TransHeads*>(heads)->d, B, N, B).total * sizeof(float);
+}
+
+int mmb_trans_forward(const MmbEpicModel* trunk, const MmbTransHeads* heads, const float* x, const float* onehot, const int32_t* dims,
+                      const float* ts, const int32_t* nearest_in, const float* u_nearest, const MmbForwardRate* forward_rate, int B, int N,
+                      float* d_xt, float* rate, float* auto_mean, float* auto_std, float* x0_dim_logits, float* near_atom_logits,
+                      int32_t* nearest_out, void* workspace, size_t workspace_bytes, int precision, void* stream) {
+    const EpicModel* m = reinterpret_cast<const EpicModel*>(trunk);
+    const TransHeads* h = reinterpret_cast<const TransHeads*>(heads);
+    if (!m || !h || !x || !onehot || !dims || !ts || !forward_rate || !d_xt || !rate || !x0_dim_logits || !near_atom_logits || !workspace)
+        return fail(MMB_EINVAL, "mmb_trans_forward: null argument");
+    if (!nearest_in && !u_nearest) return fail(MMB_EINVAL, "mmb_trans_forward: give nearest_in or u_nearest");
+    if ((auto_mean == nullptr) != (auto_std == nullptr)) return fail(MMB_EINVAL, "mmb_trans_forward: auto_mean and auto_std go together");
+    if (B < 0) return fail(MMB_EINVAL, "mmb_trans_forward: negative size");
+    if (int rc = check_pair(m, h, N)) return rc;
+    const TransWs L(m->dims, h->d, B, N, B);
+    if (workspace_bytes < L.total * sizeof(float)) return fail(MMB_ENOMEM, "mmb_trans_forward: workspace %zu B < %zu B", workspace_bytes, L.total * sizeof(float));
+    if (B == 0) return MMB_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* ws = static_cast<float*>(workspace);
+    const int S = h->d.vocab_size, F = 3 + S, T = m->dims.dim_time_emb;
+    trans_time_kernel<<<(B + kTimeJets - 1) / kTimeJets, kC, 0, s>>>(h->time_wT, h->d.n_blocks, ts, B, T, ws + L.temb, ws + L.tb1, ws + L.tb2);
+    if (int rc = cuda_ok(cudaGetLastError(), "trans time launch")) return rc;
+    if (auto_mean) {
+        if (int rc = cuda_ok(cudaMemsetAsync(auto_mean, 0, (size_t)B * N * F * sizeof(float), s), "auto_mean clear")) return rc;
+        if (int rc = cuda_ok(cudaMemsetAsync(auto_std, 0, (size_t)B * N * F * sizeof(float), s), "auto_std clear")) return rc;
+    }
+    if (int rc = trans_eval(m, h, x, onehot, dims, ts, 1, ws + L.temb, ws + L.tb1, ws + L.tb2, 1, nearest_in, u_nearest, *forward_rate, B, N,
+                            ws, L, x0_dim_logits, near_atom_logits, auto_mean, auto_std, precision, s))
+        return rc;
+    // D_xt = [all continuous slots | all one-hot slots] per jet (transdimensional_model.py:277-280)
+    int rc = cuda_ok(cudaMemcpy2DAsync(d_xt, (size_t)N * F * 4, ws + L.v, (size_t)N * 3 * 4, (size_t)N * 3 * 4, B, cudaMemcpyDeviceToDevice, s), "D_xt v");
+    if (!rc) rc = cuda_ok(cudaMemcpy2DAsync(d_xt + (size_t)N * 3, (size_t)N * F * 4, ws + L.logits, (size_t)N * S * 4, (size_t)N * S * 4, B,
+                                            cudaMemcpyDeviceToDevice, s), "D_xt logits");
+    if (!rc) rc = cuda_ok(cudaMemcpyAsync(rate, ws + L.rate, (size_t)B * 4, cudaMemcpyDeviceToDevice, s), "rate");
+    if (!rc && nearest_out) rc = cuda_ok(cudaMemcpyAsync(nearest_out, ws + L.nearest, (size_t)B * 4, cudaMemcpyDeviceToDevice, s), "nearest");
+    return rc;
+}
+
+size_t mmb_trans_sample_workspace_bytes(const MmbEpicModel* trunk, const MmbTransHeads* heads, int B, int N) {
+    if (!trunk || !heads || B < 0 || N < 0) return 0;
+    // time tables for up to 4096 steps
+    return TransWs(reinterpret_cast<const EpicModel*>(trunk)->dims, reinterpret_cast<const TransHeads*>(heads)->d, B, N, 4096).total * sizeof(float);
+}
+
+int mmb_trans_sample(const MmbEpicModel* trunk, const MmbTransHeads* heads, float* x, float* onehot, int32_t* dims,
+                     const MmbJumpSchedule* sch, const MmbForwardRate* forward_rate, const float* z_diff, const float* u_near,
+                     const float* u_jump, const float* z_new, uint64_t seed, uint64_t jet_offset, int B, int N, void* workspace,
+                     size_t workspace_bytes, int precision, void* stream) {
+    const EpicModel* m = reinterpret_cast<const EpicModel*>(trunk);
+    const TransHeads* h = reinterpret_cast<const TransHeads*>(heads);
+    if (!m || !h || !x || !onehot || !dims || !sch || !forward_rate || !workspace) return fail(MMB_EINVAL, "mmb_trans_sample: null argument");
+    if (!sch->ts || !sch->c_decay || !sch->c_score || !sch->c_noise || !sch->inv_std) return fail(MMB_EINVAL, "mmb_trans_sample: incomplete schedule");
+    const int n = sch->n_steps;
+    if (B < 0 || n < 0 || n > 4096) return fail(MMB_EINVAL, "mmb_trans_sample: 0..4096 steps");
+    const bool injected = z_diff || u_near || u_jump || z_new;
+    if (injected && !(z_diff && u_near && u_jump && z_new)) return fail(MMB_EINVAL, "mmb_trans_sample: inject all four noise arrays or none");
+    if (int rc = check_pair(m, h, N)) return rc;
+    const TransWs L(m->dims, h->d, B, N, 4096);
+    if (workspace_bytes < L.total * sizeof(float)) return fail(MMB_ENOMEM, "mmb_trans_sample: workspace too small");
+    if (B == 0 || n == 0) return MMB_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* ws = static_cast<float*>(workspace);
+    const int S = h->d.vocab_size, F = 3 + S, T = m->dims.dim_time_emb, nb = h->d.n_blocks;
+    // all jets share ts: the time terms of every step are computed once, as a batch of n "jets"
+    float* ts_dev = ws + L.ts;
+    if (int rc = cuda_ok(cudaMemcpyAsync(ts_dev, sch->ts, (size_t)n * 4, cudaMemcpyHostToDevice, s), "schedule upload")) return rc;
+    trans_time_kernel<<<(n + kTimeJets - 1) / kTimeJets, kC, 0, s>>>(h->time_wT, nb, ts_dev, n, T, ws + L.temb, ws + L.tb1, ws + L.tb2);
+    if (int rc = cuda_ok(cudaGetLastError(), "trans time launch")) return rc;
+    for (int i = 0; i < n; ++i) {
+        const float* un = u_near ? u_near + (size_t)i * B : ws + L.u_near;
+        if (!u_near) {
+            trans_philox_u_near_kernel<<<(B + 255) / 256, 256, 0, s>>>(ws + L.u_near, seed, jet_offset, i, B);
+            if (int rc = cuda_ok(cudaGetLastError(), "u_near launch")) return rc;
+        }
+        int rc = trans_eval(m, h, x, onehot, dims, ts_dev + i, 0, ws + L.temb + (size_t)i * T, ws + L.tb1 + (size_t)i * nb * kC,
+                            ws + L.tb2 + (size_t)i * nb * kC, 0, nullptr, un, *forward_rate, B, N, ws, L, nullptr, nullptr, nullptr, nullptr,
+                            precision, s);
+        if (!rc)
+            rc = launch_sampler_update(x, onehot, dims, ws + L.v, ws + L.logits, ws + L.rate, ws + L.new_mean, ws + L.new_std, sch->c_decay[i],
+                                       sch->c_score[i], sch->c_noise[i], sch->inv_std[i], sch->jump_dt,
+                                       z_diff ? z_diff + (size_t)i * B * N * F : nullptr, u_jump ? u_jump + (size_t)i * B : nullptr,
+                                       z_new ? z_new + (size_t)i * B * F : nullptr, seed, jet_offset, i, B, N, S, s);
+        if (rc) return rc;
+    }
+    return MMB_OK;
+}
+
+int mmb_trans_sampler_update(float* x, float* onehot, int32_t* dims, const float* v, const float* logits, const float* rate,
+                             const float* new_mean, const float* new_std, float c_decay, float c_score, float c_noise, float inv_std,
+                             float jump_dt, const float* z_diff, const float* u_jump, const float* z_new, uint64_t seed,
+                             uint64_t jet_offset, int step, int B, int N, int S, void* stream) {
+    if (!x || !onehot || !dims || !v || !logits || !rate || !new_mean || !new_std) return fail(MMB_EINVAL, "mmb_trans_sampler_update: null argument");
+    if (B < 0) return fail(MMB_EINVAL, "mmb_trans_sampler_update: negative size");
+    if (B == 0) return MMB_OK;
+    return launch_sampler_update(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score, c_noise, inv_std, jump_dt, z_diff,
+                                 u_jump, z_new, seed, jet_offset, step, B, N, S, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+"""GPU: the trans-dimensional jump diffusion (BASELINE configs 3/4) through the C ABI,
+against the fp32 oracle and the fixture produced by the reference (tests/golden/make_golden_trans.py).
+
+Stated tolerances.  The two transformer stacks run ~16 chained bf16 GEMMs, three GroupNorms and a softmax per block:
+per-particle / per-jet head outputs within 3 % of the largest reference magnitude (as for the absorbing head).
+The trunk in fp32 is the oracle's arithmetic; its time embedding is evaluated with CUDA sinf/cosf instead of libm, so
+D_xt agrees to 2e-5 of its scale rather than bit for bit.  The birth rate is a smooth function of the x0-dimension
+logits: 5 % relative.  Discrete decisions (tokens, births, nearest particle) are bit-exact given identical inputs:
+the fused sampler update is checked against the oracle with the oracle's own network outputs fed to both sides.
+"""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import oracle_lib as ol
+from multimodal_particles_b200 import _native
+from multimodal_particles_b200.config_classes.transdimensional_unconditional_config import TransdimensionalEpicConfig
+from multimodal_particles_b200.transdimensional import (JumpSampler, StructuredDataBatch, TransdimensionalJumpDiffusion,
+                                                        jump_schedule)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def to_dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def close(got, want, frac, floor=1e-6):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got
+    assert np.isfinite(got).all()
+    err, scale = np.abs(got - want).max(), max(np.abs(want).max(), floor)
+    assert err <= frac * scale, (err, scale)
+
+
+@pytest.fixture(scope="module")
+def fixture(golden_dir):
+    z, cfg, model = ol.load_trans_golden(os.path.join(golden_dir, "trans.npz"))
+    packed = ol.trans_packed(model)
+    return z, cfg, model.to(DEV), packed
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_given_nearest_matches_reference(fixture, precision):
+    z, cfg, model, packed = fixture
+    net = model.net
+    net.model.precision = precision
+    st = model.make_batch(to_dev(z["fwd/x"]), to_dev(z["fwd/onehot"]), to_dev(z["fwd/dims"]))
+    B, N, S = z["fwd/onehot"].shape
+    D, rate, (am, asd), x0l, nal = net(st, to_dev(z["fwd/ts"]), forward_rate=model.forward_rate, predict="eps",
+                                       nearest_atom=to_dev(z["fwd/nearest"]))
+    assert D.shape == (B, N * (3 + S)) and rate.shape == (B, 1) and am.shape == D.shape and x0l.shape == (B, N) and nal.shape == (B, N)
+    close(D, z["fwd/d_xt"], 2e-5 if precision == "fp32" else 0.02)
+    close(x0l, z["fwd/x0_dim_logits"], 0.03)
+    close(nal, z["fwd/near_atom_logits"], 0.03)
+    np.testing.assert_allclose(rate.view(-1).cpu().numpy(), z["fwd/rate"], rtol=0.05, atol=1e-4)
+    close(am, z["fwd/auto_mean"], 0.03)
+    close(asd, z["fwd/auto_std"], 0.03)
+    # only the slot a birth fills is non-zero (structure.py:175-184); none when the jet is full
+    assert ((am.cpu().numpy() != 0) == (z["fwd/auto_mean"] != 0)).all()
+    assert torch.equal(net.model.last_nearest_atom.cpu(), torch.from_numpy(z["fwd/nearest"]))
+
+
+def test_forward_samples_nearest_by_inverse_cdf(fixture):
+    z, cfg, model, packed = fixture
+    net = model.net
+    net.model.precision = "bf16"
+    st = model.make_batch(to_dev(z["fwd/x"]), to_dev(z["fwd/onehot"]), to_dev(z["fwd/dims"]))
+    out = net(st, to_dev(z["fwd/ts"]), forward_rate=model.forward_rate, predict="eps", nearest_atom=None, sample_nearest_atom=True,
+              u_nearest=to_dev(z["fwd/u_near"]))
+    near = net.model.last_nearest_atom.cpu().numpy()
+    assert (near == z["fwd/nearest_sampled"]).mean() >= 5 / 6      # a draw within the bf16 tolerance of a CDF edge may move
+    same = near == z["fwd/nearest_sampled"]
+    close(out[2][0].cpu().numpy()[same], z["fwd/auto_mean_sampled"][same], 0.03)
+
+
+def test_tokens_in_the_underflow_regime(fixture):
+    """late sampler states of the fixture hold one-hot values ~1e3: the batch-axis softmax underflows into the denormals and
+    a wrong token changes D_xt by O(1).  fp32 trunk vs oracle on those states."""
+    z, cfg, model, packed = fixture
+    model.net.model.precision = "fp32"
+    fr = model.forward_rate.as_c()
+    for i in (12, 17, 19):
+        x, oh, dims = z["smp/x_traj"][i], z["smp/oh_traj"][i], z["smp/dims_traj"][i]
+        B = x.shape[0]
+        ts = np.full(B, z["smp/ts"][i], np.float32)
+        want = ol.trans_forward(packed, x, oh, dims, ts, fr, u_nearest=z["smp/u_near"][i])
+        st = model.make_batch(to_dev(x), to_dev(oh), to_dev(dims))
+        D = model.net(st, to_dev(ts), forward_rate=model.forward_rate, nearest_atom=None, sample_nearest_atom=True,
+                      u_nearest=to_dev(z["smp/u_near"][i]))[0]
+        close(D, want.d_xt, 1e-4)
+
+
+def test_sampler_update_kernel_matches_oracle():
+    """the fused HBM-bound update alone, same inputs on both sides: dims bit-exact, state to fp32 summation-order noise"""
+    g = np.random.default_rng(5)
+    for (B, N, S) in ((7, 16, 8), (64, 128, 8), (5, 30, 4)):
+        F = 3 + S
+        dims = g.integers(1, N + 1, B).astype(np.int32)
+        dims[0], dims[1] = 1, N
+        m = (np.arange(N)[None] < dims[:, None])[..., None]
+        x = (g.standard_normal((B, N, 3)) * m).astype(np.float32)
+        oh = (g.standard_normal((B, N, S)) * m).astype(np.float32)
+        v, lg = g.standard_normal((B, N, 3)).astype(np.float32), g.standard_normal((B, N, S)).astype(np.float32)
+        rate = (g.random(B) * 20).astype(np.float32)
+        nm, ns = g.standard_normal((B, F)).astype(np.float32) * 3, g.standard_normal((B, F)).astype(np.float32) * 12
+        z_diff, u_jump, z_new = (g.standard_normal((B, N * F)).astype(np.float32), g.random(B).astype(np.float32),
+                                 g.standard_normal((B, F)).astype(np.float32))
+        x[2, 0, 0] = np.nan
+        for c_noise in (0.3, 0.0):
+            sc = (1.004, 0.009, c_noise, 1.7, 0.05)
+            wx, wo, wd = ol.trans_sampler_update(x, oh, dims, v, lg, rate, nm, ns, *sc, z_diff, u_jump, z_new)
+            tx, to, td = to_dev(x), to_dev(oh), to_dev(dims)
+            _native.trans_sampler_update(tx, to, td, to_dev(v), to_dev(lg), to_dev(rate), to_dev(nm), to_dev(ns), *sc,
+                                         z_diff=to_dev(z_diff), u_jump=to_dev(u_jump), z_new=to_dev(z_new))
+            assert np.array_equal(td.cpu().numpy(), wd) and (wd > dims).any()
+            np.testing.assert_allclose(tx.cpu().numpy(), wx, rtol=1e-5, atol=2e-6)
+            np.testing.assert_allclose(to.cpu().numpy(), wo, rtol=1e-5, atol=2e-6)
+
+
+def test_sampler_steps_against_reference_trajectory(fixture):
+    """every recorded step of the reference run: one native evaluation + update from the reference's state"""
+    z, cfg, model, packed = fixture
+    m = model.net.model
+    dev = torch.device(DEV)
+    sched = jump_schedule(float(z["smp/dt"]), model.noise_schedule)
+    fr = model.forward_rate.as_c()
+    checked = 0
+    for i in range(sched.n_steps):
+        x, oh, dims = to_dev(z["smp/x_traj"][i]), to_dev(z["smp/oh_traj"][i]), to_dev(z["smp/dims_traj"][i])
+        one = SimpleNamespace(n_steps=1, ts=sched.ts[i:i + 1], c_decay=sched.c_decay[i:i + 1], c_score=sched.c_score[i:i + 1],
+                              c_noise=sched.c_noise[i:i + 1], inv_std=sched.inv_std[i:i + 1], jump_dt=sched.jump_dt)
+        noise = SimpleNamespace(z_diff=to_dev(z["smp/z_diff"][i:i + 1]), u_near=to_dev(z["smp/u_near"][i:i + 1]),
+                                u_jump=to_dev(z["smp/u_jump"][i:i + 1]), z_new=to_dev(z["smp/z_new"][i:i + 1]))
+        _native.trans_sample(m.native_trunk(dev), m.native_heads(dev), x, oh, dims, one, fr, noise=noise, precision="bf16")
+        last = i + 1 == sched.n_steps
+        rx, ro, rd = ((z["smp/x_final"], z["smp/oh_final"], z["smp/dims_final"]) if last else
+                      (z["smp/x_traj"][i + 1], z["smp/oh_traj"][i + 1], z["smp/dims_traj"][i + 1]))
+        # a birth decision is u < rate*dt: skip jets whose draw lies within the rate tolerance of the threshold
+        thr = z["smp/rate_traj"][i] * sched.jump_dt
+        safe = np.abs(z["smp/u_jump"][i] - thr) > 0.06 * thr
+        assert np.array_equal(dims.cpu().numpy()[safe], rd[safe]), f"step {i}"
+        # jets whose nearest particle (hence the new particle) could differ are those that gave birth; the others must
+        # follow the reference closely
+        quiet = safe & (rd == z["smp/dims_traj"][i])
+        if not quiet.any():
+            continue
+        scale = max(1.0, np.abs(rx).max(), np.abs(ro).max())
+        assert np.abs(x.cpu().numpy()[quiet] - rx[quiet]).max() <= 0.02 * scale, f"step {i}"
+        assert np.abs(oh.cpu().numpy()[quiet] - ro[quiet]).max() <= 0.02 * scale, f"step {i}"
+        checked += int(quiet.sum())
+    assert checked >= sched.n_steps * 2
+
+
+def test_jump_sampler_end_to_end_properties():
+    """JumpSampler.sample through the public API with in-kernel Philox draws at the transepic shape (N = 128):
+    deterministic, multiplicities grow from 1, state finite, dead slots zero, continuous features centred."""
+    cfg = TransdimensionalEpicConfig()
+    cfg.sampler_kwargs.dt = 0.02
+    torch.manual_seed(0)
+    model = TransdimensionalJumpDiffusion(cfg).to(DEV)
+    N, S = cfg.data.max_num_particles, cfg.data.vocab_size_features
+    B = 300
+    sk = {k: v for k, v in vars(cfg.sampler_kwargs).items() if k not in ("class_name", "do_jump_back", "jump_back_start_time")}
+    sampler = JumpSampler(structure=model.structure, **sk)
+    sampler.seed = 9
+    in_st = model.make_batch(torch.zeros(B, N, 3, device=DEV), torch.zeros(B, N, S, device=DEV), torch.full((B,), N, device=DEV))
+    a = sampler.sample(model.net, in_st, model.jump_diffusion_loss, jet_offset=0)
+    b = sampler.sample(model.net, in_st, model.jump_diffusion_loss, jet_offset=0)
+    assert torch.equal(a.tuple_batch[0], b.tuple_batch[0]) and torch.equal(a.get_dims(), b.get_dims())
+    dims = a.get_dims()
+    x, oh = a.tuple_batch
+    assert x.is_cuda and dims.dtype == torch.int64 and dims.min() >= 1 and dims.max() <= N and dims.float().mean() > 1.5
+    assert torch.isfinite(x).all() and torch.isfinite(oh).all()
+    dead = torch.arange(N, device=DEV)[None] >= dims[:, None]
+    assert (x[dead] == 0).all() and (oh[dead] == 0).all()
+    com = x.sum(1) / dims[:, None]
+    assert com.abs().max() <= 1e-3 * max(1.0, float(x.abs().max()))
+
+
+def test_trans_errors_are_loud(fixture):
+    z, cfg, model, packed = fixture
+    m = model.net.model
+    dev = torch.device(DEV)
+    st = model.make_batch(torch.from_numpy(z["fwd/x"]), torch.from_numpy(z["fwd/onehot"]), torch.from_numpy(z["fwd/dims"]))
+    with pytest.raises(_native.MmbError):
+        model.net(st, torch.from_numpy(z["fwd/ts"]), forward_rate=model.forward_rate, nearest_atom=torch.zeros(6).long())   # host tensors
+    with pytest.raises(_native.MmbError):
+        _native.TransHeads(m.trans_dims(), torch.zeros(10), dev)
