@@ -260,9 +260,9 @@ __global__ void __launch_bounds__(128) trans_auto_kernel(const float* __restrict
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);   // (0, 1]
     const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
-    const float r = sqrtf(-2.0f * logf(u1));
+    const float r = sqrtf(-2.0f * __logf(u1));
     float s, c;
-    sincosf(6.283185307179586f * u2, &s, &c);
+    __sincosf(6.283185307179586f * u2, &s, &c);
     n0 = r * c;
     n1 = r * s;
 }
@@ -279,11 +279,10 @@ __device__ __forceinline__ float nan_to_num(float a) {
 }
 __device__ __forceinline__ float softplus(float a) { return a > 20.0f ? a : log1pf(expf(a)); }
 
-// block-wide sum of three values (128 threads), result broadcast
+// block-wide sum of three values (128 threads), result broadcast; one barrier, its own scratch per call site
 __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (*s_red)[4]) {
     a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
     const int w = threadIdx.x >> 5;
-    __syncthreads();   // previous use of s_red is over
     if ((threadIdx.x & 31) == 0) { s_red[0][w] = a; s_red[1][w] = b; s_red[2][w] = c; }
     __syncthreads();
     a = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
@@ -291,7 +290,9 @@ __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (
     c = (s_red[2][0] + s_red[2][1]) + (s_red[2][2] + s_red[2][3]);
 }
 
-// one block (128 threads) per jet, thread n = particle slot n
+// One block (128 threads) per jet, thread n = particle slot n.  Dead slots (n >= dims) hold zeros — the sampler's
+// invariant, asserted by the reference in adjust_st_batch (jets_dataloader.py:451-452) — and stay zero under the update, so
+// they are neither read nor written: the pass moves 133 B per LIVE particle-step.
 template <int S>
 __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __restrict__ x, float* __restrict__ onehot, int32_t* __restrict__ dims,
                                                                    const float* __restrict__ v, const float* __restrict__ logits,
@@ -301,21 +302,18 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
                                                                    const float* __restrict__ z_diff, const float* __restrict__ u_jump,
                                                                    const float* __restrict__ z_new, uint64_t seed, uint64_t jet_offset,
                                                                    int step, int N) {
-    __shared__ float s_red[3][4];
+    __shared__ float s_red[3][3][4];
     constexpr int F = 3 + S;
     const int b = blockIdx.x, n = threadIdx.x;
     const int dim = dims[b];
-    const bool in = n < N, live = n < dim;
+    const bool live = n < dim;
     const size_t pi = (size_t)b * N + n;
-    float xs[3] = {0, 0, 0}, oh[S], z[12];
+    float xs[3] = {0, 0, 0}, oh[S], z[12], vs[3] = {0, 0, 0}, lg[S];
 #pragma unroll
     for (int i = 0; i < 12; ++i) z[i] = 0.0f;
 #pragma unroll
-    for (int s = 0; s < S; ++s) oh[s] = 0.0f;
-    float vs[3] = {0, 0, 0}, lg[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) lg[s] = 0.0f;
-    if (in) {
+    for (int s = 0; s < S; ++s) { oh[s] = 0.0f; lg[s] = 0.0f; }
+    if (live) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) { xs[c] = x[pi * 3 + c]; vs[c] = __ldg(v + pi * 3 + c); }
         if constexpr (S % 4 == 0) {
@@ -330,75 +328,73 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
 #pragma unroll
             for (int s = 0; s < S; ++s) { oh[s] = onehot[pi * S + s]; lg[s] = __ldg(logits + pi * S + s); }
         }
-    }
-    if (live && c_noise != 0.0f) {
-        if (z_diff) {
-            const float* zb = z_diff + (size_t)b * N * F;
+        if (c_noise != 0.0f) {
+            if (z_diff) {
+                const float* zb = z_diff + (size_t)b * N * F;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) z[c] = __ldg(zb + n * 3 + c);
+                for (int c = 0; c < 3; ++c) z[c] = __ldg(zb + n * 3 + c);
 #pragma unroll
-            for (int s = 0; s < S; ++s) z[3 + s] = __ldg(zb + (size_t)N * 3 + n * S + s);
-        } else {
-            philox_normals12(seed, jet_offset + (uint64_t)b, 2, step, n, z);
+                for (int s = 0; s < S; ++s) z[3 + s] = __ldg(zb + (size_t)N * 3 + n * S + s);
+            } else {
+                philox_normals12(seed, jet_offset + (uint64_t)b, 2, step, n, z);
+            }
         }
     }
+    // birth decision and the new particle's values (sampler.py:238-255) — independent of the diffusion step
+    const float uj = u_jump ? __ldg(u_jump + b) : u01(philox_block(seed, jet_offset + (uint64_t)b, 5, step, 0).y);
+    const bool born = (uj < __ldg(rate + b) * jump_dt) && dim < N;
+    const int new_dim = born ? dim + 1 : dim;
     // noise: delete_dims + centre-of-mass removal of its continuous part (sampler.py:224-229)
     {
         float a0 = z[0], a1 = z[1], a2 = z[2];
-        block_sum3(a0, a1, a2, s_red);
+        block_sum3(a0, a1, a2, s_red[0]);
         const float inv = 1.0f / (float)dim;
         if (live) { z[0] -= a0 * inv; z[1] -= a1 * inv; z[2] -= a2 * inv; }
     }
-    // Euler-Maruyama on the live slots (sampler.py:221-231); dead slots only decay (they hold zeros)
-    const float m = live ? 1.0f : 0.0f;
+    // Euler-Maruyama on the live slots (sampler.py:221-231)
+    if (live) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float a = c_decay * xs[c] + m * (c_score * -(inv_std * vs[c]));
-        if (c_noise != 0.0f) a = a + m * (c_noise * z[c]);
-        xs[c] = nan_to_num(a);
-    }
+        for (int c = 0; c < 3; ++c) {
+            float a = c_decay * xs[c] + (c_score * -(inv_std * vs[c]));
+            if (c_noise != 0.0f) a = a + (c_noise * z[c]);
+            xs[c] = nan_to_num(a);
+        }
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-        float a = c_decay * oh[s] + m * (c_score * -(inv_std * lg[s]));
-        if (c_noise != 0.0f) a = a + m * (c_noise * z[3 + s]);
-        oh[s] = nan_to_num(a);
+        for (int s = 0; s < S; ++s) {
+            float a = c_decay * oh[s] + (c_score * -(inv_std * lg[s]));
+            if (c_noise != 0.0f) a = a + (c_noise * z[3 + s]);
+            oh[s] = nan_to_num(a);
+        }
     }
     // adjust_st_batch: remove the mean of the continuous features over the live particles
     {
         float a0 = xs[0], a1 = xs[1], a2 = xs[2];
-        block_sum3(a0, a1, a2, s_red);
+        block_sum3(a0, a1, a2, s_red[1]);
         const float inv = 1.0f / (float)dim;
         if (live) { xs[0] -= a0 * inv; xs[1] -= a1 * inv; xs[2] -= a2 * inv; }
     }
-    // birth (sampler.py:238-255): the new particle takes slot `dim`
-    const float uj = u_jump ? __ldg(u_jump + b) : u01(philox_block(seed, jet_offset + (uint64_t)b, 5, step, 0).y);
-    const bool born = (uj < __ldg(rate + b) * jump_dt) && dim < N;
-    int new_dim = dim;
-    if (born) {
-        new_dim = dim + 1;
-        if (n == dim) {
-            float zn[12];
-            if (z_new) {
+    if (born && n == dim) {   // the new particle takes slot `dim`
+        float zn[12];
+        if (z_new) {
 #pragma unroll
-                for (int i = 0; i < F; ++i) zn[i] = __ldg(z_new + (size_t)b * F + i);
-            } else {
-                philox_normals12(seed, jet_offset + (uint64_t)b, 6, step, 0, zn);
-            }
-            const float* nm = new_mean + (size_t)b * F;
-            const float* ns = new_std + (size_t)b * F;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) xs[c] = nan_to_num(__ldg(nm + c) + zn[c] * softplus(__ldg(ns + c)));
-#pragma unroll
-            for (int s = 0; s < S; ++s) oh[s] = nan_to_num(__ldg(nm + 3 + s) + zn[3 + s] * softplus(__ldg(ns + 3 + s)));
+            for (int i = 0; i < F; ++i) zn[i] = __ldg(z_new + (size_t)b * F + i);
+        } else {
+            philox_normals12(seed, jet_offset + (uint64_t)b, 6, step, 0, zn);
         }
+        const float* nm = new_mean + (size_t)b * F;
+        const float* ns = new_std + (size_t)b * F;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xs[c] = nan_to_num(__ldg(nm + c) + zn[c] * softplus(__ldg(ns + c)));
+#pragma unroll
+        for (int s = 0; s < S; ++s) oh[s] = nan_to_num(__ldg(nm + 3 + s) + zn[3 + s] * softplus(__ldg(ns + 3 + s)));
     }
     {   // second adjust_st_batch with the new multiplicity (it runs whether or not a particle was born)
         float a0 = xs[0], a1 = xs[1], a2 = xs[2];
-        block_sum3(a0, a1, a2, s_red);
+        block_sum3(a0, a1, a2, s_red[2]);
         const float inv = 1.0f / (float)new_dim;
         if (n < new_dim) { xs[0] -= a0 * inv; xs[1] -= a1 * inv; xs[2] -= a2 * inv; }
     }
-    if (in) {
+    if (n < new_dim) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) x[pi * 3 + c] = xs[c];
         if constexpr (S % 4 == 0) {
