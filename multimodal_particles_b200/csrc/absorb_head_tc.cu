@@ -151,21 +151,75 @@ constexpr int kSmemW = 2 * kSlot;                         // weight ring
 constexpr int kOffA = kSmemW, kOffQ = kOffA + 32768, kOffK = kOffQ + 32768, kOffV = kOffK + 32768;
 constexpr int kOffOnes = kOffV + 32768, kOffTab = kOffOnes + 4096;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 
+// packed fp32 pair arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): two IEEE fp32 operations per issue slot
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ float tanh_fast(float a) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(a));
+    return t;
+}
+__device__ __forceinline__ float ex2_fast(float a) {
+    float t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a));
+    return t;
+}
+
+// Sum `vals[0..CNT)` over the 32 lanes of a warp by recursive halving: each stage exchanges half of the values a lane still
+// holds (CNT-1 shuffles in total instead of 5*CNT).  On return lane l holds, in vals[0], the warp total of the value whose index
+// has bit log2(CNT/2) = lane bit 4, ..., i.e. idx = sum_k ((l >> (4-k)) & 1) * (CNT >> (k+1)); CNT <= 32, a power of two.
+template <int CNT>
+__device__ __forceinline__ void warp_halving_sum(float (&vals)[CNT], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int cnt = CNT; cnt > 1; cnt >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt / 2; ++i) {
+            const float keep = upper ? vals[cnt / 2 + i] : vals[i];
+            const float send = upper ? vals[i] : vals[cnt / 2 + i];
+            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    for (; off >= 1; off >>= 1) vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], off);
+}
+template <int CNT>
+__device__ __forceinline__ int warp_halving_index(int lane) {
+    int idx = 0, off = 16;
+#pragma unroll
+    for (int cnt = CNT; cnt > 1; cnt >>= 1, off >>= 1) idx += (lane & off) ? cnt / 2 : 0;
+    return idx;
+}
+
+// One CTA of 16 warps owns one jet at a time.  Thread (r, cq): particle r = TMEM lane r (warp & 3 selects the lane quarter the
+// warp may touch), channel quarter cq = warp >> 2 -> 32 consecutive accumulator columns = one tcgen05.ld per pass.
 __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t s_tmem_slot;
-    __shared__ __align__(8) uint64_t s_bars[3];  // full[0], full[1], mma
-    __shared__ float s_stat[256];                // per channel: scale = rstd*gamma [128], shift = beta - mean*scale (+bias) [128]
-    __shared__ float s_part[4][64];              // GroupNorm partial column sums (4 row quarters)
-    __shared__ float s_dot[128];                 // rate-vector partial of the upper-half threads
-    __shared__ float s_mean[128];                // mean of the residual stream over the N slots (per-jet head)
-    const int tid = threadIdx.x, r = tid & 127, half = tid >> 7, warp = tid >> 5;
+    __shared__ __align__(8) uint64_t s_bars[3];             // full[0], full[1], mma
+    __shared__ __align__(16) float s_stat[256];             // per channel: scale [128], shift [128] of the running GroupNorm
+    __shared__ __align__(16) float s_part[16][32];          // per-warp partial sums (GroupNorm statistics / column sums)
+    __shared__ __align__(16) float s_bias2[kMaxBlocks][kC]; // conv1 bias + this jet's time term, per block
+    __shared__ float s_rowx[4][128];                        // softmax row max, then row sum, per (channel quarter, row)
+    __shared__ float s_dot[4][128];                         // per-particle output partials
+    __shared__ float s_mean[128];                           // mean of the residual stream over the N slots (per-jet head)
+    const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7, warp = tid >> 5, lane = tid & 31;
     const int nblk = p.n_blocks, n_seq = 1 + 6 * nblk;
     uint8_t *sA = smem + kOffA, *sQ = smem + kOffQ, *sK = smem + kOffK, *sV = smem + kOffV, *sOnes = smem + kOffOnes;
     float* sTab = reinterpret_cast<float*>(smem + kOffTab);
-    float* sRed = reinterpret_cast<float*>(sK);   // [128][65] floats, aliases K/V tiles (dead during GroupNorm)
     uint8_t* sA0 = sV;                            // [128 x 32] proj_in operand, aliases V (dead at jet start)
 
     for (int i = tid; i < HeadTable::floats(nblk); i += kThreads) sTab[i] = __ldg(p.table + i);
@@ -179,7 +233,8 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_slot;
-    const uint32_t lane_off = ((uint32_t)((warp & 3) * 32) << 16) + half * 64;  // this thread's lane and its 64-column half
+    const uint32_t lane_off = ((uint32_t)((warp & 3) * 32) << 16);   // this warp's TMEM lane quarter
+    const int col0 = cq * 32;                                        // this thread's 32 accumulator columns
     const uint32_t dX = tmem, dACC = tmem + 128, dS0 = tmem + 256, dS1 = tmem + 384;
 
     const int my_jets = p.B > (int)blockIdx.x ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -219,78 +274,71 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         }
     };
 
-    // GroupNorm(32 groups of 4 channels) over the N live rows of a TMEM tile (+ per-channel bias) -> bf16 A tile
-    auto group_norm_to_A = [&](uint32_t d_src, const float* bias /*nullable, smem*/, const float* bias2 /*nullable, global*/,
-                               const float* gamma, const float* beta, bool swish, bool valid) {
+    // GroupNorm(32 groups of 4 channels) over the N live rows of a TMEM tile (+ per-channel bias) -> bf16 A tile.
+    // One TMEM read: the 32 values stay in registers across the statistics exchange.
+    auto group_norm_to_A = [&](uint32_t d_src, const float* bias /*nullable, smem*/, const float* gamma, const float* beta,
+                               bool swish, bool valid) {
         float v[32];
-#pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
-            const int c0 = half * 64 + c2 * 32;
-            tmem_ld32(d_src + lane_off + c2 * 32, v);
+        tmem_ld32(d_src + lane_off + col0, v);
+        if (bias) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                float s = 0.0f, q = 0.0f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float a = v[4 * g + j];
-                    if (bias) a += bias[c0 + 4 * g + j];
-                    if (bias2) a += __ldg(bias2 + c0 + 4 * g + j);
-                    s += a; q = fmaf(a, a, q);
-                }
-                sRed[r * 65 + (c0 >> 2) + g] = valid ? s : 0.0f;
-                sRed[r * 65 + 32 + (c0 >> 2) + g] = valid ? q : 0.0f;
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + j);
+                fadd2(v[j], v[j + 1], v[j], v[j + 1], b4.x, b4.y);
+                fadd2(v[j + 2], v[j + 3], v[j + 2], v[j + 3], b4.z, b4.w);
             }
         }
-        __syncthreads();
-        {   // 256 threads: column (tid & 63) of the [128][64] partials, rows of quarter (tid >> 6)
-            const int col = tid & 63, qt = tid >> 6;
-            float acc = 0.0f;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) acc += sRed[(qt * 32 + i) * 65 + col];
-            s_part[qt][col] = acc;
+        float st[16];   // 8 group sums, 8 group sums of squares
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            float s0, s1, q0, q1;
+            fadd2(s0, s1, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            fmul2(q0, q1, v[4 * g], v[4 * g + 1], v[4 * g], v[4 * g + 1]);
+            ffma2(q0, q1, v[4 * g + 2], v[4 * g + 3], v[4 * g + 2], v[4 * g + 3], q0, q1);
+            st[g] = valid ? s0 + s1 : 0.0f;
+            st[8 + g] = valid ? q0 + q1 : 0.0f;
         }
+        warp_halving_sum<16>(st, lane);
+        if ((lane & 1) == 0) s_part[warp][warp_halving_index<16>(lane)] = st[0];
         __syncthreads();
         if (tid < 128) {  // one thread per channel: y = x*scale + shift with the statistics of its group folded in
-            const int g = tid >> 2;
-            const float s = (s_part[0][g] + s_part[1][g]) + (s_part[2][g] + s_part[3][g]);
-            const float q = (s_part[0][32 + g] + s_part[1][32 + g]) + (s_part[2][32 + g] + s_part[3][32 + g]);
+            const int g = tid >> 2, w0 = (g >> 3) * 4, gi = g & 7;   // group g lives in the warps of channel quarter g >> 3
+            const float s = (s_part[w0][gi] + s_part[w0 + 1][gi]) + (s_part[w0 + 2][gi] + s_part[w0 + 3][gi]);
+            const float q = (s_part[w0][8 + gi] + s_part[w0 + 1][8 + gi]) + (s_part[w0 + 2][8 + gi] + s_part[w0 + 3][8 + gi]);
             const float inv = 1.0f / (4.0f * (float)p.N);
             const float mean = s * inv;
             const float var = fmaxf(q * inv - mean * mean, 0.0f);
-            const float scale = rsqrtf(var + 1e-6f) * gamma[tid];
-            float pre = 0.0f;
-            if (bias) pre += bias[tid];
-            if (bias2) pre += __ldg(bias2 + tid);
+            const float h = swish ? 0.5f : 1.0f;   // swish(a) = a/2 * tanh(a/2) + a/2: the halving rides on the affine
+            const float scale = rsqrtf(var + 1e-6f) * gamma[tid] * h;
             s_stat[tid] = scale;
-            s_stat[128 + tid] = fmaf(pre - mean, scale, beta[tid]);
+            s_stat[128 + tid] = fmaf(-mean, scale, beta[tid] * h);
         }
         __syncthreads();
-#pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
-            const int c0 = half * 64 + c2 * 32;
-            tmem_ld32(d_src + lane_off + c2 * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                const float a = fmaf(v[j], s_stat[c], s_stat[128 + c]);
-                v[j] = swish ? swish_fast(a) : a;
-            }
-            store_row32(sA, r, half * 2 + c2, v);
+        for (int j = 0; j < 32; j += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_stat + col0 + j);
+            const float4 sh = *reinterpret_cast<const float4*>(s_stat + 128 + col0 + j);
+            ffma2(v[j], v[j + 1], v[j], v[j + 1], sc.x, sc.y, sh.x, sh.y);
+            ffma2(v[j + 2], v[j + 3], v[j + 2], v[j + 3], sc.z, sc.w, sh.z, sh.w);
         }
+        if (swish) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const float t0 = tanh_fast(v[j]), t1 = tanh_fast(v[j + 1]);
+                ffma2(v[j], v[j + 1], v[j], v[j + 1], t0, t1, v[j], v[j + 1]);
+            }
+        }
+        store_row32(sA, r, cq, v);
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
     };
-    // ACC (+ bias) -> bf16 tile (Q, K or V)
-    auto acc_to_tile = [&](uint8_t* tile, const float* bias) {
+    // ACC -> bf16 tile (Q, K or V); their biases are handled algebraically (Q: extra K-step; K: softmax-invariant, dropped;
+    // V: folded into the proj_out bias because softmax rows sum to one)
+    auto acc_to_tile = [&](uint8_t* tile) {
         float v[32];
-#pragma unroll 1
-        for (int c2 = 0; c2 < 2; ++c2) {
-            tmem_ld32(dACC + lane_off + c2 * 32, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias[half * 64 + c2 * 32 + j];
-            store_row32(tile, r, half * 2 + c2, v);
-        }
+        tmem_ld32(dACC + lane_off + col0, v);
+        store_row32(tile, r, cq, v);
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
@@ -302,11 +350,11 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         // ---- proj_in: mode 0 [hidden, one_hot(mask)] (absorbing_flows.py:113-118); mode 1 [hidden, onehot]
         //      (transdimensional_model.py:295-303); mode 2 mask * [hidden, onehot, distance to the nearest particle,
         //      its one-hot flag pair] (transdimensional_model.py:341-367)
-        {
+        if (cq == 0) {
             float row[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) row[i] = 0.0f;
-            if (valid && half == 0) {
+            if (valid) {
                 const int H = p.H;
                 const int m = p.mask[pidx] ? 1 : 0;
                 for (int i = 0; i < H; ++i) row[i] = p.hidden[pidx * H + i];
@@ -330,11 +378,14 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                 }
             }
             uint8_t* q = sA0 + (r >> 3) * 512 + (r & 7) * 16;
-            if (half == 0)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
                 *reinterpret_cast<uint4*>(q + c * 128) = make_uint4(pack_bf16(row[8 * c], row[8 * c + 1]), pack_bf16(row[8 * c + 2], row[8 * c + 3]),
                                                                     pack_bf16(row[8 * c + 4], row[8 * c + 5]), pack_bf16(row[8 * c + 6], row[8 * c + 7]));
+        } else {   // conv1 bias + this jet's time term of every block
+            const float* tb = p.tbias + (size_t)jet * p.tbias_stride;
+            for (int i = tid - 128; i < nblk * kC; i += kThreads - 128)
+                s_bias2[i >> 7][i & 127] = sTab[(i >> 7) * HeadTable::kPerBlock + 2 * kC + (i & 127)] + __ldg(tb + i);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -342,27 +393,26 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         if (tid == 0) gemm_w(dX, smem_u32(sA0), 512, 2, false, true);
         mma_done(true);
 
-        const float* tb = p.tbias + (size_t)jet * p.tbias_stride;
         for (int blk = 0; blk < nblk; ++blk) {
             const float* T = sTab + blk * HeadTable::kPerBlock;
             // ---- ResnetBlock (gsdm.py:54-66)
-            group_norm_to_A(dX, nullptr, nullptr, T + 0 * kC, T + 1 * kC, true, valid);
+            group_norm_to_A(dX, nullptr, T + 0 * kC, T + 1 * kC, true, valid);
             if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // conv1
             mma_done(true);
-            group_norm_to_A(dACC, T + 2 * kC, tb + blk * kC, T + 3 * kC, T + 4 * kC, true, valid);
+            group_norm_to_A(dACC, s_bias2[blk], T + 3 * kC, T + 4 * kC, true, valid);
             if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true);               // X += conv2(.) + b2
             mma_done(true);
             // ---- AttnBlock (gsdm.py:142-168)
-            group_norm_to_A(dX, nullptr, nullptr, T + 5 * kC, T + 6 * kC, false, valid);
-            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // q
+            group_norm_to_A(dX, nullptr, T + 5 * kC, T + 6 * kC, false, valid);
+            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, true);            // q (+ bq)
             mma_done(true);
-            acc_to_tile(sQ, T + 7 * kC);
+            acc_to_tile(sQ);
             if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // k
             mma_done(true);
-            acc_to_tile(sK, T + 8 * kC);
+            acc_to_tile(sK);
             if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // v
             mma_done(true);
-            acc_to_tile(sV, T + 9 * kC);
+            acc_to_tile(sV);
             if (tid == 0) {                                                  // S_h = Q_h K_h^T, K = 64
                 tc_fence_after();
                 for (int h = 0; h < kHeads; ++h)
@@ -372,33 +422,48 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                 umma_commit(bar_mma);
             }
             mma_done(false);
-            // softmax over the N keys of this thread's query row; P (unnormalised) -> A tile (head 0) / Q tile (head 1)
-            float rinv;
+            // softmax over the N keys: thread (r, cq) serves head cq >> 1, keys [64 (cq & 1), +64); the two halves of a row
+            // exchange max and sum through shared memory.  P (unnormalised, bf16) -> A tile (head 0) / Q tile (head 1)
             {
-                const int h = half;  // this thread's head: S_h row r, 128 keys
-                const uint32_t dS = (h ? dS1 : dS0) + ((uint32_t)((warp & 3) * 32) << 16);
+                const int h = cq >> 1, kh = cq & 1;
+                const uint32_t dS = (h ? dS1 : dS0) + lane_off + kh * 64;
+                const bool full = p.N == 128;
                 float v[32], mx = -3.0e38f;
 #pragma unroll 1
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    tmem_ld32(dS + c4 * 32, v);
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld32(dS + c * 32, v);
+                    if (full) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = (c4 * 32 + j < p.N) ? fmaxf(mx, v[j]) : mx;
-                }
-                float sum = 0.0f;
-                const float sc = 0.125f * 1.4426950408889634f;  // dh^-1/2 * log2(e)
-#pragma unroll 1
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    tmem_ld32(dS + c4 * 32, v);
+                        for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(v[j], v[j + 1]));
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float e = (c4 * 32 + j < p.N) ? exp2f((v[j] - mx) * sc) : 0.0f;
-                        // the sum runs over the bf16-rounded weights the PV GEMM will actually use
-                        v[j] = __bfloat162float(__float2bfloat16_rn(e));
-                        sum += v[j];
+                        for (int j = 0; j < 32; ++j) mx = (kh * 64 + c * 32 + j < p.N) ? fmaxf(mx, v[j]) : mx;
                     }
-                    store_row32(h ? sQ : sA, r, c4, v);
                 }
-                rinv = 1.0f / sum;
+                s_rowx[cq][r] = mx;
+                __syncthreads();
+                mx = fmaxf(mx, s_rowx[cq ^ 1][r]);
+                __syncthreads();   // s_rowx is reused for the sums
+                const float sc = 0.125f * 1.4426950408889634f;  // dh^-1/2 * log2(e)
+                const float off = -mx * sc;
+                float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    tmem_ld32(dS + c * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        ffma2(v[j], v[j + 1], v[j], v[j + 1], sc, sc, off, off);
+                        v[j] = ex2_fast(v[j]);
+                        v[j + 1] = ex2_fast(v[j + 1]);
+                        if (!full) {
+                            v[j] = (kh * 64 + c * 32 + j < p.N) ? v[j] : 0.0f;
+                            v[j + 1] = (kh * 64 + c * 32 + j + 1 < p.N) ? v[j + 1] : 0.0f;
+                        }
+                        fadd2(s0, s1, s0, s1, v[j], v[j + 1]);
+                    }
+                    store_row32(h ? sQ : sA, r, kh * 2 + c, v);
+                }
+                s_rowx[cq][r] = s0 + s1;
             }
             tc_fence_before();
             fence_proxy_async();
@@ -413,19 +478,17 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             }
             mma_done(false);
             {
-                float v[32];  // columns [64*half, 64*half+64) of O = head `half`: normalised by this thread's own row sum
-#pragma unroll 1
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    tmem_ld32(dACC + lane_off + c2 * 32, v);
+                float v[32];  // columns [32 cq, +32) of O belong to head cq >> 1: normalised by that head's row sum
+                const float rinv = 1.0f / (s_rowx[cq][r] + s_rowx[cq ^ 1][r]);
+                tmem_ld32(dACC + lane_off + col0, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] *= rinv;
-                    store_row32(sA, r, half * 2 + c2, v);
-                }
+                for (int j = 0; j < 32; j += 2) fmul2(v[j], v[j + 1], v[j], v[j + 1], rinv, rinv);
+                store_row32(sA, r, cq, v);
             }
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true);               // X += proj_out(.) + b
+            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true);               // X += proj_out(.) + (b_o + W_o b_v)
             mma_done(true);
         }
         // ---- per-particle output: one 128-vector against the residual stream (absorbing: post_rate_proj(pre_rate_proj(X))
@@ -433,44 +496,40 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         //      the mean of X over the N slots followed by a folded [n_jet x 128] Linear (transdimensional_model.py:309-311,403-405)
         {
             const float* w = sTab + HeadTable::rate_w(nblk);
-            float acc = half ? 0.0f : sTab[HeadTable::rate_c(nblk)], v[32];
-#pragma unroll 1
-            for (int c2 = 0; c2 < 2; ++c2) {
-                tmem_ld32(dX + lane_off + c2 * 32, v);
+            float v[32], a0 = 0.0f, a1 = 0.0f;
+            tmem_ld32(dX + lane_off + col0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc = fmaf(w[half * 64 + c2 * 32 + j], v[j], acc);
-                if (p.n_jet > 0) {   // column sums of this 64-column slice: rows -> sRed, 4 row quarters, then one thread per column
-                    if (c2) __syncthreads();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sRed[r * 65 + half * 32 + j] = valid ? v[j] : 0.0f;
-                    __syncthreads();
-                    {
-                        const int col = tid & 63, qt = tid >> 6;
-                        float a2 = 0.0f;
-#pragma unroll 8
-                        for (int i = 0; i < 32; ++i) a2 += sRed[(qt * 32 + i) * 65 + col];
-                        s_part[qt][col] = a2;
-                    }
-                    __syncthreads();
-                    if (tid < 64) {
-                        const int c = (tid >> 5) * 64 + c2 * 32 + (tid & 31);   // sRed column tid = (half, j)
-                        s_mean[c] = ((s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid])) * (1.0f / (float)p.N);
-                    }
-                }
+            for (int j = 0; j < 32; j += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(w + col0 + j);
+                ffma2(a0, a1, v[j], v[j + 1], w4.x, w4.y, a0, a1);
+                ffma2(a0, a1, v[j + 2], v[j + 3], w4.z, w4.w, a0, a1);
             }
-            if (half) s_dot[r] = acc;
+            s_dot[cq][r] = a0 + a1;
+            if (p.n_jet > 0) {   // column sums over the rows: halving reduction inside the warp, then the four lane quarters
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] : 0.0f;
+                warp_halving_sum<32>(v, lane);
+                s_part[warp][warp_halving_index<32>(lane)] = v[0];
+            }
             __syncthreads();
-            if (valid && !half) p.logit_out[pidx] = acc + s_dot[r];
-            if (p.n_jet > 0 && tid < p.n_jet) {
-                float a0 = __ldg(p.jet_b + tid), a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-#pragma unroll 4
-                for (int c = 0; c < kC; c += 4) {
-                    a0 = fmaf(__ldg(p.jet_wT + (size_t)c * p.n_jet + tid), s_mean[c], a0);
-                    a1 = fmaf(__ldg(p.jet_wT + (size_t)(c + 1) * p.n_jet + tid), s_mean[c + 1], a1);
-                    a2 = fmaf(__ldg(p.jet_wT + (size_t)(c + 2) * p.n_jet + tid), s_mean[c + 2], a2);
-                    a3 = fmaf(__ldg(p.jet_wT + (size_t)(c + 3) * p.n_jet + tid), s_mean[c + 3], a3);
+            if (cq == 0 && valid) p.logit_out[pidx] = sTab[HeadTable::rate_c(nblk)] + (s_dot[0][r] + s_dot[1][r]) + (s_dot[2][r] + s_dot[3][r]);
+            if (p.n_jet > 0) {
+                if (tid < 128) {
+                    const int w0 = (tid >> 5) * 4, ci = tid & 31;
+                    s_mean[tid] = ((s_part[w0][ci] + s_part[w0 + 1][ci]) + (s_part[w0 + 2][ci] + s_part[w0 + 3][ci])) * (1.0f / (float)p.N);
                 }
-                p.jet_out[(size_t)jet * p.n_jet + tid] = (a0 + a1) + (a2 + a3);
+                __syncthreads();
+                if (tid < p.n_jet) {
+                    float b0 = __ldg(p.jet_b + tid), b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+#pragma unroll 4
+                    for (int c = 0; c < kC; c += 4) {
+                        b0 = fmaf(__ldg(p.jet_wT + (size_t)c * p.n_jet + tid), s_mean[c], b0);
+                        b1 = fmaf(__ldg(p.jet_wT + (size_t)(c + 1) * p.n_jet + tid), s_mean[c + 1], b1);
+                        b2 = fmaf(__ldg(p.jet_wT + (size_t)(c + 2) * p.n_jet + tid), s_mean[c + 2], b2);
+                        b3 = fmaf(__ldg(p.jet_wT + (size_t)(c + 3) * p.n_jet + tid), s_mean[c + 3], b3);
+                    }
+                    p.jet_out[(size_t)jet * p.n_jet + tid] = (b0 + b1) + (b2 + b3);
+                }
             }
         }
         tc_fence_before();
@@ -529,8 +588,20 @@ int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* bloc
         const int s0 = 1 + 6 * blk;
         put_matrix(s0 + 0, c1, C);
         put_matrix(s0 + 1, c2, C); put_bias(s0 + 1, c2 + (size_t)C * C);
-        put_matrix(s0 + 2, wq, C); put_matrix(s0 + 3, wk, C); put_matrix(s0 + 4, wv, C);
-        put_matrix(s0 + 5, wo, C); put_bias(s0 + 5, wo + (size_t)C * C);
+        put_matrix(s0 + 2, wq, C); put_bias(s0 + 2, wq + (size_t)C * C);
+        put_matrix(s0 + 3, wk, C);          // k bias: a per-query constant in the logits, softmax-invariant
+        put_matrix(s0 + 4, wv, C);          // v bias: softmax rows sum to one -> O gains b_v, i.e. proj_out gains W_o b_v
+        put_matrix(s0 + 5, wo, C);
+        {
+            std::vector<float> bo(C);
+            const float* bv = wv + (size_t)C * C;
+            for (int o = 0; o < C; ++o) {
+                double acc = wo[(size_t)C * C + o];
+                for (int c = 0; c < C; ++c) acc += (double)wo[(size_t)o * C + c] * bv[c];
+                bo[o] = (float)acc;
+            }
+            put_bias(s0 + 5, bo.data());
+        }
         for (int c = 0; c < C; ++c) {
             T[0 * kC + c] = n1g[c]; T[1 * kC + c] = n1b[c]; T[2 * kC + c] = c1[(size_t)C * C + c];
             T[3 * kC + c] = n2g[c]; T[4 * kC + c] = n2b[c]; T[5 * kC + c] = ng[c]; T[6 * kC + c] = nb[c];
@@ -567,6 +638,11 @@ int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B,
     p.tbias = io.tbias; p.tbias_stride = io.tbias_stride; p.B = B; p.N = N; p.logit_out = io.dot_out;
     p.jet_wT = st->jet_wT; p.jet_b = st->jet_b; p.n_jet = io.jet_out ? st->n_jet : 0; p.jet_out = io.jet_out;
     const size_t bytes = kOffTab + (size_t)HeadTable::floats(st->n_blocks) * 4 + 1024;
+    cudaFuncAttributes attr;
+    if (int rc = cuda_ok(cudaFuncGetAttributes(&attr, absorb_head_tc_kernel), "head attributes")) return rc;
+    if (bytes + attr.sharedSizeBytes > 232448)
+        return fail(MMB_EUNSUPPORTED, "transformer stack with %d blocks needs %zu B of shared memory per CTA (limit 232448)", st->n_blocks,
+                    bytes + attr.sharedSizeBytes);
     if (int rc = cuda_ok(cudaFuncSetAttribute(absorb_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "head smem attribute"))
         return rc;
     const int grid = B < sm_count ? B : sm_count;

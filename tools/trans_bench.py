@@ -1,7 +1,7 @@
 """Throughput of the trans-dimensional path (BASELINE config 3: transepic, B=8192, N=128, bf16):
 one TransdimensionalEPiC evaluation (mmb_trans_forward) against the bf16 tensor roofline
 (144.5 MFLOP per jet-evaluation in the two transformer stacks + 0.83 in the trunk),
-the fused sampler update against the HBM roofline (133 B per particle-step with in-kernel Philox),
+the fused sampler update against the HBM roofline (133 B per live particle-step with in-kernel Philox),
 and a short JumpSampler run (dt = 0.02 -> 50 evaluations) as generated jets/s.  Prints one JSON line."""
 import json
 import os
@@ -59,7 +59,7 @@ rate = torch.rand(B, device=dev) * 5
 nm, ns = torch.randn(B, 3 + S, device=dev), torch.randn(B, 3 + S, device=dev)
 xs, ohs, ds = x.clone(), oh.clone(), dims32.clone()
 upd_ms = timed(lambda: _native.trans_sampler_update(xs, ohs, ds, v, lg, rate, nm, ns, 1.001, 0.004, 0.06, 1.2, 0.02, seed=3, step=1), 20)
-upd_bytes = 133 * B * N
+upd_bytes = 133 * int(dims.sum())   # dead slots are neither read nor written: 133 B per LIVE particle-step
 gbs = upd_bytes / (upd_ms * 1e-3) / 1e9
 
 # short sampler run
