@@ -38,32 +38,53 @@ namespace {
 constexpr int kC = 128;
 
 // ---- tokens: batch-axis softmax (structure.py:231-232) ----------------------------------------------------------------
-// One block per 32 columns of the flattened [N*S] axis; warp w owns the jets b = w (mod 8) in ascending order.
-__global__ void __launch_bounds__(256) trans_colstats_kernel(const float* __restrict__ onehot, int B, int NS, float* __restrict__ M,
-                                                             float* __restrict__ Z) {
+// Column statistics over the batch in a fixed order (the oracle's): the batch is cut into chunks of 128 jets; inside a chunk
+// eight partial sums over b mod 8 (ascending b) are combined by a balanced tree; chunk sums are added in ascending order.
+// Grid (column groups of 32, chunks); warp w of a block owns the jets b = w (mod 8) of its chunk.
+constexpr int kChunk = 128;
+__global__ void __launch_bounds__(256) trans_colmax_kernel(const float* __restrict__ onehot, int B, int NS, float* __restrict__ pmax) {
     __shared__ float s_red[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane;
-    const bool ok = c < NS;
+    const int c = blockIdx.x * 32 + lane, b0 = blockIdx.y * kChunk, b1 = min(B, b0 + kChunk);
     float mx = -INFINITY;
-    if (ok)
-        for (int b = w; b < B; b += 8) mx = fmaxf(mx, __ldg(onehot + (size_t)b * NS + c));
+    if (c < NS)
+        for (int b = b0 + w; b < b1; b += 8) mx = fmaxf(mx, __ldg(onehot + (size_t)b * NS + c));
     s_red[w][lane] = mx;
     __syncthreads();
-    mx = s_red[0][lane];
+    if (w == 0 && c < NS) {
 #pragma unroll
-    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i][lane]);
-    __syncthreads();
-    float part = 0.0f;
-    if (ok)
-        for (int b = w; b < B; b += 8) part = __fadd_rn(part, expf_exact_dn(__fadd_rn(__ldg(onehot + (size_t)b * NS + c), -mx)));
+        for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i][lane]);
+        pmax[(size_t)blockIdx.y * NS + c] = mx;
+    }
+}
+__global__ void __launch_bounds__(256) trans_colsum_kernel(const float* __restrict__ onehot, int B, int NS, const float* __restrict__ pmax,
+                                                           int n_chunks, float* __restrict__ psum) {
+    __shared__ float s_red[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane, b0 = blockIdx.y * kChunk, b1 = min(B, b0 + kChunk);
+    float mx = -INFINITY, part = 0.0f;
+    if (c < NS) {
+        for (int k = 0; k < n_chunks; ++k) mx = fmaxf(mx, __ldg(pmax + (size_t)k * NS + c));
+        for (int b = b0 + w; b < b1; b += 8) part = __fadd_rn(part, expf_exact_dn(__fadd_rn(__ldg(onehot + (size_t)b * NS + c), -mx)));
+    }
     s_red[w][lane] = part;
     __syncthreads();
-    if (w == 0 && ok) {
-        M[c] = mx;
-        Z[c] = __fadd_rn(__fadd_rn(__fadd_rn(s_red[0][lane], s_red[1][lane]), __fadd_rn(s_red[2][lane], s_red[3][lane])),
-                         __fadd_rn(__fadd_rn(s_red[4][lane], s_red[5][lane]), __fadd_rn(s_red[6][lane], s_red[7][lane])));
+    if (w == 0 && c < NS)
+        psum[(size_t)blockIdx.y * NS + c] =
+            __fadd_rn(__fadd_rn(__fadd_rn(s_red[0][lane], s_red[1][lane]), __fadd_rn(s_red[2][lane], s_red[3][lane])),
+                      __fadd_rn(__fadd_rn(s_red[4][lane], s_red[5][lane]), __fadd_rn(s_red[6][lane], s_red[7][lane])));
+}
+__global__ void trans_colcombine_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int n_chunks, int NS,
+                                        float* __restrict__ M, float* __restrict__ Z) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= NS) return;
+    float mx = -INFINITY, z = 0.0f;
+    for (int k = 0; k < n_chunks; ++k) {
+        mx = fmaxf(mx, __ldg(pmax + (size_t)k * NS + c));
+        z = __fadd_rn(z, __ldg(psum + (size_t)k * NS + c));
     }
+    M[c] = mx;
+    Z[c] = z;
 }
 
 __global__ void trans_tokens_kernel(const float* __restrict__ onehot, const float* __restrict__ M, const float* __restrict__ Z,
@@ -85,7 +106,7 @@ __global__ void trans_tokens_kernel(const float* __restrict__ onehot, const floa
 
 // ---- time terms (utils.py:183-198; gsdm.py:8-26,58; transdimensional_model.py:288-290) ---------------------------------
 // 128 threads = output channels; a block serves kTimeJets jets so every weight row is read once per block.
-constexpr int kTimeJets = 8;
+constexpr int kTimeJets = 32;
 __global__ void __launch_bounds__(kC) trans_time_kernel(const float* __restrict__ wT, int nblk, const float* __restrict__ ts, int B, int T,
                                                         float* __restrict__ temb_epic, float* __restrict__ tb1, float* __restrict__ tb2) {
     __shared__ float s_in[kTimeJets][kC];
@@ -188,10 +209,16 @@ __global__ void __launch_bounds__(128) trans_rate_kernel(const float* __restrict
             ratio = fmaxf((1.0f / I) * (float)((i + 1) - d), 0.0f);
         } else {   // x_t has one particle: ratio of Poisson probabilities with the truncated normaliser (noising.py:199-212)
             auto logp = [&](int k) { return (k == 0 ? 0.0f : (float)k * logI) - I - __ldg(logfact + k); };
-            float m2 = -INFINITY;
-            for (int j = 0; j < 2 * R; ++j) m2 = fmaxf(m2, logp(i + j));
+            // the Poisson pmf is log-concave with its mode at floor(I): the window maximum sits at the mode clamped into the
+            // window, and past the mode the terms only fall, so the sum stops once they drop below e^-25 of it
+            const int mode = min(max((int)I, i), i + 2 * R - 1);
+            const float m2 = logp(mode);
             float se = 0.0f;
-            for (int j = 0; j < 2 * R; ++j) se += expf(logp(i + j) - m2);
+            for (int j = 0; j < 2 * R; ++j) {
+                const float a = logp(i + j) - m2;
+                se += expf(a);
+                if (i + j > mode && a < -25.0f) break;
+            }
             const float dim1 = m2 + logf(se);
             const float dim2 = i == 0 ? -1000.0f : logp(i - 1);
             ratio = expf(dim2 - dim1);
@@ -418,7 +445,7 @@ inline size_t align64(size_t n) { return (n + 63) & ~(size_t)63; }
 
 // workspace carve-up shared by the forward and the sampler (in floats, every region 256-byte aligned)
 struct TransWs {
-    size_t k, mask, M, Z, temb, tb1, tb2, v, logits, hidden, near_logits, vec_w, x0_logits, post_auto, nearest, new_mean, new_std, rate,
+    size_t k, mask, M, Z, pmax, psum, temb, tb1, tb2, v, logits, hidden, near_logits, vec_w, x0_logits, post_auto, nearest, new_mean, new_std, rate,
         u_near, ts, total;
     TransWs(const MmbEpicDims& e, const MmbTransDims& d, int B, int N, int n_time) {
         const size_t P = (size_t)B * N, F = 3 + d.vocab_size;
@@ -426,6 +453,8 @@ struct TransWs {
         auto take = [&](size_t floats) { const size_t o = at; at += align64(floats); return o; };
         k = take((P + 3) / 4); mask = take((P + 3) / 4);
         M = take((size_t)N * d.vocab_size); Z = take((size_t)N * d.vocab_size);
+        const size_t chunks = ((size_t)B + kChunk - 1) / kChunk;
+        pmax = take(chunks * N * d.vocab_size); psum = take(chunks * N * d.vocab_size);
         temb = take((size_t)n_time * e.dim_time_emb);
         tb1 = take((size_t)n_time * d.n_blocks * kC); tb2 = take((size_t)n_time * d.n_blocks * kC);
         v = take(P * 3); logits = take(P * d.vocab_size); hidden = take(P * e.dim_hidden_local);
@@ -549,7 +578,13 @@ static int trans_eval(const EpicModel* m, const TransHeads* h, const float* x, c
     int32_t* nearest = reinterpret_cast<int32_t*>(ws + L.nearest);
     float* x0l = x0_logits_out ? x0_logits_out : ws + L.x0_logits;
     float* nl = near_logits_out ? near_logits_out : ws + L.near_logits;
-    trans_colstats_kernel<<<(N * S + 31) / 32, 256, 0, s>>>(onehot, B, N * S, ws + L.M, ws + L.Z);
+    {
+        const int NS = N * S, chunks = (B + kChunk - 1) / kChunk;
+        const dim3 grid((NS + 31) / 32, chunks);
+        trans_colmax_kernel<<<grid, 256, 0, s>>>(onehot, B, NS, ws + L.pmax);
+        trans_colsum_kernel<<<grid, 256, 0, s>>>(onehot, B, NS, ws + L.pmax, chunks, ws + L.psum);
+        trans_colcombine_kernel<<<(NS + 127) / 128, 128, 0, s>>>(ws + L.pmax, ws + L.psum, chunks, NS, ws + L.M, ws + L.Z);
+    }
     trans_tokens_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(onehot, ws + L.M, ws + L.Z, dims, B, N, S, k, mask);
     if (int rc = cuda_ok(cudaGetLastError(), "trans tokens launch")) return rc;
     int rc = mmb_epic_forward(reinterpret_cast<const MmbEpicModel*>(m), x, k, mask, temb, time_stride ? T : 0, B, N, ws + L.v, ws + L.logits,

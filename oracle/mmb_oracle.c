@@ -524,8 +524,8 @@ size_t mmbo_trans_floats(const MmbTransDims* d) {
 }
 
 /* tokens = argmax_s softmax_BATCH(onehot)[b,n,s]: F.softmax without dim on a 3-D tensor normalises over
- * dim 0 (structure.py:231-232).  Column sums in the order the kernel uses: 8 partial sums over b mod 8
- * (ascending b), then a balanced tree. */
+ * dim 0 (structure.py:231-232).  Column sums in the order the kernels use: chunks of 128 jets; inside a chunk 8
+ * partial sums over b mod 8 (ascending b) combined by a balanced tree; chunk sums added in ascending order. */
 void mmbo_trans_tokens(const float* onehot, int B, int N, int S, uint8_t* k) {
     const int NS = N * S;
     float* M = (float*)malloc(sizeof(float) * (size_t)NS);
@@ -533,10 +533,14 @@ void mmbo_trans_tokens(const float* onehot, int B, int N, int S, uint8_t* k) {
     for (int c = 0; c < NS; ++c) {
         float mx = -INFINITY;
         for (int b = 0; b < B; ++b) { float a = onehot[(size_t)b * NS + c]; mx = a > mx ? a : mx; }
-        float part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int b = 0; b < B; ++b) part[b & 7] = part[b & 7] + mmbo_expf_dn(onehot[(size_t)b * NS + c] - mx);
+        float z = 0.0f;
+        for (int b0 = 0; b0 < B; b0 += 128) {
+            float part[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int b = b0; b < B && b < b0 + 128; ++b) part[b & 7] = part[b & 7] + mmbo_expf_dn(onehot[(size_t)b * NS + c] - mx);
+            z = z + (((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7])));
+        }
         M[c] = mx;
-        Z[c] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+        Z[c] = z;
     }
     for (int b = 0; b < B; ++b)
         for (int n = 0; n < N; ++n) {

@@ -122,6 +122,47 @@ def test_sampler_update_kernel_matches_oracle():
             np.testing.assert_allclose(to.cpu().numpy(), wo, rtol=1e-5, atol=2e-6)
 
 
+def test_sampler_update_in_kernel_normals_are_standard():
+    """Philox + Box-Muller draws of the update kernel: with x = v = 0 and c_noise = 1 the output IS the centred noise."""
+    B, N, S = 512, 128, 8
+    dims = torch.full((B,), N, dtype=torch.int32, device=DEV)
+    x, oh = torch.zeros(B, N, 3, device=DEV), torch.zeros(B, N, S, device=DEV)
+    zero = lambda *s: torch.zeros(*s, device=DEV)
+    _native.trans_sampler_update(x, oh, dims, zero(B, N, 3), zero(B, N, S), zero(B), zero(B, 3 + S), zero(B, 3 + S), 0.0, 0.0, 1.0, 1.0,
+                                 0.02, seed=5, jet_offset=17, step=3)
+    z = oh.flatten()
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.05 and float(z.abs().max()) > 4.0
+    assert x.sum(1).abs().max() < 1e-4 and abs(float(x.std()) - (1 - 1 / N) ** 0.5) < 5e-3     # centred over the live particles
+    x2, oh2 = torch.zeros_like(x), torch.zeros_like(oh)
+    _native.trans_sampler_update(x2[:100], oh2[:100], dims[:100].clone(), zero(100, N, 3), zero(100, N, S), zero(100), zero(100, 3 + S),
+                                 zero(100, 3 + S), 0.0, 0.0, 1.0, 1.0, 0.02, seed=5, jet_offset=17 + 50, step=3)
+    assert torch.equal(oh2[:50], oh[50:100])       # keyed by the global jet index: shard-invariant draws
+
+
+def test_tokens_with_many_jets_follow_the_oracle():
+    """the chunked column statistics (B > 128) give the oracle's tokens: fp32 trunk output vs oracle on 300 jets"""
+    cfg = TransdimensionalEpicConfig()
+    cfg.data.max_num_particles = 16
+    torch.manual_seed(2)
+    model = TransdimensionalJumpDiffusion(cfg).to(DEV)
+    model.net.model.precision = "fp32"
+    packed = ol.trans_packed(model.cpu())
+    model.to(DEV)
+    g = np.random.default_rng(3)
+    B, N, S = 300, 16, 8
+    dims = g.integers(1, N + 1, B).astype(np.int32)
+    m = (np.arange(N)[None] < dims[:, None])[..., None]
+    x = (g.standard_normal((B, N, 3)) * m).astype(np.float32)
+    oh = (g.standard_normal((B, N, S)) * 40 * m).astype(np.float32)     # wide spread: deep in the underflow regime
+    ts = g.random(B).astype(np.float32) * 0.99 + 0.005
+    near = (g.random(B) * dims).astype(np.int32)
+    want = ol.trans_forward(packed, x, oh, dims, ts, model.forward_rate.as_c(), nearest=near)
+    D = model.net(model.make_batch(to_dev(x), to_dev(oh), to_dev(dims)), to_dev(ts), forward_rate=model.forward_rate,
+                  nearest_atom=to_dev(near))[0]
+    close(D, want.d_xt, 1e-4)
+
+
 def test_sampler_steps_against_reference_trajectory(fixture):
     """every recorded step of the reference run: one native evaluation + update from the reference's state"""
     z, cfg, model, packed = fixture
