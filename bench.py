@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 side measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -285,6 +286,12 @@ def main():
             v, dt_cpu, cores = cpu_port_jets_per_s(CPU_SAMPLE_JETS)   # ~10-20 s of CPU work
             cpu = {"value": v, "unit": "jets/s", "cores": cores, "kind": "port",
                    "sample": f"{CPU_SAMPLE_JETS} jets x 99 solver steps of the same workload ({dt_cpu:.1f} s), OpenMP over jets"}
+        other = None
+        if world == 1 and not args.no_secondary:
+            try:
+                other = secondary_configs(torch, _native, device, pk)
+            except Exception as exc:  # the headline line must not depend on the side measurements
+                other = {"error": f"{type(exc).__name__}: {exc}"}
         launches = K * (1 + (3 if world > 1 else 0))
         line = {"metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -294,10 +301,81 @@ def main():
                            "rng": "in-kernel Philox4x32-10", "parallelism": f"jets sharded over {world} GPU(s)"},
                 "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roofline, "roofline_update": roofline_update,
-                "cpu_baseline": cpu, "clocks": clocks.summary(), "wall_s_timed_region": t_wall}
+                "cpu_baseline": cpu, "clocks": clocks.summary(), "wall_s_timed_region": t_wall, "other_configs": other}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def secondary_configs(torch, _native, device, pk):
+    """BASELINE configs 3 and 4 on this GPU, reported next to the headline (rank 0, N=1): one C3 transepic evaluation
+    (B=8192, N=128; 145.3 MFLOP per jet-evaluation, SURVEY.md §8d) and one C4 absorbing-flow generation (B=4096, 99 steps;
+    72.0 MFLOP per jet-step in the rate head).  CUDA events on the launch stream, inputs resident."""
+    from multimodal_particles_b200.absorbing_flows import AbsorbingFlow
+    from multimodal_particles_b200.config_classes.absorbing_flows_config import AbsorbingConfig
+    from multimodal_particles_b200.config_classes.transdimensional_unconditional_config import TransdimensionalEpicConfig
+    from multimodal_particles_b200.databatch import jetclass_like_databatch
+    from multimodal_particles_b200.epic import as_u8
+    from multimodal_particles_b200.transdimensional import TransdimensionalJumpDiffusion
+
+    def timed(fn, reps, warm):
+        for _ in range(warm):
+            fn()
+        ms = []
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize()
+            ms.append(s.elapsed_time(e))
+        return sum(ms) / len(ms)
+
+    out = {}
+    # ---- C3
+    B, N, S = 8192, N_PART, 8
+    torch.manual_seed(0)
+    model = TransdimensionalJumpDiffusion(TransdimensionalEpicConfig()).to(device)
+    m = model.net.model
+    trunk, heads = m.native_trunk(device), m.native_heads(device)
+    g = torch.Generator().manual_seed(1234)
+    dims = torch.randint(1, N + 1, (B,), generator=g)
+    mask = (torch.arange(N)[None] < dims[:, None]).float().unsqueeze(-1)
+    x = torch.randn(B, N, 3, generator=g) * mask
+    x = x - (x.sum(1, keepdim=True) / dims.view(B, 1, 1)) * mask
+    oh, ts = torch.randn(B, N, S, generator=g) * mask, torch.rand(B, generator=g) * 0.999 + 1e-3
+    near = (torch.rand(B, generator=g) * dims).long()
+    x, oh, d32, ts, near = x.to(device), oh.to(device), dims.to(device, torch.int32), ts.to(device), near.to(device, torch.int32)
+    fr = model.forward_rate.as_c()
+    ms = timed(lambda: _native.trans_forward(trunk, heads, x, oh, d32, ts, near, None, fr, precision="bf16", want_auto=False), 3, 2)
+    tf = 145.33e6 * B / (ms * 1e-3) / 1e12
+    out["C3_transepic_evaluation"] = {"workload": "TransdimensionalEPiC.forward, B=8192, N=128, bf16 stacks", "ms": ms,
+                                      "jet_evals_per_s": B / (ms * 1e-3),
+                                      "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
+                                                   "frac": tf / pk["bf16"]}}
+    del model, trunk, heads
+    # ---- C4
+    B = 4096
+    cfg = AbsorbingConfig()
+    cfg.data.max_num_particles, cfg.bridge.num_timesteps = N_PART, N_TIMESTEPS
+    torch.manual_seed(0)
+    flow = AbsorbingFlow(cfg).to(device)
+    gen = flow.generator
+    b = jetclass_like_databatch(B, N_PART, generator=torch.Generator().manual_seed(1234))
+    table = flow.step_table()
+    tb = gen.time_bias(table.t)
+    trunk, head = gen.native_trunk(device), gen.native_head(device)
+    x0, k0, m0 = b.source_continuous.to(device).contiguous(), as_u8(b.source_discrete.to(device)), as_u8(b.source_mask.to(device))
+
+    def run():
+        _native.generate_absorbing(trunk, head, x0.clone(), k0.clone(), m0.clone(), table, tb, seed=1, jet_offset=0, precision="bf16")
+
+    ms = timed(run, 2, 1)
+    hid = torch.randn(B, N_PART, 16, device=device)
+    tb1 = tb[:1].to(device)
+    hms = timed(lambda: head.forward(hid, m0, tb1), 5, 2)
+    tf = 72.0e6 * B / (hms * 1e-3) / 1e12
+    out["C4_absorbing_generation"] = {"workload": "AbsorbingFlow generation, B=4096, N=128, 99 steps", "ms": ms, "jets_per_s": B / (ms * 1e-3),
+                                      "roofline_head": {"bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
+                                                        "frac": tf / pk["bf16"], "ms_per_launch": hms}}
+    return out
 
 
 def native_supports_bf16(native, _native_mod):
