@@ -403,20 +403,23 @@ def time_update_kernel(torch, _native, device, pk, flush, jets=32768, reps=20):
     stream = torch.cuda.current_stream()
     for _ in range(3):
         _native.bridge_update(x, k, m, v, lg, u, 0.0101, 5.0, 0.4)
-    times = []
-    for _ in range(reps):
-        flush.zero_()
+    # the working set (315 MB) is larger than L2 (126 MB), so back-to-back launches all stream from HBM; ten launches per
+    # event pair keep the host-side launch gap between the two events out of the kernel time
+    inner, times = 10, []
+    for _ in range(max(reps // inner, 3)):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(stream)
-        _native.bridge_update(x, k, m, v, lg, u, 0.0101, 5.0, 0.4)
+        for _ in range(inner):
+            _native.bridge_update(x, k, m, v, lg, u, 0.0101, 5.0, 0.4)
         e.record(stream)
         torch.cuda.synchronize()
-        times.append(s.elapsed_time(e))
+        times.append(s.elapsed_time(e) / inner)
     ms = sum(times) / len(times)
     nbytes = UPDATE_BYTES_PER_PARTICLE * B * N
     gbs = nbytes / (ms * 1e-3) / 1e9
     return {"kernel": "mmb::bridge_update_vec4_kernel<8>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
             "frac": gbs / pk["hbm"], "traffic": None, "peak_source": pk["src"], "jets": jets,
+            "l2": "working set 315 MB > 126 MB L2; 10 launches per event pair",
             "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms}
 
 

@@ -306,20 +306,10 @@ __device__ __forceinline__ float nan_to_num(float a) {
 }
 __device__ __forceinline__ float softplus(float a) { return a > 20.0f ? a : log1pf(expf(a)); }
 
-// block-wide sum of three values (128 threads), result broadcast; one barrier, its own scratch per call site
-__device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float (*s_red)[4]) {
-    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { s_red[0][w] = a; s_red[1][w] = b; s_red[2][w] = c; }
-    __syncthreads();
-    a = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
-    b = (s_red[1][0] + s_red[1][1]) + (s_red[1][2] + s_red[1][3]);
-    c = (s_red[2][0] + s_red[2][1]) + (s_red[2][2] + s_red[2][3]);
-}
-
-// One block (128 threads) per jet, thread n = particle slot n.  Dead slots (n >= dims) hold zeros — the sampler's
-// invariant, asserted by the reference in adjust_st_batch (jets_dataloader.py:451-452) — and stay zero under the update, so
-// they are neither read nor written: the pass moves 133 B per LIVE particle-step.
+// One WARP per jet: lane l serves the particle slots l, l+32, l+64, l+96, so the three centre-of-mass reductions are warp
+// shuffles and no block-wide barrier sits in the pass; four jets per 128-thread block.  Dead slots (n >= dims) hold zeros —
+// the sampler's invariant, asserted by the reference in adjust_st_batch (jets_dataloader.py:451-452) — and stay zero under the
+// update, so they are neither read nor written: the pass moves 133 B per LIVE particle-step.
 template <int S>
 __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __restrict__ x, float* __restrict__ onehot, int32_t* __restrict__ dims,
                                                                    const float* __restrict__ v, const float* __restrict__ logits,
@@ -328,111 +318,151 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
                                                                    float c_noise, float inv_std, float jump_dt,
                                                                    const float* __restrict__ z_diff, const float* __restrict__ u_jump,
                                                                    const float* __restrict__ z_new, uint64_t seed, uint64_t jet_offset,
-                                                                   int step, int N) {
-    __shared__ float s_red[3][3][4];
-    constexpr int F = 3 + S;
-    const int b = blockIdx.x, n = threadIdx.x;
+                                                                   int step, int B, int N) {
+    constexpr int F = 3 + S, SL = 4;   // up to 128 slots = 4 per lane
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
     const int dim = dims[b];
-    const bool live = n < dim;
-    const size_t pi = (size_t)b * N + n;
-    float xs[3] = {0, 0, 0}, oh[S], z[12], vs[3] = {0, 0, 0}, lg[S];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) z[i] = 0.0f;
-#pragma unroll
-    for (int s = 0; s < S; ++s) { oh[s] = 0.0f; lg[s] = 0.0f; }
-    if (live) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { xs[c] = x[pi * 3 + c]; vs[c] = __ldg(v + pi * 3 + c); }
-        if constexpr (S % 4 == 0) {
-#pragma unroll
-            for (int s = 0; s < S; s += 4) {
-                const float4 a = *reinterpret_cast<const float4*>(onehot + pi * S + s);
-                const float4 l = __ldg(reinterpret_cast<const float4*>(logits + pi * S + s));
-                oh[s] = a.x; oh[s + 1] = a.y; oh[s + 2] = a.z; oh[s + 3] = a.w;
-                lg[s] = l.x; lg[s + 1] = l.y; lg[s + 2] = l.z; lg[s + 3] = l.w;
-            }
-        } else {
-#pragma unroll
-            for (int s = 0; s < S; ++s) { oh[s] = onehot[pi * S + s]; lg[s] = __ldg(logits + pi * S + s); }
-        }
-        if (c_noise != 0.0f) {
-            if (z_diff) {
-                const float* zb = z_diff + (size_t)b * N * F;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) z[c] = __ldg(zb + n * 3 + c);
-#pragma unroll
-                for (int s = 0; s < S; ++s) z[3 + s] = __ldg(zb + (size_t)N * 3 + n * S + s);
-            } else {
-                philox_normals12(seed, jet_offset + (uint64_t)b, 2, step, n, z);
-            }
-        }
-    }
-    // birth decision and the new particle's values (sampler.py:238-255) — independent of the diffusion step
-    const float uj = u_jump ? __ldg(u_jump + b) : u01(philox_block(seed, jet_offset + (uint64_t)b, 5, step, 0).y);
+    const uint64_t jet = jet_offset + (uint64_t)b;
+    const float uj = u_jump ? __ldg(u_jump + b) : u01(philox_block(seed, jet, 5, step, 0).y);
     const bool born = (uj < __ldg(rate + b) * jump_dt) && dim < N;
     const int new_dim = born ? dim + 1 : dim;
-    // noise: delete_dims + centre-of-mass removal of its continuous part (sampler.py:224-229)
-    {
-        float a0 = z[0], a1 = z[1], a2 = z[2];
-        block_sum3(a0, a1, a2, s_red[0]);
-        const float inv = 1.0f / (float)dim;
-        if (live) { z[0] -= a0 * inv; z[1] -= a1 * inv; z[2] -= a2 * inv; }
-    }
-    // Euler-Maruyama on the live slots (sampler.py:221-231)
-    if (live) {
+    const float* zb = z_diff ? z_diff + (size_t)b * N * F : nullptr;
+    const bool noisy = c_noise != 0.0f;
+    const float cs = -(c_score * inv_std);   // c_score * -(inv_std * D): one rounding apart from the reference order
+    // ---- one-hot block: purely element-wise (sampler.py:221-231 on the one-hot slots; the birth fills slot `dim`)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float a = c_decay * xs[c] + (c_score * -(inv_std * vs[c]));
-            if (c_noise != 0.0f) a = a + (c_noise * z[c]);
-            xs[c] = nan_to_num(a);
+    for (int q = 0; q < SL; ++q) {
+        const int n = lane + 32 * q;
+        const size_t pi = (size_t)b * N + n;
+        if (n < dim) {
+            float oh[S], lg[S], z[8];
+            if constexpr (S % 4 == 0) {
+#pragma unroll
+                for (int s2 = 0; s2 < S; s2 += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(onehot + pi * S + s2);
+                    const float4 l = __ldg(reinterpret_cast<const float4*>(logits + pi * S + s2));
+                    oh[s2] = a.x; oh[s2 + 1] = a.y; oh[s2 + 2] = a.z; oh[s2 + 3] = a.w;
+                    lg[s2] = l.x; lg[s2 + 1] = l.y; lg[s2 + 2] = l.z; lg[s2 + 3] = l.w;
+                }
+            } else {
+#pragma unroll
+                for (int s2 = 0; s2 < S; ++s2) { oh[s2] = onehot[pi * S + s2]; lg[s2] = __ldg(logits + pi * S + s2); }
+            }
+            if (noisy) {
+                if (zb) {
+#pragma unroll
+                    for (int s2 = 0; s2 < S; ++s2) z[s2] = __ldg(zb + (size_t)N * 3 + n * S + s2);
+                } else {
+                    const uint4 r0 = philox_block(seed, jet, 3, step, n);
+                    box_muller(r0.x, r0.y, z[0], z[1]);
+                    box_muller(r0.z, r0.w, z[2], z[3]);
+                    if constexpr (S > 4) {
+                        const uint4 r1 = philox_block(seed, jet, 4, step, n);
+                        box_muller(r1.x, r1.y, z[4], z[5]);
+                        box_muller(r1.z, r1.w, z[6], z[7]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) {
+                float a = c_decay * oh[s2] + cs * lg[s2];
+                if (noisy) a = a + c_noise * z[s2];
+                oh[s2] = nan_to_num(a);
+            }
+            if constexpr (S % 4 == 0) {
+#pragma unroll
+                for (int s2 = 0; s2 < S; s2 += 4) *reinterpret_cast<float4*>(onehot + pi * S + s2) = make_float4(oh[s2], oh[s2 + 1], oh[s2 + 2], oh[s2 + 3]);
+            } else {
+#pragma unroll
+                for (int s2 = 0; s2 < S; ++s2) onehot[pi * S + s2] = oh[s2];
+            }
+        }
+    }
+    // ---- continuous block: Euler-Maruyama with the noise centred over the live particles, then centre-of-mass removal,
+    //      the birth, and a second centre-of-mass removal (sampler.py:221-255, jets_dataloader.py:433-478)
+    float xs[SL][3], zc[SL][3];
+#pragma unroll
+    for (int q = 0; q < SL; ++q) {
+        const int n = lane + 32 * q;
+        const size_t pi = (size_t)b * N + n;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { xs[q][c] = 0.0f; zc[q][c] = 0.0f; }
+        if (n < dim) {
+            float vs[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { xs[q][c] = x[pi * 3 + c]; vs[c] = __ldg(v + pi * 3 + c); }
+            if (noisy) {
+                if (zb) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) zc[q][c] = __ldg(zb + n * 3 + c);
+                } else {
+                    const uint4 r0 = philox_block(seed, jet, 2, step, n);
+                    float spare;
+                    box_muller(r0.x, r0.y, zc[q][0], zc[q][1]);
+                    box_muller(r0.z, r0.w, zc[q][2], spare);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xs[q][c] = c_decay * xs[q][c] + cs * vs[c];
+        }
+    }
+    const float inv_dim = 1.0f / (float)dim;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (noisy) {
+            const float zm = warp_sum((zc[0][c] + zc[1][c]) + (zc[2][c] + zc[3][c])) * inv_dim;
+#pragma unroll
+            for (int q = 0; q < SL; ++q)
+                if (lane + 32 * q < dim) xs[q][c] = xs[q][c] + c_noise * (zc[q][c] - zm);
         }
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            float a = c_decay * oh[s] + (c_score * -(inv_std * lg[s]));
-            if (c_noise != 0.0f) a = a + (c_noise * z[3 + s]);
-            oh[s] = nan_to_num(a);
-        }
+        for (int q = 0; q < SL; ++q) xs[q][c] = nan_to_num(xs[q][c]);
+        const float xm = warp_sum((xs[0][c] + xs[1][c]) + (xs[2][c] + xs[3][c])) * inv_dim;
+#pragma unroll
+        for (int q = 0; q < SL; ++q)
+            if (lane + 32 * q < dim) xs[q][c] -= xm;
     }
-    // adjust_st_batch: remove the mean of the continuous features over the live particles
-    {
-        float a0 = xs[0], a1 = xs[1], a2 = xs[2];
-        block_sum3(a0, a1, a2, s_red[1]);
-        const float inv = 1.0f / (float)dim;
-        if (live) { xs[0] -= a0 * inv; xs[1] -= a1 * inv; xs[2] -= a2 * inv; }
-    }
-    if (born && n == dim) {   // the new particle takes slot `dim`
+    if (born && lane == (dim & 31)) {   // the new particle takes slot `dim` (sampler.py:238-255)
         float zn[12];
         if (z_new) {
 #pragma unroll
             for (int i = 0; i < F; ++i) zn[i] = __ldg(z_new + (size_t)b * F + i);
         } else {
-            philox_normals12(seed, jet_offset + (uint64_t)b, 6, step, 0, zn);
+            philox_normals12(seed, jet, 6, step, 0, zn);
         }
         const float* nm = new_mean + (size_t)b * F;
         const float* ns = new_std + (size_t)b * F;
+        float nx[3], no[S];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) xs[c] = nan_to_num(__ldg(nm + c) + zn[c] * softplus(__ldg(ns + c)));
+        for (int c = 0; c < 3; ++c) nx[c] = nan_to_num(__ldg(nm + c) + zn[c] * softplus(__ldg(ns + c)));
 #pragma unroll
-        for (int s = 0; s < S; ++s) oh[s] = nan_to_num(__ldg(nm + 3 + s) + zn[3 + s] * softplus(__ldg(ns + 3 + s)));
+        for (int s2 = 0; s2 < S; ++s2) no[s2] = nan_to_num(__ldg(nm + 3 + s2) + zn[3 + s2] * softplus(__ldg(ns + 3 + s2)));
+#pragma unroll
+        for (int q = 0; q < SL; ++q)
+            if (q == (dim >> 5)) { xs[q][0] = nx[0]; xs[q][1] = nx[1]; xs[q][2] = nx[2]; }
+        const size_t pi = (size_t)b * N + dim;
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2) onehot[pi * S + s2] = no[s2];
     }
-    {   // second adjust_st_batch with the new multiplicity (it runs whether or not a particle was born)
-        float a0 = xs[0], a1 = xs[1], a2 = xs[2];
-        block_sum3(a0, a1, a2, s_red[2]);
-        const float inv = 1.0f / (float)new_dim;
-        if (n < new_dim) { xs[0] -= a0 * inv; xs[1] -= a1 * inv; xs[2] -= a2 * inv; }
+    const float inv_new = 1.0f / (float)new_dim;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {   // second adjust_st_batch with the new multiplicity (it runs whether or not a particle was born)
+        const float xm = warp_sum((xs[0][c] + xs[1][c]) + (xs[2][c] + xs[3][c])) * inv_new;
+#pragma unroll
+        for (int q = 0; q < SL; ++q)
+            if (lane + 32 * q < new_dim) xs[q][c] -= xm;
     }
-    if (n < new_dim) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) x[pi * 3 + c] = xs[c];
-        if constexpr (S % 4 == 0) {
+    for (int q = 0; q < SL; ++q) {
+        const int n = lane + 32 * q;
+        if (n < new_dim) {
+            const size_t pi = (size_t)b * N + n;
 #pragma unroll
-            for (int s = 0; s < S; s += 4) *reinterpret_cast<float4*>(onehot + pi * S + s) = make_float4(oh[s], oh[s + 1], oh[s + 2], oh[s + 3]);
-        } else {
-#pragma unroll
-            for (int s = 0; s < S; ++s) onehot[pi * S + s] = oh[s];
+            for (int c = 0; c < 3; ++c) x[pi * 3 + c] = xs[q][c];
         }
     }
-    if (n == 0 && born) dims[b] = new_dim;
+    if (lane == 0 && born) dims[b] = new_dim;
 }
 
 // broadcast ts[step] for the sampler's per-jet uniform of the nearest particle when drawn in-kernel
@@ -609,8 +639,8 @@ static int launch_sampler_update(float* x, float* onehot, int32_t* dims, const f
                                  uint64_t jet_offset, int step, int B, int N, int S, cudaStream_t s) {
     if (N > 128 || N < 1) return fail(MMB_EUNSUPPORTED, "sampler update handles 1..128 particle slots per jet");
 #define MMB_UPD(SV)                                                                                                                  \
-    trans_sampler_update_kernel<SV><<<B, 128, 0, s>>>(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score, c_noise, \
-                                                      inv_std, jump_dt, z_diff, u_jump, z_new, seed, jet_offset, step, N)
+    trans_sampler_update_kernel<SV><<<(B + 3) / 4, 128, 0, s>>>(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score,  \
+                                                                c_noise, inv_std, jump_dt, z_diff, u_jump, z_new, seed, jet_offset, step, B, N)
     switch (S) {
         case 4: MMB_UPD(4); break;
         case 5: MMB_UPD(5); break;
