@@ -24,6 +24,8 @@
 // with the tolerance stated in tests/test_gpu_absorbing.py.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "mmb_device.cuh"
@@ -145,6 +147,7 @@ struct HeadParams {
     const float* jet_b;      // [n_jet]
     int n_jet;
     float* jet_out;          // [B][n_jet]
+    long long* trace;        // debug: clock64() stamps of the first jet of CTA 0 (tools/stack_trace.py); null in production
 };
 
 constexpr int kSmemW = 2 * kSlot;                         // weight ring
@@ -209,12 +212,12 @@ __device__ __forceinline__ int warp_halving_index(int lane) {
 __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t s_tmem_slot;
-    __shared__ __align__(8) uint64_t s_bars[3];             // full[0], full[1], mma
+    __shared__ __align__(8) uint64_t s_bars[4];             // full[0], full[1], mma, mma2 (the v GEMM that runs under the softmax)
     __shared__ __align__(16) float s_stat[256];             // per channel: scale [128], shift [128] of the running GroupNorm
     __shared__ __align__(16) float s_part[16][32];          // per-warp partial sums (GroupNorm statistics / column sums)
     __shared__ __align__(16) float s_bias2[kMaxBlocks][kC]; // conv1 bias + this jet's time term, per block
-    __shared__ float s_rowx[4][128];                        // softmax row max, then row sum, per (channel quarter, row)
-    __shared__ float s_dot[4][128];                         // per-particle output partials
+    __shared__ float s_rowx[4][128], s_sum[4][128];         // softmax row max and row sum per (channel quarter, row)
+    float (*s_dot)[128] = s_rowx;                           // per-particle output partials (after the last softmax)
     __shared__ float s_mean[128];                           // mean of the residual stream over the N slots (per-jet head)
     const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7, warp = tid >> 5, lane = tid & 31;
     const int nblk = p.n_blocks, n_seq = 1 + 6 * nblk;
@@ -224,8 +227,8 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
 
     for (int i = tid; i < HeadTable::floats(nblk); i += kThreads) sTab[i] = __ldg(p.table + i);
     for (int i = tid; i < 256; i += kThreads) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-    const uint32_t bar_full0 = smem_u32(&s_bars[0]), bar_full1 = smem_u32(&s_bars[1]), bar_mma = smem_u32(&s_bars[2]);
-    if (tid == 0) { mbar_init(bar_full0, 1); mbar_init(bar_full1, 1); mbar_init(bar_mma, 1); }
+    const uint32_t bar_full0 = smem_u32(&s_bars[0]), bar_full1 = smem_u32(&s_bars[1]), bar_mma = smem_u32(&s_bars[2]), bar_mma2 = smem_u32(&s_bars[3]);
+    if (tid == 0) { mbar_init(bar_full0, 1); mbar_init(bar_full1, 1); mbar_init(bar_mma, 1); mbar_init(bar_mma2, 1); }
     if (warp == 0) tmem_alloc(smem_u32(&s_tmem_slot), 512);
     fence_barrier_init();
     fence_proxy_async();
@@ -240,42 +243,61 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     const int my_jets = p.B > (int)blockIdx.x ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t total_mats = (uint32_t)my_jets * n_seq;
     const uint32_t wbase = smem_u32(smem);
+    // Ring slot 0 = [bias tile | weight tile], slot 1 = [weight tile | bias tile]: the two weight tiles are adjacent in shared
+    // memory, so a pair of streamed matrices can be consumed as ONE [256 x 128] B operand (the fused q/k GEMM).
+    auto w_addr = [&](uint32_t slot) { return wbase + (slot ? kSlot : 4096u); };
+    auto b_addr = [&](uint32_t slot) { return wbase + (slot ? kSlot + 32768u : 0u); };
     auto issue_load = [&](uint32_t i) {  // thread 0 only
         const uint32_t bar = (i & 1) ? bar_full1 : bar_full0;
+        const uint8_t* src = p.image + (size_t)(i % n_seq) * kSlot;
         mbar_expect_tx(bar, kSlot);
-        bulk_g2s(wbase + (i & 1) * kSlot, p.image + (size_t)(i % n_seq) * kSlot, kSlot, bar);
+        bulk_g2s(w_addr(i & 1), src, 32768, bar);
+        bulk_g2s(b_addr(i & 1), src + 32768, 4096, bar);
     };
     if (tid == 0) {
         if (total_mats > 0) issue_load(0);
         if (total_mats > 1) issue_load(1);
     }
-    uint32_t wseq = 0, mma_phase = 0;
-    constexpr uint32_t idesc128 = instr_desc(128, 128, false), idesc64mn = instr_desc(128, 64, true);
+    uint32_t wseq = 0, mma_phase = 0, mma2_phase = 0;
+    constexpr uint32_t idesc128 = instr_desc(128, 128, false), idesc64mn = instr_desc(128, 64, true), idesc256 = instr_desc(128, 256, false);
     const uint64_t ones_desc = smem_desc(smem_u32(sOnes), 128, 256);
     const uint32_t aA = smem_u32(sA), aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
 
     // D (+)= A[128 x 16*nk] * W^T with the streamed matrix `wseq`; optional bias K-step; commit.  Thread 0.
-    auto gemm_w = [&](uint32_t d, uint32_t a_addr, uint32_t a_sbo, int nk, bool accumulate, bool bias) {
-        const uint32_t wb = wbase + (wseq & 1) * kSlot;
+    auto gemm_w = [&](uint32_t d, uint32_t a_addr, uint32_t a_sbo, int nk, bool accumulate, bool bias, uint32_t bar_done) {
+        const uint32_t wb = w_addr(wseq & 1);
         mbar_wait((wseq & 1) ? bar_full1 : bar_full0, (wseq >> 1) & 1);
         tc_fence_after();
         for (int j = 0; j < nk; ++j)
             umma(d, smem_desc(a_addr + j * 256, 128, a_sbo), smem_desc(wb + j * 256, 128, 2048), idesc128, (accumulate || j > 0) ? 1u : 0u);
-        if (bias) umma(d, ones_desc, smem_desc(wb + 32768, 128, 256), idesc128, 1u);
+        if (bias) umma(d, ones_desc, smem_desc(b_addr(wseq & 1), 128, 256), idesc128, 1u);
+        umma_commit(bar_done);
+    };
+    // The q and k projections as one M128 x N256 GEMM over the two ring slots: D columns [0,128) come from the matrix in
+    // slot 0, [128,256) from the one in slot 1 (which of q, k sits where alternates from jet to jet: n_seq is odd).
+    // The q bias rides on one more K-step into q's half.  Thread 0.
+    auto gemm_qk = [&](uint32_t d, uint32_t a_addr) {
+        mbar_wait((wseq & 1) ? bar_full1 : bar_full0, (wseq >> 1) & 1);
+        mbar_wait(((wseq + 1) & 1) ? bar_full1 : bar_full0, ((wseq + 1) >> 1) & 1);
+        tc_fence_after();
+        for (int j = 0; j < 8; ++j)
+            umma(d, smem_desc(a_addr + j * 256, 128, 2048), smem_desc(w_addr(0) + j * 256, 128, 2048), idesc256, j > 0 ? 1u : 0u);
+        umma(d + (wseq & 1) * 128, ones_desc, smem_desc(b_addr(wseq & 1), 128, 256), idesc128, 1u);
         umma_commit(bar_mma);
     };
     // all threads: wait for the committed MMAs; the ring slot of matrix `wseq` is free again -> prefetch wseq+2
-    auto mma_done = [&](bool used_weights) {
+    auto mma_done = [&](int used_weights) {
         mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
         tc_fence_after();
-        if (used_weights) {
+        for (int i = 0; i < used_weights; ++i) {
             if (tid == 0 && wseq + 2 < total_mats) issue_load(wseq + 2);
             ++wseq;
         }
     };
 
     // GroupNorm(32 groups of 4 channels) over the N live rows of a TMEM tile (+ per-channel bias) -> bf16 A tile.
-    // One TMEM read: the 32 values stay in registers across the statistics exchange.
+    // One TMEM read: the 32 values stay in registers across the statistics exchange, which only involves the four warps of a
+    // channel quarter (named barrier 1 + cq, 128 threads) — the quarters do not wait for each other until the tile is complete.
     auto group_norm_to_A = [&](uint32_t d_src, const float* bias /*nullable, smem*/, const float* gamma, const float* beta,
                                bool swish, bool valid) {
         float v[32];
@@ -300,20 +322,20 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         }
         warp_halving_sum<16>(st, lane);
         if ((lane & 1) == 0) s_part[warp][warp_halving_index<16>(lane)] = st[0];
-        __syncthreads();
-        if (tid < 128) {  // one thread per channel: y = x*scale + shift with the statistics of its group folded in
-            const int g = tid >> 2, w0 = (g >> 3) * 4, gi = g & 7;   // group g lives in the warps of channel quarter g >> 3
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + cq) : "memory");
+        if ((warp & 3) == 0) {  // first warp of the quarter, one lane per channel: y = x*scale + shift with its group's statistics
+            const int c = col0 + lane, gi = lane >> 2, w0 = cq * 4;
             const float s = (s_part[w0][gi] + s_part[w0 + 1][gi]) + (s_part[w0 + 2][gi] + s_part[w0 + 3][gi]);
             const float q = (s_part[w0][8 + gi] + s_part[w0 + 1][8 + gi]) + (s_part[w0 + 2][8 + gi] + s_part[w0 + 3][8 + gi]);
             const float inv = 1.0f / (4.0f * (float)p.N);
             const float mean = s * inv;
             const float var = fmaxf(q * inv - mean * mean, 0.0f);
             const float h = swish ? 0.5f : 1.0f;   // swish(a) = a/2 * tanh(a/2) + a/2: the halving rides on the affine
-            const float scale = rsqrtf(var + 1e-6f) * gamma[tid] * h;
-            s_stat[tid] = scale;
-            s_stat[128 + tid] = fmaf(-mean, scale, beta[tid] * h);
+            const float scale = rsqrtf(var + 1e-6f) * gamma[c] * h;
+            s_stat[c] = scale;
+            s_stat[128 + c] = fmaf(-mean, scale, beta[c] * h);
         }
-        __syncthreads();
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + cq) : "memory");
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             const float4 sc = *reinterpret_cast<const float4*>(s_stat + col0 + j);
@@ -333,19 +355,12 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         fence_proxy_async();
         __syncthreads();
     };
-    // ACC -> bf16 tile (Q, K or V); their biases are handled algebraically (Q: extra K-step; K: softmax-invariant, dropped;
-    // V: folded into the proj_out bias because softmax rows sum to one)
-    auto acc_to_tile = [&](uint8_t* tile) {
-        float v[32];
-        tmem_ld32(dACC + lane_off + col0, v);
-        store_row32(tile, r, cq, v);
-        tc_fence_before();
-        fence_proxy_async();
-        __syncthreads();
-    };
-
+    // q / k / v biases are handled algebraically: q rides on an extra K-step; k is a per-query constant in the logits
+    // (softmax-invariant) and is dropped; v is folded into the proj_out bias because softmax rows sum to one.
+#define STK_TRACE(id) do { if (p.trace && blockIdx.x == 0 && jet == 0 && tid == 32) p.trace[id] = clock64(); } while (0)
     for (int jet = blockIdx.x; jet < p.B; jet += gridDim.x) {
         const bool valid = r < p.N;
+        STK_TRACE(0);
         const size_t pidx = (size_t)jet * p.N + r;
         // ---- proj_in: mode 0 [hidden, one_hot(mask)] (absorbing_flows.py:113-118); mode 1 [hidden, onehot]
         //      (transdimensional_model.py:295-303); mode 2 mask * [hidden, onehot, distance to the nearest particle,
@@ -390,29 +405,42 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
-        if (tid == 0) gemm_w(dX, smem_u32(sA0), 512, 2, false, true);
-        mma_done(true);
+        STK_TRACE(1);
+        if (tid == 0) gemm_w(dX, smem_u32(sA0), 512, 2, false, true, bar_mma);
+        mma_done(1);
+        STK_TRACE(2);
 
         for (int blk = 0; blk < nblk; ++blk) {
             const float* T = sTab + blk * HeadTable::kPerBlock;
             // ---- ResnetBlock (gsdm.py:54-66)
             group_norm_to_A(dX, nullptr, T + 0 * kC, T + 1 * kC, true, valid);
-            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // conv1
-            mma_done(true);
+            if (blk == 0) STK_TRACE(3);
+            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false, bar_mma);           // conv1
+            mma_done(1);
+            if (blk == 0) STK_TRACE(4);
             group_norm_to_A(dACC, s_bias2[blk], T + 3 * kC, T + 4 * kC, true, valid);
-            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true);               // X += conv2(.) + b2
-            mma_done(true);
+            if (blk == 0) STK_TRACE(5);
+            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true, bar_mma);               // X += conv2(.) + b2
+            mma_done(1);
+            if (blk == 0) STK_TRACE(6);
             // ---- AttnBlock (gsdm.py:142-168)
             group_norm_to_A(dX, nullptr, T + 5 * kC, T + 6 * kC, false, valid);
-            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, true);            // q (+ bq)
-            mma_done(true);
-            acc_to_tile(sQ);
-            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // k
-            mma_done(true);
-            acc_to_tile(sK);
-            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false);           // v
-            mma_done(true);
-            acc_to_tile(sV);
+            if (blk == 0) STK_TRACE(7);
+            const uint32_t q_half = wseq & 1;                                // q sits in ring slot wseq & 1
+            if (tid == 0) gemm_qk(dACC, aA);                                 // [q | k] (+ bq), one N = 256 GEMM into ACC | S0
+            mma_done(2);
+            if (blk == 0) STK_TRACE(8);
+            {   // both tiles in one epilogue phase
+                float v[32];
+                tmem_ld32(dACC + q_half * 128 + lane_off + col0, v);
+                store_row32(sQ, r, cq, v);
+                tmem_ld32(dACC + (q_half ^ 1) * 128 + lane_off + col0, v);
+                store_row32(sK, r, cq, v);
+                tc_fence_before();
+                fence_proxy_async();
+                __syncthreads();
+            }
+            if (blk == 0) STK_TRACE(9);
             if (tid == 0) {                                                  // S_h = Q_h K_h^T, K = 64
                 tc_fence_after();
                 for (int h = 0; h < kHeads; ++h)
@@ -420,10 +448,13 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                         umma(h ? dS1 : dS0, smem_desc(aQ + h * 1024 + j * 256, 128, 2048), smem_desc(aK + h * 1024 + j * 256, 128, 2048),
                              idesc128, j > 0);
                 umma_commit(bar_mma);
+                gemm_w(dACC, aA, 2048, 8, false, false, bar_mma2);            // v: runs under the softmax, its own barrier
             }
-            mma_done(false);
+            mma_done(0);
+            if (blk == 0) STK_TRACE(11);
             // softmax over the N keys: thread (r, cq) serves head cq >> 1, keys [64 (cq & 1), +64); the two halves of a row
-            // exchange max and sum through shared memory.  P (unnormalised, bf16) -> A tile (head 0) / Q tile (head 1)
+            // exchange max and sum through shared memory.  P (unnormalised, bf16) -> K tile (head 0) / Q tile (head 1), both
+            // dead once S is complete; the A tile still feeds the v GEMM.
             {
                 const int h = cq >> 1, kh = cq & 1;
                 const uint32_t dS = (h ? dS1 : dS0) + lane_off + kh * 64;
@@ -441,9 +472,8 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                     }
                 }
                 s_rowx[cq][r] = mx;
-                __syncthreads();
+                asm volatile("bar.sync %0, 256;" ::"r"(5 + h) : "memory");   // the two key halves of a head
                 mx = fmaxf(mx, s_rowx[cq ^ 1][r]);
-                __syncthreads();   // s_rowx is reused for the sums
                 const float sc = 0.125f * 1.4426950408889634f;  // dh^-1/2 * log2(e)
                 const float off = -mx * sc;
                 float s0 = 0.0f, s1 = 0.0f;
@@ -461,25 +491,34 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                         }
                         fadd2(s0, s1, s0, s1, v[j], v[j + 1]);
                     }
-                    store_row32(h ? sQ : sA, r, kh * 2 + c, v);
+                    store_row32(h ? sQ : sK, r, kh * 2 + c, v);
                 }
-                s_rowx[cq][r] = s0 + s1;
+                s_sum[cq][r] = s0 + s1;
+                // the v GEMM finished long ago: its tile joins this phase's fence and barrier
+                mbar_wait(bar_mma2, mma2_phase); mma2_phase ^= 1;
+                tc_fence_after();
+                if (tid == 0 && wseq + 2 < total_mats) issue_load(wseq + 2);
+                ++wseq;
+                tmem_ld32(dACC + lane_off + col0, v);
+                store_row32(sV, r, cq, v);
             }
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();
+            if (blk == 0) STK_TRACE(12);
             if (tid == 0) {                                                  // O_h = P_h V_h, K = 128 keys, N = 64
                 tc_fence_after();
                 for (int h = 0; h < kHeads; ++h)
                     for (int j = 0; j < 8; ++j)
-                        umma(dACC + h * 64, smem_desc((h ? aQ : aA) + j * 256, 128, 2048),
+                        umma(dACC + h * 64, smem_desc((h ? aQ : aK) + j * 256, 128, 2048),
                              smem_desc(aV + h * 1024 + j * 4096, 2048, 128), idesc64mn, j > 0);
                 umma_commit(bar_mma);
             }
-            mma_done(false);
+            mma_done(0);
+            if (blk == 0) STK_TRACE(13);
             {
                 float v[32];  // columns [32 cq, +32) of O belong to head cq >> 1: normalised by that head's row sum
-                const float rinv = 1.0f / (s_rowx[cq][r] + s_rowx[cq ^ 1][r]);
+                const float rinv = 1.0f / (s_sum[cq][r] + s_sum[cq ^ 1][r]);
                 tmem_ld32(dACC + lane_off + col0, v);
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) fmul2(v[j], v[j + 1], v[j], v[j + 1], rinv, rinv);
@@ -488,9 +527,12 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true);               // X += proj_out(.) + (b_o + W_o b_v)
-            mma_done(true);
+            if (blk == 0) STK_TRACE(14);
+            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true, bar_mma);               // X += proj_out(.) + (b_o + W_o b_v)
+            mma_done(1);
+            if (blk == 0) STK_TRACE(15);
         }
+        STK_TRACE(16);
         // ---- per-particle output: one 128-vector against the residual stream (absorbing: post_rate_proj(pre_rate_proj(X))
         //      folded, absorbing_flows.py:127-131; trans: near_atom_proj / vec_weighting_proj) and, for the per-jet heads,
         //      the mean of X over the N slots followed by a folded [n_jet x 128] Linear (transdimensional_model.py:309-311,403-405)
@@ -534,6 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         }
         tc_fence_before();
         __syncthreads();  // X and the operand tiles are rewritten by the next jet
+        STK_TRACE(17);
     }
     tc_fence_before();
     __syncthreads();
@@ -629,6 +672,21 @@ int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* bloc
     return rc;
 }
 
+// MMB_STACK_TRACE=1: per-phase clock64() stamps of the first jet of CTA 0 (tools/stack_trace.py reads them)
+static long long* g_stack_trace = nullptr;
+static long long* stack_trace_buffer() {
+    static const bool on = [] { const char* e = getenv("MMB_STACK_TRACE"); return e && e[0] == '1'; }();
+    if (!on) return nullptr;
+    if (!g_stack_trace && cudaMalloc(&g_stack_trace, 64 * sizeof(long long)) == cudaSuccess) cudaMemset(g_stack_trace, 0, 64 * sizeof(long long));
+    return g_stack_trace;
+}
+int stack_read_trace(long long* out, int n) {
+    if (!g_stack_trace) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, g_stack_trace, sizeof(long long) * (n < 64 ? n : 64), cudaMemcpyDeviceToHost);
+    return n < 64 ? n : 64;
+}
+
 int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B, int N, cudaStream_t stream) {
     if (N < 1 || N > 128) return fail(MMB_EUNSUPPORTED, "transformer stack handles 1..128 particle slots per jet (got %d)", N);
     if (B == 0) return MMB_OK;
@@ -637,6 +695,7 @@ int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B,
     p.mode = io.mode; p.S = io.S; p.hidden = io.hidden; p.mask = io.mask; p.onehot = io.onehot; p.x = io.x; p.nearest = io.nearest;
     p.tbias = io.tbias; p.tbias_stride = io.tbias_stride; p.B = B; p.N = N; p.logit_out = io.dot_out;
     p.jet_wT = st->jet_wT; p.jet_b = st->jet_b; p.n_jet = io.jet_out ? st->n_jet : 0; p.jet_out = io.jet_out;
+    p.trace = stack_trace_buffer();
     const size_t bytes = kOffTab + (size_t)HeadTable::floats(st->n_blocks) * 4 + 1024;
     cudaFuncAttributes attr;
     if (int rc = cuda_ok(cudaFuncGetAttributes(&attr, absorb_head_tc_kernel), "head attributes")) return rc;

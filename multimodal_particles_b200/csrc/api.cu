@@ -246,5 +246,6 @@ int mmb_validation_histograms(const float* x, const uint8_t* k, const uint8_t* m
 
 // debug only (not part of include/mmbridge.h): phase timestamps of the tcgen05 generation kernel, see tools/tc_trace.py
 int mmb_debug_read_trace(long long* out, int n) { return tc_read_trace(out, n); }
+int mmb_debug_read_stack_trace(long long* out, int n) { return stack_read_trace(out, n); }
 
 }  // extern "C"

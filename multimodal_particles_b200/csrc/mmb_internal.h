@@ -59,6 +59,7 @@ int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* bloc
                    const float* jet_w, const float* jet_b, int n_jet);
 void tf_stack_free(TfStack* st);
 int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B, int N, cudaStream_t stream);
+int stack_read_trace(long long* out, int n);
 
 struct AbsorbHead;
 int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, size_t n_floats, int device, AbsorbHead** out);
