@@ -376,6 +376,24 @@ int mmb_trans_sampler_update(float* x, float* onehot, int32_t* dims, const float
 int mmb_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,
                               int bins, float lo, float hi, int max_mult, uint64_t* counts, void* stream);
 
+/*
+ * Post-processing + jet-level observables of a generated batch in one pass, so that validation needs the
+ * 44-byte jet rows instead of the particle clouds:
+ *   ParticleClouds.postprocess(input_continuous="standardize", input_discrete="tokens")  (mp/data/particle_clouds/particles.py:124-156):
+ *     x_phys = (x * std + mean) * mask;  tokens_to_physics (mp/data/particle_clouds/utils.py:310-337): flavor 0..4, charge -1/0/+1, both * mask;
+ *   ParticleClouds.compute_4mom (particles.py:85-89) and JetClassHighLevelFeatures.__init__ / jet_charge
+ *     (mp/data/particle_clouds/jets.py:90-107,138-141): per jet px, py, pz, e (sums over ALL slots of the masked cloud),
+ *     pt = sqrt(max(px^2+py^2, 0)), m = sqrt(max(e^2-px^2-py^2-pz^2, 0)), eta = 0.5 log((pt+pz)/(pt-pz)), phi = atan2(py, px),
+ *     multiplicity, Q_total = sum charge, Q_jet = sum charge*pt / pt_jet.
+ * x [B,N,3] f32, k [B,N] u8 tokens (0..7), mask [B,N] u8; mean / std: HOST float[3], or NULL for data that is not standardised.
+ * Outputs (each nullable): x_phys [B,N,3] f32; flavor_charge [B,N,2] int8 (flavor, charge; 0,0 on masked slots);
+ * jets [B][MMB_JET_OBS] f32 in the order of the enum below.
+ */
+enum { MMB_JET_PX = 0, MMB_JET_PY, MMB_JET_PZ, MMB_JET_E, MMB_JET_PT, MMB_JET_M, MMB_JET_ETA, MMB_JET_PHI, MMB_JET_MULT,
+       MMB_JET_QTOTAL, MMB_JET_QJET, MMB_JET_OBS };
+int mmb_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* std, int B, int N,
+                        float* x_phys, int8_t* flavor_charge, float* jets, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

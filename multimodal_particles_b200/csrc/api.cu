@@ -244,6 +244,15 @@ int mmb_validation_histograms(const float* x, const uint8_t* k, const uint8_t* m
                                         reinterpret_cast<unsigned long long*>(counts), static_cast<cudaStream_t>(stream));
 }
 
+int mmb_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* std, int B, int N,
+                        float* x_phys, int8_t* flavor_charge, float* jets, void* stream) {
+    if (!x || !k || !mask) return fail(MMB_EINVAL, "mmb_jet_observables: null argument");
+    if ((mean == nullptr) != (std == nullptr)) return fail(MMB_EINVAL, "mmb_jet_observables: mean and std go together");
+    if (B < 0 || N < 0) return fail(MMB_EINVAL, "mmb_jet_observables: negative size");
+    if (B == 0 || N == 0) return MMB_OK;
+    return launch_jet_observables(x, k, mask, mean, std, B, N, x_phys, flavor_charge, jets, static_cast<cudaStream_t>(stream));
+}
+
 // debug only (not part of include/mmbridge.h): phase timestamps of the tcgen05 generation kernel, see tools/tc_trace.py
 int mmb_debug_read_trace(long long* out, int n) { return tc_read_trace(out, n); }
 int mmb_debug_read_stack_trace(long long* out, int n) { return stack_read_trace(out, n); }

@@ -55,4 +55,51 @@ int launch_validation_histograms(const float* x, const uint8_t* k, const uint8_t
     return cuda_ok(cudaGetLastError(), "validation_histograms launch");
 }
 
+// ---- post-processing + jet observables (particles.py:85-89,124-156; utils.py:310-337; jets.py:90-107,138-141) ----------
+// One warp per jet, lane l serves the slots l, l+32, ...: 28 B per particle (x r+w 24, token 1, mask 1, flavor/charge 2)
+// plus one 44-byte row per jet; the seven jet sums are warp shuffles.
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(128) jet_observables_kernel(const float* __restrict__ x, const uint8_t* __restrict__ k,
+                                                              const uint8_t* __restrict__ mask, float3 mean, float3 sd, int B, int N,
+                                                              float* __restrict__ x_phys, int8_t* __restrict__ fc, float* __restrict__ jets) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    float px = 0, py = 0, pz = 0, e = 0, mult = 0, q0 = 0, q1 = 0;
+    for (int n = lane; n < N; n += 32) {
+        const size_t p = (size_t)b * N + n;
+        const float m = mask[p] ? 1.0f : 0.0f;
+        const float pt = (x[p * 3] * sd.x + mean.x) * m, eta = (x[p * 3 + 1] * sd.y + mean.y) * m, phi = (x[p * 3 + 2] * sd.z + mean.z) * m;
+        const int tok = k[p];
+        // tokens_to_physics: 0 photon, 1 neutral hadron, 2/3 charged hadron -/+, 4/5 electron -/+, 6/7 muon -/+
+        const int flavor = m != 0.0f ? (tok < 2 ? tok : 1 + (tok >> 1)) : 0;
+        const int charge = m != 0.0f ? (tok < 2 ? 0 : ((tok & 1) ? 1 : -1)) : 0;
+        if (x_phys) { x_phys[p * 3] = pt; x_phys[p * 3 + 1] = eta; x_phys[p * 3 + 2] = phi; }
+        if (fc) { fc[p * 2] = (int8_t)flavor; fc[p * 2 + 1] = (int8_t)charge; }
+        px += pt * cosf(phi); py += pt * sinf(phi); pz += pt * sinhf(eta); e += pt * coshf(eta);
+        mult += m; q0 += (float)charge; q1 += (float)charge * pt;
+    }
+    px = wsum(px); py = wsum(py); pz = wsum(pz); e = wsum(e); mult = wsum(mult); q0 = wsum(q0); q1 = wsum(q1);
+    if (lane == 0 && jets) {
+        float* o = jets + (size_t)b * MMB_JET_OBS;
+        const float pt = sqrtf(fmaxf(px * px + py * py, 0.0f));
+        o[MMB_JET_PX] = px; o[MMB_JET_PY] = py; o[MMB_JET_PZ] = pz; o[MMB_JET_E] = e; o[MMB_JET_PT] = pt;
+        o[MMB_JET_M] = sqrtf(fmaxf(e * e - px * px - py * py - pz * pz, 0.0f));
+        o[MMB_JET_ETA] = 0.5f * logf((pt + pz) / (pt - pz));
+        o[MMB_JET_PHI] = atan2f(py, px);
+        o[MMB_JET_MULT] = mult; o[MMB_JET_QTOTAL] = q0; o[MMB_JET_QJET] = q1 / pt;
+    }
+}
+
+int launch_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* sd, int B, int N,
+                           float* x_phys, int8_t* fc, float* jets, cudaStream_t stream) {
+    const float3 m = mean ? make_float3(mean[0], mean[1], mean[2]) : make_float3(0.0f, 0.0f, 0.0f);
+    const float3 s = sd ? make_float3(sd[0], sd[1], sd[2]) : make_float3(1.0f, 1.0f, 1.0f);
+    jet_observables_kernel<<<(B + 3) / 4, 128, 0, stream>>>(x, k, mask, m, s, B, N, x_phys, fc, jets);
+    return cuda_ok(cudaGetLastError(), "jet_observables launch");
+}
+
 }  // namespace mmb

@@ -73,6 +73,9 @@ int launch_absorb_head(const AbsorbHead* h, const float* hidden, const uint8_t* 
 int launch_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,
                                  int bins, float lo, float hi, int max_mult, unsigned long long* counts, cudaStream_t stream);
 
+int launch_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* sd, int B, int N,
+                           float* x_phys, int8_t* fc, float* jets, cudaStream_t stream);
+
 // epic_fp32.cu — CUDA-core path, bit-identical to the oracle
 int launch_epic_forward_fp32(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
                              const float* temb, int temb_stride, int B, int N,

@@ -861,6 +861,39 @@ void mmbo_trans_sample(const MmbEpicDims* ed, const float* epacked, const MmbTra
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* ParticleClouds.postprocess + compute_4mom + JetClassHighLevelFeatures kinematics / charges
+ * (mp/data/particle_clouds/particles.py:85-89,124-156; utils.py:310-337; jets.py:90-107,138-141) */
+void mmbo_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* sd, int B, int N,
+                          float* x_phys, int8_t* fc, float* jets) {
+    for (int b = 0; b < B; ++b) {
+        double px = 0, py = 0, pz = 0, e = 0, mult = 0, q0 = 0, q1 = 0;
+        for (int n = 0; n < N; ++n) {
+            const size_t p = (size_t)b * N + n;
+            const float m = mask[p] ? 1.0f : 0.0f;
+            float c[3];
+            for (int i = 0; i < 3; ++i) c[i] = (x[p * 3 + i] * (sd ? sd[i] : 1.0f) + (mean ? mean[i] : 0.0f)) * m;
+            const int tok = k[p];
+            const int flavor = m != 0.0f ? (tok < 2 ? tok : 1 + (tok >> 1)) : 0;
+            const int charge = m != 0.0f ? (tok < 2 ? 0 : ((tok & 1) ? 1 : -1)) : 0;
+            if (x_phys) for (int i = 0; i < 3; ++i) x_phys[p * 3 + i] = c[i];
+            if (fc) { fc[p * 2] = (int8_t)flavor; fc[p * 2 + 1] = (int8_t)charge; }
+            px += c[0] * cosf(c[2]); py += c[0] * sinf(c[2]); pz += c[0] * sinhf(c[1]); e += c[0] * coshf(c[1]);
+            mult += m; q0 += charge; q1 += charge * c[0];
+        }
+        if (jets) {
+            float* o = jets + (size_t)b * MMB_JET_OBS;
+            const float fpx = (float)px, fpy = (float)py, fpz = (float)pz, fe = (float)e;
+            const float pt = sqrtf(fmaxf(fpx * fpx + fpy * fpy, 0.0f));
+            o[MMB_JET_PX] = fpx; o[MMB_JET_PY] = fpy; o[MMB_JET_PZ] = fpz; o[MMB_JET_E] = fe; o[MMB_JET_PT] = pt;
+            o[MMB_JET_M] = sqrtf(fmaxf(fe * fe - fpx * fpx - fpy * fpy - fpz * fpz, 0.0f));
+            o[MMB_JET_ETA] = 0.5f * logf((pt + fpz) / (pt - fpz));
+            o[MMB_JET_PHI] = atan2f(fpy, fpx);
+            o[MMB_JET_MULT] = (float)mult; o[MMB_JET_QTOTAL] = (float)q0; o[MMB_JET_QJET] = (float)q1 / pt;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 int mmbo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -87,6 +87,10 @@ void mmbo_trans_sample(const MmbEpicDims* ed, const float* epacked, const MmbTra
                        float* x, float* onehot, int32_t* dims, const MmbJumpSchedule* sch, const MmbForwardRate* fr,
                        const float* z_diff, const float* u_near, const float* u_jump, const float* z_new, int B, int N);
 
+/* post-processing + jet observables (mmb_jet_observables); jet sums accumulated in double */
+void mmbo_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* sd, int B, int N,
+                          float* x_phys, int8_t* fc, float* jets);
+
 int mmbo_max_threads(void);
 
 #ifdef __cplusplus

@@ -249,3 +249,15 @@ def trans_initial_state(z_init, N, S):
     oh = np.zeros((B, N, S), np.float32)
     oh[:, 0, :] = z_init[:, N * 3: N * 3 + S]
     return x, oh, np.ones(B, np.int32)
+
+
+# ---- post-processing + jet observables ------------------------------------------------------------------
+def jet_observables(x, k, mask, stats=None):
+    B, N, _ = x.shape
+    x, k, mask = f32(x), u8(k).reshape(B, N), u8(mask).reshape(B, N)
+    mean = None if stats is None else f32(stats["mean"][:3])
+    sd = None if stats is None else f32(stats["std"][:3])
+    x_phys, fc, jets = np.empty((B, N, 3), np.float32), np.empty((B, N, 2), np.int8), np.empty((B, 11), np.float32)
+    lib().mmbo_jet_observables(_p(x), _p(k, _u8p), _p(mask, _u8p), _p(mean), _p(sd), B, N, _p(x_phys),
+                               fc.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), _p(jets))
+    return x_phys, fc, jets
