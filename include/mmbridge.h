@@ -394,6 +394,21 @@ enum { MMB_JET_PX = 0, MMB_JET_PY, MMB_JET_PZ, MMB_JET_E, MMB_JET_PT, MMB_JET_M,
 int mmb_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* std, int B, int N,
                         float* x_phys, int8_t* flavor_charge, float* jets, void* stream);
 
+/*
+ * Source-state construction on the device, so that a generation run needs no host data loader:
+ *   sample_noise("GaussNoise") (mp/data/particle_clouds/utils.py:222-251): x ~ N(0,1) * scale, flavor ~ Categorical(cat_probs[5]),
+ *   charge = +-1 (0 for photons / neutral hadrons), turned into the 8 tokens of physics_to_onehot + argmax
+ *   (utils.py:289-307; ParticleClouds.preprocess "tokens", particles.py:111-113);
+ *   sample_masks (utils.py:254-286): multiplicity ~ Categorical(histogram of the target multiplicities), prefix mask;
+ *   x and k are multiplied by the mask (particles.py:65-69).
+ * Draws come from Philox4x32-10 keyed by (seed, jet_offset + jet, particle) — streams 9 (normals) and 10 (flavor, charge),
+ * 11 (multiplicity) — so a sharded run produces the same jets as a single-GPU run.
+ *   cat_probs: HOST float[5];  mult_cdf: DEVICE float[N+1] cumulative multiplicity probabilities (m = first i with u < cdf[i]),
+ *   or NULL for full jets.  Outputs: x [B,N,3] f32, k [B,N] u8, mask [B,N] u8.
+ */
+int mmb_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
+                      uint64_t seed, uint64_t jet_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,7 @@ SIGNATURES = {
                                     _vp, _sz, _i, _vp]),
     "mmb_validation_histograms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp]),
     "mmb_jet_observables": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "mmb_sample_source": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _u64, _u64, _vp]),
     "mmb_trans_packed_floats": (_sz, [ctypes.POINTER(TransDims)]),
     "mmb_trans_create": (_i, [ctypes.POINTER(TransDims), _vp, _sz, _i, ctypes.POINTER(_vp)]),
     "mmb_trans_destroy": (None, [_vp]),

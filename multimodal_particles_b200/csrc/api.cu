@@ -253,6 +253,14 @@ int mmb_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, c
     return launch_jet_observables(x, k, mask, mean, std, B, N, x_phys, flavor_charge, jets, static_cast<cudaStream_t>(stream));
 }
 
+int mmb_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
+                      uint64_t seed, uint64_t jet_offset, void* stream) {
+    if (!x || !k || !mask || !cat_probs) return fail(MMB_EINVAL, "mmb_sample_source: null argument");
+    if (B < 0 || N < 0) return fail(MMB_EINVAL, "mmb_sample_source: negative size");
+    if (B == 0 || N == 0) return MMB_OK;
+    return launch_sample_source(x, k, mask, B, N, scale, cat_probs, mult_cdf, seed, jet_offset, static_cast<cudaStream_t>(stream));
+}
+
 // debug only (not part of include/mmbridge.h): phase timestamps of the tcgen05 generation kernel, see tools/tc_trace.py
 int mmb_debug_read_trace(long long* out, int n) { return tc_read_trace(out, n); }
 int mmb_debug_read_stack_trace(long long* out, int n) { return stack_read_trace(out, n); }

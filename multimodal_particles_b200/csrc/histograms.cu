@@ -2,6 +2,7 @@
 // only a few KB of int64 counts cross NVLink (all-reduce) instead of the particle clouds.
 // Observables that need no clustering (mp/data/particle_clouds/jets.py:90-107): per-particle
 // histograms of the continuous features, token frequencies, particle multiplicity per jet.
+#include "mmb_device.cuh"
 #include "mmb_internal.h"
 
 namespace mmb {
@@ -100,6 +101,61 @@ int launch_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask
     const float3 s = sd ? make_float3(sd[0], sd[1], sd[2]) : make_float3(1.0f, 1.0f, 1.0f);
     jet_observables_kernel<<<(B + 3) / 4, 128, 0, stream>>>(x, k, mask, m, s, B, N, x_phys, fc, jets);
     return cuda_ok(cudaGetLastError(), "jet_observables launch");
+}
+
+// ---- source state on the device (utils.py:222-286; particles.py:65-69,111-113) -------------------------------------
+// One warp per jet.  The integer side (multiplicity, flavor, charge -> token) is a pure function of the Philox words and
+// matches oracle/mmb_oracle.c bit for bit; the normals go through Box-Muller with the fast log / sincos.
+__global__ void __launch_bounds__(128) sample_source_kernel(float* __restrict__ x, uint8_t* __restrict__ k, uint8_t* __restrict__ mask,
+                                                            int B, int N, float scale, float c0, float c1, float c2, float c3,
+                                                            const float* __restrict__ mult_cdf, uint64_t seed, uint64_t jet_offset) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const uint64_t jet = jet_offset + (uint64_t)b;
+    int mult = N;
+    if (mult_cdf) {
+        const float u = u01(philox_block(seed, jet, 11, 0, 0).x);
+        int cnt = 0;   // number of cdf entries <= u  = first index with u < cdf[i]
+        for (int i = lane; i <= N; i += 32) cnt += (u < __ldg(mult_cdf + i)) ? 0 : 1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        mult = cnt < N ? cnt : N;
+    }
+    for (int n = lane; n < N; n += 32) {
+        const size_t p = (size_t)b * N + n;
+        const bool live = n < mult;
+        float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f;
+        int tok = 0;
+        if (live) {
+            const uint4 r = philox_block(seed, jet, 9, 0, n);
+            {
+                const float u1 = ((float)(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+                const float rad = sqrtf(-2.0f * __logf(u1));
+                float sn, cs;
+                __sincosf(6.283185307179586f * u2, &sn, &cs);
+                z0 = rad * cs; z1 = rad * sn;
+            }
+            {
+                const float u1 = ((float)(r.z >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(r.w >> 8) * (1.0f / 16777216.0f);
+                z2 = sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+            }
+            const uint4 q = philox_block(seed, jet, 10, 0, n);
+            const float uf = u01(q.x);
+            const int flavor = uf < c0 ? 0 : uf < c1 ? 1 : uf < c2 ? 2 : uf < c3 ? 3 : 4;
+            tok = flavor < 2 ? flavor : 2 * flavor - 2 + (int)(q.y >> 31);   // charged: token pair (-, +)
+        }
+        x[p * 3] = z0 * scale; x[p * 3 + 1] = z1 * scale; x[p * 3 + 2] = z2 * scale;
+        k[p] = (uint8_t)tok;
+        mask[p] = live ? 1 : 0;
+    }
+}
+
+int launch_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
+                         uint64_t seed, uint64_t jet_offset, cudaStream_t stream) {
+    float c[4], acc = 0.0f;
+    for (int i = 0; i < 4; ++i) { acc = acc + cat_probs[i]; c[i] = acc; }
+    sample_source_kernel<<<(B + 3) / 4, 128, 0, stream>>>(x, k, mask, B, N, scale, c[0], c[1], c[2], c[3], mult_cdf, seed, jet_offset);
+    return cuda_ok(cudaGetLastError(), "sample_source launch");
 }
 
 }  // namespace mmb

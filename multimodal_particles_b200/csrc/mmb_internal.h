@@ -76,6 +76,9 @@ int launch_validation_histograms(const float* x, const uint8_t* k, const uint8_t
 int launch_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* sd, int B, int N,
                            float* x_phys, int8_t* fc, float* jets, cudaStream_t stream);
 
+int launch_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
+                         uint64_t seed, uint64_t jet_offset, cudaStream_t stream);
+
 // epic_fp32.cu — CUDA-core path, bit-identical to the oracle
 int launch_epic_forward_fp32(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
                              const float* temb, int temb_stride, int B, int N,

@@ -894,6 +894,51 @@ void mmbo_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask,
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* sample_noise("GaussNoise") + sample_masks + tokens (mp/data/particle_clouds/utils.py:222-307; particles.py:65-69,111-113),
+ * driven by the Philox streams of mmb_sample_source.  Integer outputs are exact functions of the Philox words. */
+static void philox_words(uint64_t seed, uint64_t jet, int stream_id, int step, int idx, uint32_t out[4]) {
+    uint32_t c[4] = {(uint32_t)idx, (uint32_t)step, (uint32_t)jet, (uint32_t)(jet >> 32) * 4u + (uint32_t)stream_id};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    memcpy(out, c, sizeof(c));
+}
+void mmbo_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
+                        uint64_t seed, uint64_t jet_offset) {
+    float c[4], acc = 0.0f;
+    for (int i = 0; i < 4; ++i) { acc = acc + cat_probs[i]; c[i] = acc; }
+    for (int b = 0; b < B; ++b) {
+        const uint64_t jet = jet_offset + (uint64_t)b;
+        int mult = N;
+        uint32_t r[4], q[4];
+        if (mult_cdf) {
+            philox_words(seed, jet, 11, 0, 0, r);
+            const float u = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
+            mult = 0;
+            while (mult < N && !(u < mult_cdf[mult])) ++mult;
+        }
+        for (int n = 0; n < N; ++n) {
+            const size_t p = (size_t)b * N + n;
+            float z[3] = {0, 0, 0};
+            int tok = 0;
+            if (n < mult) {
+                philox_words(seed, jet, 9, 0, n, r);
+                const float u1 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(r[1] >> 8) * (1.0f / 16777216.0f);
+                const float rad = sqrtf(-2.0f * logf(u1));
+                z[0] = rad * cosf(6.283185307179586f * u2); z[1] = rad * sinf(6.283185307179586f * u2);
+                const float u3 = ((float)(r[2] >> 8) + 1.0f) * (1.0f / 16777216.0f), u4 = (float)(r[3] >> 8) * (1.0f / 16777216.0f);
+                z[2] = sqrtf(-2.0f * logf(u3)) * cosf(6.283185307179586f * u4);
+                philox_words(seed, jet, 10, 0, n, q);
+                const float uf = (float)(q[0] >> 8) * (1.0f / 16777216.0f);
+                const int flavor = uf < c[0] ? 0 : uf < c[1] ? 1 : uf < c[2] ? 2 : uf < c[3] ? 3 : 4;
+                tok = flavor < 2 ? flavor : 2 * flavor - 2 + (int)(q[1] >> 31);
+            }
+            for (int i = 0; i < 3; ++i) x[p * 3 + i] = z[i] * scale;
+            k[p] = (uint8_t)tok;
+            mask[p] = n < mult;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 int mmbo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -91,6 +91,10 @@ void mmbo_trans_sample(const MmbEpicDims* ed, const float* epacked, const MmbTra
 void mmbo_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* sd, int B, int N,
                           float* x_phys, int8_t* fc, float* jets);
 
+/* source state from the Philox streams of mmb_sample_source (tokens / masks exact, normals through libm) */
+void mmbo_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
+                        uint64_t seed, uint64_t jet_offset);
+
 int mmbo_max_threads(void);
 
 #ifdef __cplusplus

@@ -261,3 +261,12 @@ def jet_observables(x, k, mask, stats=None):
     lib().mmbo_jet_observables(_p(x), _p(k, _u8p), _p(mask, _u8p), _p(mean), _p(sd), B, N, _p(x_phys),
                                fc.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), _p(jets))
     return x_phys, fc, jets
+
+
+# ---- source state ---------------------------------------------------------------------------------------
+def sample_source(B, N, scale, cat_probs, mult_cdf, seed, jet_offset):
+    x, k, mask = np.empty((B, N, 3), np.float32), np.empty((B, N), np.uint8), np.empty((B, N), np.uint8)
+    cdf = None if mult_cdf is None else f32(mult_cdf)
+    lib().mmbo_sample_source(_p(x), _p(k, _u8p), _p(mask, _u8p), B, N, ctypes.c_float(scale), _p(f32(cat_probs)), _p(cdf),
+                             ctypes.c_uint64(seed), ctypes.c_uint64(jet_offset))
+    return x, k, mask
