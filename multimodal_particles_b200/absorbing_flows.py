@@ -18,7 +18,7 @@ from torch import nn
 from . import _native
 from .bridges import AbsorbingBridge, LinearUniformBridge, TelegraphBridge
 from .epic import EPiCWrapper, as_u8
-from .multimodal_bridge_matching import MultiHeadLoss, _ModuleBase
+from .multimodal_bridge_matching import MultiHeadLoss, _ModuleBase, to_host_async
 from .states import AbsorbingBridgeState, OutputHeads
 from .steptable import build_step_table
 
@@ -200,9 +200,14 @@ class AbsorbingFlow(_ModuleBase):
         _native.generate_absorbing(gen.native_trunk(device), gen.native_head(device), x, k, mask, table,
                                    gen.time_bias(table.t), prep(uniforms_jump), prep(uniforms_absorb),
                                    seed=self.seed, jet_offset=jet_offset, precision=precision or self.precision)
-        out = AbsorbingBridgeState(time=torch.full((B, 1), float(table.t[-1]), device=device), continuous=x,
-                                   discrete=k.to(k64.dtype).unsqueeze(-1), mask_t=mask.to(torch.int64).unsqueeze(-1))
-        return out if return_device else out.detach().cpu()
+        if return_device:
+            return AbsorbingBridgeState(time=torch.full((B, 1), float(table.t[-1]), device=device), continuous=x,
+                                        discrete=k.to(k64.dtype).unsqueeze(-1), mask_t=mask.to(torch.int64).unsqueeze(-1))
+        # compact tensors cross PCIe into page-locked memory; tokens and masks are widened to int64 on the host
+        x_host, k_host, m_host = to_host_async(x), to_host_async(k), to_host_async(mask)
+        torch.cuda.current_stream(device).synchronize()
+        return AbsorbingBridgeState(time=torch.full((B, 1), float(table.t[-1])), continuous=x_host,
+                                    discrete=k_host.to(k64.dtype).unsqueeze(-1), mask_t=m_host.to(torch.int64).unsqueeze(-1))
 
     def _training_not_in_scope(self, *args, **kwargs):
         raise NotImplementedError("training is outside the B200 generation hot path (SURVEY.md §8f N2)")

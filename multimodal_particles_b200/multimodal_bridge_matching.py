@@ -71,6 +71,13 @@ class MultiModalEPiC(nn.Module):
         return v, logits, mask
 
 
+def to_host_async(t: torch.Tensor) -> torch.Tensor:
+    """Device tensor -> pinned host tensor, asynchronous on the current stream (the caller synchronises once)."""
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    return out
+
+
 class MultiModalBridgeMatching(_ModuleBase):
     """Model for hybrid data with varying size (mbm.py:115-269), generation side.
 
@@ -140,8 +147,11 @@ class MultiModalBridgeMatching(_ModuleBase):
                                discrete=k.to(k64.dtype).unsqueeze(-1), absorbing=state.absorbing.to(device))
         # host result in the reference's layout.  Only what changed crosses PCIe: fp32 features and uint8 tokens
         # (widened to int64 on the host); the mask is the caller's own (it never changes in this bridge).
-        return HybridState(time=torch.full((B, 1), t_last), continuous=x.cpu(),
-                           discrete=k.cpu().to(k64.dtype).unsqueeze(-1), absorbing=state.absorbing.detach().cpu())
+        # Copies land in page-locked memory (torch's caching host allocator recycles the blocks), issued back to back.
+        x_host, k_host = to_host_async(x), to_host_async(k)
+        torch.cuda.current_stream(device).synchronize()
+        return HybridState(time=torch.full((B, 1), t_last), continuous=x_host,
+                           discrete=k_host.to(k64.dtype).unsqueeze(-1), absorbing=state.absorbing.detach().cpu())
 
     def predict_step(self, batch, batch_idx) -> HybridState:
         initial_state = HybridState(None, batch.source_continuous, batch.source_discrete, batch.source_mask)
