@@ -143,10 +143,8 @@ struct HeadParams {
     int tbias_stride;
     int B, N;
     float* logit_out;        // [B,N] per-particle output
-    const float* jet_wT;     // [128][n_jet] per-jet head applied to the mean over the N slots (nullable)
-    const float* jet_b;      // [n_jet]
-    int n_jet;
-    float* jet_out;          // [B][n_jet]
+    int n_jet;               // > 0: also write the mean of X over the N slots
+    float* jet_out;          // [B][128] slot means (the per-jet head consumes them)
     long long* trace;        // debug: clock64() stamps of the first jet of CTA 0 (tools/stack_trace.py); null in production
 };
 
@@ -218,7 +216,6 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     __shared__ __align__(16) float s_bias2[kMaxBlocks][kC]; // conv1 bias + this jet's time term, per block
     __shared__ float s_rowx[4][128], s_sum[4][128];         // softmax row max and row sum per (channel quarter, row)
     float (*s_dot)[128] = s_rowx;                           // per-particle output partials (after the last softmax)
-    __shared__ float s_mean[128];                           // mean of the residual stream over the N slots (per-jet head)
     const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7, warp = tid >> 5, lane = tid & 31;
     const int nblk = p.n_blocks, n_seq = 1 + 6 * nblk;
     uint8_t *sA = smem + kOffA, *sQ = smem + kOffQ, *sK = smem + kOffK, *sV = smem + kOffV, *sOnes = smem + kOffOnes;
@@ -555,23 +552,10 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             }
             __syncthreads();
             if (cq == 0 && valid) p.logit_out[pidx] = sTab[HeadTable::rate_c(nblk)] + (s_dot[0][r] + s_dot[1][r]) + (s_dot[2][r] + s_dot[3][r]);
-            if (p.n_jet > 0) {
-                if (tid < 128) {
-                    const int w0 = (tid >> 5) * 4, ci = tid & 31;
-                    s_mean[tid] = ((s_part[w0][ci] + s_part[w0 + 1][ci]) + (s_part[w0 + 2][ci] + s_part[w0 + 3][ci])) * (1.0f / (float)p.N);
-                }
-                __syncthreads();
-                if (tid < p.n_jet) {
-                    float b0 = __ldg(p.jet_b + tid), b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
-#pragma unroll 4
-                    for (int c = 0; c < kC; c += 4) {
-                        b0 = fmaf(__ldg(p.jet_wT + (size_t)c * p.n_jet + tid), s_mean[c], b0);
-                        b1 = fmaf(__ldg(p.jet_wT + (size_t)(c + 1) * p.n_jet + tid), s_mean[c + 1], b1);
-                        b2 = fmaf(__ldg(p.jet_wT + (size_t)(c + 2) * p.n_jet + tid), s_mean[c + 2], b2);
-                        b3 = fmaf(__ldg(p.jet_wT + (size_t)(c + 3) * p.n_jet + tid), s_mean[c + 3], b3);
-                    }
-                    p.jet_out[(size_t)jet * p.n_jet + tid] = (b0 + b1) + (b2 + b3);
-                }
+            if (p.n_jet > 0 && tid < 128) {   // the folded per-jet Linear runs afterwards, batched over jets (jet_head_kernel)
+                const int w0 = (tid >> 5) * 4, ci = tid & 31;
+                p.jet_out[(size_t)jet * kC + tid] =
+                    ((s_part[w0][ci] + s_part[w0 + 1][ci]) + (s_part[w0 + 2][ci] + s_part[w0 + 3][ci])) * (1.0f / (float)p.N);
             }
         }
         tc_fence_before();
@@ -672,6 +656,43 @@ int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* bloc
     return rc;
 }
 
+// Per-jet head: out[b][o] = bias[o] + sum_c W^T[c][o] * mean[b][c], batched so that every weight row is read once per 16 jets.
+__global__ void __launch_bounds__(128) jet_head_kernel(const float* __restrict__ means, const float* __restrict__ wT, const float* __restrict__ bias,
+                                                       int n_out, int B, float* __restrict__ out) {
+    constexpr int JB = 16;
+    __shared__ __align__(16) float s_m[kC][JB];   // [channel][jet]: one LDS.128 serves four jets
+    const int o = threadIdx.x, j0 = blockIdx.x * JB;
+    for (int i = threadIdx.x; i < JB * kC; i += 128) {
+        const int j = i / kC, c = i % kC;
+        s_m[c][j] = j0 + j < B ? __ldg(means + (size_t)(j0 + j) * kC + c) : 0.0f;
+    }
+    __syncthreads();
+    if (o >= n_out) return;
+    float acc[JB];
+    const float b = __ldg(bias + o);
+#pragma unroll
+    for (int j = 0; j < JB; ++j) acc[j] = b;
+#pragma unroll 8
+    for (int c = 0; c < kC; ++c) {
+        const float w = __ldg(wT + (size_t)c * n_out + o);
+#pragma unroll
+        for (int j = 0; j < JB; j += 4) {
+            const float4 m4 = *reinterpret_cast<const float4*>(&s_m[c][j]);
+            acc[j] = fmaf(w, m4.x, acc[j]); acc[j + 1] = fmaf(w, m4.y, acc[j + 1]);
+            acc[j + 2] = fmaf(w, m4.z, acc[j + 2]); acc[j + 3] = fmaf(w, m4.w, acc[j + 3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < JB; ++j)
+        if (j0 + j < B) out[(size_t)(j0 + j) * n_out + o] = acc[j];
+}
+
+int launch_jet_head(const TfStack* st, const float* means, int B, float* out, cudaStream_t stream) {
+    if (B == 0 || st->n_jet == 0) return MMB_OK;
+    jet_head_kernel<<<(B + 15) / 16, 128, 0, stream>>>(means, st->jet_wT, st->jet_b, st->n_jet, B, out);
+    return cuda_ok(cudaGetLastError(), "jet head launch");
+}
+
 // MMB_STACK_TRACE=1: per-phase clock64() stamps of the first jet of CTA 0 (tools/stack_trace.py reads them)
 static long long* g_stack_trace = nullptr;
 static long long* stack_trace_buffer() {
@@ -694,7 +715,7 @@ int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B,
     p.image = static_cast<const uint8_t*>(st->image); p.table = st->table; p.n_blocks = st->n_blocks; p.H = io.H;
     p.mode = io.mode; p.S = io.S; p.hidden = io.hidden; p.mask = io.mask; p.onehot = io.onehot; p.x = io.x; p.nearest = io.nearest;
     p.tbias = io.tbias; p.tbias_stride = io.tbias_stride; p.B = B; p.N = N; p.logit_out = io.dot_out;
-    p.jet_wT = st->jet_wT; p.jet_b = st->jet_b; p.n_jet = io.jet_out ? st->n_jet : 0; p.jet_out = io.jet_out;
+    p.n_jet = io.jet_out ? st->n_jet : 0; p.jet_out = io.jet_out;
     p.trace = stack_trace_buffer();
     const size_t bytes = kOffTab + (size_t)HeadTable::floats(st->n_blocks) * 4 + 1024;
     cudaFuncAttributes attr;

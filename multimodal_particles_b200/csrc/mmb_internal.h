@@ -53,13 +53,15 @@ struct TfStackIO {
     const float* tbias;       // [B or 1][n_blocks][128]
     int tbias_stride;
     float* dot_out;           // [B,N]
-    float* jet_out;           // [B][n_jet] or null
+    float* jet_out;           // [B][128] means of X over the slots (input of launch_jet_head) or null
 };
 int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* blocks, int n_blocks, const float* dot_w, float dot_c,
                    const float* jet_w, const float* jet_b, int n_jet);
 void tf_stack_free(TfStack* st);
 int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B, int N, cudaStream_t stream);
 int stack_read_trace(long long* out, int n);
+// out [B][n_jet] = folded per-jet Linear of the stack applied to the slot means written by launch_tf_stack
+int launch_jet_head(const TfStack* st, const float* means, int B, float* out, cudaStream_t stream);
 
 struct AbsorbHead;
 int absorb_head_create(int H, int C, int n_heads, int n_blocks, const float* W, size_t n_floats, int device, AbsorbHead** out);

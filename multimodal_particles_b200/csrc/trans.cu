@@ -57,15 +57,23 @@ __global__ void __launch_bounds__(256) trans_colmax_kernel(const float* __restri
         pmax[(size_t)blockIdx.y * NS + c] = mx;
     }
 }
-__global__ void __launch_bounds__(256) trans_colsum_kernel(const float* __restrict__ onehot, int B, int NS, const float* __restrict__ pmax,
-                                                           int n_chunks, float* __restrict__ psum) {
+__global__ void __launch_bounds__(256) trans_colsum_kernel(const float* __restrict__ onehot, int B, int NS, const float* __restrict__ M,
+                                                           float* __restrict__ psum) {
     __shared__ float s_red[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane, b0 = blockIdx.y * kChunk, b1 = min(B, b0 + kChunk);
-    float mx = -INFINITY, part = 0.0f;
+    float mx, part = 0.0f;
     if (c < NS) {
-        for (int k = 0; k < n_chunks; ++k) mx = fmaxf(mx, __ldg(pmax + (size_t)k * NS + c));
-        for (int b = b0 + w; b < b1; b += 8) part = __fadd_rn(part, expf_exact_dn(__fadd_rn(__ldg(onehot + (size_t)b * NS + c), -mx)));
+        mx = __ldg(M + c);
+        float e[kChunk / 8];   // the loads and exponentials are independent; only the adds are ordered
+#pragma unroll
+        for (int i = 0; i < kChunk / 8; ++i) {
+            const int b = b0 + w + 8 * i;
+            e[i] = b < b1 ? expf_exact_dn(__fadd_rn(__ldg(onehot + (size_t)b * NS + c), -mx)) : -1.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < kChunk / 8; ++i)
+            if (e[i] >= 0.0f) part = __fadd_rn(part, e[i]);
     }
     s_red[w][lane] = part;
     __syncthreads();
@@ -74,17 +82,21 @@ __global__ void __launch_bounds__(256) trans_colsum_kernel(const float* __restri
             __fadd_rn(__fadd_rn(__fadd_rn(s_red[0][lane], s_red[1][lane]), __fadd_rn(s_red[2][lane], s_red[3][lane])),
                       __fadd_rn(__fadd_rn(s_red[4][lane], s_red[5][lane]), __fadd_rn(s_red[6][lane], s_red[7][lane])));
 }
-__global__ void trans_colcombine_kernel(const float* __restrict__ pmax, const float* __restrict__ psum, int n_chunks, int NS,
-                                        float* __restrict__ M, float* __restrict__ Z) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per column: the chunk partials are fetched in parallel, then added in ascending chunk order (the oracle's order)
+__global__ void __launch_bounds__(128) trans_colcombine_kernel(const float* __restrict__ part, int n_chunks, int NS, int is_max,
+                                                               float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, c = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (c >= NS) return;
-    float mx = -INFINITY, z = 0.0f;
-    for (int k = 0; k < n_chunks; ++k) {
-        mx = fmaxf(mx, __ldg(pmax + (size_t)k * NS + c));
-        z = __fadd_rn(z, __ldg(psum + (size_t)k * NS + c));
+    float acc = is_max ? -INFINITY : 0.0f;
+    for (int k0 = 0; k0 < n_chunks; k0 += 32) {
+        const float v = k0 + lane < n_chunks ? __ldg(part + (size_t)(k0 + lane) * NS + c) : (is_max ? -INFINITY : 0.0f);
+        const int cnt = min(32, n_chunks - k0);
+        for (int i = 0; i < cnt; ++i) {
+            const float vi = __shfl_sync(0xffffffffu, v, i);
+            acc = is_max ? fmaxf(acc, vi) : __fadd_rn(acc, vi);
+        }
     }
-    M[c] = mx;
-    Z[c] = z;
+    if (lane == 0) out[c] = acc;
 }
 
 __global__ void trans_tokens_kernel(const float* __restrict__ onehot, const float* __restrict__ M, const float* __restrict__ Z,
@@ -105,21 +117,23 @@ __global__ void trans_tokens_kernel(const float* __restrict__ onehot, const floa
 }
 
 // ---- time terms (utils.py:183-198; gsdm.py:8-26,58; transdimensional_model.py:288-290) ---------------------------------
-// 128 threads = output channels; a block serves kTimeJets jets so every weight row is read once per block.
+// A block serves kTimeJets jets: thread (o, half) owns output channel o of 16 of them, so every weight row is read once per
+// block and the activations are read from shared memory four jets at a time.
 constexpr int kTimeJets = 32;
-__global__ void __launch_bounds__(kC) trans_time_kernel(const float* __restrict__ wT, int nblk, const float* __restrict__ ts, int B, int T,
-                                                        float* __restrict__ temb_epic, float* __restrict__ tb1, float* __restrict__ tb2) {
-    __shared__ float s_in[kTimeJets][kC];
-    const int o = threadIdx.x, j0 = blockIdx.x * kTimeJets;
+__global__ void __launch_bounds__(2 * kC) trans_time_kernel(const float* __restrict__ wT, int nblk, const float* __restrict__ ts, int B, int T,
+                                                            float* __restrict__ temb_epic, float* __restrict__ tb1, float* __restrict__ tb2) {
+    __shared__ __align__(16) float s_in[kC][kTimeJets];   // [channel][jet]
+    constexpr int JT = kTimeJets / 2;
+    const int o = threadIdx.x & (kC - 1), jh = threadIdx.x >> 7, j0 = blockIdx.x * kTimeJets;
     const int half = kC / 2;
-    for (int j = 0; j < kTimeJets; ++j) {
-        const int b = j0 + j;
+    for (int jj = 0; jj < JT; ++jj) {
+        const int j = jh * JT + jj, b = j0 + j;
         float val = 0.0f;
         if (b < B) {
             const float t = __ldg(ts + b);
             const float fe = (float)(9.210340371976184 / (double)(half - 1));   // ln(10000) / (half - 1)
-            const int jj = o < half ? o : o - half;
-            const float a = (t * 1000.0f) * expf((float)jj * -fe);
+            const int q = o < half ? o : o - half;
+            const float a = (t * 1000.0f) * expf((float)q * -fe);
             val = o < half ? sinf(a) : cosf(a);
             if (o < T) {   // EPiC embedding: [cos(t f), sin(t f)], f_i = exp(-ln(1e4) i / (T/2))
                 const int h2 = T / 2, i2 = o < h2 ? o : o - h2;
@@ -127,41 +141,38 @@ __global__ void __launch_bounds__(kC) trans_time_kernel(const float* __restrict_
                 temb_epic[(size_t)b * T + o] = (T % 2 && o == T - 1) ? 0.0f : (o < h2 ? cosf(t * f) : sinf(t * f));
             }
         }
-        s_in[j][o] = val;
+        s_in[o][j] = val;
     }
     __syncthreads();
     const size_t mat = (size_t)kC * kC + kC;
-    float acc[kTimeJets];
-    {   // temb = temb_net(emb); act = swish(temb)
-        const float* W = wT;
+    float acc[JT];
+    auto gemv = [&](const float* W) {
         const float bias = __ldg(W + (size_t)kC * kC + o);
 #pragma unroll
-        for (int j = 0; j < kTimeJets; ++j) acc[j] = bias;
+        for (int j = 0; j < JT; ++j) acc[j] = bias;
+#pragma unroll 4
         for (int c = 0; c < kC; ++c) {
             const float w = __ldg(W + (size_t)c * kC + o);
 #pragma unroll
-            for (int j = 0; j < kTimeJets; ++j) acc[j] = fmaf(w, s_in[j][c], acc[j]);
+            for (int j = 0; j < JT; j += 4) {
+                const float4 m4 = *reinterpret_cast<const float4*>(&s_in[c][jh * JT + j]);
+                acc[j] = fmaf(w, m4.x, acc[j]); acc[j + 1] = fmaf(w, m4.y, acc[j + 1]);
+                acc[j + 2] = fmaf(w, m4.z, acc[j + 2]); acc[j + 3] = fmaf(w, m4.w, acc[j + 3]);
+            }
         }
-    }
+    };
+    gemv(wT);   // temb = temb_net(emb); act = swish(temb)
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kTimeJets; ++j) s_in[j][o] = acc[j] / (1.0f + expf(-acc[j]));
+    for (int j = 0; j < JT; ++j) s_in[o][jh * JT + j] = acc[j] / (1.0f + expf(-acc[j]));
     __syncthreads();
     for (int m = 0; m < 2 * nblk; ++m) {
-        const float* W = wT + (size_t)(1 + m) * mat;
-        const float bias = __ldg(W + (size_t)kC * kC + o);
-#pragma unroll
-        for (int j = 0; j < kTimeJets; ++j) acc[j] = bias;
-        for (int c = 0; c < kC; ++c) {
-            const float w = __ldg(W + (size_t)c * kC + o);
-#pragma unroll
-            for (int j = 0; j < kTimeJets; ++j) acc[j] = fmaf(w, s_in[j][c], acc[j]);
-        }
+        gemv(wT + (size_t)(1 + m) * mat);
         float* out = m < nblk ? tb1 : tb2;
         const int blk = m < nblk ? m : m - nblk;
 #pragma unroll
-        for (int j = 0; j < kTimeJets; ++j)
-            if (j0 + j < B) out[((size_t)(j0 + j) * nblk + blk) * kC + o] = acc[j];
+        for (int j = 0; j < JT; ++j)
+            if (j0 + jh * JT + j < B) out[((size_t)(j0 + jh * JT + j) * nblk + blk) * kC + o] = acc[j];
     }
 }
 
@@ -475,7 +486,7 @@ inline size_t align64(size_t n) { return (n + 63) & ~(size_t)63; }
 
 // workspace carve-up shared by the forward and the sampler (in floats, every region 256-byte aligned)
 struct TransWs {
-    size_t k, mask, M, Z, pmax, psum, temb, tb1, tb2, v, logits, hidden, near_logits, vec_w, x0_logits, post_auto, nearest, new_mean, new_std, rate,
+    size_t k, mask, M, Z, pmax, psum, means, temb, tb1, tb2, v, logits, hidden, near_logits, vec_w, x0_logits, post_auto, nearest, new_mean, new_std, rate,
         u_near, ts, total;
     TransWs(const MmbEpicDims& e, const MmbTransDims& d, int B, int N, int n_time) {
         const size_t P = (size_t)B * N, F = 3 + d.vocab_size;
@@ -485,6 +496,7 @@ struct TransWs {
         M = take((size_t)N * d.vocab_size); Z = take((size_t)N * d.vocab_size);
         const size_t chunks = ((size_t)B + kChunk - 1) / kChunk;
         pmax = take(chunks * N * d.vocab_size); psum = take(chunks * N * d.vocab_size);
+        means = take((size_t)B * kC);
         temb = take((size_t)n_time * e.dim_time_emb);
         tb1 = take((size_t)n_time * d.n_blocks * kC); tb2 = take((size_t)n_time * d.n_blocks * kC);
         v = take(P * 3); logits = take(P * d.vocab_size); hidden = take(P * e.dim_hidden_local);
@@ -612,8 +624,9 @@ static int trans_eval(const EpicModel* m, const TransHeads* h, const float* x, c
         const int NS = N * S, chunks = (B + kChunk - 1) / kChunk;
         const dim3 grid((NS + 31) / 32, chunks);
         trans_colmax_kernel<<<grid, 256, 0, s>>>(onehot, B, NS, ws + L.pmax);
-        trans_colsum_kernel<<<grid, 256, 0, s>>>(onehot, B, NS, ws + L.pmax, chunks, ws + L.psum);
-        trans_colcombine_kernel<<<(NS + 127) / 128, 128, 0, s>>>(ws + L.pmax, ws + L.psum, chunks, NS, ws + L.M, ws + L.Z);
+        trans_colcombine_kernel<<<(NS + 3) / 4, 128, 0, s>>>(ws + L.pmax, chunks, NS, 1, ws + L.M);
+        trans_colsum_kernel<<<grid, 256, 0, s>>>(onehot, B, NS, ws + L.M, ws + L.psum);
+        trans_colcombine_kernel<<<(NS + 3) / 4, 128, 0, s>>>(ws + L.psum, chunks, NS, 0, ws + L.Z);
     }
     trans_tokens_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(onehot, ws + L.M, ws + L.Z, dims, B, N, S, k, mask);
     if (int rc = cuda_ok(cudaGetLastError(), "trans tokens launch")) return rc;
@@ -622,12 +635,14 @@ static int trans_eval(const EpicModel* m, const TransHeads* h, const float* x, c
     if (rc) return rc;
     TfStackIO io{};
     io.mode = 1; io.H = H; io.S = S; io.hidden = ws + L.hidden; io.mask = mask; io.onehot = onehot;
-    io.tbias = tb1; io.tbias_stride = time_stride ? nb * kC : 0; io.dot_out = nl; io.jet_out = x0l;
+    io.tbias = tb1; io.tbias_stride = time_stride ? nb * kC : 0; io.dot_out = nl; io.jet_out = ws + L.means;
     if ((rc = launch_tf_stack(&h->s1, h->sm_count, io, B, N, s))) return rc;
+    if ((rc = launch_jet_head(&h->s1, ws + L.means, B, x0l, s))) return rc;
     trans_rate_kernel<<<(B + 3) / 4, 128, 0, s>>>(x0l, nl, dims, ts, ts_stride, nearest_in, u_nearest, fr, h->logfact, B, N, R, ws + L.rate, nearest);
     if ((rc = cuda_ok(cudaGetLastError(), "trans rate launch"))) return rc;
-    io.mode = 2; io.x = x; io.nearest = nearest; io.tbias = tb2; io.dot_out = ws + L.vec_w; io.jet_out = ws + L.post_auto;
+    io.mode = 2; io.x = x; io.nearest = nearest; io.tbias = tb2; io.dot_out = ws + L.vec_w; io.jet_out = ws + L.means;
     if ((rc = launch_tf_stack(&h->s2, h->sm_count, io, B, N, s))) return rc;
+    if ((rc = launch_jet_head(&h->s2, ws + L.means, B, ws + L.post_auto, s))) return rc;
     trans_auto_kernel<<<(B + 3) / 4, 128, 0, s>>>(x, mask, nearest, ws + L.vec_w, ws + L.post_auto, dims, B, N, S, ws + L.new_mean,
                                                  ws + L.new_std, auto_mean, auto_std);
     return cuda_ok(cudaGetLastError(), "trans auto launch");
@@ -693,7 +708,7 @@ int mmb_trans_forward(const MmbEpicModel* trunk, const MmbTransHeads* heads, con
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     float* ws = static_cast<float*>(workspace);
     const int S = h->d.vocab_size, F = 3 + S, T = m->dims.dim_time_emb;
-    trans_time_kernel<<<(B + kTimeJets - 1) / kTimeJets, kC, 0, s>>>(h->time_wT, h->d.n_blocks, ts, B, T, ws + L.temb, ws + L.tb1, ws + L.tb2);
+    trans_time_kernel<<<(B + kTimeJets - 1) / kTimeJets, 2 * kC, 0, s>>>(h->time_wT, h->d.n_blocks, ts, B, T, ws + L.temb, ws + L.tb1, ws + L.tb2);
     if (int rc = cuda_ok(cudaGetLastError(), "trans time launch")) return rc;
     if (auto_mean) {
         if (int rc = cuda_ok(cudaMemsetAsync(auto_mean, 0, (size_t)B * N * F * sizeof(float), s), "auto_mean clear")) return rc;
@@ -739,7 +754,7 @@ int mmb_trans_sample(const MmbEpicModel* trunk, const MmbTransHeads* heads, floa
     // all jets share ts: the time terms of every step are computed once, as a batch of n "jets"
     float* ts_dev = ws + L.ts;
     if (int rc = cuda_ok(cudaMemcpyAsync(ts_dev, sch->ts, (size_t)n * 4, cudaMemcpyHostToDevice, s), "schedule upload")) return rc;
-    trans_time_kernel<<<(n + kTimeJets - 1) / kTimeJets, kC, 0, s>>>(h->time_wT, nb, ts_dev, n, T, ws + L.temb, ws + L.tb1, ws + L.tb2);
+    trans_time_kernel<<<(n + kTimeJets - 1) / kTimeJets, 2 * kC, 0, s>>>(h->time_wT, nb, ts_dev, n, T, ws + L.temb, ws + L.tb1, ws + L.tb2);
     if (int rc = cuda_ok(cudaGetLastError(), "trans time launch")) return rc;
     for (int i = 0; i < n; ++i) {
         const float* un = u_near ? u_near + (size_t)i * B : ws + L.u_near;
