@@ -312,8 +312,8 @@ __device__ __forceinline__ void philox_normals12(uint64_t seed, uint64_t jet, in
         box_muller(r.z, r.w, z[4 * q + 2], z[4 * q + 3]);
     }
 }
-__device__ __forceinline__ float nan_to_num(float a) {
-    return a != a ? 0.0f : fminf(fmaxf(a, -3.4028234664e38f), 3.4028234664e38f);
+__device__ __forceinline__ float nan_to_num(float a) {   // torch.nan_to_num: NaN -> 0, +-inf -> +-FLT_MAX; finite values take one compare
+    return fabsf(a) <= 3.4028234664e38f ? a : (a != a ? 0.0f : copysignf(3.4028234664e38f, a));
 }
 __device__ __forceinline__ float softplus(float a) { return a > 20.0f ? a : log1pf(expf(a)); }
 

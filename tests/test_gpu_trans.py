@@ -223,6 +223,52 @@ def test_jump_sampler_end_to_end_properties():
     assert com.abs().max() <= 1e-3 * max(1.0, float(x.abs().max()))
 
 
+def test_c3_full_size_properties():
+    """BASELINE config 3 shape (B = 8192, N = 128) — size-independent properties of one evaluation and of a sampler run:
+    the network treats a jet the same wherever it sits in the batch (tokens use per-column batch statistics, which a
+    duplicated jet shares), nothing is written outside the live slot of a birth, a full jet cannot give birth, and the
+    sampler keeps its invariants (dead slots zero, centred continuous features, multiplicities in range and growing)."""
+    cfg = TransdimensionalEpicConfig()
+    torch.manual_seed(4)
+    model = TransdimensionalJumpDiffusion(cfg).to(DEV)
+    B, N, S = 8192, cfg.data.max_num_particles, cfg.data.vocab_size_features
+    g = torch.Generator().manual_seed(5)
+    dims = torch.randint(1, N + 1, (B,), generator=g)
+    dims[:64] = N
+    m = (torch.arange(N)[None] < dims[:, None]).float().unsqueeze(-1)
+    x, oh = torch.randn(B, N, 3, generator=g) * m, torch.randn(B, N, S, generator=g) * m
+    ts = torch.rand(B, generator=g) * 0.99 + 0.005
+    near = (torch.rand(B, generator=g) * dims).long()
+    src = torch.arange(100, 164)
+    dst = torch.arange(5000, 5064)     # copies of 64 jets far away in the batch (a different CTA, a different position in its queue)
+    for t in (x, oh, dims, ts, near):
+        t[dst] = t[src]
+    out = model.net(model.make_batch(x.to(DEV), oh.to(DEV), dims.to(DEV)), ts.to(DEV), forward_rate=model.forward_rate,
+                    nearest_atom=near.to(DEV))
+    D, rate, (am, asd), x0l, nal = [o.cpu() if torch.is_tensor(o) else tuple(t.cpu() for t in o) for o in out]
+    for t in (D, rate, am, asd, x0l, nal):
+        assert torch.isfinite(t).all() and torch.equal(t[dst], t[src])
+    assert (rate[:64] == 0).all() and (am[:64] == 0).all()                    # full jets: no slot to fill
+    F = 3 + S
+    slot = torch.zeros(B, N * F, dtype=torch.bool)
+    rows = torch.arange(B)[dims < N]
+    for c in range(3):
+        slot[rows, dims[rows] * 3 + c] = True
+    for s_ in range(S):
+        slot[rows, N * 3 + dims[rows] * S + s_] = True
+    assert (am[~slot] == 0).all() and (asd[~slot] == 0).all() and (rate >= 0).all()
+    cfg.sampler_kwargs.dt = 0.1
+    sk = {k: v for k, v in vars(cfg.sampler_kwargs).items() if k not in ("class_name", "do_jump_back", "jump_back_start_time")}
+    sampler = JumpSampler(structure=model.structure, **sk)
+    in_st = model.make_batch(torch.zeros(B, N, 3, device=DEV), torch.zeros(B, N, S, device=DEV), torch.full((B,), N, device=DEV))
+    st = sampler.sample(model.net, in_st, model.jump_diffusion_loss, jet_offset=0)
+    d, (xs, ohs) = st.get_dims(), st.tuple_batch
+    assert d.min() >= 1 and d.max() <= N and d.float().mean() > 1.2 and torch.isfinite(xs).all() and torch.isfinite(ohs).all()
+    dead = torch.arange(N, device=DEV)[None] >= d[:, None]
+    assert (xs[dead] == 0).all() and (ohs[dead] == 0).all()
+    assert (xs.sum(1) / d[:, None]).abs().max() <= 1e-3 * max(1.0, float(xs.abs().max()))
+
+
 def test_trans_errors_are_loud(fixture):
     z, cfg, model, packed = fixture
     m = model.net.model
