@@ -122,8 +122,8 @@ __device__ __forceinline__ void store_row32(uint8_t* tile, int row, int chunk4, 
 
 // fp32 side table (floats), per block then the per-particle output vector
 struct HeadTable {
-    // per block: n1g n1b b1 n2g n2b n3g n3b bq bk bv  (10 x 128)
-    static constexpr int kPerBlock = 10 * kC;
+    // per block: n1g n1b b1 n2g n2b n3g n3b  (7 x 128); the q / k / v biases live in the operand image or are folded away
+    static constexpr int kPerBlock = 7 * kC;
     __host__ __device__ static int rate_w(int nblk) { return nblk * kPerBlock; }       // [128] per-particle output vector
     __host__ __device__ static int rate_c(int nblk) { return nblk * kPerBlock + kC; }  // its constant
     __host__ __device__ static int floats(int nblk) { return nblk * kPerBlock + kC + 4; }
@@ -152,7 +152,9 @@ constexpr int kSmemW = 2 * kSlot;                         // weight ring
 constexpr int kOffA = kSmemW, kOffQ = kOffA + 32768, kOffK = kOffQ + 32768, kOffV = kOffK + 32768;
 constexpr int kOffOnes = kOffV + 32768, kOffTab = kOffOnes + 4096;
 
-constexpr int kThreads = 512;
+constexpr int kCW = 32;                   // accumulator columns per thread (16 = 32 warps: measured slower, 393 vs 435 TFLOP/s)
+constexpr int kNQ = kC / kCW;             // channel slices per row
+constexpr int kThreads = 128 * kNQ;       // 16 warps at kCW = 32
 
 // packed fp32 pair arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): two IEEE fp32 operations per issue slot
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
@@ -205,21 +207,47 @@ __device__ __forceinline__ int warp_halving_index(int lane) {
     return idx;
 }
 
-// One CTA of 16 warps owns one jet at a time.  Thread (r, cq): particle r = TMEM lane r (warp & 3 selects the lane quarter the
-// warp may touch), channel quarter cq = warp >> 2 -> 32 consecutive accumulator columns = one tcgen05.ld per pass.
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+// thread `row` stores columns [col, col + CW) of its row of a K-major bf16 tile (16-byte k-chunks 128 B apart)
+template <int CW>
+__device__ __forceinline__ void store_row(uint8_t* tile, int row, int col, const float (&v)[CW]) {
+    uint8_t* p = tile + (row >> 3) * 2048 + (row & 7) * 16 + (col >> 3) * 128;
+#pragma unroll
+    for (int c = 0; c < CW / 8; ++c)
+        *reinterpret_cast<uint4*>(p + c * 128) = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                                                            pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+}
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// One CTA owns one jet at a time.  Thread (r, cq): particle r = TMEM lane r (warp & 3 selects the lane quarter the warp may
+// touch), channel slice cq = warp >> 2 -> kCW consecutive accumulator columns = one tcgen05.ld per pass.
 __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int CW = kCW, NQ = kNQ, G = CW / 4, HQ = NQ / 2;   // HQ: threads per (row, attention head)
     __shared__ uint32_t s_tmem_slot;
     __shared__ __align__(8) uint64_t s_bars[4];             // full[0], full[1], mma, mma2 (the v GEMM that runs under the softmax)
     __shared__ __align__(16) float s_stat[256];             // per channel: scale [128], shift [128] of the running GroupNorm
-    __shared__ __align__(16) float s_part[16][32];          // per-warp partial sums (GroupNorm statistics / column sums)
-    __shared__ __align__(16) float s_bias2[kMaxBlocks][kC]; // conv1 bias + this jet's time term, per block
-    __shared__ float s_rowx[4][128], s_sum[4][128];         // softmax row max and row sum per (channel quarter, row)
+    __shared__ __align__(16) float s_part[4 * NQ][CW];      // per-warp partial sums (GroupNorm statistics / column sums)
+    __shared__ float s_rowx[NQ][128], s_sum[NQ][128];       // softmax row max and row sum per (channel slice, row)
     float (*s_dot)[128] = s_rowx;                           // per-particle output partials (after the last softmax)
     const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7, warp = tid >> 5, lane = tid & 31;
     const int nblk = p.n_blocks, n_seq = 1 + 6 * nblk;
     uint8_t *sA = smem + kOffA, *sQ = smem + kOffQ, *sK = smem + kOffK, *sV = smem + kOffV, *sOnes = smem + kOffOnes;
     float* sTab = reinterpret_cast<float*>(smem + kOffTab);
+    float* s_bias2 = sTab + HeadTable::floats(nblk);        // [nblk][128] conv1 bias + this jet's time term
     uint8_t* sA0 = sV;                            // [128 x 32] proj_in operand, aliases V (dead at jet start)
 
     for (int i = tid; i < HeadTable::floats(nblk); i += kThreads) sTab[i] = __ldg(p.table + i);
@@ -234,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     tc_fence_after();
     const uint32_t tmem = s_tmem_slot;
     const uint32_t lane_off = ((uint32_t)((warp & 3) * 32) << 16);   // this warp's TMEM lane quarter
-    const int col0 = cq * 32;                                        // this thread's 32 accumulator columns
+    const int col0 = cq * CW;                                        // this thread's accumulator columns
     const uint32_t dX = tmem, dACC = tmem + 128, dS0 = tmem + 256, dS1 = tmem + 384;
 
     const int my_jets = p.B > (int)blockIdx.x ? (p.B - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -282,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         umma(d + (wseq & 1) * 128, ones_desc, smem_desc(b_addr(wseq & 1), 128, 256), idesc128, 1u);
         umma_commit(bar_mma);
     };
-    // all threads: wait for the committed MMAs; the ring slot of matrix `wseq` is free again -> prefetch wseq+2
+    // all threads: wait for the committed MMAs; the ring slots of the consumed matrices are free again -> prefetch
     auto mma_done = [&](int used_weights) {
         mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
         tc_fence_after();
@@ -293,37 +321,37 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     };
 
     // GroupNorm(32 groups of 4 channels) over the N live rows of a TMEM tile (+ per-channel bias) -> bf16 A tile.
-    // One TMEM read: the 32 values stay in registers across the statistics exchange, which only involves the four warps of a
-    // channel quarter (named barrier 1 + cq, 128 threads) — the quarters do not wait for each other until the tile is complete.
+    // One TMEM read: the values stay in registers across the statistics exchange, which only involves the four warps of a
+    // channel slice (named barrier 1 + cq, 128 threads) — the slices do not wait for each other until the tile is complete.
     auto group_norm_to_A = [&](uint32_t d_src, const float* bias /*nullable, smem*/, const float* gamma, const float* beta,
                                bool swish, bool valid) {
-        float v[32];
-        tmem_ld32(d_src + lane_off + col0, v);
+        float v[CW];
+        tmem_ldw(d_src + lane_off + col0, v);
         if (bias) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < CW; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + j);
                 fadd2(v[j], v[j + 1], v[j], v[j + 1], b4.x, b4.y);
                 fadd2(v[j + 2], v[j + 3], v[j + 2], v[j + 3], b4.z, b4.w);
             }
         }
-        float st[16];   // 8 group sums, 8 group sums of squares
+        float st[2 * G];   // G group sums, G group sums of squares
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < G; ++g) {
             float s0, s1, q0, q1;
             fadd2(s0, s1, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
             fmul2(q0, q1, v[4 * g], v[4 * g + 1], v[4 * g], v[4 * g + 1]);
             ffma2(q0, q1, v[4 * g + 2], v[4 * g + 3], v[4 * g + 2], v[4 * g + 3], q0, q1);
             st[g] = valid ? s0 + s1 : 0.0f;
-            st[8 + g] = valid ? q0 + q1 : 0.0f;
+            st[G + g] = valid ? q0 + q1 : 0.0f;
         }
-        warp_halving_sum<16>(st, lane);
-        if ((lane & 1) == 0) s_part[warp][warp_halving_index<16>(lane)] = st[0];
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + cq) : "memory");
-        if ((warp & 3) == 0) {  // first warp of the quarter, one lane per channel: y = x*scale + shift with its group's statistics
+        warp_halving_sum<2 * G>(st, lane);
+        if ((lane & (32 / (2 * G) - 1)) == 0) s_part[warp][warp_halving_index<2 * G>(lane)] = st[0];
+        named_bar(1 + cq, 128);
+        if ((warp & 3) == 0 && lane < CW) {  // first warp of the slice, one lane per channel: y = x*scale + shift
             const int c = col0 + lane, gi = lane >> 2, w0 = cq * 4;
             const float s = (s_part[w0][gi] + s_part[w0 + 1][gi]) + (s_part[w0 + 2][gi] + s_part[w0 + 3][gi]);
-            const float q = (s_part[w0][8 + gi] + s_part[w0 + 1][8 + gi]) + (s_part[w0 + 2][8 + gi] + s_part[w0 + 3][8 + gi]);
+            const float q = (s_part[w0][G + gi] + s_part[w0 + 1][G + gi]) + (s_part[w0 + 2][G + gi] + s_part[w0 + 3][G + gi]);
             const float inv = 1.0f / (4.0f * (float)p.N);
             const float mean = s * inv;
             const float var = fmaxf(q * inv - mean * mean, 0.0f);
@@ -332,9 +360,9 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             s_stat[c] = scale;
             s_stat[128 + c] = fmaf(-mean, scale, beta[c] * h);
         }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + cq) : "memory");
+        named_bar(1 + cq, 128);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < CW; j += 4) {
             const float4 sc = *reinterpret_cast<const float4*>(s_stat + col0 + j);
             const float4 sh = *reinterpret_cast<const float4*>(s_stat + 128 + col0 + j);
             ffma2(v[j], v[j + 1], v[j], v[j + 1], sc.x, sc.y, sh.x, sh.y);
@@ -342,12 +370,12 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         }
         if (swish) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
+            for (int j = 0; j < CW; j += 2) {
                 const float t0 = tanh_fast(v[j]), t1 = tanh_fast(v[j + 1]);
                 ffma2(v[j], v[j + 1], v[j], v[j + 1], t0, t1, v[j], v[j + 1]);
             }
         }
-        store_row32(sA, r, cq, v);
+        store_row<CW>(sA, r, col0, v);
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
@@ -397,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         } else {   // conv1 bias + this jet's time term of every block
             const float* tb = p.tbias + (size_t)jet * p.tbias_stride;
             for (int i = tid - 128; i < nblk * kC; i += kThreads - 128)
-                s_bias2[i >> 7][i & 127] = sTab[(i >> 7) * HeadTable::kPerBlock + 2 * kC + (i & 127)] + __ldg(tb + i);
+                s_bias2[i] = sTab[(i >> 7) * HeadTable::kPerBlock + 2 * kC + (i & 127)] + __ldg(tb + i);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -415,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false, bar_mma);           // conv1
             mma_done(1);
             if (blk == 0) STK_TRACE(4);
-            group_norm_to_A(dACC, s_bias2[blk], T + 3 * kC, T + 4 * kC, true, valid);
+            group_norm_to_A(dACC, s_bias2 + blk * kC, T + 3 * kC, T + 4 * kC, true, valid);
             if (blk == 0) STK_TRACE(5);
             if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true, bar_mma);               // X += conv2(.) + b2
             mma_done(1);
@@ -428,11 +456,11 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             mma_done(2);
             if (blk == 0) STK_TRACE(8);
             {   // both tiles in one epilogue phase
-                float v[32];
-                tmem_ld32(dACC + q_half * 128 + lane_off + col0, v);
-                store_row32(sQ, r, cq, v);
-                tmem_ld32(dACC + (q_half ^ 1) * 128 + lane_off + col0, v);
-                store_row32(sK, r, cq, v);
+                float v[CW];
+                tmem_ldw(dACC + q_half * 128 + lane_off + col0, v);
+                store_row<CW>(sQ, r, col0, v);
+                tmem_ldw(dACC + (q_half ^ 1) * 128 + lane_off + col0, v);
+                store_row<CW>(sK, r, col0, v);
                 tc_fence_before();
                 fence_proxy_async();
                 __syncthreads();
@@ -449,46 +477,47 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             }
             mma_done(0);
             if (blk == 0) STK_TRACE(11);
-            // softmax over the N keys: thread (r, cq) serves head cq >> 1, keys [64 (cq & 1), +64); the two halves of a row
-            // exchange max and sum through shared memory.  P (unnormalised, bf16) -> K tile (head 0) / Q tile (head 1), both
-            // dead once S is complete; the A tile still feeds the v GEMM.
+            // softmax over the N keys: thread (r, cq) serves head cq / HQ, keys [2 CW (cq % HQ), + 2 CW); the HQ threads of a
+            // (row, head) exchange max and sum through shared memory.  P (unnormalised, bf16) -> K tile (head 0) / Q tile
+            // (head 1), both dead once S is complete; the A tile still feeds the v GEMM.
+            const int h = cq / HQ, key0 = (cq % HQ) * 2 * CW;
             {
-                const int h = cq >> 1, kh = cq & 1;
-                const uint32_t dS = (h ? dS1 : dS0) + lane_off + kh * 64;
+                const uint32_t dS = (h ? dS1 : dS0) + lane_off + key0;
                 const bool full = p.N == 128;
-                float v[32], mx = -3.0e38f;
+                float v[CW], mx = -3.0e38f;
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
-                    tmem_ld32(dS + c * 32, v);
+                    tmem_ldw(dS + c * CW, v);
                     if (full) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(v[j], v[j + 1]));
+                        for (int j = 0; j < CW; j += 2) mx = fmaxf(mx, fmaxf(v[j], v[j + 1]));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = (kh * 64 + c * 32 + j < p.N) ? fmaxf(mx, v[j]) : mx;
+                        for (int j = 0; j < CW; ++j) mx = (key0 + c * CW + j < p.N) ? fmaxf(mx, v[j]) : mx;
                     }
                 }
                 s_rowx[cq][r] = mx;
-                asm volatile("bar.sync %0, 256;" ::"r"(5 + h) : "memory");   // the two key halves of a head
-                mx = fmaxf(mx, s_rowx[cq ^ 1][r]);
+                named_bar(1 + NQ + h, 128 * HQ);   // the key slices of a head
+#pragma unroll
+                for (int i = 0; i < HQ; ++i) mx = fmaxf(mx, s_rowx[h * HQ + i][r]);
                 const float sc = 0.125f * 1.4426950408889634f;  // dh^-1/2 * log2(e)
                 const float off = -mx * sc;
                 float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
-                    tmem_ld32(dS + c * 32, v);
+                    tmem_ldw(dS + c * CW, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
+                    for (int j = 0; j < CW; j += 2) {
                         ffma2(v[j], v[j + 1], v[j], v[j + 1], sc, sc, off, off);
                         v[j] = ex2_fast(v[j]);
                         v[j + 1] = ex2_fast(v[j + 1]);
                         if (!full) {
-                            v[j] = (kh * 64 + c * 32 + j < p.N) ? v[j] : 0.0f;
-                            v[j + 1] = (kh * 64 + c * 32 + j + 1 < p.N) ? v[j + 1] : 0.0f;
+                            v[j] = (key0 + c * CW + j < p.N) ? v[j] : 0.0f;
+                            v[j + 1] = (key0 + c * CW + j + 1 < p.N) ? v[j + 1] : 0.0f;
                         }
                         fadd2(s0, s1, s0, s1, v[j], v[j + 1]);
                     }
-                    store_row32(h ? sQ : sK, r, kh * 2 + c, v);
+                    store_row<CW>(h ? sQ : sK, r, key0 + c * CW, v);
                 }
                 s_sum[cq][r] = s0 + s1;
                 // the v GEMM finished long ago: its tile joins this phase's fence and barrier
@@ -496,8 +525,8 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                 tc_fence_after();
                 if (tid == 0 && wseq + 2 < total_mats) issue_load(wseq + 2);
                 ++wseq;
-                tmem_ld32(dACC + lane_off + col0, v);
-                store_row32(sV, r, cq, v);
+                tmem_ldw(dACC + lane_off + col0, v);
+                store_row<CW>(sV, r, col0, v);
             }
             tc_fence_before();
             fence_proxy_async();
@@ -505,21 +534,24 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             if (blk == 0) STK_TRACE(12);
             if (tid == 0) {                                                  // O_h = P_h V_h, K = 128 keys, N = 64
                 tc_fence_after();
-                for (int h = 0; h < kHeads; ++h)
+                for (int hh = 0; hh < kHeads; ++hh)
                     for (int j = 0; j < 8; ++j)
-                        umma(dACC + h * 64, smem_desc((h ? aQ : aK) + j * 256, 128, 2048),
-                             smem_desc(aV + h * 1024 + j * 4096, 2048, 128), idesc64mn, j > 0);
+                        umma(dACC + hh * 64, smem_desc((hh ? aQ : aK) + j * 256, 128, 2048),
+                             smem_desc(aV + hh * 1024 + j * 4096, 2048, 128), idesc64mn, j > 0);
                 umma_commit(bar_mma);
             }
             mma_done(0);
             if (blk == 0) STK_TRACE(13);
             {
-                float v[32];  // columns [32 cq, +32) of O belong to head cq >> 1: normalised by that head's row sum
-                const float rinv = 1.0f / (s_sum[cq][r] + s_sum[cq ^ 1][r]);
-                tmem_ld32(dACC + lane_off + col0, v);
+                float v[CW];  // columns [col0, +CW) of O belong to head cq / HQ: normalised by that head's row sum
+                float tot = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) fmul2(v[j], v[j + 1], v[j], v[j + 1], rinv, rinv);
-                store_row32(sA, r, cq, v);
+                for (int i = 0; i < HQ; ++i) tot += s_sum[h * HQ + i][r];
+                const float rinv = 1.0f / tot;
+                tmem_ldw(dACC + lane_off + col0, v);
+#pragma unroll
+                for (int j = 0; j < CW; j += 2) fmul2(v[j], v[j + 1], v[j], v[j + 1], rinv, rinv);
+                store_row<CW>(sA, r, col0, v);
             }
             tc_fence_before();
             fence_proxy_async();
@@ -532,13 +564,13 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         STK_TRACE(16);
         // ---- per-particle output: one 128-vector against the residual stream (absorbing: post_rate_proj(pre_rate_proj(X))
         //      folded, absorbing_flows.py:127-131; trans: near_atom_proj / vec_weighting_proj) and, for the per-jet heads,
-        //      the mean of X over the N slots followed by a folded [n_jet x 128] Linear (transdimensional_model.py:309-311,403-405)
+        //      the mean of X over the N slots (transdimensional_model.py:309-311,403-405; the folded Linear follows in jet_head_kernel)
         {
             const float* w = sTab + HeadTable::rate_w(nblk);
-            float v[32], a0 = 0.0f, a1 = 0.0f;
-            tmem_ld32(dX + lane_off + col0, v);
+            float v[CW], a0 = 0.0f, a1 = 0.0f;
+            tmem_ldw(dX + lane_off + col0, v);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int j = 0; j < CW; j += 4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(w + col0 + j);
                 ffma2(a0, a1, v[j], v[j + 1], w4.x, w4.y, a0, a1);
                 ffma2(a0, a1, v[j + 2], v[j + 3], w4.z, w4.w, a0, a1);
@@ -546,14 +578,19 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             s_dot[cq][r] = a0 + a1;
             if (p.n_jet > 0) {   // column sums over the rows: halving reduction inside the warp, then the four lane quarters
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = valid ? v[j] : 0.0f;
-                warp_halving_sum<32>(v, lane);
-                s_part[warp][warp_halving_index<32>(lane)] = v[0];
+                for (int j = 0; j < CW; ++j) v[j] = valid ? v[j] : 0.0f;
+                warp_halving_sum<CW>(v, lane);
+                if ((lane & (32 / CW - 1)) == 0) s_part[warp][warp_halving_index<CW>(lane)] = v[0];
             }
             __syncthreads();
-            if (cq == 0 && valid) p.logit_out[pidx] = sTab[HeadTable::rate_c(nblk)] + (s_dot[0][r] + s_dot[1][r]) + (s_dot[2][r] + s_dot[3][r]);
+            if (cq == 0 && valid) {
+                float tot = sTab[HeadTable::rate_c(nblk)];
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) tot += s_dot[i][r];
+                p.logit_out[pidx] = tot;
+            }
             if (p.n_jet > 0 && tid < 128) {   // the folded per-jet Linear runs afterwards, batched over jets (jet_head_kernel)
-                const int w0 = (tid >> 5) * 4, ci = tid & 31;
+                const int w0 = (tid / CW) * 4, ci = tid % CW;
                 p.jet_out[(size_t)jet * kC + tid] =
                     ((s_part[w0][ci] + s_part[w0 + 1][ci]) + (s_part[w0 + 2][ci] + s_part[w0 + 3][ci])) * (1.0f / (float)p.N);
             }
@@ -632,7 +669,6 @@ int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* bloc
         for (int c = 0; c < C; ++c) {
             T[0 * kC + c] = n1g[c]; T[1 * kC + c] = n1b[c]; T[2 * kC + c] = c1[(size_t)C * C + c];
             T[3 * kC + c] = n2g[c]; T[4 * kC + c] = n2b[c]; T[5 * kC + c] = ng[c]; T[6 * kC + c] = nb[c];
-            T[7 * kC + c] = wq[(size_t)C * C + c]; T[8 * kC + c] = wk[(size_t)C * C + c]; T[9 * kC + c] = wv[(size_t)C * C + c];
         }
     }
     for (int c = 0; c < C; ++c) tab[HeadTable::rate_w(n_blocks) + c] = dot_w[c];
@@ -717,7 +753,7 @@ int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B,
     p.tbias = io.tbias; p.tbias_stride = io.tbias_stride; p.B = B; p.N = N; p.logit_out = io.dot_out;
     p.n_jet = io.jet_out ? st->n_jet : 0; p.jet_out = io.jet_out;
     p.trace = stack_trace_buffer();
-    const size_t bytes = kOffTab + (size_t)HeadTable::floats(st->n_blocks) * 4 + 1024;
+    const size_t bytes = kOffTab + (size_t)(HeadTable::floats(st->n_blocks) + st->n_blocks * kC) * 4;
     cudaFuncAttributes attr;
     if (int rc = cuda_ok(cudaFuncGetAttributes(&attr, absorb_head_tc_kernel), "head attributes")) return rc;
     if (bytes + attr.sharedSizeBytes > 232448)

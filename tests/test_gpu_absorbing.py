@@ -46,15 +46,17 @@ def test_rate_head_within_tolerance_of_oracle_and_reference(fixture):
         assert np.abs(got - s("a")[..., 0]).max() <= 0.03 * np.abs(s("a")).max()
 
 
-def test_rate_head_per_jet_time_bias_and_full_width():
-    """N = 128 slots, a different time (tbias row) per jet, B not a multiple of the grid."""
+@pytest.mark.parametrize("N", [128, 109, 1])
+def test_rate_head_per_jet_time_bias_and_full_width(N):
+    """N = 128 slots (and 109, the reference's config-absorbing-test.yaml, and the single-slot edge), a different time
+    (tbias row) per jet, B not a multiple of the grid."""
     cfg = AbsorbingConfig()
-    cfg.data.max_num_particles = 128
+    cfg.data.max_num_particles = N
     torch.manual_seed(3)
     model = AbsorbingFlow(cfg)
     g = model.generator
     blob = g.pack_head_weights().numpy()
-    B, N = 5, 128
+    B = 5
     gen = torch.Generator().manual_seed(4)
     hidden = torch.randn(B, N, 16, generator=gen)
     mask = (torch.rand(B, N, generator=gen) < 0.5).to(torch.uint8)
