@@ -409,6 +409,33 @@ int mmb_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, c
 int mmb_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
                       uint64_t seed, uint64_t jet_offset, void* stream);
 
+/*
+ * Forward half of a training / validation step — bridge sampling and the masked losses; the backward pass
+ * stays out of scope.
+ *
+ * mmb_sample_bridges = MultiModalBridgeMatching.sample_bridges (mp/models/generative/multimodal_bridge_matching.py:148-165) given the
+ * per-jet times t [B]:  xt = (t x1 + (1-t) x0) + sigma z  (LinearUniformBridge.sample, bridges.py:23-27);
+ * kt ~ Categorical(P(k | k0, k1, t)) with the telegraph-bridge posterior (TelegraphBridge.sample, bridges.py:99-104,134-177),
+ * drawn by inverse CDF on one uniform per particle.  z [B,N,3] / u [B,N] inject the draws (both or neither); NULL = Philox
+ * streams 12/13 keyed by (seed, jet_offset + jet, particle).
+ */
+int mmb_sample_bridges(const float* x0, const float* x1, const uint8_t* k0, const uint8_t* k1, const float* t, float sigma, float gamma,
+                       int S, const float* z, const float* u, uint64_t seed, uint64_t jet_offset, int B, int N,
+                       float* xt, uint8_t* kt, void* stream);
+/* AbsorbingBridge.sample (bridges.py:233-249): mask_t = [u < SP(t)] | target_mask, sp [B] = survival probability at each jet's time
+ * (bridges.py:218-231, computed by the caller); u [B,N] or NULL for Philox stream 14. */
+int mmb_absorbing_sample(const float* sp, const uint8_t* target_mask, const float* u, uint64_t seed, uint64_t jet_offset, int B, int N,
+                         uint8_t* mask_t, void* stream);
+/*
+ * loss_continuous + loss_discrete (multimodal_bridge_matching.py:167-197): masked MSE between the velocity head and the drift
+ * target x1 - x0, masked cross entropy between the logits and the target tokens, both divided by the number of live particles.
+ * out [3] (device) = { mse, ce, live particles }.  workspace: mmb_bridge_losses_workspace_bytes(B, N) bytes.
+ * Sums are reduced in a fixed order (deterministic).
+ */
+size_t mmb_bridge_losses_workspace_bytes(int B, int N);
+int mmb_bridge_losses(const float* v, const float* logits, const float* x0, const float* x1, const uint8_t* k1, const uint8_t* mask,
+                      int B, int N, int S, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

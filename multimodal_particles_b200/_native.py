@@ -91,6 +91,10 @@ SIGNATURES = {
     "mmb_validation_histograms": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _vp, _vp]),
     "mmb_jet_observables": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "mmb_sample_source": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _u64, _u64, _vp]),
+    "mmb_sample_bridges": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _vp, _u64, _u64, _i, _i, _vp, _vp, _vp]),
+    "mmb_absorbing_sample": (_i, [_vp, _vp, _vp, _u64, _u64, _i, _i, _vp, _vp]),
+    "mmb_bridge_losses_workspace_bytes": (_sz, [_i, _i]),
+    "mmb_bridge_losses": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mmb_trans_packed_floats": (_sz, [ctypes.POINTER(TransDims)]),
     "mmb_trans_create": (_i, [ctypes.POINTER(TransDims), _vp, _sz, _i, ctypes.POINTER(_vp)]),
     "mmb_trans_destroy": (None, [_vp]),
@@ -348,3 +352,38 @@ def trans_sampler_update(x, onehot, dims, v, logits, rate, new_mean, new_std, c_
         check(load().mmb_trans_sampler_update(_ptr(x), _ptr(onehot), _ptr(dims), _ptr(v), _ptr(logits), _ptr(rate), _ptr(new_mean),
                                               _ptr(new_std), c_decay, c_score, c_noise, inv_std, jump_dt, _ptr(z_diff), _ptr(u_jump),
                                               _ptr(z_new), seed, jet_offset, step, B, N, S, _stream()))
+
+
+# ---- forward half of a training / validation step ---------------------------------------------------------
+def sample_bridges(x0, x1, k0_u8, k1_u8, t, sigma, gamma, S, z=None, u=None, seed=0, jet_offset=0):
+    """-> (xt [B,N,3] f32, kt [B,N] u8) on the device of x0."""
+    _require_cuda(x0, x1, k0_u8, k1_u8, t, z, u)
+    B, N, _ = x0.shape
+    xt = torch.empty_like(x0)
+    kt = torch.empty(B, N, dtype=torch.uint8, device=x0.device)
+    with torch.cuda.device(x0.device):
+        check(load().mmb_sample_bridges(_ptr(x0), _ptr(x1), _ptr(k0_u8), _ptr(k1_u8), _ptr(t), float(sigma), float(gamma), S, _ptr(z), _ptr(u),
+                                        seed, jet_offset, B, N, _ptr(xt), _ptr(kt), _stream()))
+    return xt, kt
+
+
+def absorbing_sample(sp, target_mask_u8, u=None, seed=0, jet_offset=0):
+    _require_cuda(sp, target_mask_u8, u)
+    B, N = target_mask_u8.shape
+    out = torch.empty_like(target_mask_u8)
+    with torch.cuda.device(sp.device):
+        check(load().mmb_absorbing_sample(_ptr(sp), _ptr(target_mask_u8), _ptr(u), seed, jet_offset, B, N, _ptr(out), _stream()))
+    return out
+
+
+def bridge_losses(v, logits, x0, x1, k1_u8, mask_u8):
+    """-> device tensor [3] = (masked MSE, masked cross entropy, live particles)."""
+    _require_cuda(v, logits, x0, x1, k1_u8, mask_u8)
+    B, N, S = logits.shape
+    lib = load()
+    out = torch.empty(3, device=v.device, dtype=torch.float32)
+    ws = torch.empty(max(lib.mmb_bridge_losses_workspace_bytes(B, N), 16), device=v.device, dtype=torch.uint8)
+    with torch.cuda.device(v.device):
+        check(lib.mmb_bridge_losses(_ptr(v), _ptr(logits), _ptr(x0), _ptr(x1), _ptr(k1_u8), _ptr(mask_u8), B, N, S, _ptr(out), _ptr(ws),
+                                    ws.numel(), _stream()))
+    return out

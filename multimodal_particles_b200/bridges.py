@@ -13,8 +13,9 @@ Differences from the reference, by design:
   (parity tests), otherwise ``torch.rand`` on the state's device;
 * tokens/masks are narrowed to uint8 for the kernel and written back in the state's int64 layout.
 
-The training-time samplers (``sample``, ``drift``, ``transition_probability``; bridges.py:23-33,
-99-104,134-177,233-249) are outside the generation path.
+The training-time samplers of the continuous and discrete bridges (bridges.py:23-33,99-104,134-177) run fused inside
+``MultiModalBridgeMatching.sample_bridges`` (``mmb_sample_bridges``); ``AbsorbingBridge.sample`` (bridges.py:233-249) is
+mirrored here.
 """
 import torch
 
@@ -86,6 +87,16 @@ class AbsorbingBridge:
 
     def survival_probability(self, t):
         return survival_probability(t, float(self.gamma_absorb))
+
+    def sample(self, time, target_mask, uniforms=None):
+        """time [B,1,1], target_mask [B,N,1] -> mask_t [B,N,1] int64: particles alive at ``time`` (bridges.py:233-249);
+        ``uniforms`` [B,N] injects the draws, default in-kernel Philox."""
+        dev = target_mask.device
+        B, N = target_mask.shape[0], target_mask.shape[1]
+        sp = self.survival_probability(time.reshape(B).float().cpu()).to(dev).contiguous()
+        u = None if uniforms is None else uniforms.reshape(B, N).to(dev, torch.float32).contiguous()
+        self._sampled = getattr(self, "_sampled", 0) + B
+        return _native.absorbing_sample(sp, as_u8(target_mask), u, jet_offset=self._sampled - B).to(torch.int64).unsqueeze(-1)
 
     def solver_step(self, state, heads, delta_t, uniforms=None):
         m64 = state.mask_t

@@ -261,6 +261,38 @@ int mmb_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float s
     return launch_sample_source(x, k, mask, B, N, scale, cat_probs, mult_cdf, seed, jet_offset, static_cast<cudaStream_t>(stream));
 }
 
+int mmb_sample_bridges(const float* x0, const float* x1, const uint8_t* k0, const uint8_t* k1, const float* t, float sigma, float gamma,
+                       int S, const float* z, const float* u, uint64_t seed, uint64_t jet_offset, int B, int N, float* xt, uint8_t* kt,
+                       void* stream) {
+    if (!x0 || !x1 || !k0 || !k1 || !t || !xt || !kt) return fail(MMB_EINVAL, "mmb_sample_bridges: null argument");
+    if ((z == nullptr) != (u == nullptr)) return fail(MMB_EINVAL, "mmb_sample_bridges: inject z and u together or neither");
+    if (B < 0 || N < 0 || S < 1 || S > 255) return fail(MMB_EINVAL, "mmb_sample_bridges: bad size");
+    if (B == 0 || N == 0) return MMB_OK;
+    return launch_sample_bridges(x0, x1, k0, k1, t, sigma, gamma, S, z, u, seed, jet_offset, B, N, xt, kt, static_cast<cudaStream_t>(stream));
+}
+
+int mmb_absorbing_sample(const float* sp, const uint8_t* target_mask, const float* u, uint64_t seed, uint64_t jet_offset, int B, int N,
+                         uint8_t* mask_t, void* stream) {
+    if (!sp || !target_mask || !mask_t) return fail(MMB_EINVAL, "mmb_absorbing_sample: null argument");
+    if (B < 0 || N < 0) return fail(MMB_EINVAL, "mmb_absorbing_sample: negative size");
+    if (B == 0 || N == 0) return MMB_OK;
+    return launch_absorbing_sample(sp, target_mask, u, seed, jet_offset, B, N, mask_t, static_cast<cudaStream_t>(stream));
+}
+
+size_t mmb_bridge_losses_workspace_bytes(int B, int N) {
+    if (B < 0 || N < 0) return 0;
+    return (size_t)bridge_losses_blocks((size_t)B * N) * 3 * sizeof(float);
+}
+
+int mmb_bridge_losses(const float* v, const float* logits, const float* x0, const float* x1, const uint8_t* k1, const uint8_t* mask,
+                      int B, int N, int S, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!v || !logits || !x0 || !x1 || !k1 || !mask || !out || !workspace) return fail(MMB_EINVAL, "mmb_bridge_losses: null argument");
+    if (B < 1 || N < 1 || S < 1) return fail(MMB_EINVAL, "mmb_bridge_losses: bad size");
+    if (workspace_bytes < mmb_bridge_losses_workspace_bytes(B, N)) return fail(MMB_ENOMEM, "mmb_bridge_losses: workspace too small");
+    return launch_bridge_losses(v, logits, x0, x1, k1, mask, (size_t)B * N, S, out, static_cast<float*>(workspace),
+                                static_cast<cudaStream_t>(stream));
+}
+
 // debug only (not part of include/mmbridge.h): phase timestamps of the tcgen05 generation kernel, see tools/tc_trace.py
 int mmb_debug_read_trace(long long* out, int n) { return tc_read_trace(out, n); }
 int mmb_debug_read_stack_trace(long long* out, int n) { return stack_read_trace(out, n); }

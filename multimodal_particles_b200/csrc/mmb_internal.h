@@ -81,6 +81,16 @@ int launch_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask
 int launch_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
                          uint64_t seed, uint64_t jet_offset, cudaStream_t stream);
 
+// bridge_sample.cu — forward half of a training / validation step
+int launch_sample_bridges(const float* x0, const float* x1, const uint8_t* k0, const uint8_t* k1, const float* ts, float sigma, float gamma,
+                          int S, const float* z, const float* u, uint64_t seed, uint64_t jet_offset, int B, int N, float* xt, uint8_t* kt,
+                          cudaStream_t stream);
+int launch_absorbing_sample(const float* sp, const uint8_t* target_mask, const float* u, uint64_t seed, uint64_t jet_offset, int B, int N,
+                            uint8_t* mask_t, cudaStream_t stream);
+int bridge_losses_blocks(size_t P);
+int launch_bridge_losses(const float* v, const float* logits, const float* x0, const float* x1, const uint8_t* k1, const uint8_t* mask,
+                         size_t P, int S, float* out, float* partial, cudaStream_t stream);
+
 // epic_fp32.cu — CUDA-core path, bit-identical to the oracle
 int launch_epic_forward_fp32(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
                              const float* temb, int temb_stride, int B, int N,

@@ -8,6 +8,8 @@ containers and tensor layouts, same state-dict keys.  The compute is libmmbridge
 of ~725 eager ops and 4 host syncs per step.  Training methods
 (``sample_bridges``, losses, ``training_step``) are outside this path and raise.
 """
+from types import SimpleNamespace
+
 import torch
 from torch import nn
 
@@ -42,6 +44,11 @@ class MultiHeadLoss(nn.Module):
     def __init__(self, number_of_losses=2):
         super().__init__()
         self.weights = nn.Parameter(torch.zeros(number_of_losses))
+
+    def forward(self, losses):
+        """'learnable' mode of the reference: sum_i exp(-w_i) L_i + w_i  (mp/utils/losses.py:21-29)"""
+        w = self.weights.to(losses[0].device)
+        return sum(torch.exp(-w[i]) * losses[i] + w[i] for i in range(len(losses))), losses
 
 
 class MultiModalEPiC(nn.Module):
@@ -167,9 +174,53 @@ class MultiModalBridgeMatching(_ModuleBase):
             dev = torch.device("cuda", torch.cuda.current_device())
         return dev
 
+    # ---- forward half of a training / validation step ---------------------------------
+    def reshape_time(self, t, x):
+        return t if isinstance(t, (float, int)) else t.reshape(-1, *([1] * (x.dim() - 1)))
+
+    @torch.no_grad()
+    def sample_bridges(self, batch, t=None, z=None, u=None) -> HybridState:
+        """Sample stochastic bridges (mbm.py:148-165): ``t ~ U(0,1)`` per jet, ``x_t = t x1 + (1-t) x0 + sigma z`` and
+        ``k_t ~ telegraph posterior`` in one kernel.  ``t`` [B], ``z`` [B,N,3], ``u`` [B,N] inject the draws (parity);
+        default: torch.rand for the times, in-kernel Philox for the rest."""
+        device = self._compute_device(SimpleNamespace(continuous=batch.target_continuous))
+        x1 = batch.target_continuous.to(device, torch.float32).contiguous()
+        x0 = batch.source_continuous.to(device, torch.float32).contiguous()
+        B = x1.shape[0]
+        t = torch.rand(B, device=device) if t is None else t.to(device, torch.float32).contiguous()
+        prep = lambda a: None if a is None else a.to(device, torch.float32).contiguous()
+        jet_offset, self._bridges_sampled = getattr(self, "_bridges_sampled", 0), getattr(self, "_bridges_sampled", 0) + B
+        xt, kt = _native.sample_bridges(x0, x1, as_u8(batch.source_discrete.to(device)), as_u8(batch.target_discrete.to(device)), t,
+                                        self.bridge_continuous.sigma, self.bridge_discrete.gamma, self.vocab_size, prep(z), prep(u),
+                                        seed=self.seed, jet_offset=jet_offset)
+        return HybridState(self.reshape_time(t, x1), xt, kt.long().unsqueeze(-1), batch.target_mask.to(device))
+
+    @torch.no_grad()
+    def _losses(self, heads: MultiHeadOutput, state: HybridState, batch) -> torch.Tensor:
+        dev = heads.continuous.device
+        f = lambda a: a.to(dev, torch.float32).contiguous()
+        return _native.bridge_losses(f(heads.continuous), f(heads.discrete), f(batch.source_continuous), f(batch.target_continuous),
+                                     as_u8(batch.target_discrete.to(dev)), as_u8(state.absorbing.to(dev)))
+
+    def loss_continuous(self, heads: MultiHeadOutput, state: HybridState, batch) -> torch.Tensor:
+        """masked mean square error of the drift (mbm.py:167-183); forward value only (no autograd)"""
+        return self._losses(heads, state, batch)[0]
+
+    def loss_discrete(self, heads: MultiHeadOutput, state: HybridState, batch) -> torch.Tensor:
+        """masked cross entropy of the token classifier (mbm.py:185-197); forward value only (no autograd)"""
+        return self._losses(heads, state, batch)[1]
+
+    @torch.no_grad()
+    def validation_step(self, batch, batch_idx=0) -> torch.Tensor:
+        """mbm.py:241-250: bridges -> heads -> the two losses -> learnable multi-head weighting (forward only)."""
+        state = self.sample_bridges(batch)
+        heads = self.forward(state, batch)
+        both = self._losses(heads, state, batch)
+        loss, _ = self.loss_multihead([both[0], both[1]])
+        return loss
+
     # ---- outside the generation path ----------------------------------------------------------
     def _training_not_in_scope(self, *args, **kwargs):
-        raise NotImplementedError("training is outside the B200 generation hot path (SURVEY.md §8f N2)")
+        raise NotImplementedError("the backward pass / optimiser are outside the B200 hot path (SURVEY.md §8f N2: forward only)")
 
-    sample_bridges = loss_continuous = loss_discrete = training_step = validation_step = _training_not_in_scope
-    configure_optimizers = _training_not_in_scope
+    training_step = configure_optimizers = _training_not_in_scope

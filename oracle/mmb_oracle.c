@@ -939,6 +939,68 @@ void mmbo_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Forward half of a training / validation step (multimodal_bridge_matching.py:148-197; bridges.py:23-27,99-104,134-177,233-249) */
+void mmbo_sample_bridges(const float* x0, const float* x1, const uint8_t* k0, const uint8_t* k1, const float* ts, float sigma, float gamma,
+                         int S, const float* z, const float* u, int B, int N, float* xt, uint8_t* kt) {
+    const float neg_s_gamma = (float)(-(double)S * (double)gamma);
+    const float inv_s = 1.0f / (float)S, ninv_s = -1.0f / (float)S;
+    for (int b = 0; b < B; ++b) {
+        const float t = ts[b], omt = 1.0f - t;
+        const float w1 = mmbo_expf(neg_s_gamma * (1.0f - t)), w0 = mmbo_expf(neg_s_gamma * (t - 0.0f)), w01 = mmbo_expf(neg_s_gamma * 1.0f);
+        for (int n = 0; n < N; ++n) {
+            const size_t i = (size_t)b * N + n;
+            for (int c = 0; c < 3; ++c) {
+                const float lin = t * x1[i * 3 + c] + omt * x0[i * 3 + c];
+                xt[i * 3 + c] = lin + sigma * z[i * 3 + c];
+            }
+            const int a0 = k0[i], a1 = k1[i];
+            const float p01 = inv_s + w01 * (ninv_s + (a0 == a1 ? 1.0f : 0.0f));
+            float tot = 0.0f;
+            for (int k = 0; k < S; ++k) {
+                const float pa = inv_s + w1 * (ninv_s + (k == a1 ? 1.0f : 0.0f));
+                const float pb = inv_s + w0 * (ninv_s + (k == a0 ? 1.0f : 0.0f));
+                tot = tot + (pa * pb) / p01;
+            }
+            int pick = S - 1;
+            float c = 0.0f;
+            for (int k = 0; k < S; ++k) {
+                const float pa = inv_s + w1 * (ninv_s + (k == a1 ? 1.0f : 0.0f));
+                const float pb = inv_s + w0 * (ninv_s + (k == a0 ? 1.0f : 0.0f));
+                c = c + ((pa * pb) / p01) / tot;
+                if (u[i] < c) { pick = k; break; }
+            }
+            kt[i] = (uint8_t)pick;
+        }
+    }
+}
+
+void mmbo_absorbing_sample(const float* sp, const uint8_t* target_mask, const float* u, int B, int N, uint8_t* mask_t) {
+    for (int b = 0; b < B; ++b)
+        for (int n = 0; n < N; ++n) {
+            const size_t i = (size_t)b * N + n;
+            mask_t[i] = (target_mask[i] || u[i] < sp[b]) ? 1 : 0;
+        }
+}
+
+void mmbo_bridge_losses(const float* v, const float* logits, const float* x0, const float* x1, const uint8_t* k1, const uint8_t* mask,
+                        int B, int N, int S, float* out) {
+    double mse = 0, ce = 0, cnt = 0;
+    for (size_t i = 0; i < (size_t)B * N; ++i) {
+        if (!mask[i]) continue;
+        for (int c = 0; c < 3; ++c) {
+            const float d = v[i * 3 + c] - (x1[i * 3 + c] - x0[i * 3 + c]);
+            mse += (double)d * d;
+        }
+        double mx = -INFINITY, se = 0;
+        for (int s = 0; s < S; ++s) mx = logits[i * S + s] > mx ? logits[i * S + s] : mx;
+        for (int s = 0; s < S; ++s) se += exp((double)logits[i * S + s] - mx);
+        ce += (mx + log(se)) - logits[i * S + k1[i]];
+        cnt += 1;
+    }
+    out[0] = (float)(mse / cnt); out[1] = (float)(ce / cnt); out[2] = (float)cnt;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 int mmbo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -95,6 +95,13 @@ void mmbo_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask,
 void mmbo_sample_source(float* x, uint8_t* k, uint8_t* mask, int B, int N, float scale, const float* cat_probs, const float* mult_cdf,
                         uint64_t seed, uint64_t jet_offset);
 
+/* forward half of a training / validation step, draws injected (mmb_sample_bridges, mmb_absorbing_sample, mmb_bridge_losses) */
+void mmbo_sample_bridges(const float* x0, const float* x1, const uint8_t* k0, const uint8_t* k1, const float* ts, float sigma, float gamma,
+                         int S, const float* z, const float* u, int B, int N, float* xt, uint8_t* kt);
+void mmbo_absorbing_sample(const float* sp, const uint8_t* target_mask, const float* u, int B, int N, uint8_t* mask_t);
+void mmbo_bridge_losses(const float* v, const float* logits, const float* x0, const float* x1, const uint8_t* k1, const uint8_t* mask,
+                        int B, int N, int S, float* out);
+
 int mmbo_max_threads(void);
 
 #ifdef __cplusplus

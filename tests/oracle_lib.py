@@ -270,3 +270,27 @@ def sample_source(B, N, scale, cat_probs, mult_cdf, seed, jet_offset):
     lib().mmbo_sample_source(_p(x), _p(k, _u8p), _p(mask, _u8p), B, N, ctypes.c_float(scale), _p(f32(cat_probs)), _p(cdf),
                              ctypes.c_uint64(seed), ctypes.c_uint64(jet_offset))
     return x, k, mask
+
+
+# ---- forward half of a training / validation step -----------------------------------------------------
+def sample_bridges(x0, x1, k0, k1, t, sigma, gamma, S, z, u):
+    B, N, _ = x0.shape
+    xt, kt = np.empty((B, N, 3), np.float32), np.empty((B, N), np.uint8)
+    lib().mmbo_sample_bridges(_p(f32(x0)), _p(f32(x1)), _p(u8(k0).reshape(B, N), _u8p), _p(u8(k1).reshape(B, N), _u8p), _p(f32(t)),
+                              ctypes.c_float(sigma), ctypes.c_float(gamma), S, _p(f32(z)), _p(f32(u)), B, N, _p(xt), _p(kt, _u8p))
+    return xt, kt
+
+
+def absorbing_sample(sp, target_mask, u):
+    B, N = target_mask.shape
+    out = np.empty((B, N), np.uint8)
+    lib().mmbo_absorbing_sample(_p(f32(sp)), _p(u8(target_mask), _u8p), _p(f32(u)), B, N, _p(out, _u8p))
+    return out
+
+
+def bridge_losses(v, logits, x0, x1, k1, mask):
+    B, N, S = logits.shape
+    out = np.empty(3, np.float32)
+    lib().mmbo_bridge_losses(_p(f32(v)), _p(f32(logits)), _p(f32(x0)), _p(f32(x1)), _p(u8(k1).reshape(B, N), _u8p),
+                             _p(u8(mask).reshape(B, N), _u8p), B, N, S, _p(out))
+    return out
