@@ -234,6 +234,7 @@ __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("b
 
 // One CTA owns one jet at a time.  Thread (r, cq): particle r = TMEM lane r (warp & 3 selects the lane quarter the warp may
 // touch), channel slice cq = warp >> 2 -> kCW consecutive accumulator columns = one tcgen05.ld per pass.
+template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int CW = kCW, NQ = kNQ, G = CW / 4, HQ = NQ / 2;   // HQ: threads per (row, attention head)
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     };
     // q / k / v biases are handled algebraically: q rides on an extra K-step; k is a per-query constant in the logits
     // (softmax-invariant) and is dropped; v is folded into the proj_out bias because softmax rows sum to one.
-#define STK_TRACE(id) do { if (p.trace && blockIdx.x == 0 && jet == 0 && tid == 32) p.trace[id] = clock64(); } while (0)
+#define STK_TRACE(id) do { if constexpr (TRACE) { if (p.trace && blockIdx.x == 0 && jet == 0 && tid == 32) p.trace[id] = clock64(); } } while (0)
     for (int jet = blockIdx.x; jet < p.B; jet += gridDim.x) {
         const bool valid = r < p.N;
         STK_TRACE(0);
@@ -754,15 +755,16 @@ int launch_tf_stack(const TfStack* st, int sm_count, const TfStackIO& io, int B,
     p.n_jet = io.jet_out ? st->n_jet : 0; p.jet_out = io.jet_out;
     p.trace = stack_trace_buffer();
     const size_t bytes = kOffTab + (size_t)(HeadTable::floats(st->n_blocks) + st->n_blocks * kC) * 4;
+    auto kern = p.trace ? absorb_head_tc_kernel<true> : absorb_head_tc_kernel<false>;
     cudaFuncAttributes attr;
-    if (int rc = cuda_ok(cudaFuncGetAttributes(&attr, absorb_head_tc_kernel), "head attributes")) return rc;
+    if (int rc = cuda_ok(cudaFuncGetAttributes(&attr, kern), "head attributes")) return rc;
     if (bytes + attr.sharedSizeBytes > 232448)
         return fail(MMB_EUNSUPPORTED, "transformer stack with %d blocks needs %zu B of shared memory per CTA (limit 232448)", st->n_blocks,
                     bytes + attr.sharedSizeBytes);
-    if (int rc = cuda_ok(cudaFuncSetAttribute(absorb_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "head smem attribute"))
+    if (int rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "head smem attribute"))
         return rc;
     const int grid = B < sm_count ? B : sm_count;
-    absorb_head_tc_kernel<<<grid, kThreads, bytes, stream>>>(p);
+    kern<<<grid, kThreads, bytes, stream>>>(p);
     return cuda_ok(cudaGetLastError(), "transformer stack launch");
 }
 

@@ -284,7 +284,7 @@ struct JetVec {
     int cnt[4];
 };
 
-template <int DC, int S, int SH, bool GENERATE>
+template <int DC, int S, int SH, bool GENERATE, bool TRACE = false>
 __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const TcLayout& lay = p.lay;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         const int o16 = lane & 15, hf = lane >> 4;
 
         const int n_steps = GENERATE ? p.n_steps : 1;
-#define MMB_TRACE(id) do { if (p.trace && jet == 0 && step == 3 && gt == 32 * ((swq + 1) & 3)) p.trace[id] = clock64(); } while (0)
+#define MMB_TRACE(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && gt == 32 * ((swq + 1) & 3)) p.trace[id] = clock64(); } } while (0)
         for (int step = 0; step < n_steps; ++step) {
             MMB_TRACE(0);
             // ---- (a) time vectors (warp 0) and the first A row [x_hi, x_lo, onehot(k)] * m
@@ -685,10 +685,10 @@ size_t tc_smem_bytes(const TcLayout& lay) {
     return (size_t)lay.n_bops * 512 + 4096 + (size_t)lay.n_floats * 4 + kJPC * grp + 1024;
 }
 
-template <int DC, int S, int SH, bool GEN>
+template <int DC, int S, int SH, bool GEN, bool TRACE = false>
 int launch(const TcParams& p, cudaStream_t stream) {
     const size_t bytes = tc_smem_bytes(p.lay);
-    auto kern = epic_tc_kernel<DC, S, SH, GEN>;
+    auto kern = epic_tc_kernel<DC, S, SH, GEN, TRACE>;
     if (int rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "tc smem attribute")) return rc;
     const int grid = (p.B + kJPC - 1) / kJPC;
     kern<<<grid, kJPC * 128, bytes, stream>>>(p);
@@ -698,6 +698,9 @@ int launch(const TcParams& p, cudaStream_t stream) {
 template <bool GEN>
 int dispatch(const MmbEpicDims& d, const TcParams& p, cudaStream_t stream) {
     const int sh = d.disc_head_hidden;
+    if constexpr (GEN) {   // the phase trace (tools/tc_trace.py) is a separate instantiation: production kernels carry none of it
+        if (p.trace && d.dim_continuous == 3 && d.vocab_size == 8 && sh == 8) return launch<3, 8, 8, true, true>(p, stream);
+    }
     if (d.dim_continuous == 3 && d.vocab_size == 8 && sh == 8) return launch<3, 8, 8, GEN>(p, stream);
     if (d.dim_continuous == 3 && d.vocab_size == 8 && sh == 0) return launch<3, 8, 0, GEN>(p, stream);
     if (d.dim_continuous == 3 && d.vocab_size == 4 && sh == 4) return launch<3, 4, 4, GEN>(p, stream);
