@@ -248,6 +248,26 @@ __device__ __forceinline__ int telegraph_jump_fast(const float (&lg)[S], int k, 
 }
 
 __device__ __forceinline__ float lrelu_fast(float a) { return fmaxf(a, 0.01f * a); }
+// out = lrelu(a [+ b]) on 16 values with packed fp32 pair instructions (one FADD2 + one FMUL2 + two FMNMX per pair)
+__device__ __forceinline__ void lrelu16(float (&out)[16], const float (&a)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        float t0, t1;
+        fmul2(t0, t1, a[i], a[i + 1], 0.01f, 0.01f);
+        out[i] = fmaxf(a[i], t0);
+        out[i + 1] = fmaxf(a[i + 1], t1);
+    }
+}
+__device__ __forceinline__ void lrelu16_sum(float (&out)[16], const float (&a)[16], const float (&b)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        float s0, s1, t0, t1;
+        fadd2(s0, s1, a[i], a[i + 1], b[i], b[i + 1]);
+        fmul2(t0, t1, s0, s1, 0.01f, 0.01f);
+        out[i] = fmaxf(s0, t0);
+        out[i + 1] = fmaxf(s1, t1);
+    }
+}
 __device__ __forceinline__ float selu_fast(float a) {
     const float scale = 1.0507009873554804934193349852946f;
     const float alpha_scale = 1.0507009873554804934193349852946f * 1.6732632423543772848170429916717f;
@@ -469,8 +489,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             MMB_TRACE(2);
             float acc[16], xl[16];
             tmem_ld16(t_main, acc);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) xl[i] = lrelu_fast(acc[i]);
+            lrelu16(xl, acc);
             if (lay.skip) tmem_st16(t_skip, xl);   // x_local_skip (epic.py:148) parked in TMEM, not in registers
             store_a_row(abuf, r, xl);
             tc_fence_before();
@@ -557,8 +576,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 {
                     float l1[16], bl[16];
                     lds16(jv.bias_l1, bl);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) l1[i] = lrelu_fast(acc[i] + bl[i]);
+                    lrelu16_sum(l1, acc, bl);
                     store_a_row(abuf, r, l1);
                 }
                 tc_fence_before();
@@ -576,12 +594,11 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(6 + 4 * l);
                 tc_fence_after();
                 tmem_ld16(t_main, acc);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) xl[i] = lrelu_fast(acc[i] + xl[i]);  // dead rows: unused garbage, zeroed at pack
+                lrelu16_sum(xl, acc, xl);  // dead rows: unused garbage, zeroed at pack
                 if (lay.skip) {
                     tmem_ld16(t_skip, acc);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) xl[i] += acc[i];
+                    for (int i = 0; i < 16; i += 2) fadd2(xl[i], xl[i + 1], xl[i], xl[i + 1], acc[i], acc[i + 1]);
                 }
                 store_a_row_masked(abuf, r, xl, live);
                 tc_fence_before();
