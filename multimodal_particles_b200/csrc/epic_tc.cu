@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         const int o16 = lane & 15, hf = lane >> 4;
 
         const int n_steps = GENERATE ? p.n_steps : 1;
+        uint32_t uq0 = 0, uq1 = 0, uq2 = 0, uq3 = 0;   // this particle's jump uniforms of the current group of four steps
 #define MMB_TRACE(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && gt == 32 * ((swq + 1) & 3)) p.trace[id] = clock64(); } } while (0)
         for (int step = 0; step < n_steps; ++step) {
             MMB_TRACE(0);
@@ -663,9 +664,29 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 const StepScalars sc{p.dt, __ldg(p.step_tab + step * 4 + 0), __ldg(p.step_tab + step * 4 + 1), 0.0f};
 #pragma unroll
                 for (int c = 0; c < DC; ++c) xs[c] = fmaf(p.dt, h[c], xs[c]);  // h = 0 on dead rows, x there stays 0
+                // One Philox block carries the uniforms of four consecutive particles at one step.  Instead of every lane
+                // recomputing the block of its quad each step, lane j of a quad generates the block of step (s & ~3) + j once per
+                // four steps and a 4 x 4 transpose inside the quad (four shuffles) hands every lane its own word of each step:
+                // the same (seed, jet, step, particle) -> uniform map as philox_uniform(), a quarter of the arithmetic.
+                if (!p.u_jump && (step & 3) == 0) {
+                    const uint4 blk = philox_block(p.seed, p.jet_offset + (uint64_t)jet, 0, step + (r & 3), r >> 2);
+                    uint32_t a0 = blk.x, a1 = blk.y, a2 = blk.z, a3 = blk.w;
+                    {   // exchange 2 x 2 blocks with lane ^ 2
+                        const bool hi = (lane & 2) != 0;
+                        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, hi ? a0 : a2, 2), r1 = __shfl_xor_sync(0xffffffffu, hi ? a1 : a3, 2);
+                        if (hi) { a0 = r0; a1 = r1; } else { a2 = r0; a3 = r1; }
+                    }
+                    {   // then single elements with lane ^ 1
+                        const bool hi = (lane & 1) != 0;
+                        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, hi ? a0 : a1, 1), r1 = __shfl_xor_sync(0xffffffffu, hi ? a2 : a3, 1);
+                        if (hi) { a0 = r0; a2 = r1; } else { a1 = r0; a3 = r1; }
+                    }
+                    uq0 = a0; uq1 = a1; uq2 = a2; uq3 = a3;   // word (r & 3) of the blocks of steps s, s+1, s+2, s+3
+                }
                 if (valid) {
+                    const int ph = step & 3;
                     const float u = p.u_jump ? __ldg(p.u_jump + ((size_t)step * p.B + jet) * N + r)
-                                             : philox_uniform(p.seed, p.jet_offset + (uint64_t)jet, 0, step, r);
+                                             : u01(ph == 0 ? uq0 : ph == 1 ? uq1 : ph == 2 ? uq2 : uq3);
                     kk = telegraph_jump_fast<S>(lg, kk, u, sc) * m;
                 }
                 MMB_TRACE(16);

@@ -85,6 +85,25 @@ def test_generation_bf16_tracks_fp32(case, golden_dir):
     assert torch.equal(e.continuous, c.continuous[1:3]) and torch.equal(e.discrete, c.discrete[1:3])
 
 
+@pytest.mark.parametrize("case", ["mbm_c1", "mbm_n128"])
+def test_in_kernel_philox_equals_injected_philox_uniforms(case, golden_dir):
+    """The generation kernel builds each particle's uniforms from Philox blocks shared inside a lane quad over four steps; the
+    result must be the SAME (seed, jet, step, particle) -> uniform map that mmb_philox_uniforms / the oracle define: a run
+    with in-kernel draws equals a run with those uniforms injected, bit for bit."""
+    from multimodal_particles_b200 import _native
+    z, cfg, model = golden_model(golden_dir, case)
+    mk = lambda: HybridState(None, torch.from_numpy(z["x0"]), torch.from_numpy(z["k0"]).long(), torch.from_numpy(z["mask"]).long())
+    B, N = z["x0"].shape[:2]
+    n_steps = model.step_table().n_steps
+    model.seed = 77
+    u = _native.philox_uniforms(77, 1000, n_steps, B, N, torch.device(DEV))
+    assert np.array_equal(u.cpu().numpy(), ol.philox_uniforms(77, 1000, n_steps, B, N))
+    for precision in ("bf16", "fp32"):
+        a = model.simulate_dynamics(mk(), None, precision=precision, jet_offset=1000)
+        b = model.simulate_dynamics(mk(), None, uniforms=u, precision=precision)
+        assert torch.equal(a.discrete, b.discrete) and torch.equal(a.continuous, b.continuous), precision
+
+
 def w1(a, b):
     a, b = np.sort(np.asarray(a, np.float64)), np.sort(np.asarray(b, np.float64))
     n = min(len(a), len(b))
