@@ -248,6 +248,20 @@ __device__ __forceinline__ int telegraph_jump_fast(const float (&lg)[S], int k, 
 }
 
 __device__ __forceinline__ float lrelu_fast(float a) { return fmaxf(a, 0.01f * a); }
+// init + sum_{k<K} w[k * wstride] * x(k) with four independent accumulators: the serial per-jet global MLP is a chain of such
+// dots on one warp, and a single accumulator makes every one of them K dependent FMAs long
+template <int K, typename XF>
+__device__ __forceinline__ float dot4(float init, const float* w, int wstride, XF x) {
+    float a0 = init, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; k += 4) {
+        a0 = fmaf(w[(k + 0) * wstride], x(k + 0), a0);
+        a1 = fmaf(w[(k + 1) * wstride], x(k + 1), a1);
+        a2 = fmaf(w[(k + 2) * wstride], x(k + 2), a2);
+        a3 = fmaf(w[(k + 3) * wstride], x(k + 3), a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
 // out = lrelu(a [+ b]) on 16 values with packed fp32 pair instructions (one FADD2 + one FMUL2 + two FMNMX per pair)
 __device__ __forceinline__ void lrelu16(float (&out)[16], const float (&a)[16]) {
 #pragma unroll
@@ -520,20 +534,17 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                         float g = hf ? 0.0f : jv.tv_g0[o16];
                         const float* Wsel = s_wf + (hf ? lay.g0s : lay.g0m);
                         const float sc = hf ? 1.0f : inv_cnt;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) g = fmaf(Wsel[k * 16 + o16], sv[k] * sc, g);
+                        g = dot4<16>(g, Wsel + o16, 16, [&](int k) { return sv[k] * sc; });
                         g += __shfl_xor_sync(0xffffffffu, g, 16);
                         if (hf == 0) jv.gv[o16] = lrelu_fast(g);
                         __syncwarp();
                         g = hf ? 0.0f : s_wf[lay.g1b + o16];
-#pragma unroll
-                        for (int kq = 0; kq < 8; ++kq) g = fmaf(s_wf[lay.g1 + (hf * 8 + kq) * 16 + o16], jv.gv[hf * 8 + kq], g);
+                        g = dot4<8>(g, s_wf + lay.g1 + hf * 8 * 16 + o16, 16, [&](int kq) { return jv.gv[hf * 8 + kq]; });
                         g += __shfl_xor_sync(0xffffffffu, g, 16);
                         if (hf == 0) jv.gv2[o16] = lrelu_fast(g);
                         __syncwarp();
                         g = s_wf[lay.g2b + lane];
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) g = fmaf(s_wf[lay.g2 + k * kGP + lane], jv.gv2[k], g);
+                        g = dot4<16>(g, s_wf + lay.g2 + lane, kGP, [&](int k) { return jv.gv2[k]; });
                         g = lrelu_fast(g);
                         jv.xg[lane] = g;
                         jv.skipg[lane] = lay.skip ? g : 0.0f;
@@ -544,18 +555,15 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     {
                         const float* Wsel = Wl + (hf ? lay.l_g1s : lay.l_g1m);
                         const float sc = hf ? 1.0f : inv_cnt;
-#pragma unroll
-                        for (int k = 0; k < 16; ++k) g = fmaf(Wsel[k * 16 + o16], sv[k] * sc, g);
+                        g = dot4<16>(g, Wsel + o16, 16, [&](int k) { return sv[k] * sc; });
                     }
-#pragma unroll
-                    for (int q = 0; q < kGP / 2; ++q) g = fmaf(Wl[lay.l_g1g + (hf * (kGP / 2) + q) * 16 + o16], jv.xg[hf * (kGP / 2) + q], g);
+                    g = dot4<kGP / 2>(g, Wl + lay.l_g1g + hf * (kGP / 2) * 16 + o16, 16, [&](int q) { return jv.xg[hf * (kGP / 2) + q]; });
                     g += __shfl_xor_sync(0xffffffffu, g, 16);
                     __syncwarp();
                     if (hf == 0) jv.gv[o16] = lrelu_fast(g);
                     __syncwarp();
                     g = Wl[lay.l_g2b + lane];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) g = fmaf(Wl[lay.l_g2 + k * kGP + lane], jv.gv[k], g);
+                    g = dot4<16>(g, Wl + lay.l_g2 + lane, kGP, [&](int k) { return jv.gv[k]; });
                     const float xmid = lrelu_fast(g + jv.xg[lane]);
                     __syncwarp();
                     jv.xgmid[lane] = xmid;
@@ -563,8 +571,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     __syncwarp();
                     // per-jet bias of fc_local1: time part + Wl1[:, H:H+G] xg   (epic.py:233-238)
                     g = hf ? 0.0f : jv.tv_l1[l][o16];
-#pragma unroll
-                    for (int q = 0; q < kGP / 2; ++q) g = fmaf(Wl[lay.l_l1g + (hf * (kGP / 2) + q) * 16 + o16], jv.xgmid[hf * (kGP / 2) + q], g);
+                    g = dot4<kGP / 2>(g, Wl + lay.l_l1g + hf * (kGP / 2) * 16 + o16, 16, [&](int q) { return jv.xgmid[hf * (kGP / 2) + q]; });
                     g += __shfl_xor_sync(0xffffffffu, g, 16);
                     if (hf == 0) jv.bias_l1[o16] = g;
                     tc_fence_before();
