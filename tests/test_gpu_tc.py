@@ -144,3 +144,22 @@ def test_distributions_within_seed_to_seed_spread():
     spread = np.abs(freq(fa, la) - freq(fb, lb)).sum()
     assert np.abs(freq(tc, la) - freq(fa, la)).sum() <= spread
     assert (fa.discrete != ba.source_discrete)[la].float().mean() > 0.3
+    # jet-level observables through the fused post-processing kernel (north star: W1 on pT / eta / phi / jet mass and on the
+    # flavor multiplicities): bf16 vs fp32 on the same jets no further apart than two independent fp32 samples
+    from multimodal_particles_b200.epic import as_u8
+    from multimodal_particles_b200.observables import JET_COLUMNS, jet_observables
+    stats = {"mean": [1.2, 0.0, 0.0], "std": [0.35, 0.2, 0.2]}    # de-standardisation to a jet-like scale (pT > 0)
+
+    def obs(st, b):
+        fc_jets = jet_observables(st.continuous.to(DEV).contiguous(), as_u8(st.discrete.to(DEV)), as_u8(b.source_mask.to(DEV)), stats)
+        return fc_jets[1].cpu(), fc_jets[2].cpu().numpy()
+
+    (ca, ja), (cb, jb), (ct, jt) = obs(fa, ba), obs(fb, bb), obs(tc, ba)
+    for name in ("pt", "m", "eta", "phi", "Q_total"):
+        i = JET_COLUMNS.index(name)
+        ok = np.isfinite(ja[:, i]) & np.isfinite(jt[:, i])
+        spread, dist = w1(ja[:, i][np.isfinite(ja[:, i])], jb[:, i][np.isfinite(jb[:, i])]), w1(jt[ok, i], ja[ok, i])
+        assert dist <= spread, f"jet {name}: W1(bf16, fp32) {dist} vs sample-to-sample spread {spread}"
+    for flavor in range(5):   # multiplicity of each flavor per jet
+        ma, mb, mt = [((c[..., 0] == flavor) & live).sum(1).numpy() for c, live in ((ca, la), (cb, lb), (ct, la))]
+        assert w1(mt, ma) <= max(w1(ma, mb), 1e-9), f"flavor {flavor} multiplicity"
