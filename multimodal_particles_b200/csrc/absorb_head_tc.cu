@@ -367,6 +367,29 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         fence_proxy_async();
         __syncthreads();
     };
+    // Raw inputs of a jet (hidden | onehot | x | mask, a few KB) are staged into the upper half of the V tile with 16-byte cp.async
+    // while the previous jet finishes (V is dead after its last PV GEMM), so the first A operand is built from shared memory
+    // instead of waiting on global loads at the head of every jet.
+    float* sStage = reinterpret_cast<float*>(sV + 16384);
+    const int st_oh = p.N * p.H, st_x = st_oh + (p.mode ? p.N * p.S : 0), st_m = st_x + (p.mode == 2 ? p.N * 3 : 0);
+    // every region must be a whole number of 16-byte chunks at a 16-byte aligned offset, for every jet
+    const bool stage_ok = ((p.N * p.H) & 3) == 0 && ((p.N * p.S) & 3) == 0 && ((p.N * 3) & 3) == 0 && (p.N & 15) == 0 &&
+                          (st_m + p.N / 4) * 4 <= 16384 && (reinterpret_cast<uintptr_t>(p.hidden) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0 && (!p.mode || (reinterpret_cast<uintptr_t>(p.onehot) & 15) == 0) &&
+                          (p.mode != 2 || (reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    auto prefetch_inputs = [&](int j) {
+        auto copy16 = [&](int dst_word, const void* src, int n_chunks) {
+            for (int i = tid; i < n_chunks; i += kThreads)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sStage + dst_word + i * 4)),
+                             "l"(reinterpret_cast<const uint8_t*>(src) + (size_t)i * 16) : "memory");
+        };
+        copy16(0, p.hidden + (size_t)j * p.N * p.H, p.N * p.H / 4);
+        if (p.mode) copy16(st_oh, p.onehot + (size_t)j * p.N * p.S, p.N * p.S / 4);
+        if (p.mode == 2) copy16(st_x, p.x + (size_t)j * p.N * 3, p.N * 3 / 4);
+        copy16(st_m, p.mask + (size_t)j * p.N, p.N / 16);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (stage_ok && (int)blockIdx.x < p.B) prefetch_inputs(blockIdx.x);
     // q / k / v biases are handled algebraically: q rides on an extra K-step; k is a per-query constant in the logits
     // (softmax-invariant) and is dropped; v is folded into the proj_out bias because softmax rows sum to one.
 #define STK_TRACE(id) do { if constexpr (TRACE) { if (p.trace && blockIdx.x == 0 && jet == 0 && tid == 32) p.trace[id] = clock64(); } } while (0)
@@ -377,23 +400,30 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         // ---- proj_in: mode 0 [hidden, one_hot(mask)] (absorbing_flows.py:113-118); mode 1 [hidden, onehot]
         //      (transdimensional_model.py:295-303); mode 2 mask * [hidden, onehot, distance to the nearest particle,
         //      its one-hot flag pair] (transdimensional_model.py:341-367)
+        if (stage_ok) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+        }
         if (cq == 0) {
             float row[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) row[i] = 0.0f;
             if (valid) {
                 const int H = p.H;
-                const int m = p.mask[pidx] ? 1 : 0;
-                for (int i = 0; i < H; ++i) row[i] = p.hidden[pidx * H + i];
+                const float* hid = stage_ok ? sStage + r * H : p.hidden + pidx * H;
+                const float* ohp = stage_ok ? sStage + st_oh + r * p.S : p.onehot + pidx * p.S;
+                const float* xj = stage_ok ? sStage + st_x : p.x + (size_t)jet * p.N * 3;
+                const int m = (stage_ok ? reinterpret_cast<const uint8_t*>(sStage + st_m)[r] : p.mask[pidx]) ? 1 : 0;
+                for (int i = 0; i < H; ++i) row[i] = hid[i];
                 if (p.mode == 0) {
                     row[H] = m ? 0.0f : 1.0f;
                     row[H + 1] = m ? 1.0f : 0.0f;
                 } else {
-                    for (int i = 0; i < p.S; ++i) row[H + i] = p.onehot[pidx * p.S + i];
+                    for (int i = 0; i < p.S; ++i) row[H + i] = ohp[i];
                     if (p.mode == 2) {
                         const int near = p.nearest[jet];
-                        const float* xa = p.x + ((size_t)jet * p.N + near) * 3;
-                        const float* xr = p.x + pidx * 3;
+                        const float* xa = xj + near * 3;
+                        const float* xr = xj + r * 3;
                         const float d0 = xa[0] - xr[0], d1 = xa[1] - xr[1], d2 = xa[2] - xr[2];
                         row[H + p.S] = sqrtf((d0 * d0 + d1 * d1) + d2 * d2);
                         row[H + p.S + 1] = r == near ? 1.0f : 0.0f;
@@ -529,6 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             }
             mma_done(0);
             if (blk == 0) STK_TRACE(13);
+            if (stage_ok && blk == nblk - 1 && jet + (int)gridDim.x < p.B) prefetch_inputs(jet + gridDim.x);   // V is dead now
             {
                 float v[CW];  // columns [col0, +CW) of O belong to head cq / HQ: normalised by that head's row sum
                 float tot = 0.0f;
