@@ -35,7 +35,7 @@ namespace mmb {
 namespace {
 
 constexpr int kC = 128;            // transformer width this kernel is built for
-constexpr int kHeads = 2, kDh = 64;
+constexpr int kHeads = 2;            // 64 channels per head
 constexpr int kSlot = 36864;       // bytes per streamed matrix: 32 KB weight tile + 4 KB bias tile
 constexpr int kMaxBlocks = 4;
 
@@ -101,13 +101,6 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N, bool b_mn) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
-}
-// x sigmoid(x) = 0.5 x (1 + tanh(x/2)): one MUFU (tanh.approx) instead of ex2 + rcp
-__device__ __forceinline__ float swish_fast(float a) {
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * a));
-    const float ha = 0.5f * a;
-    return fmaf(ha, t, ha);
 }
 
 // [128 rows x 128 k] bf16 tile, K-major canonical: 8-row groups 2048 B apart (SBO), 16-byte k-chunks
