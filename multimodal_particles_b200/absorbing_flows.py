@@ -209,8 +209,37 @@ class AbsorbingFlow(_ModuleBase):
         return AbsorbingBridgeState(time=torch.full((B, 1), float(table.t[-1])), continuous=x_host,
                                     discrete=k_host.to(k64.dtype).unsqueeze(-1), mask_t=m_host.to(torch.int64).unsqueeze(-1))
 
-    def _training_not_in_scope(self, *args, **kwargs):
-        raise NotImplementedError("training is outside the B200 generation hot path (SURVEY.md §8f N2)")
+    def reshape_time(self, t, x):
+        return t if isinstance(t, (float, int)) else t.reshape(-1, *([1] * (x.dim() - 1)))
 
-    sample_bridges = loss_continuous = loss_discrete = loss_absorbing = _training_not_in_scope
+    @torch.no_grad()
+    def sample_bridges(self, batch, t=None, z=None, u=None, u_absorb=None) -> AbsorbingBridgeState:
+        """Sample stochastic bridges (absorbing_flows.py:187-208): ``t = min_t + (1 - min_t) U``, the continuous and telegraph
+        bridges in one kernel (``mmb_sample_bridges``) and the absorbing bridge's mask (``mmb_absorbing_sample``).
+        ``t`` [B], ``z`` [B,N,3], ``u`` / ``u_absorb`` [B,N] inject the draws."""
+        device = batch.target_continuous.device
+        if device.type != "cuda":
+            if not torch.cuda.is_available():
+                raise _native.MmbError("sample_bridges needs a CUDA device: libmmbridge has no CPU path")
+            device = torch.device("cuda", torch.cuda.current_device())
+        x1 = batch.target_continuous.to(device, torch.float32).contiguous()
+        x0 = batch.source_continuous.to(device, torch.float32).contiguous()
+        B = x1.shape[0]
+        if t is None:
+            t = self.min_t + (1 - self.min_t) * torch.rand(B, device=device)
+        t = t.to(device, torch.float32).contiguous()
+        prep = lambda a: None if a is None else a.to(device, torch.float32).contiguous()
+        off, self._bridges_sampled = getattr(self, "_bridges_sampled", 0), getattr(self, "_bridges_sampled", 0) + B
+        xt, kt = _native.sample_bridges(x0, x1, as_u8(batch.source_discrete.to(device)), as_u8(batch.target_discrete.to(device)), t,
+                                        self.bridge_continuous.sigma, self.bridge_discrete.gamma, self.vocab_size, prep(z), prep(u),
+                                        seed=self.seed, jet_offset=off)
+        time = self.reshape_time(t, x1)
+        mask_t = self.bridge_absorbing.sample(time, batch.target_mask.to(device), uniforms=u_absorb)
+        return AbsorbingBridgeState(time, xt, kt.long().unsqueeze(-1), mask_t)
+
+    def _training_not_in_scope(self, *args, **kwargs):
+        raise NotImplementedError("losses / backward of the absorbing flow are outside the B200 hot path (SURVEY.md §8f N2: "
+                                  "bridge sampling only)")
+
+    loss_continuous = loss_discrete = loss_absorbing = _training_not_in_scope
     training_step = validation_step = configure_optimizers = _training_not_in_scope

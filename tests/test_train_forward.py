@@ -85,6 +85,13 @@ def test_mirror_api_and_full_size_properties():
     assert val.ndim == 0 and torch.isfinite(val)
     with pytest.raises(NotImplementedError):
         model.training_step(batch, 0)
+    from multimodal_particles_b200.absorbing_flows import AbsorbingFlow
+    acfg = AbsorbingConfig()
+    acfg.data.max_num_particles = N
+    flow = AbsorbingFlow(acfg).to("cuda:0")
+    ast = flow.sample_bridges(batch, t=t)
+    assert ast.mask_t.shape == (B, N, 1) and (ast.mask_t.cpu() >= mask).all() and ast.discrete.shape == (B, N, 1)
+    assert torch.equal(ast.discrete[0].cpu(), batch.source_discrete[0]) and ast.continuous.shape == (B, N, 3)
     ab = AbsorbingBridge(AbsorbingConfig())
     mt = ab.sample(t.view(B, 1, 1).cuda(), mask.cuda())
     assert mt.shape == (B, N, 1) and (mt.cpu() >= mask).all() and torch.equal(mt[1].cpu(), mask[1])   # t = 1: only the targets survive
