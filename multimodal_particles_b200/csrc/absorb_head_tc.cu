@@ -506,8 +506,10 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                         for (int j = 0; j < CW; ++j) mx = (key0 + c * CW + j < p.N) ? fmaxf(mx, v[j]) : mx;
                     }
                 }
+                if (blk == 0) STK_TRACE(30);
                 s_rowx[cq][r] = mx;
                 named_bar(1 + NQ + h, 128 * HQ);   // the key slices of a head
+                if (blk == 0) STK_TRACE(31);
 #pragma unroll
                 for (int i = 0; i < HQ; ++i) mx = fmaxf(mx, s_rowx[h * HQ + i][r]);
                 const float sc = 0.125f * 1.4426950408889634f;  // dh^-1/2 * log2(e)
@@ -530,6 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                     store_row<CW>(h ? sQ : sK, r, key0 + c * CW, v);
                 }
                 s_sum[cq][r] = s0 + s1;
+                if (blk == 0) STK_TRACE(32);
                 // the v GEMM finished long ago: its tile joins this phase's fence and barrier
                 mbar_wait(bar_mma2, mma2_phase); mma2_phase ^= 1;
                 tc_fence_after();
@@ -537,9 +540,11 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                 ++wseq;
                 tmem_ldw(dACC + lane_off + col0, v);
                 store_row<CW>(sV, r, col0, v);
+                if (blk == 0) STK_TRACE(33);
             }
             tc_fence_before();
             fence_proxy_async();
+            if (blk == 0) STK_TRACE(34);
             __syncthreads();
             if (blk == 0) STK_TRACE(12);
             if (tid == 0) {                                                  // O_h = P_h V_h, K = 128 keys, N = 64

@@ -21,11 +21,17 @@ for B in (1, 1184):
     tb = gen.time_bias(torch.tensor([0.5])).to(dev)
     for _ in range(2):
         head.forward(hid, m, tb)
-    buf = (ctypes.c_longlong * 32)()
-    _native.load().mmb_debug_read_stack_trace(buf, 32)
+    buf = (ctypes.c_longlong * 48)()
+    _native.load().mmb_debug_read_stack_trace(buf, 48)
     t = list(buf)
     print(f"--- B={B}: first jet of CTA 0 = {t[17] - t[0]} cycles")
     prev = t[0]
     for i in sorted(names):
         print(f"  {names[i]:36s} {t[i] - prev:7d}")
+        prev = t[i]
+    sm = {30: "max pass (2 tcgen05.ld)", 31: "max exchange barrier", 32: "exp pass (2 tcgen05.ld, P tile)", 33: "V tile", 34: "fences", 12: "block barrier"}
+    print("  inside the softmax phase of block 0:")
+    prev = t[11]
+    for i in (30, 31, 32, 33, 34, 12):
+        print(f"    {sm[i]:36s} {t[i] - prev:7d}")
         prev = t[i]
