@@ -14,6 +14,10 @@ __global__ void k(float* out, int iters) {
             if (OP == 1) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
             if (OP == 2) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
             if (OP == 3) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(a[i]));
+            if (OP == 5) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(*reinterpret_cast<unsigned*>(&a[i])));
+            if (OP == 6) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(*reinterpret_cast<unsigned*>(&a[i])));
+            if (OP == 7) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(*reinterpret_cast<unsigned*>(&a[i])));
+            if (OP == 8) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(*reinterpret_cast<unsigned*>(&a[i])));
         }
         if (OP == 4) {
 #pragma unroll
@@ -41,5 +45,6 @@ void run(const char* name, int per_iter) {
 }
 int main() {
     run<0>("tanh.approx.f32", 8); run<1>("ex2.approx.ftz.f32", 8); run<2>("rcp.approx.ftz.f32", 8); run<3>("fma.rn.f32", 8); run<4>("fma.rn.f32x2 (pairs)", 8);
+    run<5>("tanh.approx.bf16x2 (x2)", 16); run<6>("ex2.approx.bf16x2 (x2)", 16); run<7>("tanh.approx.f16x2 (x2)", 16); run<8>("ex2.approx.f16x2 (x2)", 16);
     return 0;
 }
