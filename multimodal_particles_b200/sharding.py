@@ -1,8 +1,8 @@
 """Multi-GPU layer of the generation path: jets are independent, so ranks
 generate disjoint slices with no data-path collective.  The only exchanges happen once per batch,
 after generation: an all-gather of the generated jets in the compact layout (fp32 features, uint8
-tokens, uint8 masks = 1 792 B / jet at N=128) and an all-reduce (SUM, int64) of the validation
-histograms.  One process per GPU; ``torch.distributed`` is the plumbing (NCCL on GPUs, gloo in the
+tokens, uint8 masks = 1 792 B / jet at N=128; one collective when the state lives in a ``PackedJets``
+allocation) and an all-reduce (SUM, int64) of the validation histograms.  One process per GPU; ``torch.distributed`` is the plumbing (NCCL on GPUs, gloo in the
 CPU tests).  The reference has no distributed code at all: this layer is new.
 """
 from dataclasses import dataclass
@@ -33,6 +33,51 @@ class GatherBuffers:
         self.x = torch.empty(world * batch, n, dim_continuous, device=device, dtype=torch.float32)
         self.k = torch.empty(world * batch, n, device=device, dtype=torch.uint8)
         self.mask = torch.empty(world * batch, n, device=device, dtype=torch.uint8)
+
+
+class PackedJets:
+    """One contiguous allocation for the compact state of a batch — [x fp32 | tokens u8 | mask u8], 14 B per particle — so the
+    per-batch exchange is ONE all-gather instead of three.  ``x`` / ``k`` / ``mask`` are views the kernels work on in place."""
+
+    def __init__(self, batch: int, n: int, dim_continuous: int, device):
+        self.batch, self.n, self.dc = batch, n, dim_continuous
+        nx, nk = batch * n * dim_continuous * 4, batch * n
+        self.bytes = torch.empty(nx + 2 * nk, dtype=torch.uint8, device=device)
+        self.x = self.bytes[:nx].view(torch.float32).view(batch, n, dim_continuous)
+        self.k = self.bytes[nx:nx + nk].view(batch, n)
+        self.mask = self.bytes[nx + nk:].view(batch, n)
+
+    def load(self, x, k_u8, mask_u8):
+        self.x.copy_(x), self.k.copy_(k_u8), self.mask.copy_(mask_u8)
+        return self
+
+
+class PackedGather:
+    """Receive side of the packed all-gather: ``world`` PackedJets-shaped slices of one buffer."""
+
+    def __init__(self, batch: int, n: int, dim_continuous: int, world: int, device):
+        self.world, self.batch, self.n, self.dc = world, batch, n, dim_continuous
+        self.nx, self.nk = batch * n * dim_continuous * 4, batch * n
+        self.bytes = torch.empty(world, self.nx + 2 * self.nk, dtype=torch.uint8, device=device)
+
+    def gather(self, packed: PackedJets, counts=None):
+        """One all-gather of the packed jets, one all-reduce (SUM) of the histogram counts."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            self.bytes[0].copy_(packed.bytes)
+            return counts
+        dist.all_gather_into_tensor(self.bytes.view(-1), packed.bytes)
+        if counts is not None:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        return counts
+
+    def x(self, rank: int) -> torch.Tensor:
+        return self.bytes[rank, :self.nx].view(torch.float32).view(self.batch, self.n, self.dc)
+
+    def k(self, rank: int) -> torch.Tensor:
+        return self.bytes[rank, self.nx:self.nx + self.nk].view(self.batch, self.n)
+
+    def mask(self, rank: int) -> torch.Tensor:
+        return self.bytes[rank, self.nx + self.nk:].view(self.batch, self.n)
 
 
 class ValidationHistograms:

@@ -52,6 +52,14 @@ def _worker(rank, world, port, total, out_path):
         counts = hist.accumulate(x, k, m)
         buf = sharding.GatherBuffers(hi - lo, 32, 3, world, "cpu")
         counts = sharding.gather_and_reduce(buf, x, k, m, counts)
+        # the same exchange as ONE collective on the packed layout [x | tokens | mask]
+        pk = sharding.PackedJets(hi - lo, 32, 3, "cpu").load(x, k, m)
+        pg = sharding.PackedGather(hi - lo, 32, 3, world, "cpu")
+        pg.gather(pk)
+        px = torch.cat([pg.x(r) for r in range(world)])
+        pk_ = torch.cat([pg.k(r) for r in range(world)])
+        pm = torch.cat([pg.mask(r) for r in range(world)])
+        assert torch.equal(px, buf.x) and torch.equal(pk_, buf.k) and torch.equal(pm, buf.mask)
         if rank == 0:
             np.savez(out_path, x=buf.x.numpy(), k=buf.k.numpy(), mask=buf.mask.numpy(), counts=counts.numpy())
     finally:
