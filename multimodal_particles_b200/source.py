@@ -21,16 +21,22 @@ def multiplicity_cdf(target_multiplicity, max_num_particles: int) -> np.ndarray:
 
 def sample_source_state(num_jets: int, max_num_particles: int = 128, target_multiplicity=None, min_num_particles: int = 0,
                         scale: float = 1.0, cat_probs=(0.2, 0.2, 0.2, 0.2, 0.2), device="cuda", seed: int = 0, jet_offset: int = 0,
-                        compact: bool = False):
+                        compact: bool = False, out=None):
     """-> HybridState(None, continuous [B,N,3] f32, discrete [B,N,1] int64, absorbing = mask [B,N,1] int64) on ``device``
-    (``compact=True``: the uint8 [B,N] tensors the kernels consume, no widening)."""
+    (``compact=True``: the uint8 [B,N] tensors the kernels consume, no widening; ``out=(x, k, mask)``: write into existing
+    device tensors, e.g. the views of a ``sharding.PackedJets``)."""
     device = torch.device(device)
     if device.type != "cuda":
         raise _native.MmbError("sample_source_state needs a CUDA device: libmmbridge has no CPU path")
     B, N = num_jets, max_num_particles
-    x = torch.empty(B, N, 3, device=device)
-    k = torch.empty(B, N, dtype=torch.uint8, device=device)
-    mask = torch.empty(B, N, dtype=torch.uint8, device=device)
+    if out is not None:
+        x, k, mask = out
+        _native._require_cuda(x, k, mask)
+        assert x.shape == (B, N, 3) and k.shape == (B, N) and mask.shape == (B, N)
+    else:
+        x = torch.empty(B, N, 3, device=device)
+        k = torch.empty(B, N, dtype=torch.uint8, device=device)
+        mask = torch.empty(B, N, dtype=torch.uint8, device=device)
     cdf = None
     if target_multiplicity is not None and min_num_particles != max_num_particles:   # sample_masks' two "all ones" exits
         cdf = torch.from_numpy(multiplicity_cdf(target_multiplicity, N)).to(device)

@@ -7,7 +7,7 @@ Each rank owns a contiguous slice of the jets (sharding.shard_range; its start i
 depend on the number of GPUs) and walks it in micro-batches of 4096: source state on the device (mmb_sample_source), the fused
 99-step generation (mmb_generate), post-processing + jet observables (mmb_jet_observables) and the validation histograms
 (mmb_validation_histograms) accumulated into per-GPU int64 counts.  Collectives, once per micro-batch and overlapped with the
-next one on a side stream: NCCL all-gather of the generated jets (1 792 B / jet) and, at the end, one all-reduce of the
+next one on a side stream: ONE NCCL all-gather of the packed micro-batch (1 792 B / jet) and, at the end, one all-reduce of the
 histograms and of the jet-observable sums.  Prints one JSON line on rank 0 (device time by CUDA events, max over ranks)."""
 import argparse
 import json
@@ -47,7 +47,8 @@ def main():
     counts = torch.zeros(hist.size, dtype=torch.int64, device=dev)
     jet_sums = torch.zeros(11, dtype=torch.float64, device=dev)
     stats = {"mean": [1.2, 0.0, 0.0], "std": [0.35, 0.2, 0.2]}
-    bufs = [sharding.GatherBuffers(MB, N, 3, world, dev) for _ in range(2)] if world > 1 else None
+    packs = [sharding.PackedJets(MB, N, 3, dev) for _ in range(3)]      # state of a micro-batch: [x | tokens | mask], one allocation
+    recv = [sharding.PackedGather(MB, N, 3, world, dev) for _ in range(2)] if world > 1 else None
     side = torch.cuda.Stream(device=dev)
     main_s = torch.cuda.current_stream(dev)
 
@@ -55,7 +56,12 @@ def main():
         pending = None
         for i, start in enumerate(range(n_jets_from, n_jets_to, MB)):
             B = min(MB, n_jets_to - start)
-            x, k, m = sample_source_state(B, N, target_multiplicity=mult_hist, min_num_particles=0, seed=7, jet_offset=start, compact=True)
+            pk = packs[i % 3]
+            if B == MB:
+                x, k, m = sample_source_state(B, N, target_multiplicity=mult_hist, min_num_particles=0, seed=7, jet_offset=start, compact=True,
+                                              out=(pk.x, pk.k, pk.mask))
+            else:
+                x, k, m = sample_source_state(B, N, target_multiplicity=mult_hist, min_num_particles=0, seed=7, jet_offset=start, compact=True)
             native.generate(x, k, m, table, seed=11, jet_offset=start, precision="bf16")
             _, _, jets = jet_observables(x, k, m, stats, want_particles=False)
             counts.add_(hist.accumulate(x, k, m))
@@ -64,9 +70,8 @@ def main():
                 ev = torch.cuda.Event(); ev.record(main_s)
                 with torch.cuda.stream(side):
                     side.wait_event(ev)
-                    b = bufs[i & 1]
-                    dist.all_gather_into_tensor(b.x, x); dist.all_gather_into_tensor(b.k, k); dist.all_gather_into_tensor(b.mask, m)
-                    x.record_stream(side); k.record_stream(side); m.record_stream(side)
+                    recv[i & 1].gather(pk)          # one all-gather of the packed micro-batch
+                    pk.bytes.record_stream(side)
                 pending = side
         if pending is not None:
             main_s.wait_stream(side)
