@@ -273,8 +273,10 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         const uint32_t wb = w_addr(wseq & 1);
         mbar_wait((wseq & 1) ? bar_full1 : bar_full0, (wseq >> 1) & 1);
         tc_fence_after();
-        for (int j = 0; j < nk; ++j)
-            umma(d, smem_desc(a_addr + j * 256, 128, a_sbo), smem_desc(wb + j * 256, 128, 2048), idesc128, (accumulate || j > 0) ? 1u : 0u);
+        // descriptors advance by 256 B per K-step: +16 in the (address >> 4) field, no per-step re-encoding
+        const uint64_t ad = smem_desc(a_addr, 128, a_sbo), wd = smem_desc(wb, 128, 2048);
+#pragma unroll 8
+        for (int j = 0; j < nk; ++j) umma(d, ad + (uint64_t)(j * 16), wd + (uint64_t)(j * 16), idesc128, (accumulate || j > 0) ? 1u : 0u);
         if (bias) umma(d, ones_desc, smem_desc(b_addr(wseq & 1), 128, 256), idesc128, 1u);
         umma_commit(bar_done);
     };
@@ -285,8 +287,9 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         mbar_wait((wseq & 1) ? bar_full1 : bar_full0, (wseq >> 1) & 1);
         mbar_wait(((wseq + 1) & 1) ? bar_full1 : bar_full0, ((wseq + 1) >> 1) & 1);
         tc_fence_after();
-        for (int j = 0; j < 8; ++j)
-            umma(d, smem_desc(a_addr + j * 256, 128, 2048), smem_desc(w_addr(0) + j * 256, 128, 2048), idesc256, j > 0 ? 1u : 0u);
+        const uint64_t ad = smem_desc(a_addr, 128, 2048), wd = smem_desc(w_addr(0), 128, 2048);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) umma(d, ad + (uint64_t)(j * 16), wd + (uint64_t)(j * 16), idesc256, j > 0 ? 1u : 0u);
         umma(d + (wseq & 1) * 128, ones_desc, smem_desc(b_addr(wseq & 1), 128, 256), idesc128, 1u);
         umma_commit(bar_mma);
     };
@@ -478,10 +481,12 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             if (blk == 0) STK_TRACE(9);
             if (tid == 0) {                                                  // S_h = Q_h K_h^T, K = 64
                 tc_fence_after();
+                const uint64_t qd = smem_desc(aQ, 128, 2048), kd = smem_desc(aK, 128, 2048);
+#pragma unroll
                 for (int h = 0; h < kHeads; ++h)
-                    for (int j = 0; j < 4; ++j)
-                        umma(h ? dS1 : dS0, smem_desc(aQ + h * 1024 + j * 256, 128, 2048), smem_desc(aK + h * 1024 + j * 256, 128, 2048),
-                             idesc128, j > 0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)   // head h = K-steps 4h .. 4h+3 of the Q and K tiles (1024 B = 64 in the address field)
+                        umma(h ? dS1 : dS0, qd + (uint64_t)(h * 64 + j * 16), kd + (uint64_t)(h * 64 + j * 16), idesc128, j > 0);
                 umma_commit(bar_mma);
                 gemm_w(dACC, aA, 2048, 8, false, false, bar_mma2);            // v: runs under the softmax, its own barrier
             }
@@ -549,10 +554,14 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             if (blk == 0) STK_TRACE(12);
             if (tid == 0) {                                                  // O_h = P_h V_h, K = 128 keys, N = 64
                 tc_fence_after();
-                for (int hh = 0; hh < kHeads; ++hh)
-                    for (int j = 0; j < 8; ++j)
-                        umma(dACC + hh * 64, smem_desc((hh ? aQ : aK) + j * 256, 128, 2048),
-                             smem_desc(aV + hh * 1024 + j * 4096, 2048, 128), idesc64mn, j > 0);
+                const uint64_t vd = smem_desc(aV, 2048, 128);
+#pragma unroll
+                for (int hh = 0; hh < kHeads; ++hh) {
+                    const uint64_t pd = smem_desc(hh ? aQ : aK, 128, 2048);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)   // V MN-major: head hh starts 1024 B in, a K-step of 16 keys is 4096 B
+                        umma(dACC + hh * 64, pd + (uint64_t)(j * 16), vd + (uint64_t)(hh * 64 + j * 256), idesc64mn, j > 0);
+                }
                 umma_commit(bar_mma);
             }
             mma_done(0);
