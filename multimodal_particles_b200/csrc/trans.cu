@@ -317,8 +317,67 @@ __device__ __forceinline__ float nan_to_num(float a) {   // torch.nan_to_num: Na
 }
 __device__ __forceinline__ float softplus(float a) { return a > 20.0f ? a : log1pf(expf(a)); }
 
-// One WARP per jet: lane l serves the particle slots l, l+32, l+64, l+96, so the three centre-of-mass reductions are warp
-// shuffles and no block-wide barrier sits in the pass; four jets per 128-thread block.  Dead slots (n >= dims) hold zeros —
+// The one-hot block of the update is purely element-wise (sampler.py:221-231 on the one-hot slots): one thread per particle slot
+// over a flat grid, 96 B per live slot (one-hot r+w 64, logits 32), two Philox blocks for its eight normals.  It runs BEFORE the
+// continuous kernel below (which updates dims and writes the one-hot row of a newborn particle into slot `dims`).
+template <int S>
+__global__ void __launch_bounds__(256) trans_sampler_onehot_kernel(float* __restrict__ onehot, const int32_t* __restrict__ dims,
+                                                                   const float* __restrict__ logits, float c_decay, float cs, float c_noise,
+                                                                   const float* __restrict__ z_diff, uint64_t seed, uint64_t jet_offset,
+                                                                   int step, int B, int N) {
+    constexpr int F = 3 + S;
+    const size_t pi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= (size_t)B * N) return;
+    const int b = (int)(pi / N), n = (int)(pi % N);
+    if (n >= __ldg(dims + b)) return;
+    const bool noisy = c_noise != 0.0f;
+    float oh[S], lg[S], z[8];
+    if constexpr (S % 4 == 0) {
+#pragma unroll
+        for (int s2 = 0; s2 < S; s2 += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(onehot + pi * S + s2);
+            const float4 l = __ldg(reinterpret_cast<const float4*>(logits + pi * S + s2));
+            oh[s2] = a.x; oh[s2 + 1] = a.y; oh[s2 + 2] = a.z; oh[s2 + 3] = a.w;
+            lg[s2] = l.x; lg[s2 + 1] = l.y; lg[s2 + 2] = l.z; lg[s2 + 3] = l.w;
+        }
+    } else {
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2) { oh[s2] = onehot[pi * S + s2]; lg[s2] = __ldg(logits + pi * S + s2); }
+    }
+    if (noisy) {
+        if (z_diff) {
+            const float* zb = z_diff + (size_t)b * N * F;
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) z[s2] = __ldg(zb + (size_t)N * 3 + n * S + s2);
+        } else {
+            const uint64_t jet = jet_offset + (uint64_t)b;
+            const uint4 r0 = philox_block(seed, jet, 3, step, n);
+            box_muller(r0.x, r0.y, z[0], z[1]);
+            box_muller(r0.z, r0.w, z[2], z[3]);
+            if constexpr (S > 4) {
+                const uint4 r1 = philox_block(seed, jet, 4, step, n);
+                box_muller(r1.x, r1.y, z[4], z[5]);
+                box_muller(r1.z, r1.w, z[6], z[7]);
+            }
+        }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < S; ++s2) {
+        float a = c_decay * oh[s2] + cs * lg[s2];
+        if (noisy) a = a + c_noise * z[s2];
+        oh[s2] = nan_to_num(a);
+    }
+    if constexpr (S % 4 == 0) {
+#pragma unroll
+        for (int s2 = 0; s2 < S; s2 += 4) *reinterpret_cast<float4*>(onehot + pi * S + s2) = make_float4(oh[s2], oh[s2 + 1], oh[s2 + 2], oh[s2 + 3]);
+    } else {
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2) onehot[pi * S + s2] = oh[s2];
+    }
+}
+
+// Continuous block, one WARP per jet: lane l serves the particle slots l, l+32, l+64, l+96, so the three centre-of-mass reductions
+// are warp shuffles and no block-wide barrier sits in the pass; four jets per 128-thread block.  (The one-hot block is the kernel above.)  Dead slots (n >= dims) hold zeros —
 // the sampler's invariant, asserted by the reference in adjust_st_batch (jets_dataloader.py:451-452) — and stay zero under the
 // update, so they are neither read nor written: the pass moves 133 B per LIVE particle-step.
 template <int S>
@@ -341,55 +400,6 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
     const float* zb = z_diff ? z_diff + (size_t)b * N * F : nullptr;
     const bool noisy = c_noise != 0.0f;
     const float cs = -(c_score * inv_std);   // c_score * -(inv_std * D): one rounding apart from the reference order
-    // ---- one-hot block: purely element-wise (sampler.py:221-231 on the one-hot slots; the birth fills slot `dim`)
-#pragma unroll
-    for (int q = 0; q < SL; ++q) {
-        const int n = lane + 32 * q;
-        const size_t pi = (size_t)b * N + n;
-        if (n < dim) {
-            float oh[S], lg[S], z[8];
-            if constexpr (S % 4 == 0) {
-#pragma unroll
-                for (int s2 = 0; s2 < S; s2 += 4) {
-                    const float4 a = *reinterpret_cast<const float4*>(onehot + pi * S + s2);
-                    const float4 l = __ldg(reinterpret_cast<const float4*>(logits + pi * S + s2));
-                    oh[s2] = a.x; oh[s2 + 1] = a.y; oh[s2 + 2] = a.z; oh[s2 + 3] = a.w;
-                    lg[s2] = l.x; lg[s2 + 1] = l.y; lg[s2 + 2] = l.z; lg[s2 + 3] = l.w;
-                }
-            } else {
-#pragma unroll
-                for (int s2 = 0; s2 < S; ++s2) { oh[s2] = onehot[pi * S + s2]; lg[s2] = __ldg(logits + pi * S + s2); }
-            }
-            if (noisy) {
-                if (zb) {
-#pragma unroll
-                    for (int s2 = 0; s2 < S; ++s2) z[s2] = __ldg(zb + (size_t)N * 3 + n * S + s2);
-                } else {
-                    const uint4 r0 = philox_block(seed, jet, 3, step, n);
-                    box_muller(r0.x, r0.y, z[0], z[1]);
-                    box_muller(r0.z, r0.w, z[2], z[3]);
-                    if constexpr (S > 4) {
-                        const uint4 r1 = philox_block(seed, jet, 4, step, n);
-                        box_muller(r1.x, r1.y, z[4], z[5]);
-                        box_muller(r1.z, r1.w, z[6], z[7]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int s2 = 0; s2 < S; ++s2) {
-                float a = c_decay * oh[s2] + cs * lg[s2];
-                if (noisy) a = a + c_noise * z[s2];
-                oh[s2] = nan_to_num(a);
-            }
-            if constexpr (S % 4 == 0) {
-#pragma unroll
-                for (int s2 = 0; s2 < S; s2 += 4) *reinterpret_cast<float4*>(onehot + pi * S + s2) = make_float4(oh[s2], oh[s2 + 1], oh[s2 + 2], oh[s2 + 3]);
-            } else {
-#pragma unroll
-                for (int s2 = 0; s2 < S; ++s2) onehot[pi * S + s2] = oh[s2];
-            }
-        }
-    }
     // ---- continuous block: Euler-Maruyama with the noise centred over the live particles, then centre-of-mass removal,
     //      the birth, and a second centre-of-mass removal (sampler.py:221-255, jets_dataloader.py:433-478)
     float xs[SL][3], zc[SL][3];
@@ -654,6 +664,8 @@ static int launch_sampler_update(float* x, float* onehot, int32_t* dims, const f
                                  uint64_t jet_offset, int step, int B, int N, int S, cudaStream_t s) {
     if (N > 128 || N < 1) return fail(MMB_EUNSUPPORTED, "sampler update handles 1..128 particle slots per jet");
 #define MMB_UPD(SV)                                                                                                                  \
+    trans_sampler_onehot_kernel<SV><<<(unsigned)(((size_t)B * N + 255) / 256), 256, 0, s>>>(onehot, dims, logits, c_decay,             \
+                                                                -(c_score * inv_std), c_noise, z_diff, seed, jet_offset, step, B, N);   \
     trans_sampler_update_kernel<SV><<<(B + 3) / 4, 128, 0, s>>>(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score,  \
                                                                 c_noise, inv_std, jump_dt, z_diff, u_jump, z_new, seed, jet_offset, step, B, N)
     switch (S) {

@@ -89,7 +89,7 @@ print(json.dumps({"workload": f"C3 transepic: B={B}, N=128, S=8, bf16 stacks (2 
                   "roofline_forward": {"kernel": "mmb_trans_forward (2 x absorb_head_tc_kernel + trunk)", "bound": "tensor", "achieved": tf,
                                        "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tf / pk["bf16"],
                                        "algorithmic_flops_per_launch": flops, "peak_source": pk["src"]},
-                  "roofline_update": {"kernel": "mmb::trans_sampler_update_kernel<8>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
+                  "roofline_update": {"kernel": "mmb::trans_sampler_onehot_kernel<8> + trans_sampler_update_kernel<8>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
                                       "unit": "GB/s", "frac": gbs / pk["hbm"], "ms_per_launch": upd_ms, "jets": BU, "l2": "inputs larger than L2, 10 launches per event pair",
                                       "algorithmic_bytes_per_launch": upd_bytes, "peak_source": pk["src"]},
                   "sampler": {"dt": 0.02, "evaluations": n_eval, "ms_per_run": smp_ms, "jets_per_s": B / (smp_ms * 1e-3),
