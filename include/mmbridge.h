@@ -329,31 +329,41 @@ int mmb_trans_forward(const MmbEpicModel* trunk, const MmbTransHeads* heads,
                       void* workspace, size_t workspace_bytes, int precision, void* stream);
 
 /*
- * JumpSampler.sample (mp/models/generative/transdimensional/sampler.py:157-324; live subset: uniform dt, no corrector,
- * no conditioning, sample_near_atom) — reverse VP-SDE Euler-Maruyama on the flat latents with a birth jump per step.
- * The per-step scalars are a host table computed with torch fp32 ops in the reference's order (all jets share ts):
- *   ts, c_decay = 2 - sqrt(1 - beta dt), c_score = beta dt, c_noise = sqrt(beta dt) (0 where the reference adds no
- *   noise: no_noise_final_step), inv_std = 1/clamp(std(ts), 1e-3), jump_dt = dt.
+ * JumpSampler.sample (mp/models/generative/transdimensional/sampler.py:157-324; sample_near_atom, no conditioning) —
+ * reverse VP-SDE Euler-Maruyama on the flat latents with a birth jump per step, optionally followed by Langevin
+ * corrector evaluations (sampler.py:258-282) with their own birth/death jumps (do_jump_corrector, :285-312).
+ * The schedule is a host table with one ROW PER NETWORK EVALUATION, computed with torch fp32 ops in the reference's
+ * order (all jets share ts):
+ *   predictor row (kind 0): ts, c_decay = 2 - sqrt(1 - beta dt), c_score = beta dt, c_noise = sqrt(beta dt) (0 where
+ *     the reference adds no noise: no_noise_final_step), inv_std = 1/clamp(std(ts), 1e-3);
+ *   corrector row (kind 1): ts = t - dt, c_score = alpha = 1 - dt beta(t - dt), c_noise = 1 (0: the final corrector
+ *     under no_noise_final_step), inv_std at t - dt, death_prob = forward_rate(t - dt) dt; c_decay unused.  The step
+ *     size (corrector_snr * mean_b|noise_b| / mean_b|score_b|)^2 * 2 alpha is a batch statistic computed on the device.
+ * jump_dt = dt.  kind == NULL means predictor rows only.
  * State in/out: x [B,N,3], onehot [B,N,S], dims [B] int32 — the caller initialises them like sampler.py:170-183
  * (x_T ~ N(0,I), dims = 1, delete_dims, adjust_st_batch) or passes any intermediate state.
- * Noise: either injected (device pointers; parity runs)
+ * Noise: either injected (device pointers indexed by row; parity runs)
  *   z_diff [n_steps][B][N*(3+S)] (rnd.randn_like(xt)), u_near [n_steps][B], u_jump [n_steps][B],
- *   z_new [n_steps][B][3+S] (the draw that lands in the new slot),
- * or all NULL: in-kernel Philox4x32-10 keyed by (seed, jet_offset + jet, step, element) + Box-Muller.
+ *   z_new [n_steps][B][3+S] (the draw that lands in the new slot), u_death [n_steps][B] (jump corrector only, else NULL),
+ * or all NULL: in-kernel Philox4x32-10 keyed by (seed, jet_offset + jet, row, element) + Box-Muller.
  */
 typedef struct MmbJumpSchedule {
-    int32_t n_steps;
+    int32_t n_steps;       /* rows = network evaluations */
     const float* ts;       /* HOST [n_steps] */
     const float* c_decay;  /* HOST [n_steps] */
     const float* c_score;  /* HOST [n_steps] */
     const float* c_noise;  /* HOST [n_steps] */
     const float* inv_std;  /* HOST [n_steps] */
     float jump_dt;
+    const uint8_t* kind;     /* HOST [n_steps] or NULL */
+    const float* death_prob; /* HOST [n_steps] or NULL (needed when jump_corrector) */
+    float corrector_snr;
+    int32_t jump_corrector;
 } MmbJumpSchedule;
 size_t mmb_trans_sample_workspace_bytes(const MmbEpicModel* trunk, const MmbTransHeads* heads, int B, int N);
 int mmb_trans_sample(const MmbEpicModel* trunk, const MmbTransHeads* heads, float* x, float* onehot, int32_t* dims,
                      const MmbJumpSchedule* schedule, const MmbForwardRate* forward_rate,
-                     const float* z_diff, const float* u_near, const float* u_jump, const float* z_new,
+                     const float* z_diff, const float* u_near, const float* u_jump, const float* z_new, const float* u_death,
                      uint64_t seed, uint64_t jet_offset, int B, int N,
                      void* workspace, size_t workspace_bytes, int precision, void* stream);
 /* one sampler update alone (sampler.py:221-255 + adjust_st_batch, jets_dataloader.py:433-478): the fused,
@@ -364,6 +374,15 @@ int mmb_trans_sampler_update(float* x, float* onehot, int32_t* dims, const float
                              float c_decay, float c_score, float c_noise, float inv_std, float jump_dt,
                              const float* z_diff, const float* u_jump, const float* z_new,
                              uint64_t seed, uint64_t jet_offset, int step, int B, int N, int S, void* stream);
+/* one Langevin corrector update alone (sampler.py:258-282; with jump_corrector also :285-312): batch norms of the
+ * score and of the centred noise -> step size -> increment on the slots the predictor step's mask covers
+ * (mask_dims [B], NULL = dims) -> centre-of-mass removal -> optional birth/death.  alpha = 1 - dt beta(t - dt);
+ * scratch: 2B + 4 device floats (scratch[2B+3] returns the step size). */
+int mmb_trans_corrector_update(float* x, float* onehot, int32_t* dims, const int32_t* mask_dims, const float* v, const float* logits,
+                               const float* rate, const float* new_mean, const float* new_std, float alpha, int noise_on, float inv_std,
+                               float corrector_snr, float jump_dt, int jump_corrector, float death_prob, const float* z_diff,
+                               const float* u_jump, const float* u_death, const float* z_new, uint64_t seed, uint64_t jet_offset, int step,
+                               int B, int N, int S, float* scratch, void* stream);
 
 /*
  * Validation histograms of a generated batch, ACCUMULATED into counts (caller zeroes it): the

@@ -56,13 +56,22 @@ class JumpSchedule(ctypes.Structure):
     """ctypes image of ``MmbJumpSchedule``; keeps the numpy arrays it points into alive."""
 
     _fields_ = [("n_steps", ctypes.c_int32), ("ts", _fptr), ("c_decay", _fptr), ("c_score", _fptr), ("c_noise", _fptr),
-                ("inv_std", _fptr), ("jump_dt", ctypes.c_float)]
+                ("inv_std", _fptr), ("jump_dt", ctypes.c_float), ("kind", ctypes.POINTER(ctypes.c_uint8)), ("death_prob", _fptr),
+                ("corrector_snr", ctypes.c_float), ("jump_corrector", ctypes.c_int32)]
 
     @classmethod
     def from_schedule(cls, sched):
         import numpy as np
         keep = [np.ascontiguousarray(getattr(sched, n), dtype=np.float32) for n in ("ts", "c_decay", "c_score", "c_noise", "inv_std")]
-        out = cls(int(sched.n_steps), *[a.ctypes.data_as(_fptr) for a in keep], float(sched.jump_dt))
+        kind = getattr(sched, "kind", None)
+        kind_p, death_p = None, None
+        if kind is not None and np.any(kind):
+            kind = np.ascontiguousarray(kind, dtype=np.uint8)
+            death = np.ascontiguousarray(sched.death_prob, dtype=np.float32)
+            keep += [kind, death]
+            kind_p, death_p = kind.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), death.ctypes.data_as(_fptr)
+        out = cls(int(sched.n_steps), *[a.ctypes.data_as(_fptr) for a in keep[:5]], float(sched.jump_dt), kind_p, death_p,
+                  float(getattr(sched, "corrector_snr", 0.0)), int(bool(getattr(sched, "jump_corrector", False))))
         out._keep = keep
         return out
 
@@ -103,9 +112,11 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "mmb_trans_sample_workspace_bytes": (_sz, [_vp, _vp, _i, _i]),
     "mmb_trans_sample": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(JumpSchedule), ctypes.POINTER(ForwardRate),
-                              _vp, _vp, _vp, _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
+                              _vp, _vp, _vp, _vp, _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
     "mmb_trans_sampler_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _vp, _vp, _vp,
                                       _u64, _u64, _i, _i, _i, _i, _vp]),
+    "mmb_trans_corrector_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _f, _f, _f, _i, _f, _vp, _vp, _vp, _vp,
+                                        _u64, _u64, _i, _i, _i, _i, _vp, _vp]),
 }
 
 
@@ -329,16 +340,16 @@ def trans_sample(trunk: EpicModel, heads: TransHeads, x, onehot, dims, sched, fo
     assert dims.dtype == torch.int32
     B, N, _ = x.shape
     dev = x.device
-    get = lambda name: _f32(getattr(noise, name), dev) if noise is not None else None
-    z_diff, u_near, u_jump, z_new = get("z_diff"), get("u_near"), get("u_jump"), get("z_new")
+    get = lambda name: _f32(getattr(noise, name), dev) if noise is not None and getattr(noise, name, None) is not None else None
+    z_diff, u_near, u_jump, z_new, u_death = get("z_diff"), get("u_near"), get("u_jump"), get("z_new"), get("u_death")
     lib = load()
     need = lib.mmb_trans_sample_workspace_bytes(trunk._handle, heads._handle, B, N)
     ws = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
     csched = JumpSchedule.from_schedule(sched)
     with torch.cuda.device(dev):
         check(lib.mmb_trans_sample(trunk._handle, heads._handle, _ptr(x), _ptr(onehot), _ptr(dims), ctypes.byref(csched),
-                                   ctypes.byref(forward_rate), _ptr(z_diff), _ptr(u_near), _ptr(u_jump), _ptr(z_new), seed,
-                                   jet_offset, B, N, _ptr(ws), ws.numel(), PRECISIONS[precision], _stream()))
+                                   ctypes.byref(forward_rate), _ptr(z_diff), _ptr(u_near), _ptr(u_jump), _ptr(z_new), _ptr(u_death),
+                                   seed, jet_offset, B, N, _ptr(ws), ws.numel(), PRECISIONS[precision], _stream()))
     return x, onehot, dims
 
 
@@ -352,6 +363,22 @@ def trans_sampler_update(x, onehot, dims, v, logits, rate, new_mean, new_std, c_
         check(load().mmb_trans_sampler_update(_ptr(x), _ptr(onehot), _ptr(dims), _ptr(v), _ptr(logits), _ptr(rate), _ptr(new_mean),
                                               _ptr(new_std), c_decay, c_score, c_noise, inv_std, jump_dt, _ptr(z_diff), _ptr(u_jump),
                                               _ptr(z_new), seed, jet_offset, step, B, N, S, _stream()))
+
+
+def trans_corrector_update(x, onehot, dims, v, logits, rate, new_mean, new_std, alpha, noise_on, inv_std, corrector_snr, jump_dt,
+                           jump_corrector=False, death_prob=0.0, mask_dims=None, z_diff=None, u_jump=None, u_death=None, z_new=None,
+                           seed=0, jet_offset=0, step=0):
+    """One Langevin corrector update in place; returns the step size the batch norms gave (a device scalar)."""
+    _require_cuda(x, onehot, dims, v, logits, rate, new_mean, new_std, mask_dims, z_diff, u_jump, u_death, z_new)
+    B, N, _ = x.shape
+    S = onehot.shape[-1]
+    scratch = torch.empty(2 * B + 4, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        check(load().mmb_trans_corrector_update(_ptr(x), _ptr(onehot), _ptr(dims), _ptr(mask_dims), _ptr(v), _ptr(logits), _ptr(rate),
+                                                _ptr(new_mean), _ptr(new_std), alpha, int(noise_on), inv_std, corrector_snr, jump_dt,
+                                                int(jump_corrector), death_prob, _ptr(z_diff), _ptr(u_jump), _ptr(u_death), _ptr(z_new),
+                                                seed, jet_offset, step, B, N, S, _ptr(scratch), _stream()))
+    return scratch[2 * B + 3]
 
 
 # ---- forward half of a training / validation step ---------------------------------------------------------

@@ -373,9 +373,9 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         float xs[DC];
         int kk = 0, m = 0;
         if (valid) {
-#pragma unroll
             m = p.mask[pidx] ? 1 : 0;
             // dead particles: the first Euler step multiplies them to 0 (bridges.py:42) and nothing reads them before
+#pragma unroll
             for (int c = 0; c < DC; ++c) xs[c] = m ? p.x[pidx * DC + c] : 0.0f;
             kk = m ? p.k[pidx] : 0;
         } else {

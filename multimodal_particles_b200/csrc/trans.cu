@@ -323,6 +323,7 @@ __device__ __forceinline__ float softplus(float a) { return a > 20.0f ? a : log1
 template <int S>
 __global__ void __launch_bounds__(256) trans_sampler_onehot_kernel(float* __restrict__ onehot, const int32_t* __restrict__ dims,
                                                                    const float* __restrict__ logits, float c_decay, float cs, float c_noise,
+                                                                   const float* __restrict__ coef, const int32_t* __restrict__ mask_dims,
                                                                    const float* __restrict__ z_diff, uint64_t seed, uint64_t jet_offset,
                                                                    int step, int B, int N) {
     constexpr int F = 3 + S;
@@ -330,6 +331,8 @@ __global__ void __launch_bounds__(256) trans_sampler_onehot_kernel(float* __rest
     if (pi >= (size_t)B * N) return;
     const int b = (int)(pi / N), n = (int)(pi % N);
     if (n >= __ldg(dims + b)) return;
+    if (mask_dims && n >= __ldg(mask_dims + b)) return;   // corrector rows: the predictor step's mask (sampler.py:219, 277-279)
+    if (coef) { c_decay = __ldg(coef); cs = __ldg(coef + 1); c_noise = __ldg(coef + 2); }
     const bool noisy = c_noise != 0.0f;
     float oh[S], lg[S], z[8];
     if constexpr (S % 4 == 0) {
@@ -386,20 +389,37 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
                                                                    const float* __restrict__ rate, const float* __restrict__ new_mean,
                                                                    const float* __restrict__ new_std, float c_decay, float c_score,
                                                                    float c_noise, float inv_std, float jump_dt,
+                                                                   const float* __restrict__ coef, const int32_t* __restrict__ mask_dims,
+                                                                   int jump_mode, float death_prob,
                                                                    const float* __restrict__ z_diff, const float* __restrict__ u_jump,
+                                                                   const float* __restrict__ u_death,
                                                                    const float* __restrict__ z_new, uint64_t seed, uint64_t jet_offset,
                                                                    int step, int B, int N) {
+    // jump_mode: 1 = predictor row (birth); 0 = corrector row without jumps (one centre-of-mass removal, sampler.py:280-282);
+    //            2 = corrector row with the jump corrector (birth and death, sampler.py:285-312)
     constexpr int F = 3 + S, SL = 4;   // up to 128 slots = 4 per lane
     const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= B) return;
     const int dim = dims[b];
+    const int upd = mask_dims ? min(__ldg(mask_dims + b), dim) : dim;   // slots that take the increment (stale mask of a corrector row)
     const uint64_t jet = jet_offset + (uint64_t)b;
-    const float uj = u_jump ? __ldg(u_jump + b) : u01(philox_block(seed, jet, 5, step, 0).y);
-    const bool born = (uj < __ldg(rate + b) * jump_dt) && dim < N;
-    const int new_dim = born ? dim + 1 : dim;
+    bool born = false, dies = false;
+    if (jump_mode != 0) {
+        const bool drawn = !u_jump || (jump_mode == 2 && !u_death);
+        const uint4 ur = drawn ? philox_block(seed, jet, 5, step, 0) : make_uint4(0, 0, 0, 0);
+        const float uj = u_jump ? __ldg(u_jump + b) : u01(ur.y);
+        born = (uj < __ldg(rate + b) * jump_dt) && dim < N;
+        if (jump_mode == 2) {
+            const float ud = u_death ? __ldg(u_death + b) : u01(ur.z);
+            dies = (ud < death_prob) && dim > 1;
+            if (born && dies) born = dies = false;   // the newborn is the particle delete_dims removes: the state is as before
+        }
+    }
+    const int new_dim = born ? dim + 1 : (dies ? dim - 1 : dim);
     const float* zb = z_diff ? z_diff + (size_t)b * N * F : nullptr;
+    float cs = -(c_score * inv_std);   // c_score * -(inv_std * D): one rounding apart from the reference order
+    if (coef) { c_decay = __ldg(coef); cs = __ldg(coef + 1); c_noise = __ldg(coef + 2); }
     const bool noisy = c_noise != 0.0f;
-    const float cs = -(c_score * inv_std);   // c_score * -(inv_std * D): one rounding apart from the reference order
     // ---- continuous block: Euler-Maruyama with the noise centred over the live particles, then centre-of-mass removal,
     //      the birth, and a second centre-of-mass removal (sampler.py:221-255, jets_dataloader.py:433-478)
     float xs[SL][3], zc[SL][3];
@@ -424,8 +444,10 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
                     box_muller(r0.z, r0.w, zc[q][2], spare);
                 }
             }
+            if (n < upd) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) xs[q][c] = c_decay * xs[q][c] + cs * vs[c];
+                for (int c = 0; c < 3; ++c) xs[q][c] = c_decay * xs[q][c] + cs * vs[c];
+            }
         }
     }
     const float inv_dim = 1.0f / (float)dim;
@@ -435,7 +457,7 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
             const float zm = warp_sum((zc[0][c] + zc[1][c]) + (zc[2][c] + zc[3][c])) * inv_dim;
 #pragma unroll
             for (int q = 0; q < SL; ++q)
-                if (lane + 32 * q < dim) xs[q][c] = xs[q][c] + c_noise * (zc[q][c] - zm);
+                if (lane + 32 * q < upd) xs[q][c] = xs[q][c] + c_noise * (zc[q][c] - zm);
         }
 #pragma unroll
         for (int q = 0; q < SL; ++q) xs[q][c] = nan_to_num(xs[q][c]);
@@ -466,7 +488,20 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
 #pragma unroll
         for (int s2 = 0; s2 < S; ++s2) onehot[pi * S + s2] = no[s2];
     }
+    if (dies) {   // delete_dims removes the last live particle (sampler.py:305-308); its slot goes back to zero
+        if (lane == (new_dim & 31)) {
+#pragma unroll
+            for (int q = 0; q < SL; ++q)
+                if (q == (new_dim >> 5)) { xs[q][0] = 0.0f; xs[q][1] = 0.0f; xs[q][2] = 0.0f; }
+            const size_t pi = (size_t)b * N + new_dim;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[pi * 3 + c] = 0.0f;
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) onehot[pi * S + s2] = 0.0f;
+        }
+    }
     const float inv_new = 1.0f / (float)new_dim;
+    if (jump_mode != 0)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {   // second adjust_st_batch with the new multiplicity (it runs whether or not a particle was born)
         const float xm = warp_sum((xs[0][c] + xs[1][c]) + (xs[2][c] + xs[3][c])) * inv_new;
@@ -483,7 +518,96 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
             for (int c = 0; c < 3; ++c) x[pi * 3 + c] = xs[q][c];
         }
     }
-    if (lane == 0 && born) dims[b] = new_dim;
+    if (lane == 0 && new_dim != dim) dims[b] = new_dim;
+}
+
+// ---- Langevin corrector step size (sampler.py:264-274): grad_norm = mean_b |score_b|, noise_norm = mean_b |noise_b| over the
+// whole batch, step = (snr noise_norm / grad_norm)^2 2 alpha.  One warp per jet writes its two norms (the noise is the same
+// Philox draw the update kernels regenerate, centred over the live particles); one block reduces them in a fixed order and
+// leaves coef = {1, -step inv_std, sqrt(2 step) or 0} for the update kernels.
+template <int S>
+__global__ void __launch_bounds__(128) trans_corrector_norms_kernel(const int32_t* __restrict__ dims, const float* __restrict__ v,
+                                                                    const float* __restrict__ logits, float inv_std,
+                                                                    const float* __restrict__ z_diff, uint64_t seed, uint64_t jet_offset,
+                                                                    int step, int B, int N, float* __restrict__ norm_s,
+                                                                    float* __restrict__ norm_n) {
+    constexpr int F = 3 + S, SL = 4;
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int dim = dims[b];
+    const uint64_t jet = jet_offset + (uint64_t)b;
+    const float* zb = z_diff ? z_diff + (size_t)b * N * F : nullptr;
+    float zc[SL][3], g2 = 0.0f, n2 = 0.0f;
+#pragma unroll
+    for (int q = 0; q < SL; ++q) {
+        const int n = lane + 32 * q;
+        const size_t pi = (size_t)b * N + n;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) zc[q][c] = 0.0f;
+        if (n < dim) {
+            float zo[8];
+            if (zb) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) zc[q][c] = __ldg(zb + n * 3 + c);
+#pragma unroll
+                for (int s2 = 0; s2 < S; ++s2) zo[s2] = __ldg(zb + (size_t)N * 3 + n * S + s2);
+            } else {
+                const uint4 r0 = philox_block(seed, jet, 2, step, n);
+                float spare;
+                box_muller(r0.x, r0.y, zc[q][0], zc[q][1]);
+                box_muller(r0.z, r0.w, zc[q][2], spare);
+                const uint4 r1 = philox_block(seed, jet, 3, step, n);
+                box_muller(r1.x, r1.y, zo[0], zo[1]);
+                box_muller(r1.z, r1.w, zo[2], zo[3]);
+                if constexpr (S > 4) {
+                    const uint4 r2 = philox_block(seed, jet, 4, step, n);
+                    box_muller(r2.x, r2.y, zo[4], zo[5]);
+                    box_muller(r2.z, r2.w, zo[6], zo[7]);
+                }
+            }
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) n2 += zo[s2] * zo[s2];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const float sc = inv_std * __ldg(v + pi * 3 + c); g2 += sc * sc; }
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) { const float sc = inv_std * __ldg(logits + pi * S + s2); g2 += sc * sc; }
+        }
+    }
+    const float inv_dim = 1.0f / (float)dim;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float zm = warp_sum((zc[0][c] + zc[1][c]) + (zc[2][c] + zc[3][c])) * inv_dim;
+#pragma unroll
+        for (int q = 0; q < SL; ++q)
+            if (lane + 32 * q < dim) { const float a = zc[q][c] - zm; n2 += a * a; }
+    }
+    g2 = warp_sum(g2);
+    n2 = warp_sum(n2);
+    if (lane == 0) { norm_s[b] = sqrtf(g2); norm_n[b] = sqrtf(n2); }
+}
+
+__global__ void __launch_bounds__(256) trans_corrector_coef_kernel(const float* __restrict__ norm_s, const float* __restrict__ norm_n, int B,
+                                                                   float snr, float alpha, float inv_std, int noise_on,
+                                                                   float* __restrict__ coef) {
+    __shared__ double sg[256], sn[256];
+    double g = 0.0, n = 0.0;
+    for (int b = threadIdx.x; b < B; b += 256) { g += (double)norm_s[b]; n += (double)norm_n[b]; }
+    sg[threadIdx.x] = g;
+    sn[threadIdx.x] = n;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { sg[threadIdx.x] += sg[threadIdx.x + w]; sn[threadIdx.x] += sn[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float grad_norm = (float)(sg[0] / B), noise_norm = (float)(sn[0] / B);
+        const float r = snr * noise_norm / grad_norm;
+        const float step = r * r * 2.0f * alpha;
+        coef[0] = 1.0f;
+        coef[1] = -(step * inv_std);
+        coef[2] = noise_on ? sqrtf(2.0f * step) : 0.0f;
+        coef[3] = step;
+    }
 }
 
 // broadcast ts[step] for the sampler's per-jet uniform of the nearest particle when drawn in-kernel
@@ -497,7 +621,7 @@ inline size_t align64(size_t n) { return (n + 63) & ~(size_t)63; }
 // workspace carve-up shared by the forward and the sampler (in floats, every region 256-byte aligned)
 struct TransWs {
     size_t k, mask, M, Z, pmax, psum, means, temb, tb1, tb2, v, logits, hidden, near_logits, vec_w, x0_logits, post_auto, nearest, new_mean, new_std, rate,
-        u_near, ts, total;
+        u_near, ts, norm_s, norm_n, coef, mask_dims, total;
     TransWs(const MmbEpicDims& e, const MmbTransDims& d, int B, int N, int n_time) {
         const size_t P = (size_t)B * N, F = 3 + d.vocab_size;
         size_t at = 0;
@@ -513,6 +637,7 @@ struct TransWs {
         near_logits = take(P); vec_w = take(P); x0_logits = take((size_t)B * d.max_particles);
         post_auto = take((size_t)B * (2 * d.vocab_size + 1)); nearest = take(B); new_mean = take((size_t)B * F);
         new_std = take((size_t)B * F); rate = take(B); u_near = take(B); ts = take(n_time);
+        norm_s = take(B); norm_n = take(B); coef = take(4); mask_dims = take(B);
         total = at;
     }
 };
@@ -658,16 +783,26 @@ static int trans_eval(const EpicModel* m, const TransHeads* h, const float* x, c
     return cuda_ok(cudaGetLastError(), "trans auto launch");
 }
 
+struct CorrectorArgs {   // a corrector row: device coefficients, the predictor step's mask, jump corrector
+    const float* coef = nullptr;
+    const int32_t* mask_dims = nullptr;
+    int jump_mode = 1;
+    float death_prob = 0.0f;
+    const float* u_death = nullptr;
+};
+
 static int launch_sampler_update(float* x, float* onehot, int32_t* dims, const float* v, const float* logits, const float* rate,
                                  const float* new_mean, const float* new_std, float c_decay, float c_score, float c_noise, float inv_std,
                                  float jump_dt, const float* z_diff, const float* u_jump, const float* z_new, uint64_t seed,
-                                 uint64_t jet_offset, int step, int B, int N, int S, cudaStream_t s) {
+                                 uint64_t jet_offset, int step, int B, int N, int S, cudaStream_t s, const CorrectorArgs& ca = CorrectorArgs()) {
     if (N > 128 || N < 1) return fail(MMB_EUNSUPPORTED, "sampler update handles 1..128 particle slots per jet");
 #define MMB_UPD(SV)                                                                                                                  \
-    trans_sampler_onehot_kernel<SV><<<(unsigned)(((size_t)B * N + 255) / 256), 256, 0, s>>>(onehot, dims, logits, c_decay,             \
-                                                                -(c_score * inv_std), c_noise, z_diff, seed, jet_offset, step, B, N);   \
+    trans_sampler_onehot_kernel<SV><<<(unsigned)(((size_t)B * N + 255) / 256), 256, 0, s>>>(                                           \
+        onehot, dims, logits, c_decay, -(c_score * inv_std), c_noise, ca.coef, ca.mask_dims, z_diff, seed, jet_offset, step, B, N);     \
     trans_sampler_update_kernel<SV><<<(B + 3) / 4, 128, 0, s>>>(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score,  \
-                                                                c_noise, inv_std, jump_dt, z_diff, u_jump, z_new, seed, jet_offset, step, B, N)
+                                                                c_noise, inv_std, jump_dt, ca.coef, ca.mask_dims, ca.jump_mode,         \
+                                                                ca.death_prob, z_diff, u_jump, ca.u_death, z_new, seed, jet_offset,    \
+                                                                step, B, N)
     switch (S) {
         case 4: MMB_UPD(4); break;
         case 5: MMB_UPD(5); break;
@@ -677,6 +812,36 @@ static int launch_sampler_update(float* x, float* onehot, int32_t* dims, const f
     }
 #undef MMB_UPD
     return cuda_ok(cudaGetLastError(), "sampler update launch");
+}
+
+// Langevin corrector row: batch norms -> step size on the device -> the same two update kernels with device coefficients
+static int launch_corrector_update(float* x, float* onehot, int32_t* dims, const int32_t* mask_dims, const float* v, const float* logits,
+                                   const float* rate, const float* new_mean, const float* new_std, float alpha, int noise_on, float inv_std,
+                                   float snr, float jump_dt, int jump_corrector, float death_prob, const float* z_diff, const float* u_jump,
+                                   const float* u_death, const float* z_new, uint64_t seed, uint64_t jet_offset, int step, int B, int N, int S,
+                                   float* norm_s, float* norm_n, float* coef, cudaStream_t s) {
+    if (N > 128 || N < 1) return fail(MMB_EUNSUPPORTED, "sampler update handles 1..128 particle slots per jet");
+#define MMB_NORMS(SV)                                                                                                                  \
+    trans_corrector_norms_kernel<SV><<<(B + 3) / 4, 128, 0, s>>>(dims, v, logits, inv_std, z_diff, seed, jet_offset, step, B, N, norm_s, norm_n)
+    switch (S) {
+        case 4: MMB_NORMS(4); break;
+        case 5: MMB_NORMS(5); break;
+        case 6: MMB_NORMS(6); break;
+        case 8: MMB_NORMS(8); break;
+        default: return fail(MMB_EUNSUPPORTED, "sampler update is built for vocab sizes 4, 5, 6, 8 (got %d)", S);
+    }
+#undef MMB_NORMS
+    trans_corrector_coef_kernel<<<1, 256, 0, s>>>(norm_s, norm_n, B, snr, alpha, inv_std, noise_on, coef);
+    if (int rc = cuda_ok(cudaGetLastError(), "corrector norms launch")) return rc;
+    CorrectorArgs ca;
+    ca.coef = coef;
+    ca.mask_dims = mask_dims;
+    ca.jump_mode = jump_corrector ? 2 : 0;
+    ca.death_prob = death_prob;
+    ca.u_death = u_death;
+    // c_noise only tells the kernels whether noise is drawn at all; the value comes from coef
+    return launch_sampler_update(x, onehot, dims, v, logits, rate, new_mean, new_std, 1.0f, 0.0f, noise_on ? 1.0f : 0.0f, inv_std, jump_dt,
+                                 z_diff, u_jump, z_new, seed, jet_offset, step, B, N, S, s, ca);
 }
 
 }  // namespace mmb
@@ -746,16 +911,25 @@ size_t mmb_trans_sample_workspace_bytes(const MmbEpicModel* trunk, const MmbTran
 
 int mmb_trans_sample(const MmbEpicModel* trunk, const MmbTransHeads* heads, float* x, float* onehot, int32_t* dims,
                      const MmbJumpSchedule* sch, const MmbForwardRate* forward_rate, const float* z_diff, const float* u_near,
-                     const float* u_jump, const float* z_new, uint64_t seed, uint64_t jet_offset, int B, int N, void* workspace,
-                     size_t workspace_bytes, int precision, void* stream) {
+                     const float* u_jump, const float* z_new, const float* u_death, uint64_t seed, uint64_t jet_offset, int B, int N,
+                     void* workspace, size_t workspace_bytes, int precision, void* stream) {
     const EpicModel* m = reinterpret_cast<const EpicModel*>(trunk);
     const TransHeads* h = reinterpret_cast<const TransHeads*>(heads);
     if (!m || !h || !x || !onehot || !dims || !sch || !forward_rate || !workspace) return fail(MMB_EINVAL, "mmb_trans_sample: null argument");
     if (!sch->ts || !sch->c_decay || !sch->c_score || !sch->c_noise || !sch->inv_std) return fail(MMB_EINVAL, "mmb_trans_sample: incomplete schedule");
     const int n = sch->n_steps;
     if (B < 0 || n < 0 || n > 4096) return fail(MMB_EINVAL, "mmb_trans_sample: 0..4096 steps");
-    const bool injected = z_diff || u_near || u_jump || z_new;
+    const bool injected = z_diff || u_near || u_jump || z_new || u_death;
     if (injected && !(z_diff && u_near && u_jump && z_new)) return fail(MMB_EINVAL, "mmb_trans_sample: inject all four noise arrays or none");
+    bool correctors = false;
+    for (int i = 0; sch->kind && i < n; ++i) {
+        if (sch->kind[i] > 1) return fail(MMB_EINVAL, "mmb_trans_sample: row kind %d", (int)sch->kind[i]);
+        correctors = correctors || sch->kind[i] == 1;
+    }
+    if (correctors && sch->jump_corrector) {
+        if (!sch->death_prob) return fail(MMB_EINVAL, "mmb_trans_sample: jump corrector needs death_prob");
+        if (injected && !u_death) return fail(MMB_EINVAL, "mmb_trans_sample: jump corrector with injected noise needs u_death");
+    }
     if (int rc = check_pair(m, h, N)) return rc;
     const TransWs L(m->dims, h->d, B, N, 4096);
     if (workspace_bytes < L.total * sizeof(float)) return fail(MMB_ENOMEM, "mmb_trans_sample: workspace too small");
@@ -765,6 +939,9 @@ int mmb_trans_sample(const MmbEpicModel* trunk, const MmbTransHeads* heads, floa
     const int S = h->d.vocab_size, F = 3 + S, T = m->dims.dim_time_emb, nb = h->d.n_blocks;
     // all jets share ts: the time terms of every step are computed once, as a batch of n "jets"
     float* ts_dev = ws + L.ts;
+    int32_t* mask_dims = reinterpret_cast<int32_t*>(ws + L.mask_dims);
+    if (correctors)   // a schedule that opens with corrector rows takes the current dims as its mask
+        if (int rc = cuda_ok(cudaMemcpyAsync(mask_dims, dims, (size_t)B * 4, cudaMemcpyDeviceToDevice, s), "mask dims")) return rc;
     if (int rc = cuda_ok(cudaMemcpyAsync(ts_dev, sch->ts, (size_t)n * 4, cudaMemcpyHostToDevice, s), "schedule upload")) return rc;
     trans_time_kernel<<<(n + kTimeJets - 1) / kTimeJets, 2 * kC, 0, s>>>(h->time_wT, nb, ts_dev, n, T, ws + L.temb, ws + L.tb1, ws + L.tb2);
     if (int rc = cuda_ok(cudaGetLastError(), "trans time launch")) return rc;
@@ -777,11 +954,23 @@ int mmb_trans_sample(const MmbEpicModel* trunk, const MmbTransHeads* heads, floa
         int rc = trans_eval(m, h, x, onehot, dims, ts_dev + i, 0, ws + L.temb + (size_t)i * T, ws + L.tb1 + (size_t)i * nb * kC,
                             ws + L.tb2 + (size_t)i * nb * kC, 0, nullptr, un, *forward_rate, B, N, ws, L, nullptr, nullptr, nullptr, nullptr,
                             precision, s);
-        if (!rc)
-            rc = launch_sampler_update(x, onehot, dims, ws + L.v, ws + L.logits, ws + L.rate, ws + L.new_mean, ws + L.new_std, sch->c_decay[i],
-                                       sch->c_score[i], sch->c_noise[i], sch->inv_std[i], sch->jump_dt,
-                                       z_diff ? z_diff + (size_t)i * B * N * F : nullptr, u_jump ? u_jump + (size_t)i * B : nullptr,
-                                       z_new ? z_new + (size_t)i * B * F : nullptr, seed, jet_offset, i, B, N, S, s);
+        const float* zd = z_diff ? z_diff + (size_t)i * B * N * F : nullptr;
+        const float* uj = u_jump ? u_jump + (size_t)i * B : nullptr;
+        const float* zn = z_new ? z_new + (size_t)i * B * F : nullptr;
+        if (!rc && sch->kind && sch->kind[i] == 1) {
+            rc = launch_corrector_update(x, onehot, dims, mask_dims, ws + L.v, ws + L.logits, ws + L.rate, ws + L.new_mean, ws + L.new_std,
+                                         sch->c_score[i], sch->c_noise[i] != 0.0f, sch->inv_std[i], sch->corrector_snr, sch->jump_dt,
+                                         sch->jump_corrector, sch->death_prob ? sch->death_prob[i] : 0.0f, zd, uj,
+                                         u_death ? u_death + (size_t)i * B : nullptr, zn, seed, jet_offset, i, B, N, S, ws + L.norm_s,
+                                         ws + L.norm_n, ws + L.coef, s);
+        } else if (!rc) {
+            // corrector rows reuse the live mask of their predictor step (sampler.py:219): keep the dims it was built from
+            if (correctors) rc = cuda_ok(cudaMemcpyAsync(mask_dims, dims, (size_t)B * 4, cudaMemcpyDeviceToDevice, s), "mask dims");
+            if (!rc)
+                rc = launch_sampler_update(x, onehot, dims, ws + L.v, ws + L.logits, ws + L.rate, ws + L.new_mean, ws + L.new_std,
+                                           sch->c_decay[i], sch->c_score[i], sch->c_noise[i], sch->inv_std[i], sch->jump_dt, zd, uj, zn, seed,
+                                           jet_offset, i, B, N, S, s);
+        }
         if (rc) return rc;
     }
     return MMB_OK;
@@ -796,6 +985,20 @@ int mmb_trans_sampler_update(float* x, float* onehot, int32_t* dims, const float
     if (B == 0) return MMB_OK;
     return launch_sampler_update(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score, c_noise, inv_std, jump_dt, z_diff,
                                  u_jump, z_new, seed, jet_offset, step, B, N, S, static_cast<cudaStream_t>(stream));
+}
+
+int mmb_trans_corrector_update(float* x, float* onehot, int32_t* dims, const int32_t* mask_dims, const float* v, const float* logits,
+                               const float* rate, const float* new_mean, const float* new_std, float alpha, int noise_on, float inv_std,
+                               float corrector_snr, float jump_dt, int jump_corrector, float death_prob, const float* z_diff,
+                               const float* u_jump, const float* u_death, const float* z_new, uint64_t seed, uint64_t jet_offset, int step,
+                               int B, int N, int S, float* scratch, void* stream) {
+    if (!x || !onehot || !dims || !v || !logits || !scratch) return fail(MMB_EINVAL, "mmb_trans_corrector_update: null argument");
+    if (jump_corrector && (!rate || !new_mean || !new_std)) return fail(MMB_EINVAL, "mmb_trans_corrector_update: jump corrector needs rate, new_mean, new_std");
+    if (B < 0) return fail(MMB_EINVAL, "mmb_trans_corrector_update: negative size");
+    if (B == 0) return MMB_OK;
+    return launch_corrector_update(x, onehot, dims, mask_dims ? mask_dims : dims, v, logits, rate, new_mean, new_std, alpha, noise_on, inv_std,
+                                   corrector_snr, jump_dt, jump_corrector, death_prob, z_diff, u_jump, u_death, z_new, seed, jet_offset, step, B,
+                                   N, S, scratch, scratch + B, scratch + 2 * (size_t)B, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

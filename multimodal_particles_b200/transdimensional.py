@@ -13,7 +13,8 @@ Differences from the reference, all deliberate:
   ``EpsilonPrecond.forward`` drops ``sample_nearest_atom``/``rnd``); here both are in place.
 * draws: ``rnd.multinomial`` / ``rnd.rand`` / ``rnd.randn_like`` are replaced by in-kernel Philox4x32-10 keyed by the
   global jet index (results do not depend on how jets are sharded), or by injected arrays for parity runs.
-* only the live sampler configuration is built (uniform dt, no corrector steps, no conditioning).
+* the sampler covers the live configuration, the 'C' time grid, ``no_noise_final_step``, Langevin corrector steps and the
+  jump corrector; conditioning/guidance is not built (it differentiates through the network).
 """
 import ctypes
 import math
@@ -386,26 +387,61 @@ class TransdimensionalJumpDiffusion(_ModuleBase):
 
 
 # ---- sampler.py ----------------------------------------------------------------------------------------
-def jump_schedule(dt: float, noise_schedule: VP_SDE, no_noise_final_step: bool = False) -> SimpleNamespace:
-    """Per-step scalars of JumpSampler.sample for the uniform dt schedule, with torch fp32 ops in the reference's order
-    (sampler.py:185-231, 315-319; noising.py:15-16, 26-39): all jets share ``ts``, so these are B-independent."""
+def jump_schedule(dt: float, noise_schedule: VP_SDE, no_noise_final_step: bool = False, dt_schedule: str = "uniform",
+                  dt_schedule_h: float = 0.001, dt_schedule_l: float = 0.001, dt_schedule_tc: float = 0.5, corrector_steps: int = 0,
+                  corrector_snr: float = 0.1, corrector_start_time: float = 0.1, corrector_finish_time: float = 0.003,
+                  do_jump_corrector: bool = False, forward_rate=None) -> SimpleNamespace:
+    """One row per network evaluation of JumpSampler.sample, with torch fp32 ops in the reference's order (sampler.py:79-88,
+    185-231, 258-282, 315-319; noising.py:15-16, 26-39): all jets share ``ts``, so these are B-independent.
+
+    * predictor rows (``kind`` 0) — the Euler-Maruyama step at ``ts``.  ``dt_schedule='C'`` only changes the time GRID
+      (``ts -= h`` above ``tc``, ``l`` below): the reference keeps ``self.dt`` in the update coefficients, the birth
+      probability and the stopping rule (sampler.py:187, 221-222, 238).
+    * corrector rows (``kind`` 1) — ``corrector_steps`` Langevin evaluations at ``ts - dt`` after every predictor step with
+      ``corrector_finish_time < ts < corrector_start_time`` (:199-202): ``c_score`` holds alpha = 1 - dt beta(ts - dt),
+      ``c_noise`` 1/0 (noise on/off), ``death_prob`` = forward_rate(ts - dt) dt for the jump corrector (:289)."""
+    if dt_schedule not in ("uniform", "C"):
+        raise NotImplementedError(dt_schedule)
     ts = torch.ones((1,))
     finish_at = dt / 2
+
+    def get_dt(ts):
+        if dt_schedule == "uniform":
+            return dt
+        return (ts > dt_schedule_tc).long() * dt_schedule_h + (ts <= dt_schedule_tc).long() * dt_schedule_l
+
+    def beta_of(t):
+        return t * noise_schedule.beta_max + (1 - t) * noise_schedule.beta_min
+
+    def inv_std_of(t):
+        log_term = -0.25 * t ** 2 * (noise_schedule.beta_max - noise_schedule.beta_min) - 0.5 * t * noise_schedule.beta_min
+        return (1 / torch.clamp(torch.sqrt(1 - torch.exp(2. * log_term)), min=0.001)).item()
+
     rows = []
+    will_finish = False
     while True:
-        will_finish = bool((ts - dt).clamp(min=finish_at / 2).max() < finish_at)
-        beta = ts * noise_schedule.beta_max + (1 - ts) * noise_schedule.beta_min
-        log_term = -0.25 * ts ** 2 * (noise_schedule.beta_max - noise_schedule.beta_min) - 0.5 * ts * noise_schedule.beta_min
-        std = torch.sqrt(1 - torch.exp(2. * log_term))
-        no_noise = no_noise_final_step and will_finish
-        rows.append((ts.item(), (2 - torch.sqrt(1 - beta * dt)).item(), (beta * dt).item(),
-                     0.0 if no_noise else torch.sqrt(beta * dt).item(), (1 / torch.clamp(std, min=0.001)).item()))
-        ts = (ts - dt).clamp(min=finish_at / 2)
+        if (ts - get_dt(ts)).clamp(min=finish_at / 2).max() < finish_at:
+            will_finish = True
+        n_corr = corrector_steps if (ts.min() < corrector_start_time and ts.max() > corrector_finish_time) else 0
+        beta = beta_of(ts)
+        no_noise = n_corr == 0 and no_noise_final_step and will_finish
+        rows.append((0, ts.item(), (2 - torch.sqrt(1 - beta * dt)).item(), (beta * dt).item(),
+                     0.0 if no_noise else torch.sqrt(beta * dt).item(), inv_std_of(ts), 0.0))
+        for ci in range(n_corr):
+            tm1 = ts - dt
+            quiet = ci == n_corr - 1 and no_noise_final_step and will_finish
+            death = 0.0
+            if do_jump_corrector:
+                death = float((torch.as_tensor(forward_rate.get_rate(None, tm1), dtype=torch.float32) * dt).reshape(-1)[0])
+            rows.append((1, tm1.item(), 1.0, (1 - dt * beta_of(tm1)).item(), 0.0 if quiet else 1.0, inv_std_of(tm1), death))
+        ts = (ts - get_dt(ts)).clamp(min=finish_at / 2)
         if ts.max() < finish_at:
             break
-    cols = [np.ascontiguousarray(c, dtype=np.float32) for c in zip(*rows)]
-    return SimpleNamespace(n_steps=len(rows), ts=cols[0], c_decay=cols[1], c_score=cols[2], c_noise=cols[3], inv_std=cols[4],
-                           jump_dt=float(np.float32(dt)))
+    cols = list(zip(*rows))
+    f = [np.ascontiguousarray(c, dtype=np.float32) for c in cols[1:]]
+    return SimpleNamespace(n_steps=len(rows), kind=np.ascontiguousarray(cols[0], dtype=np.uint8), ts=f[0], c_decay=f[1], c_score=f[2],
+                           c_noise=f[3], inv_std=f[4], death_prob=f[5], jump_dt=float(np.float32(dt)),
+                           corrector_snr=float(corrector_snr), jump_corrector=bool(do_jump_corrector and corrector_steps > 0))
 
 
 class JumpSampler:
@@ -415,15 +451,20 @@ class JumpSampler:
                  do_conditioning, condition_type, condition_sweep_idx, condition_sweep_path, guidance_weight, do_jump_corrector,
                  sample_near_atom, dt_schedule, dt_schedule_h, dt_schedule_l, dt_schedule_tc, no_noise_final_step):
         self.structure, self.dt = structure, dt
-        if corrector_steps != 0 or do_conditioning or do_jump_corrector or dt_schedule != 'uniform' or not sample_near_atom:
-            raise NotImplementedError("native JumpSampler covers the live configuration: uniform dt, no corrector steps, "
-                                      "no conditioning, sample_near_atom=True (SURVEY.md §8f N4)")
+        if do_conditioning or dt_schedule not in ('uniform', 'C') or not sample_near_atom:
+            raise NotImplementedError("native JumpSampler: sample_near_atom=True, uniform or 'C' time grid, no conditioning "
+                                      "(guidance needs the network's backward pass; SURVEY.md §8f N4)")
+        self.corrector_snr, self.corrector_start_time, self.corrector_finish_time = corrector_snr, corrector_start_time, corrector_finish_time
+        self.do_jump_corrector = do_jump_corrector
+        self.dt_schedule, self.dt_schedule_h, self.dt_schedule_l, self.dt_schedule_tc = dt_schedule, dt_schedule_h, dt_schedule_l, dt_schedule_tc
         self.corrector_steps, self.sample_near_atom, self.no_noise_final_step = corrector_steps, sample_near_atom, no_noise_final_step
         self.seed = 0
         self._jets_generated = 0
 
     def get_dt(self, ts):
-        return self.dt
+        if self.dt_schedule == 'uniform':
+            return self.dt
+        return (ts > self.dt_schedule_tc).long() * self.dt_schedule_h + (ts <= self.dt_schedule_tc).long() * self.dt_schedule_l
 
     @torch.no_grad()
     def sample(self, net, in_st_batch, loss, rnd=None, known_dims=None, dataset_obj=None, noise=None, jet_offset=None,
@@ -455,7 +496,10 @@ class JumpSampler:
         dims = torch.ones((B,), dtype=torch.int32, device=device)
         state.delete_dims(new_dims=dims)
         state.gs.adjust_st_batch(state)
-        sched = jump_schedule(self.dt, loss.noise_schedule, self.no_noise_final_step)
+        sched = jump_schedule(self.dt, loss.noise_schedule, self.no_noise_final_step, self.dt_schedule, self.dt_schedule_h,
+                              self.dt_schedule_l, self.dt_schedule_tc, self.corrector_steps, self.corrector_snr,
+                              self.corrector_start_time, self.corrector_finish_time, self.do_jump_corrector, loss.forward_rate)
+        self.last_n_steps = sched.n_steps   # the reference prints this as 'nfe' (sampler.py:323)
         x, onehot = state.tuple_batch[0].contiguous(), state.tuple_batch[1].contiguous()
         _native.trans_sample(model.native_trunk(device), model.native_heads(device), x, onehot, dims, sched,
                              loss.forward_rate.as_c(), noise=noise, seed=self.seed, jet_offset=jet_offset,

@@ -832,10 +832,89 @@ void mmbo_trans_sampler_update(float* x, float* onehot, int32_t* dims, const flo
     free(zc);
 }
 
+/* one Langevin corrector update (sampler.py:258-282) and, with jump_corrector, its birth/death jumps (:285-312).
+ * v / logits / rate / new_mean / new_std come from the evaluation at t - dt; alpha = 1 - dt beta(t - dt).
+ * mask_dims: the reference reuses the `mask` of the predictor step (sampler.py:219) in every corrector of that step, so
+ * particles born since then take no Langevin increment; the noise is centred, and the state re-centred, over the
+ * current dims. */
+void mmbo_trans_corrector_update(float* x, float* onehot, int32_t* dims, const int32_t* mask_dims, const float* v, const float* logits, const float* rate,
+                                 const float* new_mean, const float* new_std, float alpha, int noise_on, float inv_std, float snr,
+                                 float jump_dt, int jump_corrector, float death_prob, const float* z_diff, const float* u_jump,
+                                 const float* u_death, const float* z_new, int B, int N, int S) {
+    const int F = 3 + S;
+    float* zc = (float*)malloc(sizeof(float) * (size_t)B * N * F);   /* noise after delete_dims + adjust_st_batch, [x | one-hot] */
+    double gsum = 0.0, nsum = 0.0;
+    for (int b = 0; b < B; ++b) {
+        const float* zb = z_diff + (size_t)b * N * F;
+        float* zj = zc + (size_t)b * N * F;
+        const int dim = dims[b];
+        for (int i = 0; i < N * 3; ++i) zj[i] = (i / 3) < dim ? zb[i] : 0.0f;
+        for (int i = 0; i < N * S; ++i) zj[N * 3 + i] = (i / S) < dim ? zb[N * 3 + i] : 0.0f;
+        for (int c = 0; c < 3; ++c) {
+            float acc = 0.0f;
+            for (int n = 0; n < N; ++n) acc += zj[n * 3 + c];
+            const float mean = acc / (float)dim;
+            for (int n = 0; n < dim; ++n) zj[n * 3 + c] = zj[n * 3 + c] - mean;
+        }
+        double g2 = 0.0, n2 = 0.0;
+        for (int i = 0; i < N * 3; ++i) { const float sc = -(inv_std * v[(size_t)b * N * 3 + i]); g2 += (double)sc * sc; }
+        for (int i = 0; i < N * S; ++i) { const float sc = -(inv_std * logits[(size_t)b * N * S + i]); g2 += (double)sc * sc; }
+        for (int i = 0; i < N * F; ++i) n2 += (double)zj[i] * zj[i];
+        gsum += (double)(float)sqrt(g2);
+        nsum += (double)(float)sqrt(n2);
+    }
+    const float grad_norm = (float)(gsum / B), noise_norm = (float)(nsum / B);
+    float r = snr * noise_norm / grad_norm;
+    const float step = r * r * 2.0f * alpha;
+    const float sq = sqrtf(2.0f * step);
+    for (int b = 0; b < B; ++b) {
+        float* xb = x + (size_t)b * N * 3;
+        float* ob = onehot + (size_t)b * N * S;
+        const float* zj = zc + (size_t)b * N * F;
+        const int dim = dims[b];
+        const int upd = mask_dims[b] < dim ? mask_dims[b] : dim;   /* slots in [dim, mask_dims) are dead: score = noise = 0 there */
+        for (int n = 0; n < upd; ++n) {
+            for (int c = 0; c < 3; ++c) {
+                const float score = -(inv_std * v[((size_t)b * N + n) * 3 + c]);
+                const float inc = noise_on ? step * score + sq * zj[n * 3 + c] : step * score;
+                xb[n * 3 + c] = xb[n * 3 + c] + inc;
+            }
+            for (int s = 0; s < S; ++s) {
+                const float score = -(inv_std * logits[((size_t)b * N + n) * S + s]);
+                const float inc = noise_on ? step * score + sq * zj[N * 3 + n * S + s] : step * score;
+                ob[n * S + s] = ob[n * S + s] + inc;
+            }
+        }
+        adjust_jet(xb, ob, dim, N, S);
+        if (!jump_corrector) continue;
+        const int born = u_jump[b] < rate[b] * jump_dt && dim < N;
+        const int dies = u_death[b] < death_prob && dim > 1;
+        int nd = dim;
+        if (born) {
+            for (int c = 0; c < 3; ++c)
+                xb[dim * 3 + c] = new_mean[(size_t)b * F + c] + z_new[(size_t)b * F + c] * softplusf(new_std[(size_t)b * F + c]);
+            for (int s = 0; s < S; ++s)
+                ob[dim * S + s] = new_mean[(size_t)b * F + 3 + s] + z_new[(size_t)b * F + 3 + s] * softplusf(new_std[(size_t)b * F + 3 + s]);
+            nd += 1;
+        }
+        if (dies) nd -= 1;
+        for (int n = nd; n < N; ++n) {   /* delete_dims */
+            for (int c = 0; c < 3; ++c) xb[n * 3 + c] = 0.0f;
+            for (int s = 0; s < S; ++s) ob[n * S + s] = 0.0f;
+        }
+        dims[b] = nd;
+        adjust_jet(xb, ob, nd, N, S);
+    }
+    free(zc);
+}
+
 void mmbo_trans_sample(const MmbEpicDims* ed, const float* epacked, const MmbTransDims* d, const float* W,
                        float* x, float* onehot, int32_t* dims, const MmbJumpSchedule* sch, const MmbForwardRate* fr,
-                       const float* z_diff, const float* u_near, const float* u_jump, const float* z_new, int B, int N) {
+                       const float* z_diff, const float* u_near, const float* u_jump, const float* z_new, const float* u_death,
+                       const int32_t* mask_dims_in, int B, int N) {
     const int S = d->vocab_size, F = 3 + S, R = d->max_particles;
+    int32_t* mdims = (int32_t*)malloc(sizeof(int32_t) * (size_t)B);
+    memcpy(mdims, mask_dims_in ? mask_dims_in : dims, sizeof(int32_t) * (size_t)B);
     float* dx = (float*)malloc(sizeof(float) * (size_t)B * N * F);
     float* v = (float*)malloc(sizeof(float) * (size_t)B * N * 3);
     float* lg = (float*)malloc(sizeof(float) * (size_t)B * N * S);
@@ -853,11 +932,20 @@ void mmbo_trans_sample(const MmbEpicDims* ed, const float* epacked, const MmbTra
             memcpy(v + (size_t)b * N * 3, dx + (size_t)b * N * F, sizeof(float) * (size_t)N * 3);
             memcpy(lg + (size_t)b * N * S, dx + (size_t)b * N * F + (size_t)N * 3, sizeof(float) * (size_t)N * S);
         }
-        mmbo_trans_sampler_update(x, onehot, dims, v, lg, rate, nm, ns, sch->c_decay[step], sch->c_score[step], sch->c_noise[step],
-                                  sch->inv_std[step], sch->jump_dt, z_diff + (size_t)step * B * N * F, u_jump + (size_t)step * B,
-                                  z_new + (size_t)step * B * F, B, N, S);
+        if (sch->kind && sch->kind[step] == 1)
+            mmbo_trans_corrector_update(x, onehot, dims, mdims, v, lg, rate, nm, ns, sch->c_score[step], sch->c_noise[step] != 0.0f,
+                                        sch->inv_std[step], sch->corrector_snr, sch->jump_dt, sch->jump_corrector,
+                                        sch->death_prob ? sch->death_prob[step] : 0.0f, z_diff + (size_t)step * B * N * F,
+                                        u_jump + (size_t)step * B, u_death ? u_death + (size_t)step * B : NULL,
+                                        z_new + (size_t)step * B * F, B, N, S);
+        else {
+            memcpy(mdims, dims, sizeof(int32_t) * (size_t)B);
+            mmbo_trans_sampler_update(x, onehot, dims, v, lg, rate, nm, ns, sch->c_decay[step], sch->c_score[step], sch->c_noise[step],
+                                      sch->inv_std[step], sch->jump_dt, z_diff + (size_t)step * B * N * F, u_jump + (size_t)step * B,
+                                      z_new + (size_t)step * B * F, B, N, S);
+        }
     }
-    free(dx); free(v); free(lg); free(rate); free(xl); free(nl); free(nm); free(ns); free(ts);
+    free(dx); free(v); free(lg); free(rate); free(xl); free(nl); free(nm); free(ns); free(ts); free(mdims);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -83,9 +83,14 @@ void mmbo_trans_sampler_update(float* x, float* onehot, int32_t* dims, const flo
                                const float* new_mean, const float* new_std,
                                float c_decay, float c_score, float c_noise, float inv_std, float jump_dt,
                                const float* z_diff, const float* u_jump, const float* z_new, int B, int N, int S);
+void mmbo_trans_corrector_update(float* x, float* onehot, int32_t* dims, const int32_t* mask_dims, const float* v, const float* logits, const float* rate,
+                                 const float* new_mean, const float* new_std, float alpha, int noise_on, float inv_std, float snr,
+                                 float jump_dt, int jump_corrector, float death_prob, const float* z_diff, const float* u_jump,
+                                 const float* u_death, const float* z_new, int B, int N, int S);
 void mmbo_trans_sample(const MmbEpicDims* ed, const float* epacked, const MmbTransDims* d, const float* W,
                        float* x, float* onehot, int32_t* dims, const MmbJumpSchedule* sch, const MmbForwardRate* fr,
-                       const float* z_diff, const float* u_near, const float* u_jump, const float* z_new, int B, int N);
+                       const float* z_diff, const float* u_near, const float* u_jump, const float* z_new, const float* u_death,
+                       const int32_t* mask_dims_in, int B, int N);
 
 /* post-processing + jet observables (mmb_jet_observables); jet sums accumulated in double */
 void mmbo_jet_observables(const float* x, const uint8_t* k, const uint8_t* mask, const float* mean, const float* sd, int B, int N,

@@ -93,6 +93,38 @@ class InjectedRnd:
         return idx.view(-1, 1)
 
 
+class EvalRnd:
+    """``rnd`` indexed by NETWORK EVALUATION (every evaluation starts with the nearest-particle multinomial): within
+    evaluation e the first randn_like is the diffusion/Langevin noise z_diff[e], the second the new particle z_new[e];
+    the first rand is the birth uniform u_jump[e], the second the death uniform u_death[e] (jump corrector only)."""
+
+    def __init__(self, N, S, z_init, z_diff, u_near, u_jump, u_death, z_new):
+        self.N, self.S = N, S
+        self.z_init, self.z_diff, self.u_near, self.u_jump, self.u_death, self.z_new = z_init, z_diff, u_near, u_jump, u_death, z_new
+        self.e, self.first, self.n_randn, self.n_rand = -1, True, 0, 0
+
+    def multinomial(self, probs, num_samples=1):
+        self.e, self.n_randn, self.n_rand = self.e + 1, 0, 0
+        c = torch.cumsum(probs, 1)
+        return (self.u_near[self.e][:, None] >= c).sum(1).clamp(max=probs.shape[1] - 1).view(-1, 1)
+
+    def randn_like(self, t):
+        if self.first:
+            self.first = False
+            return self.z_init.clone()
+        i, self.n_randn = self.n_randn, self.n_randn + 1
+        if i == 0:
+            return self.z_diff[self.e].clone()
+        z = self.z_new[self.e]
+        B = z.shape[0]
+        return torch.cat([z[:, None, :3].expand(B, self.N, 3).reshape(B, -1),
+                          z[:, None, 3:].expand(B, self.N, self.S).reshape(B, -1)], 1).clone()
+
+    def rand(self, size, device=None):
+        i, self.n_rand = self.n_rand, self.n_rand + 1
+        return (self.u_jump if i == 0 else self.u_death)[self.e].clone()
+
+
 def patched_precond_forward(self, st_batch, ts, predict='eps', forward_rate=None, nearest_atom=None, **kw):
     """EpsilonPrecond.forward (transdimensional_model.py:124-133) with the missing kwargs passed through."""
     eps, *others = self.model(st_batch, ts, nearest_atom=nearest_atom, forward_rate=forward_rate, **kw)
@@ -189,6 +221,58 @@ def main():
                 "smp/nearest_traj": torch.stack(rnd.nearest).numpy().astype(np.int32),
                 "smp/x_final": final.tuple_batch[0].numpy(), "smp/oh_final": final.tuple_batch[1].numpy(),
                 "smp/dims_final": final.get_dims().numpy().astype(np.int32)})
+    # ---- same sampler on the 'C' time grid (sampler.py:79-88) with no_noise_final_step: only the grid and the last step change
+    skc = dict(sk, dt_schedule="C", dt_schedule_h=0.1, dt_schedule_l=0.04, dt_schedule_tc=0.5, no_noise_final_step=True)
+    sampler_c = JumpSampler(structure=model.structure, **skc)
+    rnd_c = InjectedRnd(N, S, z_init=z_init, z_diff=z_diff, u_near=u_near_s, u_jump=u_jump, z_new=z_new)
+    ts_c = []
+    orig_c = sampler_c.get_score
+    sampler_c.get_score = lambda st_, net_, loss_, ts_, d_, r_: (ts_c.append(ts_[0].item()), orig_c(st_, net_, loss_, ts_, d_, r_))[1]
+    in_st_c = StructuredDataBatch([torch.zeros(Bs, N, 3), torch.zeros(Bs, N, S)], torch.full((Bs,), N), dm.observed, dm.exist,
+                                  dm.is_onehot, gs)
+    with quiet(), torch.no_grad():
+        final_c = sampler_c.sample(net, in_st_c, model.jump_diffusion_loss, rnd_c)
+    assert len(ts_c) <= steps
+    out.update({"smpC/ts": np.array(ts_c, np.float32), "smpC/x_final": final_c.tuple_batch[0].numpy(),
+                "smpC/oh_final": final_c.tuple_batch[1].numpy(), "smpC/dims_final": final_c.get_dims().numpy().astype(np.int32)})
+    # ---- Langevin corrector steps + jump corrector (sampler.py:258-312), dt = 0.02, correctors below t = 0.25 down to the end,
+    #      no_noise_final_step: 50 predictor rows + 24 corrector rows
+    dtl, rows = 0.02, 74
+    skl = dict(sk, dt=dtl, corrector_steps=2, corrector_snr=0.2, corrector_start_time=0.25, corrector_finish_time=0.0,
+               do_jump_corrector=True, no_noise_final_step=True)
+    sampler_l = JumpSampler(structure=model.structure, **skl)
+    gl = torch.Generator().manual_seed(303)
+    zl_init = torch.randn(Bs, N * F, generator=gl)
+    zl_diff = torch.randn(rows, Bs, N * F, generator=gl)
+    ul_near, ul_jump, ul_death = (torch.rand(rows, Bs, generator=gl) for _ in range(3))
+    zl_new = torch.randn(rows, Bs, F, generator=gl)
+    rnd_l = EvalRnd(N, S, zl_init, zl_diff, ul_near, ul_jump, ul_death, zl_new)
+    recl = dict(ts=[], dims=[], x=[], oh=[])
+    orig_l = sampler_l.get_score
+
+    def get_score_l(state_st_batch, net_, loss, ts_, dataset_obj, rnd_):
+        recl["ts"].append(ts_[0].item())
+        recl["dims"].append(state_st_batch.get_dims().clone())
+        recl["x"].append(state_st_batch.tuple_batch[0].clone())
+        recl["oh"].append(state_st_batch.tuple_batch[1].clone())
+        return orig_l(state_st_batch, net_, loss, ts_, dataset_obj, rnd_)
+
+    sampler_l.get_score = get_score_l
+    in_st_l = StructuredDataBatch([torch.zeros(Bs, N, 3), torch.zeros(Bs, N, S)], torch.full((Bs,), N), dm.observed, dm.exist,
+                                  dm.is_onehot, gs)
+    with quiet(), torch.no_grad():
+        final_l = sampler_l.sample(net, in_st_l, model.jump_diffusion_loss, rnd_l)
+    assert len(recl["ts"]) == rows, len(recl["ts"])
+    dl = torch.stack(recl["dims"])
+    print("corrector run: dims per row", dl[:, 0].tolist(), "final", final_l.get_dims().tolist())
+    out.update({"smpL/dt": np.float64(dtl), "smpL/kwargs": json.dumps({k: skl[k] for k in ("corrector_steps", "corrector_snr",
+                "corrector_start_time", "corrector_finish_time", "do_jump_corrector", "no_noise_final_step")}),
+                "smpL/z_init": zl_init.numpy(), "smpL/z_diff": zl_diff.numpy(), "smpL/u_near": ul_near.numpy(),
+                "smpL/u_jump": ul_jump.numpy(), "smpL/u_death": ul_death.numpy(), "smpL/z_new": zl_new.numpy(),
+                "smpL/ts": np.array(recl["ts"], np.float32), "smpL/dims_traj": dl.numpy().astype(np.int32),
+                "smpL/x_traj": torch.stack(recl["x"]).numpy(), "smpL/oh_traj": torch.stack(recl["oh"]).numpy(),
+                "smpL/x_final": final_l.tuple_batch[0].numpy(), "smpL/oh_final": final_l.tuple_batch[1].numpy(),
+                "smpL/dims_final": final_l.get_dims().numpy().astype(np.int32)})
     out.update(mg.np_state_dict(model))
     path = os.path.join(HERE, "trans.npz")
     np.savez_compressed(path, **out)

@@ -229,7 +229,21 @@ def trans_sampler_update(x, onehot, dims, v, logits, rate, new_mean, new_std, c_
     return x, onehot, dims
 
 
-def trans_sample(packed, x, onehot, dims, sched, fr: ForwardRate, z_diff, u_near, u_jump, z_new):
+def trans_corrector_update(x, onehot, dims, mask_dims, v, logits, rate, new_mean, new_std, alpha, noise_on, inv_std, snr, jump_dt,
+                           jump_corrector, death_prob, z_diff, u_jump, u_death, z_new):
+    """Returns updated copies (x, onehot, dims)."""
+    B, N, _ = x.shape
+    S = onehot.shape[-1]
+    x, onehot, dims = f32(x).copy(), f32(onehot).copy(), i32(dims).copy()
+    cf = ctypes.c_float
+    lib().mmbo_trans_corrector_update(_p(x), _p(onehot), _p(dims, _i32p), _p(i32(mask_dims), _i32p), _p(f32(v)), _p(f32(logits)),
+                                      _p(f32(rate)), _p(f32(new_mean)), _p(f32(new_std)), cf(alpha), int(noise_on), cf(inv_std), cf(snr),
+                                      cf(jump_dt), int(jump_corrector), cf(death_prob), _p(f32(z_diff)), _p(f32(u_jump)),
+                                      _p(f32(u_death)), _p(f32(z_new)), B, N, S)
+    return x, onehot, dims
+
+
+def trans_sample(packed, x, onehot, dims, sched, fr: ForwardRate, z_diff, u_near, u_jump, z_new, u_death=None, mask_dims=None):
     """Returns final copies (x, onehot, dims)."""
     edims, eblob, tdims, tblob = packed
     B, N, _ = x.shape
@@ -237,7 +251,8 @@ def trans_sample(packed, x, onehot, dims, sched, fr: ForwardRate, z_diff, u_near
     cs = JumpSchedule.from_schedule(sched)
     lib().mmbo_trans_sample(ctypes.byref(edims), _p(f32(eblob)), ctypes.byref(tdims), _p(f32(tblob)), _p(x), _p(onehot),
                             _p(dims, _i32p), ctypes.byref(cs), ctypes.byref(fr), _p(f32(z_diff)), _p(f32(u_near)), _p(f32(u_jump)),
-                            _p(f32(z_new)), B, N)
+                            _p(f32(z_new)), _p(None if u_death is None else f32(u_death)),
+                            _p(None if mask_dims is None else i32(mask_dims), _i32p), B, N)
     return x, onehot, dims
 
 

@@ -122,6 +122,63 @@ def test_sampler_update_kernel_matches_oracle():
             np.testing.assert_allclose(to.cpu().numpy(), wo, rtol=1e-5, atol=2e-6)
 
 
+def test_corrector_update_kernels_match_oracle():
+    """Langevin corrector (+ jump corrector) alone, same inputs on both sides: the batch-norm step size, the stale predictor
+    mask, births and deaths: dims bit-exact, state to fp32 summation-order noise (sampler.py:258-312)"""
+    g = np.random.default_rng(11)
+    for (B, N, S) in ((7, 16, 8), (300, 128, 8), (5, 30, 4)):
+        F = 3 + S
+        dims = g.integers(1, N + 1, B).astype(np.int32)
+        dims[0], dims[1] = 1, N
+        mask_dims = np.clip(dims + g.integers(-2, 2, B), 1, N).astype(np.int32)   # born / died since the predictor step
+        m = (np.arange(N)[None] < dims[:, None])[..., None]
+        x = (g.standard_normal((B, N, 3)) * m).astype(np.float32)
+        oh = (g.standard_normal((B, N, S)) * m).astype(np.float32)
+        v, lg = (g.standard_normal((B, N, 3)) * m).astype(np.float32), (g.standard_normal((B, N, S)) * m).astype(np.float32)
+        rate = (g.random(B) * 20).astype(np.float32)
+        nm, ns = g.standard_normal((B, F)).astype(np.float32) * 3, g.standard_normal((B, F)).astype(np.float32) * 12
+        z_diff, z_new = g.standard_normal((B, N * F)).astype(np.float32), g.standard_normal((B, F)).astype(np.float32)
+        u_jump, u_death = g.random(B).astype(np.float32), g.random(B).astype(np.float32)
+        for noise_on, jump in ((1, 1), (0, 1), (1, 0)):
+            sc = dict(alpha=0.97, noise_on=noise_on, inv_std=1.7, snr=0.2, jump_dt=0.05, jump_corrector=jump, death_prob=0.4)
+            wx, wo, wd = ol.trans_corrector_update(x, oh, dims, mask_dims, v, lg, rate, nm, ns, sc["alpha"], noise_on, sc["inv_std"],
+                                                   sc["snr"], sc["jump_dt"], jump, sc["death_prob"], z_diff, u_jump, u_death, z_new)
+            tx, to, td = to_dev(x), to_dev(oh), to_dev(dims)
+            step = _native.trans_corrector_update(tx, to, td, to_dev(v), to_dev(lg), to_dev(rate), to_dev(nm), to_dev(ns), sc["alpha"],
+                                                  noise_on, sc["inv_std"], sc["snr"], sc["jump_dt"], bool(jump), sc["death_prob"],
+                                                  mask_dims=to_dev(mask_dims), z_diff=to_dev(z_diff), u_jump=to_dev(u_jump),
+                                                  u_death=to_dev(u_death), z_new=to_dev(z_new))
+            assert 0 < float(step) < 1
+            assert np.array_equal(td.cpu().numpy(), wd)
+            if jump:
+                assert (wd > dims).any() and (wd < dims).any()
+            else:
+                assert np.array_equal(wd, dims)
+            np.testing.assert_allclose(tx.cpu().numpy(), wx, rtol=1e-5, atol=3e-6)
+            np.testing.assert_allclose(to.cpu().numpy(), wo, rtol=1e-5, atol=3e-6)
+            dead = np.arange(N)[None] >= wd[:, None]
+            assert (tx.cpu().numpy()[dead] == 0).all() and (to.cpu().numpy()[dead] == 0).all()
+
+
+def test_corrector_in_kernel_noise_matches_the_norm_pass():
+    """Philox path of a corrector row: the norm kernel and the update kernels regenerate the same draws — with score = 0 and
+    snr chosen so that sqrt(2 step) = 1 the state moves by exactly the centred noise whose norm set the step."""
+    B, N, S = 256, 128, 8
+    dims = torch.full((B,), N, dtype=torch.int32, device=DEV)
+    x, oh = torch.zeros(B, N, 3, device=DEV), torch.zeros(B, N, S, device=DEV)
+    v, lg = torch.ones(B, N, 3, device=DEV), torch.ones(B, N, S, device=DEV)   # |score_b| = sqrt(N F) for every jet
+    step = _native.trans_corrector_update(x, oh, dims, v, lg, None, None, None, 1.0, True, 1.0, 1.0, 0.02, seed=3, jet_offset=40, step=9)
+    step = float(step)
+    sq, F = (2 * step) ** 0.5, 3 + S
+    noise_oh = (oh + step) / sq           # increment = -step * 1 + sqrt(2 step) * z
+    assert abs(float(noise_oh.mean())) < 5e-3 and abs(float(noise_oh.std()) - 1.0) < 5e-3
+    # step = (noise_norm / grad_norm)^2 * 2 with grad_norm = sqrt(N F): recover noise_norm and compare with the noise actually applied
+    noise_norm = (step / 2) ** 0.5 * (N * F) ** 0.5
+    # the continuous part lost the (constant) -step score under the centre-of-mass removal: it is the centred noise itself
+    applied = torch.cat([(x / sq).flatten(1), noise_oh.flatten(1)], 1)
+    assert abs(float(applied.norm(dim=1).mean()) - noise_norm) < 2e-3 * noise_norm
+
+
 def test_sampler_update_in_kernel_normals_are_standard():
     """Philox + Box-Muller draws of the update kernel: with x = v = 0 and c_noise = 1 the output IS the centred noise."""
     B, N, S = 512, 128, 8
@@ -221,6 +278,92 @@ def test_jump_sampler_end_to_end_properties():
     assert (x[dead] == 0).all() and (oh[dead] == 0).all()
     com = x.sum(1) / dims[:, None]
     assert com.abs().max() <= 1e-3 * max(1.0, float(x.abs().max()))
+
+
+def test_jump_sampler_c_time_grid_runs_the_reference_grid(fixture):
+    """dt_schedule='C' + no_noise_final_step through the public API, injected draws: same number of evaluations as the
+    reference run, and the jets that never came near a birth threshold end where the reference's did."""
+    z, cfg, model, packed = fixture
+    B, N, S = z["smpC/oh_final"].shape
+    sk = {k: v for k, v in vars(cfg.sampler_kwargs).items() if k not in ("class_name", "do_jump_back", "jump_back_start_time")}
+    sk.update(dt=float(z["smp/dt"]), dt_schedule="C", dt_schedule_h=0.1, dt_schedule_l=0.04, dt_schedule_tc=0.5, no_noise_final_step=True)
+    sampler = JumpSampler(structure=model.structure, **sk)
+    n = len(z["smpC/ts"])
+    noise = SimpleNamespace(z_init=to_dev(z["smp/z_init"]), z_diff=to_dev(z["smp/z_diff"][:n]), u_near=to_dev(z["smp/u_near"][:n]),
+                            u_jump=to_dev(z["smp/u_jump"][:n]), z_new=to_dev(z["smp/z_new"][:n]))
+    in_st = model.make_batch(torch.zeros(B, N, 3, device=DEV), torch.zeros(B, N, S, device=DEV), torch.full((B,), N, device=DEV))
+    out = sampler.sample(model.net, in_st, model.jump_diffusion_loss, noise=noise, precision="fp32")
+    assert sampler.last_n_steps == n
+    dims = out.get_dims().cpu().numpy()
+    assert (np.abs(dims - z["smpC/dims_final"]) <= 1).all() and (dims == z["smpC/dims_final"]).sum() >= B - 1
+    same = dims == z["smpC/dims_final"]
+    x = out.tuple_batch[0].cpu().numpy()
+    assert np.isfinite(x).all()
+    scale = max(1.0, np.abs(z["smpC/x_final"]).max())
+    assert np.median(np.abs(x[same] - z["smpC/x_final"][same])) <= 0.02 * scale
+
+
+def test_jump_sampler_with_correctors_follows_the_reference_groups(fixture):
+    """corrector_steps = 2 + jump corrector + no_noise_final_step: every predictor step of the reference run together with
+    its corrector rows, restarted from the reference's recorded state (fp32 trunk), ends where the reference's did"""
+    import json
+    z, cfg, model, packed = fixture
+    m = model.net.model
+    dev = torch.device(DEV)
+    kw = json.loads(str(z["smpL/kwargs"]))
+    sched = jump_schedule(float(z["smpL/dt"]), model.noise_schedule, kw["no_noise_final_step"], corrector_steps=kw["corrector_steps"],
+                          corrector_snr=kw["corrector_snr"], corrector_start_time=kw["corrector_start_time"],
+                          corrector_finish_time=kw["corrector_finish_time"], do_jump_corrector=kw["do_jump_corrector"],
+                          forward_rate=model.forward_rate)
+    assert sched.n_steps == len(z["smpL/ts"])
+    starts = [i for i in range(sched.n_steps) if sched.kind[i] == 0] + [sched.n_steps]
+    fr = model.forward_rate.as_c()
+    same = total = 0
+    errs = []
+    for a, b in zip(starts[:-1], starts[1:]):
+        if b - a == 1:
+            continue   # predictor-only rows are covered by test_sampler_steps_against_reference_trajectory
+        x, oh, dims = to_dev(z["smpL/x_traj"][a]), to_dev(z["smpL/oh_traj"][a]), to_dev(z["smpL/dims_traj"][a])
+        sub = SimpleNamespace(n_steps=b - a, kind=sched.kind[a:b], ts=sched.ts[a:b], c_decay=sched.c_decay[a:b], c_score=sched.c_score[a:b],
+                              c_noise=sched.c_noise[a:b], inv_std=sched.inv_std[a:b], death_prob=sched.death_prob[a:b],
+                              jump_dt=sched.jump_dt, corrector_snr=sched.corrector_snr, jump_corrector=sched.jump_corrector)
+        noise = SimpleNamespace(z_diff=to_dev(z["smpL/z_diff"][a:b]), u_near=to_dev(z["smpL/u_near"][a:b]),
+                                u_jump=to_dev(z["smpL/u_jump"][a:b]), z_new=to_dev(z["smpL/z_new"][a:b]),
+                                u_death=to_dev(z["smpL/u_death"][a:b]))
+        _native.trans_sample(m.native_trunk(dev), m.native_heads(dev), x, oh, dims, sub, fr, noise=noise, precision="fp32")
+        last = b == sched.n_steps
+        rx, rd = ((z["smpL/x_final"], z["smpL/dims_final"]) if last else (z["smpL/x_traj"][b], z["smpL/dims_traj"][b]))
+        got = dims.cpu().numpy()
+        total += len(rd)
+        same += int((got == rd).sum())
+        quiet = (got == rd) & (rd == z["smpL/dims_traj"][a])
+        if quiet.any():
+            errs.append(np.abs(x.cpu().numpy()[quiet] - rx[quiet]).max() / max(1.0, np.abs(rx).max()))
+    assert total >= 50 and same >= 0.9 * total, (same, total)
+    assert len(errs) >= 5 and np.median(errs) <= 0.02, errs
+
+
+def test_jump_sampler_with_correctors_philox_properties():
+    """the same configuration through JumpSampler.sample with in-kernel draws at N = 128: deterministic, finite,
+    dead slots zero, centred (the Langevin step size is a statistic of the whole batch, as in the reference)"""
+    cfg = TransdimensionalEpicConfig()
+    torch.manual_seed(0)
+    model = TransdimensionalJumpDiffusion(cfg).to(DEV)
+    N, S, B = cfg.data.max_num_particles, cfg.data.vocab_size_features, 200
+    sk = {k: v for k, v in vars(cfg.sampler_kwargs).items() if k not in ("class_name", "do_jump_back", "jump_back_start_time")}
+    sk.update(dt=0.02, corrector_steps=1, corrector_snr=0.1, corrector_start_time=0.5, corrector_finish_time=0.05, do_jump_corrector=True)
+    sampler = JumpSampler(structure=model.structure, **sk)
+    sampler.seed = 4
+    start = lambda n: model.make_batch(torch.zeros(n, N, 3, device=DEV), torch.zeros(n, N, S, device=DEV), torch.full((n,), N, device=DEV))
+    a = sampler.sample(model.net, start(B), model.jump_diffusion_loss, jet_offset=0)
+    assert sampler.last_n_steps > 50
+    b = sampler.sample(model.net, start(B), model.jump_diffusion_loss, jet_offset=0)
+    assert torch.equal(a.tuple_batch[0], b.tuple_batch[0]) and torch.equal(a.get_dims(), b.get_dims())
+    dims, (x, oh) = a.get_dims(), a.tuple_batch
+    assert dims.min() >= 1 and dims.max() <= N and torch.isfinite(x).all() and torch.isfinite(oh).all()
+    dead = torch.arange(N, device=DEV)[None] >= dims[:, None]
+    assert (x[dead] == 0).all() and (oh[dead] == 0).all()
+    assert (x.sum(1) / dims[:, None]).abs().max() <= 1e-3 * max(1.0, float(x.abs().max()))
 
 
 def test_c3_full_size_properties():

@@ -1,6 +1,7 @@
 """The CPU oracle's trans-dimensional path against the fixture produced by the reference
 (tests/golden/make_golden_trans.py): TransdimensionalEPiC.forward and JumpSampler.sample."""
 import os
+from types import SimpleNamespace
 
 import numpy as np
 import pytest
@@ -99,3 +100,71 @@ def test_sampler_whole_trajectory(gold):
     assert np.array_equal(dims, z["smp/dims_final"])
     np.testing.assert_allclose(x, z["smp/x_final"], rtol=1e-4, atol=2e-3)
     np.testing.assert_allclose(oh, z["smp/oh_final"], rtol=1e-4, atol=2e-3)
+
+
+def test_sampler_c_time_grid(gold):
+    """dt_schedule='C' + no_noise_final_step (sampler.py:79-88, 230): the reference's time grid and final state."""
+    z, cfg, model, packed = gold
+    B, N, S = z["smpC/oh_final"].shape
+    sched = jump_schedule(float(z["smp/dt"]), model.noise_schedule, True, "C", 0.1, 0.04, 0.5)
+    assert sched.n_steps == len(z["smpC/ts"]) and np.array_equal(sched.ts, z["smpC/ts"])
+    assert sched.c_noise[-1] == 0.0 and np.all(sched.c_noise[:-1] > 0)
+    n = sched.n_steps
+    x, oh, dims = ol.trans_initial_state(z["smp/z_init"], N, S)
+    x, oh, dims = ol.trans_sample(packed, x, oh, dims, sched, model.forward_rate.as_c(), z["smp/z_diff"][:n], z["smp/u_near"][:n],
+                                  z["smp/u_jump"][:n], z["smp/z_new"][:n])
+    assert np.array_equal(dims, z["smpC/dims_final"])
+    np.testing.assert_allclose(x, z["smpC/x_final"], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(oh, z["smpC/oh_final"], rtol=1e-4, atol=2e-3)
+
+
+def _corrector_schedule(z, model):
+    import json
+    kw = json.loads(str(z["smpL/kwargs"]))
+    return jump_schedule(float(z["smpL/dt"]), model.noise_schedule, kw["no_noise_final_step"], corrector_steps=kw["corrector_steps"],
+                         corrector_snr=kw["corrector_snr"], corrector_start_time=kw["corrector_start_time"],
+                         corrector_finish_time=kw["corrector_finish_time"], do_jump_corrector=kw["do_jump_corrector"],
+                         forward_rate=model.forward_rate)
+
+
+def test_corrector_rows_follow_the_reference(gold):
+    """Langevin corrector + jump corrector (sampler.py:258-312): every evaluation of the reference run, restarted from
+    the reference's recorded state, lands on the reference's next state."""
+    z, cfg, model, packed = gold
+    sched = _corrector_schedule(z, model)
+    assert sched.n_steps == len(z["smpL/ts"]) and np.array_equal(sched.ts, z["smpL/ts"])
+    assert sched.kind.sum() == 24 and sched.c_noise[-1] == 0.0 and sched.kind[-1] == 1 and sched.c_noise[-3] > 0
+    one = lambda i: SimpleNamespace(n_steps=1, kind=sched.kind[i:i + 1], ts=sched.ts[i:i + 1], c_decay=sched.c_decay[i:i + 1],
+                                    c_score=sched.c_score[i:i + 1], c_noise=sched.c_noise[i:i + 1], inv_std=sched.inv_std[i:i + 1],
+                                    death_prob=sched.death_prob[i:i + 1], jump_dt=sched.jump_dt, corrector_snr=sched.corrector_snr,
+                                    jump_corrector=sched.jump_corrector)
+    births = deaths = stale = 0
+    for i in range(sched.n_steps):
+        x, oh, dims = z["smpL/x_traj"][i], z["smpL/oh_traj"][i], z["smpL/dims_traj"][i]
+        if sched.kind[i] == 0:
+            mask_dims = dims   # the corrector rows reuse the mask of their predictor step (sampler.py:219)
+        stale += int((mask_dims != dims).any())
+        x2, oh2, d2 = ol.trans_sample(packed, x, oh, dims, one(i), model.forward_rate.as_c(), z["smpL/z_diff"][i:i + 1],
+                                      z["smpL/u_near"][i:i + 1], z["smpL/u_jump"][i:i + 1], z["smpL/z_new"][i:i + 1],
+                                      z["smpL/u_death"][i:i + 1], mask_dims)
+        last = i + 1 == sched.n_steps
+        rx, ro, rd = ((z["smpL/x_final"], z["smpL/oh_final"], z["smpL/dims_final"]) if last else
+                      (z["smpL/x_traj"][i + 1], z["smpL/oh_traj"][i + 1], z["smpL/dims_traj"][i + 1]))
+        assert np.array_equal(d2, rd), f"row {i}"
+        births += int((rd > dims).sum()) if sched.kind[i] else 0
+        deaths += int((rd < dims).sum())
+        np.testing.assert_allclose(x2, rx, rtol=2e-5, atol=3e-5, err_msg=f"row {i}")
+        np.testing.assert_allclose(oh2, ro, rtol=2e-5, atol=3e-5, err_msg=f"row {i}")
+    assert births >= 1 and deaths >= 1 and stale >= 1   # both jumps of the corrector, and correctors with a stale mask
+
+
+def test_corrector_whole_trajectory(gold):
+    z, cfg, model, packed = gold
+    B, N, S = z["smpL/oh_final"].shape
+    sched = _corrector_schedule(z, model)
+    x, oh, dims = ol.trans_initial_state(z["smpL/z_init"], N, S)
+    x, oh, dims = ol.trans_sample(packed, x, oh, dims, sched, model.forward_rate.as_c(), z["smpL/z_diff"], z["smpL/u_near"],
+                                  z["smpL/u_jump"], z["smpL/z_new"], z["smpL/u_death"])
+    assert np.array_equal(dims, z["smpL/dims_final"])
+    np.testing.assert_allclose(x, z["smpL/x_final"], rtol=1e-3, atol=5e-3)
+    np.testing.assert_allclose(oh, z["smpL/oh_final"], rtol=1e-3, atol=5e-3)
