@@ -8,50 +8,69 @@
 namespace mmb {
 
 // counts layout: [Dc][bins] feature histograms | [S] token counts | [max_mult + 1] multiplicities
-__global__ void __launch_bounds__(128)
+// One WARP per jet (grid-stride), no block barrier inside the pass.  Feature bins go to a histogram private to the warp (shared-
+// memory atomics only collide inside one warp), token counts are ballots accumulated in a register of lane s, the multiplicity
+// is a popcount; the block merges its warps once at the end and adds to the global int64 counts.  14 B per particle read.
+constexpr int kHistWarps = 8;
+__global__ void __launch_bounds__(kHistWarps * 32)
 validation_histograms_kernel(const float* __restrict__ x, const uint8_t* __restrict__ k, const uint8_t* __restrict__ mask,
                              int B, int N, int Dc, int S, int bins, float lo, float scale, int max_mult,
                              unsigned long long* __restrict__ counts) {
-    extern __shared__ unsigned int hist[];  // Dc*bins + S + max_mult + 1
-    const int size = Dc * bins + S + max_mult + 1;
-    for (int i = threadIdx.x; i < size; i += blockDim.x) hist[i] = 0u;
+    extern __shared__ unsigned int hist[];  // kHistWarps x (Dc*bins) | S + max_mult + 1
+    const int nf = Dc * bins, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int* mine = hist + warp * nf;
+    unsigned int* shared_tail = hist + kHistWarps * nf;   // [S] tokens, [max_mult + 1] multiplicities
+    for (int i = threadIdx.x; i < kHistWarps * nf + S + max_mult + 1; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
-    for (int jet = blockIdx.x; jet < B; jet += gridDim.x) {
+    unsigned int tok_count = 0;   // lane s counts token s
+    for (int jet = blockIdx.x * kHistWarps + warp; jet < B; jet += gridDim.x * kHistWarps) {
         int live_here = 0;
-        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        for (int n0 = 0; n0 < N; n0 += 32) {
+            const int n = n0 + lane;
             const size_t p = (size_t)jet * N + n;
-            if (mask[p]) {
-                ++live_here;
+            const bool live = n < N && mask[p] != 0;
+            int tok = -1;
+            if (live) {
+                tok = k[p];
                 for (int c = 0; c < Dc; ++c) {
                     int b = (int)floorf((x[p * Dc + c] - lo) * scale);
                     b = b < 0 ? 0 : (b > bins - 1 ? bins - 1 : b);
-                    atomicAdd(&hist[c * bins + b], 1u);
+                    atomicAdd(&mine[c * bins + b], 1u);
                 }
-                atomicAdd(&hist[Dc * bins + k[p]], 1u);
+            }
+            live_here += __popc(__ballot_sync(0xffffffffu, live));
+            if (S <= 32) {
+                for (int s = 0; s < S; ++s) {
+                    const unsigned int votes = __popc(__ballot_sync(0xffffffffu, tok == s));
+                    if (lane == s) tok_count += votes;
+                }
+            } else if (live) {
+                atomicAdd(&shared_tail[tok], 1u);
             }
         }
-        // block-wide sum of live_here
-        __shared__ int part[4];
-        const int w = __reduce_add_sync(0xffffffffu, live_here);
-        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int m = part[0] + part[1] + part[2] + part[3];
-            m = m > max_mult ? max_mult : m;
-            atomicAdd(&hist[Dc * bins + S + m], 1u);
-        }
-        __syncthreads();
+        if (lane == 0) atomicAdd(&shared_tail[S + (live_here > max_mult ? max_mult : live_here)], 1u);
     }
+    if (S <= 32 && lane < S && tok_count) atomicAdd(&shared_tail[lane], tok_count);
     __syncthreads();
-    for (int i = threadIdx.x; i < size; i += blockDim.x)
-        if (hist[i]) atomicAdd(&counts[i], (unsigned long long)hist[i]);
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        unsigned int a = 0;
+        for (int w = 0; w < kHistWarps; ++w) a += hist[w * nf + i];
+        if (a) atomicAdd(&counts[i], (unsigned long long)a);
+    }
+    for (int i = threadIdx.x; i < S + max_mult + 1; i += blockDim.x)
+        if (shared_tail[i]) atomicAdd(&counts[nf + i], (unsigned long long)shared_tail[i]);
 }
 
 int launch_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,
                                  int bins, float lo, float hi, int max_mult, unsigned long long* counts, cudaStream_t stream) {
-    const int size = Dc * bins + S + max_mult + 1;
-    const int grid = B < 148 * 4 ? B : 148 * 4;
-    validation_histograms_kernel<<<grid, 128, size * sizeof(unsigned int), stream>>>(
+    const size_t smem = ((size_t)kHistWarps * Dc * bins + S + max_mult + 1) * sizeof(unsigned int);
+    if (smem > 200 * 1024) return fail(MMB_EUNSUPPORTED, "validation histograms: %d x %d bins do not fit in shared memory", Dc, bins);
+    if (smem > 48 * 1024)
+        if (int rc = cuda_ok(cudaFuncSetAttribute(validation_histograms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "histogram smem"))
+            return rc;
+    const int jets_per_block_pass = kHistWarps, want = (B + jets_per_block_pass - 1) / jets_per_block_pass;
+    const int grid = want < 148 * 8 ? (want > 0 ? want : 1) : 148 * 8;
+    validation_histograms_kernel<<<grid, kHistWarps * 32, smem, stream>>>(
         x, k, mask, B, N, Dc, S, bins, lo, (float)bins / (hi - lo), max_mult, counts);
     return cuda_ok(cudaGetLastError(), "validation_histograms launch");
 }
