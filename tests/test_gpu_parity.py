@@ -235,6 +235,13 @@ def test_full_size_c2_properties():
     out = model.simulate_dynamics(mk(), b, precision="fp32", jet_offset=0)
     again = model.simulate_dynamics(mk(), b, precision="fp32", jet_offset=0)
     assert torch.equal(out.continuous, again.continuous) and torch.equal(out.discrete, again.discrete)
+    # the host -> host call above ran as pipeline slices on their own streams; one slice and odd slicings give the same jets
+    assert model.pipeline_chunks > 1 and 4096 >= model.pipeline_chunks * model.pipeline_min_jets
+    for chunks in (1, 3):
+        model.pipeline_chunks = chunks
+        whole = model.simulate_dynamics(mk(), b, precision="fp32", jet_offset=0)
+        assert torch.equal(out.continuous, whole.continuous) and torch.equal(out.discrete, whole.discrete)
+    model.pipeline_chunks = 4
     part = model.simulate_dynamics(mk(slice(1000, 1100)), b, precision="fp32", jet_offset=1000)
     assert torch.equal(part.continuous, out.continuous[1000:1100]) and torch.equal(part.discrete, out.discrete[1000:1100])
     dead = b.source_mask == 0
