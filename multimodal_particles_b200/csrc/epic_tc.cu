@@ -346,7 +346,14 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
     const int grp = tid >> 7, gt = tid & 127, wq = gt >> 5, lane = tid & 31;
     // the "special" warp of a group issues its MMAs and runs its per-jet global MLP; warp w lives on SM sub-partition
     // w % 4, so rotating the role with the group index spreads that serial work over all four schedulers
-    const int swq = grp & 3;
+    const long jet = (long)blockIdx.x * kJPC + grp;
+    // Generation: a jet's particles sit live-first (prefix mask), so the row quarters 1..3 of most jets are dead.  The tile rows
+    // are rotated by `rot` quarters per jet (the network is permutation-invariant; keyed by the GLOBAL jet index, so results do
+    // not depend on the batch slicing): the live quarters of the four jets of a CTA land on four different SM sub-partitions,
+    // warps whose 32 particles are all dead skip every epilogue (their A rows stay zero, they only keep the barriers), and the
+    // special role goes to the warp of the last quarter, which is the least likely to have row work of its own.
+    const int rot = GENERATE ? (int)((p.jet_offset + (uint64_t)jet) & 3) : 0;
+    const int swq = GENERATE ? ((rot + 3) & 3) : (grp & 3);
     uint8_t* abuf = s_grp + grp * kGrpBytes;
     uint8_t* amask = abuf + 4096;   // A tile of the bias K-steps: columns 0,1 = mask of the row's particle
     uint8_t* bb0 = abuf + 8192;     // B tile carrying this step's local_0 bias (hi, lo) in columns 0,1
@@ -364,11 +371,11 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
     const uint32_t t_pool = t_main + 16, t_skip = t_main + 32;
     const uint32_t d_main = tmem_base + grp * kTmemPerJet, d_pool = d_main + 16;
 
-    const long jet = (long)blockIdx.x * kJPC + grp;
     if (jet < p.B) {
-        const int N = p.N, r = gt;
-        const bool valid = r < N;
-        const size_t pidx = (size_t)jet * N + r;
+        const int N = p.N, r = gt;                       // r: tile row (TMEM lane); n: the particle it carries
+        const int n = (r + 128 - 32 * rot) & 127;
+        const bool valid = n < N;
+        const size_t pidx = (size_t)jet * N + n;
         // ---- state
         float xs[DC];
         int kk = 0, m = 0;
@@ -390,9 +397,19 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             *reinterpret_cast<uint4*>(q + 128) = make_uint4(0u, 0u, 0u, 0u);
             if (gt < 32) reinterpret_cast<uint4*>(bb0)[gt] = make_uint4(0u, 0u, 0u, 0u);
         }
+        bool skip = false;   // this warp has no live particle: no epilogue work at all (generation only)
         {
             const unsigned bal = __ballot_sync(0xffffffffu, m);
             if (lane == 0) jv.cnt[wq] = __popc(bal);
+            if constexpr (GENERATE) {
+                skip = bal == 0u;
+                if (skip) {   // its A rows are never written again: zero them once
+                    float zero[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) zero[i] = 0.0f;
+                    store_a_row(abuf, r, zero);
+                }
+            }
         }
         group_bar(1 + grp);
         const float inv_cnt = 1.0f / (float)(jv.cnt[0] + jv.cnt[1] + jv.cnt[2] + jv.cnt[3]);
@@ -475,7 +492,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     if (hf == 0) { jv.tv_g1[l][o16] = b0; jv.tv_l1[l][o16] = b1; }
                 }
             }
-            {
+            if (!skip) {
                 float row[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) row[i] = 0.0f;
@@ -503,10 +520,12 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_after();
             MMB_TRACE(2);
             float acc[16], xl[16];
-            tmem_ld16(t_main, acc);
-            lrelu16(xl, acc);
-            if (lay.skip) tmem_st16(t_skip, xl);   // x_local_skip (epic.py:148) parked in TMEM, not in registers
-            store_a_row(abuf, r, xl);
+            if (!skip) {
+                tmem_ld16(t_main, acc);
+                lrelu16(xl, acc);
+                if (lay.skip) tmem_st16(t_skip, xl);   // x_local_skip (epic.py:148) parked in TMEM, not in registers
+                store_a_row(abuf, r, xl);
+            }
             tc_fence_before();
             fence_proxy_async();
             group_bar(1 + grp);
@@ -580,8 +599,8 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(4 + 4 * l);
                 // ---- (f) fc_local1 epilogue -> A operand of fc_local2
                 tc_fence_after();
-                tmem_ld16(t_main, acc);
-                {
+                if (!skip) {
+                    tmem_ld16(t_main, acc);
                     float l1[16], bl[16];
                     lds16(jv.bias_l1, bl);
                     lrelu16_sum(l1, acc, bl);
@@ -601,14 +620,16 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 wait_mma();
                 MMB_TRACE(6 + 4 * l);
                 tc_fence_after();
-                tmem_ld16(t_main, acc);
-                lrelu16_sum(xl, acc, xl);  // dead rows: unused garbage, zeroed at pack
-                if (lay.skip) {
-                    tmem_ld16(t_skip, acc);
+                if (!skip) {
+                    tmem_ld16(t_main, acc);
+                    lrelu16_sum(xl, acc, xl);  // dead rows: unused garbage, zeroed at pack
+                    if (lay.skip) {
+                        tmem_ld16(t_skip, acc);
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) fadd2(xl[i], xl[i + 1], xl[i], xl[i + 1], acc[i], acc[i + 1]);
+                        for (int i = 0; i < 16; i += 2) fadd2(xl[i], xl[i + 1], xl[i], xl[i + 1], acc[i], acc[i + 1]);
+                    }
+                    store_a_row_masked(abuf, r, xl, live);
                 }
-                store_a_row_masked(abuf, r, xl, live);
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
@@ -628,10 +649,10 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_after();
             MMB_TRACE(12);
             float h[16];
-            tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
+            if (!skip) tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
             float lg[S];
             if constexpr (SH > 0) {
-                {
+                if (!skip) {
                     float z1[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) z1[i] = i < SH ? selu_fast(h[DC + (i < SH ? i : 0)]) : 0.0f;
@@ -649,7 +670,8 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 wait_mma();
                 tc_fence_after();
                 MMB_TRACE(14);
-                if constexpr (S <= 8) {
+                if (skip) {
+                } else if constexpr (S <= 8) {
                     float l8[8];
                     tmem_ld8(t_main, l8);
 #pragma unroll
@@ -666,7 +688,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_before();  // orders this step's last tcgen05.ld before the next step's first MMA (via the group barrier)
             MMB_TRACE(15);
 
-            if constexpr (GENERATE) {
+            if constexpr (GENERATE) if (!skip) {
                 // ---- (k) hybrid update in registers (bridges.py:38-45,179-201)
                 const StepScalars sc{p.dt, __ldg(p.step_tab + step * 4 + 0), __ldg(p.step_tab + step * 4 + 1), 0.0f};
 #pragma unroll
@@ -676,7 +698,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 // four steps and a 4 x 4 transpose inside the quad (four shuffles) hands every lane its own word of each step:
                 // the same (seed, jet, step, particle) -> uniform map as philox_uniform(), a quarter of the arithmetic.
                 if (!p.u_jump && (step & 3) == 0) {
-                    const uint4 blk = philox_block(p.seed, p.jet_offset + (uint64_t)jet, 0, step + (r & 3), r >> 2);
+                    const uint4 blk = philox_block(p.seed, p.jet_offset + (uint64_t)jet, 0, step + (n & 3), n >> 2);
                     uint32_t a0 = blk.x, a1 = blk.y, a2 = blk.z, a3 = blk.w;
                     {   // exchange 2 x 2 blocks with lane ^ 2
                         const bool hi = (lane & 2) != 0;
@@ -692,12 +714,13 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 }
                 if (valid) {
                     const int ph = step & 3;
-                    const float u = p.u_jump ? __ldg(p.u_jump + ((size_t)step * p.B + jet) * N + r)
+                    const float u = p.u_jump ? __ldg(p.u_jump + ((size_t)step * p.B + jet) * N + n)
                                              : u01(ph == 0 ? uq0 : ph == 1 ? uq1 : ph == 2 ? uq2 : uq3);
                     kk = telegraph_jump_fast<S>(lg, kk, u, sc) * m;
                 }
                 MMB_TRACE(16);
-            } else {
+            }
+            if constexpr (!GENERATE) {
                 if (valid) {
 #pragma unroll
                     for (int c = 0; c < DC; ++c) p.v_out[pidx * DC + c] = h[c];
