@@ -130,9 +130,45 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 in, fp32 accumulate); one thread issues
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// The pooling GEMM: up to eight K-steps (B descriptor advances by 512 B = 32 address units per step) into one accumulator.
+// All descriptors are formed before the first MMA so their moves to uniform registers can overlap; K-steps whose bit in
+// `live` is clear are skipped (their rows are all zero); the first issued step overwrites, the rest accumulate.
+__device__ __forceinline__ void umma_pool8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc0, uint32_t idesc, uint32_t live) {
+    if (live == 0u) live = 1u;   // nothing live: one step over zero rows still defines the accumulator
+    const uint32_t first = live & (0u - live);   // lowest set bit: the step that does not accumulate
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e0, e1, e2, e3, e4, e5, e6, e7, a0, a1, a2, a3, a4, a5, a6, a7;\n\t"
+        ".reg .b64 b1, b2, b3, b4, b5, b6, b7;\n\t"
+        ".reg .b32 t;\n\t"
+        "add.s64 b1, %2, 32;\n\t add.s64 b2, %2, 64;\n\t add.s64 b3, %2, 96;\n\t add.s64 b4, %2, 128;\n\t"
+        "add.s64 b5, %2, 160;\n\t add.s64 b6, %2, 192;\n\t add.s64 b7, %2, 224;\n\t"
+        "and.b32 t, %4, 1;\n\t setp.ne.b32 e0, t, 0;\n\t and.b32 t, %4, 2;\n\t setp.ne.b32 e1, t, 0;\n\t"
+        "and.b32 t, %4, 4;\n\t setp.ne.b32 e2, t, 0;\n\t and.b32 t, %4, 8;\n\t setp.ne.b32 e3, t, 0;\n\t"
+        "and.b32 t, %4, 16;\n\t setp.ne.b32 e4, t, 0;\n\t and.b32 t, %4, 32;\n\t setp.ne.b32 e5, t, 0;\n\t"
+        "and.b32 t, %4, 64;\n\t setp.ne.b32 e6, t, 0;\n\t and.b32 t, %4, 128;\n\t setp.ne.b32 e7, t, 0;\n\t"
+        "setp.ne.b32 a0, %5, 1;\n\t setp.ne.b32 a1, %5, 2;\n\t setp.ne.b32 a2, %5, 4;\n\t setp.ne.b32 a3, %5, 8;\n\t"
+        "setp.ne.b32 a4, %5, 16;\n\t setp.ne.b32 a5, %5, 32;\n\t setp.ne.b32 a6, %5, 64;\n\t setp.ne.b32 a7, %5, 128;\n\t"
+        "@e0 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, a0;\n\t"
+        "@e1 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b1, %3, a1;\n\t"
+        "@e2 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b2, %3, a2;\n\t"
+        "@e3 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b3, %3, a3;\n\t"
+        "@e4 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b4, %3, a4;\n\t"
+        "@e5 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b5, %3, a5;\n\t"
+        "@e6 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b6, %3, a6;\n\t"
+        "@e7 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b7, %3, a7;\n\t"
+        "}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc0), "r"(idesc), "r"(live), "r"(first) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -316,6 +352,7 @@ struct JetVec {
     float gv[16], gv2[16], xg[kGP], xgmid[kGP], skipg[kGP], bias_l1[16];
     float tv_bias0[16], tv_g0[16], tv_g1[kMaxL][16], tv_l1[kMaxL][16];
     int cnt[4];
+    uint32_t live16[4];   // per row quarter: bit 0 / 1 = rows 0-15 / 16-31 of the quarter hold a live particle
 };
 
 template <int DC, int S, int SH, bool GENERATE, bool TRACE = false>
@@ -343,7 +380,11 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         const uint32_t one2 = 0x3F803F80u;  // bf16 1.0 twice
         for (int i = tid; i < 256; i += blockDim.x) reinterpret_cast<uint4*>(s_ones)[i] = make_uint4(one2, one2, one2, one2);
     }
-    const int grp = tid >> 7, gt = tid & 127, wq = gt >> 5, lane = tid & 31;
+    // warp-uniform indices come from a broadcast so that the compiler keeps everything derived from them (shared-memory
+    // addresses, TMEM addresses, UMMA descriptors) in uniform registers: a tcgen05.mma whose operands are not provably uniform
+    // is wrapped in an elect/broadcast loop of ~15 instructions
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int grp = warp_u >> 2, gt = tid & 127, wq = warp_u & 3, lane = tid & 31;
     // the "special" warp of a group issues its MMAs and runs its per-jet global MLP; warp w lives on SM sub-partition
     // w % 4, so rotating the role with the group index spreads that serial work over all four schedulers
     const long jet = (long)blockIdx.x * kJPC + grp;
@@ -366,7 +407,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = s_tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, s_tmem_slot, 0);
     const uint32_t t_main = tmem_base + grp * kTmemPerJet + ((uint32_t)(wq * 32) << 16);
     const uint32_t t_pool = t_main + 16, t_skip = t_main + 32;
     const uint32_t d_main = tmem_base + grp * kTmemPerJet, d_pool = d_main + 16;
@@ -400,7 +441,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         bool skip = false;   // this warp has no live particle: no epilogue work at all (generation only)
         {
             const unsigned bal = __ballot_sync(0xffffffffu, m);
-            if (lane == 0) jv.cnt[wq] = __popc(bal);
+            if (lane == 0) { jv.cnt[wq] = __popc(bal); jv.live16[wq] = ((bal & 0xffffu) ? 1u : 0u) | ((bal >> 16) ? 2u : 0u); }
             if constexpr (GENERATE) {
                 skip = bal == 0u;
                 if (skip) {   // its A rows are never written again: zero them once
@@ -413,6 +454,8 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         }
         group_bar(1 + grp);
         const float inv_cnt = 1.0f / (float)(jv.cnt[0] + jv.cnt[1] + jv.cnt[2] + jv.cnt[3]);
+        // K-steps of the pooling GEMM (16 particles each) that hold a live particle; the others would add zeros
+        const uint32_t pool_live = __shfl_sync(0xffffffffu, GENERATE ? (jv.live16[0] | (jv.live16[1] << 2) | (jv.live16[2] << 4) | (jv.live16[3] << 6)) : 0xffu, 0);
 
         const uint32_t a_addr = smem_u32(abuf);
         const uint32_t bops_addr = smem_u32(s_bops);
@@ -510,7 +553,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             group_bar(1 + grp);
             MMB_TRACE(1);
             // ---- (b) local_0
-            if (gt == swq * 32) {
+            if (wq == swq && elect_one()) {
                 tc_fence_after();
                 gemm(lay.bop_local0());
                 umma(d_main, amask_desc, bb0_desc, idesc_k, 1);  // + bias on live rows; dead rows stay exactly 0
@@ -534,11 +577,9 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             for (int l = 0; l < L; ++l) {
                 const float* Wl = s_wf + lay.layer0 + l * lay.layer_stride;
                 // ---- (d) pooling GEMM (ones x XL, K = 128 particles) + fc_local1 on the same tile
-                if (gt == swq * 32) {
+                if (wq == swq && elect_one()) {
                     tc_fence_after();
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)  // K-step j = particles 16j..16j+15: two 8-row groups, MN-major
-                        umma(d_pool, ones_desc, pool_desc0 + (uint64_t)(j * 32), idesc_pool, j > 0);
+                    umma_pool8(d_pool, ones_desc, pool_desc0, idesc_pool, pool_live);  // K-step j = rows 16j..16j+15, MN-major
                     gemm(lay.bop_l1(l));
                     umma_commit(mbar);
                 }
@@ -611,7 +652,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 group_bar(1 + grp);
                 MMB_TRACE(5 + 4 * l);
                 // ---- (g) fc_local2
-                if (gt == swq * 32) {
+                if (wq == swq && elect_one()) {
                     tc_fence_after();
                     gemm(lay.bop_l2(l));
                     umma(d_main, amask_desc, bop_desc(lay.bop_bias_l2(l)), idesc_k, 1);
@@ -636,7 +677,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(7 + 4 * l);
             }
             // ---- (i) output layer (epic.py:158-162)
-            if (gt == swq * 32) {
+            if (wq == swq && elect_one()) {
                 tc_fence_after();
                 // with a discrete head the operand is [W_out(v rows) ; F1 W_out(z rows)]: the output layer and the first
                 // head Linear have no nonlinearity between them, so columns DC.. are already F1 z + f1 (mbm.py:105-111)
@@ -661,7 +702,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
-                if (gt == swq * 32) {
+                if (wq == swq && elect_one()) {
                     tc_fence_after();
                     gemm(lay.bop_h2());
                     umma(d_main, ones_desc, bop_desc(lay.bop_bias_h2()), idesc_k, 1);
