@@ -69,6 +69,12 @@ __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
@@ -223,7 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     __shared__ __align__(16) float s_part[4 * NQ][CW];      // per-warp partial sums (GroupNorm statistics / column sums)
     __shared__ float s_rowx[NQ][128], s_sum[NQ][128];       // softmax row max and row sum per (channel slice, row)
     float (*s_dot)[128] = s_rowx;                           // per-particle output partials (after the last softmax)
-    const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7, warp = tid >> 5, lane = tid & 31;
+    // the warp index is broadcast so that the compiler sees it (and what derives from it) as warp-uniform
+    const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int nblk = p.n_blocks, n_seq = 1 + 6 * nblk;
     uint8_t *sA = smem + kOffA, *sQ = smem + kOffQ, *sK = smem + kOffK, *sV = smem + kOffV, *sOnes = smem + kOffOnes;
     float* sTab = reinterpret_cast<float*>(smem + kOffTab);
@@ -240,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = s_tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, s_tmem_slot, 0);   // broadcast: provably warp-uniform, so UMMA operands stay in uniform registers
     const uint32_t lane_off = ((uint32_t)((warp & 3) * 32) << 16);   // this warp's TMEM lane quarter
     const int col0 = cq * CW;                                        // this thread's accumulator columns
     const uint32_t dX = tmem, dACC = tmem + 128, dS0 = tmem + 256, dS1 = tmem + 384;
@@ -269,7 +276,16 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     const uint32_t aA = smem_u32(sA), aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
 
     // D (+)= A[128 x 16*nk] * W^T with the streamed matrix `wseq`; optional bias K-step; commit.  Thread 0.
-    auto gemm_w = [&](uint32_t d, uint32_t a_addr, uint32_t a_sbo, int nk, bool accumulate, bool bias, uint32_t bar_done) {
+    // MMA issue: warp 0 enters as a whole, broadcasts the streamed-matrix counter (a tcgen05.mma whose descriptor operands are
+    // not provably warp-uniform is wrapped by the compiler in an elect/broadcast loop of ~15 instructions per instruction), and
+    // one elected lane issues.
+    auto mma_issue = [&](auto&& fn) {
+        if (warp == 0) {
+            const uint32_t ws = __shfl_sync(0xffffffffu, wseq, 0);
+            if (elect_one()) fn(ws);
+        }
+    };
+    auto gemm_w = [&](uint32_t wseq, uint32_t d, uint32_t a_addr, uint32_t a_sbo, int nk, bool accumulate, bool bias, uint32_t bar_done) {
         const uint32_t wb = w_addr(wseq & 1);
         mbar_wait((wseq & 1) ? bar_full1 : bar_full0, (wseq >> 1) & 1);
         tc_fence_after();
@@ -283,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
     // The q and k projections as one M128 x N256 GEMM over the two ring slots: D columns [0,128) come from the matrix in
     // slot 0, [128,256) from the one in slot 1 (which of q, k sits where alternates from jet to jet: n_seq is odd).
     // The q bias rides on one more K-step into q's half.  Thread 0.
-    auto gemm_qk = [&](uint32_t d, uint32_t a_addr) {
+    auto gemm_qk = [&](uint32_t wseq, uint32_t d, uint32_t a_addr) {
         mbar_wait((wseq & 1) ? bar_full1 : bar_full0, (wseq >> 1) & 1);
         mbar_wait(((wseq + 1) & 1) ? bar_full1 : bar_full0, ((wseq + 1) >> 1) & 1);
         tc_fence_after();
@@ -444,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         fence_proxy_async();
         __syncthreads();
         STK_TRACE(1);
-        if (tid == 0) gemm_w(dX, smem_u32(sA0), 512, 2, false, true, bar_mma);
+        mma_issue([&](uint32_t ws) { gemm_w(ws, dX, smem_u32(sA0), 512, 2, false, true, bar_mma); });
         mma_done(1);
         STK_TRACE(2);
 
@@ -453,19 +469,19 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             // ---- ResnetBlock (gsdm.py:54-66)
             group_norm_to_A(dX, nullptr, T + 0 * kC, T + 1 * kC, true, valid);
             if (blk == 0) STK_TRACE(3);
-            if (tid == 0) gemm_w(dACC, aA, 2048, 8, false, false, bar_mma);           // conv1
+            mma_issue([&](uint32_t ws) { gemm_w(ws, dACC, aA, 2048, 8, false, false, bar_mma); });           // conv1
             mma_done(1);
             if (blk == 0) STK_TRACE(4);
             group_norm_to_A(dACC, s_bias2 + blk * kC, T + 3 * kC, T + 4 * kC, true, valid);
             if (blk == 0) STK_TRACE(5);
-            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true, bar_mma);               // X += conv2(.) + b2
+            mma_issue([&](uint32_t ws) { gemm_w(ws, dX, aA, 2048, 8, true, true, bar_mma); });               // X += conv2(.) + b2
             mma_done(1);
             if (blk == 0) STK_TRACE(6);
             // ---- AttnBlock (gsdm.py:142-168)
             group_norm_to_A(dX, nullptr, T + 5 * kC, T + 6 * kC, false, valid);
             if (blk == 0) STK_TRACE(7);
             const uint32_t q_half = wseq & 1;                                // q sits in ring slot wseq & 1
-            if (tid == 0) gemm_qk(dACC, aA);                                 // [q | k] (+ bq), one N = 256 GEMM into ACC | S0
+            mma_issue([&](uint32_t ws) { gemm_qk(ws, dACC, aA); });                                 // [q | k] (+ bq), one N = 256 GEMM into ACC | S0
             mma_done(2);
             if (blk == 0) STK_TRACE(8);
             {   // both tiles in one epilogue phase
@@ -479,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                 __syncthreads();
             }
             if (blk == 0) STK_TRACE(9);
-            if (tid == 0) {                                                  // S_h = Q_h K_h^T, K = 64
+            mma_issue([&](uint32_t ws) {                                     // S_h = Q_h K_h^T, K = 64
                 tc_fence_after();
                 const uint64_t qd = smem_desc(aQ, 128, 2048), kd = smem_desc(aK, 128, 2048);
 #pragma unroll
@@ -488,8 +504,8 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                     for (int j = 0; j < 4; ++j)   // head h = K-steps 4h .. 4h+3 of the Q and K tiles (1024 B = 64 in the address field)
                         umma(h ? dS1 : dS0, qd + (uint64_t)(h * 64 + j * 16), kd + (uint64_t)(h * 64 + j * 16), idesc128, j > 0);
                 umma_commit(bar_mma);
-                gemm_w(dACC, aA, 2048, 8, false, false, bar_mma2);            // v: runs under the softmax, its own barrier
-            }
+                gemm_w(ws, dACC, aA, 2048, 8, false, false, bar_mma2);        // v: runs under the softmax, its own barrier
+            });
             mma_done(0);
             if (blk == 0) STK_TRACE(11);
             // softmax over the N keys: thread (r, cq) serves head cq / HQ, keys [2 CW (cq % HQ), + 2 CW); the HQ threads of a
@@ -552,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             if (blk == 0) STK_TRACE(34);
             __syncthreads();
             if (blk == 0) STK_TRACE(12);
-            if (tid == 0) {                                                  // O_h = P_h V_h, K = 128 keys, N = 64
+            mma_issue([&](uint32_t) {                                        // O_h = P_h V_h, K = 128 keys, N = 64
                 tc_fence_after();
                 const uint64_t vd = smem_desc(aV, 2048, 128);
 #pragma unroll
@@ -563,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
                         umma(dACC + hh * 64, pd + (uint64_t)(j * 16), vd + (uint64_t)(hh * 64 + j * 256), idesc64mn, j > 0);
                 }
                 umma_commit(bar_mma);
-            }
+            });
             mma_done(0);
             if (blk == 0) STK_TRACE(13);
             if (stage_ok && blk == nblk - 1 && jet + (int)gridDim.x < p.B) prefetch_inputs(jet + gridDim.x);   // V is dead now
@@ -582,7 +598,7 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
             fence_proxy_async();
             __syncthreads();
             if (blk == 0) STK_TRACE(14);
-            if (tid == 0) gemm_w(dX, aA, 2048, 8, true, true, bar_mma);               // X += proj_out(.) + (b_o + W_o b_v)
+            mma_issue([&](uint32_t ws) { gemm_w(ws, dX, aA, 2048, 8, true, true, bar_mma); });               // X += proj_out(.) + (b_o + W_o b_v)
             mma_done(1);
             if (blk == 0) STK_TRACE(15);
         }

@@ -320,7 +320,7 @@ __device__ __forceinline__ float softplus(float a) { return a > 20.0f ? a : log1
 // The one-hot block of the update is purely element-wise (sampler.py:221-231 on the one-hot slots): one thread per particle slot
 // over a flat grid, 96 B per live slot (one-hot r+w 64, logits 32), two Philox blocks for its eight normals.  It runs BEFORE the
 // continuous kernel below (which updates dims and writes the one-hot row of a newborn particle into slot `dims`).
-template <int S>
+template <int S, bool CORR>   // CORR: corrector row (device coefficients, predictor-step mask)
 __global__ void __launch_bounds__(256) trans_sampler_onehot_kernel(float* __restrict__ onehot, const int32_t* __restrict__ dims,
                                                                    const float* __restrict__ logits, float c_decay, float cs, float c_noise,
                                                                    const float* __restrict__ coef, const int32_t* __restrict__ mask_dims,
@@ -331,8 +331,10 @@ __global__ void __launch_bounds__(256) trans_sampler_onehot_kernel(float* __rest
     if (pi >= (size_t)B * N) return;
     const int b = (int)(pi / N), n = (int)(pi % N);
     if (n >= __ldg(dims + b)) return;
-    if (mask_dims && n >= __ldg(mask_dims + b)) return;   // corrector rows: the predictor step's mask (sampler.py:219, 277-279)
-    if (coef) { c_decay = __ldg(coef); cs = __ldg(coef + 1); c_noise = __ldg(coef + 2); }
+    if constexpr (CORR) {
+        if (n >= __ldg(mask_dims + b)) return;   // corrector rows: the predictor step's mask (sampler.py:219, 277-279)
+        c_decay = __ldg(coef); cs = __ldg(coef + 1); c_noise = __ldg(coef + 2);
+    }
     const bool noisy = c_noise != 0.0f;
     float oh[S], lg[S], z[8];
     if constexpr (S % 4 == 0) {
@@ -383,25 +385,27 @@ __global__ void __launch_bounds__(256) trans_sampler_onehot_kernel(float* __rest
 // are warp shuffles and no block-wide barrier sits in the pass; four jets per 128-thread block.  (The one-hot block is the kernel above.)  Dead slots (n >= dims) hold zeros —
 // the sampler's invariant, asserted by the reference in adjust_st_batch (jets_dataloader.py:451-452) — and stay zero under the
 // update, so they are neither read nor written: the pass moves 133 B per LIVE particle-step.
-template <int S>
+template <int S, int JUMP_MODE>
 __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __restrict__ x, float* __restrict__ onehot, int32_t* __restrict__ dims,
                                                                    const float* __restrict__ v, const float* __restrict__ logits,
                                                                    const float* __restrict__ rate, const float* __restrict__ new_mean,
                                                                    const float* __restrict__ new_std, float c_decay, float c_score,
                                                                    float c_noise, float inv_std, float jump_dt,
                                                                    const float* __restrict__ coef, const int32_t* __restrict__ mask_dims,
-                                                                   int jump_mode, float death_prob,
+                                                                   float death_prob,
                                                                    const float* __restrict__ z_diff, const float* __restrict__ u_jump,
                                                                    const float* __restrict__ u_death,
                                                                    const float* __restrict__ z_new, uint64_t seed, uint64_t jet_offset,
                                                                    int step, int B, int N) {
+    constexpr int jump_mode = JUMP_MODE;
+    constexpr bool CORR = JUMP_MODE != 1;   // corrector rows take device coefficients and the predictor step's mask
     // jump_mode: 1 = predictor row (birth); 0 = corrector row without jumps (one centre-of-mass removal, sampler.py:280-282);
     //            2 = corrector row with the jump corrector (birth and death, sampler.py:285-312)
     constexpr int F = 3 + S, SL = 4;   // up to 128 slots = 4 per lane
     const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= B) return;
     const int dim = dims[b];
-    const int upd = mask_dims ? min(__ldg(mask_dims + b), dim) : dim;   // slots that take the increment (stale mask of a corrector row)
+    const int upd = CORR ? min(__ldg(mask_dims + b), dim) : dim;   // slots that take the increment (stale mask of a corrector row)
     const uint64_t jet = jet_offset + (uint64_t)b;
     bool born = false, dies = false;
     if (jump_mode != 0) {
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(128) trans_sampler_update_kernel(float* __rest
     const int new_dim = born ? dim + 1 : (dies ? dim - 1 : dim);
     const float* zb = z_diff ? z_diff + (size_t)b * N * F : nullptr;
     float cs = -(c_score * inv_std);   // c_score * -(inv_std * D): one rounding apart from the reference order
-    if (coef) { c_decay = __ldg(coef); cs = __ldg(coef + 1); c_noise = __ldg(coef + 2); }
+    if constexpr (CORR) { c_decay = __ldg(coef); cs = __ldg(coef + 1); c_noise = __ldg(coef + 2); }
     const bool noisy = c_noise != 0.0f;
     // ---- continuous block: Euler-Maruyama with the noise centred over the live particles, then centre-of-mass removal,
     //      the birth, and a second centre-of-mass removal (sampler.py:221-255, jets_dataloader.py:433-478)
@@ -796,13 +800,18 @@ static int launch_sampler_update(float* x, float* onehot, int32_t* dims, const f
                                  float jump_dt, const float* z_diff, const float* u_jump, const float* z_new, uint64_t seed,
                                  uint64_t jet_offset, int step, int B, int N, int S, cudaStream_t s, const CorrectorArgs& ca = CorrectorArgs()) {
     if (N > 128 || N < 1) return fail(MMB_EUNSUPPORTED, "sampler update handles 1..128 particle slots per jet");
-#define MMB_UPD(SV)                                                                                                                  \
-    trans_sampler_onehot_kernel<SV><<<(unsigned)(((size_t)B * N + 255) / 256), 256, 0, s>>>(                                           \
+#define MMB_UPD2(SV, MODE)                                                                                                            \
+    trans_sampler_onehot_kernel<SV, MODE != 1><<<(unsigned)(((size_t)B * N + 255) / 256), 256, 0, s>>>(                                \
         onehot, dims, logits, c_decay, -(c_score * inv_std), c_noise, ca.coef, ca.mask_dims, z_diff, seed, jet_offset, step, B, N);     \
-    trans_sampler_update_kernel<SV><<<(B + 3) / 4, 128, 0, s>>>(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay, c_score,  \
-                                                                c_noise, inv_std, jump_dt, ca.coef, ca.mask_dims, ca.jump_mode,         \
-                                                                ca.death_prob, z_diff, u_jump, ca.u_death, z_new, seed, jet_offset,    \
-                                                                step, B, N)
+    trans_sampler_update_kernel<SV, MODE><<<(B + 3) / 4, 128, 0, s>>>(x, onehot, dims, v, logits, rate, new_mean, new_std, c_decay,      \
+                                                                      c_score, c_noise, inv_std, jump_dt, ca.coef, ca.mask_dims,        \
+                                                                      ca.death_prob, z_diff, u_jump, ca.u_death, z_new, seed,          \
+                                                                      jet_offset, step, B, N)
+#define MMB_UPD(SV)                                                                                                                  \
+    do {                                                                                                                             \
+        if (ca.jump_mode == 1) { MMB_UPD2(SV, 1); } else if (ca.jump_mode == 0) { MMB_UPD2(SV, 0); } else { MMB_UPD2(SV, 2); }          \
+    } while (0)
+    if (ca.jump_mode != 1 && (!ca.coef || !ca.mask_dims)) return fail(MMB_EINVAL, "corrector update without coefficients / mask");
     switch (S) {
         case 4: MMB_UPD(4); break;
         case 5: MMB_UPD(5); break;
@@ -810,6 +819,7 @@ static int launch_sampler_update(float* x, float* onehot, int32_t* dims, const f
         case 8: MMB_UPD(8); break;
         default: return fail(MMB_EUNSUPPORTED, "sampler update is built for vocab sizes 4, 5, 6, 8 (got %d)", S);
     }
+#undef MMB_UPD2
 #undef MMB_UPD
     return cuda_ok(cudaGetLastError(), "sampler update launch");
 }
