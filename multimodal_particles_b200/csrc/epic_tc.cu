@@ -32,6 +32,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include <vector>
 
 #include "mmb_device.cuh"
@@ -474,19 +476,29 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             umma(d_main, a_desc, bop_desc(op), idesc_k, 0);
             umma(d_main, a_desc, bop_desc(op + n_w), idesc_k, 1);
         };
+        const int T = lay.T, L = lay.L;
+        const int o16 = lane & 15, hf = lane >> 4;
+
+        const int n_steps = GENERATE ? p.n_steps : 1;
+#define MMB_TRACE(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && gt == 32 * ((swq + 1) & 3)) p.trace[id] = clock64(); } } while (0)
+        // The step loop exists twice: once for row warps (and special warps that also carry live particles), once for a special
+        // warp without live particles (SOLO) — there no per-particle state is alive, so the whole register budget is free to
+        // pipeline the shared-memory loads of the per-jet global MLP, the longest serial stretch of a step.  All mutable
+        // per-thread state lives inside the lambda (nothing captured by reference is written).
+        auto run_steps = [&](auto solo_tag, const float (&xs_in)[DC], const int kk_in) {
+        constexpr bool SOLO = decltype(solo_tag)::value;
+        float xs[DC];
+#pragma unroll
+        for (int c = 0; c < DC; ++c) xs[c] = xs_in[c];
+        int kk = kk_in;
         uint32_t phase = 0;
-        // MMA completion: warp 0 polls the mbarrier, warps 1-3 block on the named barrier (no issue slots burnt spinning)
+        // MMA completion: the special warp polls the mbarrier, the others block on the named barrier (no issue slots burnt spinning)
         auto wait_mma = [&]() {
             if (wq == swq) mbar_wait(mbar, phase);
             phase ^= 1;
             group_bar(1 + grp);
         };
-        const int T = lay.T, L = lay.L;
-        const int o16 = lane & 15, hf = lane >> 4;
-
-        const int n_steps = GENERATE ? p.n_steps : 1;
         uint32_t uq0 = 0, uq1 = 0, uq2 = 0, uq3 = 0;   // this particle's jump uniforms of the current group of four steps
-#define MMB_TRACE(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && gt == 32 * ((swq + 1) & 3)) p.trace[id] = clock64(); } } while (0)
         for (int step = 0; step < n_steps; ++step) {
             MMB_TRACE(0);
             // ---- (a) time vectors (warp 0) and the first A row [x_hi, x_lo, onehot(k)] * m
@@ -535,7 +547,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     if (hf == 0) { jv.tv_g1[l][o16] = b0; jv.tv_l1[l][o16] = b1; }
                 }
             }
-            if (!skip) {
+            if constexpr (!SOLO) if (!skip) {
                 float row[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) row[i] = 0.0f;
@@ -563,7 +575,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_after();
             MMB_TRACE(2);
             float acc[16], xl[16];
-            if (!skip) {
+            if constexpr (!SOLO) if (!skip) {
                 tmem_ld16(t_main, acc);
                 lrelu16(xl, acc);
                 if (lay.skip) tmem_st16(t_skip, xl);   // x_local_skip (epic.py:148) parked in TMEM, not in registers
@@ -640,7 +652,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(4 + 4 * l);
                 // ---- (f) fc_local1 epilogue -> A operand of fc_local2
                 tc_fence_after();
-                if (!skip) {
+                if constexpr (!SOLO) if (!skip) {
                     tmem_ld16(t_main, acc);
                     float l1[16], bl[16];
                     lds16(jv.bias_l1, bl);
@@ -661,7 +673,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 wait_mma();
                 MMB_TRACE(6 + 4 * l);
                 tc_fence_after();
-                if (!skip) {
+                if constexpr (!SOLO) if (!skip) {
                     tmem_ld16(t_main, acc);
                     lrelu16_sum(xl, acc, xl);  // dead rows: unused garbage, zeroed at pack
                     if (lay.skip) {
@@ -690,10 +702,10 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_after();
             MMB_TRACE(12);
             float h[16];
-            if (!skip) tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
+            if constexpr (!SOLO) if (!skip) tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
             float lg[S];
             if constexpr (SH > 0) {
-                if (!skip) {
+                if constexpr (!SOLO) if (!skip) {
                     float z1[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) z1[i] = i < SH ? selu_fast(h[DC + (i < SH ? i : 0)]) : 0.0f;
@@ -711,7 +723,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 wait_mma();
                 tc_fence_after();
                 MMB_TRACE(14);
-                if (skip) {
+                if (SOLO || skip) {
                 } else if constexpr (S <= 8) {
                     float l8[8];
                     tmem_ld8(t_main, l8);
@@ -729,7 +741,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_before();  // orders this step's last tcgen05.ld before the next step's first MMA (via the group barrier)
             MMB_TRACE(15);
 
-            if constexpr (GENERATE) if (!skip) {
+            if constexpr (GENERATE && !SOLO) if (!skip) {
                 // ---- (k) hybrid update in registers (bridges.py:38-45,179-201)
                 const StepScalars sc{p.dt, __ldg(p.step_tab + step * 4 + 0), __ldg(p.step_tab + step * 4 + 1), 0.0f};
 #pragma unroll
@@ -783,6 +795,8 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 p.k[pidx] = (uint8_t)kk;
             }
         }
+        };
+        if (GENERATE && skip && wq == swq) run_steps(std::true_type{}, xs, kk); else run_steps(std::false_type{}, xs, kk);
     }
     tc_fence_before();
     __syncthreads();
