@@ -49,16 +49,18 @@ constexpr int kTmemPerJet = 64;  // columns: main 16 | pool 16 | skip 16 | spare
 constexpr int kRows = 128;  // UMMA M
 constexpr int kMaxL = 4;
 constexpr int kMaxT = 32;
+constexpr int kS16 = 20, kS32 = 36;   // padded row strides (floats) of the global-MLP matrices with 16 / 32 inputs
 
 // ---- image layout (host builds, kernel copies to shared memory) --------------------------------
 // bf16 region: n_bops matrices of [16 out][16 k] in UMMA canonical K-major no-swizzle layout
 //   (core matrix = 8 rows x 16 B; k-chunks 128 B apart (LBO), 8-row groups 256 B apart (SBO)).
-// fp32 region: vectors and [k][o] matrices for the CUDA-core side (o fastest: conflict-free reads).
+// fp32 region: vectors, [t][o] time matrices (o fastest), and the matrices of the per-jet global MLP as [o][k] rows with k
+// contiguous and a padded row stride (kS16 / kS32 floats): a lane reads its 8-16 weights with 128-bit loads, conflict-free.
 struct TcLayout {
     int L, G, T, Sh, skip, n_bops;
     // float offsets
-    int b0, c0, w0t, g0m, g0s, g0t, g0b, g1, g1b, g2, g2b, layer0, layer_stride;
-    int l_g1m, l_g1s, l_g1g, l_g1t, l_g1b, l_g2, l_g2b, l_l1g, l_l1t, l_l1b, l_l2b;  // within a layer
+    int b0, c0, w0t, g0ms, g0t, g0b, g1, g1b, g2, g2b, layer0, layer_stride;
+    int l_g1ms, l_g1g, l_g1t, l_g1b, l_g2, l_g2b, l_l1g, l_l1t, l_l1b, l_l2b;  // within a layer
     int bout, bh0, bh2, n_floats;
     __host__ __device__ int bop_local0() const { return 0; }
     __host__ __device__ int bop_l1(int l) const { return 1 + 2 * l; }
@@ -83,16 +85,16 @@ TcLayout make_layout(const MmbEpicDims& d) {
     int o = 0;
     auto take = [&](int n) { int r = o; o += n; return r; };
     t.b0 = take(16); t.c0 = take(16); t.w0t = take(t.T * 16);
-    t.g0m = take(256); t.g0s = take(256); t.g0t = take(t.T * 16); t.g0b = take(16);
-    t.g1 = take(256); t.g1b = take(16);
-    t.g2 = take(16 * kGP); t.g2b = take(kGP);
+    t.g0ms = take(16 * kS32); t.g0t = take(t.T * 16); t.g0b = take(16);   // [o][mean 16 | sum 16]
+    t.g1 = take(16 * kS16); t.g1b = take(16);
+    t.g2 = take(kGP * kS16); t.g2b = take(kGP);
     t.layer0 = o;
     {
         int p = 0;
         auto tk = [&](int n) { int r = p; p += n; return r; };
-        t.l_g1m = tk(256); t.l_g1s = tk(256); t.l_g1g = tk(kGP * 16); t.l_g1t = tk(t.T * 16); t.l_g1b = tk(16);
-        t.l_g2 = tk(16 * kGP); t.l_g2b = tk(kGP);
-        t.l_l1g = tk(kGP * 16); t.l_l1t = tk(t.T * 16); t.l_l1b = tk(16); t.l_l2b = tk(16);
+        t.l_g1ms = tk(16 * kS32); t.l_g1g = tk(16 * kS32); t.l_g1t = tk(t.T * 16); t.l_g1b = tk(16);
+        t.l_g2 = tk(kGP * kS16); t.l_g2b = tk(kGP);
+        t.l_l1g = tk(16 * kS32); t.l_l1t = tk(t.T * 16); t.l_l1b = tk(16); t.l_l2b = tk(16);
         t.layer_stride = p;
     }
     o += t.layer_stride * t.L;
@@ -288,6 +290,27 @@ __device__ __forceinline__ int telegraph_jump_fast(const float (&lg)[S], int k, 
 __device__ __forceinline__ float lrelu_fast(float a) { return fmaxf(a, 0.01f * a); }
 // init + sum_{k<K} w[k * wstride] * x(k) with four independent accumulators: the serial per-jet global MLP is a chain of such
 // dots on one warp, and a single accumulator makes every one of them K dependent FMAs long
+// init + sum_k w[k] x[k] over K contiguous floats (K % 4 == 0); w and x 16-byte aligned shared memory: 128-bit loads
+template <int K>
+__device__ __forceinline__ float dotv(float init, const float* w, const float* x) {
+    float a0 = init, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(w + k), b = *reinterpret_cast<const float4*>(x + k);
+        a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+// the same with x in registers, scaled by sc
+__device__ __forceinline__ float dotr16(float init, const float* w, const float (&x)[16], float sc) {
+    float a0 = init, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(w + k);
+        a0 = fmaf(a.x, x[k] * sc, a0); a1 = fmaf(a.y, x[k + 1] * sc, a1); a2 = fmaf(a.z, x[k + 2] * sc, a2); a3 = fmaf(a.w, x[k + 3] * sc, a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
 template <int K, typename XF>
 __device__ __forceinline__ float dot4(float init, const float* w, int wstride, XF x) {
     float a0 = init, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
@@ -604,19 +627,18 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     tmem_ld16(t_pool, sv);
                     if (l == 0) {  // EPiC_Projection globals (epic.py:187-190)
                         float g = hf ? 0.0f : jv.tv_g0[o16];
-                        const float* Wsel = s_wf + (hf ? lay.g0s : lay.g0m);
                         const float sc = hf ? 1.0f : inv_cnt;
-                        g = dot4<16>(g, Wsel + o16, 16, [&](int k) { return sv[k] * sc; });
+                        g = dotr16(g, s_wf + lay.g0ms + o16 * kS32 + hf * 16, sv, sc);
                         g += __shfl_xor_sync(0xffffffffu, g, 16);
                         if (hf == 0) jv.gv[o16] = lrelu_fast(g);
                         __syncwarp();
                         g = hf ? 0.0f : s_wf[lay.g1b + o16];
-                        g = dot4<8>(g, s_wf + lay.g1 + hf * 8 * 16 + o16, 16, [&](int kq) { return jv.gv[hf * 8 + kq]; });
+                        g = dotv<8>(g, s_wf + lay.g1 + o16 * kS16 + hf * 8, jv.gv + hf * 8);
                         g += __shfl_xor_sync(0xffffffffu, g, 16);
                         if (hf == 0) jv.gv2[o16] = lrelu_fast(g);
                         __syncwarp();
                         g = s_wf[lay.g2b + lane];
-                        g = dot4<16>(g, s_wf + lay.g2 + lane, kGP, [&](int k) { return jv.gv2[k]; });
+                        g = dotv<16>(g, s_wf + lay.g2 + lane * kS16, jv.gv2);
                         g = lrelu_fast(g);
                         jv.xg[lane] = g;
                         jv.skipg[lane] = lay.skip ? g : 0.0f;
@@ -624,18 +646,14 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     }
                     // EPiC_layer globals (epic.py:228-232)
                     float g = hf ? 0.0f : jv.tv_g1[l][o16];
-                    {
-                        const float* Wsel = Wl + (hf ? lay.l_g1s : lay.l_g1m);
-                        const float sc = hf ? 1.0f : inv_cnt;
-                        g = dot4<16>(g, Wsel + o16, 16, [&](int k) { return sv[k] * sc; });
-                    }
-                    g = dot4<kGP / 2>(g, Wl + lay.l_g1g + hf * (kGP / 2) * 16 + o16, 16, [&](int q) { return jv.xg[hf * (kGP / 2) + q]; });
+                    g = dotr16(g, Wl + lay.l_g1ms + o16 * kS32 + hf * 16, sv, hf ? 1.0f : inv_cnt);
+                    g = dotv<kGP / 2>(g, Wl + lay.l_g1g + o16 * kS32 + hf * (kGP / 2), jv.xg + hf * (kGP / 2));
                     g += __shfl_xor_sync(0xffffffffu, g, 16);
                     __syncwarp();
                     if (hf == 0) jv.gv[o16] = lrelu_fast(g);
                     __syncwarp();
                     g = Wl[lay.l_g2b + lane];
-                    g = dot4<16>(g, Wl + lay.l_g2 + lane, kGP, [&](int k) { return jv.gv[k]; });
+                    g = dotv<16>(g, Wl + lay.l_g2 + lane * kS16, jv.gv);
                     const float xmid = lrelu_fast(g + jv.xg[lane]);
                     __syncwarp();
                     jv.xgmid[lane] = xmid;
@@ -643,7 +661,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     __syncwarp();
                     // per-jet bias of fc_local1: time part + Wl1[:, H:H+G] xg   (epic.py:233-238)
                     g = hf ? 0.0f : jv.tv_l1[l][o16];
-                    g = dot4<kGP / 2>(g, Wl + lay.l_l1g + hf * (kGP / 2) * 16 + o16, 16, [&](int q) { return jv.xgmid[hf * (kGP / 2) + q]; });
+                    g = dotv<kGP / 2>(g, Wl + lay.l_l1g + o16 * kS32 + hf * (kGP / 2), jv.xgmid + hf * (kGP / 2));
                     g += __shfl_xor_sync(0xffffffffu, g, 16);
                     if (hf == 0) jv.bias_l1[o16] = g;
                     tc_fence_before();
@@ -963,14 +981,14 @@ int tc_build_image(EpicModel* m, const float* W) {
         for (int t = 0; t < T; ++t) wf[lay.w0t + t * 16 + o] = w0[t];
         // projection globals
         const float* g0 = W + Lo.global0_w + (size_t)o * (2 * H + T);
-        for (int k = 0; k < H; ++k) { wf[lay.g0m + k * 16 + o] = g0[k]; wf[lay.g0s + k * 16 + o] = g0[H + k]; }
+        for (int k = 0; k < H; ++k) { wf[lay.g0ms + o * kS32 + k] = g0[k]; wf[lay.g0ms + o * kS32 + 16 + k] = g0[H + k]; }
         for (int t = 0; t < T; ++t) wf[lay.g0t + t * 16 + o] = g0[2 * H + t];
         wf[lay.g0b + o] = W[Lo.global0_b + o];
-        for (int k = 0; k < H; ++k) wf[lay.g1 + k * 16 + o] = W[Lo.global1_w + (size_t)o * H + k];
+        for (int k = 0; k < H; ++k) wf[lay.g1 + o * kS16 + k] = W[Lo.global1_w + (size_t)o * H + k];
         wf[lay.g1b + o] = W[Lo.global1_b + o];
     }
     for (int g = 0; g < G; ++g) {
-        for (int k = 0; k < H; ++k) wf[lay.g2 + k * kGP + g] = W[Lo.global2_w + (size_t)g * H + k];
+        for (int k = 0; k < H; ++k) wf[lay.g2 + g * kS16 + k] = W[Lo.global2_w + (size_t)g * H + k];
         wf[lay.g2b + g] = W[Lo.global2_b + g];
     }
     for (int l = 0; l < L; ++l) {
@@ -979,20 +997,20 @@ int tc_build_image(EpicModel* m, const float* W) {
         const int Kg = 2 * H + G + T, Kl = H + G + T;
         for (int o = 0; o < H; ++o) {
             const float* g1 = Wl + Lo.l_g1_w + (size_t)o * Kg;
-            for (int k = 0; k < H; ++k) { F[lay.l_g1m + k * 16 + o] = g1[k]; F[lay.l_g1s + k * 16 + o] = g1[H + k]; }
-            for (int g = 0; g < G; ++g) F[lay.l_g1g + g * 16 + o] = g1[2 * H + g];
+            for (int k = 0; k < H; ++k) { F[lay.l_g1ms + o * kS32 + k] = g1[k]; F[lay.l_g1ms + o * kS32 + 16 + k] = g1[H + k]; }
+            for (int g = 0; g < G; ++g) F[lay.l_g1g + o * kS32 + g] = g1[2 * H + g];
             for (int t = 0; t < T; ++t) F[lay.l_g1t + t * 16 + o] = g1[2 * H + G + t];
             F[lay.l_g1b + o] = Wl[Lo.l_g1_b + o];
             const float* l1 = Wl + Lo.l_l1_w + (size_t)o * Kl;
             for (int k = 0; k < H; ++k) setb(lay.bop_l1(l), o, k, l1[k]);
-            for (int g = 0; g < G; ++g) F[lay.l_l1g + g * 16 + o] = l1[H + g];
+            for (int g = 0; g < G; ++g) F[lay.l_l1g + o * kS32 + g] = l1[H + g];
             for (int t = 0; t < T; ++t) F[lay.l_l1t + t * 16 + o] = l1[H + G + t];
             F[lay.l_l1b + o] = Wl[Lo.l_l1_b + o];
             for (int k = 0; k < H; ++k) setb(lay.bop_l2(l), o, k, Wl[Lo.l_l2_w + (size_t)o * H + k]);
             F[lay.l_l2b + o] = Wl[Lo.l_l2_b + o];
         }
         for (int g = 0; g < G; ++g) {
-            for (int k = 0; k < H; ++k) F[lay.l_g2 + k * kGP + g] = Wl[Lo.l_g2_w + (size_t)g * H + k];
+            for (int k = 0; k < H; ++k) F[lay.l_g2 + g * kS16 + k] = Wl[Lo.l_g2_w + (size_t)g * H + k];
             F[lay.l_g2b + g] = Wl[Lo.l_g2_b + g];
         }
     }
