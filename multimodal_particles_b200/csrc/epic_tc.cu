@@ -516,13 +516,19 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         int kk = kk_in;
         uint32_t phase = 0;
         // MMA completion: the special warp polls the mbarrier, the others block on the named barrier (no issue slots burnt spinning)
-        auto wait_mma = [&]() {
-            if (wq == swq) mbar_wait(mbar, phase);
+        int trace_step = 0;
+        auto wait_mma = [&](int trace_id = -1) {
+            if (wq == swq) {
+                mbar_wait(mbar, phase);
+                if constexpr (TRACE) { if (trace_id >= 0 && p.trace && jet == 0 && trace_step == 3 && lane == 0) p.trace[trace_id] = clock64(); }
+            }
             phase ^= 1;
             group_bar(1 + grp);
         };
+#define MMB_TRACE_X(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && wq == swq && lane == 0) p.trace[id] = clock64(); } } while (0)
         uint32_t uq0 = 0, uq1 = 0, uq2 = 0, uq3 = 0;   // this particle's jump uniforms of the current group of four steps
         for (int step = 0; step < n_steps; ++step) {
+            trace_step = step;
             MMB_TRACE(0);
             // ---- (a) time vectors (warp 0) and the first A row [x_hi, x_lo, onehot(k)] * m
             if (GENERATE && p.tvec) {
@@ -588,13 +594,15 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             group_bar(1 + grp);
             MMB_TRACE(1);
             // ---- (b) local_0
+            MMB_TRACE_X(20);
             if (wq == swq && elect_one()) {
                 tc_fence_after();
                 gemm(lay.bop_local0());
                 umma(d_main, amask_desc, bb0_desc, idesc_k, 1);  // + bias on live rows; dead rows stay exactly 0
                 umma_commit(mbar);
             }
-            wait_mma();
+            MMB_TRACE_X(21);
+            wait_mma(22);
             tc_fence_after();
             MMB_TRACE(2);
             float acc[16], xl[16];
@@ -682,13 +690,15 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 group_bar(1 + grp);
                 MMB_TRACE(5 + 4 * l);
                 // ---- (g) fc_local2
+                if (l == 0) MMB_TRACE_X(23);
                 if (wq == swq && elect_one()) {
                     tc_fence_after();
                     gemm(lay.bop_l2(l));
                     umma(d_main, amask_desc, bop_desc(lay.bop_bias_l2(l)), idesc_k, 1);
                     umma_commit(mbar);
                 }
-                wait_mma();
+                if (l == 0) MMB_TRACE_X(24);
+                wait_mma(l == 0 ? 25 : -1);
                 MMB_TRACE(6 + 4 * l);
                 tc_fence_after();
                 if constexpr (!SOLO) if (!skip) {

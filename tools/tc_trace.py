@@ -25,6 +25,7 @@ for B in (1, 1184):
     _native.load().mmb_debug_read_trace(buf, 32)
     t = list(buf)
     print(f"--- B={B}: one solver step of jet 0 = {t[16] - t[0]} cycles")
+    print(f"  special lane: local_0 issue {t[21] - t[20]}, commit->mbarrier {t[22] - t[21]}; L0 fc_local2 issue {t[24] - t[23]}, commit->mbarrier {t[25] - t[24]}")
     prev = t[0]
     for i in sorted(names):
         print(f"  {names[i]:48s} {t[i] - prev:6d}")
