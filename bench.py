@@ -268,7 +268,7 @@ def main():
     achieved_tf = flops / (kern * 1e-3) / 1e12
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_bench_launches.md):
     # the state lives in registers for all 99 steps, HBM only sees the source state (the result stays in L2 until evicted)
-    traffic = 3.63e6 if (precision == "bf16" and B == 4096) else None
+    traffic = 3.8e6 if (precision == "bf16" and B == 4096) else None
     roofline = {"kernel": f"mmb::generate ({precision})", "bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16"],
                 "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16"], "traffic": traffic, "peak_source": pk["src"],
                 "algorithmic_flops_per_launch": flops, "ms_per_launch": kern}
