@@ -515,15 +515,18 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         for (int c = 0; c < DC; ++c) xs[c] = xs_in[c];
         int kk = kk_in;
         uint32_t phase = 0;
-        // MMA completion: the special warp polls the mbarrier, the others block on the named barrier (no issue slots burnt spinning)
         int trace_step = 0;
+        // MMA completion: every warp that is going to read the accumulator polls the mbarrier itself (try_wait suspends in
+        // hardware, and 60 % of the issue slots are idle anyway); warps without row work, the special warp included, do not
+        // wait at all — the barrier after the epilogue is what orders the next MMA behind this one's readers.
         auto wait_mma = [&](int trace_id = -1) {
-            if (wq == swq) {
+            bool waits = !skip;
+            if constexpr (SOLO) waits = false;
+            if (waits) {
                 mbar_wait(mbar, phase);
                 if constexpr (TRACE) { if (trace_id >= 0 && p.trace && jet == 0 && trace_step == 3 && lane == 0) p.trace[trace_id] = clock64(); }
             }
             phase ^= 1;
-            group_bar(1 + grp);
         };
 #define MMB_TRACE_X(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && wq == swq && lane == 0) p.trace[id] = clock64(); } } while (0)
         uint32_t uq0 = 0, uq1 = 0, uq2 = 0, uq3 = 0;   // this particle's jump uniforms of the current group of four steps
