@@ -20,8 +20,15 @@
 //     K-steps into a second TMEM accumulator, issued together with the next layer's GEMM.  Every
 //     TMEM lane then holds all 16 column sums, so the warp that runs the tiny global MLP reads
 //     them with one tcgen05.ld — no shuffles, no shared-memory reduction;
-//   * two jets per CTA (256 threads) share one copy of the weights; several CTAs per SM interleave
-//     their chains to hide the MMA -> commit -> mbarrier -> tcgen05.ld round trips.
+//   * four jets per CTA (512 threads, 64 registers) share one copy of the weights; two CTAs per SM interleave
+//     eight chains to hide the MMA -> commit -> mbarrier -> tcgen05.ld round trips;
+//   * one warp per jet is "special": an elected lane issues the jet's MMAs and the warp runs the per-jet global MLP.
+//     Everything a tcgen05.mma consumes (descriptors, TMEM addresses) derives from broadcast, provably warp-uniform values,
+//     otherwise the compiler wraps every MMA in an elect / R2UR.BROADCAST loop;
+//   * generation only: a jet's rows are rotated by (global jet index & 3) quarters of the tile, so the live quarters of the
+//     four jets of a CTA sit on four different SM sub-partitions; warps whose 32 particles are all dead skip every epilogue
+//     (their A rows stay zero, their pooling K-steps are not issued); the special role goes to the warp of the last quarter,
+//     and when that warp has no live particle it runs its own copy of the step loop with no per-particle state alive.
 //
 // Numerics: bf16 operands, fp32 accumulate, fp32 residual stream / biases / global MLP / update.
 // Not bit-comparable with the fp32 path; tests/test_gpu_tc.py states the tolerance.
