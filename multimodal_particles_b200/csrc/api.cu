@@ -112,10 +112,10 @@ int mmb_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, const
 
 size_t mmb_generate_workspace_bytes(const MmbEpicModel* handle, int B, int N, int precision) {
     const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
-    (void)B; (void)N; (void)precision;
+    (void)N; (void)precision;
     if (!m) return 0;
-    // room for the device image of a step table of up to 4096 steps + the tcgen05 path's per-step time vectors
-    return (table_floats(4096, m->dims.dim_time_emb) + tc_generate_scratch_floats(&m->dims, 4096)) * sizeof(float);
+    // room for the device image of a step table of up to 4096 steps + the tcgen05 path's per-step time vectors and jet lists
+    return (table_floats(4096, m->dims.dim_time_emb) + tc_generate_scratch_floats(&m->dims, 4096, B)) * sizeof(float);
 }
 
 int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t* mask,
@@ -127,7 +127,7 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate: negative size");
     const int T = m->dims.dim_time_emb, n = st->n_steps;
     const size_t need = table_floats(n, T) * sizeof(float);
-    if (workspace_bytes < need + tc_generate_scratch_floats(&m->dims, n) * sizeof(float))
+    if (workspace_bytes < need + tc_generate_scratch_floats(&m->dims, n, B) * sizeof(float))
         return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B too small for %d steps", workspace_bytes, n);
     if (B == 0 || N == 0 || n == 0) return MMB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);

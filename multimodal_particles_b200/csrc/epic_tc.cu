@@ -154,7 +154,7 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
 // The pooling GEMM: up to eight K-steps (B descriptor advances by 512 B = 32 address units per step) into one accumulator.
 // All descriptors are formed before the first MMA so their moves to uniform registers can overlap; K-steps whose bit in
 // `live` is clear are skipped (their rows are all zero); the first issued step overwrites, the rest accumulate.
-__device__ __forceinline__ void umma_pool8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc0, uint32_t idesc, uint32_t live) {
+__device__ __forceinline__ void umma_pool8(uint32_t d_tmem, uint64_t adesc, uint64_t adesc_hi, uint64_t bdesc0, uint32_t idesc, uint32_t live) {
     if (live == 0u) live = 1u;   // nothing live: one step over zero rows still defines the accumulator
     const uint32_t first = live & (0u - live);   // lowest set bit: the step that does not accumulate
     asm volatile(
@@ -174,12 +174,12 @@ __device__ __forceinline__ void umma_pool8(uint32_t d_tmem, uint64_t adesc, uint
         "@e1 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b1, %3, a1;\n\t"
         "@e2 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b2, %3, a2;\n\t"
         "@e3 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b3, %3, a3;\n\t"
-        "@e4 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b4, %3, a4;\n\t"
-        "@e5 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b5, %3, a5;\n\t"
-        "@e6 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b6, %3, a6;\n\t"
-        "@e7 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, b7, %3, a7;\n\t"
+        "@e4 tcgen05.mma.cta_group::1.kind::f16 [%0], %6, b4, %3, a4;\n\t"
+        "@e5 tcgen05.mma.cta_group::1.kind::f16 [%0], %6, b5, %3, a5;\n\t"
+        "@e6 tcgen05.mma.cta_group::1.kind::f16 [%0], %6, b6, %3, a6;\n\t"
+        "@e7 tcgen05.mma.cta_group::1.kind::f16 [%0], %6, b7, %3, a7;\n\t"
         "}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc0), "r"(idesc), "r"(live), "r"(first) : "memory");
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc0), "r"(idesc), "r"(live), "r"(first), "l"(adesc_hi) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -372,6 +372,9 @@ struct TcParams {
     uint64_t seed, jet_offset;
     int B, N;
     float *v_out, *logits_out, *hidden_out;  // forward outputs
+    // generate, optional: jets binned by tc_bin kernels — big_list [counts[0]] jets with a live particle at index >= 64 (one per
+    // tile), small_list [counts[1]] the others (two per tile, 64 rows each); null = jet s on tile s
+    const int32_t *big_list, *small_list, *counts;
     const float* tvec;     // generate: [n_steps][2+2L][16] per-step time vectors from tc_time_vectors_kernel; forward: null
     long long* trace;      // debug: clock64() stamps of jet 0, step 3 (tools/tc_trace.py); null in production
 };
@@ -394,11 +397,24 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
     const int tid = threadIdx.x;
     // ---- carve
     uint8_t* s_bops = smem;                                   // n_bops * 512 B
-    uint8_t* s_ones = s_bops + lay.n_bops * 512;              // 4 KB: A operand of the pooling GEMM
-    float* s_wf = reinterpret_cast<float*>(s_ones + 4096);    // fp32 tables
+    uint8_t* s_ones = s_bops + lay.n_bops * 512;              // 4 KB: A operand of the pooling GEMM (and of the all-row bias steps)
+    uint8_t* s_ones_tb = s_ones + 4096;                       // 2 x 4 KB: ones in rows 0-63 only / rows 64-127 only (paired tiles)
+    float* s_wf = reinterpret_cast<float*>(s_ones_tb + 8192); // fp32 tables
     uint8_t* s_grp = reinterpret_cast<uint8_t*>(s_wf + lay.n_floats);
-    constexpr int kGrpBytes = kGrpFixed + ((sizeof(JetVec) + 15) & ~15) + 16;
+    constexpr int kJV = (sizeof(JetVec) + 15) & ~15;
+    constexpr int kGrpBytes = kGrpFixed + 2 * kJV + 16;   // a tile carries one jet, or two small ones (one JetVec each)
     __shared__ uint32_t s_tmem_slot;
+    // binned generation: the tiles are [pairs of small jets | big jets]; CTAs past the last tile leave before any set-up
+    int n_big = 0, n_small = 0;
+    long n_slots = p.B;
+    if constexpr (GENERATE) {
+        if (p.counts) {
+            n_big = __ldg(p.counts);
+            n_small = __ldg(p.counts + 1);
+            n_slots = (long)n_big + (n_small + 1) / 2;
+            if ((long)blockIdx.x * kJPC >= n_slots) return;
+        }
+    }
 
     // ---- one-time: weights -> smem, ones, barriers, TMEM
     {
@@ -411,6 +427,10 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         for (int i = tid; i < lay.n_floats / 4; i += blockDim.x) dstf[i] = __ldg(srcf + i);
         const uint32_t one2 = 0x3F803F80u;  // bf16 1.0 twice
         for (int i = tid; i < 256; i += blockDim.x) reinterpret_cast<uint4*>(s_ones)[i] = make_uint4(one2, one2, one2, one2);
+        for (int i = tid; i < 512; i += blockDim.x) {   // rows 8g..8g+7 of a K-major tile are the 256 bytes at 256 g
+            const uint32_t v = ((i < 256) == ((i & 255) < 128)) ? one2 : 0u;
+            reinterpret_cast<uint4*>(s_ones_tb)[i] = make_uint4(v, v, v, v);
+        }
     }
     // warp-uniform indices come from a broadcast so that the compiler keeps everything derived from them (shared-memory
     // addresses, TMEM addresses, UMMA descriptors) in uniform registers: a tcgen05.mma whose operands are not provably uniform
@@ -419,19 +439,43 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
     const int grp = warp_u >> 2, gt = tid & 127, wq = warp_u & 3, lane = tid & 31;
     // the "special" warp of a group issues its MMAs and runs its per-jet global MLP; warp w lives on SM sub-partition
     // w % 4, so rotating the role with the group index spreads that serial work over all four schedulers
-    const long jet = (long)blockIdx.x * kJPC + grp;
+    const long slot = (long)blockIdx.x * kJPC + grp;
+    const bool have = slot < n_slots;
+    // tile -> jet(s).  `paired` feeds MMA operands, so it is broadcast; the jet ids only feed per-thread addresses and keys.
+    bool paired = false;
+    long jet = slot;        // the jet of THIS thread's rows (-1: none)
+    if constexpr (GENERATE) {
+        if (p.counts && have) {
+            const long n_pairs = (n_small + 1) / 2;   // paired tiles take longer per step: they go first, the single-jet tiles fill the tail
+            if (slot >= n_pairs) {
+                jet = __ldg(p.big_list + (slot - n_pairs));
+            } else {
+                paired = true;
+                const long t2 = 2 * slot + ((tid >> 6) & 1);   // rows 0-63: first jet of the pair, rows 64-127: second
+                jet = t2 < n_small ? (long)__ldg(p.small_list + t2) : -1;
+            }
+        }
+    }
+    paired = __shfl_sync(0xffffffffu, (int)paired, 0) != 0;
+    const int half = paired ? (wq >> 1) : 0;
+    const bool has_jet = have && jet >= 0;
     // Generation: a jet's particles sit live-first (prefix mask), so the row quarters 1..3 of most jets are dead.  The tile rows
     // are rotated by `rot` quarters per jet (the network is permutation-invariant; keyed by the GLOBAL jet index, so results do
     // not depend on the batch slicing): the live quarters of the four jets of a CTA land on four different SM sub-partitions,
     // warps whose 32 particles are all dead skip every epilogue (their A rows stay zero, they only keep the barriers), and the
     // special role goes to the warp of the last quarter, which is the least likely to have row work of its own.
-    const int rot = GENERATE ? (int)((p.jet_offset + (uint64_t)jet) & 3) : 0;
-    const int swq = GENERATE ? ((rot + 3) & 3) : (grp & 3);
+    // A paired tile gives each jet two row quarters: the same rotation by (global jet index & 1), the special role on the jet's
+    // second quarter; the special warp of the first jet issues the tile's MMAs.
+    const int rot = GENERATE ? (int)((p.jet_offset + (uint64_t)(jet < 0 ? 0 : jet)) & (paired ? 1 : 3)) : 0;
+    const int swq = GENERATE ? (paired ? 2 * half + ((rot + 1) & 1) : ((rot + 3) & 3)) : (grp & 3);
+    const bool is_special = has_jet && wq == swq;
+    const bool is_issuer = paired ? (half == 0 && wq == swq) : (wq == swq);
     uint8_t* abuf = s_grp + grp * kGrpBytes;
     uint8_t* amask = abuf + 4096;   // A tile of the bias K-steps: columns 0,1 = mask of the row's particle
     uint8_t* bb0 = abuf + 8192;     // B tile carrying this step's local_0 bias (hi, lo) in columns 0,1
-    JetVec& jv = *reinterpret_cast<JetVec*>(abuf + kGrpFixed);
-    const uint32_t mbar = smem_u32(abuf + kGrpFixed + ((sizeof(JetVec) + 15) & ~15));
+    JetVec& jv = *reinterpret_cast<JetVec*>(abuf + kGrpFixed + half * kJV);     // this thread's jet
+    JetVec& jv0 = *reinterpret_cast<JetVec*>(abuf + kGrpFixed);                  // tile-level fields live in the first one
+    const uint32_t mbar = smem_u32(abuf + kGrpFixed + 2 * kJV);
     if (gt == 0) mbar_init(mbar, 1);
     if (tid < 32) tmem_alloc(smem_u32(&s_tmem_slot), kJPC * kTmemPerJet);
     fence_barrier_init();
@@ -444,10 +488,10 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
     const uint32_t t_pool = t_main + 16, t_skip = t_main + 32;
     const uint32_t d_main = tmem_base + grp * kTmemPerJet, d_pool = d_main + 16;
 
-    if (jet < p.B) {
+    if (have) {
         const int N = p.N, r = gt;                       // r: tile row (TMEM lane); n: the particle it carries
-        const int n = (r + 128 - 32 * rot) & 127;
-        const bool valid = n < N;
+        const int n = paired ? (32 * (((wq & 1) - rot) & 1) + lane) : ((r + 128 - 32 * rot) & 127);
+        const bool valid = has_jet && n < N;
         const size_t pidx = (size_t)jet * N + n;
         // ---- state
         float xs[DC];
@@ -473,7 +517,10 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         bool skip = false;   // this warp has no live particle: no epilogue work at all (generation only)
         {
             const unsigned bal = __ballot_sync(0xffffffffu, m);
-            if (lane == 0) { jv.cnt[wq] = __popc(bal); jv.live16[wq] = ((bal & 0xffffu) ? 1u : 0u) | ((bal >> 16) ? 2u : 0u); }
+            if (lane == 0) {
+                jv.cnt[paired ? (wq & 1) : wq] = __popc(bal);
+                jv0.live16[wq] = ((bal & 0xffffu) ? 1u : 0u) | ((bal >> 16) ? 2u : 0u);   // by tile quarter
+            }
             if constexpr (GENERATE) {
                 skip = bal == 0u;
                 if (skip) {   // its A rows are never written again: zero them once
@@ -485,14 +532,17 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             }
         }
         group_bar(1 + grp);
-        const float inv_cnt = 1.0f / (float)(jv.cnt[0] + jv.cnt[1] + jv.cnt[2] + jv.cnt[3]);
+        const float inv_cnt = 1.0f / (float)(paired ? jv.cnt[0] + jv.cnt[1] : jv.cnt[0] + jv.cnt[1] + jv.cnt[2] + jv.cnt[3]);
         // K-steps of the pooling GEMM (16 particles each) that hold a live particle; the others would add zeros
-        const uint32_t pool_live = __shfl_sync(0xffffffffu, GENERATE ? (jv.live16[0] | (jv.live16[1] << 2) | (jv.live16[2] << 4) | (jv.live16[3] << 6)) : 0xffu, 0);
+        const uint32_t pool_live = __shfl_sync(0xffffffffu, GENERATE ? (jv0.live16[0] | (jv0.live16[1] << 2) | (jv0.live16[2] << 4) | (jv0.live16[3] << 6)) : 0xffu, 0);
 
         const uint32_t a_addr = smem_u32(abuf);
         const uint32_t bops_addr = smem_u32(s_bops);
         const uint64_t a_desc = smem_desc(a_addr, 128, 256);
         const uint64_t ones_desc = smem_desc(smem_u32(s_ones), 128, 256);
+        // pooling A operand per K-step half: a paired tile sums rows 0-63 into rows 0-63 and rows 64-127 into rows 64-127
+        const uint64_t pool_a_lo = paired ? smem_desc(smem_u32(s_ones_tb), 128, 256) : ones_desc;
+        const uint64_t pool_a_hi = paired ? smem_desc(smem_u32(s_ones_tb + 4096), 128, 256) : ones_desc;
         const uint64_t amask_desc = smem_desc(smem_u32(amask), 128, 256);
         const uint64_t bb0_desc = smem_desc(smem_u32(bb0), 128, 256);
         const uint64_t bops_desc0 = smem_desc(bops_addr, 128, 256);
@@ -510,7 +560,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         const int o16 = lane & 15, hf = lane >> 4;
 
         const int n_steps = GENERATE ? p.n_steps : 1;
-#define MMB_TRACE(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && gt == 32 * ((swq + 1) & 3)) p.trace[id] = clock64(); } } while (0)
+#define MMB_TRACE(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && n == 0) p.trace[id] = clock64(); } } while (0)
         // The step loop exists twice: once for row warps (and special warps that also carry live particles), once for a special
         // warp without live particles (SOLO) — there no per-particle state is alive, so the whole register budget is free to
         // pipeline the shared-memory loads of the per-jet global MLP, the longest serial stretch of a step.  All mutable
@@ -535,7 +585,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             }
             phase ^= 1;
         };
-#define MMB_TRACE_X(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && wq == swq && lane == 0) p.trace[id] = clock64(); } } while (0)
+#define MMB_TRACE_X(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && is_special && lane == 0) p.trace[id] = clock64(); } } while (0)
         uint32_t uq0 = 0, uq1 = 0, uq2 = 0, uq3 = 0;   // this particle's jump uniforms of the current group of four steps
         for (int step = 0; step < n_steps; ++step) {
             trace_step = step;
@@ -543,7 +593,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             // ---- (a) time vectors (warp 0) and the first A row [x_hi, x_lo, onehot(k)] * m
             if (GENERATE && p.tvec) {
                 // the time is shared by all jets at generation: the vectors were computed once per step by the prologue kernel
-                if (wq == swq) {
+                if (is_special) {
                     const float* tv = p.tvec + (size_t)step * (2 + 2 * L) * 16;
                     const int vi = lane >> 4;   // two vectors per pass
                     for (int v0 = 0; v0 < 2 + 2 * L; v0 += 2) {
@@ -557,7 +607,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                         else jv.tv_l1[(v - 2) >> 1][o16] = val;
                     }
                 }
-            } else if (wq == swq) {
+            } else if (is_special) {
                 const float* te = GENERATE ? p.temb + (size_t)step * T : p.temb + (size_t)jet * p.temb_stride;
                 const int t0 = hf * (T / 2), t1 = t0 + T / 2;
                 float a0 = hf ? 0.0f : s_wf[lay.c0 + o16], a1 = hf ? 0.0f : s_wf[lay.g0b + o16];
@@ -605,7 +655,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             MMB_TRACE(1);
             // ---- (b) local_0
             MMB_TRACE_X(20);
-            if (wq == swq && elect_one()) {
+            if (is_issuer && elect_one()) {
                 tc_fence_after();
                 gemm(lay.bop_local0());
                 umma(d_main, amask_desc, bb0_desc, idesc_k, 1);  // + bias on live rows; dead rows stay exactly 0
@@ -630,15 +680,15 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             for (int l = 0; l < L; ++l) {
                 const float* Wl = s_wf + lay.layer0 + l * lay.layer_stride;
                 // ---- (d) pooling GEMM (ones x XL, K = 128 particles) + fc_local1 on the same tile
-                if (wq == swq && elect_one()) {
+                if (is_issuer && elect_one()) {
                     tc_fence_after();
-                    umma_pool8(d_pool, ones_desc, pool_desc0, idesc_pool, pool_live);  // K-step j = rows 16j..16j+15, MN-major
+                    umma_pool8(d_pool, pool_a_lo, pool_a_hi, pool_desc0, idesc_pool, pool_live);  // K-step j = rows 16j..16j+15, MN-major
                     gemm(lay.bop_l1(l));
                     umma_commit(mbar);
                 }
                 phase ^= 1;
                 // ---- (e) global path on warp 0 of the group (fp32, CUDA cores); the other warps park at the barrier below
-                if (wq == swq) {
+                if (is_special) {
                     mbar_wait(mbar, phase ^ 1);
                     tc_fence_after();
                     float sv[16];
@@ -701,7 +751,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(5 + 4 * l);
                 // ---- (g) fc_local2
                 if (l == 0) MMB_TRACE_X(23);
-                if (wq == swq && elect_one()) {
+                if (is_issuer && elect_one()) {
                     tc_fence_after();
                     gemm(lay.bop_l2(l));
                     umma(d_main, amask_desc, bop_desc(lay.bop_bias_l2(l)), idesc_k, 1);
@@ -727,7 +777,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(7 + 4 * l);
             }
             // ---- (i) output layer (epic.py:158-162)
-            if (wq == swq && elect_one()) {
+            if (is_issuer && elect_one()) {
                 tc_fence_after();
                 // with a discrete head the operand is [W_out(v rows) ; F1 W_out(z rows)]: the output layer and the first
                 // head Linear have no nonlinearity between them, so columns DC.. are already F1 z + f1 (mbm.py:105-111)
@@ -752,7 +802,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
-                if (wq == swq && elect_one()) {
+                if (is_issuer && elect_one()) {
                     tc_fence_after();
                     gemm(lay.bop_h2());
                     umma(d_main, ones_desc, bop_desc(lay.bop_bias_h2()), idesc_k, 1);
@@ -831,10 +881,15 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
 #pragma unroll
                 for (int c = 0; c < DC; ++c) p.x[pidx * DC + c] = xs[c];
                 p.k[pidx] = (uint8_t)kk;
+                if (paired && n + 64 < N) {   // a small jet's particles 64.. are dead and have no row in a paired tile: final state 0
+#pragma unroll
+                    for (int c = 0; c < DC; ++c) p.x[(pidx + 64) * DC + c] = 0.0f;
+                    p.k[pidx + 64] = 0;
+                }
             }
         }
         };
-        if (GENERATE && skip && wq == swq) run_steps(std::true_type{}, xs, kk); else run_steps(std::false_type{}, xs, kk);
+        if (GENERATE && skip && is_special) run_steps(std::true_type{}, xs, kk); else run_steps(std::false_type{}, xs, kk);
     }
     tc_fence_before();
     __syncthreads();
@@ -842,8 +897,8 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
 }
 
 size_t tc_smem_bytes(const TcLayout& lay) {
-    const size_t grp = kGrpFixed + ((sizeof(JetVec) + 15) & ~15) + 16;
-    return (size_t)lay.n_bops * 512 + 4096 + (size_t)lay.n_floats * 4 + kJPC * grp + 1024;
+    const size_t grp = kGrpFixed + 2 * ((sizeof(JetVec) + 15) & ~15) + 16;
+    return (size_t)lay.n_bops * 512 + 4096 + 8192 + (size_t)lay.n_floats * 4 + kJPC * grp + 1024;
 }
 
 template <int DC, int S, int SH, bool GEN, bool TRACE = false>
@@ -941,7 +996,81 @@ __global__ void tc_time_vectors_kernel(const uint8_t* __restrict__ image, TcLayo
     tvec[((size_t)step * (2 + 2 * lay.L) + v) * 16 + o] = a0 + a1;
 }
 
-size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps) { return (size_t)n_steps * (2 + 2 * d->num_blocks) * 16; }
+// ---- binning of the jets of a generation call: "small" = no live particle at index >= 64 (two of them share a tile) ---------
+// Order-preserving (deterministic) compaction in three small kernels: per-block counts, a one-warp scan, the fill.
+constexpr int kBinThreads = 256;
+__global__ void __launch_bounds__(kBinThreads) tc_bin_count_kernel(const uint8_t* __restrict__ mask, int B, int N, int vec_ok, int first_dead, uint8_t* __restrict__ flag,
+                                                                   int32_t* __restrict__ block_small) {
+    const int jet = blockIdx.x * kBinThreads + threadIdx.x;
+    int small = 0;
+    if (jet < B) {
+        small = 1;
+        const uint8_t* row = mask + (size_t)jet * N;
+        if (vec_ok) {
+            for (int n = first_dead; n < N; n += 16) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(row + n));
+                if (q.x | q.y | q.z | q.w) small = 0;
+            }
+        } else {
+            for (int n = first_dead; n < N; ++n) if (row[n]) small = 0;
+        }
+        flag[jet] = (uint8_t)small;
+    }
+    const int c = __syncthreads_count(small);
+    if (threadIdx.x == 0) block_small[blockIdx.x] = c;
+}
+__global__ void tc_bin_scan_kernel(const int32_t* __restrict__ block_small, int nblocks, int B, int32_t* __restrict__ block_off,
+                                   int32_t* __restrict__ counts) {
+    const int lane = threadIdx.x;   // one warp
+    int carry = 0;
+    for (int base = 0; base < nblocks; base += 32) {
+        const int i = base + lane;
+        const int v = i < nblocks ? block_small[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (i < nblocks) block_off[i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) { counts[0] = B - carry; counts[1] = carry; }
+}
+__global__ void __launch_bounds__(kBinThreads) tc_bin_fill_kernel(const uint8_t* __restrict__ flag, const int32_t* __restrict__ block_off, int B,
+                                                                  int32_t* __restrict__ small_list, int32_t* __restrict__ big_list) {
+    __shared__ int warp_small[kBinThreads / 32];
+    const int jet = blockIdx.x * kBinThreads + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool in = jet < B;
+    const bool small = in && flag[jet] != 0;
+    const unsigned bs = __ballot_sync(0xffffffffu, small);
+    if (lane == 0) warp_small[w] = __popc(bs);
+    __syncthreads();
+    int small_before = 0;
+    for (int i = 0; i < w; ++i) small_before += warp_small[i];
+    small_before += __popc(bs & ((1u << lane) - 1u));
+    if (!in) return;
+    const int off = block_off[blockIdx.x];
+    if (small) small_list[off + small_before] = jet;
+    else big_list[(blockIdx.x * kBinThreads - off) + (threadIdx.x - small_before)] = jet;
+}
+struct BinLayout {   // in 4-byte units after the time vectors
+    size_t counts, block_small, block_off, small_list, big_list, flag, total;
+    int nblocks;
+    explicit BinLayout(int B) {
+        nblocks = (B + kBinThreads - 1) / kBinThreads;
+        size_t at = 0;
+        auto take = [&](size_t n) { const size_t o = at; at += (n + 3) & ~(size_t)3; return o; };
+        counts = take(4); block_small = take(nblocks); block_off = take(nblocks); small_list = take(B); big_list = take(B);
+        flag = take(((size_t)B + 3) / 4);
+        total = at;
+    }
+};
+constexpr int kBinMinJets = 8;   // below this a call runs one jet per tile in the caller's order
+
+size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B) {
+    return (((size_t)n_steps * (2 + 2 * d->num_blocks) * 16 + 3) & ~(size_t)3) + BinLayout(B > 0 ? B : 0).total;
+}
 
 // MMB_TC_TRACE=1: per-phase clock64() stamps of jet 0 (tools/tc_trace.py reads them through mmb_debug_read_trace)
 static long long* g_trace_dev = nullptr;
@@ -1108,6 +1237,20 @@ int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* 
         tc_time_vectors_kernel<<<n_steps, 16 * (2 + 2 * kMaxL), 0, stream>>>(p.image, p.lay, p.temb, scratch);
         if (int rc = cuda_ok(cudaGetLastError(), "tc_time_vectors launch")) return rc;
         p.tvec = scratch;
+        static const int pair_max = [] { const char* e = getenv("MMB_PAIR_MAX"); return e ? atoi(e) : 64; }();
+        if (B >= kBinMinJets && pair_max > 0) {   // bin the jets: big ones get a tile each, small ones share tiles in pairs
+            const BinLayout bl(B);
+            int32_t* base = reinterpret_cast<int32_t*>(scratch + (((size_t)n_steps * (2 + 2 * m->dims.num_blocks) * 16 + 3) & ~(size_t)3));
+            uint8_t* flag = reinterpret_cast<uint8_t*>(base + bl.flag);
+            tc_bin_count_kernel<<<bl.nblocks, kBinThreads, 0, stream>>>(mask, B, N, ((N & 15) == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0) ? 1 : 0, pair_max,
+                                                                        flag, base + bl.block_small);
+            tc_bin_scan_kernel<<<1, 32, 0, stream>>>(base + bl.block_small, bl.nblocks, B, base + bl.block_off, base + bl.counts);
+            tc_bin_fill_kernel<<<bl.nblocks, kBinThreads, 0, stream>>>(flag, base + bl.block_off, B, base + bl.small_list, base + bl.big_list);
+            if (int rc = cuda_ok(cudaGetLastError(), "tc_bin launch")) return rc;
+            p.counts = base + bl.counts;
+            p.small_list = base + bl.small_list;
+            p.big_list = base + bl.big_list;
+        }
     }
     return dispatch<true>(m->dims, p, stream);
 }

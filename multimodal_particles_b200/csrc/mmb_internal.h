@@ -107,7 +107,7 @@ int tc_build_image(EpicModel* m, const float* packed_host);
 int launch_epic_forward_tc(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
                            const float* temb, int temb_stride, int B, int N,
                            float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream);
-size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps);
+size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B);
 int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
                        int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                        int B, int N, cudaStream_t stream);
