@@ -319,7 +319,7 @@ def main():
                 other = secondary_configs(torch, _native, device, pk)
             except Exception as exc:  # the headline line must not depend on the side measurements
                 other = {"error": f"{type(exc).__name__}: {exc}"}
-        launches = K * (2 + (1 if world > 1 else 0))   # time-vector prologue + generation kernel (+ histogram kernel); NCCL's own kernels not counted
+        launches = K * (5 + (1 if world > 1 else 0))   # time-vector prologue + 3 jet-binning kernels + generation kernel (+ histogram kernel); NCCL's own kernels not counted
         line = {"metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",

@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
     const bool have = slot < n_slots;
     // tile -> jet(s).  `paired` feeds MMA operands, so it is broadcast; the jet ids only feed per-thread addresses and keys.
     bool paired = false;
-    long jet = slot;        // the jet of THIS thread's rows (-1: none)
+    int jet = (int)slot;    // the jet of THIS thread's rows (-1: none); 32-bit on purpose: it stays live through the whole loop
     if constexpr (GENERATE) {
         if (p.counts && have) {
             const long n_pairs = (n_small + 1) / 2;   // paired tiles take longer per step: they go first, the single-jet tiles fill the tail
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             } else {
                 paired = true;
                 const long t2 = 2 * slot + ((tid >> 6) & 1);   // rows 0-63: first jet of the pair, rows 64-127: second
-                jet = t2 < n_small ? (long)__ldg(p.small_list + t2) : -1;
+                jet = t2 < n_small ? __ldg(p.small_list + t2) : -1;
             }
         }
     }
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         const int N = p.N, r = gt;                       // r: tile row (TMEM lane); n: the particle it carries
         const int n = paired ? (32 * (((wq & 1) - rot) & 1) + lane) : ((r + 128 - 32 * rot) & 127);
         const bool valid = has_jet && n < N;
-        const size_t pidx = (size_t)jet * N + n;
+        const size_t pidx = (size_t)jet * N + n;   // prologue loads only; the stores at the end recompute it
         // ---- state
         float xs[DC];
         int kk = 0, m = 0;
@@ -566,7 +566,12 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         // pipeline the shared-memory loads of the per-jet global MLP, the longest serial stretch of a step.  All mutable
         // per-thread state lives inside the lambda (nothing captured by reference is written).
         auto run_steps = [&](auto solo_tag, const float (&xs_in)[DC], const int kk_in) {
-        constexpr bool SOLO = decltype(solo_tag)::value;
+        // MODE 0: a warp with live particles (all row work; possibly special as well); 1: a special warp without live particles;
+        // 2: neither — it only keeps the barriers.  `skip` is a compile-time fact inside each copy.
+        constexpr int MODE = decltype(solo_tag)::value;
+        constexpr bool SOLO = MODE == 1, ROWS = MODE == 0;
+        const bool special_here = MODE == 1 ? true : (MODE == 2 ? false : is_special);
+        const bool issuer_here = MODE == 2 ? false : is_issuer;
         float xs[DC];
 #pragma unroll
         for (int c = 0; c < DC; ++c) xs[c] = xs_in[c];
@@ -577,15 +582,13 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         // hardware, and 60 % of the issue slots are idle anyway); warps without row work, the special warp included, do not
         // wait at all — the barrier after the epilogue is what orders the next MMA behind this one's readers.
         auto wait_mma = [&](int trace_id = -1) {
-            bool waits = !skip;
-            if constexpr (SOLO) waits = false;
-            if (waits) {
+            if constexpr (ROWS) {
                 mbar_wait(mbar, phase);
                 if constexpr (TRACE) { if (trace_id >= 0 && p.trace && jet == 0 && trace_step == 3 && lane == 0) p.trace[trace_id] = clock64(); }
             }
             phase ^= 1;
         };
-#define MMB_TRACE_X(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && is_special && lane == 0) p.trace[id] = clock64(); } } while (0)
+#define MMB_TRACE_X(id) do { if constexpr (TRACE) { if (p.trace && jet == 0 && step == 3 && special_here && lane == 0) p.trace[id] = clock64(); } } while (0)
         uint32_t uq0 = 0, uq1 = 0, uq2 = 0, uq3 = 0;   // this particle's jump uniforms of the current group of four steps
         for (int step = 0; step < n_steps; ++step) {
             trace_step = step;
@@ -593,7 +596,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             // ---- (a) time vectors (warp 0) and the first A row [x_hi, x_lo, onehot(k)] * m
             if (GENERATE && p.tvec) {
                 // the time is shared by all jets at generation: the vectors were computed once per step by the prologue kernel
-                if (is_special) {
+                if (special_here) {
                     const float* tv = p.tvec + (size_t)step * (2 + 2 * L) * 16;
                     const int vi = lane >> 4;   // two vectors per pass
                     for (int v0 = 0; v0 < 2 + 2 * L; v0 += 2) {
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                         else jv.tv_l1[(v - 2) >> 1][o16] = val;
                     }
                 }
-            } else if (is_special) {
+            } else if (special_here) {
                 const float* te = GENERATE ? p.temb + (size_t)step * T : p.temb + (size_t)jet * p.temb_stride;
                 const int t0 = hf * (T / 2), t1 = t0 + T / 2;
                 float a0 = hf ? 0.0f : s_wf[lay.c0 + o16], a1 = hf ? 0.0f : s_wf[lay.g0b + o16];
@@ -636,7 +639,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                     if (hf == 0) { jv.tv_g1[l][o16] = b0; jv.tv_l1[l][o16] = b1; }
                 }
             }
-            if constexpr (!SOLO) if (!skip) {
+            if constexpr (ROWS) {
                 float row[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) row[i] = 0.0f;
@@ -655,7 +658,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             MMB_TRACE(1);
             // ---- (b) local_0
             MMB_TRACE_X(20);
-            if (is_issuer && elect_one()) {
+            if (issuer_here && elect_one()) {
                 tc_fence_after();
                 gemm(lay.bop_local0());
                 umma(d_main, amask_desc, bb0_desc, idesc_k, 1);  // + bias on live rows; dead rows stay exactly 0
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_after();
             MMB_TRACE(2);
             float acc[16], xl[16];
-            if constexpr (!SOLO) if (!skip) {
+            if constexpr (ROWS) {
                 tmem_ld16(t_main, acc);
                 lrelu16(xl, acc);
                 if (lay.skip) tmem_st16(t_skip, xl);   // x_local_skip (epic.py:148) parked in TMEM, not in registers
@@ -680,7 +683,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             for (int l = 0; l < L; ++l) {
                 const float* Wl = s_wf + lay.layer0 + l * lay.layer_stride;
                 // ---- (d) pooling GEMM (ones x XL, K = 128 particles) + fc_local1 on the same tile
-                if (is_issuer && elect_one()) {
+                if (issuer_here && elect_one()) {
                     tc_fence_after();
                     umma_pool8(d_pool, pool_a_lo, pool_a_hi, pool_desc0, idesc_pool, pool_live);  // K-step j = rows 16j..16j+15, MN-major
                     gemm(lay.bop_l1(l));
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 }
                 phase ^= 1;
                 // ---- (e) global path on warp 0 of the group (fp32, CUDA cores); the other warps park at the barrier below
-                if (is_special) {
+                if (special_here) {
                     mbar_wait(mbar, phase ^ 1);
                     tc_fence_after();
                     float sv[16];
@@ -738,7 +741,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(4 + 4 * l);
                 // ---- (f) fc_local1 epilogue -> A operand of fc_local2
                 tc_fence_after();
-                if constexpr (!SOLO) if (!skip) {
+                if constexpr (ROWS) {
                     tmem_ld16(t_main, acc);
                     float l1[16], bl[16];
                     lds16(jv.bias_l1, bl);
@@ -751,7 +754,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(5 + 4 * l);
                 // ---- (g) fc_local2
                 if (l == 0) MMB_TRACE_X(23);
-                if (is_issuer && elect_one()) {
+                if (issuer_here && elect_one()) {
                     tc_fence_after();
                     gemm(lay.bop_l2(l));
                     umma(d_main, amask_desc, bop_desc(lay.bop_bias_l2(l)), idesc_k, 1);
@@ -761,7 +764,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 wait_mma(l == 0 ? 25 : -1);
                 MMB_TRACE(6 + 4 * l);
                 tc_fence_after();
-                if constexpr (!SOLO) if (!skip) {
+                if constexpr (ROWS) {
                     tmem_ld16(t_main, acc);
                     lrelu16_sum(xl, acc, xl);  // dead rows: unused garbage, zeroed at pack
                     if (lay.skip) {
@@ -777,7 +780,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 MMB_TRACE(7 + 4 * l);
             }
             // ---- (i) output layer (epic.py:158-162)
-            if (is_issuer && elect_one()) {
+            if (issuer_here && elect_one()) {
                 tc_fence_after();
                 // with a discrete head the operand is [W_out(v rows) ; F1 W_out(z rows)]: the output layer and the first
                 // head Linear have no nonlinearity between them, so columns DC.. are already F1 z + f1 (mbm.py:105-111)
@@ -790,10 +793,10 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_after();
             MMB_TRACE(12);
             float h[16];
-            if constexpr (!SOLO) if (!skip) tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
+            if constexpr (ROWS) tmem_ld16(t_main, h);   // h[0..DC) = velocity (0 on dead rows); h[DC..) = head pre-activation or raw logits
             float lg[S];
             if constexpr (SH > 0) {
-                if constexpr (!SOLO) if (!skip) {
+                if constexpr (ROWS) {
                     float z1[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) z1[i] = i < SH ? selu_fast(h[DC + (i < SH ? i : 0)]) : 0.0f;
@@ -802,7 +805,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 tc_fence_before();
                 fence_proxy_async();
                 group_bar(1 + grp);
-                if (is_issuer && elect_one()) {
+                if (issuer_here && elect_one()) {
                     tc_fence_after();
                     gemm(lay.bop_h2());
                     umma(d_main, ones_desc, bop_desc(lay.bop_bias_h2()), idesc_k, 1);
@@ -811,7 +814,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
                 wait_mma();
                 tc_fence_after();
                 MMB_TRACE(14);
-                if (SOLO || skip) {
+                if constexpr (!ROWS) {
                 } else if constexpr (S <= 8) {
                     float l8[8];
                     tmem_ld8(t_main, l8);
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             tc_fence_before();  // orders this step's last tcgen05.ld before the next step's first MMA (via the group barrier)
             MMB_TRACE(15);
 
-            if constexpr (GENERATE && !SOLO) if (!skip) {
+            if constexpr (GENERATE && ROWS) {
                 // ---- (k) hybrid update in registers (bridges.py:38-45,179-201)
                 const StepScalars sc{p.dt, __ldg(p.step_tab + step * 4 + 0), __ldg(p.step_tab + step * 4 + 1), 0.0f};
 #pragma unroll
@@ -864,13 +867,15 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             if constexpr (!GENERATE) {
                 if (valid) {
 #pragma unroll
-                    for (int c = 0; c < DC; ++c) p.v_out[pidx * DC + c] = h[c];
+                    const size_t pout = (size_t)jet * p.N + n;
 #pragma unroll
-                    for (int s = 0; s < S; ++s) p.logits_out[pidx * S + s] = lg[s];
+                    for (int c = 0; c < DC; ++c) p.v_out[pout * DC + c] = h[c];
+#pragma unroll
+                    for (int s = 0; s < S; ++s) p.logits_out[pout * S + s] = lg[s];
                     if (p.hidden_out) {
 #pragma unroll
                         for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(p.hidden_out + pidx * 16 + i) =
+                            *reinterpret_cast<float4*>(p.hidden_out + pout * 16 + i) =
                                 live ? make_float4(xl[i], xl[i + 1], xl[i + 2], xl[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
@@ -878,18 +883,21 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         }
         if constexpr (GENERATE) {
             if (valid) {
+                const size_t pout = (size_t)jet * p.N + n;
 #pragma unroll
-                for (int c = 0; c < DC; ++c) p.x[pidx * DC + c] = xs[c];
-                p.k[pidx] = (uint8_t)kk;
-                if (paired && n + 64 < N) {   // a small jet's particles 64.. are dead and have no row in a paired tile: final state 0
+                for (int c = 0; c < DC; ++c) p.x[pout * DC + c] = xs[c];
+                p.k[pout] = (uint8_t)kk;
+                if (paired && n + 64 < p.N) {   // a small jet's particles 64.. are dead and have no row in a paired tile: final state 0
 #pragma unroll
-                    for (int c = 0; c < DC; ++c) p.x[(pidx + 64) * DC + c] = 0.0f;
-                    p.k[pidx + 64] = 0;
+                    for (int c = 0; c < DC; ++c) p.x[(pout + 64) * DC + c] = 0.0f;
+                    p.k[pout + 64] = 0;
                 }
             }
         }
         };
-        if (GENERATE && skip && is_special) run_steps(std::true_type{}, xs, kk); else run_steps(std::false_type{}, xs, kk);
+        if (!skip) run_steps(std::integral_constant<int, 0>{}, xs, kk);
+        else if (is_special) run_steps(std::integral_constant<int, 1>{}, xs, kk);
+        else run_steps(std::integral_constant<int, 2>{}, xs, kk);
     }
     tc_fence_before();
     __syncthreads();

@@ -16,7 +16,7 @@ names = {1: "time vectors + A0 row + barrier", 2: "local_0 MMA round trip", 3: "
          7: "L0 fc_local2 epilogue + barrier", 8: "L1 pool+fc_local1 MMA, global MLP, barrier", 9: "L1 fc_local1 epilogue + barrier",
          10: "L1 fc_local2 MMA round trip", 11: "L1 fc_local2 epilogue + barrier", 12: "out+head0 MMA round trip",
          14: "selu + barrier + head2 MMA round trip", 15: "logits load", 16: "update (Euler, philox, jump)"}
-for B in (1, 1184):
+for B in (1, 1184, 2368):
     b = bench.source_batch(B, 1)
     x, k, m = b.source_continuous.to(dev).contiguous(), as_u8(b.source_discrete.to(dev)), as_u8(b.source_mask.to(dev))
     for _ in range(2):
