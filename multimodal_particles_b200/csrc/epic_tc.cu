@@ -1074,7 +1074,8 @@ struct BinLayout {   // in 4-byte units after the time vectors
         total = at;
     }
 };
-constexpr int kBinMinJets = 8;   // below this a call runs one jet per tile in the caller's order
+constexpr int kBinMinJets = 1;   // every call is binned: where a jet runs (paired tile or not, which rotation) depends on the jet alone,
+                                 // so its result does not depend on the size or composition of the call
 
 size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B) {
     return (((size_t)n_steps * (2 + 2 * d->num_blocks) * 16 + 3) & ~(size_t)3) + BinLayout(B > 0 ? B : 0).total;

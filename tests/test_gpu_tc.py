@@ -104,6 +104,36 @@ def test_in_kernel_philox_equals_injected_philox_uniforms(case, golden_dir):
         assert torch.equal(a.discrete, b.discrete) and torch.equal(a.continuous, b.continuous), precision
 
 
+def test_paired_tiles_give_the_same_jets_as_single_tiles():
+    """mmb_generate bins the jets of a call and lets two small jets share one 128-row tile.  Whether a jet runs in a paired
+    tile, and with which row rotation, depends on the jet alone: calls of 1, 3 or 4 jets (different tile mates, or none)
+    give the same jets as one call of 515, bit for bit."""
+    cfg = MultimodalBridgeMatchingConfig()
+    cfg.bridge.num_timesteps = 20
+    torch.manual_seed(3)
+    model = MultiModalBridgeMatching(cfg).to(DEV)
+    with torch.no_grad():
+        model.encoder.fc_layer[2].weight.mul_(6.0)
+        model.encoder.epic.epic.output_layer.weight_g.mul_(3.0)
+    b = jetclass_like_databatch(515, generator=torch.Generator().manual_seed(5))   # odd count: one small jet stays alone in its tile
+    mult = b.source_mask[..., 0].sum(1)
+    assert (mult <= 32).sum() > 20 and ((mult > 32) & (mult <= 64)).sum() > 50 and (mult > 64).sum() > 20
+    mk = lambda sl: HybridState(None, b.source_continuous[sl].clone(), b.source_discrete[sl].clone(), b.source_mask[sl].clone())
+    model.seed = 11
+    whole = model.simulate_dynamics(mk(slice(None)), None, precision="bf16", jet_offset=0)
+    lo = 0
+    for size in [4, 1, 3] * 60:
+        if lo >= 515:
+            break
+        part = model.simulate_dynamics(mk(slice(lo, lo + size)), None, precision="bf16", jet_offset=lo)
+        same = torch.equal(part.continuous, whole.continuous[lo:lo + size]) and torch.equal(part.discrete, whole.discrete[lo:lo + size])
+        assert same, (lo, size)
+        lo += size
+    dead = b.source_mask == 0
+    assert (whole.discrete[dead] == 0).all() and (whole.continuous[dead.expand(-1, -1, 3)] == 0).all()
+    assert (whole.discrete != b.source_discrete).float().mean() > 0.05
+
+
 def w1(a, b):
     a, b = np.sort(np.asarray(a, np.float64)), np.sort(np.asarray(b, np.float64))
     n = min(len(a), len(b))
