@@ -109,16 +109,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// [128 rows x 128 k] bf16 tile, K-major canonical: 8-row groups 2048 B apart (SBO), 16-byte k-chunks
-// 128 B apart (LBO).  Thread `row` stores columns [32*chunk4, 32*chunk4+32) of its row (4 x 16 B).
-__device__ __forceinline__ void store_row32(uint8_t* tile, int row, int chunk4, const float (&v)[32]) {
-    uint8_t* p = tile + (row >> 3) * 2048 + (row & 7) * 16 + chunk4 * 4 * 128;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(p + c * 128) = make_uint4(pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                                                            pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-}
-
 // fp32 side table (floats), per block then the per-particle output vector
 struct HeadTable {
     // per block: n1g n1b b1 n2g n2b n3g n3b  (7 x 128); the q / k / v biases live in the operand image or are folded away
@@ -192,21 +182,9 @@ __device__ __forceinline__ int warp_halving_index(int lane) {
     return idx;
 }
 
-// 16 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 __device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
-__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
-// thread `row` stores columns [col, col + CW) of its row of a K-major bf16 tile (16-byte k-chunks 128 B apart)
+// [128 rows x 128 k] bf16 tile, K-major canonical: 8-row groups 2048 B apart (SBO), 16-byte k-chunks 128 B apart (LBO).
+// thread `row` stores columns [col, col + CW) of its row
 template <int CW>
 __device__ __forceinline__ void store_row(uint8_t* tile, int row, int col, const float (&v)[CW]) {
     uint8_t* p = tile + (row >> 3) * 2048 + (row & 7) * 16 + (col >> 3) * 128;

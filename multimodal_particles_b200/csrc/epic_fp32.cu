@@ -208,8 +208,6 @@ __device__ void epic_forward_jet(const float* __restrict__ W, const MmbEpicLayou
             }
             for (; o < H; ++o) l1[o] = lrelu(dot_from(s.pj[o], Wl + Lo.l_l1_w + (size_t)o * Kl, xn, H));
             // fc_local2 + residual, mask, trunk skip.  New values overwrite xn only after all H are known.
-            float* nw = s.skipl;  // not used as scratch: see below
-            (void)nw;
             for (o = 0; o + 4 <= H; o += 4) {
                 float acc[4] = {__ldg(Wl + Lo.l_l2_b + o), __ldg(Wl + Lo.l_l2_b + o + 1), __ldg(Wl + Lo.l_l2_b + o + 2),
                                 __ldg(Wl + Lo.l_l2_b + o + 3)};

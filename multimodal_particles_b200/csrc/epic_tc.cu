@@ -73,7 +73,6 @@ struct TcLayout {
     __host__ __device__ int bop_l1(int l) const { return 1 + 2 * l; }
     __host__ __device__ int bop_l2(int l) const { return 2 + 2 * l; }
     __host__ __device__ int bop_out() const { return 1 + 2 * L; }
-    __host__ __device__ int bop_h0() const { return 2 + 2 * L; }
     __host__ __device__ int bop_h2() const { return 3 + 2 * L; }
     // bias operands ([o][0] = hi, [o][1] = lo as bf16): consumed as one more K-step against a mask/ones A tile
     // every weight operand w has a low-order companion at w + n_weights(): W = hi + lo with both halves
@@ -506,7 +505,6 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
 #pragma unroll
             for (int c = 0; c < DC; ++c) xs[c] = 0.0f;
         }
-        const float mf = (float)m;
         const bool live = m != 0;
         {
             uint8_t* q = amask + (r >> 3) * 256 + (r & 7) * 16;
@@ -569,7 +567,7 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         // MODE 0: a warp with live particles (all row work; possibly special as well); 1: a special warp without live particles;
         // 2: neither — it only keeps the barriers.  `skip` is a compile-time fact inside each copy.
         constexpr int MODE = decltype(solo_tag)::value;
-        constexpr bool SOLO = MODE == 1, ROWS = MODE == 0;
+        constexpr bool ROWS = MODE == 0;
         const bool special_here = MODE == 1 ? true : (MODE == 2 ? false : is_special);
         const bool issuer_here = MODE == 2 ? false : is_issuer;
         float xs[DC];
@@ -866,7 +864,6 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             }
             if constexpr (!GENERATE) {
                 if (valid) {
-#pragma unroll
                     const size_t pout = (size_t)jet * p.N + n;
 #pragma unroll
                     for (int c = 0; c < DC; ++c) p.v_out[pout * DC + c] = h[c];
