@@ -221,7 +221,10 @@ int mmb_bridge_update(float* x, uint8_t* k, uint8_t* mask,
  * (mbm.py:199-216) minus the final .cpu().
  *   u_jump: [n_steps,B,N] pre-drawn uniforms, or NULL to draw in-kernel with Philox4x32-10 keyed by
  *   (seed, jet_offset + jet, step, particle) — results are then invariant to how jets are sharded.
- *   workspace: mmb_generate_workspace_bytes(m, B, N, precision) bytes of device memory.
+ *   workspace: mmb_generate_workspace_bytes(m, B, N, precision) bytes of device memory (step table image, per-step
+ *   time vectors, and the jet lists of the tensor-core path, which bins the jets of a call on the device: jets without a
+ *   live particle at index >= 64 share a 128-row tile in pairs.  Where a jet runs depends on the jet alone, so results
+ *   do not depend on the size or composition of the call either).
  */
 size_t mmb_generate_workspace_bytes(const MmbEpicModel* m, int B, int N, int precision);
 int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mask,
