@@ -16,10 +16,8 @@ Differences from the reference, all deliberate:
 * the sampler covers the live configuration, the 'C' time grid, ``no_noise_final_step``, Langevin corrector steps and the
   jump corrector; conditioning/guidance is not built (it differentiates through the network).
 """
-import ctypes
 import math
 from types import SimpleNamespace
-from typing import Optional
 
 import numpy as np
 import torch

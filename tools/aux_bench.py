@@ -14,7 +14,6 @@ import bench  # noqa: E402
 from multimodal_particles_b200 import _native  # noqa: E402
 from multimodal_particles_b200.observables import jet_observables  # noqa: E402
 from multimodal_particles_b200.sharding import ValidationHistograms  # noqa: E402
-from multimodal_particles_b200.source import sample_source_state  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
