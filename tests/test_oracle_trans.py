@@ -168,3 +168,17 @@ def test_corrector_whole_trajectory(gold):
     assert np.array_equal(dims, z["smpL/dims_final"])
     np.testing.assert_allclose(x, z["smpL/x_final"], rtol=1e-3, atol=5e-3)
     np.testing.assert_allclose(oh, z["smpL/oh_final"], rtol=1e-3, atol=5e-3)
+
+
+def test_jump_sampler_constructor_accepts_the_optional_features_and_rejects_conditioning(gold):
+    """host logic only: corrector steps, the jump corrector and the 'C' grid are built; conditioning is not (it needs the
+    network's backward pass, sampler.py:133-135) and says so instead of silently sampling unconditionally"""
+    from multimodal_particles_b200.transdimensional import JumpSampler
+    z, cfg, model, packed = gold
+    sk = {k: v for k, v in vars(cfg.sampler_kwargs).items() if k not in ("class_name", "do_jump_back", "jump_back_start_time")}
+    ok = JumpSampler(structure=model.structure, **dict(sk, corrector_steps=2, do_jump_corrector=True, dt_schedule="C",
+                                                       no_noise_final_step=True))
+    assert ok.corrector_steps == 2 and ok.do_jump_corrector and abs(float(ok.get_dt(torch.tensor([0.9]))) - sk["dt_schedule_h"]) < 1e-9
+    for bad in (dict(do_conditioning=True), dict(dt_schedule="quadratic"), dict(sample_near_atom=False)):
+        with pytest.raises(NotImplementedError):
+            JumpSampler(structure=model.structure, **dict(sk, **bad))
