@@ -105,8 +105,17 @@ def source_batch(n_jets, seed):
     return jetclass_like_databatch(n_jets, N_PART, generator=torch.Generator().manual_seed(seed))
 
 
+def host_threads():
+    """Threads the CPU arm uses: every core this process may run on.  Set explicitly — torchrun exports OMP_NUM_THREADS=1,
+    which would otherwise serialise the OpenMP port (round 1: the reference arm timed out at N = 2, 4, 8)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_jets_per_s(n_jets, repeats=1, seed=1234):
-    """The oracle port on the host cores, all OpenMP threads, same workload distribution."""
+    """The oracle port on the host cores, all host threads (OpenMP over jets), same workload distribution."""
     import oracle_lib as ol
     _, model = build_model(None)
     dims, packed = ol.packed_model(model)
@@ -116,16 +125,20 @@ def cpu_port_jets_per_s(n_jets, repeats=1, seed=1234):
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        ol.generate(dims, packed, x, k, m, tab, seed=7, jet_offset=0)
+        ol.generate(dims, packed, x, k, m, tab, seed=7, jet_offset=0, nthreads=host_threads())
         best = min(best, time.perf_counter() - t0)
-    return n_jets / best, best, ol.lib().mmbo_max_threads()
+    return n_jets / best, best, host_threads()
 
 
 def run_reference(args, rank):
     """--impl reference: the CPU implementation of the path (oracle port), rank 0 only."""
     if rank != 0:
         return
-    sample = 4096                        # ~4 s per step on 16 host threads
+    # bounded sample: size each step so that warm-up + K steps stay under ~100 s of CPU work whatever the host is
+    rate, _, _ = cpu_port_jets_per_s(256)
+    budget_s = 100.0
+    sample = int(min(4096, max(64, rate * budget_s / (args.steps + 1))))
+    sample -= sample % 64
     for _ in range(max(min(args.warmup, 1), 1)):
         cpu_port_jets_per_s(sample)
     times = []

@@ -20,6 +20,7 @@ from .bridges import AbsorbingBridge, LinearUniformBridge, TelegraphBridge
 from .epic import EPiCWrapper, as_u8
 from .multimodal_bridge_matching import MultiHeadLoss, _ModuleBase, to_host_async
 from .states import AbsorbingBridgeState, OutputHeads
+from .sharding import next_jet_offset
 from .steptable import build_step_table
 
 
@@ -194,8 +195,7 @@ class AbsorbingFlow(_ModuleBase):
         k, mask = as_u8(k64.to(device)), as_u8(state.mask_t.to(device)).clone()
         B, N, _ = x.shape
         if jet_offset is None:
-            jet_offset = self._jets_generated
-            self._jets_generated += B
+            jet_offset = next_jet_offset(self, B)
         prep = lambda u: None if u is None else u.to(device, torch.float32).reshape(table.n_steps, B, N).contiguous()
         _native.generate_absorbing(gen.native_trunk(device), gen.native_head(device), x, k, mask, table,
                                    gen.time_bias(table.t), prep(uniforms_jump), prep(uniforms_absorb),
@@ -229,11 +229,12 @@ class AbsorbingFlow(_ModuleBase):
             t = self.min_t + (1 - self.min_t) * torch.rand(B, device=device)
         t = t.to(device, torch.float32).contiguous()
         prep = lambda a: None if a is None else a.to(device, torch.float32).contiguous()
-        off, self._bridges_sampled = getattr(self, "_bridges_sampled", 0), getattr(self, "_bridges_sampled", 0) + B
+        off = next_jet_offset(self, B, "_bridges_sampled")
         xt, kt = _native.sample_bridges(x0, x1, as_u8(batch.source_discrete.to(device)), as_u8(batch.target_discrete.to(device)), t,
                                         self.bridge_continuous.sigma, self.bridge_discrete.gamma, self.vocab_size, prep(z), prep(u),
                                         seed=self.seed, jet_offset=off)
         time = self.reshape_time(t, x1)
+        self.bridge_absorbing.seed = self.seed
         mask_t = self.bridge_absorbing.sample(time, batch.target_mask.to(device), uniforms=u_absorb)
         return AbsorbingBridgeState(time, xt, kt.long().unsqueeze(-1), mask_t)
 

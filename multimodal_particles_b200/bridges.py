@@ -21,6 +21,7 @@ import torch
 
 from . import _native
 from .epic import as_u8
+from .sharding import next_jet_offset
 from .steptable import survival_probability, telegraph_coefficients
 
 NO_EULER, NO_JUMP = 2, 4
@@ -84,6 +85,7 @@ class AbsorbingBridge:
         self.gamma_absorb = torch.tensor(config.bridge.gamma_absorb, dtype=torch.float32)
         self.time_epsilon = config.bridge.time_eps
         self.vocab_size = 2
+        self.seed = 0   # Philox key of sample() when no uniforms are injected (AbsorbingFlow.sample_bridges sets its own)
 
     def survival_probability(self, t):
         return survival_probability(t, float(self.gamma_absorb))
@@ -95,8 +97,8 @@ class AbsorbingBridge:
         B, N = target_mask.shape[0], target_mask.shape[1]
         sp = self.survival_probability(time.reshape(B).float().cpu()).to(dev).contiguous()
         u = None if uniforms is None else uniforms.reshape(B, N).to(dev, torch.float32).contiguous()
-        self._sampled = getattr(self, "_sampled", 0) + B
-        return _native.absorbing_sample(sp, as_u8(target_mask), u, jet_offset=self._sampled - B).to(torch.int64).unsqueeze(-1)
+        return _native.absorbing_sample(sp, as_u8(target_mask), u, seed=self.seed,
+                                        jet_offset=next_jet_offset(self, B, "_sampled")).to(torch.int64).unsqueeze(-1)
 
     def solver_step(self, state, heads, delta_t, uniforms=None):
         m64 = state.mask_t

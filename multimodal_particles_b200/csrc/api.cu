@@ -4,8 +4,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
-#include <vector>
 
 #include "mmb_device.cuh"
 #include "mmb_internal.h"
@@ -30,6 +30,110 @@ int cuda_ok(cudaError_t e, const char* what) {
 // device image of the step table: [n_steps][4] = (bc, cc, sp, 0) then [n_steps][T] temb
 static size_t table_floats(int n_steps, int T) { return (size_t)n_steps * (4 + (size_t)T); }
 
+// ---- table cache -------------------------------------------------------------------------------------------------------
+// A generation call gets its per-step scalars as HOST arrays (MmbStepTable).  They are a function of the bridge config only,
+// so the device image is built once per distinct table and kept on the model handle.  Steady state: hash the host arrays
+// (a few KB), find the slot, launch — no allocation, no copy, nothing that blocks the host.  First use of a table: fill the
+// slot's page-locked staging buffer and enqueue ONE cudaMemcpyAsync on the caller's stream (buffers grow on demand).  A fifth
+// distinct table evicts the oldest slot after a device synchronisation (kernels of any stream may still be reading it).
+constexpr int kTableSlots = 4;
+struct TableSlot {
+    uint64_t hash = 0;
+    size_t floats = 0, cap = 0;
+    float* dev = nullptr;
+    float* pinned = nullptr;
+    bool valid = false;
+};
+struct TableCache {
+    std::mutex mu;
+    TableSlot slot[kTableSlots];
+    int next = 0;
+};
+
+TableCache* table_cache_create() { return new (std::nothrow) TableCache(); }
+
+void table_cache_destroy(TableCache* c) {
+    if (!c) return;
+    for (TableSlot& s : c->slot) {
+        if (s.dev) cudaFree(s.dev);
+        if (s.pinned) cudaFreeHost(s.pinned);
+    }
+    delete c;
+}
+
+static uint64_t hash_words(uint64_t h, const void* data, size_t bytes) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0x100000001B3ull;
+        h ^= h >> 29;
+    }
+    for (; i < bytes; ++i) h = (h ^ p[i]) * 0x100000001B3ull;
+    return h;
+}
+
+// Device image with `floats` floats and content hash `hash`; `fill(dst)` writes it into host memory on a miss.
+template <typename Fill>
+static int table_cache_get(TableCache* c, uint64_t hash, size_t floats, cudaStream_t stream, Fill fill, const float** out) {
+    if (!c) return fail(MMB_EINVAL, "model has no table cache");
+    std::lock_guard<std::mutex> lock(c->mu);
+    for (TableSlot& s : c->slot)
+        if (s.valid && s.hash == hash && s.floats == floats) {
+            *out = s.dev;
+            return MMB_OK;
+        }
+    TableSlot* s = nullptr;
+    for (TableSlot& t : c->slot)
+        if (!t.valid) { s = &t; break; }
+    if (!s) {   // evict round-robin; the old image may still be in use on some stream
+        s = &c->slot[c->next];
+        c->next = (c->next + 1) % kTableSlots;
+        if (int rc = cuda_ok(cudaDeviceSynchronize(), "table cache eviction")) return rc;
+        s->valid = false;
+    }
+    if (s->cap < floats) {
+        if (s->dev) cudaFree(s->dev);
+        if (s->pinned) cudaFreeHost(s->pinned);
+        s->dev = s->pinned = nullptr;
+        s->cap = 0;
+        if (int rc = cuda_ok(cudaMalloc(&s->dev, floats * sizeof(float)), "cudaMalloc step table")) return rc;
+        if (int rc = cuda_ok(cudaMallocHost(&s->pinned, floats * sizeof(float)), "cudaMallocHost step table")) return rc;
+        s->cap = floats;
+    }
+    fill(s->pinned);
+    if (int rc = cuda_ok(cudaMemcpyAsync(s->dev, s->pinned, floats * sizeof(float), cudaMemcpyHostToDevice, stream), "step table upload")) return rc;
+    s->hash = hash;
+    s->floats = floats;
+    s->valid = true;
+    *out = s->dev;
+    return MMB_OK;
+}
+
+static uint64_t step_table_hash(const MmbStepTable* st, int T, bool with_sp) {
+    const size_t n = (size_t)st->n_steps;
+    uint64_t h = 0xCBF29CE484222325ull;
+    h = hash_words(h, &st->n_steps, sizeof(st->n_steps));
+    h = hash_words(h, &T, sizeof(T));
+    h = hash_words(h, st->bc, n * sizeof(float));
+    h = hash_words(h, st->cc, n * sizeof(float));
+    if (with_sp && st->sp) h = hash_words(h, st->sp, n * sizeof(float));
+    if (st->t) h = hash_words(h, st->t, n * sizeof(float));
+    return hash_words(h, st->temb, n * T * sizeof(float));
+}
+
+static void fill_step_table(float* img, const MmbStepTable* st, int T) {
+    const int n = st->n_steps;
+    for (int i = 0; i < n; ++i) {
+        img[(size_t)i * 4 + 0] = st->bc[i];
+        img[(size_t)i * 4 + 1] = st->cc[i];
+        img[(size_t)i * 4 + 2] = st->sp ? st->sp[i] : 0.0f;
+        img[(size_t)i * 4 + 3] = st->t ? st->t[i] : 0.0f;
+    }
+    memcpy(img + (size_t)n * 4, st->temb, (size_t)n * T * sizeof(float));
+}
+
 }  // namespace mmb
 
 using namespace mmb;
@@ -51,6 +155,7 @@ int mmb_epic_create(const MmbEpicDims* dims, const float* packed, size_t n_float
     if (int rc = cuda_ok(cudaSetDevice(device), "cudaSetDevice")) return rc;
     EpicModel* m = new (std::nothrow) EpicModel();
     if (!m) return fail(MMB_ENOMEM, "out of host memory");
+    m->tables = table_cache_create();
     m->dims = *dims;
     m->layout = lo;
     m->device = device;
@@ -60,7 +165,11 @@ int mmb_epic_create(const MmbEpicDims* dims, const float* packed, size_t n_float
     int rc = cuda_ok(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device), "sm count");
     if (!rc) rc = cuda_ok(cudaMalloc(&m->w, lo.total * sizeof(float)), "cudaMalloc weights");
     if (!rc) rc = cuda_ok(cudaMemcpy(m->w, packed, lo.total * sizeof(float), cudaMemcpyHostToDevice), "weight upload");
-    if (!rc && tc_supported(dims, 128)) rc = tc_build_image(m, packed);
+    try {   // the one-time packing uses std::vector: nothing may throw across the C ABI
+        if (!rc && tc_supported(dims, 128)) rc = tc_build_image(m, packed);
+    } catch (...) {
+        rc = fail(MMB_ENOMEM, "mmb_epic_create: out of host memory");
+    }
     cudaSetDevice(prev);
     if (rc) {
         mmb_epic_destroy(reinterpret_cast<MmbEpicModel*>(m));
@@ -75,6 +184,7 @@ void mmb_epic_destroy(MmbEpicModel* handle) {
     if (!m) return;
     if (m->w) cudaFree(m->w);
     if (m->tc_image) cudaFree(m->tc_image);
+    table_cache_destroy(m->tables);
     delete m;
 }
 
@@ -114,8 +224,8 @@ size_t mmb_generate_workspace_bytes(const MmbEpicModel* handle, int B, int N, in
     const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
     (void)N; (void)precision;
     if (!m) return 0;
-    // room for the device image of a step table of up to 4096 steps + the tcgen05 path's per-step time vectors and jet lists
-    return (table_floats(4096, m->dims.dim_time_emb) + tc_generate_scratch_floats(&m->dims, 4096, B)) * sizeof(float);
+    // the tensor-core paths' per-step time vectors (up to 4096 steps) and jet lists; the step table itself is cached on the handle
+    return tc_generate_scratch_floats(&m->dims, 4096, B) * sizeof(float);
 }
 
 int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t* mask,
@@ -126,29 +236,24 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     if (!st->temb || !st->bc || !st->cc) return fail(MMB_EINVAL, "mmb_generate: incomplete step table");
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate: negative size");
     const int T = m->dims.dim_time_emb, n = st->n_steps;
-    const size_t need = table_floats(n, T) * sizeof(float);
-    if (workspace_bytes < need + tc_generate_scratch_floats(&m->dims, n, B) * sizeof(float))
+    if (workspace_bytes < tc_generate_scratch_floats(&m->dims, n, B) * sizeof(float))
         return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B too small for %d steps", workspace_bytes, n);
     if (B == 0 || N == 0 || n == 0) return MMB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // stage the table (a few KB); pageable source: the copy is staged before the call returns
-    std::vector<float> img(table_floats(n, T));
-    for (int i = 0; i < n; ++i) {
-        img[(size_t)i * 4 + 0] = st->bc[i];
-        img[(size_t)i * 4 + 1] = st->cc[i];
-        img[(size_t)i * 4 + 2] = st->sp ? st->sp[i] : 0.0f;
-        img[(size_t)i * 4 + 3] = st->t ? st->t[i] : 0.0f;
+    const float* table = nullptr;   // device image, cached on the handle (no copy, no allocation once this table has been seen)
+    try {
+        if (int rc = table_cache_get(m->tables, step_table_hash(st, T, false), table_floats(n, T), s,
+                                     [&](float* img) { fill_step_table(img, st, T); }, &table))
+            return rc;
+    } catch (...) {
+        return fail(MMB_ENOMEM, "mmb_generate: host-side failure while caching the step table");
     }
-    memcpy(img.data() + (size_t)n * 4, st->temb, (size_t)n * T * sizeof(float));
-    if (int rc = cuda_ok(cudaMemcpyAsync(workspace, img.data(), need, cudaMemcpyHostToDevice, s), "step table upload")) return rc;
-    const float* table = static_cast<const float*>(workspace);
     if (precision == MMB_PREC_FP32)
         return launch_generate_fp32(m, x, k, mask, table, n, st->dt, u_jump, seed, jet_offset, B, N, s);
     if (precision == MMB_PREC_BF16) {
         if (!m->tc_image || !tc_supported(&m->dims, N))
             return fail(MMB_EUNSUPPORTED, "tcgen05 path is built for H=16, G<=32, Dc+S<=16, head<=16, N<=128; use fp32");
-        return launch_generate_tc(m, x, k, mask, table, static_cast<float*>(workspace) + table_floats(n, T), n, st->dt, u_jump, seed,
-                                  jet_offset, B, N, s);
+        return launch_generate_tc(m, x, k, mask, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N, s);
     }
     return fail(MMB_EINVAL, "unknown precision %d", precision);
 }
@@ -162,7 +267,11 @@ int mmb_absorb_head_create(int hidden, int transformer_dim, int n_heads, int n_b
                            int device, MmbAbsorbHead** out) {
     if (!packed || !out) return fail(MMB_EINVAL, "mmb_absorb_head_create: null argument");
     AbsorbHead* h = nullptr;
-    if (int rc = absorb_head_create(hidden, transformer_dim, n_heads, n_blocks, packed, n_floats, device, &h)) return rc;
+    try {   // the one-time packing uses std::vector: nothing may throw across the C ABI
+        if (int rc = absorb_head_create(hidden, transformer_dim, n_heads, n_blocks, packed, n_floats, device, &h)) return rc;
+    } catch (...) {
+        return fail(MMB_ENOMEM, "mmb_absorb_head_create: out of host memory");
+    }
     *out = reinterpret_cast<MmbAbsorbHead*>(h);
     return MMB_OK;
 }
@@ -177,11 +286,12 @@ int mmb_absorb_head_forward(const MmbAbsorbHead* head, const float* hidden, cons
                               static_cast<cudaStream_t>(stream));
 }
 
-// workspace of mmb_generate_absorbing (floats): step table image | tbias [steps][blocks][128] | v | logits | hidden | a | uj | ua
+// workspace of mmb_generate_absorbing (floats): v | logits | hidden | a | uj | ua   (the step table and the time biases are
+// cached on the trunk's handle)
 static size_t absorbing_ws_floats(const EpicModel* m, const AbsorbHead* h, int B, int N, int n_steps) {
+    (void)h; (void)n_steps;
     const size_t P = (size_t)B * N;
-    return table_floats(n_steps, m->dims.dim_time_emb) + (size_t)n_steps * absorb_head_blocks(h) * 128 +
-           P * (m->dims.dim_continuous + m->dims.vocab_size + m->dims.dim_hidden_local + 3) + 64;
+    return P * (m->dims.dim_continuous + m->dims.vocab_size + m->dims.dim_hidden_local + 3) + 64;
 }
 
 size_t mmb_generate_absorbing_workspace_bytes(const MmbEpicModel* model, const MmbAbsorbHead* head, int B, int N, int n_steps) {
@@ -205,14 +315,22 @@ int mmb_generate_absorbing(const MmbEpicModel* model, const MmbAbsorbHead* head,
     if (B == 0 || N == 0 || n == 0) return MMB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t P = (size_t)B * N, tf = table_floats(n, T), nb = (size_t)n * nblk * 128;
-    std::vector<float> img(tf + nb);
-    memcpy(img.data() + (size_t)n * 4, st->temb, (size_t)n * T * sizeof(float));
-    memcpy(img.data() + tf, tbias, nb * sizeof(float));
-    if (int rc = cuda_ok(cudaMemcpyAsync(workspace, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice, s), "table upload")) return rc;
+    const float* img = nullptr;
+    try {
+        uint64_t hsh = hash_words(step_table_hash(st, T, true), tbias, nb * sizeof(float));
+        hsh = hash_words(hsh, &nblk, sizeof(nblk));
+        if (int rc = table_cache_get(m->tables, hsh, tf + nb, s, [&](float* dst) {
+                fill_step_table(dst, st, T);
+                memcpy(dst + tf, tbias, nb * sizeof(float));
+            }, &img))
+            return rc;
+    } catch (...) {
+        return fail(MMB_ENOMEM, "mmb_generate_absorbing: host-side failure while caching the step table");
+    }
     float* ws = static_cast<float*>(workspace);
-    const float* temb_dev = ws + (size_t)n * 4;
-    const float* tb_dev = ws + tf;
-    float* v = ws + tf + nb;
+    const float* temb_dev = img + (size_t)n * 4;
+    const float* tb_dev = img + tf;
+    float* v = ws;
     float* logits = v + P * Dc;
     float* hidden = logits + P * S;
     float* alog = hidden + P * H;

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) absorbing_sample_kernel(const float* __re
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * N) return;
     const int b = (int)(i / N), n = (int)(i % N);
-    const float uu = u ? __ldg(u + i) : u01(philox_block(seed, jet_offset + (uint64_t)b, 14, 0, n >> 2).x);
+    const float uu = u ? __ldg(u + i) : philox_uniform(seed, jet_offset + (uint64_t)b, 14, 0, n);   // word n & 3 of the quad's block, like the vector branch
     mask_t[i] = (target_mask[i] || uu < __ldg(sp + b)) ? 1 : 0;
 }
 

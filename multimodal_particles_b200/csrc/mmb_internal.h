@@ -17,7 +17,15 @@ int cuda_ok(cudaError_t e, const char* what);
 
 // Device-resident model: the packed fp32 blob (layout of include/mmbridge.h) plus the operand
 // images the tcgen05 path consumes.
+// Device copies of the per-step host tables (MmbStepTable rows, absorbing time biases), cached on the model handle and
+// keyed by a hash of their content: the first call with a table uploads it through a page-locked staging buffer on the
+// caller's stream, later calls neither copy nor allocate (api.cu).
+struct TableCache;
+TableCache* table_cache_create();
+void table_cache_destroy(TableCache* c);
+
 struct EpicModel {
+    TableCache* tables;
     MmbEpicDims dims;
     MmbEpicLayout layout;
     int device;

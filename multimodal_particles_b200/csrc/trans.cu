@@ -865,7 +865,11 @@ size_t mmb_trans_packed_floats(const MmbTransDims* dims) { return dims ? trans_f
 int mmb_trans_create(const MmbTransDims* dims, const float* packed, size_t n_floats, int device, MmbTransHeads** out) {
     if (!dims || !packed || !out) return fail(MMB_EINVAL, "mmb_trans_create: null argument");
     TransHeads* h = nullptr;
-    if (int rc = trans_create(dims, packed, n_floats, device, &h)) return rc;
+    try {   // the one-time packing uses std::vector: nothing may throw across the C ABI
+        if (int rc = trans_create(dims, packed, n_floats, device, &h)) return rc;
+    } catch (...) {
+        return fail(MMB_ENOMEM, "mmb_trans_create: out of host memory");
+    }
     *out = reinterpret_cast<MmbTransHeads*>(h);
     return MMB_OK;
 }

@@ -16,6 +16,7 @@ from torch import nn
 from . import _native
 from .bridges import LinearUniformBridge, TelegraphBridge
 from .epic import EPiCWrapper, as_u8
+from .sharding import next_jet_offset
 from .states import HybridState, MultiHeadOutput
 from .steptable import build_step_table
 
@@ -149,8 +150,7 @@ class MultiModalBridgeMatching(_ModuleBase):
         B, N, _ = x.shape
         u = None if uniforms is None else uniforms.to(device, torch.float32).reshape(table.n_steps, B, N).contiguous()
         if jet_offset is None:
-            jet_offset = self._jets_generated
-            self._jets_generated += B
+            jet_offset = next_jet_offset(self, B)
         model = self.encoder.native_model(device)
         model.generate(x, k, mask, table, u_jump=u, seed=self.seed, jet_offset=jet_offset,
                        precision=precision or self.precision)
@@ -172,8 +172,7 @@ class MultiModalBridgeMatching(_ModuleBase):
         their tails.  Philox is keyed by the global jet index, so the result does not depend on the slicing."""
         B, N, _ = state.continuous.shape
         if jet_offset is None:
-            jet_offset = self._jets_generated
-            self._jets_generated += B
+            jet_offset = next_jet_offset(self, B)
         k64 = state.discrete
         model = self.encoder.native_model(device)
         x_host = torch.empty(state.continuous.shape, dtype=torch.float32, pin_memory=True)
@@ -231,7 +230,7 @@ class MultiModalBridgeMatching(_ModuleBase):
         B = x1.shape[0]
         t = torch.rand(B, device=device) if t is None else t.to(device, torch.float32).contiguous()
         prep = lambda a: None if a is None else a.to(device, torch.float32).contiguous()
-        jet_offset, self._bridges_sampled = getattr(self, "_bridges_sampled", 0), getattr(self, "_bridges_sampled", 0) + B
+        jet_offset = next_jet_offset(self, B, "_bridges_sampled")
         xt, kt = _native.sample_bridges(x0, x1, as_u8(batch.source_discrete.to(device)), as_u8(batch.target_discrete.to(device)), t,
                                         self.bridge_continuous.sigma, self.bridge_discrete.gamma, self.vocab_size, prep(z), prep(u),
                                         seed=self.seed, jet_offset=jet_offset)

@@ -21,6 +21,29 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+RANK_STRIDE = 1 << 40   # jets a single rank can draw before its Philox indices would reach the next rank's block
+
+
+def global_rank() -> int:
+    """Rank of this process in the job: torch.distributed when initialised, else torchrun's / Lightning's environment."""
+    import os
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank()
+    for name in ("RANK", "GLOBAL_RANK", "SLURM_PROCID"):
+        if os.environ.get(name, "").isdigit():
+            return int(os.environ[name])
+    return 0
+
+
+def next_jet_offset(owner, count: int, attr: str = "_jets_generated") -> int:
+    """Default Philox ``jet_offset`` of a call that draws ``count`` jets: ``rank * 2**40 + jets this process drew before``.
+    One process per GPU (Lightning predict / DDP) therefore never reuses a (seed, jet index) pair across ranks; a caller
+    that shards explicitly passes its own offset (``shard_range``) and gets results independent of the GPU count."""
+    done = getattr(owner, attr, 0)
+    setattr(owner, attr, done + count)
+    return global_rank() * RANK_STRIDE + done
+
+
 @dataclass
 class GatherBuffers:
     """Preallocated receive buffers for the per-batch all-gather (no allocation in the loop)."""

@@ -27,6 +27,7 @@ from . import _native
 from .absorbing_flows import AttnBlock, ResnetBlock
 from .epic import EPiCWrapper
 from .multimodal_bridge_matching import _ModuleBase
+from .sharding import next_jet_offset
 
 
 # ---- noising.py ------------------------------------------------------------------------------------
@@ -481,7 +482,7 @@ class JumpSampler:
         x0 = state.get_flat_lats()
         B = x0.shape[0]
         if jet_offset is None:
-            jet_offset, self._jets_generated = self._jets_generated, self._jets_generated + B
+            jet_offset = next_jet_offset(self, B)
         # x_T ~ N(0, I), one particle per jet, centred (sampler.py:170-183)
         if noise is not None and getattr(noise, "z_init", None) is not None:
             xT = noise.z_init.to(device, torch.float32)
