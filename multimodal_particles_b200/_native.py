@@ -13,13 +13,16 @@ import torch
 from .steptable import CStepTable
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmmbridge.so")
+LIB_PATH = os.environ.get("MMB_LIB_PATH") or os.path.join(_HERE, "csrc", "libmmbridge.so")   # MMB_LIB_PATH: a differently built copy (kernel experiments)
 
 FLAG_MULTIMODAL = 0
 FLAG_ABSORBING = 1
 PREC_FP32 = 0
 PREC_BF16 = 1
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+PREC_F16 = 2
+PREC_BF16_MMA = 3
+# "bf16" = tcgen05 engine; "f16" / "bf16_mma" = warp-MMA engine (generation only) with fp16 / bf16 operands
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "f16": PREC_F16, "bf16_mma": PREC_BF16_MMA}
 
 
 class MmbError(RuntimeError):

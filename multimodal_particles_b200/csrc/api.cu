@@ -162,11 +162,14 @@ int mmb_epic_create(const MmbEpicDims* dims, const float* packed, size_t n_float
     m->w = nullptr;
     m->tc_image = nullptr;
     m->tc_image_bytes = 0;
+    m->mma_image_f16 = m->mma_image_bf16 = nullptr;
+    m->mma_image_f16_bytes = m->mma_image_bf16_bytes = 0;
     int rc = cuda_ok(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device), "sm count");
     if (!rc) rc = cuda_ok(cudaMalloc(&m->w, lo.total * sizeof(float)), "cudaMalloc weights");
     if (!rc) rc = cuda_ok(cudaMemcpy(m->w, packed, lo.total * sizeof(float), cudaMemcpyHostToDevice), "weight upload");
     try {   // the one-time packing uses std::vector: nothing may throw across the C ABI
         if (!rc && tc_supported(dims, 128)) rc = tc_build_image(m, packed);
+        if (!rc && mma_supported(dims, 128)) rc = mma_build_images(m, packed);
     } catch (...) {
         rc = fail(MMB_ENOMEM, "mmb_epic_create: out of host memory");
     }
@@ -184,6 +187,8 @@ void mmb_epic_destroy(MmbEpicModel* handle) {
     if (!m) return;
     if (m->w) cudaFree(m->w);
     if (m->tc_image) cudaFree(m->tc_image);
+    if (m->mma_image_f16) cudaFree(m->mma_image_f16);
+    if (m->mma_image_bf16) cudaFree(m->mma_image_bf16);
     table_cache_destroy(m->tables);
     delete m;
 }
@@ -225,7 +230,8 @@ size_t mmb_generate_workspace_bytes(const MmbEpicModel* handle, int B, int N, in
     (void)N; (void)precision;
     if (!m) return 0;
     // the tensor-core paths' per-step time vectors (up to 4096 steps) and jet lists; the step table itself is cached on the handle
-    return tc_generate_scratch_floats(&m->dims, 4096, B) * sizeof(float);
+    const size_t a = tc_generate_scratch_floats(&m->dims, 4096, B), b = mma_generate_scratch_floats(&m->dims, 4096, B);
+    return (a > b ? a : b) * sizeof(float);
 }
 
 int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t* mask,
@@ -236,7 +242,9 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     if (!st->temb || !st->bc || !st->cc) return fail(MMB_EINVAL, "mmb_generate: incomplete step table");
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate: negative size");
     const int T = m->dims.dim_time_emb, n = st->n_steps;
-    if (workspace_bytes < tc_generate_scratch_floats(&m->dims, n, B) * sizeof(float))
+    const size_t ws_need = (precision == MMB_PREC_F16 || precision == MMB_PREC_BF16_MMA) ? mma_generate_scratch_floats(&m->dims, n, B)
+                                                                                         : tc_generate_scratch_floats(&m->dims, n, B);
+    if (workspace_bytes < ws_need * sizeof(float))
         return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B too small for %d steps", workspace_bytes, n);
     if (B == 0 || N == 0 || n == 0) return MMB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -254,6 +262,12 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
         if (!m->tc_image || !tc_supported(&m->dims, N))
             return fail(MMB_EUNSUPPORTED, "tcgen05 path is built for H=16, G<=32, Dc+S<=16, head<=16, N<=128; use fp32");
         return launch_generate_tc(m, x, k, mask, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N, s);
+    }
+    if (precision == MMB_PREC_F16 || precision == MMB_PREC_BF16_MMA) {
+        if (!m->mma_image_f16 || !mma_supported(&m->dims, N))
+            return fail(MMB_EUNSUPPORTED, "warp-MMA engine is built for H=16, G<=32, Dc=3, S in {4,8}, head in {0,S}, N<=256; use fp32");
+        return launch_generate_mma(m, x, k, mask, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N,
+                                   precision == MMB_PREC_F16, s);
     }
     return fail(MMB_EINVAL, "unknown precision %d", precision);
 }

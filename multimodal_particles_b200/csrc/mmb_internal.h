@@ -33,6 +33,10 @@ struct EpicModel {
     float* w;             // [layout.total] fp32, device
     void* tc_image;       // bf16 UMMA operand image + fp32 side tables (epic_tc.cu), device; may be null
     size_t tc_image_bytes;
+    void* mma_image_f16;  // B-fragment tiles of the warp-MMA engine (epic_mma.cu), fp16 operands; may be null
+    size_t mma_image_f16_bytes;
+    void* mma_image_bf16; // same, bf16 operands with hi + lo weight tiles
+    size_t mma_image_bf16_bytes;
 };
 
 // bridge_update.cu
@@ -119,5 +123,13 @@ size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B);
 int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
                        int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                        int B, int N, cudaStream_t stream);
+
+// epic_mma.cu — warp-level MMA engine (register-resident chains), generation only
+bool mma_supported(const MmbEpicDims* d, int N);
+int mma_build_images(EpicModel* m, const float* packed_host);
+size_t mma_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B);
+int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
+                        int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
+                        int B, int N, bool f16, cudaStream_t stream);
 
 }  // namespace mmb

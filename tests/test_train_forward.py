@@ -95,3 +95,22 @@ def test_mirror_api_and_full_size_properties():
     ab = AbsorbingBridge(AbsorbingConfig())
     mt = ab.sample(t.view(B, 1, 1).cuda(), mask.cuda())
     assert mt.shape == (B, N, 1) and (mt.cpu() >= mask).all() and torch.equal(mt[1].cpu(), mask[1])   # t = 1: only the targets survive
+
+
+@pytest.mark.gpu
+def test_absorbing_sample_philox_is_per_particle_for_any_width():
+    """Default (in-kernel Philox) draws of AbsorbingBridge.sample: the scalar branch taken when N % 4 != 0 must use word
+    n & 3 of the quad's Philox block exactly like the vectorised branch — particle n of jet b gets the same draw whatever
+    the padded width is, and the four particles of a quad are independent (round-1 defect: they shared word .x)."""
+    from multimodal_particles_b200 import _native
+    B = 8192
+    sp = torch.full((B,), 0.5, device="cuda:0")
+    zeros = lambda n: torch.zeros(B, n, dtype=torch.uint8, device="cuda:0")
+    m8 = _native.absorbing_sample(sp, zeros(8), None, seed=3, jet_offset=17).cpu().numpy()     # vector branch
+    for n in (6, 7, 5, 3):                                                                          # scalar branch
+        mn = _native.absorbing_sample(sp, zeros(n), None, seed=3, jet_offset=17).cpu().numpy()
+        assert np.array_equal(mn, m8[:, :n]), n
+    m6 = m8[:, :6].astype(np.float64)
+    assert abs(m6.mean() - 0.5) < 0.01
+    c = np.corrcoef(m6.T)
+    assert np.abs(c - np.eye(6)).max() < 0.05, c     # sharing one uniform inside a quad gave correlation 1
