@@ -51,8 +51,7 @@ enum {
 enum {
     MMB_PREC_FP32 = 0, /* CUDA-core fp32, bit-identical to oracle/mmb_oracle.c */
     MMB_PREC_BF16 = 1, /* tcgen05 bf16 operands, fp32 accumulate in TMEM */
-    MMB_PREC_F16 = 2,  /* mmb_generate only: warp-level mma.sync chains held in registers, fp16 operands, fp32 accumulate */
-    MMB_PREC_BF16_MMA = 3 /* mmb_generate only: the same engine with bf16 operands (weights as hi + lo pairs) */
+    MMB_PREC_F16 = 2   /* mmb_generate only: warp-level mma.sync chains held in registers, fp16 operands, fp32 accumulate */
 };
 
 /*

@@ -20,9 +20,8 @@ FLAG_ABSORBING = 1
 PREC_FP32 = 0
 PREC_BF16 = 1
 PREC_F16 = 2
-PREC_BF16_MMA = 3
-# "bf16" = tcgen05 engine; "f16" / "bf16_mma" = warp-MMA engine (generation only) with fp16 / bf16 operands
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "f16": PREC_F16, "bf16_mma": PREC_BF16_MMA}
+# "bf16" = tcgen05 engine; "f16" = warp-MMA engine (generation only; fp16 operands, fp32 accumulate)
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "f16": PREC_F16}
 
 
 class MmbError(RuntimeError):

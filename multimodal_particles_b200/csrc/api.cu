@@ -162,14 +162,14 @@ int mmb_epic_create(const MmbEpicDims* dims, const float* packed, size_t n_float
     m->w = nullptr;
     m->tc_image = nullptr;
     m->tc_image_bytes = 0;
-    m->mma_image_f16 = m->mma_image_bf16 = nullptr;
-    m->mma_image_f16_bytes = m->mma_image_bf16_bytes = 0;
+    m->mma_image_f16 = nullptr;
+    m->mma_image_f16_bytes = 0;
     int rc = cuda_ok(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device), "sm count");
     if (!rc) rc = cuda_ok(cudaMalloc(&m->w, lo.total * sizeof(float)), "cudaMalloc weights");
     if (!rc) rc = cuda_ok(cudaMemcpy(m->w, packed, lo.total * sizeof(float), cudaMemcpyHostToDevice), "weight upload");
     try {   // the one-time packing uses std::vector: nothing may throw across the C ABI
         if (!rc && tc_supported(dims, 128)) rc = tc_build_image(m, packed);
-        if (!rc && mma_supported(dims, 128)) rc = mma_build_images(m, packed);
+        if (!rc && mma_supported(dims, 64)) rc = mma_build_images(m, packed);
     } catch (...) {
         rc = fail(MMB_ENOMEM, "mmb_epic_create: out of host memory");
     }
@@ -188,7 +188,6 @@ void mmb_epic_destroy(MmbEpicModel* handle) {
     if (m->w) cudaFree(m->w);
     if (m->tc_image) cudaFree(m->tc_image);
     if (m->mma_image_f16) cudaFree(m->mma_image_f16);
-    if (m->mma_image_bf16) cudaFree(m->mma_image_bf16);
     table_cache_destroy(m->tables);
     delete m;
 }
@@ -242,8 +241,7 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     if (!st->temb || !st->bc || !st->cc) return fail(MMB_EINVAL, "mmb_generate: incomplete step table");
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate: negative size");
     const int T = m->dims.dim_time_emb, n = st->n_steps;
-    const size_t ws_need = (precision == MMB_PREC_F16 || precision == MMB_PREC_BF16_MMA) ? mma_generate_scratch_floats(&m->dims, n, B)
-                                                                                         : tc_generate_scratch_floats(&m->dims, n, B);
+    const size_t ws_need = precision == MMB_PREC_F16 ? mma_generate_scratch_floats(&m->dims, n, B) : tc_generate_scratch_floats(&m->dims, n, B);
     if (workspace_bytes < ws_need * sizeof(float))
         return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B too small for %d steps", workspace_bytes, n);
     if (B == 0 || N == 0 || n == 0) return MMB_OK;
@@ -263,11 +261,10 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
             return fail(MMB_EUNSUPPORTED, "tcgen05 path is built for H=16, G<=32, Dc+S<=16, head<=16, N<=128; use fp32");
         return launch_generate_tc(m, x, k, mask, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N, s);
     }
-    if (precision == MMB_PREC_F16 || precision == MMB_PREC_BF16_MMA) {
+    if (precision == MMB_PREC_F16) {
         if (!m->mma_image_f16 || !mma_supported(&m->dims, N))
             return fail(MMB_EUNSUPPORTED, "warp-MMA engine is built for H=16, G<=32, Dc=3, S in {4,8}, head in {0,S}, N<=256; use fp32");
-        return launch_generate_mma(m, x, k, mask, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N,
-                                   precision == MMB_PREC_F16, s);
+        return launch_generate_mma(m, x, k, mask, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N, s);
     }
     return fail(MMB_EINVAL, "unknown precision %d", precision);
 }

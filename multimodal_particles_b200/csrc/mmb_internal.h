@@ -35,8 +35,6 @@ struct EpicModel {
     size_t tc_image_bytes;
     void* mma_image_f16;  // B-fragment tiles of the warp-MMA engine (epic_mma.cu), fp16 operands; may be null
     size_t mma_image_f16_bytes;
-    void* mma_image_bf16; // same, bf16 operands with hi + lo weight tiles
-    size_t mma_image_bf16_bytes;
 };
 
 // bridge_update.cu
@@ -130,6 +128,6 @@ int mma_build_images(EpicModel* m, const float* packed_host);
 size_t mma_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B);
 int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
                         int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
-                        int B, int N, bool f16, cudaStream_t stream);
+                        int B, int N, cudaStream_t stream);
 
 }  // namespace mmb

@@ -39,7 +39,7 @@ for case in (() if args.only else ("mbm_n128", "mbm_c1", "mbm_odd")):
     st = lambda: HybridState(None, torch.from_numpy(z["x0"]), torch.from_numpy(z["k0"]).long(), torch.from_numpy(z["mask"]).long())
     u = torch.from_numpy(z["u_jump"])
     a = model.simulate_dynamics(st(), None, uniforms=u, precision="fp32")
-    for prec in ("bf16", "f16", "bf16_mma"):
+    for prec in ("bf16", "f16"):
         try:
             b = model.simulate_dynamics(st(), None, uniforms=u, precision=prec)
         except Exception as exc:
@@ -84,7 +84,7 @@ def timed(prec, x0, k0, m0):
 
 
 ref = None
-for prec in ((args.only,) if args.only else ("fp32", "bf16", "f16", "bf16_mma")):
+for prec in ((args.only,) if args.only else ("fp32", "bf16", "f16")):
     try:
         ms, res = timed(prec, x0, k0, m0)
     except Exception as exc:
@@ -101,7 +101,7 @@ if args.dense:
     md = torch.ones_like(m0)
     xd = torch.randn(B, 128, 3, device=dev)
     kd = torch.randint(0, 8, (B, 128), device=dev, dtype=torch.uint8)
-    for prec in ("bf16", "f16", "bf16_mma"):
+    for prec in ("bf16", "f16"):
         ms, _ = timed(prec, xd, kd, md)
         print(f"dense B={B} {prec}: {ms:.3f} ms -> {B / ms * 1e3 / 1e6:.3f} M jets/s")
         out[f"dense/{prec}"] = {"ms": ms, "jets_per_s": B / ms * 1e3}
