@@ -42,13 +42,17 @@
 namespace mmb {
 namespace {
 
+#ifndef MMB_MMA_WARPS
+#define MMB_MMA_WARPS 8      // measured at C2 / dense: 8 warps x 2 CTAs per SM 4.07 / 1.98 M jets/s, 16 x 1: 3.93 / 1.73
+#endif
 #ifndef MMB_MMA_MINB
 #define MMB_MMA_MINB 2
 #endif
 constexpr int kH = 16;          // hidden width this engine is built for
-constexpr int kW = 8;           // warps per CTA
+constexpr int kW = MMB_MMA_WARPS;   // warps per CTA; the grid is persistent: MMB_MMA_MINB CTAs per SM
 constexpr int kRowsPerWarp = 64;
 constexpr int kMaxCls = 4;      // a jet spans at most this many warps (N <= 256)
+constexpr int kKeys = 4 * kMaxCls;   // work lists: key = 4 (cls - 1) + (m-tiles of the jet's last warp - 1)
 constexpr int kMaxL = 4;
 constexpr int kStageBytes = 3072;   // per warp: A tile [64 rows][48 B]  /  logits [64][8] f32 + velocity [64][4] f32
 constexpr int kSkipBytes = 4096;    // per warp: fp32 skip connection, [8][32 lanes] float4
@@ -156,8 +160,9 @@ struct MmaParams {
     uint64_t seed, jet_offset;
     int B, N;
     const float4* tvec;      // [n_steps][2 + 2L][8] bias quads of the per-step time vectors (prologue kernel)
-    const int32_t* counts;   // [1 + kMaxCls]: jets per class (class = warps the jet spans; 0 = empty jet)
-    const int32_t* lists;    // [kMaxCls][B]: jets of class c at row c - 1
+    const int32_t* counts;   // [kKeys]: jets per key (empty jets are finished by the prologue and appear in no list)
+    int32_t* cursors;        // [kMaxCls]: next unclaimed jet of each class (teams of `cls` warps claim jets dynamically)
+    const int32_t* lists;    // [kKeys][B]: jets of each key
     const int32_t* jet_cnt;  // [B] live particles
 };
 
@@ -180,27 +185,6 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
     const int g = lane >> 2, t = lane & 3;
     const int L = p.L;
 
-    // ---- CTA -> (class, jets).  CTAs are ordered by class, widest jets first; q = kW / class jets per CTA.
-    int cls = 0, first = 0, n_here = 0;
-    {
-        int b = blockIdx.x;
-#pragma unroll
-        for (int c = kMaxCls; c >= 1; --c) {
-            const int n_c = __ldg(p.counts + c);
-            const int q = kW / c;
-            const int ncta = (n_c + q - 1) / q;
-            if (cls == 0) {
-                if (b < ncta) {
-                    cls = c;
-                    first = b * q;
-                    n_here = min(q, n_c - first);
-                } else {
-                    b -= ncta;
-                }
-            }
-        }
-        if (cls == 0) return;   // past the last CTA of work (the grid is sized for the worst case)
-    }
     // ---- carve shared memory: image | per-warp staging tiles | per-warp skip buffers | pooling exchange
     const size_t image_bytes = LY::image_bytes(L);
     const uint2* tiles_lane = reinterpret_cast<const uint2*>(smem) + lane;                       // tile i of this lane: tiles_lane[32 i]
@@ -217,24 +201,25 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
     }
     __syncthreads();
 
-    const int js = warp / cls, slice = warp - js * cls;   // jet slot of this warp, its 64-row slice of the jet
-    if (js >= n_here) return;                             // idle warp slot (class does not divide kW, or the last CTA of a class)
-    const int jet = __ldg(p.lists + (size_t)(cls - 1) * p.B + first + js);
+    __shared__ int s_claim[kW];
     const int N = p.N;
+    const bool skip_on = p.skip != 0;
+    auto tile = [&](int idx) { return tiles_lane[idx * 32]; };
+    auto quad = [&](int vec, int j) { return quads_t[8 * vec + 4 * j]; };
+
+    // One jet (or this warp's 64-row slice of it) through all solver steps.  `team` = index of the group of `cls` consecutive
+    // warps that carries the jet: named barrier 1 + team, exchange buffers of the team's first warp onwards.
+    auto process = [&](const int jet, const int cls, const int slice, const int team) {
     // the two particles this lane OWNS (state, update): rows lane and lane + 32 of the warp's slice
     const int n0 = kRowsPerWarp * slice + lane, n1 = n0 + 32;
     const size_t jbase = (size_t)jet * N;
     const bool live0 = n0 < N && p.mask[jbase + n0] != 0, live1 = n1 < N && p.mask[jbase + n1] != 0;
     const unsigned bal0 = __ballot_sync(0xffffffffu, live0), bal1 = __ballot_sync(0xffffffffu, live1);
     const float inv_cnt = 1.0f / (float)__ldg(p.jet_cnt + jet);
-    const int bar_id = 1 + js, bar_threads = 32 * cls;
+    const int bar_id = 1 + team, bar_threads = 32 * cls;
     float* pool_mine = pool_all + warp * kPoolFloats;
-    const float* pool_jet = pool_all + (js * cls) * kPoolFloats;
+    const float* pool_jet = pool_all + (team * cls) * kPoolFloats;
     const uint64_t jet_key = p.jet_offset + (uint64_t)jet;
-    const bool skip_on = p.skip != 0;
-
-    auto tile = [&](int idx) { return tiles_lane[idx * 32]; };
-    auto quad = [&](int vec, int j) { return quads_t[8 * vec + 4 * j]; };
 
     auto run = [&](auto nmt_tag) {
         constexpr int NMT = decltype(nmt_tag)::value;
@@ -466,8 +451,8 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
             {
                 const uint2* tt = tiles_lane + (LY::t_layer0 + L * LY::layer_tiles) * 32;
                 const float4* qt = quads_t + 8 * (LY::v_layer0 + L * LY::layer_vecs);
-                const float4 bz = qt[0], bv = qt[4], b2 = qt[8];
-                const uint2 wz = tt[0], wv = tt[32], w2 = tt[64];
+                [[maybe_unused]] const float4 bz = qt[0], bv = qt[4], b2 = qt[8];
+                [[maybe_unused]] const uint2 wz = tt[0], wv = tt[32], w2 = tt[64];
                 float* slog = reinterpret_cast<float*>(stage);
                 float* sv = reinterpret_cast<float*>(stage + 2048);
 #pragma unroll
@@ -555,14 +540,49 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
     else if (bal1 != 0u) run(std::integral_constant<int, 3>{});
     else if ((bal0 >> 16) != 0u) run(std::integral_constant<int, 2>{});
     else run(std::integral_constant<int, 1>{});
+    };
+
+    // ---- persistent scheduling.  Jets wait in lists keyed by (warps they span, m-tiles of their last warp), widest first.
+    // A team of `cls` consecutive warps claims the next jet of its class with one atomic; single-warp jets (the bulk) are
+    // claimed warp by warp.  Claiming in list order means (a) the longest jobs start first (LPT: no tail), (b) at any moment
+    // the warps of the whole chip work on neighbours in the list, i.e. run the SAME copy of the step loop — the four copies
+    // together do not fit the instruction cache, one of them does.
+    for (int cls = kMaxCls; cls >= 1; --cls) {
+        int n_cls = 0, nk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { nk[i] = __ldg(p.counts + 4 * (cls - 1) + i); n_cls += nk[i]; }
+        if (n_cls == 0) continue;
+        const int team = warp / cls, slice = warp - team * cls;
+        if ((team + 1) * cls > kW) continue;           // warps left over when cls does not divide kW sit this class out
+        for (;;) {
+            int idx = 0;
+            if (slice == 0) {
+                if (lane == 0) idx = atomicAdd(p.cursors + (cls - 1), 1);
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                if (cls > 1 && lane == 0) s_claim[team * cls] = idx;
+            }
+            if (cls > 1) {
+                jet_bar(1 + team, 32 * cls);
+                idx = s_claim[team * cls];
+                jet_bar(1 + team, 32 * cls);             // everyone has read the claim before the leader overwrites it
+            }
+            if (idx >= n_cls) break;
+            int key = 4 * (cls - 1) + 3;                 // widest last warp first
+#pragma unroll
+            for (int i = 3; i >= 1; --i)
+                if (idx >= nk[i] && key == 4 * (cls - 1) + i) { idx -= nk[i]; --key; }
+            const int jet = __ldg(p.lists + (size_t)key * p.B + idx);
+            process(jet, cls, slice, team);
+        }
+    }
 }
 
 // ---- prologue: per-step time vectors + binning of the jets by the number of warps they span ---------------------------------------------
 // blocks [0, n_steps): vectors of one step, from the fp32 weights (same for every jet), written as C-operand quads:
 //   v0 = local_0 bias + W0[:, T:T+C] a + W0[:, :T] temb      (a = bias of the continuous embedding)
 //   v1 = global_0 bias + G0[:, 2H:] temb;  per layer: fc_global1 bias + time part, fc_local1 bias + time part
-// blocks [n_steps, ...): one thread per jet: live count, last live index -> class; jets of a class are appended to its list
-// (order irrelevant: a jet's result does not depend on where it runs).  Empty jets get the reference's result right here:
+// blocks [n_steps, ...): one thread per jet: live count, last live index -> key (warps spanned, m-tiles of the last warp); jets
+// of a key are appended to its list (order irrelevant: a jet's result does not depend on where or when it runs).  Empty jets get the reference's result right here:
 // the mean pool divides by zero (epic.py:141), every feature becomes NaN, tokens are multiplied by the mask -> 0.
 constexpr int kPrologueThreads = 256;
 __global__ void __launch_bounds__(kPrologueThreads) mma_prologue_kernel(const float* __restrict__ W, MmbEpicLayout Lo, MmbEpicDims d,
@@ -602,11 +622,11 @@ __global__ void __launch_bounds__(kPrologueThreads) mma_prologue_kernel(const fl
         }
         return;
     }
-    __shared__ int s_cnt[1 + kMaxCls], s_base[1 + kMaxCls];
-    if (threadIdx.x <= kMaxCls) s_cnt[threadIdx.x] = 0;
+    __shared__ int s_cnt[kKeys], s_base[kKeys];
+    if (threadIdx.x < kKeys) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int jet = ((int)blockIdx.x - n_steps) * kPrologueThreads + threadIdx.x;
-    int cls = -1, pos = 0;
+    int cls = -1, key = 0, pos = 0;
     if (jet < B) {
         const uint8_t* row = mask + (size_t)jet * N;
         int cnt = 0, last = 0;
@@ -626,12 +646,15 @@ __global__ void __launch_bounds__(kPrologueThreads) mma_prologue_kernel(const fl
         }
         jet_cnt[jet] = cnt;
         cls = (last + kRowsPerWarp - 1) / kRowsPerWarp;
-        pos = atomicAdd(&s_cnt[cls], 1);
+        if (cls > 0) {
+            key = 4 * (cls - 1) + (last - kRowsPerWarp * (cls - 1) + 15) / 16 - 1;   // m-tiles of the jet's last warp
+            pos = atomicAdd(&s_cnt[key], 1);
+        }
     }
     __syncthreads();
-    if (threadIdx.x <= kMaxCls) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]) : 0;
+    if (threadIdx.x < kKeys) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]) : 0;
     __syncthreads();
-    if (cls > 0) lists[(size_t)(cls - 1) * B + s_base[cls] + pos] = jet;
+    if (cls > 0) lists[(size_t)key * B + s_base[key] + pos] = jet;
     if (cls == 0) {
         const float nan = __int_as_float(0x7fc00000);
         for (int i = 0; i < N * d.dim_continuous; ++i) x[(size_t)jet * N * d.dim_continuous + i] = nan;
@@ -797,10 +820,10 @@ int mma_build_images(EpicModel* m, const float* packed_host) {
                    : build_image_gt<2>(m->dims, m->layout, packed_host, &m->mma_image_f16, &m->mma_image_f16_bytes);
 }
 
-// scratch (4-byte units): time-vector quads [n_steps][2 + 2L][8] float4 | counts [16] | jet_cnt [B] | lists [kMaxCls][B]
+// scratch (4-byte units): time-vector quads [n_steps][2 + 2L][8] float4 | counts [16] | cursors [16] | jet_cnt [B] | lists [kKeys][B]
 static size_t tvec_floats(const MmbEpicDims* d, int n_steps) { return (size_t)n_steps * (2 + 2 * d->num_blocks) * 32; }
 size_t mma_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B) {
-    return tvec_floats(d, n_steps) + 16 + (size_t)(B > 0 ? B : 0) * (1 + kMaxCls) + 16;
+    return tvec_floats(d, n_steps) + 32 + (size_t)(B > 0 ? B : 0) * (1 + kKeys) + 16;
 }
 
 int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
@@ -817,19 +840,19 @@ int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t*
     p.n_steps = n_steps; p.dt = dt; p.u_jump = u_jump; p.seed = seed; p.jet_offset = jet_offset;
     p.B = B; p.N = N;
     int32_t* counts = reinterpret_cast<int32_t*>(scratch + tvec_floats(&m->dims, n_steps));
-    int32_t* jet_cnt = counts + 16;
+    int32_t* cursors = counts + 16;
+    int32_t* jet_cnt = counts + 32;
     int32_t* lists = jet_cnt + B;
-    if (int rc = cuda_ok(cudaMemsetAsync(counts, 0, 16 * sizeof(int32_t), stream), "mma counters")) return rc;
+    if (int rc = cuda_ok(cudaMemsetAsync(counts, 0, 32 * sizeof(int32_t), stream), "mma counters")) return rc;
     const int bin_blocks = (B + kPrologueThreads - 1) / kPrologueThreads;
     mma_prologue_kernel<<<n_steps + bin_blocks, kPrologueThreads, 0, stream>>>(m->w, m->layout, m->dims, dev_table + (size_t)n_steps * 4, n_steps,
                                                                                 reinterpret_cast<float4*>(scratch), mask, B, N, counts, lists,
                                                                                 jet_cnt, x, k);
     if (int rc = cuda_ok(cudaGetLastError(), "mma prologue launch")) return rc;
-    p.tvec = reinterpret_cast<const float4*>(scratch); p.counts = counts; p.lists = lists; p.jet_cnt = jet_cnt;
-    // worst-case number of CTAs: every class rounds up once, the widest class of this N packs the fewest jets per CTA
-    const int ncls = (N + kRowsPerWarp - 1) / kRowsPerWarp;
-    const int q_min = kW / ncls > 0 ? kW / ncls : 1;
-    const int grid = (B + q_min - 1) / q_min + ncls;
+    p.tvec = reinterpret_cast<const float4*>(scratch); p.counts = counts; p.cursors = cursors; p.lists = lists; p.jet_cnt = jet_cnt;
+    // persistent grid: MMB_MMA_MINB CTAs per SM, never more warps than there could be work for
+    const int want = (B + kW - 1) / kW * ((N + kRowsPerWarp - 1) / kRowsPerWarp);
+    const int grid = want < m->sm_count * MMB_MMA_MINB ? want : m->sm_count * MMB_MMA_MINB;
     return dispatch(m->dims, p, grid, stream);
 }
 
