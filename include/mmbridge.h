@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MMB_ABI_VERSION 1
+#define MMB_ABI_VERSION 2
 
 enum {
     MMB_OK = 0,
@@ -222,16 +222,36 @@ int mmb_bridge_update(float* x, uint8_t* k, uint8_t* mask,
  * (mbm.py:199-216) minus the final .cpu().
  *   u_jump: [n_steps,B,N] pre-drawn uniforms, or NULL to draw in-kernel with Philox4x32-10 keyed by
  *   (seed, jet_offset + jet, step, particle) — results are then invariant to how jets are sharded.
- *   workspace: mmb_generate_workspace_bytes(m, B, N, precision) bytes of device memory (step table image, per-step
- *   time vectors, and the jet lists of the tensor-core path, which bins the jets of a call on the device: jets without a
- *   live particle at index >= 64 share a 128-row tile in pairs.  Where a jet runs depends on the jet alone, so results
- *   do not depend on the size or composition of the call either).
+ *   workspace: mmb_generate_workspace_bytes(m, B, N, precision) bytes of 16-byte aligned device memory (per-step time
+ *   vectors and the jet lists of the tensor-core engines, which bin the jets of a call on the device — MMB_PREC_BF16: jets
+ *   without a live particle at index >= 64 share a 128-row tile in pairs; MMB_PREC_F16: jets are claimed by warps in order of
+ *   their width.  Where and when a jet runs depends on the jet alone, so results do not depend on the size or composition
+ *   of the call either).  The device image of the step table is cached on the model handle: a call with a table the handle
+ *   has seen neither copies nor allocates.
+ *   An empty jet (mask all zero) ends with NaN features and zero tokens in every precision, as the reference's division by
+ *   the particle count gives (epic.py:141, bridges.py:42).
  */
 size_t mmb_generate_workspace_bytes(const MmbEpicModel* m, int B, int N, int precision);
+
+/*
+ * 1 if mmb_generate can run this model at N particles per jet in `precision`, else 0 (MMB_PREC_FP32 takes any shape; the
+ * tensor-core engines are built for the default EPiC widths: hidden 16, G <= 32, Dc = 3, S in {4, 8}, head width 0 or S;
+ * MMB_PREC_BF16: N <= 128, MMB_PREC_F16: N <= 256).  The host shim's precision "auto" asks in the order F16, BF16, FP32.
+ */
+int mmb_generate_supported(const MmbEpicModel* m, int N, int precision);
 int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mask,
                  const MmbStepTable* steps, const float* u_jump,
                  uint64_t seed, uint64_t jet_offset, int B, int N,
                  void* workspace, size_t workspace_bytes, int precision, void* stream);
+
+/*
+ * Diagnostics: the jump rule (TelegraphBridge.solver_step, bridges.py:179-201, as the one-uniform categorical) evaluated by
+ * its three device implementations on IDENTICAL inputs — the exact rule of MMB_PREC_FP32 / mmb_bridge_update (bit-identical to
+ * the oracle) and the fast-intrinsic variants inside the MMB_PREC_BF16 and MMB_PREC_F16 generation kernels.
+ *   logits [P,S] f32, k [P] u8, u [P] f32 -> new tokens out_exact / out_tc / out_mma [P] u8 (unmasked).  S in {4, 8}.
+ */
+int mmb_jump_variants(const float* logits, const uint8_t* k, const float* u, float dt, float bc, float cc, size_t P, int S,
+                      uint8_t* out_exact, uint8_t* out_tc, uint8_t* out_mma, void* stream);
 
 /* uniforms exactly as the in-kernel generator draws them, written to u [n_steps,B,N] (for tests) */
 int mmb_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, void* stream);

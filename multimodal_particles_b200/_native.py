@@ -91,7 +91,9 @@ SIGNATURES = {
     "mmb_epic_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "mmb_bridge_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _i, _i, _vp]),
     "mmb_generate_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "mmb_generate_supported": (_i, [_vp, _i, _i]),
     "mmb_generate": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
+    "mmb_jump_variants": (_i, [_vp, _vp, _vp, _f, _f, _f, _sz, _i, _vp, _vp, _vp, _vp]),
     "mmb_philox_uniforms": (_i, [_vp, _u64, _u64, _i, _i, _i, _vp]),
     "mmb_absorb_head_create": (_i, [_i, _i, _i, _i, _vp, _sz, _i, ctypes.POINTER(_vp)]),
     "mmb_absorb_head_destroy": (None, [_vp]),
@@ -189,12 +191,23 @@ class EpicModel:
                                           _ptr(v), _ptr(logits), _ptr(hidden), PRECISIONS[precision], _stream()))
         return (v, logits, hidden) if want_hidden else (v, logits)
 
-    def generate(self, x, k_u8, mask_u8, table, u_jump=None, seed=0, jet_offset=0, precision="bf16"):
+    def generate_precision(self, N, precision="auto"):
+        """Resolve "auto" to the fastest engine that takes this model at N particles per jet: warp-MMA fp16, tcgen05 bf16,
+        CUDA-core fp32 (any shape)."""
+        if precision != "auto":
+            return precision
+        lib = load()
+        for name in ("f16", "bf16", "fp32"):
+            if lib.mmb_generate_supported(self._handle, N, PRECISIONS[name]):
+                return name
+        return "fp32"
+
+    def generate(self, x, k_u8, mask_u8, table, u_jump=None, seed=0, jet_offset=0, precision="auto"):
         """In-place generation of x/k over all steps of ``table`` (StepTable)."""
         _require_cuda(x, k_u8, mask_u8, u_jump)
         B, N, _ = x.shape
         lib = load()
-        prec = PRECISIONS[precision]
+        prec = PRECISIONS[self.generate_precision(N, precision)]
         need = lib.mmb_generate_workspace_bytes(self._handle, B, N, prec)
         ws = torch.empty(max(need, 16), device=x.device, dtype=torch.uint8)
         ctable = CStepTable.from_table(table)
@@ -213,6 +226,17 @@ def bridge_update(x, k_u8, mask_u8, v, logits, u_jump, dt, bc, cc, absorb_logit=
     with torch.cuda.device(x.device):
         check(load().mmb_bridge_update(_ptr(x), _ptr(k_u8), _ptr(mask_u8), _ptr(v), _ptr(logits), _ptr(absorb_logit),
                                        _ptr(u_jump), _ptr(u_absorb), dt, bc, cc, sp, B, N, Dc, S, flags, _stream()))
+
+
+def jump_variants(logits, k_u8, u, dt, bc, cc):
+    """Tokens chosen by the exact jump rule and by the fast variants of the tcgen05 / warp-MMA engines on identical inputs:
+    logits [P,S] f32, k [P] u8, u [P] f32 (device) -> (exact, tc, mma) [P] u8."""
+    _require_cuda(logits, k_u8, u)
+    P, S = logits.shape
+    outs = [torch.empty(P, dtype=torch.uint8, device=logits.device) for _ in range(3)]
+    with torch.cuda.device(logits.device):
+        check(load().mmb_jump_variants(_ptr(logits), _ptr(k_u8), _ptr(u), dt, bc, cc, P, S, *[_ptr(o) for o in outs], _stream()))
+    return outs
 
 
 def philox_uniforms(seed, jet_offset, n_steps, B, N, device):

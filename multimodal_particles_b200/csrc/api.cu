@@ -233,6 +233,15 @@ size_t mmb_generate_workspace_bytes(const MmbEpicModel* handle, int B, int N, in
     return (a > b ? a : b) * sizeof(float);
 }
 
+int mmb_generate_supported(const MmbEpicModel* handle, int N, int precision) {
+    const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
+    if (!m || N < 1) return 0;
+    if (precision == MMB_PREC_FP32) return 1;
+    if (precision == MMB_PREC_BF16) return m->tc_image && tc_supported(&m->dims, N) && (m->dims.disc_head_hidden == 0 || m->dims.disc_head_hidden == m->dims.vocab_size);
+    if (precision == MMB_PREC_F16) return m->mma_image_f16 && mma_supported(&m->dims, N);
+    return 0;
+}
+
 int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t* mask,
                  const MmbStepTable* st, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                  int B, int N, void* workspace, size_t workspace_bytes, int precision, void* stream) {
@@ -272,6 +281,12 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
 int mmb_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, void* stream) {
     if (!u || n_steps < 0 || B < 0 || N < 0) return fail(MMB_EINVAL, "mmb_philox_uniforms: bad argument");
     return launch_philox_uniforms(u, seed, jet_offset, 0, 0, n_steps, B, N, static_cast<cudaStream_t>(stream));
+}
+
+int mmb_jump_variants(const float* logits, const uint8_t* k, const float* u, float dt, float bc, float cc, size_t P, int S,
+                      uint8_t* out_exact, uint8_t* out_tc, uint8_t* out_mma, void* stream) {
+    if (!logits || !k || !u || !out_exact || !out_tc || !out_mma) return fail(MMB_EINVAL, "mmb_jump_variants: null argument");
+    return launch_jump_variants(logits, k, u, StepScalars{dt, bc, cc, 0.0f}, P, S, out_exact, out_tc, out_mma, static_cast<cudaStream_t>(stream));
 }
 
 int mmb_absorb_head_create(int hidden, int transformer_dim, int n_heads, int n_blocks, const float* packed, size_t n_floats,

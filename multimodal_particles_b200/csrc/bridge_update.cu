@@ -214,4 +214,32 @@ int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int str
     return cuda_ok(cudaGetLastError(), "philox_uniforms launch");
 }
 
+// ---- the three implementations of the jump rule on IDENTICAL logits and uniforms (tests) ----------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) jump_variants_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ k,
+                                                            const float* __restrict__ u, StepScalars sc, size_t P,
+                                                            uint8_t* __restrict__ out_exact, uint8_t* __restrict__ out_tc,
+                                                            uint8_t* __restrict__ out_mma) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+        float lg[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) lg[s] = __ldg(logits + i * S + s);
+        const int kk = k[i];
+        const float uu = __ldg(u + i);
+        out_exact[i] = (uint8_t)telegraph_jump<S>(lg, kk, uu, sc);
+        out_tc[i] = (uint8_t)telegraph_jump_fast<S>(lg, kk, uu, sc);
+        out_mma[i] = (uint8_t)telegraph_jump_fast_ex2<S>(lg, kk, uu, sc.dt, sc.bc, sc.cc);
+    }
+}
+
+int launch_jump_variants(const float* logits, const uint8_t* k, const float* u, StepScalars sc, size_t P, int S, uint8_t* out_exact,
+                         uint8_t* out_tc, uint8_t* out_mma, cudaStream_t stream) {
+    if (P == 0) return MMB_OK;
+    const unsigned grid = (unsigned)((P + 255) / 256 < 148 * 16 ? (P + 255) / 256 : 148 * 16);
+    if (S == 8) jump_variants_kernel<8><<<grid, 256, 0, stream>>>(logits, k, u, sc, P, out_exact, out_tc, out_mma);
+    else if (S == 4) jump_variants_kernel<4><<<grid, 256, 0, stream>>>(logits, k, u, sc, P, out_exact, out_tc, out_mma);
+    else return fail(MMB_EINVAL, "mmb_jump_variants: S must be 4 or 8 (the shapes the tensor-core engines are built for)");
+    return cuda_ok(cudaGetLastError(), "jump_variants launch");
+}
+
 }  // namespace mmb

@@ -104,47 +104,11 @@ __device__ __forceinline__ void lrelu4(float (&c)[4]) {
     fmul2(t2, t3, c[2], c[3], 0.01f, 0.01f);
     c[0] = fmaxf(c[0], t0); c[1] = fmaxf(c[1], t1); c[2] = fmaxf(c[2], t2); c[3] = fmaxf(c[3], t3);
 }
-__device__ __forceinline__ float ex2_fast(float a) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-    return r;
-}
 __device__ __forceinline__ float selu_f(float a) {   // branch-free
     const float scale = 1.0507009873554804934193349852946f;
     const float alpha_scale = 1.0507009873554804934193349852946f * 1.6732632423543772848170429916717f;
     const float neg = fmaf(alpha_scale, ex2_fast(a * 1.4426950408889634f), -alpha_scale);
     return a > 0.0f ? scale * a : neg;
-}
-
-// The categorical jump of the tensor-core engines: the Form B rule of mmb::telegraph_jump with fast
-// intrinsics; Lambda in closed form (sum of softmax = 1).  tests/test_gpu_jump.py bounds its disagreements with the exact rule.
-template <int S>
-__device__ __forceinline__ int jump_fast(const float (&lg)[S], int k, float u, float dt, float bc, float cc) {
-    constexpr float kLog2e = 1.4426950408889634f;
-    float mx = lg[0];
-#pragma unroll
-    for (int s = 1; s < S; ++s) mx = fmaxf(mx, lg[s]);
-    const float nmx = -mx * kLog2e;
-    float e[S], z = 0.0f, ek = 0.0f;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        e[s] = ex2_fast(fmaf(lg[s], kLog2e, nmx));
-        z += e[s];
-        ek = (k == s) ? e[s] : ek;
-    }
-    const float zinv = __fdividef(1.0f, z);
-    const float base = fmaf(cc * ek, zinv, 1.0f) * dt, slope = bc * zinv * dt;
-    const float Lam = fmaf((float)S, base, bc * dt);           // sum_s (base + slope e_s) = S base + slope z
-    const float E = ex2_fast(-Lam * kLog2e);
-    const float bE = base * E, sE = slope * E;
-    float c = 0.0f;
-    int below = 0;   // number of thresholds c_s <= u  ==  index of the first s with u < c_s
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        c += fmaf(e[s], sE, bE);
-        below += (u >= c) ? 1 : 0;
-    }
-    return below < S ? below : k;
 }
 
 struct MmaParams {
@@ -512,7 +476,7 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
                     }
                     xs[0] = fmaf(p.dt, v4.x, xs[0]); xs[1] = fmaf(p.dt, v4.y, xs[1]); xs[2] = fmaf(p.dt, v4.z, xs[2]);
                     const float u = p.u_jump ? __ldg(p.u_jump + ((size_t)step * p.B + jet) * N + n) : u01(ubits);
-                    kk = jump_fast<S>(lg, kk, u, p.dt, bc, cc);
+                    kk = telegraph_jump_fast_ex2<S>(lg, kk, u, p.dt, bc, cc);
                 };
                 update(lane, n0, xs0, kk0, live0, ph == 0 ? uq[0] : ph == 1 ? uq[1] : ph == 2 ? uq[2] : uq[3]);
                 if constexpr (TWO) update(lane + 32, n1, xs1, kk1, live1, ph == 0 ? uq[4] : ph == 1 ? uq[5] : ph == 2 ? uq[6] : uq[7]);

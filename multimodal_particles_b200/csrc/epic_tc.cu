@@ -259,40 +259,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Telegraph jump of the bf16 mode: same categorical (Form B) as mmb::telegraph_jump, evaluated with
-// fast intrinsics and without branches — the logits already carry bf16 rounding, so the exact-exp
-// contract of the fp32 path buys nothing here.
-template <int S>
-__device__ __forceinline__ int telegraph_jump_fast(const float (&lg)[S], int k, float u, const StepScalars& sc) {
-    float mx = lg[0];
-#pragma unroll
-    for (int s = 1; s < S; ++s) mx = fmaxf(mx, lg[s]);
-    float e[S], z = 0.0f, ek = 0.0f;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        e[s] = __expf(lg[s] - mx);
-        z += e[s];
-        ek = (k == s) ? e[s] : ek;
-    }
-    const float zinv = __fdividef(1.0f, z);
-    const float base = (1.0f + sc.cc * ek * zinv) * sc.dt, slope = sc.bc * zinv * sc.dt;
-    float lam[S], Lam = 0.0f;
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        lam[s] = fmaf(e[s], slope, base);
-        Lam += lam[s];
-    }
-    const float E = __expf(-Lam);
-    float c = 0.0f;
-    int below = 0;  // number of thresholds c_s <= u  ==  index of the first s with u < c_s
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        c = fmaf(lam[s], E, c);
-        below += (u >= c) ? 1 : 0;
-    }
-    return below < S ? below : k;
-}
-
 __device__ __forceinline__ float lrelu_fast(float a) { return fmaxf(a, 0.01f * a); }
 // init + sum_{k<K} w[k * wstride] * x(k) with four independent accumulators: the serial per-jet global MLP is a chain of such
 // dots on one warp, and a single accumulator makes every one of them K dependent FMAs long
@@ -530,7 +496,9 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
             }
         }
         group_bar(1 + grp);
-        const float inv_cnt = 1.0f / (float)(paired ? jv.cnt[0] + jv.cnt[1] : jv.cnt[0] + jv.cnt[1] + jv.cnt[2] + jv.cnt[3]);
+        const int jet_cnt = paired ? jv.cnt[0] + jv.cnt[1] : jv.cnt[0] + jv.cnt[1] + jv.cnt[2] + jv.cnt[3];
+        const float inv_cnt = 1.0f / (float)jet_cnt;
+        const bool jet_empty = GENERATE && jet_cnt == 0;
         // K-steps of the pooling GEMM (16 particles each) that hold a live particle; the others would add zeros
         const uint32_t pool_live = __shfl_sync(0xffffffffu, GENERATE ? (jv0.live16[0] | (jv0.live16[1] << 2) | (jv0.live16[2] << 4) | (jv0.live16[3] << 6)) : 0xffu, 0);
 
@@ -881,12 +849,15 @@ __global__ void __launch_bounds__(kJPC * 128, 2) epic_tc_kernel(const TcParams p
         if constexpr (GENERATE) {
             if (valid) {
                 const size_t pout = (size_t)jet * p.N + n;
+                // an empty jet ends as in the reference: mean pool 0/0 (epic.py:141) -> NaN velocity -> (x + dt NaN) * 0 = NaN
+                // for every particle (bridges.py:42); tokens are integers times the mask = 0
+                const float dead_x = jet_empty ? __int_as_float(0x7fc00000) : 0.0f;
 #pragma unroll
-                for (int c = 0; c < DC; ++c) p.x[pout * DC + c] = xs[c];
+                for (int c = 0; c < DC; ++c) p.x[pout * DC + c] = jet_empty ? dead_x : xs[c];
                 p.k[pout] = (uint8_t)kk;
                 if (paired && n + 64 < p.N) {   // a small jet's particles 64.. are dead and have no row in a paired tile: final state 0
 #pragma unroll
-                    for (int c = 0; c < DC; ++c) p.x[(pout + 64) * DC + c] = 0.0f;
+                    for (int c = 0; c < DC; ++c) p.x[(pout + 64) * DC + c] = dead_x;
                     p.k[pout + 64] = 0;
                 }
             }

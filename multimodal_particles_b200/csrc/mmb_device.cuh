@@ -167,6 +167,82 @@ __device__ __forceinline__ int telegraph_jump_rt(const float* lg, int S, int k, 
     return k;
 }
 
+
+// ---- the jump rule of the tensor-core engines -----------------------------------------------------------------------------
+// Same categorical (Form B) as telegraph_jump above, evaluated with fast intrinsics and without branches: the logits of those
+// engines already carry 16-bit operand rounding, so the exact-exp contract of the fp32 path buys nothing there.  Given
+// IDENTICAL logits the variants can disagree with the exact rule only when the uniform lies within rounding of a threshold;
+// tests/test_gpu_jump.py feeds all three the same 5*10^7 draws and lists every disagreement with its distance to the threshold.
+__device__ __forceinline__ float ex2_fast(float a) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+}
+
+// tcgen05 engine (epic_tc.cu)
+template <int S>
+__device__ __forceinline__ int telegraph_jump_fast(const float (&lg)[S], int k, float u, const StepScalars& sc) {
+    float mx = lg[0];
+#pragma unroll
+    for (int s = 1; s < S; ++s) mx = fmaxf(mx, lg[s]);
+    float e[S], z = 0.0f, ek = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        e[s] = __expf(lg[s] - mx);
+        z += e[s];
+        ek = (k == s) ? e[s] : ek;
+    }
+    const float zinv = __fdividef(1.0f, z);
+    const float base = (1.0f + sc.cc * ek * zinv) * sc.dt, slope = sc.bc * zinv * sc.dt;
+    float lam[S], Lam = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        lam[s] = fmaf(e[s], slope, base);
+        Lam += lam[s];
+    }
+    const float E = __expf(-Lam);
+    float c = 0.0f;
+    int below = 0;  // number of thresholds c_s <= u  ==  index of the first s with u < c_s
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        c = fmaf(lam[s], E, c);
+        below += (u >= c) ? 1 : 0;
+    }
+    return below < S ? below : k;
+}
+
+
+// warp-MMA engine (epic_mma.cu): exp2 with pre-scaled arguments, Lambda in closed form (the softmax sums to one)
+template <int S>
+__device__ __forceinline__ int telegraph_jump_fast_ex2(const float (&lg)[S], int k, float u, float dt, float bc, float cc) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    float mx = lg[0];
+#pragma unroll
+    for (int s = 1; s < S; ++s) mx = fmaxf(mx, lg[s]);
+    const float nmx = -mx * kLog2e;
+    float e[S], z = 0.0f, ek = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        e[s] = ex2_fast(fmaf(lg[s], kLog2e, nmx));
+        z += e[s];
+        ek = (k == s) ? e[s] : ek;
+    }
+    const float zinv = __fdividef(1.0f, z);
+    const float base = fmaf(cc * ek, zinv, 1.0f) * dt, slope = bc * zinv * dt;
+    const float Lam = fmaf((float)S, base, bc * dt);           // sum_s (base + slope e_s) = S base + slope z
+    const float E = ex2_fast(-Lam * kLog2e);
+    const float bE = base * E, sE = slope * E;
+    float c = 0.0f;
+    int below = 0;   // number of thresholds c_s <= u  ==  index of the first s with u < c_s
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        c += fmaf(e[s], sE, bE);
+        below += (u >= c) ? 1 : 0;
+    }
+    return below < S ? below : k;
+}
+
+
 __device__ __forceinline__ int absorbing_birth(int m, float a, float u, const StepScalars& sc) {
     const float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_exact(-a)));
     float p = __fmul_rn(sc.dt, __fmul_rn(sc.sp, sg));

@@ -44,6 +44,9 @@ int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, co
 int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int stream_id, int step0, int n_steps, int B, int N,
                            cudaStream_t stream);
 
+int launch_jump_variants(const float* logits, const uint8_t* k, const float* u, StepScalars sc, size_t P, int S, uint8_t* out_exact,
+                         uint8_t* out_tc, uint8_t* out_mma, cudaStream_t stream);
+
 // absorb_head_tc.cu — 128-wide transformer stack (ResnetBlock + AttnBlock) on tcgen05
 struct TfStack {
     int Cin = 0, n_blocks = 0, n_jet = 0;

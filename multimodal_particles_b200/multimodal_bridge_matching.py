@@ -89,11 +89,12 @@ def to_host_async(t: torch.Tensor) -> torch.Tensor:
 class MultiModalBridgeMatching(_ModuleBase):
     """Model for hybrid data with varying size (mbm.py:115-269), generation side.
 
-    ``precision``: "fp32" = CUDA-core trunk, bit-identical to the CPU oracle; "bf16" = tcgen05 trunk
-    (default for ``simulate_dynamics``).  ``forward`` always evaluates in fp32 unless asked.
+    ``precision`` of ``simulate_dynamics``: "fp32" = CUDA-core trunk, bit-identical to the CPU oracle; "bf16" = tcgen05
+    engine; "f16" = warp-MMA engine (fp16 operands, fp32 accumulate: the fastest and the closest to fp32); "auto" (default)
+    = the first of f16 / bf16 / fp32 that takes the model's shape.  ``forward`` always evaluates in fp32 unless asked.
     """
 
-    def __init__(self, config, precision: str = "bf16"):
+    def __init__(self, config, precision: str = "auto"):
         super().__init__()
         self.config = config
         self.vocab_size = config.data.vocab_size_features
