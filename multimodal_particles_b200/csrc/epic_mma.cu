@@ -111,6 +111,16 @@ __device__ __forceinline__ float selu_f(float a) {   // branch-free
     return a > 0.0f ? scale * a : neg;
 }
 
+// Named barrier of team `team` of class `cls` (a team = cls consecutive warps).  Warps move from class to class on their own,
+// so teams of different classes are alive at the same time and every (class, team) pair needs its own hardware barrier:
+// ids 1 .. sum_{c=2..4} kW / c, which must stay below 16.
+__host__ __device__ constexpr int team_barrier(int cls, int team) {
+    int base = 1;
+    for (int c = kMaxCls; c > cls; --c) base += kW / c;
+    return base + team;
+}
+static_assert(team_barrier(2, kW / 2 - 1) <= 15, "too many warps per CTA for one named barrier per team");
+
 struct MmaParams {
     const uint8_t* image;
     int L, skip;
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
     const bool live0 = n0 < N && p.mask[jbase + n0] != 0, live1 = n1 < N && p.mask[jbase + n1] != 0;
     const unsigned bal0 = __ballot_sync(0xffffffffu, live0), bal1 = __ballot_sync(0xffffffffu, live1);
     const float inv_cnt = 1.0f / (float)__ldg(p.jet_cnt + jet);
-    const int bar_id = 1 + team, bar_threads = 32 * cls;
+    const int bar_id = team_barrier(cls, team), bar_threads = 32 * cls;
     float* pool_mine = pool_all + warp * kPoolFloats;
     const float* pool_jet = pool_all + (team * cls) * kPoolFloats;
     const uint64_t jet_key = p.jet_offset + (uint64_t)jet;
@@ -526,9 +536,9 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
                 if (cls > 1 && lane == 0) s_claim[team * cls] = idx;
             }
             if (cls > 1) {
-                jet_bar(1 + team, 32 * cls);
+                jet_bar(team_barrier(cls, team), 32 * cls);
                 idx = s_claim[team * cls];
-                jet_bar(1 + team, 32 * cls);             // everyone has read the claim before the leader overwrites it
+                jet_bar(team_barrier(cls, team), 32 * cls);   // everyone has read the claim before the leader overwrites it
             }
             if (idx >= n_cls) break;
             int key = 4 * (cls - 1) + 3;                 // widest last warp first

@@ -135,10 +135,14 @@ def test_paired_tiles_give_the_same_jets_as_single_tiles():
 
 
 def w1(a, b):
+    """1-D Wasserstein distance between two samples: mean |Qa - Qb| over n = min(len) mid-point quantiles (linear interpolation
+    of the sorted samples; np.quantile with ~10^5 quantile points takes minutes)."""
     a, b = np.sort(np.asarray(a, np.float64)), np.sort(np.asarray(b, np.float64))
     n = min(len(a), len(b))
     q = (np.arange(n) + 0.5) / n
-    return np.abs(np.quantile(a, q) - np.quantile(b, q)).mean()
+    qa = np.interp(q * (len(a) - 1), np.arange(len(a)), a)
+    qb = np.interp(q * (len(b) - 1), np.arange(len(b)), b)
+    return np.abs(qa - qb).mean()
 
 
 def test_distributions_within_seed_to_seed_spread():
