@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — generated jets/sec of the multimodal bridge generation loop (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision bf16|fp32]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision auto|f16|bf16|fp32] [--workload c2|c3|c4|c5]
 
 A "step" = one full generation (all 99 solver steps) of one batch of synthetic jets per GPU.
 Workload (config.workload) = BASELINE.json configs[1]: EPiC multimodal bridge, JetClass-shaped
@@ -19,7 +19,11 @@ synthetic jets (128 particles, 3 continuous + 8 tokens), batch 4096 per GPU, 100
                  (75 B / particle-step) against the measured HBM copy bandwidth
   cpu_baseline   the CPU oracle (C port of the reference algorithm, OpenMP over jets) on a bounded
                  sample of the same workload, rank 0, N=1 only
+  roofline_dense the same kernel on a batch whose jets all have 128 live particles (the C2 multiplicities skip dead rows)
   --impl reference   times that CPU port alone (the reference is pure Python and does not travel)
+  --workload     c2 (default, the headline) | c3 (one transepic evaluation, B=8192) | c4 (absorbing-flow generation, B=4096) |
+                 c5 (1 M jets sharded over the GPUs: source + generation + observables + histograms + gather); with N > 1 the
+                 c2 line carries a bounded c5 leg as well (`c5_million_jets`)
 """
 import argparse
 import json
@@ -163,9 +167,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16", "bf16", "fp32"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 side measurements")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 / C5 side measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -189,10 +194,19 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     B = B_PER_GPU
+    pk = peaks()
+
+    if args.workload != "c2":
+        line = side_workload_line(args, torch, dist, _native, device, pk, rank, world, W, K)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cfg, model = build_model(device)
     native = model.encoder.native_model(device)
-    precision = args.precision or ("bf16" if native_supports_bf16(native, _native) else "fp32")
+    precision = native.generate_precision(N_PART, args.precision)
     table = model.step_table()
     n_steps = table.n_steps
     batch = source_batch(B, 1234 + rank)
@@ -229,7 +243,7 @@ def main():
             stream.wait_stream(side)
 
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:   # sampled across warm-up + timed region (the timed region alone is ~50 ms)
+    with ClockSampler(local_rank) as clocks:   # sampled across warm-up + timed region (the timed region alone is ~10-50 ms)
         for i in range(W):
             one_step(i)
         join()
@@ -263,35 +277,52 @@ def main():
     ms_total = float(t.item())
     value = world * B * K / (ms_total * 1e-3)
 
-    # ---- kernel-only timing of the dominant kernel (generation kernel alone, same stream)
-    kern_ms = []
-    for i in range(min(K, 5)):
-        xs[i].copy_(batch.source_continuous.to(device))
-        ks[i].copy_(as_u8(batch.source_discrete.to(device)))
-        flush.zero_()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(stream)
-        native.generate(xs[i], ks[i], mask, table, seed=1, jet_offset=jet_offset, precision=precision)
-        e.record(stream)
-        torch.cuda.synchronize()
-        kern_ms.append(s.elapsed_time(e))
-    kern = sum(kern_ms) / len(kern_ms)
-    pk = peaks()
+    # ---- kernel-only timing of the dominant kernel (one mmb_generate call = prologue + generation kernel, same stream)
+    def kernel_ms(x_src, k_src, m_dev, reps):
+        out = []
+        for i in range(reps):
+            xs[i].copy_(x_src)
+            ks[i].copy_(k_src)
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(stream)
+            native.generate(xs[i], ks[i], m_dev, table, seed=1, jet_offset=jet_offset, precision=precision)
+            e.record(stream)
+            torch.cuda.synchronize()
+            out.append(s.elapsed_time(e))
+        return sum(out) / len(out)
+
+    kern = kernel_ms(batch.source_continuous.to(device), as_u8(batch.source_discrete.to(device)), mask, min(K, 5))
     flops = FLOP_PER_JET_STEP * B * n_steps
     achieved_tf = flops / (kern * 1e-3) / 1e12
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01_bench_launches.md):
+    kernel_name = {"f16": "mmb::epic_mma_generate_kernel<3,8,8,1> (warp-level mma.sync m16n8k16, fp16 operands, fp32 accumulate)",
+                   "bf16": "mmb::epic_tc_kernel<3,8,8,GENERATE> (tcgen05, bf16 operands, fp32 accumulate)",
+                   "fp32": "mmb::generate_fp32_kernel (CUDA cores)"}[precision]
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch from `ncu --set full` (not measurable inside this run):
     # the state lives in registers for all 99 steps, HBM only sees the source state (the result stays in L2 until evicted)
-    traffic = 3.8e6 if (precision == "bf16" and B == 4096) else None
-    roofline = {"kernel": f"mmb::generate ({precision})", "bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16"],
-                "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16"], "traffic": traffic, "peak_source": pk["src"],
-                "algorithmic_flops_per_launch": flops, "ms_per_launch": kern}
+    traffic = {"f16": 3.72e6, "bf16": 3.8e6}.get(precision) if B == 4096 else None
+    roofline = {"kernel": kernel_name, "bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16"],
+                "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16"], "traffic": traffic,
+                "traffic_source": "ncu --set full capture of this kernel at B=4096: profiles/r02_mma_ncu_summary.md" if traffic else None,
+                "peak_source": pk["src"], "algorithmic_flops_per_launch": flops, "ms_per_launch": kern,
+                "note": "0.819 MFLOP per jet-step counts all 128 slots of every jet; the kernel is bound by issue slots "
+                        "(ncu: 58 % issue-active, HMMA pipe 24 %), not by the tensor pipe: K = N = 16 GEMM chains"}
+    roofline_dense = None
+    if rank == 0:   # worst case for the same kernel: every jet with 128 live particles (no dead rows to skip)
+        g = torch.Generator().manual_seed(99)
+        xd = torch.randn(B, N_PART, 3, generator=g).to(device)
+        kd = torch.randint(0, 8, (B, N_PART), generator=g, dtype=torch.uint8).to(device)
+        dense_ms = kernel_ms(xd, kd, torch.ones_like(mask), 3)
+        tf = flops / (dense_ms * 1e-3) / 1e12
+        roofline_dense = {"workload": "as C2 but all 128 particles of every jet live", "jets_per_s": B / (dense_ms * 1e-3), "ms_per_launch": dense_ms,
+                          "bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tf / pk["bf16"]}
 
     # ---- standalone fused update kernel at an HBM-scale batch (32768 jets), 75 B / particle
     roofline_update = None
     if rank == 0:
         roofline_update = time_update_kernel(torch, _native, device, pk, flush)
 
-    # ---- end-to-end arm: pinned host tensors -> simulate_dynamics -> host tensors
+    # ---- end-to-end arm: pinned host tensors -> simulate_dynamics -> host tensors (one mmb_generate_host call per iteration)
     pin = lambda t: t.clone().pin_memory()
     host_states = [HybridState(None, pin(batch.source_continuous), pin(batch.source_discrete), pin(batch.source_mask))
                    for _ in range(3 + K)]
@@ -316,8 +347,16 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K / float(te.item())
     h2d = B * N_PART * (3 * 4 + 8 + 8)     # fp32 x, int64 tokens, int64 mask (reference layout), from pinned memory
-    d2h = B * N_PART * (3 * 4 + 1)         # fp32 x + uint8 tokens (widened on the host; the mask is unchanged and stays put)
-    assert out.continuous.device.type == "cpu"
+    d2h = B * N_PART * (3 * 4 + 8)         # fp32 x + int64 tokens (widened on the device; the mask is unchanged and stays put)
+    assert out.continuous.device.type == "cpu" and out.discrete.dtype == torch.int64
+
+    c5 = None
+    if world > 1 and not args.no_secondary:   # BASELINE configs[4] with the same model: 1 M jets over the GPUs of the box
+        from multimodal_particles_b200.pipeline import sharded_generation_run
+        try:
+            c5 = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=B, n_particles=N_PART, precision=precision)
+        except Exception as exc:
+            c5 = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         cpu = None
@@ -332,32 +371,65 @@ def main():
                 other = secondary_configs(torch, _native, device, pk)
             except Exception as exc:  # the headline line must not depend on the side measurements
                 other = {"error": f"{type(exc).__name__}: {exc}"}
-        launches = K * (5 + (1 if world > 1 else 0))   # time-vector prologue + 3 jet-binning kernels + generation kernel (+ histogram kernel); NCCL's own kernels not counted
+        # kernels of this repo per timed step: bf16 = time-vector prologue + 3 jet-binning kernels + generation kernel;
+        # f16 = prologue (time vectors + binning) + generation kernel; (+ histogram kernel for N > 1); NCCL's own kernels not counted
+        launches = K * ({"f16": 2, "bf16": 5, "fp32": 1}[precision] + (1 if world > 1 else 0))
         line = {"metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "dtype": {"f16": "f16", "bf16": "bf16", "fp32": "f32"}[precision], "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "precision": precision,
+                           "engine": kernel_name,
                            "l2": "256 MiB flush before the timed region; each timed step reads a fresh, never-cached source buffer",
                            "rng": "in-kernel Philox4x32-10", "parallelism": f"jets sharded over {world} GPU(s)"},
                 "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "MultiModalBridgeMatching.simulate_dynamics -> mmb_generate_host (pinned host buffers, 2 pipeline slices)",
                         "ms_per_iteration": e2e_iter_ms},
-                "gpu_launches": launches, "roofline": roofline, "roofline_update": roofline_update,
-                "cpu_baseline": cpu, "clocks": clocks.summary(), "wall_s_timed_region": t_wall, "other_configs": other}
+                "gpu_launches": launches, "roofline": roofline, "roofline_dense": roofline_dense, "roofline_update": roofline_update,
+                "cpu_baseline": cpu, "clocks": clocks.summary(), "wall_s_timed_region": t_wall, "other_configs": other,
+                "c5_million_jets": c5}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def secondary_configs(torch, _native, device, pk):
+def side_workload_line(args, torch, dist, _native, device, pk, rank, world, W, K):
+    """--workload c3 | c4 | c5: the other BASELINE configs as primary lines (same JSON contract; value = whole-job rate).
+    c3 / c4 run one independent batch per rank (jets shard, no collective); c5 is the sharded 1 M-jet run."""
+    if args.workload == "c5":
+        from multimodal_particles_b200.pipeline import sharded_generation_run
+        cfg, model = build_model(device)
+        with ClockSampler(device.index or 0) as clocks:
+            rec = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=B_PER_GPU, n_particles=N_PART,
+                                         precision=args.precision)
+        if rank != 0:
+            return None
+        return {"metric": METRIC, "value": rec["value"], "unit": "jets/s", "n_gpus": world, "steps": 1, "warmup": 2,
+                "ms_per_step": rec["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": {"f16": "f16", "bf16": "bf16", "fp32": "f32"}[rec["precision"]], "data": "synthetic",
+                "config": {"workload": rec["workload"], "global_batch": 1 << 20}, "c5_million_jets": rec, "clocks": clocks.summary(),
+                "gpu_launches": 5 * ((1 << 20) // B_PER_GPU // world)}
+    with ClockSampler(device.index or 0) as clocks:
+        rec = secondary_configs(torch, _native, device, pk, only=args.workload, reps=max(K, 2), warm=max(W, 2))
+    key = "C3_transepic_evaluation" if args.workload == "c3" else "C4_absorbing_generation"
+    r = rec[key]
+    rate = r["jet_evals_per_s"] if args.workload == "c3" else r["jets_per_s"]
+    t = torch.tensor([r["ms"]], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rate = world * (8192 if args.workload == "c3" else 4096) / (float(t.item()) * 1e-3)
+    if rank != 0:
+        return None
+    metric = "TransdimensionalEPiC evaluations/sec (jets, 128 particles)" if args.workload == "c3" else METRIC
+    return {"metric": metric, "value": rate, "unit": "jet-evaluations/s" if args.workload == "c3" else "jets/s", "n_gpus": world,
+            "steps": max(K, 2), "warmup": max(W, 2), "ms_per_step": float(t.item()), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": {"workload": r["workload"]},
+            "roofline": r.get("roofline") or r.get("roofline_head"), "clocks": clocks.summary(), "detail": r}
+
+
+def secondary_configs(torch, _native, device, pk, only=None, reps=None, warm=None):
     """BASELINE configs 3 and 4 on this GPU, reported next to the headline (rank 0, N=1): one C3 transepic evaluation
     (B=8192, N=128; 145.3 MFLOP per jet-evaluation, SURVEY.md §8d) and one C4 absorbing-flow generation (B=4096, 99 steps;
     72.0 MFLOP per jet-step in the rate head).  CUDA events on the launch stream, inputs resident."""
-    from multimodal_particles_b200.absorbing_flows import AbsorbingFlow
-    from multimodal_particles_b200.config_classes.absorbing_flows_config import AbsorbingConfig
-    from multimodal_particles_b200.config_classes.transdimensional_unconditional_config import TransdimensionalEpicConfig
-    from multimodal_particles_b200.databatch import jetclass_like_databatch
-    from multimodal_particles_b200.epic import as_u8
-    from multimodal_particles_b200.transdimensional import TransdimensionalJumpDiffusion
 
     def timed(fn, reps, warm):
         for _ in range(warm):
@@ -370,7 +442,17 @@ def secondary_configs(torch, _native, device, pk):
         return sum(ms) / len(ms)
 
     out = {}
-    # ---- C3
+    if only in (None, "c3"):
+        out.update(_c3(torch, _native, device, pk, timed, reps or 3, warm or 2))
+    if only in (None, "c4"):
+        out.update(_c4(torch, _native, device, pk, timed, reps or 2, warm or 1))
+    return out
+
+
+def _c3(torch, _native, device, pk, timed, reps, warm):
+    from multimodal_particles_b200.config_classes.transdimensional_unconditional_config import TransdimensionalEpicConfig
+    from multimodal_particles_b200.transdimensional import TransdimensionalJumpDiffusion
+    out = {}
     B, N, S = 8192, N_PART, 8
     torch.manual_seed(0)
     model = TransdimensionalJumpDiffusion(TransdimensionalEpicConfig()).to(device)
@@ -385,14 +467,21 @@ def secondary_configs(torch, _native, device, pk):
     near = (torch.rand(B, generator=g) * dims).long()
     x, oh, d32, ts, near = x.to(device), oh.to(device), dims.to(device, torch.int32), ts.to(device), near.to(device, torch.int32)
     fr = model.forward_rate.as_c()
-    ms = timed(lambda: _native.trans_forward(trunk, heads, x, oh, d32, ts, near, None, fr, precision="bf16", want_auto=False), 3, 2)
+    ms = timed(lambda: _native.trans_forward(trunk, heads, x, oh, d32, ts, near, None, fr, precision="bf16", want_auto=False), reps, warm)
     tf = 145.33e6 * B / (ms * 1e-3) / 1e12
     out["C3_transepic_evaluation"] = {"workload": "TransdimensionalEPiC.forward, B=8192, N=128, bf16 stacks", "ms": ms,
                                       "jet_evals_per_s": B / (ms * 1e-3),
                                       "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
                                                    "frac": tf / pk["bf16"]}}
-    del model, trunk, heads
-    # ---- C4
+    return out
+
+
+def _c4(torch, _native, device, pk, timed, reps, warm):
+    from multimodal_particles_b200.absorbing_flows import AbsorbingFlow
+    from multimodal_particles_b200.config_classes.absorbing_flows_config import AbsorbingConfig
+    from multimodal_particles_b200.databatch import jetclass_like_databatch
+    from multimodal_particles_b200.epic import as_u8
+    out = {}
     B = 4096
     cfg = AbsorbingConfig()
     cfg.data.max_num_particles, cfg.bridge.num_timesteps = N_PART, N_TIMESTEPS
@@ -408,7 +497,7 @@ def secondary_configs(torch, _native, device, pk):
     def run():
         _native.generate_absorbing(trunk, head, x0.clone(), k0.clone(), m0.clone(), table, tb, seed=1, jet_offset=0, precision="bf16")
 
-    ms = timed(run, 2, 1)
+    ms = timed(run, reps, warm)
     hid = torch.randn(B, N_PART, 16, device=device)
     tb1 = tb[:1].to(device)
     hms = timed(lambda: head.forward(hid, m0, tb1), 5, 2)
@@ -417,19 +506,6 @@ def secondary_configs(torch, _native, device, pk):
                                       "roofline_head": {"bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
                                                         "frac": tf / pk["bf16"], "ms_per_launch": hms}}
     return out
-
-
-def native_supports_bf16(native, _native_mod):
-    import torch
-    try:
-        x = torch.zeros(1, 128, 3, device=native.device)
-        k = torch.zeros(1, 128, dtype=torch.uint8, device=native.device)
-        m = torch.ones(1, 128, dtype=torch.uint8, device=native.device)
-        temb = torch.zeros(1, native.dims.dim_time_emb, device=native.device)
-        native.forward(x, k, m, temb, precision="bf16")
-        return True
-    except _native_mod.MmbError:
-        return False
 
 
 def time_update_kernel(torch, _native, device, pk, flush, jets=32768, reps=20):
@@ -458,8 +534,9 @@ def time_update_kernel(torch, _native, device, pk, flush, jets=32768, reps=20):
     ms = sum(times) / len(times)
     nbytes = UPDATE_BYTES_PER_PARTICLE * B * N
     gbs = nbytes / (ms * 1e-3) / 1e9
-    return {"kernel": "mmb::bridge_update_vec4_kernel<8>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-            "frac": gbs / pk["hbm"], "traffic": 269.8e6 if jets == 32768 else None,   # ncu --set full: 260.1 MB read + 9.8 MB written
+    return {"kernel": "mmb::bridge_update_vec_kernel<8,2,5>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+            "frac": gbs / pk["hbm"], "traffic": 269.8e6 if jets == 32768 else None,   # ncu --set full: 260.1 MB read + 9.8 MB written (writes still in L2)
+            "traffic_source": "ncu --set full capture at 32768 jets: profiles/r01_update_variants.md" if jets == 32768 else None,
             "peak_source": pk["src"], "jets": jets,
             "l2": "working set 315 MB > 126 MB L2; 10 launches per event pair",
             "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms}

@@ -245,6 +245,25 @@ int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mas
                  void* workspace, size_t workspace_bytes, int precision, void* stream);
 
 /*
+ * The same generation with HOST buffers in the reference's own layout — what MultiModalBridgeMatching.simulate_dynamics
+ * receives and returns (mbm.py:199-216: fp32 features [B,N,Dc], int64 tokens [B,N,1], int64 mask [B,N,1]; result on the host).
+ * The jets are cut into n_chunks slices that travel through internal streams: H2D of slice c+1 and D2H of slice c-1 run under
+ * the solver steps of slice c; tokens / masks are narrowed to uint8 and widened back on the device; Philox is keyed by the
+ * global jet index, so the result equals the unsliced call bit for bit.
+ *   x_in, k_in, mask_in, x_out, k_out, bad_tokens: HOST pointers (page-locked for the copies to be asynchronous; x_out / k_out
+ *   may alias x_in / k_in).  *bad_tokens becomes 1 if any input token lies outside [0, S) — the reference asserts that
+ *   (bridges.py:111-115); the caller raises after synchronising.  In-kernel Philox only.
+ *   workspace: mmb_generate_host_workspace_bytes(...) bytes of 256-byte aligned DEVICE memory.
+ * Asynchronous: everything is ordered after the work already on `stream`, and `stream` continues after the last copy;
+ * results are valid once the caller has synchronised `stream`.  Streams and events are created on the first call.
+ */
+size_t mmb_generate_host_workspace_bytes(const MmbEpicModel* m, int B, int N, int n_steps, int n_chunks, int precision);
+int mmb_generate_host(const MmbEpicModel* m, const float* x_in, const int64_t* k_in, const int64_t* mask_in,
+                      const MmbStepTable* st, uint64_t seed, uint64_t jet_offset, int B, int N,
+                      float* x_out, int64_t* k_out, int32_t* bad_tokens, void* workspace, size_t workspace_bytes,
+                      int n_chunks, int precision, void* stream);
+
+/*
  * Diagnostics: the jump rule (TelegraphBridge.solver_step, bridges.py:179-201, as the one-uniform categorical) evaluated by
  * its three device implementations on IDENTICAL inputs — the exact rule of MMB_PREC_FP32 / mmb_bridge_update (bit-identical to
  * the oracle) and the fast-intrinsic variants inside the MMB_PREC_BF16 and MMB_PREC_F16 generation kernels.

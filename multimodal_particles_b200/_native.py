@@ -93,6 +93,8 @@ SIGNATURES = {
     "mmb_generate_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "mmb_generate_supported": (_i, [_vp, _i, _i]),
     "mmb_generate": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
+    "mmb_generate_host_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i, _i]),
+    "mmb_generate_host": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _u64, _u64, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "mmb_jump_variants": (_i, [_vp, _vp, _vp, _f, _f, _f, _sz, _i, _vp, _vp, _vp, _vp]),
     "mmb_philox_uniforms": (_i, [_vp, _u64, _u64, _i, _i, _i, _vp]),
     "mmb_absorb_head_create": (_i, [_i, _i, _i, _i, _vp, _sz, _i, ctypes.POINTER(_vp)]),
@@ -215,6 +217,30 @@ class EpicModel:
             check(lib.mmb_generate(self._handle, _ptr(x), _ptr(k_u8), _ptr(mask_u8), ctypes.byref(ctable), _ptr(u_jump),
                                    seed, jet_offset, B, N, _ptr(ws), ws.numel(), prec, _stream()))
         return x, k_u8
+
+
+    def generate_host(self, x_host, k64_host, m64_host, table, seed=0, jet_offset=0, chunks=2, precision="auto"):
+        """Host state in the reference's layout (fp32 [B,N,Dc], int64 [B,N,1] tokens and masks) -> pinned host result
+        (x [B,N,Dc] f32, k [B,N,1] int64, flag [1] int32: 1 = a token was out of range), asynchronous on the current stream of
+        this model's device: ONE library call does the sliced H2D / narrow / generate / widen / D2H pipeline."""
+        B, N, _ = x_host.shape
+        lib = load()
+        dev = self.device
+        prec = PRECISIONS[self.generate_precision(N, precision)]
+        pin = lambda t, dt: t if (t.dtype == dt and t.is_contiguous()) else t.to(dt).contiguous()
+        x_in, k_in, m_in = pin(x_host, torch.float32), pin(k64_host, torch.int64), pin(m64_host, torch.int64)
+        x_out = torch.empty((B, N, x_in.shape[-1]), dtype=torch.float32, pin_memory=True)
+        k_out = torch.empty((B, N, 1), dtype=torch.int64, pin_memory=True)
+        flag = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        need = lib.mmb_generate_host_workspace_bytes(self._handle, B, N, table.n_steps, chunks, prec)
+        ws = getattr(self, "_host_ws", None)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = self._host_ws = torch.empty(max(need, 256), device=dev, dtype=torch.uint8)   # torch allocations are 512-byte aligned
+        ctable = CStepTable.from_table(table)
+        with torch.cuda.device(dev):
+            check(lib.mmb_generate_host(self._handle, _ptr(x_in), _ptr(k_in), _ptr(m_in), ctypes.byref(ctable), seed, jet_offset, B, N,
+                                        _ptr(x_out), _ptr(k_out), _ptr(flag), _ptr(ws), ws.numel(), chunks, prec, _stream()))
+        return x_out, k_out, flag, (x_in, k_in, m_in)   # the inputs must outlive the asynchronous copies
 
 
 def bridge_update(x, k_u8, mask_u8, v, logits, u_jump, dt, bc, cc, absorb_logit=None, u_absorb=None, sp=0.0,

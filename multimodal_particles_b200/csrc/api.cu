@@ -50,6 +50,71 @@ struct TableCache {
     int next = 0;
 };
 
+// ---- host-buffer pipeline (mmb_generate_host): internal streams and events, created on first use --------------------------
+constexpr int kHostStreams = 4, kHostMaxChunks = 16;
+struct HostPipe {
+    std::mutex mu;
+    bool ready = false;
+    cudaStream_t stream[kHostStreams] = {};
+    cudaEvent_t fork = nullptr, done[kHostMaxChunks] = {};
+};
+
+static int host_pipe_init(HostPipe* hp) {
+    std::lock_guard<std::mutex> lock(hp->mu);
+    if (hp->ready) return MMB_OK;
+    for (auto& s : hp->stream)
+        if (int rc = cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "host pipeline stream")) return rc;
+    if (int rc = cuda_ok(cudaEventCreateWithFlags(&hp->fork, cudaEventDisableTiming), "host pipeline event")) return rc;
+    for (auto& e : hp->done)
+        if (int rc = cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "host pipeline event")) return rc;
+    hp->ready = true;
+    return MMB_OK;
+}
+
+HostPipe* host_pipe_create() { return new (std::nothrow) HostPipe(); }
+
+void host_pipe_destroy(HostPipe* hp) {
+    if (!hp) return;
+    for (auto s : hp->stream)
+        if (s) cudaStreamDestroy(s);
+    if (hp->fork) cudaEventDestroy(hp->fork);
+    for (auto e : hp->done)
+        if (e) cudaEventDestroy(e);
+    delete hp;
+}
+
+// reference layout <-> device layout: int64 [P] tokens / masks (mbm.py:13-20) <-> uint8; out-of-range tokens raise a flag
+// (the reference asserts 0 <= k < S before every jump, bridges.py:111-115)
+__global__ void __launch_bounds__(256) narrow_state_kernel(const long long* __restrict__ k64, const long long* __restrict__ m64,
+                                                           uint8_t* __restrict__ k8, uint8_t* __restrict__ m8, size_t P, int S,
+                                                           int* __restrict__ bad) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= P) return;
+    bool oob = false;
+    if (i + 1 < P) {
+        const longlong2 kk = *reinterpret_cast<const longlong2*>(k64 + i), mm = *reinterpret_cast<const longlong2*>(m64 + i);
+        oob = kk.x < 0 || kk.x >= S || kk.y < 0 || kk.y >= S;
+        *reinterpret_cast<uchar2*>(k8 + i) = make_uchar2((unsigned char)kk.x, (unsigned char)kk.y);
+        *reinterpret_cast<uchar2*>(m8 + i) = make_uchar2(mm.x != 0, mm.y != 0);
+    } else {
+        const long long kk = k64[i];
+        oob = kk < 0 || kk >= S;
+        k8[i] = (uint8_t)kk;
+        m8[i] = m64[i] != 0;
+    }
+    if (oob) atomicOr(bad, 1);
+}
+__global__ void __launch_bounds__(256) widen_tokens_kernel(const uint8_t* __restrict__ k8, long long* __restrict__ k64, size_t P) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= P) return;
+    if (i + 1 < P) {
+        const uchar2 kk = *reinterpret_cast<const uchar2*>(k8 + i);
+        *reinterpret_cast<longlong2*>(k64 + i) = make_longlong2(kk.x, kk.y);
+    } else {
+        k64[i] = k8[i];
+    }
+}
+
 TableCache* table_cache_create() { return new (std::nothrow) TableCache(); }
 
 void table_cache_destroy(TableCache* c) {
@@ -156,6 +221,7 @@ int mmb_epic_create(const MmbEpicDims* dims, const float* packed, size_t n_float
     EpicModel* m = new (std::nothrow) EpicModel();
     if (!m) return fail(MMB_ENOMEM, "out of host memory");
     m->tables = table_cache_create();
+    m->host_pipe = host_pipe_create();
     m->dims = *dims;
     m->layout = lo;
     m->device = device;
@@ -189,6 +255,7 @@ void mmb_epic_destroy(MmbEpicModel* handle) {
     if (m->tc_image) cudaFree(m->tc_image);
     if (m->mma_image_f16) cudaFree(m->mma_image_f16);
     table_cache_destroy(m->tables);
+    host_pipe_destroy(m->host_pipe);
     delete m;
 }
 
@@ -242,6 +309,10 @@ int mmb_generate_supported(const MmbEpicModel* handle, int N, int precision) {
     return 0;
 }
 
+static size_t generate_ws_floats(const EpicModel* m, int n_steps, int B, int precision) {
+    return precision == MMB_PREC_F16 ? mma_generate_scratch_floats(&m->dims, n_steps, B) : tc_generate_scratch_floats(&m->dims, n_steps, B);
+}
+
 int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t* mask,
                  const MmbStepTable* st, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                  int B, int N, void* workspace, size_t workspace_bytes, int precision, void* stream) {
@@ -250,8 +321,7 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     if (!st->temb || !st->bc || !st->cc) return fail(MMB_EINVAL, "mmb_generate: incomplete step table");
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate: negative size");
     const int T = m->dims.dim_time_emb, n = st->n_steps;
-    const size_t ws_need = precision == MMB_PREC_F16 ? mma_generate_scratch_floats(&m->dims, n, B) : tc_generate_scratch_floats(&m->dims, n, B);
-    if (workspace_bytes < ws_need * sizeof(float))
+    if (workspace_bytes < generate_ws_floats(m, n, B, precision) * sizeof(float))
         return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B too small for %d steps", workspace_bytes, n);
     if (B == 0 || N == 0 || n == 0) return MMB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -276,6 +346,97 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
         return launch_generate_mma(m, x, k, mask, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N, s);
     }
     return fail(MMB_EINVAL, "unknown precision %d", precision);
+}
+
+// per-chunk device buffers of mmb_generate_host, each rounded up to 256 B: x f32 | k int64 | mask int64 | k u8 | mask u8 | scratch
+struct HostChunkLayout {
+    size_t x, k64, m64, k8, m8, scratch, total;
+    HostChunkLayout(const EpicModel* m, int Bc, int N, int n_steps, int precision) {
+        const size_t P = (size_t)Bc * N;
+        size_t at = 0;
+        auto take = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
+        x = take(P * m->dims.dim_continuous * sizeof(float));
+        k64 = take(P * 8); m64 = take(P * 8); k8 = take(P); m8 = take(P);
+        scratch = take(generate_ws_floats(m, n_steps, Bc, precision) * sizeof(float));
+        total = at;
+    }
+};
+
+static int host_chunks(int B, int n_chunks) {
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > kHostMaxChunks) n_chunks = kHostMaxChunks;
+    return n_chunks > B ? (B > 0 ? B : 1) : n_chunks;
+}
+
+size_t mmb_generate_host_workspace_bytes(const MmbEpicModel* handle, int B, int N, int n_steps, int n_chunks, int precision) {
+    const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
+    if (!m || B < 0 || N < 0 || n_steps < 0) return 0;
+    n_chunks = host_chunks(B, n_chunks);
+    const int Bc = (B + n_chunks - 1) / n_chunks;
+    return 256 + (size_t)n_chunks * HostChunkLayout(m, Bc, N, n_steps, precision).total;
+}
+
+int mmb_generate_host(const MmbEpicModel* handle, const float* x_in, const int64_t* k_in, const int64_t* mask_in,
+                      const MmbStepTable* st, uint64_t seed, uint64_t jet_offset, int B, int N,
+                      float* x_out, int64_t* k_out, int32_t* bad_tokens, void* workspace, size_t workspace_bytes,
+                      int n_chunks, int precision, void* stream) {
+    const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
+    if (!m || !x_in || !k_in || !mask_in || !st || !x_out || !k_out || !bad_tokens || !workspace)
+        return fail(MMB_EINVAL, "mmb_generate_host: null argument");
+    if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate_host: negative size");
+    if (workspace_bytes < mmb_generate_host_workspace_bytes(handle, B, N, st->n_steps, n_chunks, precision))
+        return fail(MMB_ENOMEM, "mmb_generate_host: workspace too small");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(MMB_EINVAL, "mmb_generate_host: workspace must be 256-byte aligned");
+    *bad_tokens = 0;
+    if (B == 0 || N == 0 || st->n_steps == 0) return MMB_OK;
+    HostPipe* hp = m->host_pipe;
+    if (!hp) return fail(MMB_ENOMEM, "mmb_generate_host: no pipeline state");
+    try {
+        if (int rc = host_pipe_init(hp)) return rc;
+    } catch (...) {
+        return fail(MMB_ENOMEM, "mmb_generate_host: host-side failure");
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    n_chunks = host_chunks(B, n_chunks);
+    const int Bc = (B + n_chunks - 1) / n_chunks, Dc = m->dims.dim_continuous, S = m->dims.vocab_size;
+    const HostChunkLayout lay(m, Bc, N, st->n_steps, precision);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    int* d_bad = reinterpret_cast<int*>(ws);
+    // fork: the chunk streams start after everything the caller enqueued on `stream` (and after the flag is cleared)
+    int rc = cuda_ok(cudaMemsetAsync(d_bad, 0, sizeof(int), s), "flag reset");
+    if (!rc) rc = cuda_ok(cudaEventRecord(hp->fork, s), "fork");
+    for (int c = 0; c < n_chunks && !rc; ++c) {
+        const int lo = c * Bc, hi = lo + Bc < B ? lo + Bc : B;
+        if (hi <= lo) { n_chunks = c; break; }
+        const size_t P = (size_t)(hi - lo) * N, off = (size_t)lo * N;
+        cudaStream_t cs = hp->stream[c % kHostStreams];
+        uint8_t* base = ws + 256 + (size_t)c * lay.total;
+        float* dx = reinterpret_cast<float*>(base + lay.x);
+        long long* dk64 = reinterpret_cast<long long*>(base + lay.k64);
+        long long* dm64 = reinterpret_cast<long long*>(base + lay.m64);
+        uint8_t *dk8 = base + lay.k8, *dm8 = base + lay.m8;
+        rc = cuda_ok(cudaStreamWaitEvent(cs, hp->fork, 0), "fork wait");
+        if (!rc) rc = cuda_ok(cudaMemcpyAsync(dx, x_in + off * Dc, P * Dc * sizeof(float), cudaMemcpyHostToDevice, cs), "H2D x");
+        if (!rc) rc = cuda_ok(cudaMemcpyAsync(dk64, k_in + off, P * 8, cudaMemcpyHostToDevice, cs), "H2D k");
+        if (!rc) rc = cuda_ok(cudaMemcpyAsync(dm64, mask_in + off, P * 8, cudaMemcpyHostToDevice, cs), "H2D mask");
+        if (!rc) {
+            narrow_state_kernel<<<(unsigned)((P / 2 + 256) / 256), 256, 0, cs>>>(dk64, dm64, dk8, dm8, P, S, d_bad);
+            rc = cuda_ok(cudaGetLastError(), "narrow launch");
+        }
+        if (!rc) rc = mmb_generate(handle, dx, dk8, dm8, st, nullptr, seed, jet_offset + (uint64_t)lo, hi - lo, N, base + lay.scratch,
+                                   lay.total - lay.scratch, precision, cs);
+        if (!rc) {
+            widen_tokens_kernel<<<(unsigned)((P / 2 + 256) / 256), 256, 0, cs>>>(dk8, dk64, P);
+            rc = cuda_ok(cudaGetLastError(), "widen launch");
+        }
+        if (!rc) rc = cuda_ok(cudaMemcpyAsync(x_out + off * Dc, dx, P * Dc * sizeof(float), cudaMemcpyDeviceToHost, cs), "D2H x");
+        if (!rc) rc = cuda_ok(cudaMemcpyAsync(k_out + off, dk64, P * 8, cudaMemcpyDeviceToHost, cs), "D2H k");
+        if (!rc) rc = cuda_ok(cudaEventRecord(hp->done[c], cs), "chunk done");
+    }
+    // join: the caller's stream continues after every chunk; the range flag follows them
+    for (int c = 0; c < n_chunks; ++c) cudaStreamWaitEvent(s, hp->done[c], 0);
+    if (!rc) rc = cuda_ok(cudaMemcpyAsync(bad_tokens, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H flag");
+    return rc;
 }
 
 int mmb_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int n_steps, int B, int N, void* stream) {

@@ -24,8 +24,11 @@ struct TableCache;
 TableCache* table_cache_create();
 void table_cache_destroy(TableCache* c);
 
+struct HostPipe;   // streams / events of mmb_generate_host (api.cu)
+
 struct EpicModel {
     TableCache* tables;
+    HostPipe* host_pipe;
     MmbEpicDims dims;
     MmbEpicLayout layout;
     int device;

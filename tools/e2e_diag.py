@@ -8,7 +8,7 @@ cfg, model = bench.build_model(dev)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 batch = bench.source_batch(B, 1234)
 pin = lambda t: t.clone().pin_memory()
-model.precision = "bf16"
+model.precision = sys.argv[2] if len(sys.argv) > 2 else "auto"
 ref = None
 for chunks in (1, 2, 3, 4, 8):
     model.pipeline_chunks, model.pipeline_min_jets = chunks, 1
