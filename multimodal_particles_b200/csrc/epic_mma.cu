@@ -824,9 +824,11 @@ int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t*
                                                                                 jet_cnt, x, k);
     if (int rc = cuda_ok(cudaGetLastError(), "mma prologue launch")) return rc;
     p.tvec = reinterpret_cast<const float4*>(scratch); p.counts = counts; p.cursors = cursors; p.lists = lists; p.jet_cnt = jet_cnt;
-    // persistent grid: MMB_MMA_MINB CTAs per SM, never more warps than there could be work for
-    const int want = (B + kW - 1) / kW * ((N + kRowsPerWarp - 1) / kRowsPerWarp);
-    const int grid = want < m->sm_count * MMB_MMA_MINB ? want : m->sm_count * MMB_MMA_MINB;
+    // Persistent grid: MMB_MMA_MINB CTAs per SM at most.  Any grid finishes any amount of work (warps claim jets until the
+    // lists are empty), so the size only matters for speed: a small call takes about 1.25 warps per jet (the JetClass-like
+    // mean is 1.14), which lets the kernels of neighbouring pipeline slices (mmb_generate_host) share the GPU side by side.
+    const int want = (int)(((size_t)B * 5 + 4 * kW - 1) / (4 * kW));
+    const int grid = want < m->sm_count * MMB_MMA_MINB ? (want > 0 ? want : 1) : m->sm_count * MMB_MMA_MINB;
     return dispatch(m->dims, p, grid, stream);
 }
 
