@@ -333,6 +333,9 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    import gc
+    gc.collect()
+    gc.disable()          # an iteration is ~1.3 ms: a generation-2 collection inside the loop would show up as an outlier
     t0 = time.perf_counter()
     e2e_iter_ms, t_prev = [], t0
     for i in range(K):
@@ -342,6 +345,7 @@ def main():
         t_prev = t_now
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    gc.enable()
     te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -382,7 +386,7 @@ def main():
                            "l2": "256 MiB flush before the timed region; each timed step reads a fresh, never-cached source buffer",
                            "rng": "in-kernel Philox4x32-10", "parallelism": f"jets sharded over {world} GPU(s)"},
                 "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "MultiModalBridgeMatching.simulate_dynamics -> mmb_generate_host (pinned host buffers, 2 pipeline slices)",
+                        "api": "MultiModalBridgeMatching.simulate_dynamics -> mmb_generate_host, direct mode (the kernel reads and writes the pinned host buffers itself)",
                         "ms_per_iteration": e2e_iter_ms},
                 "gpu_launches": launches, "roofline": roofline, "roofline_dense": roofline_dense, "roofline_update": roofline_update,
                 "cpu_baseline": cpu, "clocks": clocks.summary(), "wall_s_timed_region": t_wall, "other_configs": other,

@@ -253,6 +253,11 @@ int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mas
  *   x_in, k_in, mask_in, x_out, k_out, bad_tokens: HOST pointers (page-locked for the copies to be asynchronous; x_out / k_out
  *   may alias x_in / k_in).  *bad_tokens becomes 1 if any input token lies outside [0, S) — the reference asserts that
  *   (bridges.py:111-115); the caller raises after synchronising.  In-kernel Philox only.
+ *   n_chunks <= 0 selects the DIRECT mode (MMB_PREC_F16 with page-locked buffers; anything else falls back to two slices):
+ *   no slicing and no staging copies of features or tokens — each warp of the generation kernel reads the source state of the
+ *   jet it claims straight from the mapped host buffers and writes the final state straight back, so the PCIe traffic of a
+ *   jet hides under the solver steps of the others; only the masks (needed up front to order the jets) and a copy of the
+ *   tokens for the range assertion travel by DMA, on side streams.
  *   workspace: mmb_generate_host_workspace_bytes(...) bytes of 256-byte aligned DEVICE memory.
  * Asynchronous: everything is ordered after the work already on `stream`, and `stream` continues after the last copy;
  * results are valid once the caller has synchronised `stream`.  Streams and events are created on the first call.

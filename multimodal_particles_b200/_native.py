@@ -219,27 +219,40 @@ class EpicModel:
         return x, k_u8
 
 
-    def generate_host(self, x_host, k64_host, m64_host, table, seed=0, jet_offset=0, chunks=2, precision="auto"):
+    def generate_host(self, x_host, k64_host, m64_host, table, seed=0, jet_offset=0, chunks=0, precision="auto"):
         """Host state in the reference's layout (fp32 [B,N,Dc], int64 [B,N,1] tokens and masks) -> pinned host result
         (x [B,N,Dc] f32, k [B,N,1] int64, flag [1] int32: 1 = a token was out of range), asynchronous on the current stream of
-        this model's device: ONE library call does the sliced H2D / narrow / generate / widen / D2H pipeline."""
-        B, N, _ = x_host.shape
+        this model's device: ONE library call (direct mode for ``chunks=0``, else the sliced H2D / generate / D2H pipeline).
+        The host-side work of a call is kept to one page-locked allocation and the call itself (it is on the critical path
+        of a 1 ms generation)."""
+        B, N, Dc = x_host.shape
         lib = load()
         dev = self.device
         prec = PRECISIONS[self.generate_precision(N, precision)]
-        pin = lambda t, dt: t if (t.dtype == dt and t.is_contiguous()) else t.to(dt).contiguous()
-        x_in, k_in, m_in = pin(x_host, torch.float32), pin(k64_host, torch.int64), pin(m64_host, torch.int64)
-        x_out = torch.empty((B, N, x_in.shape[-1]), dtype=torch.float32, pin_memory=True)
-        k_out = torch.empty((B, N, 1), dtype=torch.int64, pin_memory=True)
-        flag = torch.empty(1, dtype=torch.int32, pin_memory=True)
-        need = lib.mmb_generate_host_workspace_bytes(self._handle, B, N, table.n_steps, chunks, prec)
+        fix = lambda t, dt: t if (t.dtype == dt and t.is_contiguous()) else t.to(dt).contiguous()
+        x_in, k_in, m_in = fix(x_host, torch.float32), fix(k64_host, torch.int64), fix(m64_host, torch.int64)
+        # one page-locked block: [x f32 | k int64 | flag], 16-byte aligned parts
+        nx, nk = B * N * Dc * 4, B * N * 8
+        block = torch.empty(nx + nk + 16, dtype=torch.uint8, pin_memory=True)
+        x_out = block[:nx].view(torch.float32).view(B, N, Dc)
+        k_out = block[nx:nx + nk].view(torch.int64).view(B, N, 1)
+        flag = block[nx + nk:nx + nk + 4].view(torch.int32)
+        key = (B, N, table.n_steps, chunks, prec)
+        cache = self.__dict__.setdefault("_host_cache", {})
+        need = cache.get(key)
+        if need is None:
+            need = cache[key] = lib.mmb_generate_host_workspace_bytes(self._handle, B, N, table.n_steps, chunks, prec)
         ws = getattr(self, "_host_ws", None)
         if ws is None or ws.numel() < need or ws.device != dev:
             ws = self._host_ws = torch.empty(max(need, 256), device=dev, dtype=torch.uint8)   # torch allocations are 512-byte aligned
-        ctable = CStepTable.from_table(table)
-        with torch.cuda.device(dev):
-            check(lib.mmb_generate_host(self._handle, _ptr(x_in), _ptr(k_in), _ptr(m_in), ctypes.byref(ctable), seed, jet_offset, B, N,
-                                        _ptr(x_out), _ptr(k_out), _ptr(flag), _ptr(ws), ws.numel(), chunks, prec, _stream()))
+        ctable = getattr(table, "_ctable", None)
+        if ctable is None:
+            ctable = table._ctable = CStepTable.from_table(table)
+        stream = torch.cuda.current_stream(dev)
+        rc = lib.mmb_generate_host(self._handle, x_in.data_ptr(), k_in.data_ptr(), m_in.data_ptr(), ctypes.byref(ctable), seed, jet_offset, B, N,
+                                   x_out.data_ptr(), k_out.data_ptr(), flag.data_ptr(), ws.data_ptr(), ws.numel(), chunks, prec,
+                                   stream.cuda_stream)
+        check(rc)
         return x_out, k_out, flag, (x_in, k_in, m_in)   # the inputs must outlive the asynchronous copies
 
 

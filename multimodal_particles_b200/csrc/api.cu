@@ -104,6 +104,30 @@ __global__ void __launch_bounds__(256) narrow_state_kernel(const long long* __re
     }
     if (oob) atomicOr(bad, 1);
 }
+// direct mode: masks only (the generation kernel reads features and tokens from the host itself), and the reference's
+// token-range assertion over ALL tokens, live or not
+__global__ void __launch_bounds__(256) narrow_mask_kernel(const long long* __restrict__ m64, uint8_t* __restrict__ m8, size_t P) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= P) return;
+    if (i + 1 < P) {
+        const longlong2 mm = *reinterpret_cast<const longlong2*>(m64 + i);
+        *reinterpret_cast<uchar2*>(m8 + i) = make_uchar2(mm.x != 0, mm.y != 0);
+    } else {
+        m8[i] = m64[i] != 0;
+    }
+}
+__global__ void __launch_bounds__(256) check_tokens_kernel(const long long* __restrict__ k64, size_t P, int S, int* __restrict__ bad) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= P) return;
+    bool oob;
+    if (i + 1 < P) {
+        const longlong2 kk = *reinterpret_cast<const longlong2*>(k64 + i);
+        oob = kk.x < 0 || kk.x >= S || kk.y < 0 || kk.y >= S;
+    } else {
+        oob = k64[i] < 0 || k64[i] >= S;
+    }
+    if (oob) atomicOr(bad, 1);
+}
 __global__ void __launch_bounds__(256) widen_tokens_kernel(const uint8_t* __restrict__ k8, long long* __restrict__ k64, size_t P) {
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (i >= P) return;
@@ -368,12 +392,39 @@ static int host_chunks(int B, int n_chunks) {
     return n_chunks > B ? (B > 0 ? B : 1) : n_chunks;
 }
 
-size_t mmb_generate_host_workspace_bytes(const MmbEpicModel* handle, int B, int N, int n_steps, int n_chunks, int precision) {
-    const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
-    if (!m || B < 0 || N < 0 || n_steps < 0) return 0;
+// direct mode (n_chunks <= 0): flag | mask int64 | mask u8 | token int64 (range check only) | scratch
+struct HostDirectLayout {
+    size_t m64, m8, k64, scratch, total;
+    HostDirectLayout(const EpicModel* m, int B, int N, int n_steps) {
+        const size_t P = (size_t)B * N;
+        size_t at = 256;
+        auto take = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
+        m64 = take(P * 8); m8 = take(P); k64 = take(P * 8);
+        scratch = take(mma_generate_scratch_floats(&m->dims, n_steps, B) * sizeof(float));
+        total = at;
+    }
+};
+constexpr int kFallbackChunks = 2;   // direct mode asked for, but a buffer is not page-locked or the engine is not the warp-MMA one
+
+static size_t host_ws_chunked(const EpicModel* m, int B, int N, int n_steps, int n_chunks, int precision) {
     n_chunks = host_chunks(B, n_chunks);
     const int Bc = (B + n_chunks - 1) / n_chunks;
     return 256 + (size_t)n_chunks * HostChunkLayout(m, Bc, N, n_steps, precision).total;
+}
+
+size_t mmb_generate_host_workspace_bytes(const MmbEpicModel* handle, int B, int N, int n_steps, int n_chunks, int precision) {
+    const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
+    if (!m || B < 0 || N < 0 || n_steps < 0) return 0;
+    if (n_chunks > 0) return host_ws_chunked(m, B, N, n_steps, n_chunks, precision);
+    const size_t a = HostDirectLayout(m, B, N, n_steps).total, b = host_ws_chunked(m, B, N, n_steps, kFallbackChunks, precision);
+    return a > b ? a : b;
+}
+
+// device-visible address of a page-locked host buffer, or null
+static void* mapped_host_pointer(const void* host) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
 int mmb_generate_host(const MmbEpicModel* handle, const float* x_in, const int64_t* k_in, const int64_t* mask_in,
@@ -397,8 +448,61 @@ int mmb_generate_host(const MmbEpicModel* handle, const float* x_in, const int64
         return fail(MMB_ENOMEM, "mmb_generate_host: host-side failure");
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int S = m->dims.vocab_size;
+    if (n_chunks <= 0) {
+        // ---- direct mode: the warp-MMA kernel reads each jet's features and tokens from the mapped host buffers when a warp
+        // claims it and writes the result straight back; only the masks (needed up front to bin the jets) and a copy of the
+        // tokens for the range assertion travel by DMA, on two streams, under the kernel
+        void *dx_in = mapped_host_pointer(x_in), *dk_in = mapped_host_pointer(k_in), *dx_out = mapped_host_pointer(x_out),
+             *dk_out = mapped_host_pointer(k_out);
+        const bool direct = precision == MMB_PREC_F16 && dx_in && dk_in && dx_out && dk_out && m->mma_image_f16 && mma_supported(&m->dims, N);
+        if (direct) {
+            const HostDirectLayout lay(m, B, N, st->n_steps);
+            uint8_t* ws = static_cast<uint8_t*>(workspace);
+            int* d_bad = reinterpret_cast<int*>(ws);
+            const size_t P = (size_t)B * N;
+            const int T = m->dims.dim_time_emb, n = st->n_steps;
+            const float* table = nullptr;
+            try {
+                if (int rc = table_cache_get(m->tables, step_table_hash(st, T, false), table_floats(n, T), s,
+                                             [&](float* img) { fill_step_table(img, st, T); }, &table))
+                    return rc;
+            } catch (...) {
+                return fail(MMB_ENOMEM, "mmb_generate_host: host-side failure while caching the step table");
+            }
+            cudaStream_t sa = hp->stream[0], sb = hp->stream[1];
+            long long* dm64 = reinterpret_cast<long long*>(ws + lay.m64);
+            long long* dk64 = reinterpret_cast<long long*>(ws + lay.k64);
+            uint8_t* dm8 = ws + lay.m8;
+            int rc = cuda_ok(cudaMemsetAsync(d_bad, 0, sizeof(int), s), "flag reset");
+            if (!rc) rc = cuda_ok(cudaEventRecord(hp->fork, s), "fork");
+            if (!rc) rc = cuda_ok(cudaStreamWaitEvent(sa, hp->fork, 0), "fork wait");
+            if (!rc) rc = cuda_ok(cudaStreamWaitEvent(sb, hp->fork, 0), "fork wait");
+            if (!rc) rc = cuda_ok(cudaMemcpyAsync(dm64, mask_in, P * 8, cudaMemcpyHostToDevice, sa), "H2D mask");
+            if (!rc) {
+                narrow_mask_kernel<<<(unsigned)((P / 2 + 256) / 256), 256, 0, sa>>>(dm64, dm8, P);
+                rc = cuda_ok(cudaGetLastError(), "narrow launch");
+            }
+            const MmaHostIO io{static_cast<const float*>(dx_in), static_cast<const long long*>(dk_in), static_cast<float*>(dx_out),
+                               static_cast<long long*>(dk_out), d_bad};
+            if (!rc) rc = launch_generate_mma(m, nullptr, nullptr, dm8, table, reinterpret_cast<float*>(ws + lay.scratch), n, st->dt, nullptr, seed,
+                                              jet_offset, B, N, sa, &io);
+            if (!rc) rc = cuda_ok(cudaEventRecord(hp->done[0], sa), "direct done");
+            if (!rc) rc = cuda_ok(cudaMemcpyAsync(dk64, k_in, P * 8, cudaMemcpyHostToDevice, sb), "H2D tokens");
+            if (!rc) {
+                check_tokens_kernel<<<(unsigned)((P / 2 + 256) / 256), 256, 0, sb>>>(dk64, P, S, d_bad);
+                rc = cuda_ok(cudaGetLastError(), "token check launch");
+            }
+            if (!rc) rc = cuda_ok(cudaEventRecord(hp->done[1], sb), "check done");
+            cudaStreamWaitEvent(s, hp->done[0], 0);
+            cudaStreamWaitEvent(s, hp->done[1], 0);
+            if (!rc) rc = cuda_ok(cudaMemcpyAsync(bad_tokens, d_bad, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H flag");
+            return rc;
+        }
+        n_chunks = kFallbackChunks;
+    }
     n_chunks = host_chunks(B, n_chunks);
-    const int Bc = (B + n_chunks - 1) / n_chunks, Dc = m->dims.dim_continuous, S = m->dims.vocab_size;
+    const int Bc = (B + n_chunks - 1) / n_chunks, Dc = m->dims.dim_continuous;
     const HostChunkLayout lay(m, Bc, N, st->n_steps, precision);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     int* d_bad = reinterpret_cast<int*>(ws);

@@ -124,9 +124,16 @@ static_assert(team_barrier(2, kW / 2 - 1) <= 15, "too many warps per CTA for one
 struct MmaParams {
     const uint8_t* image;
     int L, skip;
-    float* x;
-    uint8_t* k;
+    float* x;                // [B,N,Dc] in/out (device); HOSTIO: the OUTPUT buffer, page-locked host memory mapped into the device
+    uint8_t* k;              // [B,N] in/out (device); unused with HOSTIO
     const uint8_t* mask;
+    // HOSTIO (mmb_generate_host, direct mode): the kernel reads the source state of a jet straight from the caller's page-locked
+    // host buffers when a warp claims the jet, and writes the final state straight back — int64 tokens as the reference holds
+    // them — so the PCIe traffic of a jet hides under the solver steps of the others, with no staging copy and no slicing
+    const float* x_in;       // [B,N,Dc] host
+    const long long* k_in;   // [B,N] host, int64
+    long long* k_out;        // [B,N] host, int64
+    int* bad_tokens;         // device flag: a token of a live particle was outside [0, S)
     const float* step_tab;   // [n_steps][4] (bc, cc, sp, t)
     int n_steps;
     float dt;
@@ -150,7 +157,7 @@ __device__ __forceinline__ void vec_frag(uint32_t (&a)[4], float v00, float v01,
     a[3] = dup ? a[2] : 0u;
 }
 
-template <int DC, int S, int SH, int GT>
+template <int DC, int S, int SH, int GT, bool HOSTIO>
 __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kernel(const MmaParams p) {
     using LY = Lay<GT>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -200,13 +207,39 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
         constexpr bool TWO = NMT > 2;   // this lane owns a second particle
         float xs0[DC], xs1[DC];
         int kk0 = 0, kk1 = 0;
+        // Features of the slice: rows are 12 B apart, so per-lane scalar accesses touch every 32-byte sector three times —
+        // harmless in HBM, a 3x cost over PCIe (direct mode).  With N % 4 == 0 the rows of a slice form whole 16-byte chunks:
+        // the warp moves them as float4 through the staging tile.
+        const bool vec_io = (N & 3) == 0;
+        const float* xin = HOSTIO ? p.x_in : p.x;
+        if (vec_io) {
+            const int rows = min(16 * NMT, N - kRowsPerWarp * slice);
+            const float4* src = reinterpret_cast<const float4*>(xin + (jbase + (size_t)kRowsPerWarp * slice) * DC);
+            for (int i = lane; i < rows * DC / 4; i += 32) reinterpret_cast<float4*>(stage)[i] = __ldg(src + i);
+            __syncwarp();
+            const float* st = reinterpret_cast<const float*>(stage);
 #pragma unroll
-        for (int c = 0; c < DC; ++c) {
-            xs0[c] = live0 ? p.x[(jbase + n0) * DC + c] : 0.0f;
-            xs1[c] = (TWO && live1) ? p.x[(jbase + n1) * DC + c] : 0.0f;
+            for (int c = 0; c < DC; ++c) {
+                xs0[c] = live0 ? st[lane * DC + c] : 0.0f;
+                xs1[c] = (TWO && live1) ? st[(lane + 32) * DC + c] : 0.0f;
+            }
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int c = 0; c < DC; ++c) {
+                xs0[c] = live0 ? xin[(jbase + n0) * DC + c] : 0.0f;
+                xs1[c] = (TWO && live1) ? xin[(jbase + n1) * DC + c] : 0.0f;
+            }
         }
-        if (live0) kk0 = p.k[jbase + n0];
-        if (TWO && live1) kk1 = p.k[jbase + n1];
+        if constexpr (HOSTIO) {
+            const long long q0 = live0 ? p.k_in[jbase + n0] : 0, q1 = (TWO && live1) ? p.k_in[jbase + n1] : 0;
+            if (q0 < 0 || q0 >= S || q1 < 0 || q1 >= S) atomicOr(p.bad_tokens, 1);   // the reference asserts (bridges.py:111-115)
+            kk0 = (int)q0 & (S - 1);
+            kk1 = (int)q1 & (S - 1);
+        } else {
+            if (live0) kk0 = p.k[jbase + n0];
+            if (TWO && live1) kk1 = p.k[jbase + n1];
+        }
         // row masks of this thread's fragment rows, as multipliers of the pooling sums: [mt][hh] = row 16 mt + 8 hh + g
         float mk[NMT][2];
 #pragma unroll
@@ -494,20 +527,46 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
             __syncwarp();   // the staging tile becomes the A tile of the next step
         }
         // ---- final state: live particles as computed, dead ones 0 (x * mask, k * mask)
+        if (vec_io) {
+            float* st = reinterpret_cast<float*>(stage);
+#pragma unroll
+            for (int c = 0; c < DC; ++c) {
+                st[lane * DC + c] = live0 ? xs0[c] : 0.0f;
+                st[(lane + 32) * DC + c] = (TWO && live1) ? xs1[c] : 0.0f;
+            }
+            __syncwarp();
+            const int rows = min(kRowsPerWarp, N - kRowsPerWarp * slice);
+            float4* dst = reinterpret_cast<float4*>(p.x + (jbase + (size_t)kRowsPerWarp * slice) * DC);
+            for (int i = lane; i < rows * DC / 4; i += 32) dst[i] = reinterpret_cast<const float4*>(stage)[i];
+            __syncwarp();
+        } else {
+            if (n0 < N)
+#pragma unroll
+                for (int c = 0; c < DC; ++c) p.x[(jbase + n0) * DC + c] = live0 ? xs0[c] : 0.0f;
+            if (n1 < N)   // NMT <= 2: rows 32-63 of the slice are dead
+#pragma unroll
+                for (int c = 0; c < DC; ++c) p.x[(jbase + n1) * DC + c] = (TWO && live1) ? xs1[c] : 0.0f;
+        }
         if (n0 < N) {
-#pragma unroll
-            for (int c = 0; c < DC; ++c) p.x[(jbase + n0) * DC + c] = live0 ? xs0[c] : 0.0f;
-            p.k[jbase + n0] = (uint8_t)(live0 ? kk0 : 0);
+            if constexpr (HOSTIO) p.k_out[jbase + n0] = live0 ? kk0 : 0;
+            else p.k[jbase + n0] = (uint8_t)(live0 ? kk0 : 0);
         }
-        if (n1 < N) {   // NMT <= 2: rows 32-63 of the slice are dead
-#pragma unroll
-            for (int c = 0; c < DC; ++c) p.x[(jbase + n1) * DC + c] = (TWO && live1) ? xs1[c] : 0.0f;
-            p.k[jbase + n1] = (uint8_t)((TWO && live1) ? kk1 : 0);
+        if (n1 < N) {
+            if constexpr (HOSTIO) p.k_out[jbase + n1] = (TWO && live1) ? kk1 : 0;
+            else p.k[jbase + n1] = (uint8_t)((TWO && live1) ? kk1 : 0);
         }
-        for (int m = kRowsPerWarp * cls + 32 * slice + lane; m < N; m += 32 * cls) {   // rows past the last live particle have no warp
+        // rows past the last live particle have no warp: the team zeroes them
+        const int tail0 = kRowsPerWarp * cls;
+        if (vec_io) {
+            float4* dst = reinterpret_cast<float4*>(p.x + (jbase + (size_t)tail0) * DC);
+            for (int i = 32 * slice + lane; i < (N - tail0) * DC / 4; i += 32 * cls) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int m = tail0 + 32 * slice + lane; m < N; m += 32 * cls) {
+            if (!vec_io)
 #pragma unroll
-            for (int c = 0; c < DC; ++c) p.x[(jbase + m) * DC + c] = 0.0f;
-            p.k[jbase + m] = 0;
+                for (int c = 0; c < DC; ++c) p.x[(jbase + m) * DC + c] = 0.0f;
+            if constexpr (HOSTIO) p.k_out[jbase + m] = 0;
+            else p.k[jbase + m] = 0;
         }
     };
     if ((bal1 >> 16) != 0u) run(std::integral_constant<int, 4>{});
@@ -563,7 +622,7 @@ __global__ void __launch_bounds__(kPrologueThreads) mma_prologue_kernel(const fl
                                                                         const float* __restrict__ temb, int n_steps, float4* __restrict__ tvec,
                                                                         const uint8_t* __restrict__ mask, int B, int N, int32_t* __restrict__ counts,
                                                                         int32_t* __restrict__ lists, int32_t* __restrict__ jet_cnt,
-                                                                        float* __restrict__ x, uint8_t* __restrict__ k) {
+                                                                        float* __restrict__ x, uint8_t* __restrict__ k, long long* __restrict__ k64) {
     const int T = d.dim_time_emb, C = d.dim_cont_emb, D = d.dim_disc_emb, H = d.dim_hidden_local, G = d.dim_hidden_glob, L = d.num_blocks;
     if ((int)blockIdx.x < n_steps) {
         __shared__ float s_vec[2 + 2 * kMaxL][16];
@@ -632,7 +691,8 @@ __global__ void __launch_bounds__(kPrologueThreads) mma_prologue_kernel(const fl
     if (cls == 0) {
         const float nan = __int_as_float(0x7fc00000);
         for (int i = 0; i < N * d.dim_continuous; ++i) x[(size_t)jet * N * d.dim_continuous + i] = nan;
-        for (int i = 0; i < N; ++i) k[(size_t)jet * N + i] = 0;
+        if (k64) for (int i = 0; i < N; ++i) k64[(size_t)jet * N + i] = 0;
+        else for (int i = 0; i < N; ++i) k[(size_t)jet * N + i] = 0;
     }
 }
 
@@ -761,7 +821,7 @@ size_t smem_bytes(int L) {
 template <int DC, int S, int SH, int GT>
 int launch_kernel(const MmaParams& p, int grid, cudaStream_t stream) {
     const size_t bytes = smem_bytes<GT>(p.L);
-    auto kern = epic_mma_generate_kernel<DC, S, SH, GT>;
+    auto kern = p.x_in ? epic_mma_generate_kernel<DC, S, SH, GT, true> : epic_mma_generate_kernel<DC, S, SH, GT, false>;
     if (int rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "mma smem attribute")) return rc;
     kern<<<grid, kW * 32, bytes, stream>>>(p);
     return cuda_ok(cudaGetLastError(), "epic_mma launch");
@@ -802,7 +862,7 @@ size_t mma_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B) {
 
 int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
                         int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
-                        int B, int N, cudaStream_t stream) {
+                        int B, int N, cudaStream_t stream, const MmaHostIO* host) {
     if (B == 0 || n_steps == 0) return MMB_OK;
     if (!m->mma_image_f16) return fail(MMB_EUNSUPPORTED, "warp-MMA engine: no operand image for this model");
     if ((reinterpret_cast<uintptr_t>(scratch) & 15) != 0) return fail(MMB_EINVAL, "mmb_generate: workspace must be 16-byte aligned");
@@ -810,6 +870,9 @@ int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t*
     p.image = static_cast<const uint8_t*>(m->mma_image_f16);
     p.L = m->dims.num_blocks; p.skip = m->dims.skip_connection;
     p.x = x; p.k = k; p.mask = mask;
+    if (host) {   // direct mode: sources from / results to mapped host memory
+        p.x = host->x_out; p.k = nullptr; p.x_in = host->x_in; p.k_in = host->k_in; p.k_out = host->k_out; p.bad_tokens = host->bad_tokens;
+    }
     p.step_tab = dev_table;
     p.n_steps = n_steps; p.dt = dt; p.u_jump = u_jump; p.seed = seed; p.jet_offset = jet_offset;
     p.B = B; p.N = N;
@@ -821,7 +884,7 @@ int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t*
     const int bin_blocks = (B + kPrologueThreads - 1) / kPrologueThreads;
     mma_prologue_kernel<<<n_steps + bin_blocks, kPrologueThreads, 0, stream>>>(m->w, m->layout, m->dims, dev_table + (size_t)n_steps * 4, n_steps,
                                                                                 reinterpret_cast<float4*>(scratch), mask, B, N, counts, lists,
-                                                                                jet_cnt, x, k);
+                                                                                jet_cnt, p.x, k, host ? host->k_out : nullptr);
     if (int rc = cuda_ok(cudaGetLastError(), "mma prologue launch")) return rc;
     p.tvec = reinterpret_cast<const float4*>(scratch); p.counts = counts; p.cursors = cursors; p.lists = lists; p.jet_cnt = jet_cnt;
     // Persistent grid: MMB_MMA_MINB CTAs per SM at most.  Any grid finishes any amount of work (warps claim jets until the

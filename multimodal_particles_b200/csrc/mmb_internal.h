@@ -132,8 +132,15 @@ int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* 
 bool mma_supported(const MmbEpicDims* d, int N);
 int mma_build_images(EpicModel* m, const float* packed_host);
 size_t mma_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B);
+struct MmaHostIO {          // direct mode of mmb_generate_host: device-visible addresses of the caller's page-locked host buffers
+    const float* x_in;      // [B,N,Dc]
+    const long long* k_in;  // [B,N] int64
+    float* x_out;           // [B,N,Dc]
+    long long* k_out;       // [B,N] int64
+    int* bad_tokens;        // DEVICE flag
+};
 int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
                         int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
-                        int B, int N, cudaStream_t stream);
+                        int B, int N, cudaStream_t stream, const MmaHostIO* host = nullptr);
 
 }  // namespace mmb

@@ -105,8 +105,11 @@ class MultiModalBridgeMatching(_ModuleBase):
         self.loss_multihead = MultiHeadLoss(number_of_losses=2)
         self.precision = precision
         self.seed = 0           # Philox key of simulate_dynamics when no uniforms are injected
-        self.pipeline_chunks = 2        # host -> host calls are cut into this many slices of jets on their own streams ...
-        self.pipeline_min_jets = 1024   # ... when each slice has at least this many jets
+        # host -> host calls: 0 = direct mode (the generation kernel reads / writes the caller's page-locked buffers itself;
+        # f16 engine, pinned tensors — anything else falls back to two slices); n > 0 = n slices of jets on their own streams,
+        # when each slice has at least pipeline_min_jets jets
+        self.pipeline_chunks = 0
+        self.pipeline_min_jets = 1024
         self._jets_generated = 0
         self.save_hyperparameters()
 
@@ -142,13 +145,14 @@ class MultiModalBridgeMatching(_ModuleBase):
         model = self.encoder.native_model(device)
         on_host = (state.continuous.device.type == "cpu" and k64.device.type == "cpu" and state.absorbing.device.type == "cpu")
         if on_host and uniforms is None and not return_device:
-            # Host state in, host state out (what Trainer.predict does): ONE library call runs the sliced pipeline — H2D of
-            # slice c+1 and D2H of slice c-1 under the solver steps of slice c, tokens / masks narrowed and widened on the
-            # device, the reference's token-range assertion (bridges.py:111-115) evaluated there too.  Philox is keyed by the
-            # global jet index, so the jets are bit-identical to an unsliced call.
+            # Host state in, host state out (what Trainer.predict does): ONE library call.  Direct mode: the kernel reads each
+            # jet from the page-locked input and writes it to the page-locked output itself.  Sliced mode: H2D of slice c+1
+            # and D2H of slice c-1 under the solver steps of slice c, tokens / masks narrowed and widened on the device.
+            # Either way the reference's token-range assertion (bridges.py:111-115) is evaluated on the device, and Philox is
+            # keyed by the global jet index, so the jets are bit-identical whatever the mode.
             if jet_offset is None:
                 jet_offset = next_jet_offset(self, B)
-            chunks = self.pipeline_chunks if B >= self.pipeline_chunks * self.pipeline_min_jets else 1
+            chunks = self.pipeline_chunks if B >= self.pipeline_chunks * self.pipeline_min_jets else 1   # 0 stays 0: direct mode
             x_host, k_host, flag, keep = model.generate_host(state.continuous, k64.reshape(B, N, 1), state.absorbing.reshape(B, N, 1), table,
                                                              seed=self.seed, jet_offset=jet_offset, chunks=chunks,
                                                              precision=precision or self.precision)

@@ -157,3 +157,36 @@ def test_empty_jets_are_nan_like_the_reference_and_leave_their_neighbours_alone(
     # an empty jet alone
     alone = model.simulate_dynamics(mk(slice(5, 6)), None, precision=precision, jet_offset=105)
     assert torch.isnan(alone.continuous).all() and (alone.discrete == 0).all()
+
+
+def test_host_pipeline_modes_give_identical_jets():
+    """simulate_dynamics with host tensors: direct mode (pinned buffers, the f16 kernel reads / writes them itself), sliced
+    modes and the device-resident call produce the same jets bit for bit; the token-range assertion fires in every mode."""
+    cfg, model = sharp_model(30, seed=5)
+    b = jetclass_like_databatch(3000, generator=torch.Generator().manual_seed(31))
+    model.seed, model.pipeline_min_jets = 9, 1
+    pin = lambda t: t.clone().pin_memory()
+    mk = lambda pinned: HybridState(None, *(pin(t) if pinned else t.clone() for t in (b.source_continuous, b.source_discrete, b.source_mask)))
+    dev_state = HybridState(None, b.source_continuous.to(DEV), b.source_discrete.to(DEV), b.source_mask.to(DEV))
+    ref = model.simulate_dynamics(dev_state, None, precision="f16", jet_offset=50, return_device=True)
+    for chunks, pinned in ((0, True), (0, False), (1, True), (3, True), (2, False)):
+        model.pipeline_chunks = chunks
+        out = model.simulate_dynamics(mk(pinned), None, precision="f16", jet_offset=50)
+        assert out.continuous.device.type == "cpu" and out.discrete.dtype == torch.int64 and out.discrete.shape == (3000, 128, 1)
+        assert torch.equal(out.continuous, ref.continuous.cpu()) and torch.equal(out.discrete, ref.discrete.cpu()), (chunks, pinned)
+    # empty jets through the direct mode: NaN features, zero tokens (written by the binning prologue)
+    st = mk(True)
+    st.absorbing[7] = 0
+    model.pipeline_chunks = 0
+    out = model.simulate_dynamics(st, None, precision="f16", jet_offset=50)
+    assert torch.isnan(out.continuous[7]).all() and (out.discrete[7] == 0).all() and torch.equal(out.continuous[8], ref.continuous[8].cpu())
+    for chunks in (0, 2):
+        model.pipeline_chunks = chunks
+        bad = mk(True)
+        bad.discrete[17, 3, 0] = 8
+        with pytest.raises(AssertionError):
+            model.simulate_dynamics(bad, None, precision="f16", jet_offset=50)
+        bad = mk(True)
+        bad.discrete[17, 120, 0] = -1      # a dead particle's token: the reference asserts on every entry
+        with pytest.raises(AssertionError):
+            model.simulate_dynamics(bad, None, precision="f16", jet_offset=50)

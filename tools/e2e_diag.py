@@ -10,7 +10,7 @@ batch = bench.source_batch(B, 1234)
 pin = lambda t: t.clone().pin_memory()
 model.precision = sys.argv[2] if len(sys.argv) > 2 else "auto"
 ref = None
-for chunks in (1, 2, 3, 4, 8):
+for chunks in (1, 2, 4, 0):
     model.pipeline_chunks, model.pipeline_min_jets = chunks, 1
     times, keep = [], []
     for i in range(12):
