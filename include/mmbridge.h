@@ -296,9 +296,17 @@ typedef struct MmbAbsorbHead MmbAbsorbHead;
 int mmb_absorb_head_create(int hidden, int transformer_dim, int n_heads, int n_blocks, const float* packed, size_t n_floats,
                            int device, MmbAbsorbHead** out);
 void mmb_absorb_head_destroy(MmbAbsorbHead* head);
-/* hidden [B,N,H] (EPiC last local hidden), mask [B,N] u8 -> logit_out [B,N] (heads.absorbing[...,0]) */
+/*
+ * hidden [B,N,H] (EPiC last local hidden), mask [B,N] u8 -> logit_out [B,N] (heads.absorbing[...,0]).
+ * The reference runs the stack over all N slots, padded ones included (no attention mask, GroupNorm over every slot).  With a
+ * workspace of mmb_absorb_head_workspace_bytes(B) bytes (device, 4-byte aligned) the kernel computes the identical padded
+ * slots of a jet ONCE (a representative row carrying the weight n_dead in every sum over slots — exact) and packs several jets
+ * into one 128-row tile with block-diagonal attention; jets whose padded slots do not hold identical inputs keep one row per
+ * slot.  workspace = NULL: one jet per tile, one row per slot.
+ */
+size_t mmb_absorb_head_workspace_bytes(int B);
 int mmb_absorb_head_forward(const MmbAbsorbHead* head, const float* hidden, const uint8_t* mask, const float* tbias,
-                            int tbias_stride, int B, int N, float* logit_out, void* stream);
+                            int tbias_stride, int B, int N, float* logit_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Whole generation loop of the absorbing flow: per step trunk + discrete head (mmb_epic_forward with the last

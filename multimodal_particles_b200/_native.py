@@ -99,7 +99,8 @@ SIGNATURES = {
     "mmb_philox_uniforms": (_i, [_vp, _u64, _u64, _i, _i, _i, _vp]),
     "mmb_absorb_head_create": (_i, [_i, _i, _i, _i, _vp, _sz, _i, ctypes.POINTER(_vp)]),
     "mmb_absorb_head_destroy": (None, [_vp]),
-    "mmb_absorb_head_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "mmb_absorb_head_workspace_bytes": (_sz, [_i]),
+    "mmb_absorb_head_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "mmb_generate_absorbing_workspace_bytes": (_sz, [_vp, _vp, _i, _i, _i]),
     "mmb_generate_absorbing": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _vp, _vp, _u64, _u64, _i, _i,
                                     _vp, _sz, _i, _vp]),
@@ -312,16 +313,19 @@ class AbsorbHead:
             _lib.mmb_absorb_head_destroy(self._handle)
             self._handle = None
 
-    def forward(self, hidden, mask_u8, tbias):
-        """hidden [B,N,H] f32, mask [B,N] u8, tbias [B or 1, n_blocks, C] -> rate logits [B,N]"""
+    def forward(self, hidden, mask_u8, tbias, pack=True):
+        """hidden [B,N,H] f32, mask [B,N] u8, tbias [B or 1, n_blocks, C] -> rate logits [B,N].  ``pack``: padded slots once,
+        several jets per tile (exact); False = one jet per tile, one row per slot."""
         hidden, tbias = hidden.contiguous(), tbias.contiguous()
         _require_cuda(hidden, mask_u8, tbias)
         B, N, _ = hidden.shape
         out = torch.empty(B, N, device=hidden.device, dtype=torch.float32)
         stride = 0 if tbias.shape[0] == 1 and B != 1 else self.n_blocks * self.dim
+        lib = load()
+        ws = torch.empty(max(lib.mmb_absorb_head_workspace_bytes(B), 16), device=hidden.device, dtype=torch.uint8) if pack else None
         with torch.cuda.device(hidden.device):
-            check(load().mmb_absorb_head_forward(self._handle, _ptr(hidden), _ptr(mask_u8), _ptr(tbias), stride, B, N, _ptr(out),
-                                                 _stream()))
+            check(lib.mmb_absorb_head_forward(self._handle, _ptr(hidden), _ptr(mask_u8), _ptr(tbias), stride, B, N, _ptr(out),
+                                              _ptr(ws), ws.numel() if pack else 0, _stream()))
         return out
 
 

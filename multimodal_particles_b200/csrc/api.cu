@@ -569,12 +569,15 @@ int mmb_absorb_head_create(int hidden, int transformer_dim, int n_heads, int n_b
 
 void mmb_absorb_head_destroy(MmbAbsorbHead* h) { absorb_head_destroy(reinterpret_cast<AbsorbHead*>(h)); }
 
+size_t mmb_absorb_head_workspace_bytes(int B) { return B < 0 ? 0 : tf_pack_scratch_ints(B) * sizeof(int32_t); }
+
 int mmb_absorb_head_forward(const MmbAbsorbHead* head, const float* hidden, const uint8_t* mask, const float* tbias,
-                            int tbias_stride, int B, int N, float* logit_out, void* stream) {
+                            int tbias_stride, int B, int N, float* logit_out, void* workspace, size_t workspace_bytes, void* stream) {
     if (!head || !hidden || !mask || !tbias || !logit_out) return fail(MMB_EINVAL, "mmb_absorb_head_forward: null argument");
     if (B < 0 || N < 0) return fail(MMB_EINVAL, "mmb_absorb_head_forward: negative size");
+    if (workspace && workspace_bytes < mmb_absorb_head_workspace_bytes(B)) return fail(MMB_ENOMEM, "mmb_absorb_head_forward: workspace too small");
     return launch_absorb_head(reinterpret_cast<const AbsorbHead*>(head), hidden, mask, tbias, tbias_stride, B, N, logit_out,
-                              static_cast<cudaStream_t>(stream));
+                              static_cast<cudaStream_t>(stream), static_cast<int32_t*>(workspace), workspace ? workspace_bytes / sizeof(int32_t) : 0);
 }
 
 // workspace of mmb_generate_absorbing (floats): v | logits | hidden | a | uj | ua   (the step table and the time biases are
@@ -582,7 +585,7 @@ int mmb_absorb_head_forward(const MmbAbsorbHead* head, const float* hidden, cons
 static size_t absorbing_ws_floats(const EpicModel* m, const AbsorbHead* h, int B, int N, int n_steps) {
     (void)h; (void)n_steps;
     const size_t P = (size_t)B * N;
-    return P * (m->dims.dim_continuous + m->dims.vocab_size + m->dims.dim_hidden_local + 3) + 64;
+    return P * (m->dims.dim_continuous + m->dims.vocab_size + m->dims.dim_hidden_local + 3) + 64 + tf_pack_scratch_ints(B) + 16;
 }
 
 size_t mmb_generate_absorbing_workspace_bytes(const MmbEpicModel* model, const MmbAbsorbHead* head, int B, int N, int n_steps) {
@@ -627,10 +630,11 @@ int mmb_generate_absorbing(const MmbEpicModel* model, const MmbAbsorbHead* head,
     float* alog = hidden + P * H;
     float* uj = alog + P;
     float* ua = uj + P;
+    int32_t* pack = reinterpret_cast<int32_t*>(ua + P + 16);
     for (int i = 0; i < n; ++i) {
         // heads from the OLD mask (absorbing_flows.py:270), then birth -> Euler -> jump with the new one (:271-273)
         int rc = mmb_epic_forward(model, x, k, mask, temb_dev + (size_t)i * T, 0, B, N, v, logits, hidden, precision, stream);
-        if (!rc) rc = launch_absorb_head(h, hidden, mask, tb_dev + (size_t)i * nblk * 128, 0, B, N, alog, s);
+        if (!rc) rc = launch_absorb_head(h, hidden, mask, tb_dev + (size_t)i * nblk * 128, 0, B, N, alog, s, pack, tf_pack_scratch_ints(B));
         const float* pj = u_jump ? u_jump + (size_t)i * P : uj;
         const float* pa = u_absorb ? u_absorb + (size_t)i * P : ua;
         if (!rc && !u_jump) rc = launch_philox_uniforms(uj, seed, jet_offset, 0, i, 1, B, N, s);

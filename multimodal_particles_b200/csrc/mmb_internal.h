@@ -70,7 +70,10 @@ struct TfStackIO {
     int tbias_stride;
     float* dot_out;           // [B,N]
     float* jet_out;           // [B][128] means of X over the slots (input of launch_jet_head) or null
+    int32_t* pack_scratch;    // tf_pack_scratch_ints(B) ints of device memory: the kernel then computes padded slots once and packs
+    size_t pack_scratch_ints; // several jets into a tile; null = one jet per tile, one row per slot
 };
+size_t tf_pack_scratch_ints(int B);
 int tf_stack_build(TfStack* st, const float* proj_in, int Cin, const float* blocks, int n_blocks, const float* dot_w, float dot_c,
                    const float* jet_w, const float* jet_b, int n_jet);
 void tf_stack_free(TfStack* st);
@@ -85,7 +88,7 @@ void absorb_head_destroy(AbsorbHead* h);
 int absorb_head_hidden(const AbsorbHead* h);
 int absorb_head_blocks(const AbsorbHead* h);
 int launch_absorb_head(const AbsorbHead* h, const float* hidden, const uint8_t* mask, const float* tbias, int tbias_stride,
-                       int B, int N, float* logit_out, cudaStream_t stream);
+                       int B, int N, float* logit_out, cudaStream_t stream, int32_t* pack_scratch = nullptr, size_t pack_scratch_ints = 0);
 
 // histograms.cu
 int launch_validation_histograms(const float* x, const uint8_t* k, const uint8_t* mask, int B, int N, int Dc, int S,

@@ -625,7 +625,7 @@ inline size_t align64(size_t n) { return (n + 63) & ~(size_t)63; }
 // workspace carve-up shared by the forward and the sampler (in floats, every region 256-byte aligned)
 struct TransWs {
     size_t k, mask, M, Z, pmax, psum, means, temb, tb1, tb2, v, logits, hidden, near_logits, vec_w, x0_logits, post_auto, nearest, new_mean, new_std, rate,
-        u_near, ts, norm_s, norm_n, coef, mask_dims, total;
+        u_near, ts, norm_s, norm_n, coef, mask_dims, pack, pack_ints, total;
     TransWs(const MmbEpicDims& e, const MmbTransDims& d, int B, int N, int n_time) {
         const size_t P = (size_t)B * N, F = 3 + d.vocab_size;
         size_t at = 0;
@@ -642,6 +642,7 @@ struct TransWs {
         post_auto = take((size_t)B * (2 * d.vocab_size + 1)); nearest = take(B); new_mean = take((size_t)B * F);
         new_std = take((size_t)B * F); rate = take(B); u_near = take(B); ts = take(n_time);
         norm_s = take(B); norm_n = take(B); coef = take(4); mask_dims = take(B);
+        pack_ints = tf_pack_scratch_ints(B); pack = take(pack_ints);   // jet packing of the transformer stacks (int32)
         total = at;
     }
 };
@@ -775,6 +776,7 @@ static int trans_eval(const EpicModel* m, const TransHeads* h, const float* x, c
     TfStackIO io{};
     io.mode = 1; io.H = H; io.S = S; io.hidden = ws + L.hidden; io.mask = mask; io.onehot = onehot;
     io.tbias = tb1; io.tbias_stride = time_stride ? nb * kC : 0; io.dot_out = nl; io.jet_out = ws + L.means;
+    io.pack_scratch = reinterpret_cast<int32_t*>(ws + L.pack); io.pack_scratch_ints = L.pack_ints;
     if ((rc = launch_tf_stack(&h->s1, h->sm_count, io, B, N, s))) return rc;
     if ((rc = launch_jet_head(&h->s1, ws + L.means, B, x0l, s))) return rc;
     trans_rate_kernel<<<(B + 3) / 4, 128, 0, s>>>(x0l, nl, dims, ts, ts_stride, nearest_in, u_nearest, fr, h->logfact, B, N, R, ws + L.rate, nearest);
