@@ -658,20 +658,12 @@ __global__ void __launch_bounds__(kThreads, 1) absorb_head_tc_kernel(const HeadP
         __syncthreads();
         { TileState* tmp = ts; ts = tn; tn = tmp; }
         const int next_tile = tile + (int)gridDim.x;
-#ifdef STK_X_NOHOOK
-        const bool has_next = false;
-#else
         const bool has_next = next_tile < n_tiles;
-#endif
         if (has_next) desc_issue(next_tile);
-#ifdef STK_X_NOSEG
-        seg = 0; seg_first = 0; seg_nq = 4; w_row = 1.0f;
-#else
         seg = ts->qseg[qq];
         seg_first = seg >= 0 ? ts->seg_q0[seg] : qq;
         seg_nq = seg >= 0 ? ts->seg_nq[seg] : 1;
         w_row = ts->w[r];
-#endif
         const int slot = ts->slot[r];
         // ---- proj_in: mode 0 [hidden, one_hot(mask)] (absorbing_flows.py:113-118); mode 1 [hidden, onehot]
         //      (transdimensional_model.py:295-303); mode 2 mask * [hidden, onehot, distance to the nearest particle,
