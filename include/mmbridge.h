@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MMB_ABI_VERSION 2
+#define MMB_ABI_VERSION 3
 
 enum {
     MMB_OK = 0,
@@ -59,7 +59,10 @@ enum {
  * reference constructors read (mp/models/architectures/epic.py:20-58,
  * mp/config_classes/multimodal_bridge_matching_config.py:23-91).
  * Supported: SinusoidalPositionalEncoding time embedding, Linear continuous embedding,
- * Embedding discrete embedding, no context features (every shipped config).
+ * Embedding discrete embedding.  Context features (epic.py:72-76, utils.py:155-170; zero in every shipped config): the
+ * reference concatenates [time embedding | embedded continuous context | embedded discrete context] into one per-jet
+ * `context` vector that enters global_0, fc_global1 and fc_local1.  dim_context is the width of the part after the time
+ * embedding; the caller applies the (tiny, per-jet) context embeddings and hands over the embedded vector.
  */
 typedef struct MmbEpicDims {
     int32_t dim_continuous;    /* Dc  data.dim_features_continuous */
@@ -74,6 +77,7 @@ typedef struct MmbEpicDims {
     int32_t disc_head_hidden;  /* Sh: 0 = no discrete head; S for MultiModalEPiC.fc_layer
                                   (mp/.../multimodal_bridge_matching.py:90-100); 56 for
                                   AbsorbingGenerator.discrete_head_mlp (absorbing_flows.py:41-54) */
+    int32_t dim_context;       /* X   dim_emb_context_continuous + dim_emb_context_discrete (0: no context features) */
 } MmbEpicDims;
 
 /*
@@ -83,11 +87,11 @@ typedef struct MmbEpicDims {
  *   emb_cont  [C][Dc] + [C]
  *   emb_disc  [S][D]                      (embedding table, no bias)
  *   proj.local_0  [H][T+C+D] + [H]
- *   proj.global_0 [H][2H+T]  + [H]
+ *   proj.global_0 [H][2H+T+X] + [H]
  *   proj.global_1 [H][H]     + [H]
  *   proj.global_2 [G][H]     + [G]
- *   L x { fc_global1 [H][2H+G+T] + [H]; fc_global2 [G][H] + [G];
- *         fc_local1  [H][H+G+T]  + [H]; fc_local2  [H][H] + [H] }
+ *   L x { fc_global1 [H][2H+G+T+X] + [H]; fc_global2 [G][H] + [G];
+ *         fc_local1  [H][H+G+T+X]  + [H]; fc_local2  [H][H] + [H] }
  *   output_layer [Dc+S][H] + [Dc+S]
  *   if Sh: head0 [Sh][S] + [Sh]; head2 [S][Sh] + [S]
  */
@@ -106,13 +110,13 @@ static inline MmbEpicLayout mmb_epic_layout(const MmbEpicDims* d) {
     size_t o = 0;
     const size_t Dc = (size_t)d->dim_continuous, S = (size_t)d->vocab_size, T = (size_t)d->dim_time_emb,
                  C = (size_t)d->dim_cont_emb, D = (size_t)d->dim_disc_emb, H = (size_t)d->dim_hidden_local,
-                 G = (size_t)d->dim_hidden_glob, Sh = (size_t)d->disc_head_hidden;
+                 G = (size_t)d->dim_hidden_glob, Sh = (size_t)d->disc_head_hidden, X = (size_t)d->dim_context;
     L.emb_cont_w = o; o += C * Dc;
     L.emb_cont_b = o; o += C;
     L.emb_disc = o;   o += S * D;
     L.local0_w = o;   o += H * (T + C + D);
     L.local0_b = o;   o += H;
-    L.global0_w = o;  o += H * (2 * H + T);
+    L.global0_w = o;  o += H * (2 * H + T + X);
     L.global0_b = o;  o += H;
     L.global1_w = o;  o += H * H;
     L.global1_b = o;  o += H;
@@ -121,11 +125,11 @@ static inline MmbEpicLayout mmb_epic_layout(const MmbEpicDims* d) {
     L.layer0 = o;
     {
         size_t p = 0;
-        L.l_g1_w = p; p += H * (2 * H + G + T);
+        L.l_g1_w = p; p += H * (2 * H + G + T + X);
         L.l_g1_b = p; p += H;
         L.l_g2_w = p; p += G * H;
         L.l_g2_b = p; p += G;
-        L.l_l1_w = p; p += H * (H + G + T);
+        L.l_l1_w = p; p += H * (H + G + T + X);
         L.l_l1_b = p; p += H;
         L.l_l2_w = p; p += H * H;
         L.l_l2_b = p; p += H;
@@ -149,7 +153,7 @@ static inline MmbEpicLayout mmb_epic_layout(const MmbEpicDims* d) {
  * Per-solver-step scalars, computed ON THE HOST with the reference's own fp32 op order so that no
  * libm-vs-libdevice difference enters:
  *   t      network time of the step            (mp/.../multimodal_bridge_matching.py:203-211)
- *   temb   [T] sinusoidal embedding of t        (mp/models/architectures/utils.py:183-198)
+ *   temb   [T] sinusoidal embedding of t        (mp/models/architectures/utils.py:183-198; T = dim_time_emb, no context part)
  *   bc,cc  telegraph coefficients B=(w S)/(1-w), C=w, w=exp(-S gamma (1-t))  (bridges.py:125-130)
  *   sp     absorbing survival probability SP(t) (bridges.py:218-231); unused for MULTIMODAL
  * Arrays are HOST pointers of length n_steps (temb: n_steps*T); mmb_generate copies nothing — it
@@ -187,8 +191,10 @@ void mmb_epic_destroy(MmbEpicModel* m);
  * EPiCWrapper.forward(..., output_hidden_local=True) as AbsorbingGenerator.forward calls it
  * (absorbing_flows.py:153).
  *   x [B,N,Dc] f32, k [B,N] u8, mask [B,N] u8,
- *   temb [B,T] (temb_stride = T) or one row shared by all jets (temb_stride = 0),
+ *   temb [B,T+X] (temb_stride = T+X) or one row shared by all jets (temb_stride = 0): the time embedding followed,
+ *   when the model has context features, by the jet's embedded context (the reference's `context` vector, utils.py:166-170),
  *   v_out [B,N,Dc], logits_out [B,N,S]; hidden_out [B,N,H] nullable.
+ *   With context features MMB_PREC_FP32 only (MMB_PREC_BF16 returns MMB_EUNSUPPORTED).
  * An empty jet (mask all zero) produces NaN exactly as epic.py:141 does.
  */
 int mmb_epic_forward(const MmbEpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask,
@@ -230,6 +236,8 @@ int mmb_bridge_update(float* x, uint8_t* k, uint8_t* mask,
  *   has seen neither copies nor allocates.
  *   An empty jet (mask all zero) ends with NaN features and zero tokens in every precision, as the reference's division by
  *   the particle count gives (epic.py:141, bridges.py:42).
+ *   context: [B,X] f32 embedded context features of the jets (device; constant over the steps — batch.context_* of
+ *   mbm.py:143-144 through the context embeddings), NULL iff the model has none (X = 0).  MMB_PREC_FP32 and MMB_PREC_F16.
  */
 size_t mmb_generate_workspace_bytes(const MmbEpicModel* m, int B, int N, int precision);
 
@@ -239,7 +247,7 @@ size_t mmb_generate_workspace_bytes(const MmbEpicModel* m, int B, int N, int pre
  * MMB_PREC_BF16: N <= 128, MMB_PREC_F16: N <= 256).  The host shim's precision "auto" asks in the order F16, BF16, FP32.
  */
 int mmb_generate_supported(const MmbEpicModel* m, int N, int precision);
-int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mask,
+int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* context,
                  const MmbStepTable* steps, const float* u_jump,
                  uint64_t seed, uint64_t jet_offset, int B, int N,
                  void* workspace, size_t workspace_bytes, int precision, void* stream);
@@ -250,8 +258,8 @@ int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mas
  * The jets are cut into n_chunks slices that travel through internal streams: H2D of slice c+1 and D2H of slice c-1 run under
  * the solver steps of slice c; tokens / masks are narrowed to uint8 and widened back on the device; Philox is keyed by the
  * global jet index, so the result equals the unsliced call bit for bit.
- *   x_in, k_in, mask_in, x_out, k_out, bad_tokens: HOST pointers (page-locked for the copies to be asynchronous; x_out / k_out
- *   may alias x_in / k_in).  *bad_tokens becomes 1 if any input token lies outside [0, S) — the reference asserts that
+ *   x_in, k_in, mask_in, context_in (nullable, [B,X]), x_out, k_out, bad_tokens: HOST pointers (page-locked for the copies to
+ *   be asynchronous; x_out / k_out may alias x_in / k_in).  *bad_tokens becomes 1 if any input token lies outside [0, S) — the reference asserts that
  *   (bridges.py:111-115); the caller raises after synchronising.  In-kernel Philox only.
  *   n_chunks <= 0 selects the DIRECT mode (MMB_PREC_F16 with page-locked buffers; anything else falls back to two slices):
  *   no slicing and no staging copies of features or tokens — each warp of the generation kernel reads the source state of the
@@ -264,7 +272,7 @@ int mmb_generate(const MmbEpicModel* m, float* x, uint8_t* k, const uint8_t* mas
  */
 size_t mmb_generate_host_workspace_bytes(const MmbEpicModel* m, int B, int N, int n_steps, int n_chunks, int precision);
 int mmb_generate_host(const MmbEpicModel* m, const float* x_in, const int64_t* k_in, const int64_t* mask_in,
-                      const MmbStepTable* st, uint64_t seed, uint64_t jet_offset, int B, int N,
+                      const float* context_in, const MmbStepTable* st, uint64_t seed, uint64_t jet_offset, int B, int N,
                       float* x_out, int64_t* k_out, int32_t* bad_tokens, void* workspace, size_t workspace_bytes,
                       int n_chunks, int precision, void* stream);
 

@@ -33,7 +33,7 @@ class EpicDims(ctypes.Structure):
 
     _fields_ = [(n, ctypes.c_int32) for n in (
         "dim_continuous", "vocab_size", "dim_time_emb", "dim_cont_emb", "dim_disc_emb",
-        "dim_hidden_local", "dim_hidden_glob", "num_blocks", "skip_connection", "disc_head_hidden")]
+        "dim_hidden_local", "dim_hidden_glob", "num_blocks", "skip_connection", "disc_head_hidden", "dim_context")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -92,9 +92,9 @@ SIGNATURES = {
     "mmb_bridge_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _i, _i, _vp]),
     "mmb_generate_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "mmb_generate_supported": (_i, [_vp, _i, _i]),
-    "mmb_generate": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
+    "mmb_generate": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _vp, _u64, _u64, _i, _i, _vp, _sz, _i, _vp]),
     "mmb_generate_host_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i, _i]),
-    "mmb_generate_host": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _u64, _u64, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "mmb_generate_host": (_i, [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(CStepTable), _u64, _u64, _i, _i, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "mmb_jump_variants": (_i, [_vp, _vp, _vp, _f, _f, _f, _sz, _i, _vp, _vp, _vp, _vp]),
     "mmb_philox_uniforms": (_i, [_vp, _u64, _u64, _i, _i, _i, _vp]),
     "mmb_absorb_head_create": (_i, [_i, _i, _i, _i, _vp, _sz, _i, ctypes.POINTER(_vp)]),
@@ -181,14 +181,18 @@ class EpicModel:
             self._handle = None
 
     def forward(self, x, k_u8, mask_u8, temb, want_hidden=False, precision="fp32"):
-        """x [B,N,Dc] f32, k/mask [B,N] u8, temb [B,T] or [1,T] -> (v, logits[, hidden])."""
+        """x [B,N,Dc] f32, k/mask [B,N] u8, temb [B,T+X] or [1,T+X] (time embedding, then the jet's embedded context if the
+        model has context features) -> (v, logits[, hidden])."""
         _require_cuda(x, k_u8, mask_u8, temb)
         B, N, _ = x.shape
         d = self.dims
         v = torch.empty(B, N, d.dim_continuous, device=x.device, dtype=torch.float32)
         logits = torch.empty(B, N, d.vocab_size, device=x.device, dtype=torch.float32)
         hidden = torch.empty(B, N, d.dim_hidden_local, device=x.device, dtype=torch.float32) if want_hidden else None
-        stride = 0 if temb.shape[0] == 1 and B != 1 else d.dim_time_emb
+        width = d.dim_time_emb + d.dim_context
+        if temb.shape[-1] != width:
+            raise MmbError(f"context rows must hold {d.dim_time_emb} time + {d.dim_context} context entries, got {temb.shape[-1]}")
+        stride = 0 if temb.shape[0] == 1 and B != 1 else width
         with torch.cuda.device(x.device):
             check(load().mmb_epic_forward(self._handle, _ptr(x), _ptr(k_u8), _ptr(mask_u8), _ptr(temb), stride, B, N,
                                           _ptr(v), _ptr(logits), _ptr(hidden), PRECISIONS[precision], _stream()))
@@ -205,22 +209,34 @@ class EpicModel:
                 return name
         return "fp32"
 
-    def generate(self, x, k_u8, mask_u8, table, u_jump=None, seed=0, jet_offset=0, precision="auto"):
-        """In-place generation of x/k over all steps of ``table`` (StepTable)."""
-        _require_cuda(x, k_u8, mask_u8, u_jump)
+    def _context(self, context, B):
+        X = self.dims.dim_context
+        if (context is None) != (X == 0):
+            raise MmbError(f"the model has {X} context features, context {'missing' if context is None else 'given'}")
+        if context is None:
+            return None
+        if tuple(context.shape) != (B, X) or context.dtype != torch.float32 or not context.is_contiguous():
+            raise MmbError(f"context must be a contiguous float32 [{B}, {X}] tensor")
+        return context
+
+    def generate(self, x, k_u8, mask_u8, table, u_jump=None, seed=0, jet_offset=0, precision="auto", context=None):
+        """In-place generation of x/k over all steps of ``table`` (StepTable); ``context`` [B,X] f32: embedded context
+        features of the jets (models built with ``dim_context`` > 0)."""
+        _require_cuda(x, k_u8, mask_u8, u_jump, context)
         B, N, _ = x.shape
+        context = self._context(context, B)
         lib = load()
         prec = PRECISIONS[self.generate_precision(N, precision)]
         need = lib.mmb_generate_workspace_bytes(self._handle, B, N, prec)
         ws = torch.empty(max(need, 16), device=x.device, dtype=torch.uint8)
         ctable = CStepTable.from_table(table)
         with torch.cuda.device(x.device):
-            check(lib.mmb_generate(self._handle, _ptr(x), _ptr(k_u8), _ptr(mask_u8), ctypes.byref(ctable), _ptr(u_jump),
+            check(lib.mmb_generate(self._handle, _ptr(x), _ptr(k_u8), _ptr(mask_u8), _ptr(context), ctypes.byref(ctable), _ptr(u_jump),
                                    seed, jet_offset, B, N, _ptr(ws), ws.numel(), prec, _stream()))
         return x, k_u8
 
 
-    def generate_host(self, x_host, k64_host, m64_host, table, seed=0, jet_offset=0, chunks=0, precision="auto"):
+    def generate_host(self, x_host, k64_host, m64_host, table, seed=0, jet_offset=0, chunks=0, precision="auto", context=None):
         """Host state in the reference's layout (fp32 [B,N,Dc], int64 [B,N,1] tokens and masks) -> pinned host result
         (x [B,N,Dc] f32, k [B,N,1] int64, flag [1] int32: 1 = a token was out of range), asynchronous on the current stream of
         this model's device: ONE library call (direct mode for ``chunks=0``, else the sliced H2D / generate / D2H pipeline).
@@ -232,6 +248,9 @@ class EpicModel:
         prec = PRECISIONS[self.generate_precision(N, precision)]
         fix = lambda t, dt: t if (t.dtype == dt and t.is_contiguous()) else t.to(dt).contiguous()
         x_in, k_in, m_in = fix(x_host, torch.float32), fix(k64_host, torch.int64), fix(m64_host, torch.int64)
+        c_in = None if context is None else self._context(fix(context.reshape(B, -1), torch.float32), B)   # host [B,X]
+        if context is None:
+            self._context(None, B)
         # one page-locked block: [x f32 | k int64 | flag], 16-byte aligned parts
         nx, nk = B * N * Dc * 4, B * N * 8
         block = torch.empty(nx + nk + 16, dtype=torch.uint8, pin_memory=True)
@@ -250,11 +269,12 @@ class EpicModel:
         if ctable is None:
             ctable = table._ctable = CStepTable.from_table(table)
         stream = torch.cuda.current_stream(dev)
-        rc = lib.mmb_generate_host(self._handle, x_in.data_ptr(), k_in.data_ptr(), m_in.data_ptr(), ctypes.byref(ctable), seed, jet_offset, B, N,
+        rc = lib.mmb_generate_host(self._handle, x_in.data_ptr(), k_in.data_ptr(), m_in.data_ptr(), c_in.data_ptr() if c_in is not None else None,
+                                   ctypes.byref(ctable), seed, jet_offset, B, N,
                                    x_out.data_ptr(), k_out.data_ptr(), flag.data_ptr(), ws.data_ptr(), ws.numel(), chunks, prec,
                                    stream.cuda_stream)
         check(rc)
-        return x_out, k_out, flag, (x_in, k_in, m_in)   # the inputs must outlive the asynchronous copies
+        return x_out, k_out, flag, (x_in, k_in, m_in, c_in)   # the inputs must outlive the asynchronous copies
 
 
 def bridge_update(x, k_u8, mask_u8, v, logits, u_jump, dt, bc, cc, absorb_logit=None, u_absorb=None, sp=0.0,

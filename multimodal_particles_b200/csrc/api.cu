@@ -337,13 +337,16 @@ static size_t generate_ws_floats(const EpicModel* m, int n_steps, int B, int pre
     return precision == MMB_PREC_F16 ? mma_generate_scratch_floats(&m->dims, n_steps, B) : tc_generate_scratch_floats(&m->dims, n_steps, B);
 }
 
-int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t* mask,
+int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t* mask, const float* context,
                  const MmbStepTable* st, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                  int B, int N, void* workspace, size_t workspace_bytes, int precision, void* stream) {
     const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
     if (!m || !x || !k || !mask || !st || !workspace) return fail(MMB_EINVAL, "mmb_generate: null argument");
     if (!st->temb || !st->bc || !st->cc) return fail(MMB_EINVAL, "mmb_generate: incomplete step table");
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate: negative size");
+    if ((m->dims.dim_context > 0) != (context != nullptr))
+        return fail(MMB_EINVAL, "mmb_generate: the model has %d context features, context pointer %s", m->dims.dim_context,
+                    context ? "given" : "missing");
     const int T = m->dims.dim_time_emb, n = st->n_steps;
     if (workspace_bytes < generate_ws_floats(m, n, B, precision) * sizeof(float))
         return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B too small for %d steps", workspace_bytes, n);
@@ -358,7 +361,7 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
         return fail(MMB_ENOMEM, "mmb_generate: host-side failure while caching the step table");
     }
     if (precision == MMB_PREC_FP32)
-        return launch_generate_fp32(m, x, k, mask, table, n, st->dt, u_jump, seed, jet_offset, B, N, s);
+        return launch_generate_fp32(m, x, k, mask, context, table, n, st->dt, u_jump, seed, jet_offset, B, N, s);
     if (precision == MMB_PREC_BF16) {
         if (!m->tc_image || !tc_supported(&m->dims, N))
             return fail(MMB_EUNSUPPORTED, "tcgen05 path is built for H=16, G<=32, Dc+S<=16, head<=16, N<=128; use fp32");
@@ -367,20 +370,21 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     if (precision == MMB_PREC_F16) {
         if (!m->mma_image_f16 || !mma_supported(&m->dims, N))
             return fail(MMB_EUNSUPPORTED, "warp-MMA engine is built for H=16, G<=32, Dc=3, S in {4,8}, head in {0,S}, N<=256; use fp32");
-        return launch_generate_mma(m, x, k, mask, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N, s);
+        return launch_generate_mma(m, x, k, mask, context, table, static_cast<float*>(workspace), n, st->dt, u_jump, seed, jet_offset, B, N, s);
     }
     return fail(MMB_EINVAL, "unknown precision %d", precision);
 }
 
 // per-chunk device buffers of mmb_generate_host, each rounded up to 256 B: x f32 | k int64 | mask int64 | k u8 | mask u8 | scratch
 struct HostChunkLayout {
-    size_t x, k64, m64, k8, m8, scratch, total;
+    size_t x, k64, m64, k8, m8, ctx, scratch, total;
     HostChunkLayout(const EpicModel* m, int Bc, int N, int n_steps, int precision) {
         const size_t P = (size_t)Bc * N;
         size_t at = 0;
         auto take = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
         x = take(P * m->dims.dim_continuous * sizeof(float));
         k64 = take(P * 8); m64 = take(P * 8); k8 = take(P); m8 = take(P);
+        ctx = take((size_t)Bc * m->dims.dim_context * sizeof(float));
         scratch = take(generate_ws_floats(m, n_steps, Bc, precision) * sizeof(float));
         total = at;
     }
@@ -394,12 +398,13 @@ static int host_chunks(int B, int n_chunks) {
 
 // direct mode (n_chunks <= 0): flag | mask int64 | mask u8 | token int64 (range check only) | scratch
 struct HostDirectLayout {
-    size_t m64, m8, k64, scratch, total;
+    size_t m64, m8, k64, ctx, scratch, total;
     HostDirectLayout(const EpicModel* m, int B, int N, int n_steps) {
         const size_t P = (size_t)B * N;
         size_t at = 256;
         auto take = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
         m64 = take(P * 8); m8 = take(P); k64 = take(P * 8);
+        ctx = take((size_t)B * m->dims.dim_context * sizeof(float));
         scratch = take(mma_generate_scratch_floats(&m->dims, n_steps, B) * sizeof(float));
         total = at;
     }
@@ -428,13 +433,16 @@ static void* mapped_host_pointer(const void* host) {
 }
 
 int mmb_generate_host(const MmbEpicModel* handle, const float* x_in, const int64_t* k_in, const int64_t* mask_in,
-                      const MmbStepTable* st, uint64_t seed, uint64_t jet_offset, int B, int N,
+                      const float* context_in, const MmbStepTable* st, uint64_t seed, uint64_t jet_offset, int B, int N,
                       float* x_out, int64_t* k_out, int32_t* bad_tokens, void* workspace, size_t workspace_bytes,
                       int n_chunks, int precision, void* stream) {
     const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
     if (!m || !x_in || !k_in || !mask_in || !st || !x_out || !k_out || !bad_tokens || !workspace)
         return fail(MMB_EINVAL, "mmb_generate_host: null argument");
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate_host: negative size");
+    const int X = m->dims.dim_context;
+    if ((X > 0) != (context_in != nullptr))
+        return fail(MMB_EINVAL, "mmb_generate_host: the model has %d context features, context pointer %s", X, context_in ? "given" : "missing");
     if (workspace_bytes < mmb_generate_host_workspace_bytes(handle, B, N, st->n_steps, n_chunks, precision))
         return fail(MMB_ENOMEM, "mmb_generate_host: workspace too small");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return fail(MMB_EINVAL, "mmb_generate_host: workspace must be 256-byte aligned");
@@ -485,7 +493,9 @@ int mmb_generate_host(const MmbEpicModel* handle, const float* x_in, const int64
             }
             const MmaHostIO io{static_cast<const float*>(dx_in), static_cast<const long long*>(dk_in), static_cast<float*>(dx_out),
                                static_cast<long long*>(dk_out), d_bad};
-            if (!rc) rc = launch_generate_mma(m, nullptr, nullptr, dm8, table, reinterpret_cast<float*>(ws + lay.scratch), n, st->dt, nullptr, seed,
+            float* dctx = X ? reinterpret_cast<float*>(ws + lay.ctx) : nullptr;
+            if (!rc && X) rc = cuda_ok(cudaMemcpyAsync(dctx, context_in, (size_t)B * X * sizeof(float), cudaMemcpyHostToDevice, sa), "H2D context");
+            if (!rc) rc = launch_generate_mma(m, nullptr, nullptr, dm8, dctx, table, reinterpret_cast<float*>(ws + lay.scratch), n, st->dt, nullptr, seed,
                                               jet_offset, B, N, sa, &io);
             if (!rc) rc = cuda_ok(cudaEventRecord(hp->done[0], sa), "direct done");
             if (!rc) rc = cuda_ok(cudaMemcpyAsync(dk64, k_in, P * 8, cudaMemcpyHostToDevice, sb), "H2D tokens");
@@ -527,7 +537,10 @@ int mmb_generate_host(const MmbEpicModel* handle, const float* x_in, const int64
             narrow_state_kernel<<<(unsigned)((P / 2 + 256) / 256), 256, 0, cs>>>(dk64, dm64, dk8, dm8, P, S, d_bad);
             rc = cuda_ok(cudaGetLastError(), "narrow launch");
         }
-        if (!rc) rc = mmb_generate(handle, dx, dk8, dm8, st, nullptr, seed, jet_offset + (uint64_t)lo, hi - lo, N, base + lay.scratch,
+        float* dctx = X ? reinterpret_cast<float*>(base + lay.ctx) : nullptr;
+        if (!rc && X)
+            rc = cuda_ok(cudaMemcpyAsync(dctx, context_in + (size_t)lo * X, (size_t)(hi - lo) * X * sizeof(float), cudaMemcpyHostToDevice, cs), "H2D context");
+        if (!rc) rc = mmb_generate(handle, dx, dk8, dm8, dctx, st, nullptr, seed, jet_offset + (uint64_t)lo, hi - lo, N, base + lay.scratch,
                                    lay.total - lay.scratch, precision, cs);
         if (!rc) {
             widen_tokens_kernel<<<(unsigned)((P / 2 + 256) / 256), 256, 0, cs>>>(dk8, dk64, P);

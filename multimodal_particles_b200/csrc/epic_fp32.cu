@@ -18,6 +18,7 @@ constexpr int kThreads = 128;
 
 struct Fp32Dims {
     int Dc, S, T, C, D, H, G, L, skip, Sh;
+    int X;   // embedded context features behind the time embedding in the per-jet context vector (MmbEpicDims::dim_context)
     int HS;  // row stride of the per-particle hidden rows (odd: conflict-free private rows)
     int RS;  // row stride of the scratch rows: max(H, Sh, Dc+S, C), odd
 };
@@ -27,7 +28,7 @@ __host__ __device__ inline int imax(int a, int b) { return a > b ? a : b; }
 
 __host__ Fp32Dims make_dims(const MmbEpicDims& d) {
     Fp32Dims f{d.dim_continuous, d.vocab_size, d.dim_time_emb, d.dim_cont_emb, d.dim_disc_emb,
-               d.dim_hidden_local, d.dim_hidden_glob, d.num_blocks, d.skip_connection, d.disc_head_hidden, 0, 0};
+               d.dim_hidden_local, d.dim_hidden_glob, d.num_blocks, d.skip_connection, d.disc_head_hidden, d.dim_context, 0, 0};
     f.HS = odd(f.H);
     f.RS = odd(imax(imax(f.H, f.Sh), imax(f.Dc + f.S, f.C)));
     return f;
@@ -40,16 +41,16 @@ struct Smem {
 };
 
 __host__ __device__ inline size_t smem_floats(const Fp32Dims& f, int N) {
-    return (size_t)f.T + f.H + (2 * f.H + f.G + f.T) + f.H + f.H + f.G + f.G + f.H + 4 * f.H + 8 +
+    return (size_t)(f.T + f.X) + f.H + (2 * f.H + f.G + f.T + f.X) + f.H + f.H + f.G + f.G + f.H + 4 * f.H + 8 +
            (size_t)N * f.HS * 2 + (size_t)N * f.RS;
 }
 
 __device__ inline Smem carve(float* base, const Fp32Dims& f, int N) {
     Smem s;
     float* p = base;
-    s.temb = p; p += f.T;
+    s.temb = p; p += f.T + f.X;   // [time embedding | embedded context]: the reference's `context` vector (utils.py:166-170)
     s.pj = p; p += f.H;
-    s.pool = p; p += 2 * f.H + f.G + f.T;
+    s.pool = p; p += 2 * f.H + f.G + f.T + f.X;
     s.g0 = p; p += f.H;
     s.g1 = p; p += f.H;
     s.xg = p; p += f.G;
@@ -107,6 +108,7 @@ __device__ void epic_forward_jet(const float* __restrict__ W, const MmbEpicLayou
     const int tid = threadIdx.x;
     const int Dc = f.Dc, S = f.S, T = f.T, C = f.C, D = f.D, H = f.H, G = f.G, Sh = f.Sh;
     const int K0 = T + C + D;
+    const int TX = T + f.X;   // only the time part of s.temb is among the particle features (utils.py:139-145)
 
     // per-jet part of local_0, particle count
     for (int o = tid; o < H; o += kThreads)
@@ -145,10 +147,10 @@ __device__ void epic_forward_jet(const float* __restrict__ W, const MmbEpicLayou
         s.pool[o] = __fdiv_rn(s.sum[o], cnt);
         s.pool[H + o] = s.sum[o];
     }
-    for (int i = tid; i < T; i += kThreads) s.pool[2 * H + i] = s.temb[i];
+    for (int i = tid; i < TX; i += kThreads) s.pool[2 * H + i] = s.temb[i];
     __syncthreads();
     for (int o = tid; o < H; o += kThreads)
-        s.g0[o] = lrelu(dot_from(__ldg(W + Lo.global0_b + o), W + Lo.global0_w + (size_t)o * (2 * H + T), s.pool, 2 * H + T));
+        s.g0[o] = lrelu(dot_from(__ldg(W + Lo.global0_b + o), W + Lo.global0_w + (size_t)o * (2 * H + TX), s.pool, 2 * H + TX));
     __syncthreads();
     for (int o = tid; o < H; o += kThreads)
         s.g1[o] = lrelu(dot_from(__ldg(W + Lo.global1_b + o), W + Lo.global1_w + (size_t)o * H, s.g0, H));
@@ -177,9 +179,9 @@ __device__ void epic_forward_jet(const float* __restrict__ W, const MmbEpicLayou
             s.pool[H + o] = s.sum[o];
         }
         for (int i = tid; i < G; i += kThreads) s.pool[2 * H + i] = s.xg[i];
-        for (int i = tid; i < T; i += kThreads) s.pool[2 * H + G + i] = s.temb[i];
+        for (int i = tid; i < TX; i += kThreads) s.pool[2 * H + G + i] = s.temb[i];
         __syncthreads();
-        const int Kg = 2 * H + G + T;
+        const int Kg = 2 * H + G + TX;
         for (int o = tid; o < H; o += kThreads)
             s.g1[o] = lrelu(dot_from(__ldg(Wl + Lo.l_g1_b + o), Wl + Lo.l_g1_w + (size_t)o * Kg, s.pool, Kg));
         __syncthreads();
@@ -188,11 +190,11 @@ __device__ void epic_forward_jet(const float* __restrict__ W, const MmbEpicLayou
         __syncthreads();
         for (int o = tid; o < G; o += kThreads) s.xg[o] = s.g0[o];
         __syncthreads();
-        const int Kl = H + G + T;
+        const int Kl = H + G + TX;
         for (int o = tid; o < H; o += kThreads) {
             const float* w = Wl + Lo.l_l1_w + (size_t)o * Kl;
             float acc = dot_from(__ldg(Wl + Lo.l_l1_b + o), w + H, s.xg, G);
-            s.pj[o] = dot_from(acc, w + H + G, s.temb, T);
+            s.pj[o] = dot_from(acc, w + H + G, s.temb, TX);
         }
         __syncthreads();
         for (int n = tid; n < N; n += kThreads) {
@@ -261,7 +263,7 @@ epic_forward_fp32_kernel(const float* __restrict__ W, MmbEpicLayout Lo, Fp32Dims
     extern __shared__ float smem[];
     const Smem s = carve(smem, f, N);
     const size_t b = blockIdx.x;
-    for (int i = threadIdx.x; i < f.T; i += kThreads) s.temb[i] = temb[b * temb_stride + i];
+    for (int i = threadIdx.x; i < f.T + f.X; i += kThreads) s.temb[i] = temb[b * temb_stride + i];
     __syncthreads();
     epic_forward_jet(W, Lo, f, s, x + b * N * f.Dc, k + b * N, mask + b * N, N,
                      v_out + b * N * f.Dc, logits_out + b * N * f.S, hidden_out ? hidden_out + b * N * f.H : nullptr);
@@ -272,7 +274,7 @@ epic_forward_fp32_kernel(const float* __restrict__ W, MmbEpicLayout Lo, Fp32Dims
 __global__ void __launch_bounds__(kThreads)
 generate_fp32_kernel(const float* __restrict__ W, MmbEpicLayout Lo, Fp32Dims f,
                      float* __restrict__ x, uint8_t* __restrict__ k, const uint8_t* __restrict__ mask,
-                     const float* __restrict__ table, int n_steps, float dt,
+                     const float* __restrict__ context, const float* __restrict__ table, int n_steps, float dt,
                      const float* __restrict__ u_jump, uint64_t seed, uint64_t jet_offset, int B, int N) {
     extern __shared__ float smem[];
     const Smem s = carve(smem, f, N);
@@ -286,6 +288,7 @@ generate_fp32_kernel(const float* __restrict__ W, MmbEpicLayout Lo, Fp32Dims f,
     for (int i = tid; i < N * f.Dc; i += kThreads) sx[i] = x[b * N * f.Dc + i];
     for (int n = tid; n < N; n += kThreads) { sk[n] = k[b * N + n]; sm[n] = mask[b * N + n]; }
     const float* temb_tab = table + (size_t)n_steps * 4;
+    for (int i = tid; i < f.X; i += kThreads) s.temb[f.T + i] = context[b * f.X + i];   // constant over the steps (mbm.py:143-144)
     for (int step = 0; step < n_steps; ++step) {
         for (int i = tid; i < f.T; i += kThreads) s.temb[i] = temb_tab[(size_t)step * f.T + i];
         __syncthreads();
@@ -307,7 +310,7 @@ generate_fp32_kernel(const float* __restrict__ W, MmbEpicLayout Lo, Fp32Dims f,
 int check_dims(const MmbEpicDims& d) {
     if (d.dim_continuous < 1 || d.dim_continuous > 8 || d.vocab_size < 1 || d.vocab_size > 32)
         return fail(MMB_EINVAL, "need 1 <= Dc <= 8 and 1 <= S <= 32 (got Dc=%d S=%d)", d.dim_continuous, d.vocab_size);
-    if (d.dim_hidden_local < 1 || d.dim_hidden_glob < 1 || d.dim_time_emb < 1 || d.num_blocks < 0)
+    if (d.dim_hidden_local < 1 || d.dim_hidden_glob < 1 || d.dim_time_emb < 1 || d.num_blocks < 0 || d.dim_context < 0)
         return fail(MMB_EINVAL, "bad EPiC widths");
     return MMB_OK;
 }
@@ -330,7 +333,7 @@ int launch_epic_forward_fp32(const EpicModel* m, const float* x, const uint8_t* 
     return cuda_ok(cudaGetLastError(), "epic_forward_fp32 launch");
 }
 
-int launch_generate_fp32(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table,
+int launch_generate_fp32(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* context, const float* dev_table,
                          int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                          int B, int N, cudaStream_t stream) {
     if (int rc = check_dims(m->dims)) return rc;
@@ -341,7 +344,7 @@ int launch_generate_fp32(const EpicModel* m, float* x, uint8_t* k, const uint8_t
     if (int rc = cuda_ok(cudaFuncSetAttribute(generate_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
                          "smem attribute"))
         return rc;
-    generate_fp32_kernel<<<B, kThreads, bytes, stream>>>(m->w, m->layout, f, x, k, mask, dev_table, n_steps, dt, u_jump,
+    generate_fp32_kernel<<<B, kThreads, bytes, stream>>>(m->w, m->layout, f, x, k, mask, context, dev_table, n_steps, dt, u_jump,
                                                           seed, jet_offset, B, N);
     return cuda_ok(cudaGetLastError(), "generate_fp32 launch");
 }

@@ -141,6 +141,7 @@ struct MmaParams {
     uint64_t seed, jet_offset;
     int B, N;
     const float4* tvec;      // [n_steps][2 + 2L][8] bias quads of the per-step time vectors (prologue kernel)
+    const float4* cvec;      // [B][1 + 2L][8] quads of the per-jet context terms of global_0 / fc_global1 / fc_local1, or null
     const int32_t* counts;   // [kKeys]: jets per key (empty jets are finished by the prologue and appear in no list)
     int32_t* cursors;        // [kMaxCls]: next unclaimed jet of each class (teams of `cls` warps claim jets dynamically)
     const int32_t* lists;    // [kKeys][B]: jets of each key
@@ -157,7 +158,7 @@ __device__ __forceinline__ void vec_frag(uint32_t (&a)[4], float v00, float v01,
     a[3] = dup ? a[2] : 0u;
 }
 
-template <int DC, int S, int SH, int GT, bool HOSTIO>
+template <int DC, int S, int SH, int GT, bool HOSTIO, bool CTX>
 __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kernel(const MmaParams p) {
     using LY = Lay<GT>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -298,6 +299,15 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
 
         for (int step = 0; step < p.n_steps; ++step) {
             const float4* tvq = p.tvec + (size_t)step * (2 + 2 * L) * 8 + t;   // quad (v, j): tvq[8 v + 4 j]
+            // time vector v (>= 1) plus the jet's context term of the same Linear (the reference's context = [t_emb | ctx])
+            auto ctx_quad = [&](int v, int j) {
+                float4 b = __ldg(tvq + 8 * v + 4 * j);
+                if constexpr (CTX) {
+                    const float4 c = __ldg(p.cvec + ((size_t)jet * (1 + 2 * L) + (v - 1)) * 8 + 4 * j + t);
+                    b.x += c.x; b.y += c.y; b.z += c.z; b.w += c.w;
+                }
+                return b;
+            };
             // ---- (a) first A tile: [x_hi, x_lo, onehot(k)] per particle through the staging tile; every lane writes its rows
             // every step (dead rows: zeros — the tile doubles as the logits staging area)
             {
@@ -354,7 +364,7 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
                 float c[2][4];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    mma(c[j], a_mean, tile(LY::t_g0 + j), __ldg(tvq + 8 + 4 * j));
+                    mma(c[j], a_mean, tile(LY::t_g0 + j), ctx_quad(1, j));
                     mma_acc(c[j], a_sum, tile(LY::t_g0 + 2 + j));
                 }
                 vec_frag(a, lrelu_f(c[0][0]), lrelu_f(c[0][1]), lrelu_f(c[1][0]), lrelu_f(c[1][1]));
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
                     float c[2][4];
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        mma(c[j], a_mean, tl[(LY::o_g1 + j) * 32], __ldg(tvq + 8 * (2 + 2 * l) + 4 * j));
+                        mma(c[j], a_mean, tl[(LY::o_g1 + j) * 32], ctx_quad(2 + 2 * l, j));
                         mma_acc(c[j], a_sum, tl[(LY::o_g1 + 2 + j) * 32]);
                     }
 #pragma unroll
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
                     for (int j = 0; j < 2; ++j) {
                         float d[4];
                         vec_frag(a, xm[0][0], xm[0][1], xm[1][0], xm[1][1], true);
-                        mma(d, a, tl[(LY::o_l1g + j) * 32], __ldg(tvq + 8 * (3 + 2 * l) + 4 * j));
+                        mma(d, a, tl[(LY::o_l1g + j) * 32], ctx_quad(3 + 2 * l, j));
 #pragma unroll
                         for (int gt = 1; gt < GT; ++gt) {
                             vec_frag(a, xm[2 * gt][0], xm[2 * gt][1], xm[2 * gt + 1][0], xm[2 * gt + 1][1], true);
@@ -620,10 +630,40 @@ __global__ void __launch_bounds__(kW * 32, MMB_MMA_MINB) epic_mma_generate_kerne
 constexpr int kPrologueThreads = 256;
 __global__ void __launch_bounds__(kPrologueThreads) mma_prologue_kernel(const float* __restrict__ W, MmbEpicLayout Lo, MmbEpicDims d,
                                                                         const float* __restrict__ temb, int n_steps, float4* __restrict__ tvec,
+                                                                        const float* __restrict__ context, float4* __restrict__ cvec, int ctx_blocks,
                                                                         const uint8_t* __restrict__ mask, int B, int N, int32_t* __restrict__ counts,
                                                                         int32_t* __restrict__ lists, int32_t* __restrict__ jet_cnt,
                                                                         float* __restrict__ x, uint8_t* __restrict__ k, long long* __restrict__ k64) {
-    const int T = d.dim_time_emb, C = d.dim_cont_emb, D = d.dim_disc_emb, H = d.dim_hidden_local, G = d.dim_hidden_glob, L = d.num_blocks;
+    const int T = d.dim_time_emb, C = d.dim_cont_emb, D = d.dim_disc_emb, H = d.dim_hidden_local, G = d.dim_hidden_glob, L = d.num_blocks,
+              X = d.dim_context, TX = T + X;
+    // the context-consuming Linear `v` (1: global_0; 2 + 2l: fc_global1; 3 + 2l: fc_local1), output o: bias and its [time | context] columns
+    auto ctx_columns = [&](int v, int o, float& bias) -> const float* {
+        if (v == 1) { bias = W[Lo.global0_b + o]; return W + Lo.global0_w + (size_t)o * (2 * H + TX) + 2 * H; }
+        const float* Wl = W + Lo.layer0 + (size_t)((v - 2) >> 1) * Lo.layer_stride;
+        if (v & 1) { bias = Wl[Lo.l_l1_b + o]; return Wl + Lo.l_l1_w + (size_t)o * (H + G + TX) + H + G; }
+        bias = Wl[Lo.l_g1_b + o];
+        return Wl + Lo.l_g1_w + (size_t)o * (2 * H + G + TX) + 2 * H + G;
+    };
+    if ((int)blockIdx.x >= n_steps && (int)blockIdx.x < n_steps + ctx_blocks) {
+        // one thread per (jet, Linear, quad): W[:, T:T+X] ctx_jet for two outputs, in the C-operand quad layout of the time vectors
+        const size_t idx = (size_t)((int)blockIdx.x - n_steps) * kPrologueThreads + threadIdx.x;
+        const int q = (int)(idx & 7), v = (int)((idx >> 3) % (size_t)(1 + 2 * L)) + 1;
+        const size_t jet = (idx >> 3) / (size_t)(1 + 2 * L);
+        if (jet < (size_t)B) {
+            const int j = q >> 2, t = q & 3;
+            const float* cj = context + jet * X;
+            float unused, b[2];
+            for (int e = 0; e < 2; ++e) {
+                const float* wt = ctx_columns(v, 8 * j + 2 * t + e, unused) + T;
+                float acc = 0.0f;
+                for (int i = 0; i < X; ++i) acc = fmaf(wt[i], cj[i], acc);
+                b[e] = acc;
+            }
+            cvec[idx] = make_float4(b[0], b[1], b[0], b[1]);
+        }
+        return;
+    }
+    const int bin_block0 = n_steps + ctx_blocks;
     if ((int)blockIdx.x < n_steps) {
         __shared__ float s_vec[2 + 2 * kMaxL][16];
         const int step = blockIdx.x, v = threadIdx.x >> 4, o = threadIdx.x & 15;
@@ -636,13 +676,8 @@ __global__ void __launch_bounds__(kPrologueThreads) mma_prologue_kernel(const fl
                 acc = W[Lo.local0_b + o];
                 for (int c = 0; c < C; ++c) acc = fmaf(w0[T + c], W[Lo.emb_cont_b + c], acc);
                 wt = w0;
-            } else if (v == 1) {
-                acc = W[Lo.global0_b + o];
-                wt = W + Lo.global0_w + (size_t)o * (2 * H + T) + 2 * H;
             } else {
-                const float* Wl = W + Lo.layer0 + (size_t)((v - 2) >> 1) * Lo.layer_stride;
-                if (v & 1) { acc = Wl[Lo.l_l1_b + o]; wt = Wl + Lo.l_l1_w + (size_t)o * (H + G + T) + H + G; }
-                else { acc = Wl[Lo.l_g1_b + o]; wt = Wl + Lo.l_g1_w + (size_t)o * (2 * H + G + T) + 2 * H + G; }
+                wt = ctx_columns(v, o, acc);
             }
             for (int i = 0; i < T; ++i) acc = fmaf(wt[i], te[i], acc);
             s_vec[v][o] = acc;
@@ -658,7 +693,7 @@ __global__ void __launch_bounds__(kPrologueThreads) mma_prologue_kernel(const fl
     __shared__ int s_cnt[kKeys], s_base[kKeys];
     if (threadIdx.x < kKeys) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const int jet = ((int)blockIdx.x - n_steps) * kPrologueThreads + threadIdx.x;
+    const int jet = ((int)blockIdx.x - bin_block0) * kPrologueThreads + threadIdx.x;
     int cls = -1, key = 0, pos = 0;
     if (jet < B) {
         const uint8_t* row = mask + (size_t)jet * N;
@@ -723,7 +758,7 @@ int build_image_gt(const MmbEpicDims& d, const MmbEpicLayout& Lo, const float* W
     using LY = Lay<GT>;
     const int Dc = d.dim_continuous, S = d.vocab_size, T = d.dim_time_emb, C = d.dim_cont_emb, D = d.dim_disc_emb, H = kH,
               G = d.dim_hidden_glob, L = d.num_blocks, Sh = d.disc_head_hidden;
-    const int K0 = T + C + D;
+    const int K0 = T + C + D, TX = T + d.dim_context;   // context-consuming Linears: [... | time T | context X] columns
     std::vector<uint16_t> img((size_t)LY::n_tiles(L) * 128, 0);
     std::vector<float> quads((size_t)LY::n_vecs(L) * 32, 0.0f);
     const double inv_scale = 1.0 / (double)kSumScale;
@@ -746,8 +781,8 @@ int build_image_gt(const MmbEpicDims& d, const MmbEpicLayout& Lo, const float* W
     for (int j = 0; j < 2; ++j) {
         put(LY::t_local0 + j, 8 * j, 0, w_local0);
         // projection globals: global_0 [H][mean H | sum H | T], global_1 [H][H], global_2 [G][H]
-        put(LY::t_g0 + j, 8 * j, 0, [&](int o, int kc) { return (double)W[Lo.global0_w + (size_t)o * (2 * H + T) + kc]; });
-        put(LY::t_g0 + 2 + j, 8 * j, 0, [&](int o, int kc) { return inv_scale * W[Lo.global0_w + (size_t)o * (2 * H + T) + H + kc]; });
+        put(LY::t_g0 + j, 8 * j, 0, [&](int o, int kc) { return (double)W[Lo.global0_w + (size_t)o * (2 * H + TX) + kc]; });
+        put(LY::t_g0 + 2 + j, 8 * j, 0, [&](int o, int kc) { return inv_scale * W[Lo.global0_w + (size_t)o * (2 * H + TX) + H + kc]; });
         put(LY::t_g1 + j, 8 * j, 0, [&](int o, int kc) { return (double)W[Lo.global1_w + (size_t)o * H + kc]; });
     }
     for (int j = 0; j < 2 * GT; ++j)
@@ -757,7 +792,7 @@ int build_image_gt(const MmbEpicDims& d, const MmbEpicLayout& Lo, const float* W
     for (int l = 0; l < L; ++l) {
         const float* Wl = W + Lo.layer0 + (size_t)l * Lo.layer_stride;
         const int tl = LY::t_layer0 + l * LY::layer_tiles, vl = LY::v_layer0 + l * LY::layer_vecs;
-        const int Kg = 2 * H + G + T, Kl = H + G + T;
+        const int Kg = 2 * H + G + TX, Kl = H + G + TX;
         for (int j = 0; j < 2; ++j) {
             put(tl + LY::o_g1 + j, 8 * j, 0, [&](int o, int kc) { return (double)Wl[Lo.l_g1_w + (size_t)o * Kg + kc]; });
             put(tl + LY::o_g1 + 2 + j, 8 * j, 0, [&](int o, int kc) { return inv_scale * Wl[Lo.l_g1_w + (size_t)o * Kg + H + kc]; });
@@ -821,7 +856,8 @@ size_t smem_bytes(int L) {
 template <int DC, int S, int SH, int GT>
 int launch_kernel(const MmaParams& p, int grid, cudaStream_t stream) {
     const size_t bytes = smem_bytes<GT>(p.L);
-    auto kern = p.x_in ? epic_mma_generate_kernel<DC, S, SH, GT, true> : epic_mma_generate_kernel<DC, S, SH, GT, false>;
+    auto kern = p.x_in ? (p.cvec ? epic_mma_generate_kernel<DC, S, SH, GT, true, true> : epic_mma_generate_kernel<DC, S, SH, GT, true, false>)
+                       : (p.cvec ? epic_mma_generate_kernel<DC, S, SH, GT, false, true> : epic_mma_generate_kernel<DC, S, SH, GT, false, false>);
     if (int rc = cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "mma smem attribute")) return rc;
     kern<<<grid, kW * 32, bytes, stream>>>(p);
     return cuda_ok(cudaGetLastError(), "epic_mma launch");
@@ -845,7 +881,7 @@ bool mma_supported(const MmbEpicDims* d, int N) {
     const int gt = (d->dim_hidden_glob + 15) / 16;
     return d->dim_hidden_local == kH && d->dim_hidden_glob >= 1 && gt <= (d->vocab_size == 8 ? 2 : 1) && d->dim_time_emb >= 1 &&
            d->num_blocks >= 1 && d->num_blocks <= kMaxL && d->dim_continuous == 3 && (d->vocab_size == 8 || d->vocab_size == 4) &&
-           head_ok && N >= 1 && N <= kRowsPerWarp * kMaxCls;
+           head_ok && N >= 1 && N <= kRowsPerWarp * kMaxCls && d->dim_context >= 0;
 }
 
 int mma_build_images(EpicModel* m, const float* packed_host) {
@@ -854,13 +890,15 @@ int mma_build_images(EpicModel* m, const float* packed_host) {
                    : build_image_gt<2>(m->dims, m->layout, packed_host, &m->mma_image_f16, &m->mma_image_f16_bytes);
 }
 
-// scratch (4-byte units): time-vector quads [n_steps][2 + 2L][8] float4 | counts [16] | cursors [16] | jet_cnt [B] | lists [kKeys][B]
+// scratch (4-byte units): time-vector quads [n_steps][2 + 2L][8] float4 | context quads [B][1 + 2L][8] float4 (models with context
+// features) | counts [16] | cursors [16] | jet_cnt [B] | lists [kKeys][B]
 static size_t tvec_floats(const MmbEpicDims* d, int n_steps) { return (size_t)n_steps * (2 + 2 * d->num_blocks) * 32; }
+static size_t cvec_floats(const MmbEpicDims* d, int B) { return d->dim_context > 0 ? (size_t)(B > 0 ? B : 0) * (1 + 2 * d->num_blocks) * 32 : 0; }
 size_t mma_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B) {
-    return tvec_floats(d, n_steps) + 32 + (size_t)(B > 0 ? B : 0) * (1 + kKeys) + 16;
+    return tvec_floats(d, n_steps) + cvec_floats(d, B) + 32 + (size_t)(B > 0 ? B : 0) * (1 + kKeys) + 16;
 }
 
-int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
+int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* context, const float* dev_table, float* scratch,
                         int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                         int B, int N, cudaStream_t stream, const MmaHostIO* host) {
     if (B == 0 || n_steps == 0) return MMB_OK;
@@ -876,17 +914,21 @@ int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t*
     p.step_tab = dev_table;
     p.n_steps = n_steps; p.dt = dt; p.u_jump = u_jump; p.seed = seed; p.jet_offset = jet_offset;
     p.B = B; p.N = N;
-    int32_t* counts = reinterpret_cast<int32_t*>(scratch + tvec_floats(&m->dims, n_steps));
+    if ((m->dims.dim_context > 0) != (context != nullptr))
+        return fail(MMB_EINVAL, "mmb_generate: the model has %d context features, context pointer %s", m->dims.dim_context, context ? "given" : "missing");
+    float4* cvec = context ? reinterpret_cast<float4*>(scratch + tvec_floats(&m->dims, n_steps)) : nullptr;
+    int32_t* counts = reinterpret_cast<int32_t*>(scratch + tvec_floats(&m->dims, n_steps) + cvec_floats(&m->dims, B));
     int32_t* cursors = counts + 16;
     int32_t* jet_cnt = counts + 32;
     int32_t* lists = jet_cnt + B;
     if (int rc = cuda_ok(cudaMemsetAsync(counts, 0, 32 * sizeof(int32_t), stream), "mma counters")) return rc;
     const int bin_blocks = (B + kPrologueThreads - 1) / kPrologueThreads;
-    mma_prologue_kernel<<<n_steps + bin_blocks, kPrologueThreads, 0, stream>>>(m->w, m->layout, m->dims, dev_table + (size_t)n_steps * 4, n_steps,
-                                                                                reinterpret_cast<float4*>(scratch), mask, B, N, counts, lists,
+    const int ctx_blocks = context ? (int)(((size_t)B * (1 + 2 * m->dims.num_blocks) * 8 + kPrologueThreads - 1) / kPrologueThreads) : 0;
+    mma_prologue_kernel<<<n_steps + ctx_blocks + bin_blocks, kPrologueThreads, 0, stream>>>(m->w, m->layout, m->dims, dev_table + (size_t)n_steps * 4, n_steps,
+                                                                                reinterpret_cast<float4*>(scratch), context, cvec, ctx_blocks, mask, B, N, counts, lists,
                                                                                 jet_cnt, p.x, k, host ? host->k_out : nullptr);
     if (int rc = cuda_ok(cudaGetLastError(), "mma prologue launch")) return rc;
-    p.tvec = reinterpret_cast<const float4*>(scratch); p.counts = counts; p.cursors = cursors; p.lists = lists; p.jet_cnt = jet_cnt;
+    p.tvec = reinterpret_cast<const float4*>(scratch); p.cvec = cvec; p.counts = counts; p.cursors = cursors; p.lists = lists; p.jet_cnt = jet_cnt;
     // Persistent grid: MMB_MMA_MINB CTAs per SM at most.  Any grid finishes any amount of work (warps claim jets until the
     // lists are empty), so the size only matters for speed: a small call takes about 1.25 warps per jet (the JetClass-like
     // mean is 1.14), which lets the kernels of neighbouring pipeline slices (mmb_generate_host) share the GPU side by side.

@@ -1067,7 +1067,8 @@ int tc_read_trace(long long* out, int n) {
 bool tc_supported(const MmbEpicDims* d, int N) {
     return d->dim_hidden_local == kH && d->dim_hidden_glob <= kGP && d->dim_time_emb <= kMaxT && d->dim_time_emb % 2 == 0 &&
            d->num_blocks >= 1 && d->num_blocks <= kMaxL && d->dim_continuous == 3 &&
-           (d->vocab_size == 8 || d->vocab_size == 4) && d->disc_head_hidden <= 256 && N <= kRows && N >= 1;
+           (d->vocab_size == 8 || d->vocab_size == 4) && d->disc_head_hidden <= 256 && N <= kRows && N >= 1 &&
+           d->dim_context == 0;   // models with context features run on the fp32 kernel or the warp-MMA engine
 }
 
 // Build the device image from the packed fp32 blob (host): bf16 UMMA operands + fp32 side tables.

@@ -115,7 +115,7 @@ int launch_epic_forward_fp32(const EpicModel* m, const float* x, const uint8_t* 
                              const float* temb, int temb_stride, int B, int N,
                              float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream);
 // device step table: [n_steps] rows of (bc, cc, sp, pad) followed by [n_steps][T] temb
-int launch_generate_fp32(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table,
+int launch_generate_fp32(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* context, const float* dev_table,
                          int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                          int B, int N, cudaStream_t stream);
 
@@ -142,7 +142,7 @@ struct MmaHostIO {          // direct mode of mmb_generate_host: device-visible 
     long long* k_out;       // [B,N] int64
     int* bad_tokens;        // DEVICE flag
 };
-int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
+int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* context, const float* dev_table, float* scratch,
                         int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                         int B, int N, cudaStream_t stream, const MmaHostIO* host = nullptr);
 

@@ -46,7 +46,9 @@ class SinusoidalPositionalEncoding(nn.Module):
 
 
 class InputEmbeddings(nn.Module):
-    """utils.py:6-110.  Supported embedding kinds are the ones every shipped config uses."""
+    """utils.py:6-110.  Feature embeddings: the kinds every shipped config uses.  Context features (utils.py:84-110, 155-170):
+    ``embedding_continuous_context`` (``nn.Linear`` for the reference's kind "Embedding", identity for None), same attribute
+    name and construction order as the reference so checkpoints and seeded random-init weights match."""
 
     def __init__(self, config):
         super().__init__()
@@ -55,14 +57,45 @@ class InputEmbeddings(nn.Module):
             raise NotImplementedError("native path supports embedding_time=SinusoidalPositionalEncoding only")
         if e.embedding_features_continuous != "Linear" or e.embedding_features_discrete != "Embedding":
             raise NotImplementedError("native path supports Linear continuous / Embedding discrete feature embeddings")
-        if d.dim_context_continuous or d.dim_context_discrete:
-            raise NotImplementedError("context features are not supported by the native path (all shipped configs use 0)")
         if d.dim_features_discrete != 1:
             raise NotImplementedError("one discrete token per particle (dim_features_discrete=1)")
         self.embedding_time = SinusoidalPositionalEncoding(e.dim_emb_time, max_period=10000)
         dim_cont_emb = e.dim_emb_features_continuous or d.dim_features_continuous
         self.embedding_continuous = nn.Linear(d.dim_features_continuous, dim_cont_emb)
         self.embedding_discrete = nn.Embedding(d.vocab_size_features, e.dim_emb_features_discrete)
+        self.dim_context = 0   # width of the embedded context behind the time embedding
+        if d.dim_context_continuous:
+            kind = e.embedding_context_continuous
+            if kind == "Embedding":
+                width = e.dim_emb_context_continuous or d.dim_context_continuous
+                self.embedding_continuous_context = nn.Linear(d.dim_context_continuous, width)
+            elif kind is None:
+                width = d.dim_context_continuous
+                self.embedding_continuous_context = nn.Identity()
+            else:
+                raise NotImplementedError("embedding_context_continuous: 'Embedding' (a Linear layer in the reference) or None")
+            self.dim_context += width
+        if d.dim_context_discrete and e.dim_emb_context_discrete:
+            # The reference cannot run such a model: the constructor stores the module as `embedding_context_discrete`
+            # (utils.py:100-106), forward looks for `embedding_discrete_context` (utils.py:161), the embedding is never appended
+            # and global_0 fails with a shape error.  Nothing to be a drop-in for.
+            raise NotImplementedError("discrete context features: the reference's forward never applies their embedding "
+                                      "(utils.py:100 vs utils.py:161) and fails for dim_emb_context_discrete > 0")
+
+    @torch.no_grad()
+    def context(self, context_continuous, context_discrete, device) -> Optional[torch.Tensor]:
+        """The part of the reference's per-jet ``context`` vector behind the time embedding (utils.py:155-170): [B, dim_context]
+        fp32 on ``device`` — a Linear / table lookup on a few numbers per jet, once per call."""
+        if not self.dim_context:
+            return None
+        parts = []
+        home = self.embedding_discrete.weight.device   # evaluated where the parameters live; only the result moves
+        if hasattr(self, "embedding_continuous_context"):
+            if context_continuous is None:
+                raise ValueError("the model was built with dim_context_continuous > 0: batch.context_continuous is required")
+            c = context_continuous.to(home, torch.float32)
+            parts.append(self.embedding_continuous_context(c.reshape(c.shape[0], -1)))
+        return torch.cat(parts, dim=-1).float().to(device).contiguous()
 
 
 class EPiC_Projection(nn.Module):
@@ -114,7 +147,7 @@ class EPiCWrapper(nn.Module):
         self.epic = EPiCNetwork(
             dim_input=e.dim_emb_time + dim_cont_emb + e.dim_emb_features_discrete,
             dim_output=d.dim_features_continuous + d.dim_features_discrete * d.vocab_size_features,
-            dim_context=e.dim_emb_time,
+            dim_context=e.dim_emb_time + self.embedding.dim_context,
             num_blocks=e.num_blocks,
             dim_hidden_local=e.dim_hidden_local,
             dim_hidden_global=e.dim_hidden_glob,
@@ -125,7 +158,7 @@ class EPiCWrapper(nn.Module):
                           dim_time_emb=e.dim_emb_time, dim_cont_emb=dim_cont_emb,
                           dim_disc_emb=e.dim_emb_features_discrete, dim_hidden_local=e.dim_hidden_local,
                           dim_hidden_glob=e.dim_hidden_glob, num_blocks=e.num_blocks,
-                          skip_connection=int(bool(e.skip_connection)))
+                          skip_connection=int(bool(e.skip_connection)), dim_context=self.embedding.dim_context)
         self._cache = {}
 
     # ---- packing -----------------------------------------------------------------------------
@@ -172,10 +205,18 @@ class EPiCWrapper(nn.Module):
         emb = self.embedding.embedding_time(t.detach().reshape(t.shape[0]).float().cpu())
         return emb.contiguous().to(t.device)
 
+    def context_rows(self, t, context_continuous=None, context_discrete=None, device=None) -> torch.Tensor:
+        """The reference's per-jet context vector [time embedding | embedded context] (utils.py:133-170), [B, T + X]."""
+        device = device or t.device
+        rows = self.time_embedding(t).to(device)
+        ctx = self.embedding.context(context_continuous, context_discrete, device)
+        return rows if ctx is None else torch.cat([rows, ctx], dim=-1).contiguous()
+
     def forward(self, t, x, k=None, mask=None, context_continuous=None, context_discrete=None,
                 output_hidden_local=False):
         model = self.native_model(x.device)
-        v, z, hidden = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask), self.time_embedding(t).to(x.device),
+        v, z, hidden = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask),
+                                     self.context_rows(t, context_continuous, context_discrete, x.device),
                                      want_hidden=True, precision=self.precision)
         h = torch.cat([v, z], dim=-1)
         return (h, hidden) if output_hidden_local else h

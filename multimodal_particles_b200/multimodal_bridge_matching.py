@@ -74,8 +74,8 @@ class MultiModalEPiC(nn.Module):
 
     def forward(self, t, x, k, mask=None, context_continuous=None, context_discrete=None):
         model = self.native_model(x.device)
-        v, logits = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask), self.epic.time_embedding(t).to(x.device),
-                                  precision=self.precision)
+        v, logits = model.forward(x.contiguous().float(), as_u8(k), as_u8(mask),
+                                  self.epic.context_rows(t, context_continuous, context_discrete, x.device), precision=self.precision)
         return v, logits, mask
 
 
@@ -116,7 +116,9 @@ class MultiModalBridgeMatching(_ModuleBase):
     # ---- network ----------------------------------------------------------------------------
     def forward(self, state: HybridState, batch=None) -> MultiHeadOutput:
         continuous, discrete, absorbing = self.encoder(
-            t=state.time, x=state.continuous, k=state.discrete, mask=state.absorbing)
+            t=state.time, x=state.continuous, k=state.discrete, mask=state.absorbing,
+            context_continuous=getattr(batch, "context_continuous", None),      # mbm.py:143-144
+            context_discrete=getattr(batch, "context_discrete", None))
         return MultiHeadOutput(continuous, discrete, absorbing)
 
     # ---- generation -------------------------------------------------------------------------
@@ -143,7 +145,10 @@ class MultiModalBridgeMatching(_ModuleBase):
         k64 = state.discrete
         B, N = state.continuous.shape[0], state.continuous.shape[1]
         model = self.encoder.native_model(device)
+        # embedded context features of the jets, constant over the steps (mbm.py:143-144 -> utils.py:155-170); None without
         on_host = (state.continuous.device.type == "cpu" and k64.device.type == "cpu" and state.absorbing.device.type == "cpu")
+        embed_context = lambda where: self.encoder.epic.embedding.context(getattr(batch, "context_continuous", None),
+                                                                          getattr(batch, "context_discrete", None), where)
         if on_host and uniforms is None and not return_device:
             # Host state in, host state out (what Trainer.predict does): ONE library call.  Direct mode: the kernel reads each
             # jet from the page-locked input and writes it to the page-locked output itself.  Sliced mode: H2D of slice c+1
@@ -155,7 +160,8 @@ class MultiModalBridgeMatching(_ModuleBase):
             chunks = self.pipeline_chunks if B >= self.pipeline_chunks * self.pipeline_min_jets else 1   # 0 stays 0: direct mode
             x_host, k_host, flag, keep = model.generate_host(state.continuous, k64.reshape(B, N, 1), state.absorbing.reshape(B, N, 1), table,
                                                              seed=self.seed, jet_offset=jet_offset, chunks=chunks,
-                                                             precision=precision or self.precision)
+                                                             precision=precision or self.precision,
+                                                             context=embed_context("cpu"))
             torch.cuda.current_stream(device).synchronize()
             del keep
             assert int(flag) == 0, "Values in `k` outside of bound! (0 <= k < {})".format(self.vocab_size)
@@ -171,7 +177,7 @@ class MultiModalBridgeMatching(_ModuleBase):
         if jet_offset is None:
             jet_offset = next_jet_offset(self, B)
         model.generate(x, k, mask, table, u_jump=u, seed=self.seed, jet_offset=jet_offset,
-                       precision=precision or self.precision)
+                       precision=precision or self.precision, context=embed_context(device))
         t_last = float(table.t[-1])
         if return_device:
             return HybridState(time=torch.full((B, 1), t_last, device=device), continuous=x,

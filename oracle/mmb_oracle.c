@@ -178,6 +178,9 @@ static void epic_forward_jet(const MmbEpicDims* d, const MmbEpicLayout* Lo, cons
               D = d->dim_disc_emb, H = d->dim_hidden_local, G = d->dim_hidden_glob, L = d->num_blocks,
               Sh = d->disc_head_hidden;
     const int K0 = T + C + D;
+    /* `temb` holds the reference's per-jet `context` vector [time embedding T | embedded context X] (utils.py:166-170);
+     * only its time part is among the particle features (utils.py:139-145) */
+    const int TX = T + d->dim_context;
     float *xl = sc->xl, *skipl = sc->skipl, *l1 = sc->l1, *masked = sc->masked;
     float pj[256], pool[768], g0[256], g1[256], xg[256], skipg[256], emb[256], sum[256];
 
@@ -208,9 +211,9 @@ static void epic_forward_jet(const MmbEpicDims* d, const MmbEpicLayout* Lo, cons
         pool[o] = sum[o] / cnt;
         pool[H + o] = sum[o];
     }
-    for (int i = 0; i < T; ++i) pool[2 * H + i] = temb[i];
+    for (int i = 0; i < TX; ++i) pool[2 * H + i] = temb[i];
     for (int o = 0; o < H; ++o)
-        g0[o] = lrelu(dot_from(W[Lo->global0_b + o], W + Lo->global0_w + (size_t)o * (2 * H + T), pool, 2 * H + T));
+        g0[o] = lrelu(dot_from(W[Lo->global0_b + o], W + Lo->global0_w + (size_t)o * (2 * H + TX), pool, 2 * H + TX));
     for (int o = 0; o < H; ++o)
         g1[o] = lrelu(dot_from(W[Lo->global1_b + o], W + Lo->global1_w + (size_t)o * H, g0, H));
     for (int o = 0; o < G; ++o)
@@ -234,18 +237,18 @@ static void epic_forward_jet(const MmbEpicDims* d, const MmbEpicLayout* Lo, cons
             pool[H + o] = sum[o];
         }
         for (int i = 0; i < G; ++i) pool[2 * H + i] = xg[i];
-        for (int i = 0; i < T; ++i) pool[2 * H + G + i] = temb[i];
-        const int Kg = 2 * H + G + T;
+        for (int i = 0; i < TX; ++i) pool[2 * H + G + i] = temb[i];
+        const int Kg = 2 * H + G + TX;
         for (int o = 0; o < H; ++o)
             g1[o] = lrelu(dot_from(Wl[Lo->l_g1_b + o], Wl + Lo->l_g1_w + (size_t)o * Kg, pool, Kg));
         for (int o = 0; o < G; ++o)
             g0[o] = lrelu(dot_from(Wl[Lo->l_g2_b + o], Wl + Lo->l_g2_w + (size_t)o * H, g1, H) + xg[o]);
         memcpy(xg, g0, sizeof(float) * (size_t)G);
-        const int Kl = H + G + T;
+        const int Kl = H + G + TX;
         for (int o = 0; o < H; ++o) {
             const float* w = Wl + Lo->l_l1_w + (size_t)o * Kl;
             float acc = dot_from(Wl[Lo->l_l1_b + o], w + H, xg, G);
-            pj[o] = dot_from(acc, w + H + G, temb, T);
+            pj[o] = dot_from(acc, w + H + G, temb, TX);
         }
         for (int n = 0; n < N; ++n) {
             const float m = (float)mask[n];
@@ -288,7 +291,7 @@ static void epic_forward_jet(const MmbEpicDims* d, const MmbEpicLayout* Lo, cons
 }
 
 static int dims_ok(const MmbEpicDims* d) {
-    return d->dim_hidden_local <= 256 && d->dim_hidden_glob <= 256 && d->dim_time_emb <= 256 &&
+    return d->dim_hidden_local <= 256 && d->dim_hidden_glob <= 256 && d->dim_time_emb + d->dim_context <= 256 && d->dim_context >= 0 &&
            d->dim_cont_emb <= 256 && d->disc_head_hidden <= 256 && d->dim_continuous + d->vocab_size <= 64 &&
            d->vocab_size <= 32;
 }
@@ -1097,12 +1100,13 @@ int mmbo_max_threads(void) {
 #endif
 }
 
-void mmbo_generate(const MmbEpicDims* dims, const float* packed, float* x, uint8_t* k, const uint8_t* mask,
+void mmbo_generate(const MmbEpicDims* dims, const float* packed, float* x, uint8_t* k, const uint8_t* mask, const float* context,
                    const MmbStepTable* st, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                    int B, int N, int nthreads) {
     if (!dims_ok(dims)) return;
     const MmbEpicLayout Lo = mmb_epic_layout(dims);
-    const int Dc = dims->dim_continuous, S = dims->vocab_size, H = dims->dim_hidden_local, T = dims->dim_time_emb;
+    const int Dc = dims->dim_continuous, S = dims->vocab_size, H = dims->dim_hidden_local, T = dims->dim_time_emb,
+              X = dims->dim_context;
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
 #else
@@ -1119,8 +1123,11 @@ void mmbo_generate(const MmbEpicDims* dims, const float* packed, float* x, uint8
             float* xb = x + (size_t)b * N * Dc;
             uint8_t* kb = k + (size_t)b * N;
             memcpy(mk, mask + (size_t)b * N, (size_t)N);
+            float ctx[256];   /* [time embedding of the step | the jet's embedded context] (utils.py:133-170) */
+            for (int i = 0; i < X; ++i) ctx[T + i] = context[(size_t)b * X + i];
             for (int s = 0; s < st->n_steps; ++s) {
-                epic_forward_jet(dims, &Lo, packed, xb, kb, mk, st->temb + (size_t)s * T, N, v, lg, NULL, &sc);
+                memcpy(ctx, st->temb + (size_t)s * T, sizeof(float) * (size_t)T);
+                epic_forward_jet(dims, &Lo, packed, xb, kb, mk, ctx, N, v, lg, NULL, &sc);
                 for (int n = 0; n < N; ++n) {
                     float u = u_jump ? u_jump[((size_t)s * B + b) * N + n]
                                      : philox_uniform(seed, jet_offset + (uint64_t)b, 0, s, n);

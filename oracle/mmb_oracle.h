@@ -44,8 +44,9 @@ void mmbo_bridge_update(float* x, uint8_t* k, uint8_t* mask,
 void mmbo_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int stream_id,
                           int n_steps, int B, int N);
 
-/* MultiModalBridgeMatching.simulate_dynamics (mbm.py:199-216); OpenMP over jets (nthreads<=0: all) */
-void mmbo_generate(const MmbEpicDims* dims, const float* packed, float* x, uint8_t* k, const uint8_t* mask,
+/* MultiModalBridgeMatching.simulate_dynamics (mbm.py:199-216); OpenMP over jets (nthreads<=0: all);
+ * context [B][dims->dim_context]: the jets' embedded context features (mbm.py:143-144), NULL without */
+void mmbo_generate(const MmbEpicDims* dims, const float* packed, float* x, uint8_t* k, const uint8_t* mask, const float* context,
                    const MmbStepTable* steps, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                    int B, int N, int nthreads);
 

@@ -87,7 +87,8 @@ def prefix_masks(mults, n):
     return (torch.arange(n)[None, :] < torch.tensor(mults)[:, None]).long().unsqueeze(-1)
 
 
-def mbm_case(name, cfg, x0, k0, mask, seed, snap_steps):
+def mbm_case(name, cfg, x0, k0, mask, seed, snap_steps, batch=None, extra=None):
+    """``batch``: what the reference's forward reads context features from (mbm.py:143-144); ``extra``: arrays to store too."""
     torch.manual_seed(seed)
     model = MultiModalBridgeMatching(cfg)
     # random init leaves logits nearly flat; scale the head so tokens actually compete
@@ -121,7 +122,7 @@ def mbm_case(name, cfg, x0, k0, mask, seed, snap_steps):
         return out
 
     model.bridge_discrete.solver_step = jump
-    batch = (x0,)
+    batch = (x0,) if batch is None else batch
     state = HybridState(None, x0.clone(), k0.clone(), mask.clone())
     with InjectedNoise(u_jump=u), torch.no_grad():
         final = model.simulate_dynamics(state, batch)
@@ -147,6 +148,7 @@ def mbm_case(name, cfg, x0, k0, mask, seed, snap_steps):
         out[f"snap{i}/v"] = s["v"].numpy()
         out[f"snap{i}/logits"] = s["logits"].numpy()
     out.update(np_state_dict(model))
+    out.update(extra or {})
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **out)
     moved = (torch.stack(rec["k_traj"])[1:] != torch.stack(rec["k_traj"])[:-1]).sum().item()

@@ -51,7 +51,8 @@ def epic_forward(dims: EpicDims, packed, x, k, mask, temb, want_hidden=False):
     v = np.empty((B, N, Dc), np.float32)
     logits = np.empty((B, N, dims.vocab_size), np.float32)
     hidden = np.empty((B, N, dims.dim_hidden_local), np.float32) if want_hidden else None
-    stride = 0 if temb.reshape(-1, dims.dim_time_emb).shape[0] == 1 and B != 1 else dims.dim_time_emb
+    width = dims.dim_time_emb + dims.dim_context   # a row: [time embedding | embedded context of the jet]
+    stride = 0 if temb.reshape(-1, width).shape[0] == 1 and B != 1 else width
     lib().mmbo_epic_forward(ctypes.byref(dims), _p(packed), _p(x), _p(k, _u8p), _p(mask, _u8p), _p(temb),
                             ctypes.c_int(stride), B, N, _p(v), _p(logits), _p(hidden))
     return (v, logits, hidden) if want_hidden else (v, logits)
@@ -69,12 +70,14 @@ def bridge_update(x, k, mask, v, logits, u_jump, dt, bc, cc, absorb_logit=None, 
     return x, k, mask
 
 
-def generate(dims: EpicDims, packed, x, k, mask, table, u_jump=None, seed=0, jet_offset=0, nthreads=0):
+def generate(dims: EpicDims, packed, x, k, mask, table, u_jump=None, seed=0, jet_offset=0, nthreads=0, context=None):
     B, N, Dc = x.shape
     x, k, mask, packed = f32(x).copy(), u8(k).reshape(B, N).copy(), u8(mask).reshape(B, N), f32(packed)
     u = None if u_jump is None else f32(u_jump)
+    ctx = None if context is None else f32(context).reshape(B, dims.dim_context)
+    assert (ctx is None) == (dims.dim_context == 0)
     ct = CStepTable.from_table(table)
-    lib().mmbo_generate(ctypes.byref(dims), _p(packed), _p(x), _p(k, _u8p), _p(mask, _u8p), ctypes.byref(ct), _p(u),
+    lib().mmbo_generate(ctypes.byref(dims), _p(packed), _p(x), _p(k, _u8p), _p(mask, _u8p), _p(ctx), ctypes.byref(ct), _p(u),
                         ctypes.c_uint64(seed), ctypes.c_uint64(jet_offset), B, N, nthreads)
     return x, k
 

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/mmbridge.h but not exported"
     assert names == set(_native.SIGNATURES), "binding table and header disagree"
-    assert lib.mmb_abi_version() == 2
+    assert lib.mmb_abi_version() == 3
 
 
 def test_layout_size_matches_python_packing():
