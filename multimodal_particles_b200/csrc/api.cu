@@ -254,12 +254,14 @@ int mmb_epic_create(const MmbEpicDims* dims, const float* packed, size_t n_float
     m->tc_image_bytes = 0;
     m->mma_image_f16 = nullptr;
     m->mma_image_f16_bytes = 0;
+    m->wide = nullptr;
     int rc = cuda_ok(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device), "sm count");
     if (!rc) rc = cuda_ok(cudaMalloc(&m->w, lo.total * sizeof(float)), "cudaMalloc weights");
     if (!rc) rc = cuda_ok(cudaMemcpy(m->w, packed, lo.total * sizeof(float), cudaMemcpyHostToDevice), "weight upload");
     try {   // the one-time packing uses std::vector: nothing may throw across the C ABI
         if (!rc && tc_supported(dims, 128)) rc = tc_build_image(m, packed);
         if (!rc && mma_supported(dims, 64)) rc = mma_build_images(m, packed);
+        if (!rc && wide_supported(dims, 128)) rc = wide_build_image(m, packed);
     } catch (...) {
         rc = fail(MMB_ENOMEM, "mmb_epic_create: out of host memory");
     }
@@ -278,6 +280,7 @@ void mmb_epic_destroy(MmbEpicModel* handle) {
     if (m->w) cudaFree(m->w);
     if (m->tc_image) cudaFree(m->tc_image);
     if (m->mma_image_f16) cudaFree(m->mma_image_f16);
+    wide_free_image(m);
     table_cache_destroy(m->tables);
     host_pipe_destroy(m->host_pipe);
     delete m;
@@ -293,8 +296,10 @@ int mmb_epic_forward(const MmbEpicModel* handle, const float* x, const uint8_t* 
     if (precision == MMB_PREC_FP32)
         return launch_epic_forward_fp32(m, x, k, mask, temb, temb_stride, B, N, v_out, logits_out, hidden_out, s);
     if (precision == MMB_PREC_BF16) {
+        if (m->wide && wide_supported(&m->dims, N))
+            return launch_epic_forward_wide(m, x, k, mask, temb, temb_stride, B, N, v_out, logits_out, hidden_out, s);
         if (!m->tc_image || !tc_supported(&m->dims, N))
-            return fail(MMB_EUNSUPPORTED, "tcgen05 path is built for H=16, G<=32, Dc+S<=16, head<=16, N<=128; use fp32");
+            return fail(MMB_EUNSUPPORTED, "tcgen05 trunks are built for H=16 (G<=32, no context features) and H=128 (G<=32), Dc=3, S<=8, N<=128; use fp32");
         return launch_epic_forward_tc(m, x, k, mask, temb, temb_stride, B, N, v_out, logits_out, hidden_out, s);
     }
     return fail(MMB_EINVAL, "unknown precision %d", precision);
@@ -315,25 +320,71 @@ int mmb_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, const
                                 P, Dc, S, flags, static_cast<cudaStream_t>(stream));
 }
 
+static size_t wide_generate_scratch_floats(const EpicModel* m, int B, int N);
+
 size_t mmb_generate_workspace_bytes(const MmbEpicModel* handle, int B, int N, int precision) {
     const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
-    (void)N; (void)precision;
+    (void)precision;
     if (!m) return 0;
     // the tensor-core paths' per-step time vectors (up to 4096 steps) and jet lists; the step table itself is cached on the handle
-    const size_t a = tc_generate_scratch_floats(&m->dims, 4096, B), b = mma_generate_scratch_floats(&m->dims, 4096, B);
-    return (a > b ? a : b) * sizeof(float);
+    const size_t a = tc_generate_scratch_floats(&m->dims, 4096, B), b = mma_generate_scratch_floats(&m->dims, 4096, B),
+                 c = wide_generate_scratch_floats(m, B, N);
+    return ((a > b ? a : b) > c ? (a > b ? a : b) : c) * sizeof(float);
+}
+
+// The 128-wide tcgen05 trunk has no fused loop: a solver step is its network evaluation (~0.2 ms per 1000 jets, epic_wide_tc.cu)
+// followed by the HBM-bound update kernel on the heads it wrote, with this step's Philox draws.  Scratch (floats): heads v | logits |
+// uniforms | context rows [B][T + X] (models with context features).
+static size_t wide_generate_scratch_floats(const EpicModel* m, int B, int N) {
+    if (!m->wide) return 0;
+    const size_t P = (size_t)(B > 0 ? B : 0) * (N > 0 ? N : 0);
+    return P * (m->dims.dim_continuous + m->dims.vocab_size + 1) + (size_t)(B > 0 ? B : 0) * (m->dims.dim_time_emb + m->dims.dim_context) + 16;
+}
+
+__global__ void wide_context_rows_kernel(const float* __restrict__ temb, const float* __restrict__ ctx, int B, int T, int X, float* __restrict__ rows) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * (T + X)) return;
+    const int b = i / (T + X), c = i - b * (T + X);
+    rows[i] = c < T ? temb[c] : ctx[(size_t)b * X + (c - T)];
+}
+
+static int generate_wide(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* context, const MmbStepTable* st,
+                         const float* table, const float* u_jump, uint64_t seed, uint64_t jet_offset, int B, int N, float* ws, cudaStream_t s) {
+    const int Dc = m->dims.dim_continuous, S = m->dims.vocab_size, T = m->dims.dim_time_emb, X = m->dims.dim_context, n = st->n_steps;
+    const size_t P = (size_t)B * N;
+    float *v = ws, *logits = v + P * Dc, *u = logits + P * S, *rows = u + P;
+    for (int step = 0; step < n; ++step) {
+        const float* temb = table + (size_t)n * 4 + (size_t)step * T;
+        int stride = 0;
+        if (X > 0) {
+            wide_context_rows_kernel<<<(B * (T + X) + 255) / 256, 256, 0, s>>>(temb, context, B, T, X, rows);
+            if (int rc = cuda_ok(cudaGetLastError(), "context rows launch")) return rc;
+            temb = rows;
+            stride = T + X;
+        }
+        if (int rc = launch_epic_forward_wide(m, x, k, mask, temb, stride, B, N, v, logits, nullptr, s)) return rc;
+        const float* uj = u_jump ? u_jump + (size_t)step * P : u;
+        if (!u_jump)
+            if (int rc = launch_philox_uniforms(u, seed, jet_offset, 0, step, 1, B, N, s)) return rc;
+        if (int rc = launch_bridge_update(x, k, const_cast<uint8_t*>(mask), v, logits, nullptr, uj, nullptr,
+                                          StepScalars{st->dt, st->bc[step], st->cc[step], 0.0f}, P, Dc, S, MMB_FLAG_MULTIMODAL, s))
+            return rc;
+    }
+    return MMB_OK;
 }
 
 int mmb_generate_supported(const MmbEpicModel* handle, int N, int precision) {
     const EpicModel* m = reinterpret_cast<const EpicModel*>(handle);
     if (!m || N < 1) return 0;
     if (precision == MMB_PREC_FP32) return 1;
+    if (precision == MMB_PREC_BF16 && m->wide && wide_supported(&m->dims, N)) return 1;
     if (precision == MMB_PREC_BF16) return m->tc_image && tc_supported(&m->dims, N) && (m->dims.disc_head_hidden == 0 || m->dims.disc_head_hidden == m->dims.vocab_size);
     if (precision == MMB_PREC_F16) return m->mma_image_f16 && mma_supported(&m->dims, N);
     return 0;
 }
 
-static size_t generate_ws_floats(const EpicModel* m, int n_steps, int B, int precision) {
+static size_t generate_ws_floats(const EpicModel* m, int n_steps, int B, int N, int precision) {
+    if (precision == MMB_PREC_BF16 && m->wide) return wide_generate_scratch_floats(m, B, N);
     return precision == MMB_PREC_F16 ? mma_generate_scratch_floats(&m->dims, n_steps, B) : tc_generate_scratch_floats(&m->dims, n_steps, B);
 }
 
@@ -348,7 +399,7 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
         return fail(MMB_EINVAL, "mmb_generate: the model has %d context features, context pointer %s", m->dims.dim_context,
                     context ? "given" : "missing");
     const int T = m->dims.dim_time_emb, n = st->n_steps;
-    if (workspace_bytes < generate_ws_floats(m, n, B, precision) * sizeof(float))
+    if (workspace_bytes < generate_ws_floats(m, n, B, N, precision) * sizeof(float))
         return fail(MMB_ENOMEM, "mmb_generate: workspace %zu B too small for %d steps", workspace_bytes, n);
     if (B == 0 || N == 0 || n == 0) return MMB_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -362,6 +413,9 @@ int mmb_generate(const MmbEpicModel* handle, float* x, uint8_t* k, const uint8_t
     }
     if (precision == MMB_PREC_FP32)
         return launch_generate_fp32(m, x, k, mask, context, table, n, st->dt, u_jump, seed, jet_offset, B, N, s);
+    if (precision == MMB_PREC_BF16 && m->wide && wide_supported(&m->dims, N)) {
+        return generate_wide(m, x, k, mask, context, st, table, u_jump, seed, jet_offset, B, N, static_cast<float*>(workspace), s);
+    }
     if (precision == MMB_PREC_BF16) {
         if (!m->tc_image || !tc_supported(&m->dims, N))
             return fail(MMB_EUNSUPPORTED, "tcgen05 path is built for H=16, G<=32, Dc+S<=16, head<=16, N<=128; use fp32");
@@ -385,7 +439,7 @@ struct HostChunkLayout {
         x = take(P * m->dims.dim_continuous * sizeof(float));
         k64 = take(P * 8); m64 = take(P * 8); k8 = take(P); m8 = take(P);
         ctx = take((size_t)Bc * m->dims.dim_context * sizeof(float));
-        scratch = take(generate_ws_floats(m, n_steps, Bc, precision) * sizeof(float));
+        scratch = take(generate_ws_floats(m, n_steps, Bc, N, precision) * sizeof(float));
         total = at;
     }
 };
@@ -722,5 +776,6 @@ int mmb_bridge_losses(const float* v, const float* logits, const float* x0, cons
 // debug only (not part of include/mmbridge.h): phase timestamps of the tcgen05 generation kernel, see tools/tc_trace.py
 int mmb_debug_read_trace(long long* out, int n) { return tc_read_trace(out, n); }
 int mmb_debug_read_stack_trace(long long* out, int n) { return stack_read_trace(out, n); }
+int mmb_debug_read_wide_trace(long long* out, int n) { return wide_read_trace(out, n); }
 
 }  // extern "C"

@@ -38,6 +38,7 @@ struct EpicModel {
     size_t tc_image_bytes;
     void* mma_image_f16;  // B-fragment tiles of the warp-MMA engine (epic_mma.cu), fp16 operands; may be null
     size_t mma_image_f16_bytes;
+    void* wide;           // operand image + tables of the 128-wide tcgen05 trunk (epic_wide_tc.cu); may be null
 };
 
 // bridge_update.cu
@@ -130,6 +131,14 @@ size_t tc_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B);
 int launch_generate_tc(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* dev_table, float* scratch,
                        int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
                        int B, int N, cudaStream_t stream);
+
+// epic_wide_tc.cu — tcgen05 trunk for dim_hidden_local = 128 (the reference's class default, epic.py:99-101)
+bool wide_supported(const MmbEpicDims* d, int N);
+int wide_build_image(EpicModel* m, const float* packed_host);
+void wide_free_image(EpicModel* m);
+int wide_read_trace(long long* out, int n);
+int launch_epic_forward_wide(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask, const float* temb, int temb_stride,
+                             int B, int N, float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream);
 
 // epic_mma.cu — warp-level MMA engine (register-resident chains), generation only
 bool mma_supported(const MmbEpicDims* d, int N);

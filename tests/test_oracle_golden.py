@@ -10,7 +10,7 @@ import torch
 import oracle_lib as ol
 from multimodal_particles_b200.steptable import build_step_table
 
-MBM_CASES = ["mbm_c1", "mbm_n128", "mbm_odd"]
+MBM_CASES = ["mbm_c1", "mbm_n128", "mbm_odd", "mbm_wide"]   # mbm_wide: the class-default widths (epic.py:99-101)
 # fp32 network tolerance vs torch's CPU GEMM ordering
 HEAD_RTOL, HEAD_ATOL = 2e-5, 2e-5
 
