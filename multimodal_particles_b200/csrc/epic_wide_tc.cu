@@ -6,7 +6,11 @@
 // models (`mmb_epic_forward` / the step loop of `mmb_generate` with MMB_PREC_BF16); the H = 16 engines live in epic_tc.cu /
 // epic_mma.cu.
 //
-// One CTA (512 threads) carries TWO jets at a time ("tiles" A and B, 128 rows each = TMEM lanes), persistent over pairs of jets:
+// One CTA (512 threads) carries TWO tiles at a time (A and B, 128 rows each = TMEM lanes), persistent over pairs of tiles.  Rows are
+// LIVE particles only: every per-particle layer acts on rows independently and the pooling is masked, so padded slots need no row
+// at all (their outputs are constants, written by the pre-pass).  A jet takes ceil(live / 32) of a tile's four 32-row quarters and
+// a tile holds one or two jets (pre-pass: wide_pack_kernel bins the jets, wide_tiles_kernel composes [4] | [3,1] | [2,2] | [2,1] |
+// [1,1]), so a CTA works on up to four jets:
 //   * per tile the residual stream X [128 x 128] fp32 and one accumulator ACC [128 x 128] live in TMEM (2 x 256 = all 512 columns);
 //     thread (r, cq) serves row r, columns [32 cq, 32 cq + 32) of whichever tile is in its epilogue;
 //   * every Linear over the particles is 8 tcgen05.mma M128 x N128 x K16 with bf16 operands; the weights stream L2 -> shared
@@ -16,8 +20,10 @@
 //   * fc_local2 accumulates straight onto X (the residual add is the accumulate flag), its bias rides on one more K-step
 //     against a ones tile; fc_local1's bias is per jet (its global and context columns) and is added in the epilogue;
 //   * local_0 with the embeddings folded in is ONE K-step: the operand row is [x_hi, x_lo, onehot(k)] (two bf16 per feature);
-//   * the per-jet global path (masked mean / sum pooling -> global MLPs, epic.py:136-143, 187-190, 226-232) runs on the CUDA
-//     cores for both jets at once, so each weight is fetched from L2 once per pair, while the fc_local1 GEMMs are in flight;
+//   * the per-jet global path (masked mean / sum pooling -> global MLPs, epic.py:136-143, 187-190, 226-232) is warp-level
+//     tensor-core work too: the jets of the CTA are the rows of mma.sync m16n8k16 tiles (inputs split into bf16 hi + lo, so they
+//     enter with ~16 bits), each of the 16 warps owns eight output columns and reads its weight fragments, pre-arranged on the
+//     host, straight from L2 — once per CTA and layer, while the fc_local1 GEMMs are in flight;
 //   * the trunk skip (epic.py:148-155) is kept per tile as fp16 in shared memory.
 // Numerics: bf16 operands, fp32 accumulation, fp32 residual / pooling / global path (bf16 weights for its three wide
 // matrices).  Checked against the fp32 kernel with the tolerance written in tests/test_gpu_wide.py.
@@ -38,8 +44,7 @@ constexpr int kH = 128;
 constexpr int kSlot = 36864;        // bytes per streamed matrix: 32 KB weight tile + 4 KB bias tile
 constexpr int kThreads = 512;
 constexpr int kCW = 32;             // accumulator columns per thread
-constexpr int kMaxL = 8, kMaxG = 32, kMaxTX = 96, kMaxT = 64;
-constexpr int kJ = 2;               // jets (tiles) in flight per CTA
+constexpr int kMaxL = 8;
 
 // ---- PTX wrappers (same conventions as absorb_head_tc.cu) ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,63 +173,137 @@ __device__ __forceinline__ float selu(float a) {
     return scale * (a > 0.0f ? a : alpha * (__expf(a) - 1.0f));
 }
 
-__host__ __device__ inline int round8(int v) { return (v + 7) & ~7; }
+__host__ __device__ inline int round16(int v) { return (v + 15) & ~15; }
 
-// fp32 side table (floats) and bf16 wide matrices of the global path; every offset in elements of its array
+constexpr int kMaxJ = 4;                 // jets per CTA: two tiles x two segments
+constexpr int kMaxTXq = 64, kMaxGq = 32; // padded widths of the context vector [time | context] and of the global vector
+constexpr int kIn1Stride = (256 + kMaxTXq + kMaxGq) / 2 + 4;   // words per jet of the fc_global1 input (bf16 pairs); = 20 mod 32
+constexpr int kGvStride = 64 + 4;                              // a 128-vector; = 4 mod 32
+constexpr int kCxStride = (kMaxTXq + kMaxGq) / 2 + 4;          // [ctx | xm]; = 20 mod 32
+static_assert(kIn1Stride % 32 == 20 && kGvStride % 32 == 4 && kCxStride % 32 == 20, "row strides chosen so that (jet, t) lanes hit distinct banks");
+
+// fp32 side table (floats) and the weight fragments of the global path (uint2 per lane, see put_frag)
 struct WideLayout {
     int L, G, T, X, S, Sh, Dc, skip;
-    int Tp, TXp, Gp;            // padded widths (multiples of 8, zero weights in the padding)
+    int TXq, Gq;                // padded to multiples of 16 (zero weights in the padding)
     // fp32 table
-    int c0, w0t;                // [128], [128][Tp]: local_0 bias (+ folded embedding bias), its time columns
-    int b_g0, b_g1, g2, b_g2;   // [128], [128], [Gp][128], [Gp]
-    int layer0, layer_stride;   // per layer: b_lg1 [128] | Wg2 [Gp][128] | b_lg2 [Gp] | Wl1g [128][TXp + Gp] | b_l1 [128]
-    int o_blg1, o_wg2, o_blg2, o_wl1g, o_bl1;
-    int head0, b_head0, head2, b_head2;   // [16][16], [16], [16][16], [16]
+    int c0, b_g0, b_g1, b_g2;   // [128] local_0 bias (+ folded embedding bias), biases of global_0 / global_1 / global_2 [Gq]
+    int layer0, layer_stride;   // per layer: b_lg1 [128] | b_lg2 [Gq] | b_l1 [128]
+    int o_blg1, o_blg2, o_bl1;
+    int head0, b_head0, head2, b_head2, dead_logits;   // [16][16], [16], [16][16], [16], [8]: logits of a padded slot = head(0)
     int tab_floats;
-    // bf16 matrices
-    int g0, g1;                 // [128][256 + TXp], [128][128]
-    int wg1_0, wg1_stride;      // per layer [128][256 + TXp + Gp], columns [mean | sum | ctx | xg]
-    int big_elems;
+    // fragment image (uint2 units): matrix m occupies (N / 8) * KS * 32 entries
+    int f_w0t, f_g0, f_g1, f_g2;
+    int f_layer0, f_layer_stride, fo_wg1, fo_wg2, fo_wl1g;
+    int frag_elems;
     int n_seq;                  // streamed matrices per evaluation: local_0, L x (fc_local1, fc_local2), output
-    __host__ __device__ int K0() const { return 256 + TXp; }
-    __host__ __device__ int K1() const { return 256 + TXp + Gp; }
-    __host__ __device__ int K2() const { return TXp + Gp; }
+    __host__ __device__ int KS_t() const { return TXq / 16; }
+    __host__ __device__ int KS_0() const { return (256 + TXq) / 16; }
+    __host__ __device__ int KS_1() const { return (256 + TXq + Gq) / 16; }
+    __host__ __device__ int KS_2() const { return (TXq + Gq) / 16; }
 };
 
 WideLayout make_layout(const MmbEpicDims& d) {
     WideLayout w{};
     w.L = d.num_blocks; w.G = d.dim_hidden_glob; w.T = d.dim_time_emb; w.X = d.dim_context; w.S = d.vocab_size; w.Sh = d.disc_head_hidden;
     w.Dc = d.dim_continuous; w.skip = d.skip_connection;
-    w.Tp = round8(w.T); w.TXp = round8(w.T + w.X); w.Gp = round8(w.G);
+    w.TXq = round16(w.T + w.X); w.Gq = round16(w.G);
     int o = 0;
     auto take = [&](int n) { const int at = o; o += (n + 3) & ~3; return at; };
-    w.c0 = take(128); w.w0t = take(128 * w.Tp);
-    w.b_g0 = take(128); w.b_g1 = take(128); w.g2 = take(w.Gp * 128); w.b_g2 = take(w.Gp);
+    w.c0 = take(128); w.b_g0 = take(128); w.b_g1 = take(128); w.b_g2 = take(w.Gq);
     w.layer0 = o;
     {
         int p = 0;
         auto tk = [&](int n) { const int at = p; p += (n + 3) & ~3; return at; };
-        w.o_blg1 = tk(128); w.o_wg2 = tk(w.Gp * 128); w.o_blg2 = tk(w.Gp); w.o_wl1g = tk(128 * w.K2()); w.o_bl1 = tk(128);
+        w.o_blg1 = tk(128); w.o_blg2 = tk(w.Gq); w.o_bl1 = tk(128);
         w.layer_stride = p;
     }
     o += w.layer_stride * w.L;
-    w.head0 = take(256); w.b_head0 = take(16); w.head2 = take(256); w.b_head2 = take(16);
+    w.head0 = take(256); w.b_head0 = take(16); w.head2 = take(256); w.b_head2 = take(16); w.dead_logits = take(8);
     w.tab_floats = o;
-    int b = 0;
-    auto tb = [&](int n) { const int at = b; b += (n + 7) & ~7; return at; };
-    w.g0 = tb(128 * w.K0()); w.g1 = tb(128 * 128);
-    w.wg1_0 = b; w.wg1_stride = (128 * w.K1() + 7) & ~7;
-    b += w.wg1_stride * w.L;
-    w.big_elems = b;
+    int f = 0;
+    auto tf = [&](int n_out, int ks) { const int at = f; f += (n_out / 8) * ks * 32; return at; };
+    w.f_w0t = tf(128, w.KS_t()); w.f_g0 = tf(128, w.KS_0()); w.f_g1 = tf(128, 8); w.f_g2 = tf(w.Gq, 8);
+    w.f_layer0 = f;
+    {
+        int p = 0;
+        auto tk = [&](int n_out, int ks) { const int at = p; p += (n_out / 8) * ks * 32; return at; };
+        w.fo_wg1 = tk(128, w.KS_1()); w.fo_wg2 = tk(w.Gq, 8); w.fo_wl1g = tk(128, w.KS_2());
+        w.f_layer_stride = p;
+    }
+    f += w.f_layer_stride * w.L;
+    w.frag_elems = f;
     w.n_seq = 2 + 2 * w.L;
     return w;
+}
+
+// ---- packing pre-pass ------------------------------------------------------------------------------------------------------------
+// scratch (int32): counts[8] ([q] = jets needing q quarters, q = 1..4; [5] = tiles) | lists[4][B] | tile records [B][kRec]
+constexpr int kRec = 12;   // n_seg, then per segment: jet, q0, nq, m  (+ padding)
+__host__ __device__ inline size_t pack_ints(int B) { return 8 + (size_t)B * 4 + (size_t)B * kRec; }
+
+// warp per jet: live count -> list of its class; the heads of padded slots are constants and are written here (v = 0,
+// logits = head(0): the reference applies the head to the masked logits, mbm.py:105-111; hidden = 0); a jet without particles is
+// NaN throughout (its mean pool is 0 / 0, epic.py:141, and NaN * mask stays NaN) and is finished here
+__global__ void __launch_bounds__(256) wide_pack_kernel(const uint8_t* __restrict__ mask, int B, int N, int S, const float* __restrict__ dead_logits,
+                                                        float* __restrict__ v_out, float* __restrict__ logits_out, float* __restrict__ hidden_out,
+                                                        int32_t* __restrict__ pack) {
+    const int jet = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (jet >= B) return;
+    int m = 0;
+    for (int n0 = 0; n0 < N; n0 += 32) m += __popc(__ballot_sync(0xffffffffu, n0 + lane < N && mask[(size_t)jet * N + n0 + lane] != 0));
+    const float nan = __int_as_float(0x7fc00000);
+    for (int n = lane; n < N; n += 32) {
+        if (mask[(size_t)jet * N + n]) continue;
+        const size_t pi = (size_t)jet * N + n;
+        for (int c = 0; c < 3; ++c) v_out[pi * 3 + c] = m ? 0.0f : nan;
+        for (int s = 0; s < S; ++s) logits_out[pi * S + s] = m ? dead_logits[s] : nan;
+        if (hidden_out)
+            for (int c = 0; c < kH; c += 4) *reinterpret_cast<float4*>(hidden_out + pi * kH + c) = m ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(nan, nan, nan, nan);
+    }
+    if (lane == 0 && m > 0) {
+        const int q = (m + 31) / 32;
+        const int pos = atomicAdd(pack + q, 1);
+        pack[8 + (size_t)B * (q - 1) + pos] = jet | (m << 20);
+    }
+}
+
+// tiles: [4] x n4 | [3 (+1)] x n3 | [2,2] x n2/2 | [2 (+1)] if n2 is odd | [1,1] ...; one thread per tile
+__global__ void __launch_bounds__(256) wide_tiles_kernel(int32_t* __restrict__ pack, int B) {
+    const int n1 = pack[1], n2 = pack[2], n3 = pack[3], n4 = pack[4];
+    const int32_t *l1 = pack + 8, *l2 = l1 + B, *l3 = l2 + B, *l4 = l3 + B;
+    const int a = min(n3, n1), b = (n2 & 1) ? min(1, n1 - a) : 0;
+    const int n_tiles = n4 + n3 + n2 / 2 + (n2 & 1) + (n1 - a - b + 1) / 2;
+    if (blockIdx.x == 0 && threadIdx.x == 0) pack[5] = n_tiles;
+    int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= n_tiles) return;
+    int n_seg = 0, e[2] = {0, 0}, nq[2] = {0, 0};
+    auto add = [&](int entry, int q) { e[n_seg] = entry; nq[n_seg] = q; ++n_seg; };
+    if (t < n4) add(l4[t], 4);
+    else if ((t -= n4) < n3) { add(l3[t], 3); if (t < a) add(l1[t], 1); }
+    else if ((t -= n3) < n2 / 2) { add(l2[2 * t], 2); add(l2[2 * t + 1], 2); }
+    else {
+        t -= n2 / 2;
+        if ((n2 & 1) && t == 0) { add(l2[n2 - 1], 2); if (b) add(l1[a], 1); }
+        else {
+            t -= (n2 & 1);
+            add(l1[a + b + 2 * t], 1);
+            if (a + b + 2 * t + 1 < n1) add(l1[a + b + 2 * t + 1], 1);
+        }
+    }
+    int32_t* rec = pack + 8 + (size_t)B * 4 + (size_t)(blockIdx.x * 256 + threadIdx.x) * kRec;
+    rec[0] = n_seg;
+    for (int s = 0; s < 2; ++s) {
+        rec[1 + 4 * s] = e[s] & 0xfffff; rec[2 + 4 * s] = s ? nq[0] : 0; rec[3 + 4 * s] = nq[s]; rec[4 + 4 * s] = e[s] >> 20;
+    }
 }
 
 struct WideParams {
     const uint8_t* image;            // n_seq slots of kSlot bytes
     const float* tab;                // WideLayout fp32 table
-    const __nv_bfloat16* big;        // WideLayout bf16 matrices
+    const uint2* frag;               // WideLayout weight fragments of the global path
     WideLayout lay;
+    const int32_t* pack;             // pre-pass result
     const float* x;                  // [B,N,3]
     const uint8_t* k;                // [B,N]
     const uint8_t* mask;             // [B,N]
@@ -242,35 +321,49 @@ constexpr int kOffRing = 0;
 constexpr int kOffA = 2 * kSlot;                    // two operand tiles
 constexpr int kOffSkip = kOffA + 2 * 32768;         // two fp16 skip tiles
 constexpr int kOffOnes = kOffSkip + 2 * 32768;
-constexpr int kOffVec = kOffOnes + 4096;            // per-jet vectors (floats), see Vec
-struct Vec {   // float offsets inside the vector area
-    static constexpr int in_ld = 256 + kMaxTX + kMaxG;          // [mean 128 | sum 128 | ctx TXp | xg Gp]
-    static constexpr int in = 0;                                 // [kJ][in_ld]
-    static constexpr int g1 = in + kJ * in_ld;                   // [kJ][128]
-    static constexpr int g0 = g1 + kJ * 128;                     // [kJ][128]
-    static constexpr int bl1 = g0 + kJ * 128;                    // [kJ][128]
-    static constexpr int tv0 = bl1 + kJ * 128;                   // [kJ][128]
-    static constexpr int cx = tv0 + kJ * 128;                    // [kJ][kMaxTX + kMaxG]: [ctx | xm]
-    static constexpr int skg = cx + kJ * (kMaxTX + kMaxG);       // [kJ][kMaxG]
-    static constexpr int part = skg + kJ * kMaxG;                // [kJ][16 warps][32]
-    static constexpr int head = part + kJ * 16 * 32;             // head0 [16][16] | b0 [16] | head2 [16][16] | b2 [16] | b_out... (copied once)
-    static constexpr int floats = head + 256 + 16 + 256 + 16;
+constexpr int kOffVec = kOffOnes + 4096;            // per-jet vectors (4-byte words), see Vec
+struct Vec {
+    static constexpr int in1_hi = 0, in1_lo = in1_hi + kMaxJ * kIn1Stride;     // [mean 128 | sum 128 | ctx TXq | xg Gq] as bf16 pairs
+    static constexpr int gva_hi = in1_lo + kMaxJ * kIn1Stride, gva_lo = gva_hi + kMaxJ * kGvStride;   // 128-vectors between the stages
+    static constexpr int gvb_hi = gva_lo + kMaxJ * kGvStride, gvb_lo = gvb_hi + kMaxJ * kGvStride;
+    static constexpr int cx_hi = gvb_lo + kMaxJ * kGvStride, cx_lo = cx_hi + kMaxJ * kCxStride;       // [ctx | xm]
+    static constexpr int bl1 = cx_lo + kMaxJ * kCxStride;       // fp32 [kMaxJ][128]: per-jet bias of fc_local1 (of local_0 at tile start)
+    static constexpr int xg = bl1 + kMaxJ * 128;                // fp32 [kMaxJ][32]
+    static constexpr int skg = xg + kMaxJ * kMaxGq;             // fp32 [kMaxJ][32]
+    static constexpr int part = skg + kMaxJ * kMaxGq;           // fp32 [2 tiles][16 warps][32]
+    static constexpr int head = part + 2 * 16 * 32;             // head0 [16][16] | b0 [16] | head2 [16][16] | b2 [16]
+    static constexpr int slot = head + 256 + 16 + 256 + 16;     // int [2 tiles][128]: row -> particle slot of its jet, -1 unused
+    static constexpr int words = slot + 2 * 128;
 };
-constexpr int kSmemBytes = kOffVec + Vec::floats * 4;
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+constexpr int kSmemBytes = kOffVec + Vec::words * 4;
+static_assert(kSmemBytes + 512 <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a2, const uint2 b) {   // rows 8..15 of A are zero
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b.x), "r"(b.y));
+}
+// fp32 pair -> bf16 pair words (hi, lo): value ~ hi + lo
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const float h0 = __bfloat162float(__float2bfloat16(v0)), h1 = __bfloat162float(__float2bfloat16(v1));
+    hi = pack_bf16(h0, h1);
+    lo = pack_bf16(v0 - h0, v1 - h1);
+}
 
 __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t s_tmem_slot;
     __shared__ __align__(8) uint64_t s_bars[4];      // full[0], full[1], mma[A], mma[B]
-    __shared__ int s_cnt[kJ];
+    __shared__ int s_rec[2][kRec];                   // the two tiles of the pair
+    __shared__ int s_qseg[2][4];                     // tile, quarter -> segment (-1: empty)
     const WideLayout& ly = p.lay;
     const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
-    const int qq = warp & 3;
-    const int L = ly.L, G = ly.G, Gp = ly.Gp, TXp = ly.TXp, TX = ly.T + ly.X, S = ly.S, Sh = ly.Sh;
+    const int qq = warp & 3, g = lane >> 2, t4 = lane & 3;
+    const int L = ly.L, G = ly.G, Gq = ly.Gq, TXq = ly.TXq, TX = ly.T + ly.X, S = ly.S, Sh = ly.Sh;
     const bool skip_on = ly.skip != 0;
     uint8_t* sOnes = smem + kOffOnes;
     float* sv = reinterpret_cast<float*>(smem + kOffVec);
+    uint32_t* sw = reinterpret_cast<uint32_t*>(smem + kOffVec);
+    int* s_slot = reinterpret_cast<int*>(smem + kOffVec) + Vec::slot;
     auto sA = [&](int t) { return smem + kOffA + t * 32768; };
     auto sSkip = [&](int t) { return smem + kOffSkip + t * 32768; };
 
@@ -290,7 +383,9 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
     const int col0 = cq * kCW;
     const uint32_t dX[2] = {tmem, tmem + 256}, dACC[2] = {tmem + 128, tmem + 384};
 
-    const int n_pairs = (p.B + 1) / 2;
+    const int n_tiles = p.pack[5];
+    const int32_t* tile_recs = p.pack + 8 + (size_t)p.B * 4;
+    const int n_pairs = (n_tiles + 1) / 2;
     const int my_pairs = n_pairs > (int)blockIdx.x ? (n_pairs - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const uint32_t total_mats = (uint32_t)my_pairs * ly.n_seq;
     const uint32_t wbase = smem_u32(smem + kOffRing);
@@ -340,145 +435,153 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
         __syncthreads();
     };
 
-    // ---- global-path helpers: out[j][o] for both jets at once; thread (o = tid >> 2, kq = tid & 3) covers 16-byte weight chunks
-    // kq, kq + 4, ... of row o; the four partial sums meet by shuffle.  W row-major [n_out][K], K a multiple of 8.  The weights
-    // do not depend on the data, so a stage's chunks are fetched into registers up front (all loads in flight at once: one L2
-    // latency per stage instead of one per chunk) — `load_*` may be issued before the barrier that publishes the stage's input.
-    struct RowB { uint4 w[12]; };    // bf16 rows: K <= 384
-    struct RowF { float4 w[8]; };    // fp32 rows: K <= 128
-    auto load_rows_bf16 = [&](const __nv_bfloat16* W, int K, RowB& rw) {
-        const uint4* row = reinterpret_cast<const uint4*>(W + (size_t)(tid >> 2) * K);
+    // ---- one stage of the per-jet path: c = W in for the jets of the CTA (rows g < kMaxJ of an m16 tile).  Warp w < n_warps owns
+    // outputs 8 w .. 8 w + 7; on return lane (g, t4) holds outputs 8 w + 2 t4, + 1 of jet g in c[0], c[1].  The weight fragments
+    // do not depend on the data: `frag_load` issues all of a stage's loads at once (one L2 latency per stage) and may be called
+    // before the barrier that publishes the stage's input.
+    constexpr int kMaxKS = (256 + kMaxTXq + kMaxGq) / 16;
+    struct Frags { uint2 b[kMaxKS]; };
+    auto frag_load = [&](const uint2* base, int KS, int n_warps, Frags& f) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const int c = (tid & 3) + 4 * i;
-            rw.w[i] = c < K / 8 ? __ldg(row + c) : make_uint4(0u, 0u, 0u, 0u);
-        }
+        for (int kk = 0; kk < kMaxKS; ++kk)
+            f.b[kk] = (warp < n_warps && kk < KS) ? __ldg(base + ((size_t)warp * KS + kk) * 32 + lane) : make_uint2(0u, 0u);
     };
-    auto dot_rows_bf16 = [&](const RowB& rw, int K, const float* in, int in_ld, float (&acc)[kJ]) {
+    auto stage = [&](const Frags& f, int KS, int n_warps, const uint32_t* in_hi, const uint32_t* in_lo, int stride, float (&c)[4]) {
+        c[0] = c[1] = c[2] = c[3] = 0.0f;
+        if (warp < n_warps) {
+            const uint32_t* h = in_hi + g * stride + t4;
+            const uint32_t* l = in_lo + g * stride + t4;
 #pragma unroll
-        for (int j = 0; j < kJ; ++j) acc[j] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const int c = (tid & 3) + 4 * i;
-            if (c < K / 8) {
-                const uint32_t ww[4] = {rw.w[i].x, rw.w[i].y, rw.w[i].z, rw.w[i].w};
-#pragma unroll
-                for (int j = 0; j < kJ; ++j) {
-                    const float4 a = *reinterpret_cast<const float4*>(in + j * in_ld + 8 * c), b = *reinterpret_cast<const float4*>(in + j * in_ld + 8 * c + 4);
-                    const float xs[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        acc[j] = fmaf(__uint_as_float(ww[e] << 16), xs[2 * e], acc[j]);
-                        acc[j] = fmaf(__uint_as_float(ww[e] & 0xffff0000u), xs[2 * e + 1], acc[j]);
-                    }
+            for (int kk = 0; kk < kMaxKS; ++kk) {
+                if (kk < KS) {
+                    const bool on = g < kMaxJ;
+                    mma_bf16(c, on ? h[8 * kk] : 0u, on ? h[8 * kk + 4] : 0u, f.b[kk]);
+                    mma_bf16(c, on ? l[8 * kk] : 0u, on ? l[8 * kk + 4] : 0u, f.b[kk]);
                 }
             }
         }
-#pragma unroll
-        for (int j = 0; j < kJ; ++j) {
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
-        }
     };
-    auto load_rows_f32 = [&](const float* W, int K, int n_out, RowF& rw) {
-        const float4* row = reinterpret_cast<const float4*>(W + (size_t)(tid >> 2) * K);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = (tid & 3) + 4 * i;
-            rw.w[i] = ((tid >> 2) < n_out && c < K / 4) ? __ldg(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto dot_rows_f32 = [&](const RowF& rw, int K, const float* in, int in_ld, float (&acc)[kJ]) {
-#pragma unroll
-        for (int j = 0; j < kJ; ++j) acc[j] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = (tid & 3) + 4 * i;
-            if (c < K / 4) {
-#pragma unroll
-                for (int j = 0; j < kJ; ++j) {
-                    const float4 a = *reinterpret_cast<const float4*>(in + j * in_ld + 4 * c);
-                    acc[j] = fmaf(rw.w[i].x, a.x, acc[j]); acc[j] = fmaf(rw.w[i].y, a.y, acc[j]);
-                    acc[j] = fmaf(rw.w[i].z, a.z, acc[j]); acc[j] = fmaf(rw.w[i].w, a.w, acc[j]);
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kJ; ++j) {
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
-            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
-        }
-    };
-    float* s_in = sv + Vec::in;
-    // pooled sums of both tiles -> [mean | sum] of the jets' input vectors (epic.py:136-143)
+    // pooled sums of both tiles -> [mean | sum] of the jets' input vectors (epic.py:136-143); thread = (jet, column pair)
     auto pool_to_input = [&]() {
-        if (tid < kJ * 128) {
-            const int j = tid >> 7, c = tid & 127;
-            const float* part = sv + Vec::part + j * 16 * 32 + (c >> 5) * 4 * 32 + (c & 31);   // warps 4 cq .. 4 cq + 3 hold column c of rows 32 qq ..
-            const float s = (part[0] + part[32]) + (part[64] + part[96]);
-            s_in[j * Vec::in_ld + c] = s / (float)s_cnt[j];     // 0 / 0 = NaN for an empty jet, as the reference (epic.py:141)
-            s_in[j * Vec::in_ld + 128 + c] = s;
+        if (tid < kMaxJ * 64) {
+            const int j = tid >> 6, cp = tid & 63, t = j >> 1, s = j & 1, c = 2 * cp;
+            float s0 = 0.0f, s1 = 0.0f;
+            int m = 1;
+            if (s < s_rec[t][0]) {
+                const int q0 = s_rec[t][2 + 4 * s], nq = s_rec[t][3 + 4 * s];
+                m = s_rec[t][4 + 4 * s];
+                const float* part = sv + Vec::part + t * 16 * 32 + (c >> 5) * 4 * 32 + (c & 31);   // warps 4 cq + q hold column c of quarter q
+                for (int q = q0; q < q0 + nq; ++q) { s0 += part[q * 32]; s1 += part[q * 32 + 1]; }
+            }
+            const float inv = 1.0f / (float)m;
+            uint32_t hi, lo;
+            split_pair(s0 * inv, s1 * inv, hi, lo);
+            sw[Vec::in1_hi + j * kIn1Stride + cp] = hi; sw[Vec::in1_lo + j * kIn1Stride + cp] = lo;
+            split_pair(s0, s1, hi, lo);
+            sw[Vec::in1_hi + j * kIn1Stride + 64 + cp] = hi; sw[Vec::in1_lo + j * kIn1Stride + 64 + cp] = lo;
         }
+    };
+    // lanes (g < kMaxJ) of the warps that own outputs: store a pair of a 128-vector as bf16 hi / lo words
+    auto put_pair = [&](int hi_off, int lo_off, int stride, int word, float v0, float v1) {
+        uint32_t hi, lo;
+        split_pair(v0, v1, hi, lo);
+        sw[hi_off + g * stride + word] = hi;
+        sw[lo_off + g * stride + word] = lo;
     };
 
 #define WIDE_TRACE(id) do { if (p.trace && blockIdx.x == 0 && pi == 0 && tid == 0) p.trace[id] = clock64(); } while (0)
     for (int pi = 0; pi < my_pairs; ++pi) {
         const int pair = (int)blockIdx.x + pi * (int)gridDim.x;
         WIDE_TRACE(0);
-        const int jet0 = 2 * pair;
-        const bool has_b = jet0 + 1 < p.B;
-        bool live[2] = {false, false};
-        // ---- load the pair: masks, first operand rows [x_hi, x_lo, onehot(k)], context vectors --------------------------------
-#pragma unroll
-        for (int t = 0; t < kJ; ++t) {
-            const int jet = jet0 + t;
-            const bool on = jet < p.B;
-            live[t] = on && r < p.N && p.mask[(size_t)jet * p.N + r] != 0;
-            const int cnt = __syncthreads_count(cq == 0 && live[t]);
-            if (tid == 0) s_cnt[t] = cnt;
-            if (cq == 0) {
-                uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (live[t]) {
-                    const float* xr = p.x + ((size_t)jet * p.N + r) * 3;
-                    const float x0 = xr[0], x1 = xr[1], x2 = xr[2];
-                    const float h0 = __bfloat162float(__float2bfloat16(x0)), h1 = __bfloat162float(__float2bfloat16(x1)),
-                                h2 = __bfloat162float(__float2bfloat16(x2));
-                    const int kk = p.k[(size_t)jet * p.N + r];
-                    w[0] = pack_bf16(h0, h1); w[1] = pack_bf16(h2, x0 - h0); w[2] = pack_bf16(x1 - h1, x2 - h2);
-                    const int pos = 6 + kk;   // onehot column
-                    w[pos >> 1] |= 0x3F80u << (16 * (pos & 1));
-                }
-                uint8_t* q = sA(t) + (r >> 3) * 2048 + (r & 7) * 16;
-                *reinterpret_cast<uint4*>(q) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4*>(q + 128) = make_uint4(w[4], w[5], w[6], w[7]);
-            } else if (cq == 1) {   // context vector [time embedding | embedded context], zero padded
-                for (int i = r; i < kMaxTX; i += 128) {
-                    const float v = (on && i < TX) ? __ldg(p.temb + (size_t)jet * p.temb_stride + i) : 0.0f;
-                    s_in[t * Vec::in_ld + 256 + i] = v;
-                    sv[Vec::cx + t * (kMaxTX + kMaxG) + i] = v;
+        // ---- the pair's tiles: records, row map (row i of a segment = its i-th live particle), context vectors ---------------
+        if (tid < 2 * kRec) {
+            const int t = tid / kRec, i = tid % kRec, tile = 2 * pair + t;
+            s_rec[t][i] = tile < n_tiles ? __ldg(tile_recs + (size_t)tile * kRec + i) : 0;
+        }
+        if (tid < 256) s_slot[tid] = -1;
+        __syncthreads();
+        const bool has_b = s_rec[1][0] > 0;
+        if (tid < 8) {
+            const int t = tid >> 2, q = tid & 3;
+            int sg = -1;
+            for (int s = 0; s < s_rec[t][0]; ++s)
+                if (q >= s_rec[t][2 + 4 * s] && q < s_rec[t][2 + 4 * s] + s_rec[t][3 + 4 * s]) sg = s;
+            s_qseg[t][q] = sg;
+        }
+        if (warp < kMaxJ) {   // warp j: mask of jet j -> ranks
+            const int t = warp >> 1, s = warp & 1;
+            if (s < s_rec[t][0]) {
+                const int jet = s_rec[t][1 + 4 * s], base = 32 * s_rec[t][2 + 4 * s];
+                int before = 0;
+                for (int n0 = 0; n0 < p.N; n0 += 32) {
+                    const int n = n0 + lane;
+                    const bool on = n < p.N && p.mask[(size_t)jet * p.N + n] != 0;
+                    const uint32_t bits = __ballot_sync(0xffffffffu, on);
+                    if (on) s_slot[t * 128 + base + before + __popc(bits & ((1u << lane) - 1u))] = n;
+                    before += __popc(bits);
                 }
             }
-        }
-        publish();
-        WIDE_TRACE(1);
-        // ---- local_0 (one K-step) for both tiles; meanwhile the per-jet time vector of its bias
-        gemm(0, wseq, dX[0], 1, idesc128, false, false);
-        if (has_b) gemm(1, wseq, dX[1], 1, idesc128, false, false);
-        {
-            float acc[kJ];
-            RowF rw;
-            load_rows_f32(p.tab + ly.w0t, ly.Tp, 128, rw);
-            dot_rows_f32(rw, ly.Tp, s_in + 256, Vec::in_ld, acc);
-            if ((tid & 3) == 0) {
-                const int o = tid >> 2;
-#pragma unroll
-                for (int j = 0; j < kJ; ++j) sv[Vec::tv0 + j * 128 + o] = acc[j] + __ldg(p.tab + ly.c0 + o);
+        } else if (warp < 2 * kMaxJ) {   // warp 4 + j: context vector [time embedding | embedded context] of jet j, zero padded
+            const int j = warp - kMaxJ, t = j >> 1, s = j & 1;
+            const bool on = s < s_rec[t][0];
+            const int jet = on ? s_rec[t][1 + 4 * s] : 0;
+            for (int w = lane; w < kMaxTXq / 2; w += 32) {
+                const float v0 = (on && 2 * w < TX) ? __ldg(p.temb + (size_t)jet * p.temb_stride + 2 * w) : 0.0f;
+                const float v1 = (on && 2 * w + 1 < TX) ? __ldg(p.temb + (size_t)jet * p.temb_stride + 2 * w + 1) : 0.0f;
+                uint32_t hi, lo;
+                split_pair(v0, v1, hi, lo);
+                sw[Vec::in1_hi + j * kIn1Stride + 128 + w] = hi; sw[Vec::in1_lo + j * kIn1Stride + 128 + w] = lo;
+                sw[Vec::cx_hi + j * kCxStride + w] = hi; sw[Vec::cx_lo + j * kCxStride + w] = lo;
             }
         }
         __syncthreads();
-        // epilogue of a particle Linear: bias -> leaky-ReLU (-> mask, + skip) -> bf16 operand tile (and fp32 X, pooling sums)
-        // kind 0: local_0 (X = lrelu(X + tv0) * mask; defines the skip); 1: fc_local1 (A = lrelu(ACC + bl1)); 2: fc_local2
-        // (X = lrelu(X) * mask + skip)
+        // ---- per-thread facts of the pair; first operand rows [x_hi, x_lo, onehot(k)]
+        int slot[2], seg[2], jetr[2];
+        bool live[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            slot[t] = s_slot[t * 128 + r];
+            live[t] = slot[t] >= 0;
+            seg[t] = s_qseg[t][qq];                               // warp-uniform
+            jetr[t] = seg[t] >= 0 ? s_rec[t][1 + 4 * seg[t]] : 0;
+        }
+        if (cq < 2) {
+            const int t = cq;
+            uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (live[t]) {
+                const size_t pidx = (size_t)jetr[t] * p.N + slot[t];
+                const float* xr = p.x + pidx * 3;
+                const float x0 = xr[0], x1 = xr[1], x2 = xr[2];
+                const float h0 = __bfloat162float(__float2bfloat16(x0)), h1 = __bfloat162float(__float2bfloat16(x1)),
+                            h2 = __bfloat162float(__float2bfloat16(x2));
+                const int kk = p.k[pidx];
+                w[0] = pack_bf16(h0, h1); w[1] = pack_bf16(h2, x0 - h0); w[2] = pack_bf16(x1 - h1, x2 - h2);
+                const int pos = 6 + kk;   // onehot column
+                w[pos >> 1] |= 0x3F80u << (16 * (pos & 1));
+            }
+            uint8_t* q = sA(t) + (r >> 3) * 2048 + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(q + 128) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        publish();
+        WIDE_TRACE(1);
+        // ---- local_0 (one K-step) for both tiles; meanwhile the per-jet time vector of its bias -> bl1 buffer
+        gemm(0, wseq, dX[0], 1, idesc128, false, false);
+        if (has_b) gemm(1, wseq, dX[1], 1, idesc128, false, false);
+        {
+            Frags f;
+            float c[4];
+            frag_load(p.frag + ly.f_w0t, ly.KS_t(), 16, f);
+            stage(f, ly.KS_t(), 16, sw + Vec::in1_hi + 128, sw + Vec::in1_lo + 128, kIn1Stride, c);
+            if (g < kMaxJ) {
+                const int o = 8 * warp + 2 * t4;
+                sv[Vec::bl1 + g * 128 + o] = c[0] + __ldg(p.tab + ly.c0 + o);
+                sv[Vec::bl1 + g * 128 + o + 1] = c[1] + __ldg(p.tab + ly.c0 + o + 1);
+            }
+        }
+        __syncthreads();
+        // epilogue of a particle Linear: bias -> leaky-ReLU (-> + skip) -> bf16 operand tile (and fp32 X, pooling sums)
+        // kind 0: local_0 (X = lrelu(X + tv0); defines the skip); 1: fc_local1 (A = lrelu(ACC + bl1)); 2: fc_local2 (X = lrelu(X) + skip)
         auto epilogue = [&](int t, int kind, bool last) {
             wait_tile(t);
             const bool warp_live = __any_sync(0xffffffffu, live[t]);
@@ -486,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
             if (warp_live) {
                 tmem_ld32((kind == 1 ? dACC[t] : dX[t]) + lane_off + col0, v);
                 if (kind != 2) {
-                    const float* b = sv + (kind == 0 ? Vec::tv0 : Vec::bl1) + t * 128 + col0;
+                    const float* b = sv + Vec::bl1 + (2 * t + seg[t]) * 128 + col0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(b + j);
@@ -497,7 +600,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                 for (int j = 0; j < 32; ++j) v[j] = lrelu(v[j]);
                 if (kind != 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = live[t] ? v[j] : 0.0f;   // select: a dead row may hold anything
+                    for (int j = 0; j < 32; ++j) v[j] = live[t] ? v[j] : 0.0f;   // select: an unused row may hold anything
                     if (skip_on) {
                         if (kind == 0) {
 #pragma unroll
@@ -508,10 +611,10 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
                                 const uint4 s4 = *skip_chunk(sSkip(t), r, 4 * cq + c);
-                                const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+                                const uint32_t sk[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
                                 for (int i = 0; i < 4; ++i) {
-                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&sw[i]));
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&sk[i]));
                                     v[8 * c + 2 * i] += f.x; v[8 * c + 2 * i + 1] += f.y;
                                 }
                             }
@@ -519,105 +622,101 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                     }
                     tmem_st32(dX[t] + lane_off + col0, v);
                     if (last && p.hidden_out && live[t]) {   // the last local hidden (EPiCWrapper.forward(output_hidden_local=True), epic.py:159-160)
-                        float* h = p.hidden_out + ((size_t)(jet0 + t) * p.N + r) * kH + col0;
+                        float* h = p.hidden_out + ((size_t)jetr[t] * p.N + slot[t]) * kH + col0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(h + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
                 }
                 store_row(sA(t), r, col0, v);
-                if (kind != 1) {   // masked column sums for the next pooling (dead rows are zero already)
+                if (kind != 1) {   // column sums for the next pooling (unused rows are zero already)
                     warp_halving_sum32(v, lane);
                     sv[Vec::part + t * 16 * 32 + warp * 32 + halving_index32(lane)] = v[0];
                 }
             } else if (kind != 1) {
                 sv[Vec::part + t * 16 * 32 + warp * 32 + lane] = 0.0f;
             }
-            if (kind != 1 && last && p.hidden_out && !live[t] && jet0 + t < p.B && r < p.N) {
-                // x * mask: zero, except in a jet without particles, whose mean pool is 0 / 0 (epic.py:141) and NaN * 0 = NaN
-                const float z = s_cnt[t] == 0 ? __int_as_float(0x7fc00000) : 0.0f;
-                float* h = p.hidden_out + ((size_t)(jet0 + t) * p.N + r) * kH + col0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(h + j) = make_float4(z, z, z, z);
-            }
         };
         WIDE_TRACE(2);
         epilogue(0, 0, false);
         WIDE_TRACE(3);
         publish();
-        if (L > 0) gemm(0, wseq + 1, dACC[0], 8, idesc128, false, false);           // fc_local1 of layer 0, tile A
+        gemm(0, wseq + 1, dACC[0], 8, idesc128, false, false);                       // fc_local1 of layer 0, tile A
         if (has_b) epilogue(1, 0, false);
         publish();
         WIDE_TRACE(4);
         matrix_done();                                                               // local_0 served both tiles
-        if (has_b && L > 0) gemm(1, wseq, dACC[1], 8, idesc128, false, false);
-        // ---- EPiC_Projection globals (epic.py:187-190)
+        if (has_b) gemm(1, wseq, dACC[1], 8, idesc128, false, false);
+        // ---- EPiC_Projection globals (epic.py:187-190): g0 = lrelu(G0 [mean, sum, ctx]), g1 = lrelu(G1 g0), xg = lrelu(G2 g1)
         {
-            float acc[kJ];
-            RowB rb;
-            load_rows_bf16(p.big + ly.g0, ly.K0(), rb);
+            Frags f;
+            float c[4];
+            frag_load(p.frag + ly.f_g0, ly.KS_0(), 16, f);
             pool_to_input();
             __syncthreads();
-            dot_rows_bf16(rb, ly.K0(), s_in, Vec::in_ld, acc);
-            load_rows_bf16(p.big + ly.g1, 128, rb);
-            RowF rf;
-            load_rows_f32(p.tab + ly.g2, 128, Gp, rf);
-            if ((tid & 3) == 0)
-#pragma unroll
-                for (int j = 0; j < kJ; ++j) sv[Vec::g0 + j * 128 + (tid >> 2)] = lrelu(acc[j] + __ldg(p.tab + ly.b_g0 + (tid >> 2)));
+            stage(f, ly.KS_0(), 16, sw + Vec::in1_hi, sw + Vec::in1_lo, kIn1Stride, c);
+            frag_load(p.frag + ly.f_g1, 8, 16, f);
+            if (g < kMaxJ) {
+                const int o = 8 * warp + 2 * t4;
+                put_pair(Vec::gva_hi, Vec::gva_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(p.tab + ly.b_g0 + o)), lrelu(c[1] + __ldg(p.tab + ly.b_g0 + o + 1)));
+            }
             __syncthreads();
-            dot_rows_bf16(rb, 128, sv + Vec::g0, 128, acc);
-            if ((tid & 3) == 0)
-#pragma unroll
-                for (int j = 0; j < kJ; ++j) sv[Vec::g1 + j * 128 + (tid >> 2)] = lrelu(acc[j] + __ldg(p.tab + ly.b_g1 + (tid >> 2)));
+            stage(f, 8, 16, sw + Vec::gva_hi, sw + Vec::gva_lo, kGvStride, c);
+            frag_load(p.frag + ly.f_g2, 8, Gq / 8, f);
+            if (g < kMaxJ) {
+                const int o = 8 * warp + 2 * t4;
+                put_pair(Vec::gvb_hi, Vec::gvb_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(p.tab + ly.b_g1 + o)), lrelu(c[1] + __ldg(p.tab + ly.b_g1 + o + 1)));
+            }
             __syncthreads();
-            dot_rows_f32(rf, 128, sv + Vec::g1, 128, acc);
-            if ((tid & 3) == 0 && (tid >> 2) < Gp) {
-                const int o = tid >> 2;
-#pragma unroll
-                for (int j = 0; j < kJ; ++j) {
-                    const float xg = o < G ? lrelu(acc[j] + __ldg(p.tab + ly.b_g2 + o)) : 0.0f;
-                    s_in[j * Vec::in_ld + 256 + TXp + o] = xg;
-                    sv[Vec::skg + j * kMaxG + o] = skip_on ? xg : 0.0f;
-                }
+            stage(f, 8, Gq / 8, sw + Vec::gvb_hi, sw + Vec::gvb_lo, kGvStride, c);
+            if (g < kMaxJ && warp < Gq / 8) {
+                const int o = 8 * warp + 2 * t4;
+                const float x0 = o < G ? lrelu(c[0] + __ldg(p.tab + ly.b_g2 + o)) : 0.0f, x1 = o + 1 < G ? lrelu(c[1] + __ldg(p.tab + ly.b_g2 + o + 1)) : 0.0f;
+                sv[Vec::xg + g * kMaxGq + o] = x0; sv[Vec::xg + g * kMaxGq + o + 1] = x1;
+                sv[Vec::skg + g * kMaxGq + o] = skip_on ? x0 : 0.0f; sv[Vec::skg + g * kMaxGq + o + 1] = skip_on ? x1 : 0.0f;
+                put_pair(Vec::in1_hi, Vec::in1_lo, kIn1Stride, 128 + TXq / 2 + 4 * warp + t4, x0, x1);
             }
             __syncthreads();
         }
         WIDE_TRACE(5);
         // ---- EPiC layers (epic.py:217-241, 152-155)
         for (int l = 0; l < L; ++l) {
-            if (l == 1) WIDE_TRACE(6);
             const float* tl = p.tab + ly.layer0 + (size_t)l * ly.layer_stride;
+            const uint2* fl = p.frag + ly.f_layer0 + (size_t)l * ly.f_layer_stride;
+            if (l == 1) WIDE_TRACE(6);
             {   // per-jet path: fc_global1 -> fc_global2 (+ residual) -> the per-jet part of fc_local1
-                float acc[kJ];
-                RowB rb;
-                RowF rf2, rf3;
-                load_rows_bf16(p.big + ly.wg1_0 + (size_t)l * ly.wg1_stride, ly.K1(), rb);
-                load_rows_f32(tl + ly.o_wg2, 128, Gp, rf2);
-                load_rows_f32(tl + ly.o_wl1g, ly.K2(), 128, rf3);
+                Frags f;
+                float c[4];
+                frag_load(fl + ly.fo_wg1, ly.KS_1(), 16, f);
                 if (l > 0) {
                     pool_to_input();
                     __syncthreads();
                 }
-                dot_rows_bf16(rb, ly.K1(), s_in, Vec::in_ld, acc);
-                if ((tid & 3) == 0)
-#pragma unroll
-                    for (int j = 0; j < kJ; ++j) sv[Vec::g1 + j * 128 + (tid >> 2)] = lrelu(acc[j] + __ldg(tl + ly.o_blg1 + (tid >> 2)));
-                __syncthreads();
-                dot_rows_f32(rf2, 128, sv + Vec::g1, 128, acc);
-                if ((tid & 3) == 0 && (tid >> 2) < Gp) {
-                    const int o = tid >> 2;
-#pragma unroll
-                    for (int j = 0; j < kJ; ++j) {
-                        const float xm = o < G ? lrelu(acc[j] + __ldg(tl + ly.o_blg2 + o) + s_in[j * Vec::in_ld + 256 + TXp + o]) : 0.0f;
-                        sv[Vec::cx + j * (kMaxTX + kMaxG) + TXp + o] = xm;                               // fc_local1 sees the layer's own output
-                        s_in[j * Vec::in_ld + 256 + TXp + o] = xm + sv[Vec::skg + j * kMaxG + o];        // the next layer the skipped one (epic.py:155)
-                    }
+                stage(f, ly.KS_1(), 16, sw + Vec::in1_hi, sw + Vec::in1_lo, kIn1Stride, c);
+                frag_load(fl + ly.fo_wg2, 8, Gq / 8, f);
+                if (g < kMaxJ) {
+                    const int o = 8 * warp + 2 * t4;
+                    put_pair(Vec::gva_hi, Vec::gva_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(tl + ly.o_blg1 + o)), lrelu(c[1] + __ldg(tl + ly.o_blg1 + o + 1)));
                 }
                 __syncthreads();
-                dot_rows_f32(rf3, ly.K2(), sv + Vec::cx, kMaxTX + kMaxG, acc);
-                if ((tid & 3) == 0)
-#pragma unroll
-                    for (int j = 0; j < kJ; ++j) sv[Vec::bl1 + j * 128 + (tid >> 2)] = acc[j] + __ldg(tl + ly.o_bl1 + (tid >> 2));
+                stage(f, 8, Gq / 8, sw + Vec::gva_hi, sw + Vec::gva_lo, kGvStride, c);
+                frag_load(fl + ly.fo_wl1g, ly.KS_2(), 16, f);
+                if (g < kMaxJ && warp < Gq / 8) {
+                    const int o = 8 * warp + 2 * t4;
+                    float* xg = sv + Vec::xg + g * kMaxGq + o;
+                    const float* sk = sv + Vec::skg + g * kMaxGq + o;
+                    const float m0 = o < G ? lrelu(c[0] + __ldg(tl + ly.o_blg2 + o) + xg[0]) : 0.0f,
+                                m1 = o + 1 < G ? lrelu(c[1] + __ldg(tl + ly.o_blg2 + o + 1) + xg[1]) : 0.0f;
+                    put_pair(Vec::cx_hi, Vec::cx_lo, kCxStride, TXq / 2 + 4 * warp + t4, m0, m1);              // fc_local1 sees the layer's own output
+                    xg[0] = m0 + sk[0]; xg[1] = m1 + sk[1];                                                    // the next layer the skipped one (epic.py:155)
+                    put_pair(Vec::in1_hi, Vec::in1_lo, kIn1Stride, 128 + TXq / 2 + 4 * warp + t4, xg[0], xg[1]);
+                }
+                __syncthreads();
+                stage(f, ly.KS_2(), 16, sw + Vec::cx_hi, sw + Vec::cx_lo, kCxStride, c);
+                if (g < kMaxJ) {
+                    const int o = 8 * warp + 2 * t4;
+                    sv[Vec::bl1 + g * 128 + o] = c[0] + __ldg(tl + ly.o_bl1 + o);
+                    sv[Vec::bl1 + g * 128 + o + 1] = c[1] + __ldg(tl + ly.o_bl1 + o + 1);
+                }
                 __syncthreads();
             }
             const bool last = l == L - 1;
@@ -644,29 +743,25 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
             if (l == 1) WIDE_TRACE(13);
         }
         WIDE_TRACE(14);
-        // ---- output layer + discrete head (epic.py:158-162, mbm.py:105-113): h = out(x) * mask, logits = head(h[3:])
+        // ---- output layer + discrete head (epic.py:158-162, mbm.py:105-113) for the live particles
 #pragma unroll
-        for (int t = 0; t < kJ; ++t) {
+        for (int t = 0; t < 2; ++t) {
             if (t == 1 && !has_b) continue;
             wait_tile(t);
             if (cq == 0) {   // whole warps: tcgen05.ld is warp-collective
                 float v[32];
                 tmem_ld32(dACC[t] + lane_off, v);
-                if (r < p.N) {
-                    const size_t pidx = (size_t)(jet0 + t) * p.N + r;
-                    float h[16];
-                    const float z = s_cnt[t] == 0 ? __int_as_float(0x7fc00000) : 0.0f;   // h * mask; NaN * 0 in a jet without particles
+                if (live[t]) {
+                    const size_t pidx = (size_t)jetr[t] * p.N + slot[t];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) h[i] = live[t] ? v[i] : z;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) p.v_out[pidx * 3 + c] = h[c];
+                    for (int c = 0; c < 3; ++c) p.v_out[pidx * 3 + c] = v[c];
                     const float* hd = sv + Vec::head;
                     float z1[16], lg[8];
 #pragma unroll
                     for (int o = 0; o < 16; ++o) {   // head Linear 0 + SELU (rows >= Sh are zero in the table and unused)
                         float a = hd[256 + o];
 #pragma unroll
-                        for (int s = 0; s < 8; ++s) a = fmaf(hd[o * 16 + s], h[3 + s], a);
+                        for (int s = 0; s < 8; ++s) a = fmaf(hd[o * 16 + s], v[3 + s], a);
                         z1[o] = selu(a);
                     }
 #pragma unroll
@@ -674,7 +769,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                         float a = hd[256 + 16 + 256 + o];
 #pragma unroll
                         for (int s = 0; s < 16; ++s) a = fmaf(hd[256 + 16 + o * 16 + s], z1[s], a);
-                        lg[o] = Sh ? a : h[3 + o];
+                        lg[o] = Sh ? a : v[3 + o];
                     }
 #pragma unroll
                     for (int o = 0; o < 8; ++o)
@@ -697,18 +792,37 @@ __device__ long long g_wide_trace[32];
 // element (row o, k) of a K-major tile with 8-row groups `sbo` bytes apart -> bf16 index
 inline size_t tile_index(int o, int k, int sbo) { return ((size_t)(o / 8) * sbo + (size_t)(k / 8) * 128 + (o % 8) * 16 + (k % 8) * 2) / 2; }
 
+inline uint32_t host_pack_bf16(float lo, float hi) {
+    const __nv_bfloat16 a = __float2bfloat16(lo), b = __float2bfloat16(hi);
+    return (uint32_t)(*reinterpret_cast<const uint16_t*>(&a)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&b)) << 16);
+}
+// B fragments of y = W x for mma.sync m16n8k16 (col-major B): warp w owns outputs 8 w .. 8 w + 7; entry ((w KS + kk) 32 + lane) =
+// {W[n][16 kk + 2 t, + 1], W[n][16 kk + 2 t + 8, + 9]} with n = 8 w + lane / 4, t = lane % 4.  `w(n, k)` returns 0 outside the matrix.
+template <typename F>
+void put_frag(std::vector<uint2>& img, int base, int n_out, int ks, F w) {
+    for (int wp = 0; wp < n_out / 8; ++wp)
+        for (int kk = 0; kk < ks; ++kk)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int n = 8 * wp + lane / 4, k0 = 16 * kk + 2 * (lane % 4);
+                img[(size_t)base + ((size_t)wp * ks + kk) * 32 + lane] =
+                    make_uint2(host_pack_bf16(w(n, k0), w(n, k0 + 1)), host_pack_bf16(w(n, k0 + 8), w(n, k0 + 9)));
+            }
+}
+
 }  // namespace
 
 struct WideImage {
     void* image = nullptr;
     float* tab = nullptr;
-    __nv_bfloat16* big = nullptr;
+    uint2* frag = nullptr;
+    int32_t* pack = nullptr;      // pre-pass scratch, grown on demand (one evaluation at a time per model handle)
+    size_t pack_ints = 0;
     WideLayout lay;
 };
 
 bool wide_supported(const MmbEpicDims* d, int N) {
-    return d->dim_hidden_local == kH && d->dim_hidden_glob >= 1 && d->dim_hidden_glob <= kMaxG && d->dim_time_emb >= 1 && d->dim_time_emb <= kMaxT &&
-           d->dim_time_emb + d->dim_context <= kMaxTX && d->dim_context >= 0 && d->num_blocks >= 1 && d->num_blocks <= kMaxL &&
+    return d->dim_hidden_local == kH && d->dim_hidden_glob >= 1 && d->dim_hidden_glob <= kMaxGq && d->dim_time_emb >= 1 && d->dim_context >= 0 &&
+           d->dim_time_emb + d->dim_context <= kMaxTXq && d->num_blocks >= 1 && d->num_blocks <= kMaxL &&
            d->dim_continuous == 3 && d->vocab_size >= 1 && d->vocab_size <= 8 && d->disc_head_hidden >= 0 && d->disc_head_hidden <= 16 &&
            N >= 1 && N <= 128;
 }
@@ -718,7 +832,8 @@ void wide_free_image(EpicModel* m) {
     if (!w) return;
     if (w->image) cudaFree(w->image);
     if (w->tab) cudaFree(w->tab);
-    if (w->big) cudaFree(w->big);
+    if (w->frag) cudaFree(w->frag);
+    if (w->pack) cudaFree(w->pack);
     delete w;
     m->wide = nullptr;
 }
@@ -728,18 +843,19 @@ int wide_build_image(EpicModel* m, const float* W) {
     const MmbEpicLayout& Lo = m->layout;
     const WideLayout ly = make_layout(d);
     const int T = d.dim_time_emb, X = d.dim_context, TX = T + X, C = d.dim_cont_emb, D = d.dim_disc_emb, G = d.dim_hidden_glob, L = d.num_blocks,
-              S = d.vocab_size, Sh = d.disc_head_hidden, Dc = d.dim_continuous, H = kH;
+              S = d.vocab_size, Sh = d.disc_head_hidden, Dc = d.dim_continuous, H = kH, TXq = ly.TXq;
     const int K0 = T + C + D;
     std::vector<__nv_bfloat16> img((size_t)ly.n_seq * kSlot / 2, __float2bfloat16(0.0f));
     std::vector<float> tab((size_t)ly.tab_floats, 0.0f);
-    std::vector<__nv_bfloat16> big((size_t)ly.big_elems, __float2bfloat16(0.0f));
+    std::vector<uint2> frag((size_t)ly.frag_elems, make_uint2(0u, 0u));
     auto put = [&](int slot, int o, int k, double v) { img[(size_t)slot * kSlot / 2 + tile_index(o, k, 2048)] = __float2bfloat16((float)v); };
     auto put_bias = [&](int slot, int o, float b) {
         const __nv_bfloat16 hi = __float2bfloat16(b);
         img[(size_t)slot * kSlot / 2 + 32768 / 2 + tile_index(o, 0, 256)] = hi;
         img[(size_t)slot * kSlot / 2 + 32768 / 2 + tile_index(o, 1, 256)] = __float2bfloat16(b - __bfloat162float(hi));
     };
-    // local_0 with the embeddings folded in: operand columns [x_hi (3) | x_lo (3) | onehot (S)]
+    // local_0 with the embeddings folded in: operand columns [x_hi (3) | x_lo (3) | onehot (S)]; its time columns act on the
+    // jet's context vector (whose first T entries are the time embedding)
     for (int o = 0; o < H; ++o) {
         const float* w0 = W + Lo.local0_w + (size_t)o * K0;
         for (int j = 0; j < Dc; ++j) {
@@ -756,56 +872,63 @@ int wide_build_image(EpicModel* m, const float* W) {
         double c0 = W[Lo.local0_b + o];
         for (int c = 0; c < C; ++c) c0 += (double)w0[T + c] * W[Lo.emb_cont_b + c];
         tab[ly.c0 + o] = (float)c0;
-        for (int t = 0; t < T; ++t) tab[ly.w0t + (size_t)o * ly.Tp + t] = w0[t];
-    }
-    // projection globals: global_0 [H][mean | sum | ctx], global_1, global_2
-    for (int o = 0; o < H; ++o) {
-        const float* g0 = W + Lo.global0_w + (size_t)o * (2 * H + TX);
-        for (int k = 0; k < 2 * H + TX; ++k) big[ly.g0 + (size_t)o * ly.K0() + k] = __float2bfloat16(g0[k]);
-        for (int k = 0; k < H; ++k) big[ly.g1 + (size_t)o * 128 + k] = __float2bfloat16(W[Lo.global1_w + (size_t)o * H + k]);
         tab[ly.b_g0 + o] = W[Lo.global0_b + o];
         tab[ly.b_g1 + o] = W[Lo.global1_b + o];
     }
-    for (int o = 0; o < G; ++o) {
-        for (int k = 0; k < H; ++k) tab[ly.g2 + (size_t)o * 128 + k] = W[Lo.global2_w + (size_t)o * H + k];
-        tab[ly.b_g2 + o] = W[Lo.global2_b + o];
-    }
+    put_frag(frag, ly.f_w0t, 128, ly.KS_t(), [&](int n, int k) { return k < T ? W[Lo.local0_w + (size_t)n * K0 + k] : 0.0f; });
+    // projection globals: global_0 [H][mean | sum | ctx], global_1 [H][H], global_2 [G][H]
+    put_frag(frag, ly.f_g0, 128, ly.KS_0(), [&](int n, int k) { return k < 2 * H + TX ? W[Lo.global0_w + (size_t)n * (2 * H + TX) + k] : 0.0f; });
+    put_frag(frag, ly.f_g1, 128, 8, [&](int n, int k) { return W[Lo.global1_w + (size_t)n * H + k]; });
+    put_frag(frag, ly.f_g2, ly.Gq, 8, [&](int n, int k) { return n < G ? W[Lo.global2_w + (size_t)n * H + k] : 0.0f; });
+    for (int o = 0; o < G; ++o) tab[ly.b_g2 + o] = W[Lo.global2_b + o];
     for (int l = 0; l < L; ++l) {
         const float* Wl = W + Lo.layer0 + (size_t)l * Lo.layer_stride;
         float* tl = tab.data() + ly.layer0 + (size_t)l * ly.layer_stride;
-        __nv_bfloat16* wg1 = big.data() + ly.wg1_0 + (size_t)l * ly.wg1_stride;
+        const int fl = ly.f_layer0 + l * ly.f_layer_stride;
         const int Kg = 2 * H + G + TX, Kl = H + G + TX;
+        // fc_global1: reference columns [mean | sum | xg | ctx] -> input layout [mean | sum | ctx (TXq) | xg (Gq)]
+        put_frag(frag, fl + ly.fo_wg1, 128, ly.KS_1(), [&](int n, int k) {
+            const float* g1 = Wl + Lo.l_g1_w + (size_t)n * Kg;
+            if (k < 2 * H) return g1[k];
+            if (k < 2 * H + TXq) return k - 2 * H < TX ? g1[2 * H + G + (k - 2 * H)] : 0.0f;
+            return k - 2 * H - TXq < G ? g1[2 * H + (k - 2 * H - TXq)] : 0.0f;
+        });
+        put_frag(frag, fl + ly.fo_wg2, ly.Gq, 8, [&](int n, int k) { return n < G ? Wl[Lo.l_g2_w + (size_t)n * H + k] : 0.0f; });
+        // fc_local1 [local H | xg | ctx]: the local part streams as matrix 1 + 2l, the per-jet part acts on [ctx (TXq) | xm (Gq)]
+        put_frag(frag, fl + ly.fo_wl1g, 128, ly.KS_2(), [&](int n, int k) {
+            const float* l1 = Wl + Lo.l_l1_w + (size_t)n * Kl;
+            if (k < TXq) return k < TX ? l1[H + G + k] : 0.0f;
+            return k - TXq < G ? l1[H + (k - TXq)] : 0.0f;
+        });
         for (int o = 0; o < H; ++o) {
-            const float* g1 = Wl + Lo.l_g1_w + (size_t)o * Kg;       // reference columns [mean | sum | xg | ctx] -> [mean | sum | ctx | xg]
-            for (int k = 0; k < 2 * H; ++k) wg1[(size_t)o * ly.K1() + k] = __float2bfloat16(g1[k]);
-            for (int k = 0; k < TX; ++k) wg1[(size_t)o * ly.K1() + 256 + k] = __float2bfloat16(g1[2 * H + G + k]);
-            for (int k = 0; k < G; ++k) wg1[(size_t)o * ly.K1() + 256 + ly.TXp + k] = __float2bfloat16(g1[2 * H + k]);
             tl[ly.o_blg1 + o] = Wl[Lo.l_g1_b + o];
-            const float* l1 = Wl + Lo.l_l1_w + (size_t)o * Kl;       // [local H | xg | ctx]: the local part streams as matrix 1 + 2l
-            for (int k = 0; k < H; ++k) put(1 + 2 * l, o, k, l1[k]);
-            for (int k = 0; k < TX; ++k) tl[ly.o_wl1g + (size_t)o * ly.K2() + k] = l1[H + G + k];
-            for (int k = 0; k < G; ++k) tl[ly.o_wl1g + (size_t)o * ly.K2() + ly.TXp + k] = l1[H + k];
             tl[ly.o_bl1 + o] = Wl[Lo.l_l1_b + o];
+            for (int k = 0; k < H; ++k) put(1 + 2 * l, o, k, Wl[Lo.l_l1_w + (size_t)o * Kl + k]);
             for (int k = 0; k < H; ++k) put(2 + 2 * l, o, k, Wl[Lo.l_l2_w + (size_t)o * H + k]);
             put_bias(2 + 2 * l, o, Wl[Lo.l_l2_b + o]);
         }
-        for (int o = 0; o < G; ++o) {
-            for (int k = 0; k < H; ++k) tl[ly.o_wg2 + (size_t)o * 128 + k] = Wl[Lo.l_g2_w + (size_t)o * H + k];
-            tl[ly.o_blg2 + o] = Wl[Lo.l_g2_b + o];
-        }
+        for (int o = 0; o < G; ++o) tl[ly.o_blg2 + o] = Wl[Lo.l_g2_b + o];
     }
     for (int o = 0; o < Dc + S; ++o) {
         for (int k = 0; k < H; ++k) put(1 + 2 * L, o, k, W[Lo.out_w + (size_t)o * H + k]);
         put_bias(1 + 2 * L, o, W[Lo.out_b + o]);
     }
-    if (Sh) {
+    if (Sh) {   // discrete head; a padded slot's logits are head(0) (the reference masks before the head, mbm.py:105-111)
+        std::vector<double> z1(Sh);
         for (int o = 0; o < Sh; ++o) {
             for (int s = 0; s < S; ++s) tab[ly.head0 + o * 16 + s] = W[Lo.head0_w + (size_t)o * S + s];
             tab[ly.b_head0 + o] = W[Lo.head0_b + o];
+            const double a = W[Lo.head0_b + o];
+            z1[o] = 1.0507009873554804934193349852946 * (a > 0 ? a : 1.6732632423543772848170429916717 * (exp(a) - 1.0));
         }
         for (int o = 0; o < S; ++o) {
-            for (int s = 0; s < Sh; ++s) tab[ly.head2 + o * 16 + s] = W[Lo.head2_w + (size_t)o * Sh + s];
+            double acc = W[Lo.head2_b + o];
+            for (int s = 0; s < Sh; ++s) {
+                tab[ly.head2 + o * 16 + s] = W[Lo.head2_w + (size_t)o * Sh + s];
+                acc += (double)W[Lo.head2_w + (size_t)o * Sh + s] * z1[s];
+            }
             tab[ly.b_head2 + o] = W[Lo.head2_b + o];
+            tab[ly.dead_logits + o] = (float)acc;
         }
     }
     WideImage* w = new WideImage();
@@ -813,10 +936,10 @@ int wide_build_image(EpicModel* m, const float* W) {
     m->wide = w;
     int rc = cuda_ok(cudaMalloc(&w->image, img.size() * 2), "cudaMalloc wide image");
     if (!rc) rc = cuda_ok(cudaMalloc(&w->tab, tab.size() * 4), "cudaMalloc wide table");
-    if (!rc) rc = cuda_ok(cudaMalloc(&w->big, big.size() * 2), "cudaMalloc wide global matrices");
+    if (!rc) rc = cuda_ok(cudaMalloc(&w->frag, frag.size() * sizeof(uint2)), "cudaMalloc wide fragments");
     if (!rc) rc = cuda_ok(cudaMemcpy(w->image, img.data(), img.size() * 2, cudaMemcpyHostToDevice), "wide image upload");
     if (!rc) rc = cuda_ok(cudaMemcpy(w->tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice), "wide table upload");
-    if (!rc) rc = cuda_ok(cudaMemcpy(w->big, big.data(), big.size() * 2, cudaMemcpyHostToDevice), "wide matrices upload");
+    if (!rc) rc = cuda_ok(cudaMemcpy(w->frag, frag.data(), frag.size() * sizeof(uint2), cudaMemcpyHostToDevice), "wide fragments upload");
     if (rc) wide_free_image(m);
     return rc;
 }
@@ -829,19 +952,29 @@ int wide_read_trace(long long* out, int n) {
 
 int launch_epic_forward_wide(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask, const float* temb, int temb_stride,
                              int B, int N, float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream) {
-    const WideImage* w = static_cast<const WideImage*>(m->wide);
+    WideImage* w = static_cast<WideImage*>(m->wide);
     if (!w) return fail(MMB_EUNSUPPORTED, "wide EPiC trunk: no operand image for this model");
     if (B == 0 || N == 0) return MMB_OK;
     if (N > 128) return fail(MMB_EUNSUPPORTED, "wide EPiC trunk handles up to 128 particle slots per jet (got %d)", N);
+    if (B >= (1 << 20)) return fail(MMB_EUNSUPPORTED, "wide EPiC trunk: at most 2^20 - 1 jets per call");
+    if (w->pack_ints < pack_ints(B)) {   // the pre-pass scratch lives on the handle and grows with the largest batch seen
+        if (w->pack) { cudaStreamSynchronize(stream); cudaFree(w->pack); w->pack = nullptr; w->pack_ints = 0; }
+        if (int rc = cuda_ok(cudaMalloc(&w->pack, pack_ints(B) * sizeof(int32_t)), "cudaMalloc wide pre-pass scratch")) return rc;
+        w->pack_ints = pack_ints(B);
+    }
     WideParams p{};
-    p.image = static_cast<const uint8_t*>(w->image); p.tab = w->tab; p.big = w->big; p.lay = w->lay;
+    p.image = static_cast<const uint8_t*>(w->image); p.tab = w->tab; p.frag = w->frag; p.lay = w->lay; p.pack = w->pack;
     p.x = x; p.k = k; p.mask = mask; p.temb = temb; p.temb_stride = temb_stride; p.B = B; p.N = N;
     p.v_out = v_out; p.logits_out = logits_out; p.hidden_out = hidden_out;
     static const bool trace_on = [] { const char* e = getenv("MMB_WIDE_TRACE"); return e && e[0] == '1'; }();   // debug knob
     if (trace_on) cudaGetSymbolAddress(reinterpret_cast<void**>(&p.trace), g_wide_trace);
+    if (int rc = cuda_ok(cudaMemsetAsync(w->pack, 0, 8 * sizeof(int32_t), stream), "wide pre-pass counters")) return rc;
+    wide_pack_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, N, w->lay.S, w->tab + w->lay.dead_logits, v_out, logits_out, hidden_out, w->pack);
+    wide_tiles_kernel<<<(B + 255) / 256, 256, 0, stream>>>(w->pack, B);
+    if (int rc = cuda_ok(cudaGetLastError(), "wide pre-pass launch")) return rc;
     if (int rc = cuda_ok(cudaFuncSetAttribute(epic_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "wide smem attribute"))
         return rc;
-    const int pairs = (B + 1) / 2;
+    const int pairs = (B + 1) / 2;   // upper bound of the tile pairs (the kernel reads the count the pre-pass left)
     const int grid = pairs < m->sm_count ? pairs : m->sm_count;
     epic_wide_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
     return cuda_ok(cudaGetLastError(), "epic_wide launch");
