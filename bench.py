@@ -168,7 +168,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "bf16", "fp32"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "wide"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 / C5 side measurements")
     args = ap.parse_args()
@@ -418,7 +418,7 @@ def side_workload_line(args, torch, dist, _native, device, pk, rank, world, W, K
                 "gpu_launches": 5 * ((1 << 20) // B_PER_GPU // world)}
     with ClockSampler(device.index or 0) as clocks:
         rec = secondary_configs(torch, _native, device, pk, only=args.workload, reps=max(K, 2), warm=max(W, 2))
-    key = "C3_transepic_evaluation" if args.workload == "c3" else "C4_absorbing_generation"
+    key = {"c3": "C3_transepic_evaluation", "c4": "C4_absorbing_generation", "wide": "wide_epic"}[args.workload]
     r = rec[key]
     rate = r["jet_evals_per_s"] if args.workload == "c3" else r["jets_per_s"]
     t = torch.tensor([r["ms"]], device=device, dtype=torch.float64)
@@ -454,7 +454,50 @@ def secondary_configs(torch, _native, device, pk, only=None, reps=None, warm=Non
         out.update(_c3(torch, _native, device, pk, timed, reps or 3, warm or 2))
     if only in (None, "c4"):
         out.update(_c4(torch, _native, device, pk, timed, reps or 2, warm or 1))
+    if only in (None, "wide"):
+        out.update(_wide(torch, _native, device, pk, timed, reps or 3, warm or 2))
     return out
+
+
+def _wide(torch, _native, device, pk, timed, reps, warm):
+    """The C2 workload on an encoder of the reference's CLASS-DEFAULT widths (EPiCNetwork: num_blocks = 6, dim_hidden_local =
+    128, dim_hidden_global = 10; architectures/epic.py:99-101) — the shape where the trunk is GEMM work: 0.415 MFLOP per
+    particle and evaluation (12 x 2 x 128 x 128 + local_0 + output layer), all 128 slots of a jet in the reference."""
+    from multimodal_particles_b200 import MultiModalBridgeMatching
+    from multimodal_particles_b200.config_classes.multimodal_bridge_matching_config import MultimodalBridgeMatchingConfig
+    from multimodal_particles_b200.databatch import jetclass_like_databatch
+    from multimodal_particles_b200.epic import as_u8
+    B = 4096
+    cfg = MultimodalBridgeMatchingConfig()
+    e = cfg.encoder
+    e.dim_hidden_local, e.num_blocks, e.dim_hidden_glob = 128, 6, 10
+    cfg.data.max_num_particles, cfg.bridge.num_timesteps = N_PART, N_TIMESTEPS
+    torch.manual_seed(0)
+    model = MultiModalBridgeMatching(cfg).to(device)
+    native = model.encoder.native_model(device)
+    b = jetclass_like_databatch(B, N_PART, generator=torch.Generator().manual_seed(1234))
+    x, k, m = b.source_continuous.to(device).contiguous(), as_u8(b.source_discrete.to(device)), as_u8(b.source_mask.to(device))
+    ones = torch.ones_like(m)
+    table = model.step_table()
+    temb = table.temb[:1].to(device).contiguous()
+    flop_particle = 2 * (12 * 128 * 128 + 16 * 128 + 128 * 11)
+    flop_eval = flop_particle * B * N_PART     # the reference's count: every slot goes through the network
+
+    def line(ms_, note):
+        tf = flop_eval / (ms_ * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tf / pk["bf16"], "ms_per_launch": ms_, "rows": note}
+
+    ev = timed(lambda: native.forward(x, k, m, temb, precision="bf16"), reps, warm)
+    ev_full = timed(lambda: native.forward(x, k, ones, temb, precision="bf16"), reps, warm)
+    ev_fp32 = timed(lambda: native.forward(x[:512], k[:512], m[:512], temb, precision="fp32"), 1, 1) * (B / 512)
+    gen = timed(lambda: native.generate(x.clone(), k.clone(), m, table, seed=1, jet_offset=0, precision="bf16"), max(1, reps // 2), 1)
+    live = float(m.float().mean().item())
+    return {"wide_epic": {"workload": "EPiC at the class-default widths (H=128, L=6, G=10), B=4096, N=128: one evaluation and a 99-step generation",
+                          "ms": gen, "jets_per_s": B / (gen * 1e-3), "evaluation_ms": ev, "jet_evals_per_s": B / (ev * 1e-3),
+                          "evaluation_ms_fp32_cuda_cores": ev_fp32, "mean_live_fraction": live,
+                          "roofline": line(ev, "JetClass-like mask (mean 45 live of 128), live particles only, one or two jets per 128-row tile"),
+                          "roofline_dense": line(ev_full, "all 128 slots live"),
+                          "executed_tflops": flop_eval * live / (ev * 1e-3) / 1e12}}
 
 
 def _c3(torch, _native, device, pk, timed, reps, warm):

@@ -192,7 +192,7 @@ struct WideLayout {
     int o_blg1, o_blg2, o_bl1;
     int head0, b_head0, head2, b_head2, dead_logits;   // [16][16], [16], [16][16], [16], [8]: logits of a padded slot = head(0)
     int tab_floats;
-    // fragment image (uint2 units): matrix m occupies (N / 8) * KS * 32 entries
+    // fragment image (uint2 units): a matrix occupies (N / 8) * (KS rounded up to even) * 32 entries
     int f_w0t, f_g0, f_g1, f_g2;
     int f_layer0, f_layer_stride, fo_wg1, fo_wg2, fo_wl1g;
     int frag_elems;
@@ -222,12 +222,12 @@ WideLayout make_layout(const MmbEpicDims& d) {
     w.head0 = take(256); w.b_head0 = take(16); w.head2 = take(256); w.b_head2 = take(16); w.dead_logits = take(8);
     w.tab_floats = o;
     int f = 0;
-    auto tf = [&](int n_out, int ks) { const int at = f; f += (n_out / 8) * ks * 32; return at; };
+    auto tf = [&](int n_out, int ks) { const int at = f; f += (n_out / 8) * ((ks + 1) & ~1) * 32; return at; };   // k-steps stored in pairs
     w.f_w0t = tf(128, w.KS_t()); w.f_g0 = tf(128, w.KS_0()); w.f_g1 = tf(128, 8); w.f_g2 = tf(w.Gq, 8);
     w.f_layer0 = f;
     {
         int p = 0;
-        auto tk = [&](int n_out, int ks) { const int at = p; p += (n_out / 8) * ks * 32; return at; };
+        auto tk = [&](int n_out, int ks) { const int at = p; p += (n_out / 8) * ((ks + 1) & ~1) * 32; return at; };
         w.fo_wg1 = tk(128, w.KS_1()); w.fo_wg2 = tk(w.Gq, 8); w.fo_wl1g = tk(128, w.KS_2());
         w.f_layer_stride = p;
     }
@@ -338,6 +338,9 @@ struct Vec {
 constexpr int kSmemBytes = kOffVec + Vec::words * 4;
 static_assert(kSmemBytes + 512 <= 227 * 1024, "shared memory budget");
 
+template <int N>
+struct FragRegs { uint2 b[N]; };   // weight fragments of one stage of the per-jet path, in registers
+
 __device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a2, const uint2 b) {   // rows 8..15 of A are zero
     asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b.x), "r"(b.y));
@@ -429,37 +432,58 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
         if (tid == 0 && wseq + 2 < total_mats) issue_load(wseq + 2);
         ++wseq;
     };
+    // (A dedicated issuer warp fed through arrive-only barriers was tried: the issue latency leaves the epilogue warps, but a 17th
+    // warp costs a 4-warp register granule — 96 registers, spills in the per-jet path — and the epilogues then wait for the GEMM
+    // they used to overlap: 0.455 ms against 0.443 ms at 4096 jets.)
     auto publish = [&]() {   // operand tile / TMEM writes of all threads -> visible to the MMA proxy, then the block barrier
         tc_fence_before();
         fence_proxy_async();
         __syncthreads();
     };
+    auto compute_sync = [&]() { __syncthreads(); };
 
     // ---- one stage of the per-jet path: c = W in for the jets of the CTA (rows g < kMaxJ of an m16 tile).  Warp w < n_warps owns
     // outputs 8 w .. 8 w + 7; on return lane (g, t4) holds outputs 8 w + 2 t4, + 1 of jet g in c[0], c[1].  The weight fragments
     // do not depend on the data: `frag_load` issues all of a stage's loads at once (one L2 latency per stage) and may be called
     // before the barrier that publishes the stage's input.
     constexpr int kMaxKS = (256 + kMaxTXq + kMaxGq) / 16;
-    struct Frags { uint2 b[kMaxKS]; };
-    auto frag_load = [&](const uint2* base, int KS, int n_warps, Frags& f) {
+    static_assert(kMaxKS % 2 == 0, "stage() walks the k-steps in pairs");
+    auto frag_load = [&](const uint2* base, int KS, int n_warps, auto& f) {   // one 16-byte load per lane and pair of k-steps
+        constexpr int cap = sizeof(f.b) / sizeof(uint2);
+        static_assert(cap % 2 == 0, "fragments travel in pairs of k-steps");
+        const uint4* b4 = reinterpret_cast<const uint4*>(base) + (size_t)warp * ((KS + 1) / 2) * 32 + lane;
 #pragma unroll
-        for (int kk = 0; kk < kMaxKS; ++kk)
-            f.b[kk] = (warp < n_warps && kk < KS) ? __ldg(base + ((size_t)warp * KS + kk) * 32 + lane) : make_uint2(0u, 0u);
+        for (int kk = 0; kk < cap; kk += 2) {
+            const uint4 q = (warp < n_warps && kk < KS) ? __ldg(b4 + (kk / 2) * 32) : make_uint4(0u, 0u, 0u, 0u);
+            f.b[kk] = make_uint2(q.x, q.y);
+            f.b[kk + 1] = make_uint2(q.z, q.w);
+        }
     };
-    auto stage = [&](const Frags& f, int KS, int n_warps, const uint32_t* in_hi, const uint32_t* in_lo, int stride, float (&c)[4]) {
-        c[0] = c[1] = c[2] = c[3] = 0.0f;
+    // `lo_from`: first k-step whose input also enters with its low half (the 256 pooled features of fc_global1 / global_0 enter as
+    // plain bf16 like every activation of the particle GEMMs; the m16n8k16 rate, one per 8 cycles per scheduler, is what bounds a stage)
+    auto stage = [&](const auto& f, int KS, int n_warps, const uint32_t* in_hi, const uint32_t* in_lo, int stride, float (&c)[4], int lo_from = 0) {
+        constexpr int cap = sizeof(f.b) / sizeof(uint2);
+        const uint2* fb = f.b;
+        // four independent accumulation chains (hi / lo x even / odd k-step): a chain of dependent MMAs costs ~20 cycles a link
+        float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f}, cc[4] = {0.f, 0.f, 0.f, 0.f}, cd[4] = {0.f, 0.f, 0.f, 0.f};
         if (warp < n_warps) {
             const uint32_t* h = in_hi + g * stride + t4;
             const uint32_t* l = in_lo + g * stride + t4;
+            const bool on = g < kMaxJ;
 #pragma unroll
-            for (int kk = 0; kk < kMaxKS; ++kk) {
+            for (int kk = 0; kk < cap; kk += 2) {
                 if (kk < KS) {
-                    const bool on = g < kMaxJ;
-                    mma_bf16(c, on ? h[8 * kk] : 0u, on ? h[8 * kk + 4] : 0u, f.b[kk]);
-                    mma_bf16(c, on ? l[8 * kk] : 0u, on ? l[8 * kk + 4] : 0u, f.b[kk]);
+                    mma_bf16(ca, on ? h[8 * kk] : 0u, on ? h[8 * kk + 4] : 0u, fb[kk]);
+                    if (kk >= lo_from) mma_bf16(cb, on ? l[8 * kk] : 0u, on ? l[8 * kk + 4] : 0u, fb[kk]);
+                }
+                if (kk + 1 < KS) {
+                    mma_bf16(cc, on ? h[8 * kk + 8] : 0u, on ? h[8 * kk + 12] : 0u, fb[kk + 1]);
+                    if (kk + 1 >= lo_from) mma_bf16(cd, on ? l[8 * kk + 8] : 0u, on ? l[8 * kk + 12] : 0u, fb[kk + 1]);
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = (ca[i] + cc[i]) + (cb[i] + cd[i]);
     };
     // pooled sums of both tiles -> [mean | sum] of the jets' input vectors (epic.py:136-143); thread = (jet, column pair)
     auto pool_to_input = [&]() {
@@ -534,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                 sw[Vec::cx_hi + j * kCxStride + w] = hi; sw[Vec::cx_lo + j * kCxStride + w] = lo;
             }
         }
-        __syncthreads();
+        compute_sync();
         // ---- per-thread facts of the pair; first operand rows [x_hi, x_lo, onehot(k)]
         int slot[2], seg[2], jetr[2];
         bool live[2];
@@ -569,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
         gemm(0, wseq, dX[0], 1, idesc128, false, false);
         if (has_b) gemm(1, wseq, dX[1], 1, idesc128, false, false);
         {
-            Frags f;
+            FragRegs<kMaxTXq / 16> f;
             float c[4];
             frag_load(p.frag + ly.f_w0t, ly.KS_t(), 16, f);
             stage(f, ly.KS_t(), 16, sw + Vec::in1_hi + 128, sw + Vec::in1_lo + 128, kIn1Stride, c);
@@ -579,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                 sv[Vec::bl1 + g * 128 + o + 1] = c[1] + __ldg(p.tab + ly.c0 + o + 1);
             }
         }
-        __syncthreads();
+        compute_sync();
         // epilogue of a particle Linear: bias -> leaky-ReLU (-> + skip) -> bf16 operand tile (and fp32 X, pooling sums)
         // kind 0: local_0 (X = lrelu(X + tv0); defines the skip); 1: fc_local1 (A = lrelu(ACC + bl1)); 2: fc_local2 (X = lrelu(X) + skip)
         auto epilogue = [&](int t, int kind, bool last) {
@@ -648,26 +672,27 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
         if (has_b) gemm(1, wseq, dACC[1], 8, idesc128, false, false);
         // ---- EPiC_Projection globals (epic.py:187-190): g0 = lrelu(G0 [mean, sum, ctx]), g1 = lrelu(G1 g0), xg = lrelu(G2 g1)
         {
-            Frags f;
+            FragRegs<kMaxKS> f;
+            FragRegs<8> f1, f2;
             float c[4];
-            frag_load(p.frag + ly.f_g0, ly.KS_0(), 16, f);
+            frag_load(p.frag + ly.f_g0, ly.KS_0(), 16, f);     // all three stages' fragments in flight at once: one L2 latency
+            frag_load(p.frag + ly.f_g1, 8, 16, f1);
+            frag_load(p.frag + ly.f_g2, 8, Gq / 8, f2);
             pool_to_input();
-            __syncthreads();
-            stage(f, ly.KS_0(), 16, sw + Vec::in1_hi, sw + Vec::in1_lo, kIn1Stride, c);
-            frag_load(p.frag + ly.f_g1, 8, 16, f);
+            compute_sync();
+            stage(f, ly.KS_0(), 16, sw + Vec::in1_hi, sw + Vec::in1_lo, kIn1Stride, c, 16);
             if (g < kMaxJ) {
                 const int o = 8 * warp + 2 * t4;
                 put_pair(Vec::gva_hi, Vec::gva_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(p.tab + ly.b_g0 + o)), lrelu(c[1] + __ldg(p.tab + ly.b_g0 + o + 1)));
             }
-            __syncthreads();
-            stage(f, 8, 16, sw + Vec::gva_hi, sw + Vec::gva_lo, kGvStride, c);
-            frag_load(p.frag + ly.f_g2, 8, Gq / 8, f);
+            compute_sync();
+            stage(f1, 8, 16, sw + Vec::gva_hi, sw + Vec::gva_lo, kGvStride, c);
             if (g < kMaxJ) {
                 const int o = 8 * warp + 2 * t4;
                 put_pair(Vec::gvb_hi, Vec::gvb_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(p.tab + ly.b_g1 + o)), lrelu(c[1] + __ldg(p.tab + ly.b_g1 + o + 1)));
             }
-            __syncthreads();
-            stage(f, 8, Gq / 8, sw + Vec::gvb_hi, sw + Vec::gvb_lo, kGvStride, c);
+            compute_sync();
+            stage(f2, 8, Gq / 8, sw + Vec::gvb_hi, sw + Vec::gvb_lo, kGvStride, c);
             if (g < kMaxJ && warp < Gq / 8) {
                 const int o = 8 * warp + 2 * t4;
                 const float x0 = o < G ? lrelu(c[0] + __ldg(p.tab + ly.b_g2 + o)) : 0.0f, x1 = o + 1 < G ? lrelu(c[1] + __ldg(p.tab + ly.b_g2 + o + 1)) : 0.0f;
@@ -675,7 +700,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                 sv[Vec::skg + g * kMaxGq + o] = skip_on ? x0 : 0.0f; sv[Vec::skg + g * kMaxGq + o + 1] = skip_on ? x1 : 0.0f;
                 put_pair(Vec::in1_hi, Vec::in1_lo, kIn1Stride, 128 + TXq / 2 + 4 * warp + t4, x0, x1);
             }
-            __syncthreads();
+            compute_sync();
         }
         WIDE_TRACE(5);
         // ---- EPiC layers (epic.py:217-241, 152-155)
@@ -684,22 +709,28 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
             const uint2* fl = p.frag + ly.f_layer0 + (size_t)l * ly.f_layer_stride;
             if (l == 1) WIDE_TRACE(6);
             {   // per-jet path: fc_global1 -> fc_global2 (+ residual) -> the per-jet part of fc_local1
-                Frags f;
+                FragRegs<kMaxKS> f;
+                FragRegs<8> f2;
+                FragRegs<(kMaxTXq + kMaxGq) / 16> f3;
                 float c[4];
-                frag_load(fl + ly.fo_wg1, ly.KS_1(), 16, f);
+                frag_load(fl + ly.fo_wg1, ly.KS_1(), 16, f);   // all three stages' fragments in flight at once: one L2 latency
+                frag_load(fl + ly.fo_wg2, 8, Gq / 8, f2);
+                frag_load(fl + ly.fo_wl1g, ly.KS_2(), 16, f3);
+                if (l == 1) WIDE_TRACE(16);
                 if (l > 0) {
                     pool_to_input();
-                    __syncthreads();
+                    compute_sync();
                 }
-                stage(f, ly.KS_1(), 16, sw + Vec::in1_hi, sw + Vec::in1_lo, kIn1Stride, c);
-                frag_load(fl + ly.fo_wg2, 8, Gq / 8, f);
+                if (l == 1) WIDE_TRACE(17);
+                stage(f, ly.KS_1(), 16, sw + Vec::in1_hi, sw + Vec::in1_lo, kIn1Stride, c, 16);
+                if (l == 1) WIDE_TRACE(18);
                 if (g < kMaxJ) {
                     const int o = 8 * warp + 2 * t4;
                     put_pair(Vec::gva_hi, Vec::gva_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(tl + ly.o_blg1 + o)), lrelu(c[1] + __ldg(tl + ly.o_blg1 + o + 1)));
                 }
-                __syncthreads();
-                stage(f, 8, Gq / 8, sw + Vec::gva_hi, sw + Vec::gva_lo, kGvStride, c);
-                frag_load(fl + ly.fo_wl1g, ly.KS_2(), 16, f);
+                compute_sync();
+                if (l == 1) WIDE_TRACE(19);
+                stage(f2, 8, Gq / 8, sw + Vec::gva_hi, sw + Vec::gva_lo, kGvStride, c);
                 if (g < kMaxJ && warp < Gq / 8) {
                     const int o = 8 * warp + 2 * t4;
                     float* xg = sv + Vec::xg + g * kMaxGq + o;
@@ -710,14 +741,16 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                     xg[0] = m0 + sk[0]; xg[1] = m1 + sk[1];                                                    // the next layer the skipped one (epic.py:155)
                     put_pair(Vec::in1_hi, Vec::in1_lo, kIn1Stride, 128 + TXq / 2 + 4 * warp + t4, xg[0], xg[1]);
                 }
-                __syncthreads();
-                stage(f, ly.KS_2(), 16, sw + Vec::cx_hi, sw + Vec::cx_lo, kCxStride, c);
+                compute_sync();
+                if (l == 1) WIDE_TRACE(20);
+                stage(f3, ly.KS_2(), 16, sw + Vec::cx_hi, sw + Vec::cx_lo, kCxStride, c);
+                if (l == 1) WIDE_TRACE(21);
                 if (g < kMaxJ) {
                     const int o = 8 * warp + 2 * t4;
                     sv[Vec::bl1 + g * 128 + o] = c[0] + __ldg(tl + ly.o_bl1 + o);
                     sv[Vec::bl1 + g * 128 + o + 1] = c[1] + __ldg(tl + ly.o_bl1 + o + 1);
                 }
-                __syncthreads();
+                compute_sync();
             }
             const bool last = l == L - 1;
             if (l == 1) WIDE_TRACE(7);
@@ -778,7 +811,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
             }
         }
         tc_fence_before();
-        __syncthreads();
+        compute_sync();
         WIDE_TRACE(15);
         matrix_done();   // output layer served both tiles
     }
@@ -804,7 +837,8 @@ void put_frag(std::vector<uint2>& img, int base, int n_out, int ks, F w) {
         for (int kk = 0; kk < ks; ++kk)
             for (int lane = 0; lane < 32; ++lane) {
                 const int n = 8 * wp + lane / 4, k0 = 16 * kk + 2 * (lane % 4);
-                img[(size_t)base + ((size_t)wp * ks + kk) * 32 + lane] =
+                // k-steps travel in pairs: lane's entries of k-steps 2 i and 2 i + 1 are adjacent (one 16-byte load)
+                img[(size_t)base + (((size_t)wp * ((ks + 1) / 2) + kk / 2) * 32 + lane) * 2 + (kk & 1)] =
                     make_uint2(host_pack_bf16(w(n, k0), w(n, k0 + 1)), host_pack_bf16(w(n, k0 + 8), w(n, k0 + 9)));
             }
 }

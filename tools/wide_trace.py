@@ -24,5 +24,5 @@ for B in (2, 2368):
     print(f"--- B={B}: first pair of CTA 0 = {t[15] - t[0]} cycles")
     for i, n in enumerate(names):
         print(f"  {n:32s} {t[i + 1] - t[i]:7d}")
-    print("  inside the globals of layer 1: loads issued + pool + barrier %d | fc_global1 %d | write + barrier %d | fc_global2 .. barrier %d | fc_local1 part %d | tail %d"
-          % (t[16] - t[6], t[17] - t[16], t[18] - t[17], t[19] - t[18], t[20] - t[19], t[7] - t[20]))
+    print("  inside the globals of layer 1: frag loads issued %d | pool + barrier %d | fc_global1 %d | write + barrier %d | fc_global2 + write + barrier %d | fc_local1 part %d | write + barrier %d"
+          % (t[16] - t[6], t[17] - t[16], t[18] - t[17], t[19] - t[18], t[20] - t[19], t[21] - t[20], t[7] - t[21]))
