@@ -352,7 +352,7 @@ static int generate_wide(const EpicModel* m, float* x, uint8_t* k, const uint8_t
                          const float* table, const float* u_jump, uint64_t seed, uint64_t jet_offset, int B, int N, float* ws, cudaStream_t s) {
     const int Dc = m->dims.dim_continuous, S = m->dims.vocab_size, T = m->dims.dim_time_emb, X = m->dims.dim_context, n = st->n_steps;
     const size_t P = (size_t)B * N;
-    float *v = ws, *logits = v + P * Dc, *u = logits + P * S, *rows = u + P;
+    float *v = ws, *logits = v + P * Dc, *rows = logits + P * S + P;
     for (int step = 0; step < n; ++step) {
         const float* temb = table + (size_t)n * 4 + (size_t)step * T;
         int stride = 0;
@@ -363,11 +363,9 @@ static int generate_wide(const EpicModel* m, float* x, uint8_t* k, const uint8_t
             stride = T + X;
         }
         if (int rc = launch_epic_forward_wide(m, x, k, mask, temb, stride, B, N, v, logits, nullptr, s)) return rc;
-        const float* uj = u_jump ? u_jump + (size_t)step * P : u;
-        if (!u_jump)
-            if (int rc = launch_philox_uniforms(u, seed, jet_offset, 0, step, 1, B, N, s)) return rc;
-        if (int rc = launch_bridge_update(x, k, const_cast<uint8_t*>(mask), v, logits, nullptr, uj, nullptr,
-                                          StepScalars{st->dt, st->bc[step], st->cc[step], 0.0f}, P, Dc, S, MMB_FLAG_MULTIMODAL, s))
+        const UpdateDraws draws{seed, jet_offset, step, N};   // Philox inside the update kernel unless uniforms were injected
+        if (int rc = launch_bridge_update(x, k, const_cast<uint8_t*>(mask), v, logits, nullptr, u_jump ? u_jump + (size_t)step * P : nullptr, nullptr,
+                                          StepScalars{st->dt, st->bc[step], st->cc[step], 0.0f}, P, Dc, S, MMB_FLAG_MULTIMODAL, s, &draws))
             return rc;
     }
     return MMB_OK;
@@ -702,12 +700,12 @@ int mmb_generate_absorbing(const MmbEpicModel* model, const MmbAbsorbHead* head,
         // heads from the OLD mask (absorbing_flows.py:270), then birth -> Euler -> jump with the new one (:271-273)
         int rc = mmb_epic_forward(model, x, k, mask, temb_dev + (size_t)i * T, 0, B, N, v, logits, hidden, precision, stream);
         if (!rc) rc = launch_absorb_head(h, hidden, mask, tb_dev + (size_t)i * nblk * 128, 0, B, N, alog, s, pack, tf_pack_scratch_ints(B));
-        const float* pj = u_jump ? u_jump + (size_t)i * P : uj;
-        const float* pa = u_absorb ? u_absorb + (size_t)i * P : ua;
-        if (!rc && !u_jump) rc = launch_philox_uniforms(uj, seed, jet_offset, 0, i, 1, B, N, s);
-        if (!rc && !u_absorb) rc = launch_philox_uniforms(ua, seed, jet_offset, 1, i, 1, B, N, s);
+        // injected uniforms, or Philox drawn inside the update kernel (no uniform ever travels through HBM)
+        const float* pj = u_jump ? u_jump + (size_t)i * P : nullptr;
+        const float* pa = u_absorb ? u_absorb + (size_t)i * P : nullptr;
+        const UpdateDraws draws{seed, jet_offset, i, N};
         if (!rc) rc = launch_bridge_update(x, k, mask, v, logits, alog, pj, pa, StepScalars{st->dt, st->bc[i], st->cc[i], st->sp[i]},
-                                           P, Dc, S, MMB_FLAG_ABSORBING, s);
+                                           P, Dc, S, MMB_FLAG_ABSORBING, s, &draws);
         if (rc) return rc;
     }
     return MMB_OK;

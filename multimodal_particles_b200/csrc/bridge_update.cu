@@ -70,13 +70,33 @@ __device__ __forceinline__ void store_bytes(uint8_t* __restrict__ p, const int (
     else *p = (uint8_t)v[0];
 }
 
+// PPT uniforms of consecutive particles drawn in the kernel: Philox keyed by (seed, global jet, stream, step, particle) exactly
+// as mmb_philox_uniforms writes them (one block serves four consecutive particles of a jet)
+template <int PPT>
+__device__ __forceinline__ void draw_uniforms(const UpdateDraws& d, int stream_id, size_t first, float (&u)[PPT]) {
+    const size_t jet = first / (size_t)d.N;
+    const int n0 = (int)(first - jet * (size_t)d.N);
+    if ((n0 & 3) + PPT <= 4 && n0 + PPT <= d.N) {   // all in one Philox block of one jet
+        const uint4 r = philox_block(d.seed, d.jet_offset + jet, stream_id, d.step, n0 >> 2);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) u[j] = u01(w[(n0 & 3) + j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const size_t p = first + j, jj = p / (size_t)d.N;
+            u[j] = philox_uniform(d.seed, d.jet_offset + jj, stream_id, d.step, (int)(p - jj * (size_t)d.N));
+        }
+    }
+}
+
 // Dc = 3.  Each thread owns PPT consecutive particles; group g covers particles [g*PPT, (g+1)*PPT).
 template <int S, int PPT, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 bridge_update_vec_kernel(float* __restrict__ x, uint8_t* __restrict__ k, uint8_t* __restrict__ mask,
                          const float* __restrict__ v, const float* __restrict__ logits,
                          const float* __restrict__ absorb, const float* __restrict__ uj,
-                         const float* __restrict__ ua, StepScalars sc, size_t groups, int flags) {
+                         const float* __restrict__ ua, StepScalars sc, size_t groups, int flags, UpdateDraws draws) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= groups) return;
     const bool do_euler = !(flags & MMB_FLAG_NO_EULER), do_jump = !(flags & MMB_FLAG_NO_JUMP),
@@ -92,13 +112,15 @@ bridge_update_vec_kernel(float* __restrict__ x, uint8_t* __restrict__ k, uint8_t
     }
     if (do_jump) {
         load_bytes<PPT>(k + g * PPT, kk);
-        load_floats<PPT, true>(uj + g * PPT, u);
+        if (uj) load_floats<PPT, true>(uj + g * PPT, u);
         load_floats<S * PPT, true>(logits + g * S * PPT, lg);
     }
     if (do_birth) {
         load_floats<PPT, true>(absorb + g * PPT, a);
-        load_floats<PPT, true>(ua + g * PPT, ub);
+        if (ua) load_floats<PPT, true>(ua + g * PPT, ub);
     }
+    if (do_jump && !uj) draw_uniforms<PPT>(draws, 0, g * PPT, u);       // under the loads in flight
+    if (do_birth && !ua) draw_uniforms<PPT>(draws, 1, g * PPT, ub);
     // ---- birth (bridges.py:260-286)
     if (do_birth) {
 #pragma unroll
@@ -131,19 +153,23 @@ bridge_update_generic_kernel(float* __restrict__ x, uint8_t* __restrict__ k, uin
                              const float* __restrict__ v, const float* __restrict__ logits,
                              const float* __restrict__ absorb, const float* __restrict__ uj,
                              const float* __restrict__ ua, StepScalars sc, size_t first, size_t count,
-                             int Dc, int S, int flags) {
+                             int Dc, int S, int flags, UpdateDraws draws) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const size_t p = first + i;
     int m = mask[p];
+    float u1[1];
     if (flags & MMB_FLAG_ABSORBING) {
-        m = absorbing_birth(m, absorb[p], ua[p], sc);
+        if (ua) u1[0] = ua[p]; else draw_uniforms<1>(draws, 1, p, u1);
+        m = absorbing_birth(m, absorb[p], u1[0], sc);
         mask[p] = (uint8_t)m;
     }
     if (!(flags & MMB_FLAG_NO_EULER))
         for (int c = 0; c < Dc; ++c) x[p * Dc + c] = euler(x[p * Dc + c], v[p * Dc + c], sc.dt, (float)m);
-    if (!(flags & MMB_FLAG_NO_JUMP))
-        k[p] = (uint8_t)(telegraph_jump_rt(logits + p * S, S, k[p], uj[p], sc) * m);
+    if (!(flags & MMB_FLAG_NO_JUMP)) {
+        if (uj) u1[0] = uj[p]; else draw_uniforms<1>(draws, 0, p, u1);
+        k[p] = (uint8_t)(telegraph_jump_rt(logits + p * S, S, k[p], u1[0], sc) * m);
+    }
 }
 
 // tuning knob MMB_UPDATE_VARIANT = 10*particles_per_thread + min CTAs/SM (profiles/r01_update_variants.md)
@@ -160,7 +186,10 @@ static bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<
 
 int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, const float* logits,
                          const float* absorb, const float* uj, const float* ua, StepScalars sc,
-                         size_t P, int Dc, int S, int flags, cudaStream_t stream) {
+                         size_t P, int Dc, int S, int flags, cudaStream_t stream, const UpdateDraws* draws_in) {
+    const UpdateDraws draws = draws_in ? *draws_in : UpdateDraws{0, 0, 0, 1};
+    if (!draws_in && ((!(flags & MMB_FLAG_NO_JUMP) && !uj) || ((flags & MMB_FLAG_ABSORBING) && !ua)))
+        return fail(MMB_EINVAL, "bridge update: uniforms missing");
     size_t done = 0;
     const bool vec_ok = Dc == 3 && (S == 8 || S == 4 || (flags & MMB_FLAG_NO_JUMP)) && aligned16(x) && aligned16(v) &&
                         aligned16(logits) && aligned16(absorb) && aligned16(uj) && aligned16(ua) &&
@@ -173,8 +202,8 @@ int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, co
         const bool s4 = (S == 4 && !(flags & MMB_FLAG_NO_JUMP));
 #define MMB_LAUNCH(PP, MB)                                                                                              \
     do {                                                                                                                \
-        if (s4) bridge_update_vec_kernel<4, PP, MB><<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, groups, flags); \
-        else bridge_update_vec_kernel<8, PP, MB><<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, groups, flags);   \
+        if (s4) bridge_update_vec_kernel<4, PP, MB><<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, groups, flags, draws); \
+        else bridge_update_vec_kernel<8, PP, MB><<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, groups, flags, draws);   \
     } while (0)
         switch (var) {
             case 42: MMB_LAUNCH(4, 2); break;
@@ -189,7 +218,7 @@ int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, co
     if (done < P) {
         const size_t count = P - done;
         const unsigned grid = (unsigned)((count + 255) / 256);
-        bridge_update_generic_kernel<<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, done, count, Dc, S, flags);
+        bridge_update_generic_kernel<<<grid, 256, 0, stream>>>(x, k, mask, v, logits, absorb, uj, ua, sc, done, count, Dc, S, flags, draws);
     }
     return cuda_ok(cudaGetLastError(), "bridge_update launch");
 }

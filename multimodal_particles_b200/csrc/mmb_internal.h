@@ -42,9 +42,15 @@ struct EpicModel {
 };
 
 // bridge_update.cu
+// uniforms drawn inside the update kernel (uj / ua null): the draws of solver step `step` for jets of N particle slots, keyed like
+// mmb_philox_uniforms (stream 0 = jump, 1 = absorbing birth)
+struct UpdateDraws {
+    uint64_t seed, jet_offset;
+    int step, N;
+};
 int launch_bridge_update(float* x, uint8_t* k, uint8_t* mask, const float* v, const float* logits,
                          const float* absorb, const float* uj, const float* ua, StepScalars sc,
-                         size_t P, int Dc, int S, int flags, cudaStream_t stream);
+                         size_t P, int Dc, int S, int flags, cudaStream_t stream, const UpdateDraws* draws = nullptr);
 int launch_philox_uniforms(float* u, uint64_t seed, uint64_t jet_offset, int stream_id, int step0, int n_steps, int B, int N,
                            cudaStream_t stream);
 
