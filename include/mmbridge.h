@@ -344,7 +344,9 @@ typedef struct MmbTransDims {
     int32_t transformer_dim; /* C  encoder.transformer_dim (= temb_dim); built for 128 */
     int32_t n_heads;         /*    encoder.n_heads; built for 2 */
     int32_t n_blocks;        /*    encoder.n_attn_blocks */
-    int32_t max_particles;   /* R  rdim of post_rate_proj = data.max_num_particles (rate_use_x0_pred) */
+    int32_t max_particles;   /* R  data.max_num_particles: width of x0_dim_logits, rdim of post_rate_proj when rate_direct == 0 */
+    int32_t rate_direct;     /* 1: encoder.rate_use_x0_pred = False — post_rate_proj has ONE output, rate = softplus(.) * forward_rate(t)
+                                and x0_dim_logits = 0 (transdimensional_model.py:185-188, 326-332); 0: every shipped config */
 } MmbTransDims;
 
 /* StepForwardRate / ConstForwardRate (noising.py:123-164): rate(t) = scalar*[t > cut] + offset (step),

@@ -42,7 +42,7 @@ class EpicDims(ctypes.Structure):
 class TransDims(ctypes.Structure):
     """ctypes image of ``MmbTransDims``."""
 
-    _fields_ = [(n, ctypes.c_int32) for n in ("hidden", "vocab_size", "transformer_dim", "n_heads", "n_blocks", "max_particles")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("hidden", "vocab_size", "transformer_dim", "n_heads", "n_blocks", "max_particles", "rate_direct")]
 
 
 class ForwardRate(ctypes.Structure):

@@ -198,7 +198,7 @@ __device__ __forceinline__ float warp_max(float v) {
 __global__ void __launch_bounds__(128) trans_rate_kernel(const float* __restrict__ x0_logits, const float* __restrict__ near_logits,
                                                          const int32_t* __restrict__ dims, const float* __restrict__ ts, int ts_stride,
                                                          const int32_t* __restrict__ nearest_in, const float* __restrict__ u_nearest,
-                                                         MmbForwardRate fr, const float* __restrict__ logfact, int B, int N, int R,
+                                                         MmbForwardRate fr, const float* __restrict__ logfact, int B, int N, int R, int direct,
                                                          float* __restrict__ rate, int32_t* __restrict__ nearest_out) {
     const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -207,6 +207,10 @@ __global__ void __launch_bounds__(128) trans_rate_kernel(const float* __restrict
     const float* lg = x0_logits + (size_t)b * R;
     const float I = fr_integral(fr, t), logI = logf(I);
     float mx = -INFINITY;
+    if (direct) {   // rate_use_x0_pred = False: rate = softplus(rate logit) * forward_rate(t)   (transdimensional_model.py:328-332)
+        const float a = lg[0];
+        if (lane == 0) rate[b] = (a > 20.0f ? a : log1pf(expf(a))) * fr_rate(fr, t);   // torch softplus: beta 1, threshold 20
+    }
     for (int i = d - 1 + lane; i < R; i += 32) mx = fmaxf(mx, lg[i]);
     mx = warp_max(mx);
     float z = 0.0f;
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(128) trans_rate_kernel(const float* __restrict
         acc += ratio * prob;
     }
     acc = warp_sum(acc);
-    if (lane == 0) rate[b] = fr_rate(fr, t) * acc;
+    if (lane == 0 && !direct) rate[b] = fr_rate(fr, t) * acc;
     // nearest particle: given, or multinomial(softmax(near_atom_logits)) over ALL N slots by inverse CDF — the scan is
     // sequential in fp32 so that the chosen index is bit-identical to the oracle's
     if (lane == 0 && nearest_out) {
@@ -650,8 +654,12 @@ struct TransWs {
 }  // namespace
 
 // ---- host -------------------------------------------------------------------------------------------------------------
+// outputs of post_rate_proj: max_num_particles x0-dimension logits, or one rate logit with encoder.rate_use_x0_pred = False
+// (transdimensional_model.py:185-188)
+static int rate_dim(const MmbTransDims& d) { return d.rate_direct ? 1 : d.max_particles; }
+
 static size_t trans_floats(const MmbTransDims& d) {
-    const size_t C = d.transformer_dim, lin = C * C + C, H = d.hidden, S = d.vocab_size, R = d.max_particles;
+    const size_t C = d.transformer_dim, lin = C * C + C, H = d.hidden, S = d.vocab_size, R = rate_dim(d);
     const size_t block = 6 * C + 6 * lin;
     return lin + 2 * (size_t)d.n_blocks * lin + (C * (H + S) + C) + d.n_blocks * block + lin + (R * C + R) + (C + 1) +
            (C * (H + S + 3) + C) + d.n_blocks * block + (C + 1) + lin + ((2 * S + 1) * C + (2 * S + 1));
@@ -676,7 +684,7 @@ static int trans_create(const MmbTransDims* dims, const float* W, size_t n_float
     if (!trans_dims_ok(d))
         return fail(MMB_EUNSUPPORTED, "trans heads are built for transformer_dim=128, n_heads=2, 1..4 blocks, hidden+vocab+3<=32, <=128 particles");
     if (n_floats != trans_floats(d)) return fail(MMB_EINVAL, "trans heads blob has %zu floats, layout wants %zu", n_floats, trans_floats(d));
-    const int C = kC, H = d.hidden, S = d.vocab_size, R = d.max_particles, nb = d.n_blocks, PA = 2 * S + 1;
+    const int C = kC, H = d.hidden, S = d.vocab_size, R = rate_dim(d), nb = d.n_blocks, PA = 2 * S + 1;
     const size_t lin = (size_t)C * C + C, block = 6 * (size_t)C + 6 * lin;
     const float* temb_net = W;
     const float* s1 = W + lin + 2 * (size_t)nb * lin;
@@ -717,7 +725,7 @@ static int trans_create(const MmbTransDims* dims, const float* W, size_t n_float
             for (int c = 0; c < C; ++c) dst[(size_t)c * C + o] = src[(size_t)o * C + c];
         for (int o = 0; o < C; ++o) dst[(size_t)C * C + o] = src[(size_t)C * C + o];
     }
-    std::vector<float> lf((size_t)3 * R + 2);
+    std::vector<float> lf((size_t)3 * d.max_particles + 2);
     for (size_t k = 0; k < lf.size(); ++k) lf[k] = (float)lgamma((double)k + 1.0);
 
     int prev = 0;
@@ -753,12 +761,17 @@ static int trans_eval(const EpicModel* m, const TransHeads* h, const float* x, c
                       const int32_t* nearest_in, const float* u_nearest, const MmbForwardRate& fr, int B, int N, float* ws,
                       const TransWs& L, float* x0_logits_out, float* near_logits_out, float* auto_mean, float* auto_std,
                       int precision, cudaStream_t s) {
-    const int S = h->d.vocab_size, H = h->d.hidden, R = h->d.max_particles, nb = h->d.n_blocks, T = m->dims.dim_time_emb;
+    const int S = h->d.vocab_size, H = h->d.hidden, R = rate_dim(h->d), nb = h->d.n_blocks, T = m->dims.dim_time_emb;
+    const bool direct = h->d.rate_direct != 0;
     const size_t P = (size_t)B * N;
     uint8_t* k = reinterpret_cast<uint8_t*>(ws + L.k);
     uint8_t* mask = reinterpret_cast<uint8_t*>(ws + L.mask);
     int32_t* nearest = reinterpret_cast<int32_t*>(ws + L.nearest);
-    float* x0l = x0_logits_out ? x0_logits_out : ws + L.x0_logits;
+    // rate_use_x0_pred = False: the head's single output stays in the workspace and the caller's x0_dim_logits are zeros
+    // (transdimensional_model.py:326-327)
+    float* x0l = (x0_logits_out && !direct) ? x0_logits_out : ws + L.x0_logits;
+    if (x0_logits_out && direct)
+        if (int rc = cuda_ok(cudaMemsetAsync(x0_logits_out, 0, (size_t)B * h->d.max_particles * sizeof(float), s), "x0 logits reset")) return rc;
     float* nl = near_logits_out ? near_logits_out : ws + L.near_logits;
     {
         const int NS = N * S, chunks = (B + kChunk - 1) / kChunk;
@@ -779,7 +792,8 @@ static int trans_eval(const EpicModel* m, const TransHeads* h, const float* x, c
     io.pack_scratch = reinterpret_cast<int32_t*>(ws + L.pack); io.pack_scratch_ints = L.pack_ints;
     if ((rc = launch_tf_stack(&h->s1, h->sm_count, io, B, N, s))) return rc;
     if ((rc = launch_jet_head(&h->s1, ws + L.means, B, x0l, s))) return rc;
-    trans_rate_kernel<<<(B + 3) / 4, 128, 0, s>>>(x0l, nl, dims, ts, ts_stride, nearest_in, u_nearest, fr, h->logfact, B, N, R, ws + L.rate, nearest);
+    trans_rate_kernel<<<(B + 3) / 4, 128, 0, s>>>(x0l, nl, dims, ts, ts_stride, nearest_in, u_nearest, fr, h->logfact, B, N, R, direct ? 1 : 0,
+                                                  ws + L.rate, nearest);
     if ((rc = cuda_ok(cudaGetLastError(), "trans rate launch"))) return rc;
     io.mode = 2; io.x = x; io.nearest = nearest; io.tbias = tb2; io.dot_out = ws + L.vec_w; io.jet_out = ws + L.means;
     if ((rc = launch_tf_stack(&h->s2, h->sm_count, io, B, N, s))) return rc;

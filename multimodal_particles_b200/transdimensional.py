@@ -259,9 +259,8 @@ class TransdimensionalEPiC(nn.Module):
         C = self.transformer_dim = self.temb_dim = e.transformer_dim
         self.n_heads, self.n_attn_blocks = e.n_heads, e.n_attn_blocks
         self.rate_use_x0_pred = e.rate_use_x0_pred
-        if not self.rate_use_x0_pred:
-            raise NotImplementedError("native path is built for rate_use_x0_pred=True (every shipped config)")
-        self.rdim = d.max_num_particles
+        # False: post_rate_proj has one output, rate = softplus(.) * forward_rate(t), x0_dim_logits = 0 (model :185-188, 326-332)
+        self.rdim = d.max_num_particles if self.rate_use_x0_pred else 1
         self.temb_net = nn.Linear(C, C)
         self.transformer_1_proj_in = nn.Linear(self.output_dim_local + self.vocab_size_features, C)
         self.attn_blocks = nn.ModuleList([AttnBlock(C, e.n_heads, attn_dim_reduce=1) for _ in range(e.n_attn_blocks)])
@@ -281,7 +280,7 @@ class TransdimensionalEPiC(nn.Module):
     # ---- packing (order documented in include/mmbridge.h, mmb_trans_create) ------------------------------
     def trans_dims(self) -> "_native.TransDims":
         return _native.TransDims(self.output_dim_local, self.vocab_size_features, self.transformer_dim, self.n_heads,
-                                 self.n_attn_blocks, self.rdim)
+                                 self.n_attn_blocks, self.max_num_particles, 0 if self.rate_use_x0_pred else 1)
 
     def pack_heads(self) -> torch.Tensor:
         lin = lambda m: [m.weight, m.bias]

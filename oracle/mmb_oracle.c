@@ -518,8 +518,11 @@ void mmbo_absorb_head(const float* W, int H, int C, int n_heads, int n_blocks,
  * (mp/models/generative/transdimensional/transdimensional_model.py:245-426, sampler.py:157-324,
  *  structure.py:226-250, mp/models/generative/diffusion/noising.py:15-39,123-216,
  *  mp/data/particle_clouds/jets_dataloader.py:380-478). */
+/* outputs of post_rate_proj: max_num_particles x0-dimension logits, or one rate logit with rate_use_x0_pred = False (model :185-188) */
+static int trans_rate_dim(const MmbTransDims* d) { return d->rate_direct ? 1 : d->max_particles; }
+
 size_t mmbo_trans_floats(const MmbTransDims* d) {
-    const size_t C = d->transformer_dim, lin = C * C + C, nrm = 2 * C, H = d->hidden, S = d->vocab_size, R = d->max_particles;
+    const size_t C = d->transformer_dim, lin = C * C + C, nrm = 2 * C, H = d->hidden, S = d->vocab_size, R = (size_t)trans_rate_dim(d);
     const size_t block = 3 * nrm + 6 * lin;
     return lin + 2 * (size_t)d->n_blocks * lin
          + (C * (H + S) + C) + d->n_blocks * block + lin + (R * C + R) + (C + 1)
@@ -638,7 +641,7 @@ void mmbo_trans_forward(const MmbEpicDims* ed, const float* epacked, const MmbTr
                         const int32_t* nearest_in, const float* u_nearest, const MmbForwardRate* fr, int B, int N,
                         float* d_xt, float* rate, float* auto_mean, float* auto_std, float* x0_dim_logits,
                         float* near_atom_logits, int32_t* nearest_out, float* new_mean, float* new_std) {
-    const int C = d->transformer_dim, H = d->hidden, S = d->vocab_size, R = d->max_particles, nb = d->n_blocks, T = ed->dim_time_emb;
+    const int C = d->transformer_dim, H = d->hidden, S = d->vocab_size, R = trans_rate_dim(d), nb = d->n_blocks, T = ed->dim_time_emb;
     const int F = 3 + S;
     const size_t lin = (size_t)C * C + C, block = 6 * (size_t)C + 6 * lin;
     uint8_t* k = (uint8_t*)malloc((size_t)B * N);
@@ -698,9 +701,16 @@ void mmbo_trans_forward(const MmbEpicDims* ed, const float* epacked, const MmbTr
                 for (int n = 0; n < N; ++n) acc += s.t1[(size_t)n * C + c];
                 emb[c] = acc / (float)N;
             }
-            float* xl = x0_dim_logits + (size_t)b * R;
-            for (int r = 0; r < R; ++r) xl[r] = dot_from(post_rate[(size_t)R * C + r], post_rate + (size_t)r * C, emb, C);
-            rate[b] = mmbo_trans_rate(xl, R, dims[b], fr, ts[b]);
+            if (d->rate_direct) {   /* model :326-332: x0_dim_logits = 0, rate = softplus(rate logit) * forward_rate(t) */
+                float* xl = x0_dim_logits + (size_t)b * d->max_particles;
+                for (int r = 0; r < d->max_particles; ++r) xl[r] = 0.0f;
+                const float a = dot_from(post_rate[(size_t)C], post_rate, emb, C);
+                rate[b] = (a > 20.0f ? a : log1pf(expf(a))) * fr_rate(fr, ts[b]);   /* torch softplus: beta 1, threshold 20 */
+            } else {
+                float* xl = x0_dim_logits + (size_t)b * R;
+                for (int r = 0; r < R; ++r) xl[r] = dot_from(post_rate[(size_t)R * C + r], post_rate + (size_t)r * C, emb, C);
+                rate[b] = mmbo_trans_rate(xl, R, dims[b], fr, ts[b]);
+            }
             float* nl = near_atom_logits + (size_t)b * N;
             for (int n = 0; n < N; ++n) nl[n] = dot_from(near_w[C], near_w, h + (size_t)n * C, C);
             int near;

@@ -65,6 +65,38 @@ def test_forward_given_nearest_matches_reference(fixture, precision):
     assert torch.equal(net.model.last_nearest_atom.cpu(), torch.from_numpy(z["fwd/nearest"]))
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_with_rate_use_x0_pred_false(golden_dir, precision):
+    """encoder.rate_use_x0_pred = False: one rate logit, rate = softplus(.) * forward_rate(t), zero x0_dim_logits
+    (transdimensional_model.py:185-188, 326-332), against the reference run and the oracle; the sampler runs on such a model."""
+    z, cfg, model = ol.load_trans_golden(os.path.join(golden_dir, "trans_direct.npz"))
+    packed = ol.trans_packed(model)
+    model = model.to(DEV)
+    net = model.net
+    net.model.precision = precision
+    st = model.make_batch(to_dev(z["fwd/x"]), to_dev(z["fwd/onehot"]), to_dev(z["fwd/dims"]))
+    B, N, S = z["fwd/onehot"].shape
+    D, rate, (am, asd), x0l, nal = net(st, to_dev(z["fwd/ts"]), forward_rate=model.forward_rate, predict="eps",
+                                       nearest_atom=to_dev(z["fwd/nearest"]))
+    assert rate.shape == (B, 1) and x0l.shape == (B, N) and (x0l == 0).all()
+    close(D, z["fwd/d_xt"], 2e-5 if precision == "fp32" else 0.02)
+    close(nal, z["fwd/near_atom_logits"], 0.03)
+    # the rate logit comes out of the bf16 transformer stack whatever the trunk's precision: 5 % like the x0-pred rate
+    np.testing.assert_allclose(rate.view(-1).cpu().numpy(), z["fwd/rate"], rtol=0.05, atol=1e-4)
+    close(am, z["fwd/auto_mean"], 0.03)
+    close(asd, z["fwd/auto_std"], 0.03)
+    want = ol.trans_forward(packed, z["fwd/x"], z["fwd/onehot"], z["fwd/dims"], z["fwd/ts"], model.forward_rate.as_c(), nearest=z["fwd/nearest"])
+    np.testing.assert_allclose(rate.view(-1).cpu().numpy(), want.rate, rtol=0.05, atol=1e-4)
+    if precision == "bf16":   # the whole sampler on such a model: births happen, multiplicities stay in range
+        sk = {k: v for k, v in vars(cfg.sampler_kwargs).items() if k not in ("class_name", "do_jump_back", "jump_back_start_time")}
+        sk["dt"] = 0.05
+        sampler = JumpSampler(structure=model.structure, **sk)
+        sampler.seed = 3
+        in_st = model.make_batch(torch.zeros(64, N, 3, device=DEV), torch.zeros(64, N, S, device=DEV), torch.full((64,), N, device=DEV))
+        d = sampler.sample(model.net, in_st, model.jump_diffusion_loss, jet_offset=0).get_dims()
+        assert int(d.min()) >= 1 and int(d.max()) > 1 and int(d.max()) <= N
+
+
 def test_forward_samples_nearest_by_inverse_cdf(fixture):
     z, cfg, model, packed = fixture
     net = model.net

@@ -47,6 +47,24 @@ def test_forward_given_nearest(gold):
     assert z["fwd/rate"][2] == 0.0 and (z["fwd/auto_mean"][2] == 0).all()   # dims == N: no birth possible
 
 
+def test_forward_with_rate_use_x0_pred_false():
+    """encoder.rate_use_x0_pred = False (transdimensional_model.py:185-188, 326-332): post_rate_proj has one output,
+    rate = softplus(.) * forward_rate(t), x0_dim_logits = 0 — against the reference run of make_golden_trans_direct.py."""
+    z, cfg, model = ol.load_trans_golden(os.path.join(os.path.dirname(GOLD), "trans_direct.npz"))
+    assert cfg.encoder.rate_use_x0_pred is False and model.net.model.post_rate_proj.weight.shape[0] == 1
+    packed = ol.trans_packed(model)
+    assert packed[2].rate_direct == 1 and packed[2].max_particles == cfg.data.max_num_particles
+    out = ol.trans_forward(packed, z["fwd/x"], z["fwd/onehot"], z["fwd/dims"], z["fwd/ts"], model.forward_rate.as_c(),
+                           nearest=z["fwd/nearest"])
+    np.testing.assert_allclose(out.d_xt, z["fwd/d_xt"], rtol=0, atol=2e-5)
+    assert (out.x0_dim_logits == 0).all() and (z["fwd/x0_dim_logits"] == 0).all()
+    np.testing.assert_allclose(out.near_atom_logits, z["fwd/near_atom_logits"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(out.rate, z["fwd/rate"], rtol=2e-4, atol=1e-6)
+    assert z["fwd/rate"].min() > 0 and z["fwd/rate"].max() > 20 * z["fwd/rate"].min()   # the fixture spans both sides of the rate cut
+    np.testing.assert_allclose(out.auto_mean, z["fwd/auto_mean"], rtol=0, atol=5e-5)
+    np.testing.assert_allclose(out.auto_std, z["fwd/auto_std"], rtol=0, atol=5e-5)
+
+
 def test_forward_sampled_nearest(gold):
     z, cfg, model, packed = gold
     out = ol.trans_forward(packed, z["fwd/x"], z["fwd/onehot"], z["fwd/dims"], z["fwd/ts"], model.forward_rate.as_c(),
