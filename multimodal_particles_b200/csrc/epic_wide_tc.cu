@@ -596,11 +596,12 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
             FragRegs<kMaxTXq / 16> f;
             float c[4];
             frag_load(p.frag + ly.f_w0t, ly.KS_t(), 16, f);
+            const float2 c0 = __ldg(reinterpret_cast<const float2*>(p.tab + ly.c0 + 8 * warp + 2 * t4));
             stage(f, ly.KS_t(), 16, sw + Vec::in1_hi + 128, sw + Vec::in1_lo + 128, kIn1Stride, c);
             if (g < kMaxJ) {
                 const int o = 8 * warp + 2 * t4;
-                sv[Vec::bl1 + g * 128 + o] = c[0] + __ldg(p.tab + ly.c0 + o);
-                sv[Vec::bl1 + g * 128 + o + 1] = c[1] + __ldg(p.tab + ly.c0 + o + 1);
+                sv[Vec::bl1 + g * 128 + o] = c[0] + c0.x;
+                sv[Vec::bl1 + g * 128 + o + 1] = c[1] + c0.y;
             }
         }
         compute_sync();
@@ -678,24 +679,22 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
             frag_load(p.frag + ly.f_g0, ly.KS_0(), 16, f);     // all three stages' fragments in flight at once: one L2 latency
             frag_load(p.frag + ly.f_g1, 8, 16, f1);
             frag_load(p.frag + ly.f_g2, 8, Gq / 8, f2);
+            const int ob = 8 * warp + 2 * t4;                  // ... and the biases this lane will add
+            const float2 bias0 = __ldg(reinterpret_cast<const float2*>(p.tab + ly.b_g0 + ob));
+            const float2 bias1 = __ldg(reinterpret_cast<const float2*>(p.tab + ly.b_g1 + ob));
+            const float2 bias2 = warp < Gq / 8 ? __ldg(reinterpret_cast<const float2*>(p.tab + ly.b_g2 + ob)) : make_float2(0.f, 0.f);
             pool_to_input();
             compute_sync();
             stage(f, ly.KS_0(), 16, sw + Vec::in1_hi, sw + Vec::in1_lo, kIn1Stride, c, 16);
-            if (g < kMaxJ) {
-                const int o = 8 * warp + 2 * t4;
-                put_pair(Vec::gva_hi, Vec::gva_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(p.tab + ly.b_g0 + o)), lrelu(c[1] + __ldg(p.tab + ly.b_g0 + o + 1)));
-            }
+            if (g < kMaxJ) put_pair(Vec::gva_hi, Vec::gva_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + bias0.x), lrelu(c[1] + bias0.y));
             compute_sync();
             stage(f1, 8, 16, sw + Vec::gva_hi, sw + Vec::gva_lo, kGvStride, c);
-            if (g < kMaxJ) {
-                const int o = 8 * warp + 2 * t4;
-                put_pair(Vec::gvb_hi, Vec::gvb_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(p.tab + ly.b_g1 + o)), lrelu(c[1] + __ldg(p.tab + ly.b_g1 + o + 1)));
-            }
+            if (g < kMaxJ) put_pair(Vec::gvb_hi, Vec::gvb_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + bias1.x), lrelu(c[1] + bias1.y));
             compute_sync();
             stage(f2, 8, Gq / 8, sw + Vec::gvb_hi, sw + Vec::gvb_lo, kGvStride, c);
             if (g < kMaxJ && warp < Gq / 8) {
                 const int o = 8 * warp + 2 * t4;
-                const float x0 = o < G ? lrelu(c[0] + __ldg(p.tab + ly.b_g2 + o)) : 0.0f, x1 = o + 1 < G ? lrelu(c[1] + __ldg(p.tab + ly.b_g2 + o + 1)) : 0.0f;
+                const float x0 = o < G ? lrelu(c[0] + bias2.x) : 0.0f, x1 = o + 1 < G ? lrelu(c[1] + bias2.y) : 0.0f;
                 sv[Vec::xg + g * kMaxGq + o] = x0; sv[Vec::xg + g * kMaxGq + o + 1] = x1;
                 sv[Vec::skg + g * kMaxGq + o] = skip_on ? x0 : 0.0f; sv[Vec::skg + g * kMaxGq + o + 1] = skip_on ? x1 : 0.0f;
                 put_pair(Vec::in1_hi, Vec::in1_lo, kIn1Stride, 128 + TXq / 2 + 4 * warp + t4, x0, x1);
@@ -716,6 +715,11 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                 frag_load(fl + ly.fo_wg1, ly.KS_1(), 16, f);   // all three stages' fragments in flight at once: one L2 latency
                 frag_load(fl + ly.fo_wg2, 8, Gq / 8, f2);
                 frag_load(fl + ly.fo_wl1g, ly.KS_2(), 16, f3);
+                // ... and the biases this lane will add (a load at the end of a stage would put an L2 latency on the chain)
+                const int ob = 8 * warp + 2 * t4;
+                const float2 bias1 = __ldg(reinterpret_cast<const float2*>(tl + ly.o_blg1 + ob));
+                const float2 bias2 = warp < Gq / 8 ? __ldg(reinterpret_cast<const float2*>(tl + ly.o_blg2 + ob)) : make_float2(0.f, 0.f);
+                const float2 bias3 = __ldg(reinterpret_cast<const float2*>(tl + ly.o_bl1 + ob));
                 if (l == 1) WIDE_TRACE(16);
                 if (l > 0) {
                     pool_to_input();
@@ -724,10 +728,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                 if (l == 1) WIDE_TRACE(17);
                 stage(f, ly.KS_1(), 16, sw + Vec::in1_hi, sw + Vec::in1_lo, kIn1Stride, c, 16);
                 if (l == 1) WIDE_TRACE(18);
-                if (g < kMaxJ) {
-                    const int o = 8 * warp + 2 * t4;
-                    put_pair(Vec::gva_hi, Vec::gva_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + __ldg(tl + ly.o_blg1 + o)), lrelu(c[1] + __ldg(tl + ly.o_blg1 + o + 1)));
-                }
+                if (g < kMaxJ) put_pair(Vec::gva_hi, Vec::gva_lo, kGvStride, 4 * warp + t4, lrelu(c[0] + bias1.x), lrelu(c[1] + bias1.y));
                 compute_sync();
                 if (l == 1) WIDE_TRACE(19);
                 stage(f2, 8, Gq / 8, sw + Vec::gva_hi, sw + Vec::gva_lo, kGvStride, c);
@@ -735,8 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                     const int o = 8 * warp + 2 * t4;
                     float* xg = sv + Vec::xg + g * kMaxGq + o;
                     const float* sk = sv + Vec::skg + g * kMaxGq + o;
-                    const float m0 = o < G ? lrelu(c[0] + __ldg(tl + ly.o_blg2 + o) + xg[0]) : 0.0f,
-                                m1 = o + 1 < G ? lrelu(c[1] + __ldg(tl + ly.o_blg2 + o + 1) + xg[1]) : 0.0f;
+                    const float m0 = o < G ? lrelu(c[0] + bias2.x + xg[0]) : 0.0f, m1 = o + 1 < G ? lrelu(c[1] + bias2.y + xg[1]) : 0.0f;
                     put_pair(Vec::cx_hi, Vec::cx_lo, kCxStride, TXq / 2 + 4 * warp + t4, m0, m1);              // fc_local1 sees the layer's own output
                     xg[0] = m0 + sk[0]; xg[1] = m1 + sk[1];                                                    // the next layer the skipped one (epic.py:155)
                     put_pair(Vec::in1_hi, Vec::in1_lo, kIn1Stride, 128 + TXq / 2 + 4 * warp + t4, xg[0], xg[1]);
@@ -747,8 +747,8 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
                 if (l == 1) WIDE_TRACE(21);
                 if (g < kMaxJ) {
                     const int o = 8 * warp + 2 * t4;
-                    sv[Vec::bl1 + g * 128 + o] = c[0] + __ldg(tl + ly.o_bl1 + o);
-                    sv[Vec::bl1 + g * 128 + o + 1] = c[1] + __ldg(tl + ly.o_bl1 + o + 1);
+                    sv[Vec::bl1 + g * 128 + o] = c[0] + bias3.x;
+                    sv[Vec::bl1 + g * 128 + o + 1] = c[1] + bias3.y;
                 }
                 compute_sync();
             }
