@@ -665,6 +665,8 @@ int mmb_generate_absorbing(const MmbEpicModel* model, const MmbAbsorbHead* head,
     const EpicModel* m = reinterpret_cast<const EpicModel*>(model);
     const AbsorbHead* h = reinterpret_cast<const AbsorbHead*>(head);
     if (!m || !h || !x || !k || !mask || !st || !tbias || !workspace) return fail(MMB_EINVAL, "mmb_generate_absorbing: null argument");
+    if (m->dims.dim_context != 0)   // AbsorbingGenerator.forward passes batch.context_* on (absorbing_flows.py:150-153); not built for this loop
+        return fail(MMB_EUNSUPPORTED, "mmb_generate_absorbing: the trunk was built with %d context features; this loop has no context input", m->dims.dim_context);
     if (!st->temb || !st->bc || !st->cc || !st->sp) return fail(MMB_EINVAL, "mmb_generate_absorbing: step table needs temb, bc, cc, sp");
     if (B < 0 || N < 0 || st->n_steps < 0) return fail(MMB_EINVAL, "mmb_generate_absorbing: negative size");
     if (absorb_head_hidden(h) != m->dims.dim_hidden_local) return fail(MMB_EINVAL, "head expects hidden %d, trunk has %d", absorb_head_hidden(h), m->dims.dim_hidden_local);

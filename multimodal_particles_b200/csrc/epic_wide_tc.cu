@@ -849,8 +849,6 @@ struct WideImage {
     void* image = nullptr;
     float* tab = nullptr;
     uint2* frag = nullptr;
-    int32_t* pack = nullptr;      // pre-pass scratch, grown on demand (one evaluation at a time per model handle)
-    size_t pack_ints = 0;
     WideLayout lay;
 };
 
@@ -867,7 +865,6 @@ void wide_free_image(EpicModel* m) {
     if (w->image) cudaFree(w->image);
     if (w->tab) cudaFree(w->tab);
     if (w->frag) cudaFree(w->frag);
-    if (w->pack) cudaFree(w->pack);
     delete w;
     m->wide = nullptr;
 }
@@ -986,32 +983,36 @@ int wide_read_trace(long long* out, int n) {
 
 int launch_epic_forward_wide(const EpicModel* m, const float* x, const uint8_t* k, const uint8_t* mask, const float* temb, int temb_stride,
                              int B, int N, float* v_out, float* logits_out, float* hidden_out, cudaStream_t stream) {
-    WideImage* w = static_cast<WideImage*>(m->wide);
+    const WideImage* w = static_cast<const WideImage*>(m->wide);
     if (!w) return fail(MMB_EUNSUPPORTED, "wide EPiC trunk: no operand image for this model");
     if (B == 0 || N == 0) return MMB_OK;
     if (N > 128) return fail(MMB_EUNSUPPORTED, "wide EPiC trunk handles up to 128 particle slots per jet (got %d)", N);
     if (B >= (1 << 20)) return fail(MMB_EUNSUPPORTED, "wide EPiC trunk: at most 2^20 - 1 jets per call");
-    if (w->pack_ints < pack_ints(B)) {   // the pre-pass scratch lives on the handle and grows with the largest batch seen
-        if (w->pack) { cudaStreamSynchronize(stream); cudaFree(w->pack); w->pack = nullptr; w->pack_ints = 0; }
-        if (int rc = cuda_ok(cudaMalloc(&w->pack, pack_ints(B) * sizeof(int32_t)), "cudaMalloc wide pre-pass scratch")) return rc;
-        w->pack_ints = pack_ints(B);
-    }
+    // pre-pass scratch (jet lists, tile records): a stream-ordered allocation, so concurrent evaluations on different streams of
+    // one model handle never share it and nothing synchronises (the pool reuses the block from call to call)
+    int32_t* pack = nullptr;
+    if (int rc = cuda_ok(cudaMallocAsync(reinterpret_cast<void**>(&pack), pack_ints(B) * sizeof(int32_t), stream), "wide pre-pass scratch")) return rc;
     WideParams p{};
-    p.image = static_cast<const uint8_t*>(w->image); p.tab = w->tab; p.frag = w->frag; p.lay = w->lay; p.pack = w->pack;
+    p.image = static_cast<const uint8_t*>(w->image); p.tab = w->tab; p.frag = w->frag; p.lay = w->lay; p.pack = pack;
     p.x = x; p.k = k; p.mask = mask; p.temb = temb; p.temb_stride = temb_stride; p.B = B; p.N = N;
     p.v_out = v_out; p.logits_out = logits_out; p.hidden_out = hidden_out;
     static const bool trace_on = [] { const char* e = getenv("MMB_WIDE_TRACE"); return e && e[0] == '1'; }();   // debug knob
     if (trace_on) cudaGetSymbolAddress(reinterpret_cast<void**>(&p.trace), g_wide_trace);
-    if (int rc = cuda_ok(cudaMemsetAsync(w->pack, 0, 8 * sizeof(int32_t), stream), "wide pre-pass counters")) return rc;
-    wide_pack_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, N, w->lay.S, w->tab + w->lay.dead_logits, v_out, logits_out, hidden_out, w->pack);
-    wide_tiles_kernel<<<(B + 255) / 256, 256, 0, stream>>>(w->pack, B);
-    if (int rc = cuda_ok(cudaGetLastError(), "wide pre-pass launch")) return rc;
-    if (int rc = cuda_ok(cudaFuncSetAttribute(epic_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "wide smem attribute"))
-        return rc;
-    const int pairs = (B + 1) / 2;   // upper bound of the tile pairs (the kernel reads the count the pre-pass left)
-    const int grid = pairs < m->sm_count ? pairs : m->sm_count;
-    epic_wide_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
-    return cuda_ok(cudaGetLastError(), "epic_wide launch");
+    int rc = cuda_ok(cudaMemsetAsync(pack, 0, 8 * sizeof(int32_t), stream), "wide pre-pass counters");
+    if (!rc) {
+        wide_pack_kernel<<<(B + 7) / 8, 256, 0, stream>>>(mask, B, N, w->lay.S, w->tab + w->lay.dead_logits, v_out, logits_out, hidden_out, pack);
+        wide_tiles_kernel<<<(B + 255) / 256, 256, 0, stream>>>(pack, B);
+        rc = cuda_ok(cudaGetLastError(), "wide pre-pass launch");
+    }
+    if (!rc) rc = cuda_ok(cudaFuncSetAttribute(epic_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "wide smem attribute");
+    if (!rc) {
+        const int pairs = (B + 1) / 2;   // upper bound of the tile pairs (the kernel reads the count the pre-pass left)
+        const int grid = pairs < m->sm_count ? pairs : m->sm_count;
+        epic_wide_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
+        rc = cuda_ok(cudaGetLastError(), "epic_wide launch");
+    }
+    cudaFreeAsync(pack, stream);   // ordered after the kernel on this stream
+    return rc;
 }
 
 }  // namespace mmb

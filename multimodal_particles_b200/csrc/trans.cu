@@ -750,6 +750,7 @@ static int check_pair(const EpicModel* m, const TransHeads* h, int N) {
         return fail(MMB_EINVAL, "trunk (H=%d, S=%d, Dc=%d) does not match the trans heads (H=%d, S=%d, Dc=3)", m->dims.dim_hidden_local,
                     m->dims.vocab_size, m->dims.dim_continuous, h->d.hidden, h->d.vocab_size);
     if (m->dims.disc_head_hidden != 0) return fail(MMB_EINVAL, "the trans trunk is created without a discrete head (fc_layer is never applied)");
+    if (m->dims.dim_context != 0) return fail(MMB_EUNSUPPORTED, "the trans trunk takes no context features (its batches carry none: return_type 'list')");
     if (N < 1 || N > h->d.max_particles) return fail(MMB_EINVAL, "N=%d outside 1..max_particles=%d", N, h->d.max_particles);
     if (m->dims.dim_time_emb > kC) return fail(MMB_EUNSUPPORTED, "time embedding wider than 128");
     return MMB_OK;
