@@ -22,11 +22,11 @@
 //   * local_0 with the embeddings folded in is ONE K-step: the operand row is [x_hi, x_lo, onehot(k)] (two bf16 per feature);
 //   * the per-jet global path (masked mean / sum pooling -> global MLPs, epic.py:136-143, 187-190, 226-232) is warp-level
 //     tensor-core work too: the jets of the CTA are the rows of mma.sync m16n8k16 tiles (inputs split into bf16 hi + lo, so they
-//     enter with ~16 bits), each of the 16 warps owns eight output columns and reads its weight fragments, pre-arranged on the
+//     enter with ~16 bits — except the 256 pooled features, plain bf16 like every particle activation), each of the 16 warps owns
+//     eight output columns and reads its weight fragments, pre-arranged on the
 //     host, straight from L2 — once per CTA and layer, while the fc_local1 GEMMs are in flight;
 //   * the trunk skip (epic.py:148-155) is kept per tile as fp16 in shared memory.
-// Numerics: bf16 operands, fp32 accumulation, fp32 residual / pooling / global path (bf16 weights for its three wide
-// matrices).  Checked against the fp32 kernel with the tolerance written in tests/test_gpu_wide.py.
+// Numerics: bf16 operands (weights of both paths), fp32 accumulation, fp32 residual stream, pooling sums and biases.  Checked against the fp32 kernel with the tolerance written in tests/test_gpu_wide.py.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
