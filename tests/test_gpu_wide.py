@@ -87,6 +87,30 @@ def test_forward_tracks_fp32(kw, B, N):
         assert torch.equal(v3, v1[perm]) and torch.equal(l3, l1[perm])
 
 
+def test_full_size_batch_and_every_multiplicity():
+    """4096 jets (the C2 batch) with multiplicities 1..128 all present, incl. full jets ([4] tiles) and one-particle jets
+    ([1,1] tiles): every head against the fp32 kernel; jets ordered by multiplicity and shuffled give the same bits."""
+    cfg, model = wide_model(seed=5)
+    native = model.encoder.native_model(torch.device(DEV))
+    B, N = 4096, 128
+    g = torch.Generator().manual_seed(3)
+    mult = torch.cat([torch.arange(1, N + 1), torch.randint(1, N + 1, (B - N,), generator=g)])
+    m = (torch.arange(N)[None] < mult[:, None]).to(torch.uint8)
+    m = torch.gather(m, 1, torch.rand(B, N, generator=g).argsort(1))          # live slots anywhere, not a prefix
+    x = (torch.randn(B, N, 3, generator=g) * m[..., None]).to(DEV)
+    k = (torch.randint(0, 8, (B, N), generator=g, dtype=torch.uint8) * m).to(DEV)
+    m = m.to(DEV)
+    temb = model.step_table().temb[7:8].to(DEV)
+    v0, l0 = native.forward(x, k, m, temb, precision="fp32")
+    v1, l1 = native.forward(x, k, m, temb, precision="bf16")
+    assert rel(v1, v0) < REL and rel(l1, l0) < REL
+    per_jet = (v1 - v0).abs().amax((1, 2)) / v0.abs().amax()
+    assert per_jet.max().item() < REL, int(per_jet.argmax())
+    perm = torch.randperm(B, generator=g).to(DEV)
+    v2, l2 = native.forward(x[perm].contiguous(), k[perm].contiguous(), m[perm].contiguous(), temb, precision="bf16")
+    assert torch.equal(v2, v1[perm]) and torch.equal(l2, l1[perm])
+
+
 def test_empty_jet_is_nan_like_the_reference_and_leaves_its_partner_alone():
     cfg, model = wide_model(L=2)
     native = model.encoder.native_model(torch.device(DEV))
