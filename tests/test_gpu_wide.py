@@ -87,6 +87,25 @@ def test_forward_tracks_fp32(kw, B, N):
         assert torch.equal(v3, v1[perm]) and torch.equal(l3, l1[perm])
 
 
+@pytest.mark.parametrize("mults", [[40, 50, 64], [1, 2, 3, 4, 5], [96, 70, 10], [65, 80, 90, 5, 6, 7, 8, 9], [128], [128, 1], [33], [32, 32, 32],
+                                   [97, 128, 100, 3], [64, 64, 64, 64, 1]])
+def test_tile_compositions(mults):
+    """Every way the pre-pass composes tiles — [4] | [3,1] | [3] | [2,2] | [2,1] | [2] | [1,1] | [1] — with odd counts in each class."""
+    cfg, model = wide_model(L=2, seed=7)
+    native = model.encoder.native_model(torch.device(DEV))
+    B, N = len(mults), 128
+    g = torch.Generator().manual_seed(sum(mults))
+    m = (torch.arange(N)[None] < torch.tensor(mults)[:, None]).to(torch.uint8)
+    x = (torch.randn(B, N, 3, generator=g) * m[..., None]).to(DEV)
+    k = (torch.randint(0, 8, (B, N), generator=g, dtype=torch.uint8) * m).to(DEV)
+    m = m.to(DEV)
+    temb = torch.randn(B, cfg.encoder.dim_emb_time, generator=g).to(DEV)
+    v0, l0, h0 = native.forward(x, k, m, temb, want_hidden=True, precision="fp32")
+    v1, l1, h1 = native.forward(x, k, m, temb, want_hidden=True, precision="bf16")
+    for j in range(B):   # per jet: nobody is skipped, nobody gets a neighbour's result
+        assert rel(v1[j], v0[j]) < REL and rel(l1[j], l0[j]) < REL and rel(h1[j], h0[j]) < REL, (mults, j)
+
+
 def test_full_size_batch_and_every_multiplicity():
     """4096 jets (the C2 batch) with multiplicities 1..128 all present, incl. full jets ([4] tiles) and one-particle jets
     ([1,1] tiles): every head against the fp32 kernel; jets ordered by multiplicity and shuffled give the same bits."""
