@@ -776,12 +776,14 @@ __global__ void __launch_bounds__(kThreads, 1) epic_wide_kernel(const WideParams
             if (l == 1) WIDE_TRACE(13);
         }
         WIDE_TRACE(14);
-        // ---- output layer + discrete head (epic.py:158-162, mbm.py:105-113) for the live particles
+        // ---- output layer + discrete head (epic.py:158-162, mbm.py:105-113) for the live particles: the rows of tile A are served by
+        // the threads of column slice 0, those of tile B by slice 1, side by side
+        wait_tile(0);
+        if (has_b) wait_tile(1);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             if (t == 1 && !has_b) continue;
-            wait_tile(t);
-            if (cq == 0) {   // whole warps: tcgen05.ld is warp-collective
+            if (cq == t) {   // whole warps: tcgen05.ld is warp-collective
                 float v[32];
                 tmem_ld32(dACC[t] + lane_off, v);
                 if (live[t]) {
