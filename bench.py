@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "bf16", "fp32"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "wide"])
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: per-batch exchange of the generated jets (auto: copy-engine push over NVLink peer memory, else NCCL)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 / C5 side measurements")
     args = ap.parse_args()
@@ -216,12 +218,15 @@ def main():
     n_bufs = W + K
     mask = as_u8(batch.source_mask.to(device))
     # the state of every step lives in one packed allocation [x | tokens | mask], so the multi-GPU exchange is one all-gather
-    packs = [sharding.PackedJets(B, N_PART, 3, device).load(batch.source_continuous.to(device), as_u8(batch.source_discrete.to(device)), mask)
+    hist = sharding.ValidationHistograms(device, vocab_size=cfg.data.vocab_size_features)
+    n_counts = hist.size if world > 1 else 0      # N > 1: the histogram counts of a step ride in the packed allocation
+    packs = [sharding.PackedJets(B, N_PART, 3, device, extra_int64=n_counts).load(batch.source_continuous.to(device), as_u8(batch.source_discrete.to(device)), mask)
              for _ in range(n_bufs)]
     xs, ks = [p.x for p in packs], [p.k for p in packs]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)   # > 126 MB L2
-    gather_buf = sharding.PackedGather(B, N_PART, 3, world, device) if world > 1 else None
-    hist = sharding.ValidationHistograms(device, vocab_size=cfg.data.vocab_size_features)
+    # receive side of the per-batch exchange, two buffers in turn (sharding.PeerGather: copy-engine push over peer memory;
+    # --gather nccl: one NCCL all-gather + all-reduce)
+    gather_bufs = [sharding.make_gather(B, N_PART, 3, world, device, mode=args.gather, extra_int64=n_counts) for _ in range(2)] if world > 1 else None
     stream = torch.cuda.current_stream()
 
     side = torch.cuda.Stream(device=device) if world > 1 else None
@@ -235,8 +240,8 @@ def main():
             done.record(stream)
             with torch.cuda.stream(side):
                 side.wait_event(done)
-                counts = hist.accumulate(xs[i], ks[i], mask)
-                gather_buf.gather(packs[i], counts)
+                counts = hist.accumulate(xs[i], ks[i], mask, out=packs[i].counts)
+                gather_bufs[i & 1].gather(packs[i], counts)
 
     def join():
         if world > 1:
@@ -362,7 +367,8 @@ def main():
     if world > 1 and not args.no_secondary:   # BASELINE configs[4] with the same model: 1 M jets over the GPUs of the box
         from multimodal_particles_b200.pipeline import sharded_generation_run
         try:
-            c5 = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=B, n_particles=N_PART, precision=precision)
+            c5 = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=B, n_particles=N_PART, precision=precision,
+                                        gather=args.gather)
         except Exception as exc:
             c5 = {"error": f"{type(exc).__name__}: {exc}"}
 
@@ -388,7 +394,9 @@ def main():
                 "config": {"workload": WORKLOAD, "global_batch": world * B, "precision": precision,
                            "engine": kernel_name,
                            "l2": "256 MiB flush before the timed region; each timed step reads a fresh, never-cached source buffer",
-                           "rng": "in-kernel Philox4x32-10", "parallelism": f"jets sharded over {world} GPU(s)"},
+                           "rng": "in-kernel Philox4x32-10", "parallelism": f"jets sharded over {world} GPU(s)",
+                           **({"exchange": "per step, on a side stream under the next generation: " + gather_bufs[0].kind
+                                           + "; histogram counts travel with the jets (NCCL all-reduce in the all-gather mode)"} if world > 1 else {})},
                 "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "MultiModalBridgeMatching.simulate_dynamics -> mmb_generate_host, direct mode (the kernel reads and writes the pinned host buffers itself)",
                         "ms_per_iteration": e2e_iter_ms},
@@ -408,7 +416,7 @@ def side_workload_line(args, torch, dist, _native, device, pk, rank, world, W, K
         cfg, model = build_model(device)
         with ClockSampler(device.index or 0) as clocks:
             rec = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=B_PER_GPU, n_particles=N_PART,
-                                         precision=args.precision)
+                                         precision=args.precision, gather=args.gather)
         if rank != 0:
             return None
         return {"metric": METRIC, "value": rec["value"], "unit": "jets/s", "n_gpus": world, "steps": 1, "warmup": 2,

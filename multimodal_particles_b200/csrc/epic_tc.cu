@@ -915,35 +915,66 @@ static MmbEpicDims tc_dims(const MmbEpicDims& d) {
 template <int S>
 __global__ void __launch_bounds__(256) discrete_head_mlp_kernel(const float* __restrict__ W, MmbEpicLayout Lo, int Sh,
                                                                 float* __restrict__ logits, size_t P) {
-    extern __shared__ float sw[];  // W1 [Sh][S], b1 [Sh], W2^T [Sh][S], b2 [S]
+    // W1 [Sh][S] | b1 [Sh, padded to a multiple of 4] | W2^T [Sh][S] | b2 [S]: every weight row starts on 16 bytes
+    extern __shared__ __align__(16) float sw[];
+    const int ShP = (Sh + 3) & ~3, oB1 = Sh * S, oW2 = oB1 + ShP, oB2 = oW2 + Sh * S;
     for (int i = threadIdx.x; i < Sh * S; i += blockDim.x) {
         sw[i] = __ldg(W + Lo.head0_w + i);
         const int s = i / Sh, j = i % Sh;                       // head2_w is [S][Sh]
-        sw[Sh * S + Sh + j * S + s] = __ldg(W + Lo.head2_w + i);
+        sw[oW2 + j * S + s] = __ldg(W + Lo.head2_w + i);
     }
-    for (int i = threadIdx.x; i < Sh; i += blockDim.x) sw[Sh * S + i] = __ldg(W + Lo.head0_b + i);
-    for (int i = threadIdx.x; i < S; i += blockDim.x) sw[2 * Sh * S + Sh + i] = __ldg(W + Lo.head2_b + i);
+    for (int i = threadIdx.x; i < Sh; i += blockDim.x) sw[oB1 + i] = __ldg(W + Lo.head0_b + i);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) sw[oB2 + i] = __ldg(W + Lo.head2_b + i);
     __syncthreads();
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     float z[S], out[S];
+    // a particle's S logits are 16 / 32 contiguous bytes: 128-bit loads and stores when the caller's buffer allows; the weight
+    // rows in shared memory are read as float4 (every lane reads the same address: one broadcast per 4 weights)
+    const bool vec = (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+    float4* io = reinterpret_cast<float4*>(logits + p * S);
+    if (vec) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) { z[s] = logits[p * S + s]; out[s] = sw[2 * Sh * S + Sh + s]; }
-    for (int j = 0; j < Sh; ++j) {
-        float a = sw[Sh * S + j];
+        for (int q = 0; q < S / 4; ++q) {
+            const float4 t = io[q];
+            z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
+        }
+    } else {
 #pragma unroll
-        for (int s = 0; s < S; ++s) a = fmaf(sw[j * S + s], z[s], a);
-        a = a > 0.0f ? 1.0507009873554805f * a : 1.7580993408473766f * (__expf(a) - 1.0f);
-#pragma unroll
-        for (int s = 0; s < S; ++s) out[s] = fmaf(sw[Sh * S + Sh + j * S + s], a, out[s]);
+        for (int s = 0; s < S; ++s) z[s] = logits[p * S + s];
     }
 #pragma unroll
-    for (int s = 0; s < S; ++s) logits[p * S + s] = out[s];
+    for (int s = 0; s < S; ++s) out[s] = sw[oB2 + s];
+    const float4* w1 = reinterpret_cast<const float4*>(sw);
+    const float4* w2 = reinterpret_cast<const float4*>(sw + oW2);
+#pragma unroll 4
+    for (int j = 0; j < Sh; ++j) {
+        float a = sw[oB1 + j];
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q) {
+            const float4 w = w1[j * (S / 4) + q];
+            a = fmaf(w.x, z[4 * q], a); a = fmaf(w.y, z[4 * q + 1], a); a = fmaf(w.z, z[4 * q + 2], a); a = fmaf(w.w, z[4 * q + 3], a);
+        }
+        a = a > 0.0f ? 1.0507009873554805f * a : 1.7580993408473766f * (__expf(a) - 1.0f);
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q) {
+            const float4 w = w2[j * (S / 4) + q];
+            out[4 * q] = fmaf(w.x, a, out[4 * q]); out[4 * q + 1] = fmaf(w.y, a, out[4 * q + 1]);
+            out[4 * q + 2] = fmaf(w.z, a, out[4 * q + 2]); out[4 * q + 3] = fmaf(w.w, a, out[4 * q + 3]);
+        }
+    }
+    if (vec) {
+#pragma unroll
+        for (int q = 0; q < S / 4; ++q) io[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int s = 0; s < S; ++s) logits[p * S + s] = out[s];
+    }
 }
 
 static int launch_discrete_head_mlp(const EpicModel* m, float* logits, size_t P, cudaStream_t stream) {
     const int S = m->dims.vocab_size, Sh = m->dims.disc_head_hidden;
-    const size_t bytes = (size_t)(2 * Sh * S + Sh + S) * sizeof(float);
+    const size_t bytes = (size_t)(2 * Sh * S + ((Sh + 3) & ~3) + S) * sizeof(float);
     const unsigned grid = (unsigned)((P + 255) / 256);
     if (S == 8) discrete_head_mlp_kernel<8><<<grid, 256, bytes, stream>>>(m->w, m->layout, Sh, logits, P);
     else discrete_head_mlp_kernel<4><<<grid, 256, bytes, stream>>>(m->w, m->layout, Sh, logits, P);

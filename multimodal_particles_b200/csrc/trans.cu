@@ -117,9 +117,9 @@ __global__ void trans_tokens_kernel(const float* __restrict__ onehot, const floa
 }
 
 // ---- time terms (utils.py:183-198; gsdm.py:8-26,58; transdimensional_model.py:288-290) ---------------------------------
-// A block serves kTimeJets jets: thread (o, half) owns output channel o of 16 of them, so every weight row is read once per
+// A block serves kTimeJets jets: thread (o, half) owns output channel o of half of them, so every weight row is read once per
 // block and the activations are read from shared memory four jets at a time.
-constexpr int kTimeJets = 32;
+constexpr int kTimeJets = 16;   // 8192 jets = 512 blocks (32 jets per block: 256 blocks of 8 warps left most schedulers with two warps, 144 us)
 __global__ void __launch_bounds__(2 * kC) trans_time_kernel(const float* __restrict__ wT, int nblk, const float* __restrict__ ts, int B, int T,
                                                             float* __restrict__ temb_epic, float* __restrict__ tb1, float* __restrict__ tb2) {
     __shared__ __align__(16) float s_in[kC][kTimeJets];   // [channel][jet]
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(2 * kC) trans_time_kernel(const float* __restr
         const float bias = __ldg(W + (size_t)kC * kC + o);
 #pragma unroll
         for (int j = 0; j < JT; ++j) acc[j] = bias;
-#pragma unroll 4
+#pragma unroll 8
         for (int c = 0; c < kC; ++c) {
             const float w = __ldg(W + (size_t)c * kC + o);
 #pragma unroll

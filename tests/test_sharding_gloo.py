@@ -60,6 +60,11 @@ def _worker(rank, world, port, total, out_path):
         pk_ = torch.cat([pg.k(r) for r in range(world)])
         pm = torch.cat([pg.mask(r) for r in range(world)])
         assert torch.equal(px, buf.x) and torch.equal(pk_, buf.k) and torch.equal(pm, buf.mask)
+        # off CUDA / NCCL the factory hands out the collective, never the peer-memory push
+        mg = sharding.make_gather(hi - lo, 32, 3, world, "cpu")
+        assert type(mg) is sharding.PackedGather and mg.kind == "all-gather"
+        mg.gather(pk)
+        assert torch.equal(mg.bytes, pg.bytes)
         if rank == 0:
             np.savez(out_path, x=buf.x.numpy(), k=buf.k.numpy(), mask=buf.mask.numpy(), counts=counts.numpy())
     finally:
@@ -85,3 +90,44 @@ def test_two_rank_generation_equals_single_rank(tmp_path):
     want = hist.accumulate(torch.from_numpy(x), torch.from_numpy(k), full.source_mask[..., 0].to(torch.uint8))
     assert np.array_equal(z["counts"], want.numpy())
     assert int(z["counts"][-33:].sum()) == total  # one multiplicity entry per jet
+
+
+def _peer_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        B, N = 37, 128
+        peer = [sharding.make_gather(B, N, 3, world, dev, mode="peer", extra_int64=5) for _ in range(2)]
+        nccl = sharding.make_gather(B, N, 3, world, dev, mode="nccl", extra_int64=5)
+        assert isinstance(peer[0], sharding.PeerGather) and type(nccl) is sharding.PackedGather
+        ok = True
+        for rep in range(4):   # two receive buffers in turn, fresh bytes every time
+            pk = sharding.PackedJets(B, N, 3, dev, extra_int64=5)
+            pk.bytes.copy_(torch.randint(0, 256, (pk.bytes.numel(),), dtype=torch.uint8, generator=torch.Generator().manual_seed(100 * rep + rank)))
+            pk.counts.fill_(rank + 1 + rep)
+            nccl.gather(pk)
+            # counts inside the packed allocation travel with the pushes (even reps); counts held elsewhere take the all-reduce
+            counts = pk.counts if rep % 2 == 0 else torch.full((5,), rank + 1 + rep, dtype=torch.int64, device=dev)
+            peer[rep & 1].gather(pk, counts)
+            torch.cuda.synchronize()
+            ok = ok and torch.equal(peer[rep & 1].bytes, nccl.bytes) and int(counts[0]) == sum(r + 1 + rep for r in range(world))
+            # views of the receive buffer (compared as bytes: random bytes make NaN floats)
+            ok = ok and torch.equal(peer[rep & 1].x(rank).view(torch.uint8), pk.x.view(torch.uint8)) and torch.equal(peer[rep & 1].mask(rank), pk.mask)
+        t = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            np.savez(out_path, ok=t.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_push_gather_equals_nccl_all_gather(tmp_path):
+    """sharding.PeerGather (copy-engine push over NVLink peer memory) delivers the bytes of one NCCL all-gather; needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = str(tmp_path / "peer.npz")
+    mp.spawn(_peer_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert float(np.load(out)["ok"][0]) == 1.0
