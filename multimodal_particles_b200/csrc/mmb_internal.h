@@ -148,6 +148,7 @@ int launch_epic_forward_wide(const EpicModel* m, const float* x, const uint8_t* 
 
 // epic_mma.cu — warp-level MMA engine (register-resident chains), generation only
 bool mma_supported(const MmbEpicDims* d, int N);
+long long mma_read_trace(unsigned long long* out, long long max_words);
 int mma_build_images(EpicModel* m, const float* packed_host);
 size_t mma_generate_scratch_floats(const MmbEpicDims* d, int n_steps, int B);
 struct MmaHostIO {          // direct mode of mmb_generate_host: device-visible addresses of the caller's page-locked host buffers
@@ -156,6 +157,8 @@ struct MmaHostIO {          // direct mode of mmb_generate_host: device-visible 
     float* x_out;           // [B,N,Dc]
     long long* k_out;       // [B,N] int64
     int* bad_tokens;        // DEVICE flag
+    float* x_state;         // DEVICE scratch [B,N,Dc] / [B,N]: state of a jet between two of its time slices (epic_mma.cu)
+    uint8_t* k_state;
 };
 int launch_generate_mma(const EpicModel* m, float* x, uint8_t* k, const uint8_t* mask, const float* context, const float* dev_table, float* scratch,
                         int n_steps, float dt, const float* u_jump, uint64_t seed, uint64_t jet_offset,
