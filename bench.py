@@ -40,6 +40,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "generated jets/sec (128 particles, 100 steps)"
 WORKLOAD = "C2: EPiC multimodal bridge, JetClass-shape synthetic jets, N=128, Dc=3, S=8, B=4096/GPU, 99 solver steps"
 B_PER_GPU, N_PART, N_TIMESTEPS = 4096, 128, 100
+# micro-batch of the 1 M-jet run (BASELINE config 5 fixes the total, not the slice): a warp gets about two jets out of a 4096-jet
+# call and the kernel ends in a ragged tail (profiles/r02_mma_timeline.md); 16384 jets per call run at 4.45 M jets/s instead of 4.0 M
+C5_MICRO_BATCH = 16384
 FLOP_PER_JET_STEP = 0.819e6          # SURVEY.md §8d (2*MAC, default widths)
 UPDATE_BYTES_PER_PARTICLE = 75       # SURVEY.md §8d / BASELINE.md §4
 CPU_SAMPLE_JETS = 16384              # bounded CPU sample: ~15 s on 16 host threads at ~1.1 K jets/s
@@ -367,7 +370,7 @@ def main():
     if world > 1 and not args.no_secondary:   # BASELINE configs[4] with the same model: 1 M jets over the GPUs of the box
         from multimodal_particles_b200.pipeline import sharded_generation_run
         try:
-            c5 = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=B, n_particles=N_PART, precision=precision,
+            c5 = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=C5_MICRO_BATCH, n_particles=N_PART, precision=precision,
                                         gather=args.gather)
         except Exception as exc:
             c5 = {"error": f"{type(exc).__name__}: {exc}"}
@@ -415,7 +418,7 @@ def side_workload_line(args, torch, dist, _native, device, pk, rank, world, W, K
         from multimodal_particles_b200.pipeline import sharded_generation_run
         cfg, model = build_model(device)
         with ClockSampler(device.index or 0) as clocks:
-            rec = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=B_PER_GPU, n_particles=N_PART,
+            rec = sharded_generation_run(model, cfg, 1 << 20, rank, world, device, micro_batch=C5_MICRO_BATCH, n_particles=N_PART,
                                          precision=args.precision, gather=args.gather)
         if rank != 0:
             return None
@@ -521,21 +524,30 @@ def _c3(torch, _native, device, pk, timed, reps, warm):
     model = TransdimensionalJumpDiffusion(TransdimensionalEpicConfig()).to(device)
     m = model.net.model
     trunk, heads = m.native_trunk(device), m.native_heads(device)
-    g = torch.Generator().manual_seed(1234)
-    dims = torch.randint(1, N + 1, (B,), generator=g)
-    mask = (torch.arange(N)[None] < dims[:, None]).float().unsqueeze(-1)
-    x = torch.randn(B, N, 3, generator=g) * mask
-    x = x - (x.sum(1, keepdim=True) / dims.view(B, 1, 1)) * mask
-    oh, ts = torch.randn(B, N, S, generator=g) * mask, torch.rand(B, generator=g) * 0.999 + 1e-3
-    near = (torch.rand(B, generator=g) * dims).long()
-    x, oh, d32, ts, near = x.to(device), oh.to(device), dims.to(device, torch.int32), ts.to(device), near.to(device, torch.int32)
     fr = model.forward_rate.as_c()
-    ms = timed(lambda: _native.trans_forward(trunk, heads, x, oh, d32, ts, near, None, fr, precision="bf16", want_auto=False), reps, warm)
-    tf = 145.33e6 * B / (ms * 1e-3) / 1e12
+
+    def evaluation_ms(dims, g):
+        mask = (torch.arange(N)[None] < dims[:, None]).float().unsqueeze(-1)
+        x = torch.randn(B, N, 3, generator=g) * mask
+        x = x - (x.sum(1, keepdim=True) / dims.view(B, 1, 1)) * mask
+        oh, ts = torch.randn(B, N, S, generator=g) * mask, torch.rand(B, generator=g) * 0.999 + 1e-3
+        near = (torch.rand(B, generator=g) * dims).long()
+        x, oh, d32, ts, near = x.to(device), oh.to(device), dims.to(device, torch.int32), ts.to(device), near.to(device, torch.int32)
+        return timed(lambda: _native.trans_forward(trunk, heads, x, oh, d32, ts, near, None, fr, precision="bf16", want_auto=False), reps, warm)
+
+    def line(ms, rows):
+        tf = 145.33e6 * B / (ms * 1e-3) / 1e12     # the reference's flops: every slot of every jet
+        return {"bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tf / pk["bf16"], "ms_per_evaluation": ms,
+                "rows": rows}
+
+    g = torch.Generator().manual_seed(1234)
+    ms = evaluation_ms(torch.randint(1, N + 1, (B,), generator=g), g)
+    # the multiplicities of the other configs (C2 / C4 / C5): what the network meets when it generates JetClass-like jets
+    ms_jc = evaluation_ms((torch.randn(B, generator=g) * 18.0 + 45.0).round().clamp(1, N).long(), g)
     out["C3_transepic_evaluation"] = {"workload": "TransdimensionalEPiC.forward, B=8192, N=128, bf16 stacks", "ms": ms,
                                       "jet_evals_per_s": B / (ms * 1e-3),
-                                      "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
-                                                   "frac": tf / pk["bf16"]}}
+                                      "roofline": line(ms, "multiplicities uniform in 1..128 (mean 64.5); padded slots packed to one row per jet"),
+                                      "roofline_jetclass_multiplicities": line(ms_jc, "multiplicities ~ N(45, 18) clipped to 1..128, as in C2 / C4 / C5")}
     return out
 
 

@@ -22,7 +22,7 @@ from multimodal_particles_b200.pipeline import sharded_generation_run  # noqa: E
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jets", type=int, default=1 << 20)
-    ap.add_argument("--micro-batch", type=int, default=4096)
+    ap.add_argument("--micro-batch", type=int, default=16384)
     ap.add_argument("--precision", default="auto")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
