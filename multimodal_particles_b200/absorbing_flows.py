@@ -82,6 +82,11 @@ class AbsorbingGenerator(nn.Module):
         self.encoder_output_dim = d.dim_features_continuous + d.dim_features_discrete * d.vocab_size_features
         self.encoder_output_dim_local = config.encoder.dim_hidden_local
         self.epic = EPiCWrapper(config)
+        if self.epic.embedding.dim_context:
+            # absorbing_flows.py:150 reads the context with a trailing comma (a one-element tuple), EPiCWrapper.forward turns the
+            # non-tensor into None and the context embedding fails: the reference has no behaviour with context to match
+            raise NotImplementedError("AbsorbingGenerator with context features: the reference's forward fails there "
+                                      "(absorbing_flows.py:150 wraps batch.context_continuous in a tuple); not built")
         self.add_discrete_head = config.encoder.add_discrete_head
         if self.add_discrete_head:
             width = d.dim_features_discrete * d.vocab_size_features

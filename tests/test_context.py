@@ -88,6 +88,15 @@ def test_missing_context_is_an_error_and_discrete_context_is_refused(golden_dir)
     cfg.encoder.embedding_context_discrete, cfg.encoder.dim_emb_context_discrete = "Embedding", 4
     with pytest.raises(NotImplementedError):   # the reference's own forward fails on such a model (utils.py:100 vs :161)
         MultiModalBridgeMatching(cfg)
+    # the absorbing generator cannot take context in the reference either: absorbing_flows.py:150 wraps it in a tuple, the
+    # wrapper drops the non-tensor and the context embedding is applied to None
+    from multimodal_particles_b200.absorbing_flows import AbsorbingFlow
+    from multimodal_particles_b200.config_classes.absorbing_flows_config import AbsorbingConfig
+    acfg = AbsorbingConfig()
+    acfg.data.dim_context_continuous = 2
+    acfg.encoder.embedding_context_continuous, acfg.encoder.dim_emb_context_continuous = "Embedding", 3
+    with pytest.raises(NotImplementedError):
+        AbsorbingFlow(acfg)
 
 
 # ---- GPU --------------------------------------------------------------------------------------------------------------------
