@@ -450,8 +450,12 @@ class JumpSampler:
                  sample_near_atom, dt_schedule, dt_schedule_h, dt_schedule_l, dt_schedule_tc, no_noise_final_step):
         self.structure, self.dt = structure, dt
         if do_conditioning or dt_schedule not in ('uniform', 'C') or not sample_near_atom:
+            # sample_near_atom=False cannot run in the reference (sampler.py:95 calls the network without a nearest particle,
+            # transdimensional_model.py:341 then fails on None); conditioning asks the dataset for `condition_state`, which
+            # only the vendored, unimportable QM9 dataset defines (qm9.py:1981), and differentiates through the network
             raise NotImplementedError("native JumpSampler: sample_near_atom=True, uniform or 'C' time grid, no conditioning "
-                                      "(guidance needs the network's backward pass; SURVEY.md §8f N4)")
+                                      "(guidance needs the network's backward pass and a dataset with condition_state, which "
+                                      "no particle-cloud dataset of the reference has; SURVEY.md §8f N4)")
         self.corrector_snr, self.corrector_start_time, self.corrector_finish_time = corrector_snr, corrector_start_time, corrector_finish_time
         self.do_jump_corrector = do_jump_corrector
         self.dt_schedule, self.dt_schedule_h, self.dt_schedule_l, self.dt_schedule_tc = dt_schedule, dt_schedule_h, dt_schedule_l, dt_schedule_tc
