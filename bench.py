@@ -1,15 +1,16 @@
 #!/usr/bin/env python
 """bench.py — generated jets/sec of the multimodal bridge generation loop (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision auto|f16|bf16|fp32] [--workload c2|c3|c4|c5]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--precision auto|f16|bf16|fp32] [--workload c2|c3|c4|c5|wide]
 
 A "step" = one full generation (all 99 solver steps) of one batch of synthetic jets per GPU.
 Workload (config.workload) = BASELINE.json configs[1]: EPiC multimodal bridge, JetClass-shaped
 synthetic jets (128 particles, 3 continuous + 8 tokens), batch 4096 per GPU, 100 time points.
 
   value          whole-job jets/s with the source state already resident in HBM (CUDA events on the
-                 launch stream, one event pair around the K steps, max over ranks); N>1 includes the NCCL
-                 gather of the generated jets and the all-reduce of the validation histograms, issued on a
+                 launch stream, one event pair around the K steps, max over ranks); N>1 includes the
+                 exchange of the generated jets and of the validation histograms (copy-engine pushes over NVLink peer
+                 memory, or NCCL all-gather + all-reduce: --gather), issued on a
                  side stream under the next step's generation and joined before the end event
   e2e            same metric through the public API MultiModalBridgeMatching.simulate_dynamics with
                  PINNED HOST tensors in and host tensors out (H2D + D2H inside the timed region)
@@ -23,7 +24,8 @@ synthetic jets (128 particles, 3 continuous + 8 tokens), batch 4096 per GPU, 100
   --impl reference   times that CPU port alone (the reference is pure Python and does not travel)
   --workload     c2 (default, the headline) | c3 (one transepic evaluation, B=8192) | c4 (absorbing-flow generation, B=4096) |
                  c5 (1 M jets sharded over the GPUs: source + generation + observables + histograms + gather); with N > 1 the
-                 c2 line carries a bounded c5 leg as well (`c5_million_jets`)
+                 c2 line carries a bounded c5 leg as well (`c5_million_jets`); wide = the C2 loop on an EPiC of the reference's
+                 class-default widths (128 hidden units, 6 blocks) on the tcgen05 trunk
 """
 import argparse
 import json
